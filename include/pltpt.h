@@ -1,0 +1,376 @@
+/* pltpt.h — C ABI of the B200-native PLTPT hot path.
+ *
+ * This is the drop-in boundary: everything a Falcor-side `PLTPT` RenderPass
+ * (reference: Source/RenderPasses/PLTPT/PLTPT.{h,cpp}) needs to hand its work to
+ * hand-written CUDA for sm_100a.  Plain pointers and sizes only; no C++ or torch
+ * types cross it.  All entry points return a PltptStatus (0 = ok) and never throw;
+ * the text of the last failure of the calling thread is in pltpt_last_error().
+ *
+ * Input data layouts are Falcor's own GPU-side scene buffers (the `gScene`
+ * parameter block, reference Source/Falcor/Scene/Scene.slang:61-120), byte for byte.
+ * The structs below restate those layouts so a maintainer can memcpy / share the
+ * Falcor buffers without conversion.  Each struct cites the reference definition.
+ *
+ * Threading: a handle is thread-compatible, not thread-safe (the reference runs one
+ * execute() per frame on the render thread, PLTPT.cpp:357).  One CUDA stream per call.
+ */
+#ifndef PLTPT_H_
+#define PLTPT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PLTPT_API __attribute__((visibility("default")))
+#else
+#define PLTPT_API
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Status codes.  The host shell converts non-zero codes to Falcor::RuntimeError
+ * (reference error behaviour: Source/Falcor/Core/Errors.h:80-120, PLTPT.cpp:409).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum PltptStatus {
+    PLTPT_OK = 0,
+    PLTPT_ERR_INVALID_ARGUMENT = 1,
+    PLTPT_ERR_CUDA = 2,
+    PLTPT_ERR_UNSUPPORTED = 3, /* e.g. textured material handle, non-triangle geometry */
+    PLTPT_ERR_NO_SCENE = 4,
+    PLTPT_ERR_OUT_OF_MEMORY = 5,
+    PLTPT_ERR_NO_DEVICE = 6
+} PltptStatus;
+
+typedef struct PltptContext* PltptHandle;
+
+/* ------------------------------------------------------------------------------------------
+ * Pass properties — the 24 keys of PLTPT::parseDictionary (PLTPT.cpp:147-175),
+ * defaults from PLTPT.h:74-108.  Booleans are uint32 0/1.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct PltptOptions {
+    uint32_t maxBounces;                        /* 32  */
+    uint32_t tileSize;                          /* 512 */
+    uint32_t HWSS;                              /* 4   (1..4) */
+    uint32_t HWSSDoMIS;                         /* 1   */
+    uint32_t sampleGenerator;                   /* 1 = SAMPLE_GENERATOR_UNIFORM (only one supported) */
+    uint32_t debugView;                         /* 0   */
+    float    debugViewIntensity;                /* 1   */
+    float    sourcingAreaFromEmissiveGeometry;  /* 1 mm^2 */
+    float    sourcingMaxBeamOmega;              /* 0.025 sr */
+    uint32_t useDirectLights;                   /* 1 */
+    uint32_t useEnvLights;                      /* 1 */
+    uint32_t useEmissiveLights;                 /* 1 */
+    uint32_t useAnalyticLights;                 /* 1 */
+    uint32_t alphaMasking;                      /* 1 */
+    uint32_t doNEE;                             /* 1 */
+    uint32_t doMIS;                             /* 1 */
+    uint32_t emissiveSampler;                   /* 1 = Power, 0 = Uniform (EmissiveLightSamplerType) */
+    uint32_t doRussianRoulette;                 /* 1 */
+    uint32_t NEEUsePerTileSG;                   /* 0 */
+    uint32_t doImportanceSampleEmitters;        /* 1 */
+    uint32_t doMNEE;                            /* 1 */
+    uint32_t MNEEMaxOccluders;                  /* 2 */
+    uint32_t MNEEMaxIterations;                 /* 60 */
+    float    MNEESolverThreshold;               /* 5e-5 */
+} PltptOptions;
+
+/* Fills *opts with the reference defaults (PLTPT.h:74-108). */
+PLTPT_API void pltpt_default_options(PltptOptions* opts);
+
+/* ------------------------------------------------------------------------------------------
+ * Falcor scene buffer layouts (read-only inputs).
+ * ---------------------------------------------------------------------------------------- */
+
+/* PackedStaticVertexData, 32 B — Source/Falcor/Scene/SceneTypes.slang:246-296.
+ * packed[0] = fp16 normal.x | fp16 normal.y << 16
+ * packed[1] = fp16 normal.z | fp16 (tangent.w * curveRadius) << 16
+ * packed[2] = tangent.xyz as 2x16 snorm octahedral (encodeNormal2x16) */
+typedef struct PltptPackedVertex {
+    float    position[3];
+    uint32_t packedNormalTangentCurveRadius[3];
+    float    texCrd[2];
+} PltptPackedVertex;
+
+/* GeometryInstanceData, 32 B — SceneTypes.slang:102-137. Upper 3 bits of flags = GeometryType. */
+typedef struct PltptGeometryInstance {
+    uint32_t flags;
+    uint32_t globalMatrixID;
+    uint32_t materialID;
+    uint32_t geometryID;
+    uint32_t vbOffset;
+    uint32_t ibOffset; /* in units of 4 bytes into indexData (Scene.slang getLocalIndices: baseIndex = ibOffset*4) */
+    uint32_t instanceIndex;
+    uint32_t geometryIndex;
+} PltptGeometryInstance;
+#define PLTPT_GEOMETRY_TYPE_TRIANGLE_MESH 1u
+#define PLTPT_INSTANCE_FLAG_USE_16BIT_INDICES 0x1u
+#define PLTPT_INSTANCE_FLAG_OBJECT_FRONT_FACE_CW 0x8u
+#define PLTPT_INSTANCE_FLAG_WORLD_FRONT_FACE_CW 0x10u
+
+/* MeshDesc, 32 B — SceneTypes.slang:152-210 (indexed by GeometryInstanceData::geometryID). */
+typedef struct PltptMeshDesc {
+    uint32_t vbOffset, ibOffset, vertexCount, indexCount;
+    uint32_t skinningVbOffset, prevVbOffset, materialID, flags;
+} PltptMeshDesc;
+
+/* MaterialDataBlob, 128 B = MaterialHeader (8 B, MaterialData.slang:38-160) + BasicMaterialData
+ * (BasicMaterialData.slang:61-100).  All PLT parameters are fp16. */
+typedef struct PltptMaterialBlob {
+    uint32_t header[2];           /* packedData.x: type[0:16) nestedPriority[16:20) lobes[20:28) doubleSided 28 thin 29 emissive 30 basic 31 */
+    uint32_t flags;
+    uint16_t baseColor[4];
+    uint16_t specular[4];
+    uint16_t data1[4];
+    uint16_t data2[4];
+    uint16_t specularTransmission;
+    uint16_t transmission[3];
+    uint16_t diffuseTransmission;
+    uint16_t volumeScattering[3];
+    uint16_t IoR;
+    uint16_t volumeAbsorption[3];
+    uint16_t volumeAnisotropy;
+    uint16_t _pad0;
+    uint32_t emissionSpectralId;
+    uint32_t iorNSpectralId;
+    uint32_t iorKSpectralId;
+    float    displacementScale;
+    float    displacementOffset;
+    uint32_t texBaseColor, texSpecular, texEmissive, texNormalMap;
+    uint32_t texTransmission, texDisplacementMap, texData1, texData2; /* TextureHandle: mode = bits [29,31); only Uniform (0) supported */
+    uint32_t _pad1;
+} PltptMaterialBlob;
+#define PLTPT_NO_SPECTRAL_PROFILE 0xffffffffu
+
+/* MaterialType — Source/Falcor/Scene/Material/MaterialTypes.slang:37-54 */
+enum {
+    PLTPT_MATERIAL_STANDARD = 1,
+    PLTPT_MATERIAL_DIFFUSE = 2,
+    PLTPT_MATERIAL_CONDUCTOR = 3,
+    PLTPT_MATERIAL_DIELECTRIC = 4,
+    PLTPT_MATERIAL_OPAQUE_DIELECTRIC = 5,
+    PLTPT_MATERIAL_THIN_DIELECTRIC = 6,
+    PLTPT_MATERIAL_COATED_CONDUCTOR = 7,
+    PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC = 8,
+    PLTPT_MATERIAL_GRATED_CONDUCTOR = 9,
+    PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC = 10,
+    PLTPT_MATERIAL_MULTILAYERED_STACK = 11
+};
+
+/* LobeType — Source/Falcor/Rendering/Materials/LobeType.slang:36-68 */
+enum {
+    PLTPT_LOBE_DIFFUSE_REFLECTION = 0x01,
+    PLTPT_LOBE_SCATTER_REFLECTION = 0x02,
+    PLTPT_LOBE_DELTA_REFLECTION = 0x04,
+    PLTPT_LOBE_DISPERSIVE_DELTA_REFLECTION = 0x08,
+    PLTPT_LOBE_DIFFUSE_TRANSMISSION = 0x10,
+    PLTPT_LOBE_SCATTER_TRANSMISSION = 0x20,
+    PLTPT_LOBE_DELTA_TRANSMISSION = 0x40,
+    PLTPT_LOBE_DISPERSIVE_DELTA_TRANSMISSION = 0x80,
+    PLTPT_LOBE_DISPERSIVE_DELTA = 0x88,
+    PLTPT_LOBE_DELTA = 0xCC,
+    PLTPT_LOBE_NON_DELTA = 0x33,
+    PLTPT_LOBE_REFLECTION = 0x0f,
+    PLTPT_LOBE_TRANSMISSION = 0xf0,
+    PLTPT_LOBE_ALL = 0xffff
+};
+
+/* SpectralProfile, 1052 B — BasicMaterialData.slang:43-54; built by genSpectralProfile, SceneBuilder.cpp:911-960. */
+typedef struct PltptSpectralProfile {
+    float    rgb[3];
+    float    intensity;
+    uint32_t bins;
+    float    minWavelength;
+    float    maxWavelength;
+    float    pdf[128];
+    float    icdf[128];
+} PltptSpectralProfile;
+
+/* LightData, 208 B — Source/Falcor/Scene/Lights/LightData.slang:49-72. Matrices row-major. */
+typedef struct PltptLightData {
+    float    posW[3];
+    uint32_t type; /* 0 Point, 1 Directional, 2 Distant, 3 Rect, 4 Disc, 5 Sphere */
+    float    dirW[3];
+    float    openingAngle;
+    float    cosOpeningAngle;
+    float    cosSubtendedAngle;
+    float    penumbraAngle;
+    uint32_t intensitySpectrumId;
+    float    tangent[3];
+    float    surfaceArea;
+    float    bitangent[3];
+    float    _pad;
+    float    transMat[16];
+    float    transMatIT[16];
+} PltptLightData;
+
+/* PackedEmissiveTriangle, 64 B — Source/Falcor/Scene/Lights/LightCollectionShared.slang:76-135. */
+typedef struct PltptEmissiveTriangle {
+    float    posAndTexCoords[3][4]; /* xyz = world position, w = 2 x fp16 uv bits */
+    uint32_t normal;                /* 2x16 snorm octahedral */
+    uint32_t area;                  /* fp32 bits */
+    uint32_t materialID;
+    uint32_t lightIdx;
+} PltptEmissiveTriangle;
+
+/* EmissiveFlux, 16 B — LightCollectionShared.slang:140-144. */
+typedef struct PltptEmissiveFlux {
+    float flux;
+    float averageRadiance[3];
+} PltptEmissiveFlux;
+
+/* CameraData, 640 B — Source/Falcor/Scene/Camera/CameraData.slang:36-69. Matrices row-major. */
+typedef struct PltptCameraData {
+    float viewMat[16], prevViewMat[16], projMat[16], viewProjMat[16];
+    float invViewProj[16], viewProjMatNoJitter[16], prevViewProjMatNoJitter[16], projMatNoJitter[16];
+    float posW[3];     float focalLength;
+    float prevPosW[3]; float _padding0;
+    float up[3];       float aspectRatio;
+    float target[3];   float nearZ;
+    float cameraU[3];  float farZ;
+    float cameraV[3];  float jitterX;
+    float cameraW[3];  float jitterY;
+    float frameHeight, frameWidth, focalDistance, apertureRadius;
+    float shutterSpeed, ISOSpeed, polarizerTheta, polarizer;
+} PltptCameraData;
+
+/* BounceData, 40 B — Source/RenderPasses/PLTPT/Path.slang:113-142 (the record appendBounce writes,
+ * pltpt.slangh:138-154).  Exposed for parity checks of the sample stage. */
+typedef struct PltptBounce {
+    uint32_t hit[4];        /* PackedHitInfo, HitInfo.slang:459-487 */
+    float    encodedWi[2];  /* equal-area octahedral, MathHelpers.slang:199-240 */
+    uint32_t sampledBsdfLobe;
+    uint32_t flags;         /* RayFlags, Path.slang:47-109 */
+    float    pathContribution;
+    float    lastNonDeltaPdf;
+} PltptBounce;
+
+/* Scene description: the subset of `gScene` + light-sampler data the pass reads.
+ * If pointersAreDevice != 0 all pointers are CUDA device pointers (the Falcor interop case:
+ * Resource::getSharedApiHandle -> cudaImportExternalMemory); otherwise they are host pointers.
+ * pltpt_set_scene copies everything it needs; the caller keeps ownership. */
+typedef struct PltptSceneDesc {
+    const PltptPackedVertex*     vertices;            uint32_t vertexCount;
+    const void*                  indexData;           uint64_t indexDataBytes;
+    const PltptGeometryInstance* geometryInstances;   uint32_t instanceCount;
+    const PltptMeshDesc*         meshes;              uint32_t meshCount;
+    const float*                 worldMatrices;       /* float4x4 row-major per matrixID */
+    const float*                 inverseTransposeWorldMatrices;
+    uint32_t                     matrixCount;
+    const PltptMaterialBlob*     materialData;        uint32_t materialCount;
+    const PltptSpectralProfile*  spectralProfiles;    uint32_t profileCount;
+    const PltptLightData*        lights;              uint32_t lightCount;
+    /* LightCollection (Source/Falcor/Scene/Lights/LightCollection.slang:40-60) */
+    const PltptEmissiveTriangle* emissiveTriangles;   uint32_t emissiveTriangleCount;
+    const PltptEmissiveFlux*     emissiveFlux;
+    const uint32_t*              activeTriangles;     uint32_t activeTriangleCount;
+    const uint32_t*              perMeshInstanceOffset; /* [instanceCount], 0xffffffff = not emissive */
+    /* EmissivePowerSampler (Source/Falcor/Rendering/Lights/EmissivePowerSampler.slang:36-40) */
+    const uint32_t*              triangleAliasTable;  /* uint2 per emissive triangle */
+    float                        invWeightsSum;
+    /* HitInfo bit allocation (scene defines, Source/Falcor/Scene/HitInfo.cpp:52-90) */
+    uint32_t hitInfoTypeBits, hitInfoInstanceIDBits, hitInfoPrimitiveIndexBits;
+    uint32_t pointersAreDevice;
+} PltptSceneDesc;
+
+/* ------------------------------------------------------------------------------------------
+ * Lifetime
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_create(const PltptOptions* opts, int cudaDevice, PltptHandle* out);
+PLTPT_API int pltpt_destroy(PltptHandle h);
+PLTPT_API const char* pltpt_last_error(void);
+PLTPT_API const char* pltpt_version(void);
+
+/* Replaces PLTPT::parseDictionary + the recompile on `mOptionsChanged` (PLTPT.cpp:147-175,361-372). */
+PLTPT_API int pltpt_set_options(PltptHandle h, const PltptOptions* opts);
+
+/* Replaces PLTPT::setScene (PLTPT.cpp:501-552) and the driver BLAS/TLAS build
+ * (Source/Falcor/Scene/Scene.cpp:3092-3760): uploads the scene, builds the 8-wide BVH. */
+PLTPT_API int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* scene);
+
+/* ------------------------------------------------------------------------------------------
+ * Rendering — replaces the tile loop of PLTPT::execute (PLTPT.cpp:487-495):
+ * one call = one sample per pixel = sample stage + solve stage over the whole frame.
+ * color/albedo/normal are RGBA32F device buffers of width*height texels (row-major, like the
+ * RenderData textures "color","albedo","normal", PLTPT.cpp:65-78); albedo/normal may be NULL.
+ * `camera` is a HOST pointer.  `stream` is a cudaStream_t (0 = default).
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,
+                                 uint32_t width, uint32_t height,
+                                 float* color, float* albedo, float* normal, void* stream);
+
+/* AccumulatePass equivalent (Source/RenderPasses/AccumulatePass/Accumulate.cs.slang:148-198, Double mode):
+ * renders frames [firstFrame, firstFrame+frameStep*frameCount) with stride frameStep, applying the
+ * GBufferRT Halton-16 jitter per frame (GBufferBase.cpp:212-228), summing color into `accum`
+ * (width*height*4 doubles, device).  Used for sample-index partitioning across GPUs. */
+PLTPT_API int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount,
+                                      const PltptCameraData* camera, uint32_t width, uint32_t height,
+                                      double* accum, void* stream);
+
+/* Host-buffer convenience used by the Falcor shell when no shared CUDA surface exists:
+ * renders one frame and copies RGBA32F results to host memory (any of the three may be NULL). */
+PLTPT_API int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,
+                                      uint32_t width, uint32_t height,
+                                      float* colorHost, float* albedoHost, float* normalHost);
+
+/* Sample-stage only; copies the bounce buffer ((maxBounces+1) records per pixel, pixel-major,
+ * pltpt.slangh:132-136 with the tile spanning the whole frame) to host for parity checks. */
+PLTPT_API int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,
+                                      uint32_t width, uint32_t height, PltptBounce* bouncesHost);
+
+/* ------------------------------------------------------------------------------------------
+ * Ray queries against the scene BVH (replaces TraceRay, pltpt_sample.rt.slang:174-183,
+ * ShadowRays.slangh:68-77,115-124).  Rays are float[8] {ox,oy,oz,tmin,dx,dy,dz,tmax}.
+ * Closest hit writes uint4 {instanceID, primitiveIndex, asuint(u), asuint(v)} + t;
+ * a miss writes instanceID = 0xffffffff.  Any-hit writes 1 (occluded) / 0 (visible).
+ * Pointers are device pointers.
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_trace_closest(PltptHandle h, uint32_t rayCount, const float* rays,
+                                  uint32_t* hits, float* hitT, void* stream);
+PLTPT_API int pltpt_trace_any(PltptHandle h, uint32_t rayCount, const float* rays,
+                              uint32_t* occluded, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched PLT BSDF queries (config 1 of the benchmark; IMaterialInstance contract,
+ * Source/Falcor/Rendering/Materials/IMaterialInstance.slang:121-183).
+ *
+ * Queries use the canonical shading frame T=(1,0,0) B=(0,1,0) N=(0,0,1) at the origin.
+ * wi = direction to the light (ShadingData.V in the solve stage), wo = direction to the eye.
+ * For every query and each of `groups` hero wavelengths the HWSS set (SpectrumSampler.slang:44-54)
+ * is formed, an area beam (A = 1 mm^2, 1 m away, PLT.slang:273-290) is sourced along -wi,
+ * propagated to the surface and the BSDF is evaluated on the four basis Stokes vectors.
+ * Output: mueller[query][group][hwss][row][col], i.e. column c is the Stokes vector that
+ * eval() produces from basis vector e_c.  All pointers are device pointers.
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_bsdf_eval_mueller(PltptHandle h, uint32_t materialID, uint32_t lobe,
+                                      uint32_t queryCount, uint32_t groups,
+                                      const float* wi /*3n*/, const float* wo /*3n*/,
+                                      const float* heroWavelengths /*groups*n*/,
+                                      float* mueller /*n*groups*HWSS*16*/, void* stream);
+
+/* bsdf.sample() + bsdf.pdf(): per query a sample generator seeded SampleGenerator(pixel=(i&0xffff,i>>16), seed)
+ * is used.  out = {wo.x, wo.y, wo.z, pdf, asfloat(lobe), weight, valid(0/1), pdf(wi,wo) re-evaluated} per query. */
+PLTPT_API int pltpt_bsdf_sample(PltptHandle h, uint32_t materialID, uint32_t lobeMask, uint32_t queryCount,
+                                const float* wi /*3n*/, const float* wavelengths /*n*/, uint32_t seed,
+                                float* out /*8n*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Counters (kernel launches, rays traced, BVH nodes visited ...) for bench.py / DESIGN.md.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct PltptStats {
+    uint64_t kernelLaunches;     /* launches of our kernels since the last reset */
+    uint64_t raysClosest, raysAny;
+    uint64_t bvhNodes, bvhLeafTriangles, triangleCount;
+    uint64_t pathVertices;       /* recorded bounce vertices of the last frame */
+    uint64_t bsdfEvals;          /* IMaterialInstance.eval calls x wavelengths of the last frame (if counted) */
+    double   bvhBuildMs;
+} PltptStats;
+PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
+PLTPT_API int pltpt_reset_stats(PltptHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLTPT_H_ */
