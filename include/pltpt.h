@@ -221,7 +221,7 @@ typedef struct PltptEmissiveFlux {
     float averageRadiance[3];
 } PltptEmissiveFlux;
 
-/* CameraData, 640 B — Source/Falcor/Scene/Camera/CameraData.slang:36-69. Matrices row-major. */
+/* CameraData, 656 B — Source/Falcor/Scene/Camera/CameraData.slang:36-69. Matrices row-major. */
 typedef struct PltptCameraData {
     float viewMat[16], prevViewMat[16], projMat[16], viewProjMat[16];
     float invViewProj[16], viewProjMatNoJitter[16], prevViewProjMatNoJitter[16], projMatNoJitter[16];

@@ -1,0 +1,525 @@
+// api.cu — C ABI (include/pltpt.h): lifetime, options, scene upload + table repacking, batched BSDF queries.
+#include "context.h"
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+
+using namespace plt;
+
+namespace plt {
+static thread_local std::string g_lastError;
+void setError(const std::string& s) { g_lastError = s; }
+int cudaFail(cudaError_t e, const char* what) {
+    setError(std::string("CUDA error '") + cudaGetErrorString(e) + "' in " + what);
+    return e == cudaErrorMemoryAllocation ? PLTPT_ERR_OUT_OF_MEMORY : PLTPT_ERR_CUDA;
+}
+}  // namespace plt
+
+static int fail(int code, const std::string& msg) { setError(msg); return code; }
+
+// ------------------------------------------------------------------------------------------------ options
+extern "C" void pltpt_default_options(PltptOptions* o) {  // PLTPT.h:74-108
+    if (!o) return;
+    *o = PltptOptions{32, 512, 4, 1, 1, 0, 1.f, 1.f, .025f, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 2, 60, 5e-5f};
+}
+static int validateOptions(const PltptOptions& o) {
+    if (o.HWSS < 1 || o.HWSS > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "HWSS must be in 1..4");
+    if (o.tileSize == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "tileSize must be > 0");
+    if (o.maxBounces > 255) return fail(PLTPT_ERR_INVALID_ARGUMENT, "maxBounces must be <= 255");
+    if (o.emissiveSampler > 1) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Unknown emissive light sampler type");  // PLTPT.cpp:409
+    if (o.sampleGenerator != 1) return fail(PLTPT_ERR_UNSUPPORTED, "only SAMPLE_GENERATOR_UNIFORM (1) is supported");
+    if (o.MNEEMaxOccluders > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "MNEEMaxOccluders must be <= 4");
+    return PLTPT_OK;
+}
+
+extern "C" const char* pltpt_last_error(void) { return g_lastError.c_str(); }
+extern "C" const char* pltpt_version(void) { return "pltpt-b200 0.1 (sm_100a)"; }
+
+extern "C" int pltpt_create(const PltptOptions* opts, int cudaDevice, PltptHandle* out) {
+    if (!out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "out handle is null");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(PLTPT_ERR_NO_DEVICE, "no CUDA device: the PLTPT path has no CPU fallback");
+    if (cudaDevice < 0 || cudaDevice >= n) return fail(PLTPT_ERR_INVALID_ARGUMENT, "invalid CUDA device index");
+    PltptOptions o;
+    pltpt_default_options(&o);
+    if (opts) o = *opts;
+    if (int r = validateOptions(o)) return r;
+    PLT_CUDA(cudaSetDevice(cudaDevice));
+    PltptContext* c = new PltptContext();
+    c->device = cudaDevice;
+    c->opt = o;
+    cudaEventCreate(&c->evA);
+    cudaEventCreate(&c->evB);
+    *out = c;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_destroy(PltptHandle h) {
+    if (!h) return PLTPT_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->evA) cudaEventDestroy(h->evA);
+    if (h->evB) cudaEventDestroy(h->evB);
+    delete h;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_set_options(PltptHandle h, const PltptOptions* opts) {
+    if (!h || !opts) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int r = validateOptions(*opts)) return r;
+    h->opt = *opts;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
+    if (!h || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    *out = h->stats;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_reset_stats(PltptHandle h) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    const double b = h->stats.bvhBuildMs;
+    const uint64_t n = h->stats.bvhNodes, l = h->stats.bvhLeafTriangles, t = h->stats.triangleCount;
+    h->stats = PltptStats{};
+    h->stats.bvhBuildMs = b; h->stats.bvhNodes = n; h->stats.bvhLeafTriangles = l; h->stats.triangleCount = t;
+    return PLTPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scene upload
+namespace {
+float hostEvalSpectrum(const std::vector<PltptSpectralProfile>& profiles, uint32_t id, float lambda) {  // Scene.slang:251-270
+    if (id == PLTPT_NO_SPECTRAL_PROFILE || id >= profiles.size()) return 0.f;
+    const PltptSpectralProfile& sp = profiles[id];
+    const float x = (lambda - sp.minWavelength) / (sp.maxWavelength - sp.minWavelength) * (sp.bins - 1.0f);
+    const float i = std::floor(x), w = x - i;
+    if (lambda < sp.minWavelength || lambda > sp.maxWavelength) return 0.f;
+    const int i0 = std::max(0, std::min(int(sp.bins) - 1, int(i))), i1 = std::max(0, std::min(int(sp.bins) - 1, int(i + 1)));
+    return sp.intensity * (sp.pdf[i0] + (sp.pdf[i1] - sp.pdf[i0]) * w);
+}
+float hostFresnelConductor(float n, float k) {  // evalFresnelConductor(eta, 1) — Fresnel.slang:60-90
+    if (n == 0 && k == 0) return 0.f;
+    const std::complex<float> eta(n, k), one(1.f, 0.f);
+    const std::complex<float> ie = one / eta;
+    std::complex<float> t = std::sqrt(one - 0.f * ie * ie);
+    const std::complex<float> rs = (one - eta * t) / (one + eta * t), rp = (eta - t) / (eta + t);
+    return .5f * (std::norm(rs) + std::norm(rp));
+}
+float hostFresnelDielectric(float eta) {  // evalFresnelDielectric(eta, 1)
+    if (eta == 1) return 0.f;
+    const float rs = (1 - eta) / (1 + eta), rp = (eta - 1) / (eta + 1);
+    return .5f * (rs * rs + rp * rp);
+}
+float roughnessToT(float alpha) {  // FractalSurface.slang:45-53
+    const float meank = k2Pi / (kMeanWavelength * 1e-3f);
+    const float a2 = sqr(std::min(std::max(alpha, .0f), .75f));
+    return std::min(5000.f, (1 - a2) / (4.f * sqr(meank) * a2));
+}
+float TToRoughness(float T) {
+    const float meank = k2Pi / (kMeanWavelength * 1e-3f);
+    return 1.f / std::sqrt(1.f + 4.f * sqr(meank) * T);
+}
+void setFractal(DevMaterial& d, float roughness, float gamma) {
+    d.surfA = roughnessToT(roughness);
+    d.surfGamma = std::max(1.1f, gamma);
+    d.surfQ = TToRoughness(d.surfA);
+    d.roughnessProp = d.surfQ;
+}
+float roughnessToSigma2(float r) { return std::pow(std::min(std::max(1.f - .5f * r, .0f), 1.f), 28.f) * 2500.f; }
+void setGaussian(DevMaterial& d, float roughness) {  // GaussianSurface.slang:52-60
+    const float s2 = roughnessToSigma2(roughness), s2max = roughnessToSigma2(0.1f), s2r0 = roughnessToSigma2(.0f);
+    d.surfQ = (s2r0 - s2) / (s2r0 - s2max);
+    d.surfA = std::min(s2max, s2);
+    d.roughnessProp = 2.f * (1.f - std::pow(d.surfA / 2500.f, 1.f / 28.f));
+}
+
+// Unpacks one MaterialDataBlob exactly as the *Material.slang setupMaterialInstance() functions do (fp16 slots).
+int unpackMaterial(const PltptMaterialBlob& m, const std::vector<PltptSpectralProfile>& profiles, DevMaterial& d) {
+    std::memset(&d, 0, sizeof(d));
+    for (uint32_t t : {m.texBaseColor, m.texSpecular, m.texEmissive, m.texNormalMap, m.texTransmission, m.texData1, m.texData2})
+        if (((t >> 29) & 3u) != 0) return fail(PLTPT_ERR_UNSUPPORTED, "textured material handles are not supported (TextureHandle::Mode::Uniform only)");
+    d.type = m.header[0] & 0xffffu;
+    d.hdrFlags = (m.header[0] >> 28) & 1u;
+    const float base[4] = {h2f(m.baseColor[0]), h2f(m.baseColor[1]), h2f(m.baseColor[2]), h2f(m.baseColor[3])};
+    const float spec[4] = {h2f(m.specular[0]), h2f(m.specular[1]), h2f(m.specular[2]), h2f(m.specular[3])};
+    const float data1[4] = {h2f(m.data1[0]), h2f(m.data1[1]), h2f(m.data1[2]), h2f(m.data1[3])};
+    const float data2[4] = {h2f(m.data2[0]), h2f(m.data2[1]), h2f(m.data2[2]), h2f(m.data2[3])};
+    const float tran[3] = {h2f(m.transmission[0]), h2f(m.transmission[1]), h2f(m.transmission[2])};
+    const float IoR = h2f(m.IoR);
+    d.c0x = base[0]; d.c0y = base[1]; d.c0z = base[2];
+    d.c1x = d.c1y = d.c1z = 1.f;
+    d.opacity = base[3];
+    d.emissionId = PLTPT_NO_SPECTRAL_PROFILE;
+    d.etaN = m.iorNSpectralId; d.etaK = m.iorKSpectralId;
+    d.extEta = IoR;
+    d.albx = base[0]; d.alby = base[1]; d.albz = base[2];
+    const float meanK = k2Pi / (kMeanWavelength * 1e-3f);
+    switch (d.type) {
+        case PLTPT_MATERIAL_DIFFUSE:  // PLTDiffuseMaterial.slang:40-50, PLTDiffuseBSDF.slang:136-155
+            d.emissionId = m.emissionSpectralId;
+            d.lobes = L_DiffuseReflection;
+            d.propFlags = m.emissionSpectralId != PLTPT_NO_SPECTRAL_PROFILE ? P_IsEmissive : 0;
+            d.roughnessProp = 1.f;
+            break;
+        case PLTPT_MATERIAL_CONDUCTOR: {  // PLTConductorMaterial.slang:40-57, PLTConductorBSDF.slang:218-241
+            setFractal(d, spec[1], spec[0]);
+            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
+            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
+            const float F = hostFresnelConductor(hostEvalSpectrum(profiles, d.etaN, kMeanWavelength), hostEvalSpectrum(profiles, d.etaK, kMeanWavelength));
+            d.albx *= F; d.alby *= F; d.albz *= F;
+            break;
+        }
+        case PLTPT_MATERIAL_DIELECTRIC: {  // PLTDielectricMaterial.slang:40-57, PLTDielectricBSDF.slang:335-360
+            const float B = (tran[0] > 0 || tran[1] > 0 || tran[2] > 0) ? spec[0] : 0.f;
+            d.c1x = tran[0]; d.c1y = tran[1]; d.c1z = tran[2];
+            setGaussian(d, spec[1]);
+            d.f0 = std::max(1.f, IoR - 2.897f * B); d.f1 = spec[3]; d.f2 = B;
+            d.opacity = .5f * base[3];
+            const uint32_t dT = B != 0.f ? L_DispersiveDeltaTransmission : L_DeltaTransmission;
+            d.lobes = d.surfQ == 0.f ? (L_DeltaReflection | dT) : (L_DeltaReflection | dT | L_ScatterReflection | L_ScatterTransmission);
+            d.propFlags = P_IsTransmissive | (d.surfQ < kQcutoffForMS ? P_CanMSTransmissive : 0);
+            const float F = hostFresnelDielectric((d.f0 + B * sqr(meanK * k1_2Pi)) / d.f1);
+            d.albx *= F; d.alby *= F; d.albz *= F;
+            break;
+        }
+        case PLTPT_MATERIAL_OPAQUE_DIELECTRIC:  // PLTOpaqueDielectricMaterial.slang:40-52
+            setFractal(d, spec[1], 3.f);
+            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
+            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
+            break;
+        case PLTPT_MATERIAL_THIN_DIELECTRIC:  // PLTThinDielectricMaterial.slang:40-54
+            d.f0 = IoR; d.f1 = spec[3]; d.f2 = base[0] * spec[0]; d.f3 = base[1]; d.f4 = base[2];
+            d.opacity = .5f * base[3];
+            d.lobes = L_DeltaReflection | L_DeltaTransmission;
+            d.propFlags = P_IsTransmissive | P_CanMSReflective | P_CanMSTransmissive;
+            d.albx = d.alby = d.albz = 1.f;
+            d.roughnessProp = 0.f;
+            break;
+        case PLTPT_MATERIAL_COATED_CONDUCTOR: case PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC: {  // PLTCoatedConductorMaterial.slang:40-60
+            setFractal(d, spec[1], 3.f);
+            d.f0 = data1[3]; d.f1 = data1[0] * spec[2];
+            d.f2 = IoR + (d.f0 - IoR) * (std::min(std::max(d.f1, 0.f), .05f) / .05f);  // coatEta(), PLTCoatedConductorBSDF.slang:65-68
+            d.u0 = d.type == PLTPT_MATERIAL_COATED_CONDUCTOR ? 1u : 0u;
+            d.opacity = 1.f;
+            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
+            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
+            break;
+        }
+        case PLTPT_MATERIAL_GRATED_CONDUCTOR: case PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC: {  // PLTDiffractionGratedConductorMaterial.slang:41-73
+            setFractal(d, data2[1], 3.f);
+            d.f0 = data1[2];
+            d.f1 = data1[0] > 0.f ? 1.f / data1[0] : 0.f; d.f2 = data1[1] > 0.f ? 1.f / data1[1] : 0.f;
+            d.f3 = data2[0] * spec[0]; d.f4 = spec[1];
+            d.f5 = std::cos(d.f0); d.f6 = std::sin(d.f0);
+            const uint32_t typeAndLobes = m.data1[3];
+            d.u0 = std::min(std::max(typeAndLobes & 0xFFu, 1u), 8u);
+            d.u1 = typeAndLobes >> 8;
+            d.lobes = (d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection)) | L_DispersiveDeltaReflection;
+            d.propFlags = P_CanMSReflective;
+            const float a = std::exp(-sqr(1.f * d.f3 * meanK));
+            if (d.type == PLTPT_MATERIAL_GRATED_CONDUCTOR) {
+                const float F = hostFresnelConductor(hostEvalSpectrum(profiles, d.etaN, kMeanWavelength), hostEvalSpectrum(profiles, d.etaK, kMeanWavelength));
+                d.albx *= F; d.alby *= F; d.albz *= F;
+            }
+            d.roughnessProp = (1 - a) * d.surfQ;
+            break;
+        }
+        case PLTPT_MATERIAL_MULTILAYERED_STACK:  // PLTMultiLayeredStackMaterial.slang:40-56
+            d.f0 = data2[0]; d.f1 = data2[1]; d.f2 = data1[0]; d.f3 = data1[1]; d.u0 = m.data1[3];
+            d.lobes = L_DeltaReflection;
+            d.propFlags = P_CanMSReflective;
+            d.roughnessProp = 0.f;
+            break;
+        default:
+            return fail(PLTPT_ERR_UNSUPPORTED, "material type " + std::to_string(d.type) + " is not a PLT material (only MaterialType 2..11 are reachable from PLTPT)");
+    }
+    return PLTPT_OK;
+}
+
+void repackProfile(const PltptSpectralProfile& sp, DevProfile& d) {
+    std::memset(&d, 0, sizeof(d));
+    d.intensity = sp.intensity; d.binsF = float(sp.bins); d.minWavelength = sp.minWavelength; d.maxWavelength = sp.maxWavelength;
+    const int bins = int(std::min<uint32_t>(sp.bins, 128));
+    for (int i = 0; i < 128; ++i) {
+        const int i0 = std::max(0, std::min(bins - 1, i)), i1 = std::max(0, std::min(bins - 1, i + 1));
+        d.pair[i] = bins > 0 ? make_float2(sp.pdf[i0], sp.pdf[i1]) : make_float2(0.f, 0.f);
+        d.icdf[i] = sp.icdf[i];
+    }
+}
+
+template <typename T>
+int fetchHost(std::vector<T>& dst, const T* src, size_t count, bool device) {
+    dst.resize(count);
+    if (count == 0) return PLTPT_OK;
+    if (!src) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene buffer pointer is null but its count is non-zero");
+    if (device) PLT_CUDA(cudaMemcpy(dst.data(), src, count * sizeof(T), cudaMemcpyDeviceToHost));
+    else std::memcpy(dst.data(), src, count * sizeof(T));
+    return PLTPT_OK;
+}
+int upload(DevBuf& buf, const void* src, size_t bytes, bool device) {
+    if (bytes == 0) { buf.release(); return PLTPT_OK; }
+    if (!src) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene buffer pointer is null but its size is non-zero");
+    PLT_CUDA(buf.ensure(bytes));
+    PLT_CUDA(cudaMemcpy(buf.p, src, bytes, device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return PLTPT_OK;
+}
+}  // namespace
+
+extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
+    if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    PLT_CUDA(cudaSetDevice(h->device));
+    h->hasScene = false;
+    const bool dev = s->pointersAreDevice != 0;
+    if (s->instanceCount == 0 || s->vertexCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no geometry");
+    if (s->hitInfoTypeBits == 0 || s->hitInfoTypeBits > 8) return fail(PLTPT_ERR_INVALID_ARGUMENT, "hitInfoTypeBits out of range");
+
+    // host mirrors of the small tables
+    std::vector<PltptMaterialBlob> mats;
+    std::vector<PltptSpectralProfile> profiles;
+    if (int r = fetchHost(h->hInstances, s->geometryInstances, s->instanceCount, dev)) return r;
+    if (int r = fetchHost(h->hMeshes, s->meshes, s->meshCount, dev)) return r;
+    if (int r = fetchHost(mats, s->materialData, s->materialCount, dev)) return r;
+    if (int r = fetchHost(profiles, s->spectralProfiles, s->profileCount, dev)) return r;
+
+    h->hInstTriOffset.assign(s->instanceCount + 1, 0);
+    for (uint32_t i = 0; i < s->instanceCount; ++i) {
+        const PltptGeometryInstance& gi = h->hInstances[i];
+        if ((gi.flags >> 29) != PLTPT_GEOMETRY_TYPE_TRIANGLE_MESH) return fail(PLTPT_ERR_UNSUPPORTED, "only GeometryType::TriangleMesh instances are supported (PLTPT.cpp:527 binds triangle hit groups only)");
+        if (gi.geometryID >= s->meshCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "geometryID out of range");
+        if (gi.materialID >= s->materialCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "materialID out of range");
+        if (gi.globalMatrixID >= s->matrixCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "globalMatrixID out of range");
+        const PltptMeshDesc& m = h->hMeshes[gi.geometryID];
+        h->hInstTriOffset[i + 1] = h->hInstTriOffset[i] + (m.indexCount > 0 ? m.indexCount : m.vertexCount) / 3;
+    }
+    std::vector<DevMaterial> dmats(mats.size());
+    for (size_t i = 0; i < mats.size(); ++i) {
+        if (int r = unpackMaterial(mats[i], profiles, dmats[i])) return r;
+        for (uint32_t id : {dmats[i].emissionId, dmats[i].etaN, dmats[i].etaK})
+            if (id != PLTPT_NO_SPECTRAL_PROFILE && id >= s->profileCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "spectral profile id out of range");
+    }
+    std::vector<DevProfile> dprofiles(profiles.size());
+    for (size_t i = 0; i < profiles.size(); ++i) repackProfile(profiles[i], dprofiles[i]);
+
+    if (int r = upload(h->vertices, s->vertices, size_t(s->vertexCount) * sizeof(PltptPackedVertex), dev)) return r;
+    if (int r = upload(h->indexData, s->indexData, s->indexDataBytes, dev)) return r;
+    if (int r = upload(h->instances, h->hInstances.data(), h->hInstances.size() * sizeof(PltptGeometryInstance), false)) return r;
+    if (int r = upload(h->meshes, h->hMeshes.data(), h->hMeshes.size() * sizeof(PltptMeshDesc), false)) return r;
+    if (int r = upload(h->world, s->worldMatrices, size_t(s->matrixCount) * 64, dev)) return r;
+    if (int r = upload(h->worldIT, s->inverseTransposeWorldMatrices, size_t(s->matrixCount) * 64, dev)) return r;
+    if (int r = upload(h->materials, dmats.data(), dmats.size() * sizeof(DevMaterial), false)) return r;
+    if (int r = upload(h->profiles, dprofiles.data(), dprofiles.size() * sizeof(DevProfile), false)) return r;
+    if (int r = upload(h->lights, s->lights, size_t(s->lightCount) * sizeof(PltptLightData), dev)) return r;
+    if (int r = upload(h->etris, s->emissiveTriangles, size_t(s->emissiveTriangleCount) * sizeof(PltptEmissiveTriangle), dev)) return r;
+    if (int r = upload(h->eflux, s->emissiveFlux, size_t(s->emissiveTriangleCount) * sizeof(PltptEmissiveFlux), dev)) return r;
+    if (int r = upload(h->activeTris, s->activeTriangles, size_t(s->activeTriangleCount) * 4, dev)) return r;
+    if (int r = upload(h->perMeshOffset, s->perMeshInstanceOffset, s->perMeshInstanceOffset ? size_t(s->instanceCount) * 4 : 0, dev)) return r;
+    if (int r = upload(h->alias, s->triangleAliasTable, s->triangleAliasTable ? size_t(s->emissiveTriangleCount) * 8 : 0, dev)) return r;
+    if (int r = upload(h->instTriOffset, h->hInstTriOffset.data(), h->hInstTriOffset.size() * 4, false)) return r;
+
+    DevScene& d = h->scene;
+    d = DevScene{};
+    d.vertices = h->vertices.as<PltptPackedVertex>();
+    d.indexData = h->indexData.as<uint8_t>();
+    d.instances = h->instances.as<PltptGeometryInstance>();
+    d.meshes = h->meshes.as<PltptMeshDesc>();
+    d.world = h->world.as<float>();
+    d.worldIT = h->worldIT.as<float>();
+    d.materials = h->materials.as<DevMaterial>();
+    d.profiles = h->profiles.as<DevProfile>();
+    d.lights = h->lights.as<PltptLightData>();
+    d.etris = h->etris.as<PltptEmissiveTriangle>();
+    d.eflux = h->eflux.as<PltptEmissiveFlux>();
+    d.activeTris = h->activeTris.as<uint32_t>();
+    d.perMeshInstanceOffset = h->perMeshOffset.as<uint32_t>();
+    d.alias = h->alias.as<uint2>();
+    d.instTriOffset = h->instTriOffset.as<uint32_t>();
+    d.instanceCount = s->instanceCount;
+    d.lightCount = s->lightCount;
+    d.etriCount = s->emissiveTriangleCount;
+    d.activeTriCount = s->activeTriangleCount;
+    d.triCount = h->hInstTriOffset.back();
+    d.invWeightsSum = s->invWeightsSum;
+    d.hitTypeBits = s->hitInfoTypeBits; d.hitInstBits = s->hitInfoInstanceIDBits; d.hitPrimBits = s->hitInfoPrimitiveIndexBits;
+    h->emissiveTriangleCount = s->emissiveTriangleCount;
+    h->lightCount = s->lightCount;
+    if (d.etriCount > 0 && (!d.etris || !d.eflux || !d.perMeshInstanceOffset)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "emissive triangles present but light-collection buffers missing");
+    if (d.etriCount > 0 && h->opt.emissiveSampler == 1 && !d.alias) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table");
+    if (d.triCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no triangles");
+
+    if (int r = buildBvh(h, 0)) return r;
+    h->hasScene = true;
+    return PLTPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BSDF sweeps
+namespace {
+__device__ __forceinline__ SD canonicalSd(uint32_t materialID, float3 V) {
+    SD sd;
+    sd.posW = mk3(0.f); sd.V = V; sd.N = mk3(0.f, 0.f, 1.f); sd.T = mk3(1.f, 0.f, 0.f); sd.B = mk3(0.f, 1.f, 0.f);
+    sd.faceN = sd.N; sd.uv = mk2(0.f, 0.f); sd.materialID = materialID; sd.frontFacing = true;
+    return sd;
+}
+
+constexpr int kSweepThreads = 128;
+// One thread per (query, hero group): evaluates the BSDF on the four basis Stokes vectors; results are staged in
+// shared memory (stride 65 words: conflict-free) and written out as fully coalesced 128 B lines.
+__global__ void __launch_bounds__(kSweepThreads) k_bsdf_eval_mueller(DevScene sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups,
+                                                                     const float* __restrict__ wi, const float* __restrict__ wo, const float* __restrict__ hero,
+                                                                     float* __restrict__ out, int hwss, float maxBeamOmega) {
+    extern __shared__ float stage[];  // kSweepThreads * (hwss*16 + 1)
+    const int perThread = hwss * 16, stride = perThread + 1;
+    const uint64_t total = uint64_t(n) * groups;
+    const DevMaterial m = loadMaterial(sc.materials, materialID);
+    const BsdfCtx cx = {sc.profiles, hwss};
+    for (uint64_t base = uint64_t(blockIdx.x) * kSweepThreads; base < total; base += uint64_t(gridDim.x) * kSweepThreads) {
+        const uint64_t item = base + threadIdx.x;
+        if (item < total) {
+            const uint32_t i = uint32_t(item / groups), g = uint32_t(item % groups);
+            const float3 Wi = mk3(__ldg(wi + 3 * size_t(i)), __ldg(wi + 3 * size_t(i) + 1), __ldg(wi + 3 * size_t(i) + 2));
+            const float3 Wo = mk3(__ldg(wo + 3 * size_t(i)), __ldg(wo + 3 * size_t(i) + 1), __ldg(wo + 3 * size_t(i) + 2));
+            const float4 wl = hwssWavelengths(__ldg(hero + size_t(g) * n + i), hwss);
+            const SD sd = canonicalSd(materialID, Wi);
+            float* my = stage + threadIdx.x * stride;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                Beam beam = sourceBeamArea(Wi, -Wi, 1.f, 1.f, mk4(1.f), wl, maxBeamOmega, hwss);
+                const float4 e = mk4(c == 0 ? 1.f : 0.f, c == 1 ? 1.f : 0.f, c == 2 ? 1.f : 0.f, c == 3 ? 1.f : 0.f);
+                beam.L = mk4(e.x); beam.L1 = mk4(e.y); beam.L2 = mk4(e.z); beam.L3 = mk4(e.w);
+                beam.propagate(sd.posW);
+                bsdfEval(m, cx, sd, Wo, lobe, beam);
+                for (int j = 0; j < hwss; ++j) {
+                    const float4 SP = beam.getSP(j);
+                    my[j * 16 + 0 + c] = SP.x; my[j * 16 + 4 + c] = SP.y; my[j * 16 + 8 + c] = SP.z; my[j * 16 + 12 + c] = SP.w;
+                }
+            }
+        }
+        __syncthreads();
+        const uint64_t remaining = total - base;
+        const uint32_t valid = uint32_t(remaining < kSweepThreads ? remaining : kSweepThreads) * perThread;
+        float* dst = out + base * perThread;
+        for (uint32_t idx = threadIdx.x; idx < valid; idx += kSweepThreads) dst[idx] = stage[(idx / perThread) * stride + (idx % perThread)];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bsdf_sample(DevScene sc, uint32_t materialID, uint32_t lobeMask, uint32_t n, const float* __restrict__ wi,
+                                                     const float* __restrict__ wavelengths, uint32_t seed, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevMaterial m = loadMaterial(sc.materials, materialID);
+    const float3 Wi = mk3(wi[3 * size_t(i)], wi[3 * size_t(i) + 1], wi[3 * size_t(i) + 2]);
+    const SD sd = canonicalSd(materialID, Wi);
+    Rng sg = Rng::seed(i & 0xffff, i >> 16, seed);
+    Sample s;
+    const float wl = wavelengths[i];
+    const bool valid = bsdfSample(m, sd, sg, s, wl, lobeMask, mk3(0.f));
+    float4* o = reinterpret_cast<float4*>(out + 8 * size_t(i));
+    o[0] = mk4(s.wo.x, s.wo.y, s.wo.z, s.pdf);
+    o[1] = mk4(asfloat(s.lobe), s.weight, valid ? 1.f : 0.f, valid ? bsdfPdf(m, sd, s.wo, wl) : 0.f);
+}
+}  // namespace
+
+extern "C" int pltpt_bsdf_eval_mueller(PltptHandle h, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* wi, const float* wo,
+                                       const float* hero, float* mueller, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (materialID >= h->materials.bytes / sizeof(DevMaterial)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "materialID out of range");
+    if (n == 0 || groups == 0) return PLTPT_OK;
+    if (!wi || !wo || !hero || !mueller) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    const int hwss = int(h->opt.HWSS);
+    const uint64_t total = uint64_t(n) * groups;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const uint64_t blocksNeeded = (total + kSweepThreads - 1) / kSweepThreads;
+    const uint32_t grid = uint32_t(std::min<uint64_t>(blocksNeeded, uint64_t(sms) * 8));
+    const size_t smem = size_t(kSweepThreads) * (hwss * 16 + 1) * sizeof(float);
+    k_bsdf_eval_mueller<<<grid, kSweepThreads, smem, (cudaStream_t)stream>>>(h->scene, materialID, lobe, n, groups, wi, wo, hero, mueller, hwss, h->opt.sourcingMaxBeamOmega);
+    h->stats.kernelLaunches++;
+    h->stats.bsdfEvals += total * hwss * 4;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+extern "C" int pltpt_bsdf_sample(PltptHandle h, uint32_t materialID, uint32_t lobeMask, uint32_t n, const float* wi, const float* wavelengths, uint32_t seed, float* out, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (materialID >= h->materials.bytes / sizeof(DevMaterial)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "materialID out of range");
+    if (n == 0) return PLTPT_OK;
+    if (!wi || !wavelengths || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    k_bsdf_sample<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->scene, materialID, lobeMask, n, wi, wavelengths, seed, out);
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ray queries
+extern "C" int pltpt_trace_closest(PltptHandle h, uint32_t n, const float* rays, uint32_t* hits, float* hitT, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (n == 0) return PLTPT_OK;
+    if (!rays || !hits) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    return traceClosest(h, n, rays, hits, hitT, (cudaStream_t)stream);
+}
+extern "C" int pltpt_trace_any(PltptHandle h, uint32_t n, const float* rays, uint32_t* occluded, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (n == 0) return PLTPT_OK;
+    if (!rays || !occluded) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    return traceAny(h, n, rays, occluded, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ rendering
+static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, uint32_t hgt) {
+    if (!h || !cam) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (w == 0 || hgt == 0 || w > 65535 || hgt > 65535) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame dimensions must be in 1..65535 (path id packs the pixel in 16+16 bits, Path.slang:166)");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(PLTPT_ERR_CUDA, "cudaSetDevice failed");
+    return PLTPT_OK;
+}
+extern "C" int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* color, float* albedo, float* normal, void* stream) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    if (!color) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
+    return renderFrame(h, frameCount, cam, w, hgt, color, albedo, normal, nullptr, true, (cudaStream_t)stream);
+}
+extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
+                                       double* accum, void* stream) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    if (!accum) return fail(PLTPT_ERR_INVALID_ARGUMENT, "accum output is null");
+    if (frameStep == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep must be > 0");
+    for (uint32_t i = 0; i < frameCount; ++i) {
+        const uint32_t f = firstFrame + i * frameStep;
+        PltptCameraData c = *cam;
+        // GBufferRT Halton-16 jitter (HaltonSamplePattern.cpp:37-67, GBufferBase.cpp:212-228)
+        auto halton = [](uint32_t index, uint32_t base) { float result = 0.f, factor = 1.f; for (; index > 0; index /= base) { factor /= base; result += factor * (index % base); } return result; };
+        const uint32_t k = f % 16u;
+        float jx = halton(k, 2) + 0.5f, jy = halton(k, 3) + 0.5f;
+        jx = (jx - std::floor(jx)) - 0.5f; jy = (jy - std::floor(jy)) - 0.5f;
+        c.jitterX = jx / float(w); c.jitterY = jy / float(hgt);
+        if (int r = renderFrame(h, f, &c, w, hgt, nullptr, nullptr, nullptr, accum, true, (cudaStream_t)stream)) return r;
+    }
+    return PLTPT_OK;
+}
+extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* colorHost, float* albedoHost, float* normalHost) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    const size_t bytes = size_t(w) * hgt * 16;
+    PLT_CUDA(h->outColor.ensure(bytes));
+    PLT_CUDA(h->outAlbedo.ensure(bytes));
+    PLT_CUDA(h->outNormal.ensure(bytes));
+    if (int r = renderFrame(h, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0)) return r;
+    if (colorHost) PLT_CUDA(cudaMemcpy(colorHost, h->outColor.p, bytes, cudaMemcpyDeviceToHost));
+    if (albedoHost) PLT_CUDA(cudaMemcpy(albedoHost, h->outAlbedo.p, bytes, cudaMemcpyDeviceToHost));
+    if (normalHost) PLT_CUDA(cudaMemcpy(normalHost, h->outNormal.p, bytes, cudaMemcpyDeviceToHost));
+    return PLTPT_OK;
+}
+extern "C" int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, PltptBounce* bouncesHost) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    if (!bouncesHost) return fail(PLTPT_ERR_INVALID_ARGUMENT, "bounce output is null");
+    const size_t bytes = size_t(w) * hgt * 16;
+    PLT_CUDA(h->outColor.ensure(bytes));
+    PLT_CUDA(h->outAlbedo.ensure(bytes));
+    PLT_CUDA(h->outNormal.ensure(bytes));
+    if (int r = renderFrame(h, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, false, 0)) return r;
+    return copyBounces(h, bouncesHost, w, hgt);
+}

@@ -1,0 +1,105 @@
+// context.h — internal host-side state behind a PltptHandle and the device-side scene view.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "plt_bsdf.cuh"
+
+namespace plt {
+
+// ---- compressed 8-wide BVH node (80 B), after Ylitie/Karras/Laine 2017 "Efficient Incoherent Ray Traversal on GPUs
+// Through Compressed Wide BVHs": child boxes quantised to 8 bits on a per-node power-of-two grid.
+struct alignas(16) BvhNode {
+    float px, py, pz;          // node AABB origin
+    uint8_t ex, ey, ez, imask; // per-axis grid exponent (biased by 127), bit i of imask = child i is an inner node
+    uint32_t childBase;        // index of the first inner child node
+    uint32_t triBase;          // index of the first leaf triangle
+    uint8_t meta[8];           // inner: 0b001xxxxx | (24 + slot); leaf: (#tris in unary, 3 bits) << 5 | offset from triBase; 0 = empty
+    uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(BvhNode) == 80, "CWBVH node must be 80 B");
+
+// leaf triangle record: world-space vertices (exactly the values the intersection contract prescribes) + ids, 48 B
+struct alignas(16) BvhTri {
+    float v0x, v0y, v0z; uint32_t instanceID;
+    float v1x, v1y, v1z; uint32_t primitiveIndex;
+    float v2x, v2y, v2z; uint32_t globalIndex;
+};
+static_assert(sizeof(BvhTri) == 48, "BvhTri must be 48 B");
+
+// device view of the scene: Falcor buffers (as uploaded) + our derived tables
+struct DevScene {
+    const PltptPackedVertex* vertices;
+    const uint8_t* indexData;
+    const PltptGeometryInstance* instances;
+    const PltptMeshDesc* meshes;
+    const float* world;
+    const float* worldIT;
+    const DevMaterial* materials;
+    const DevProfile* profiles;
+    const PltptLightData* lights;
+    const PltptEmissiveTriangle* etris;
+    const PltptEmissiveFlux* eflux;
+    const uint32_t* activeTris;
+    const uint32_t* perMeshInstanceOffset;
+    const uint2* alias;
+    const uint32_t* instTriOffset;  // first global triangle of each instance (instanceCount + 1 entries)
+    const BvhNode* bvhNodes;
+    const BvhTri* bvhTris;
+    uint32_t instanceCount, lightCount, etriCount, activeTriCount, triCount;
+    float invWeightsSum;
+    uint32_t hitTypeBits, hitInstBits, hitPrimBits;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace plt
+
+struct PltptContext {
+    int device = 0;
+    PltptOptions opt{};
+    bool hasScene = false;
+    plt::DevScene scene{};
+    // owned device copies
+    plt::DevBuf vertices, indexData, instances, meshes, world, worldIT, materials, profiles, lights, etris, eflux, activeTris, perMeshOffset, alias, instTriOffset;
+    plt::DevBuf bvhNodes, bvhTris, bvhScratch[8];
+    // host mirrors needed by the host logic
+    std::vector<PltptGeometryInstance> hInstances;
+    std::vector<PltptMeshDesc> hMeshes;
+    std::vector<uint32_t> hInstTriOffset;
+    uint32_t emissiveTriangleCount = 0, lightCount = 0;
+    // per-frame work buffers (integrator.cu)
+    plt::DevBuf work[24];
+    uint32_t workW = 0, workH = 0, workBounces = 0;
+    plt::DevBuf outColor, outAlbedo, outNormal;
+    PltptStats stats{};
+    cudaEvent_t evA = nullptr, evB = nullptr;
+};
+
+namespace plt {
+void setError(const std::string& s);
+int cudaFail(cudaError_t e, const char* what);
+#define PLT_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return plt::cudaFail(_e, #call); } while (0)
+
+// bvh.cu
+int buildBvh(PltptContext* c, cudaStream_t s);
+int traceClosest(PltptContext* c, uint32_t n, const float* rays, uint32_t* hits, float* hitT, cudaStream_t s);
+int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded, cudaStream_t s);
+// integrator.cu
+int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
+                double* accum, bool solve, cudaStream_t s);
+int copyBounces(PltptContext* c, PltptBounce* host, uint32_t w, uint32_t h);
+}  // namespace plt

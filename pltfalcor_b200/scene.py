@@ -1,0 +1,749 @@
+"""Procedural scene harness: fabricates Falcor-layout scene buffers (the `gScene` inputs of the PLTPT pass).
+
+The reference gets these buffers from Falcor's SceneBuilder / MaterialSystem / LightCollection; neither Falcor nor
+any scene asset is available offline, so the named benchmark scenes are generated here in exactly the same byte
+layouts (include/pltpt.h).  Host-side restatements (each cites the reference):
+  * .spd loader and SpectralProfile builder      — Spectrum.cpp:89-112, SampledSpectrum.h:57-68, SceneBuilder.cpp:911-960
+  * PLT material parameter packing (fp16 slots)  — Rendering/Materials/PLT/*Material.{cpp,slang}
+  * LightCollection triangle list + flux         — LightCollectionShared.slang:76-135, FinalizeIntegration.cs.slang:64-110
+  * EmissivePowerSampler alias table             — EmissivePowerSampler.cpp:86-170
+  * Camera vectors and Halton jitter             — Camera.cpp:111-196, HaltonSamplePattern.cpp:37-67, GBufferBase.cpp:212-228
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+
+from . import layouts as L
+
+f32 = np.float32
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "spd_tables.json")
+
+
+# ----------------------------------------------------------------------------------------------- spectral tables
+def load_spd(path):
+    """PiecewiseLinearSpectrum::fromFile (Spectrum.cpp:89-112): `lambda value` rows, '#' comments, stop at first bad row."""
+    w, v = [], []
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line or line[0] == "#":
+                continue
+            parts = line.split()
+            try:
+                a, b = float(parts[0]), float(parts[1])
+            except (ValueError, IndexError):
+                break
+            w.append(a)
+            v.append(b)
+    if not w:
+        raise RuntimeError(f"Path could not be read '{path}'.")
+    return np.asarray(w, f32), np.asarray(v, f32)
+
+
+_tables_cache = None
+
+
+def bundled_tables():
+    """The small set of reference tables bundled as a fixture (tools/make_golden_tables.py)."""
+    global _tables_cache
+    if _tables_cache is None:
+        with open(_GOLDEN) as f:
+            _tables_cache = json.load(f)
+    return _tables_cache
+
+
+def _pls_eval(w, v, lam):
+    """PiecewiseLinearSpectrum::eval (Spectrum.h:88-106), fp32."""
+    lam = f32(lam)
+    if len(w) == 0 or lam < w[0] or lam > w[-1]:
+        return f32(0)
+    it = int(np.searchsorted(w, lam, side="left"))  # std::lower_bound
+    if it == 0:
+        return f32(v[0])
+    i = it - 1
+    t = f32(lam - w[i]) / f32(w[i + 1] - w[i])
+    return f32(v[i] + f32(v[i + 1] - v[i]) * t)
+
+
+def sampled_spectrum_from_pls(w, v, bin_min=5.0):
+    """SampledSpectrum(PiecewiseLinearSpectrum) (SampledSpectrum.h:57-68) -> (lambdaStart, lambdaEnd, samples)."""
+    w = np.asarray(w, f32)
+    v = np.asarray(v, f32)
+    start, end = f32(w[0]), f32(w[-1])
+    least = f32(end - start)
+    for i in range(1, len(w)):
+        least = min(least, f32(w[i] - w[i - 1]))
+    bin_size = max(f32(bin_min), f32(least / f32(2)))
+    n = max(1, int(f32(f32(end - start) / bin_size) + f32(0.5)))
+    samples = np.zeros(n, f32)
+    for i in range(n):
+        lam = f32(start + f32(f32(end - start) / f32(n - 1)) * f32(i)) if n > 1 else start
+        samples[i] = _pls_eval(w, v, lam)
+    return start, end, samples
+
+
+def _ss_eval(start, end, samples, lam):
+    """SampledSpectrum::eval (SampledSpectrum.h:303-317), fp32."""
+    lam = f32(lam)
+    if lam < start or lam > end:
+        return f32(0)
+    x = f32(f32(lam - start) / f32(end - start)) * f32(len(samples) - 1.0)
+    i = int(math.floor(x))
+    if i + 1 >= len(samples):
+        return f32(samples[-1])
+    wgt = f32(x - f32(i))
+    return f32(samples[i] + f32(samples[i + 1] - samples[i]) * wgt)
+
+
+def _wyman_xyz(lam):
+    def G(x, mu, s1, s2):
+        t = (x - mu) * (s1 if x < mu else s2)
+        return math.exp(-0.5 * t * t)
+    x = 0.362 * G(lam, 442.0, 0.0624, 0.0374) + 1.056 * G(lam, 599.8, 0.0264, 0.0323) - 0.065 * G(lam, 501.1, 0.0490, 0.0382)
+    y = 0.821 * G(lam, 568.8, 0.0213, 0.0247) + 0.286 * G(lam, 530.9, 0.0613, 0.0322)
+    z = 1.217 * G(lam, 437.0, 0.0845, 0.0278) + 0.681 * G(lam, 459.0, 0.0385, 0.0725)
+    return np.array([x, y, z])
+
+
+_D65 = [49.9755, 52.3118, 54.6482, 68.7015, 82.7549, 87.1204, 91.486, 92.4589, 93.4318, 90.057, 86.6823, 95.7736, 104.865, 110.936,
+        117.008, 117.41, 117.812, 116.336, 114.861, 115.392, 115.923, 112.367, 108.811, 109.082, 109.354, 108.578, 107.802, 106.296,
+        104.79, 106.239, 107.689, 106.047, 104.405, 104.225, 104.046, 102.023, 100., 98.1671, 96.3342, 96.0611, 95.788, 92.2368, 88.6856,
+        89.3459, 90.0062, 89.8026, 89.5991, 88.6489, 87.6987, 85.4936, 83.2886, 83.4939, 83.6992, 81.863, 80.0268, 80.1207, 80.2146,
+        81.2462, 82.2778, 80.281, 78.2842, 74.0027, 69.7213, 70.6652, 71.6091, 72.979, 74.349, 67.9765, 61.604]
+_XYZ2RGB = np.array([[3.240969941904522, -1.537383177570094, -0.4986107602930032],
+                     [-0.9692436362808803, 1.875967501507721, 0.04155505740717569],
+                     [0.05563007969699373, -0.2039769588889765, 1.056971514242878]])
+
+
+def _profile_rgb(start, end, samples):
+    """SpectrumUtils::toRGB_D65 (SpectrumUtils.h:78-151): trapezoid sum of XYZ(λ)·D65(λ)·s(λ) -> Rec.709 / Y_D65.
+
+    DEVIATION: the reference integrates against the CIE-1931 1 nm tables (external/include/xyzcurves); this harness
+    uses the Wyman analytic fit the device code uses (SpectrumUtils.slang:43-49).  `rgb` only feeds the per-triangle
+    flux (light-selection pdf), which the estimator divides out again, so images are unaffected in expectation.
+    """
+    n = len(samples)
+    if n < 2:
+        return np.zeros(3, f32)
+    delta = (float(end) - float(start)) / (n - 1.0)
+    acc = np.zeros(3)
+    for q in range(n):
+        lam = min(float(start) + delta * q, float(end))
+        if lam < 380.0 or lam > 720.0:
+            continue
+        d65 = np.interp((lam - 380.0) / 5.0, np.arange(69), _D65)
+        acc += _wyman_xyz(lam) * d65 * float(samples[q]) * delta * (0.5 if q in (0, n - 1) else 1.0)
+    return (_XYZ2RGB @ acc / 10567.0762).astype(f32)
+
+
+def gen_spectral_profile(wavelengths, values, compute_icdf=True, scale=1.0):
+    """genSpectralProfile (SceneBuilder.cpp:911-960) for a `.spd` table; returns a spectral_profile_dtype record."""
+    v = (np.asarray(values, f32) * f32(scale)).astype(f32)
+    start, end, samples = sampled_spectrum_from_pls(wavelengths, v)
+    sp = np.zeros((), L.spectral_profile_dtype)
+    sp["rgb"] = _profile_rgb(start, end, samples)
+    sp["intensity"] = 1.0
+    mn, mx = max(start, f32(380.0)), min(end, f32(720.0))
+    sp["minWavelength"], sp["maxWavelength"] = mn, mx
+    bins = min(128, int(f32(f32(len(samples)) * f32(mx - mn) / f32(end - start)) + f32(0.5)))
+    sp["bins"] = bins
+    if bins == 0:
+        return sp
+    r = f32(1.0) / f32(bins - 1) if bins > 1 else f32(1.0)
+    pdf = np.zeros(128, f32)
+    total = f32(0)
+    for i in range(bins):
+        lam = f32(mn + f32(mx - mn) * f32(f32(i) * r))
+        pdf[i] = _ss_eval(start, end, samples, lam)
+        total = f32(total + pdf[i])
+    if total < f32(1.192092896e-07) or not compute_icdf:
+        sp["pdf"] = pdf
+        return sp
+    for i in range(bins):
+        pdf[i] = f32(pdf[i] / total)
+    sp["intensity"] = total
+    icdf = np.zeros(128, f32)
+    cdfa, cdfb, pdfi = f32(0), f32(pdf[0]), 0
+    for icdfi in range(bins):
+        cdf = f32(f32(icdfi) * r)
+        while cdf >= cdfb and pdfi + 1 < bins:
+            cdfa = cdfb
+            pdfi += 1
+            cdfb = f32(cdfb + pdf[pdfi])
+        l = min(f32(1.0), f32(f32(cdf - cdfa) / f32(cdfb - cdfa)))
+        a = f32(max(1, pdfi)) - f32(1.0)
+        icdf[icdfi] = f32(f32(a + f32(f32(pdfi) - a) * l) * r)
+    sp["pdf"], sp["icdf"] = pdf, icdf
+    return sp
+
+
+# ----------------------------------------------------------------------------------------------- packing helpers
+def _half_bits(x):
+    return np.asarray(x, np.float16).view(np.uint16)
+
+
+def _oct_snorm(n):
+    n = np.asarray(n, np.float64)
+    p = n[:2] / (abs(n[0]) + abs(n[1]) + abs(n[2]))
+    if n[2] < 0:
+        p = np.array([(1 - abs(p[1])) * (1 if p[0] >= 0 else -1), (1 - abs(p[0])) * (1 if p[1] >= 0 else -1)])
+    return p
+
+
+def _pack_snorm16(v):
+    v = min(max(float(v), -1.0), 1.0)
+    return int(math.trunc(v * 32767.0 + (0.5 if v >= 0 else -0.5))) & 0xFFFF
+
+
+def encode_normal_2x16(n):
+    """encodeNormal2x16 (Utils/Math/PackedFormats.slang:50-54)."""
+    o = _oct_snorm(n)
+    return _pack_snorm16(o[0]) | (_pack_snorm16(o[1]) << 16)
+
+
+def pack_vertices(positions, normals, uvs=None, tangents=None):
+    """PackedStaticVertexData::pack (SceneTypes.slang:252-266). tangents: optional (n,4) with w = handedness."""
+    n = len(positions)
+    out = np.zeros(n, L.packed_vertex_dtype)
+    out["position"] = np.asarray(positions, f32)
+    if uvs is not None:
+        out["texCrd"] = np.asarray(uvs, f32)
+    nh = _half_bits(np.asarray(normals, f32)).astype(np.uint32)
+    tw = np.zeros(n, f32) if tangents is None else np.asarray(tangents, f32)[:, 3]
+    twh = _half_bits(tw).astype(np.uint32)
+    out["packed"][:, 0] = nh[:, 0] | (nh[:, 1] << 16)
+    out["packed"][:, 1] = nh[:, 2] | (twh << 16)
+    if tangents is not None:
+        out["packed"][:, 2] = [encode_normal_2x16(t[:3]) for t in np.asarray(tangents, f32)]
+    else:
+        out["packed"][:, 2] = encode_normal_2x16([1.0, 0.0, 0.0])
+    return out
+
+
+def _header(mtype, double_sided=False, emissive=False):
+    x = (mtype & 0xFFFF) | (0xFF << 20) | (int(double_sided) << 28) | (int(emissive) << 30) | (1 << 31)
+    y = int(_half_bits(0.5))  # alpha threshold 0.5, AlphaMode::Opaque (Material.cpp:63-65)
+    return x, y
+
+
+def _blank_material(mtype, double_sided=False):
+    m = np.zeros((), L.material_blob_dtype)
+    m["header"] = _header(mtype, double_sided)
+    m["baseColor"] = [1, 1, 1, 1]
+    m["transmission"] = [1, 1, 1]
+    m["IoR"] = 1.5
+    m["emissionSpectralId"] = m["iorNSpectralId"] = m["iorKSpectralId"] = L.NO_SPECTRAL_PROFILE
+    return m
+
+
+def _set_data1(m, vals=(0, 0, 0, 0), w_bits=None):
+    d = _half_bits(np.asarray(vals, f32)).copy()
+    if w_bits is not None:
+        d[3] = w_bits
+    m["data1"] = d
+
+
+# ----------------------------------------------------------------------------------------------- meshes
+def quad(p0, p1, p2, p3):
+    """Two triangles (p0,p1,p2),(p0,p2,p3); normal = normalize((p1-p0) x (p3-p0))."""
+    P = np.asarray([p0, p1, p2, p3], f32)
+    n = np.cross(P[1] - P[0], P[3] - P[0])
+    n = n / np.linalg.norm(n)
+    return P, np.tile(n, (4, 1)).astype(f32), np.asarray([[0, 0], [1, 0], [1, 1], [0, 1]], f32), np.asarray([0, 1, 2, 0, 2, 3], np.uint32)
+
+
+def box(center, half, rot_y=0.0):
+    c, s = math.cos(rot_y), math.sin(rot_y)
+    R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    hx, hy, hz = half
+    faces = [  # outward-facing quads
+        ([-hx, -hy, hz], [hx, -hy, hz], [hx, hy, hz], [-hx, hy, hz]),
+        ([hx, -hy, -hz], [-hx, -hy, -hz], [-hx, hy, -hz], [hx, hy, -hz]),
+        ([hx, -hy, hz], [hx, -hy, -hz], [hx, hy, -hz], [hx, hy, hz]),
+        ([-hx, -hy, -hz], [-hx, -hy, hz], [-hx, hy, hz], [-hx, hy, -hz]),
+        ([-hx, hy, hz], [hx, hy, hz], [hx, hy, -hz], [-hx, hy, -hz]),
+        ([-hx, -hy, -hz], [hx, -hy, -hz], [hx, -hy, hz], [-hx, -hy, hz]),
+    ]
+    Ps, Ns, UVs, Is = [], [], [], []
+    for f in faces:
+        pts = [R @ np.asarray(p, np.float64) + np.asarray(center, np.float64) for p in f]
+        P, N, UV, I = quad(*pts)
+        Is.append(I + 4 * len(Ps))
+        Ps.append(P)
+        Ns.append(N)
+        UVs.append(UV)
+    return np.concatenate(Ps), np.concatenate(Ns), np.concatenate(UVs), np.concatenate(Is).astype(np.uint32)
+
+
+def uv_sphere(center, radius, n_lat=64, n_lon=128):
+    """Tessellated sphere with smooth normals (config 3 needs >= 20k triangles for MNEE)."""
+    th = np.linspace(0.0, math.pi, n_lat + 1)
+    ph = np.linspace(0.0, 2 * math.pi, n_lon + 1)
+    T, Pm = np.meshgrid(th, ph, indexing="ij")
+    N = np.stack([np.sin(T) * np.cos(Pm), np.cos(T), np.sin(T) * np.sin(Pm)], -1).reshape(-1, 3)
+    P = N * radius + np.asarray(center)
+    UV = np.stack([Pm / (2 * math.pi), T / math.pi], -1).reshape(-1, 2)
+    idx = []
+    for i in range(n_lat):
+        for j in range(n_lon):
+            a = i * (n_lon + 1) + j
+            b = a + n_lon + 1
+            if i != 0:
+                idx += [a, a + 1, b]
+            if i != n_lat - 1:
+                idx += [a + 1, b + 1, b]
+    return P.astype(f32), N.astype(f32), UV.astype(f32), np.asarray(idx, np.uint32)
+
+
+def grid_plane(y, x0, x1, z0, z1, nx, nz, height_fn=None):
+    xs = np.linspace(x0, x1, nx + 1)
+    zs = np.linspace(z0, z1, nz + 1)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
+    Y = np.full_like(X, y) if height_fn is None else height_fn(X, Z)
+    P = np.stack([X, Y, Z], -1).reshape(-1, 3)
+    if height_fn is None:
+        N = np.tile([0.0, 1.0, 0.0], (len(P), 1))
+    else:
+        dYdx = np.gradient(Y, xs, axis=0)
+        dYdz = np.gradient(Y, zs, axis=1)
+        N = np.stack([-dYdx, np.ones_like(Y), -dYdz], -1).reshape(-1, 3)
+        N /= np.linalg.norm(N, axis=1, keepdims=True)
+    UV = np.stack([(X - x0) / (x1 - x0), (Z - z0) / (z1 - z0)], -1).reshape(-1, 2)
+    i, j = np.meshgrid(np.arange(nx), np.arange(nz), indexing="ij")
+    a = (i * (nz + 1) + j).reshape(-1)
+    b = a + nz + 1
+    idx = np.stack([a, a + 1, b + 1, a, b + 1, b], -1).reshape(-1)
+    return P.astype(f32), N.astype(f32), UV.astype(f32), idx.astype(np.uint32)
+
+
+# ----------------------------------------------------------------------------------------------- scene builder
+class SceneBuffers:
+    """Finalised Falcor-layout buffers (numpy, host) plus the PltptSceneDesc that points at them."""
+
+    def __init__(self, arrays, scalars):
+        self.arrays = arrays
+        self.scalars = scalars
+        self._keep = None
+
+    def desc(self, arrays=None, device=False) -> L.PltptSceneDesc:
+        a = arrays or self.arrays
+
+        def ptr(name):
+            x = a.get(name)
+            if x is None or (hasattr(x, "size") and x.size == 0) or (hasattr(x, "numel") and x.numel() == 0):
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+
+        s = self.scalars
+        d = L.PltptSceneDesc()
+        d.vertices, d.vertexCount = ptr("vertices"), s["vertexCount"]
+        d.indexData, d.indexDataBytes = ptr("indexData"), s["indexDataBytes"]
+        d.geometryInstances, d.instanceCount = ptr("geometryInstances"), s["instanceCount"]
+        d.meshes, d.meshCount = ptr("meshes"), s["meshCount"]
+        d.worldMatrices, d.inverseTransposeWorldMatrices, d.matrixCount = ptr("worldMatrices"), ptr("inverseTransposeWorldMatrices"), s["matrixCount"]
+        d.materialData, d.materialCount = ptr("materialData"), s["materialCount"]
+        d.spectralProfiles, d.profileCount = ptr("spectralProfiles"), s["profileCount"]
+        d.lights, d.lightCount = ptr("lights"), s["lightCount"]
+        d.emissiveTriangles, d.emissiveTriangleCount = ptr("emissiveTriangles"), s["emissiveTriangleCount"]
+        d.emissiveFlux = ptr("emissiveFlux")
+        d.activeTriangles, d.activeTriangleCount = ptr("activeTriangles"), s["emissiveTriangleCount"]
+        d.perMeshInstanceOffset = ptr("perMeshInstanceOffset")
+        d.triangleAliasTable, d.invWeightsSum = ptr("triangleAliasTable"), s["invWeightsSum"]
+        d.hitInfoTypeBits, d.hitInfoInstanceIDBits, d.hitInfoPrimitiveIndexBits = 3, s["instanceIDBits"], s["primitiveIndexBits"]
+        d.pointersAreDevice = 1 if device else 0
+        return d
+
+    def to_device(self, torch, device="cuda:0"):
+        """Uploads every buffer as a uint8 torch tensor; returns (tensors, desc) — keep `tensors` alive while in use."""
+        t = {}
+        for k, v in self.arrays.items():
+            if v is None or v.size == 0:
+                continue
+            t[k] = torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy()).to(device)
+        return t, self.desc(t, device=True)
+
+    @property
+    def triangle_count(self):
+        return self.scalars["triangleCount"]
+
+
+def _alloc_bits(count):
+    return 0 if count <= 1 else int(count - 1).bit_length()  # HitInfo.cpp allocateBits
+
+
+def generate_alias_table(weights):
+    """EmissivePowerSampler::generateAliasTable (EmissivePowerSampler.cpp:86-170) without the final random
+    permutation (the table is *a* valid alias table either way; parity is on the induced pdf flux/sum)."""
+    w = np.asarray(weights, f32).copy()
+    N = len(w)
+    total = float(np.sum(w.astype(np.float64)))
+    w = (w * f32(N / f32(total))).astype(f32)
+    perm = sorted(range(N), key=lambda i: w[i])
+    thresholds = np.zeros(N, f32)
+    redirect = np.zeros(N, np.uint32)
+    head, tail = 0, N - 1
+    if N == 1:
+        thresholds[0], redirect[0] = 1.0, 0
+    while head != tail:
+        i, j = perm[head], perm[tail]
+        thresholds[i] = w[i]
+        redirect[i] = j
+        w[j] = f32(w[j] - f32(f32(1.0) - w[i]))
+        if head == tail - 1:
+            thresholds[j] = 1.0
+            redirect[j] = j
+            break
+        elif w[j] < 1.0:
+            perm[head], perm[tail] = perm[tail], perm[head]
+            tail -= 1
+        else:
+            head += 1
+    table = np.zeros((N, 2), np.uint32)
+    prob = _half_bits(thresholds).astype(np.uint32) << 16
+    lo_x = redirect & 0xFFFFFF
+    lo_y = np.arange(N, dtype=np.uint32) & 0xFFFFFF
+    table[:, 0] = prob | ((lo_x >> 8) & 0xFFFF)
+    table[:, 1] = ((lo_x & 0xFF) << 24) | lo_y
+    return table, f32(total)
+
+
+class SceneBuilder:
+    def __init__(self):
+        self.meshes = []  # (P, N, UV, I, material, matrix)
+        self.materials = []
+        self.profiles = []
+        self.lights = []
+
+    # -- spectral profiles (SceneBuilder::addSpectralProfile*, SceneBuilder.cpp:962-999)
+    def add_profile(self, wavelengths, values, compute_icdf=True, scale=1.0):
+        self.profiles.append(gen_spectral_profile(wavelengths, values, compute_icdf, scale))
+        return len(self.profiles) - 1
+
+    def add_ior_profiles(self, name):
+        """addSpectralProfileFromMaterial: (n, k) profile ids, no icdf."""
+        t = bundled_tables()["ior"][name]
+        return (self.add_profile(t["eta"]["wavelengths"], t["eta"]["values"], False),
+                self.add_profile(t["k"]["wavelengths"], t["k"]["values"], False))
+
+    def add_emission_profile(self, name, scale=1.0):
+        t = bundled_tables()["emission"][name]
+        return self.add_profile(t["wavelengths"], t["values"], True, scale)
+
+    # -- materials: slot assignments follow the *Material.slang unpackers (see oracle/plt_bsdf.h MaterialInstance)
+    def _add(self, m):
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def add_diffuse(self, base_color, emission_profile=None, double_sided=False):
+        m = _blank_material(L.MATERIAL_DIFFUSE, double_sided)
+        m["baseColor"] = list(base_color) + [1.0]
+        if emission_profile is not None:
+            m["emissionSpectralId"] = emission_profile
+            m["header"] = _header(L.MATERIAL_DIFFUSE, double_sided, True)
+        return self._add(m)
+
+    def add_conductor(self, ior_profiles, roughness, gamma=3.0, specular=(1, 1, 1), ext_eta=1.0):
+        m = _blank_material(L.MATERIAL_CONDUCTOR)
+        m["baseColor"] = list(specular) + [1.0]
+        m["specular"] = [gamma, roughness, 1.0, 1.0]
+        m["IoR"] = ext_eta
+        m["iorNSpectralId"], m["iorKSpectralId"] = ior_profiles
+        return self._add(m)
+
+    def add_dielectric(self, ior, roughness, ext_eta=1.0, dispersion_b=0.0, specular=(1, 1, 1), transmission=(1, 1, 1)):
+        m = _blank_material(L.MATERIAL_DIELECTRIC)  # single-sided: N must not flip inside the medium (MitsubaImporter.cpp:330)
+        m["baseColor"] = list(specular) + [1.0]
+        m["specular"] = [dispersion_b, roughness, 0.0, ext_eta]
+        m["transmission"] = transmission
+        m["IoR"] = ior
+        return self._add(m)
+
+    def add_opaque_dielectric(self, base_color, roughness):
+        m = _blank_material(L.MATERIAL_OPAQUE_DIELECTRIC)
+        m["baseColor"] = list(base_color) + [1.0]
+        m["specular"] = [0.0, roughness, 0.0, 0.0]
+        return self._add(m)
+
+    def add_thin_dielectric(self, ior, tau_mm, birefringence=0.0, optic_axis_xy=(0.15, 0.04), birefringence_scale=1.0):
+        m = _blank_material(L.MATERIAL_THIN_DIELECTRIC)
+        m["baseColor"] = [birefringence, optic_axis_xy[0], optic_axis_xy[1], 1.0]
+        m["specular"] = [birefringence_scale, 0.0, 0.0, tau_mm]
+        m["IoR"] = ior
+        return self._add(m)
+
+    def add_coated_conductor(self, ior_profiles, roughness, tau_um, coat_ior, specular=(1, 1, 1), ext_eta=1.0):
+        m = _blank_material(L.MATERIAL_COATED_CONDUCTOR)
+        m["baseColor"] = list(specular) + [1.0]
+        m["specular"] = [0.0, roughness, 1.0, 0.0]
+        _set_data1(m, (tau_um, 0, 0, coat_ior))
+        m["IoR"] = ext_eta
+        m["iorNSpectralId"], m["iorKSpectralId"] = ior_profiles
+        return self._add(m)
+
+    def add_coated_opaque_dielectric(self, base_color, roughness, tau_um, coat_ior, ext_eta=1.0):
+        m = _blank_material(L.MATERIAL_COATED_OPAQUE_DIELECTRIC)
+        m["baseColor"] = list(base_color) + [1.0]
+        m["specular"] = [0.0, roughness, 1.0, 0.0]
+        _set_data1(m, (tau_um, 0, 0, coat_ior))
+        m["IoR"] = ext_eta
+        return self._add(m)
+
+    def _grating(self, m, pitch_um, direction, q, q_scale, power_mult, roughness, gtype, lobes):
+        m["specular"] = [q_scale, power_mult, 0.0, 0.0]
+        _set_data1(m, (pitch_um[0], pitch_um[1], direction, 0), w_bits=((gtype & 0xFF) << 8) | (lobes & 0xFF))
+        m["data2"] = [q, roughness, 0.0, 0.0]
+
+    def add_grated_conductor(self, ior_profiles, pitch_um, q, roughness=0.0, direction=0.0, q_scale=1.0, power_mult=1.0, gtype=0, lobes=3, specular=(1, 1, 1), ext_eta=1.0):
+        m = _blank_material(L.MATERIAL_GRATED_CONDUCTOR)
+        m["baseColor"] = list(specular) + [1.0]
+        self._grating(m, pitch_um, direction, q, q_scale, power_mult, roughness, gtype, lobes)
+        m["IoR"] = ext_eta
+        m["iorNSpectralId"], m["iorKSpectralId"] = ior_profiles
+        return self._add(m)
+
+    def add_grated_opaque_dielectric(self, base_color, pitch_um, q, roughness=0.0, direction=0.0, q_scale=1.0, power_mult=1.0, gtype=0, lobes=3):
+        m = _blank_material(L.MATERIAL_GRATED_OPAQUE_DIELECTRIC)
+        m["baseColor"] = list(base_color) + [1.0]
+        self._grating(m, pitch_um, direction, q, q_scale, power_mult, roughness, gtype, lobes)
+        return self._add(m)
+
+    def add_multilayered_stack(self, base_color, layers, thickness_um=(0.1, 0.15), iors=(1.38, 2.3), ext_eta=1.0):
+        m = _blank_material(L.MATERIAL_MULTILAYERED_STACK)
+        m["baseColor"] = list(base_color) + [1.0]
+        _set_data1(m, (thickness_um[0], thickness_um[1], 0, 0), w_bits=layers & 0xFFFF)
+        m["data2"] = [iors[0], iors[1], 0.0, 0.0]
+        m["IoR"] = ext_eta
+        return self._add(m)
+
+    # -- geometry
+    def add_mesh(self, mesh, material, matrix=None):
+        P, N, UV, I = mesh
+        self.meshes.append((np.asarray(P, f32), np.asarray(N, f32), np.asarray(UV, f32), np.asarray(I, np.uint32),
+                            material, np.eye(4, dtype=f32) if matrix is None else np.asarray(matrix, f32)))
+        return len(self.meshes) - 1
+
+    # -- analytic lights (Light.cpp:366-401 for areas; LightData.slang:49-72)
+    def add_rect_light(self, profile, center, normal, half_x, half_y):
+        n = np.asarray(normal, np.float64) / np.linalg.norm(normal)
+        t = np.cross([0, 1, 0] if abs(n[1]) < 0.9 else [1, 0, 0], n)
+        t /= np.linalg.norm(t)
+        b = np.cross(n, t)
+        M = np.eye(4)
+        M[:3, 0], M[:3, 1], M[:3, 2], M[:3, 3] = t * half_x, b * half_y, n, center
+        l = np.zeros((), L.light_data_dtype)
+        l["posW"], l["type"], l["dirW"] = center, 3, n
+        l["openingAngle"], l["cosOpeningAngle"], l["cosSubtendedAngle"] = math.pi, -1.0, 0.9999893
+        l["intensitySpectrumId"] = profile
+        l["surfaceArea"] = 4.0 * half_x * half_y
+        l["transMat"] = M.astype(f32).reshape(-1)
+        l["transMatIT"] = np.linalg.inv(M).T.astype(f32).reshape(-1)
+        self.lights.append(l)
+
+    def add_distant_light(self, profile, direction, half_angle):
+        d = np.asarray(direction, np.float64) / np.linalg.norm(direction)
+        z = -d  # cone axis points towards the light
+        t = np.cross([0, 1, 0] if abs(z[1]) < 0.9 else [1, 0, 0], z)
+        t /= np.linalg.norm(t)
+        b = np.cross(z, t)
+        M = np.eye(4)
+        M[:3, 0], M[:3, 1], M[:3, 2] = t, b, z
+        l = np.zeros((), L.light_data_dtype)
+        l["type"], l["dirW"] = 2, d
+        l["openingAngle"], l["cosOpeningAngle"], l["cosSubtendedAngle"] = math.pi, -1.0, math.cos(half_angle)
+        l["intensitySpectrumId"] = profile
+        l["transMat"] = M.astype(f32).reshape(-1)
+        l["transMatIT"] = np.linalg.inv(M).T.astype(f32).reshape(-1)
+        self.lights.append(l)
+
+    def finalize(self) -> SceneBuffers:
+        verts, idx, insts, mds, mats = [], [], [], [], []
+        vb, ib, tri_total, max_prims = 0, 0, 0, 0
+        for i, (P, N, UV, I, material, M) in enumerate(self.meshes):
+            verts.append(pack_vertices(P, N, UV))
+            idx.append(I)
+            md = np.zeros((), L.mesh_desc_dtype)
+            md["vbOffset"], md["ibOffset"], md["vertexCount"], md["indexCount"], md["materialID"] = vb, ib, len(P), len(I), material
+            mds.append(md)
+            gi = np.zeros((), L.geometry_instance_dtype)
+            gi["flags"] = 1 << 29  # GeometryType::TriangleMesh in the top 3 bits, 32-bit indices, CCW front faces
+            gi["globalMatrixID"], gi["materialID"], gi["geometryID"], gi["vbOffset"], gi["ibOffset"] = i, material, i, vb, ib
+            gi["instanceIndex"], gi["geometryIndex"] = i, 0
+            insts.append(gi)
+            mats.append(M)
+            vb += len(P)
+            ib += len(I)
+            tri_total += len(I) // 3
+            max_prims = max(max_prims, len(I) // 3)
+        world = np.stack(mats).astype(f32) if mats else np.zeros((0, 4, 4), f32)
+        invT = np.stack([np.linalg.inv(m.astype(np.float64)).T for m in mats]).astype(f32) if mats else world
+        materials = np.stack(self.materials) if self.materials else np.zeros(0, L.material_blob_dtype)
+        profiles = np.stack(self.profiles) if self.profiles else np.zeros(0, L.spectral_profile_dtype)
+
+        # LightCollection (BuildTriangleList.cs.slang, FinalizeIntegration.cs.slang:64-110)
+        etris, flux, offsets = [], [], np.full(len(self.meshes), 0xFFFFFFFF, np.uint32)
+        for i, (P, N, UV, I, material, M) in enumerate(self.meshes):
+            if materials[material]["emissionSpectralId"] == L.NO_SPECTRAL_PROFILE:
+                continue
+            offsets[i] = len(etris)
+            Pw = (P.astype(np.float64) @ M[:3, :3].T.astype(np.float64) + M[:3, 3]).astype(f32)
+            rgb = np.maximum(profiles[materials[material]["emissionSpectralId"]]["rgb"], 0)
+            for t in range(len(I) // 3):
+                a, b, c = Pw[I[3 * t]], Pw[I[3 * t + 1]], Pw[I[3 * t + 2]]
+                n = np.cross((b - a).astype(f32), (c - a).astype(f32)).astype(f32)
+                area = f32(0.5) * f32(np.linalg.norm(n))
+                n = n / np.linalg.norm(n)
+                e = np.zeros((), L.emissive_triangle_dtype)
+                for k, v in enumerate((I[3 * t], I[3 * t + 1], I[3 * t + 2])):
+                    e["posAndTexCoords"][k, :3] = Pw[v]
+                    uvb = _half_bits(UV[v]).astype(np.uint32)
+                    e["posAndTexCoords"][k, 3] = np.array([uvb[0] | (uvb[1] << 16)], np.uint32).view(f32)[0]
+                e["normal"] = encode_normal_2x16(n)
+                e["area"] = np.array([area], f32).view(np.uint32)[0]
+                e["materialID"], e["lightIdx"] = material, 0
+                etris.append(e)
+                fl = np.zeros((), L.emissive_flux_dtype)
+                lum = f32(np.dot(rgb, np.array([0.2126, 0.7152, 0.0722], f32)))
+                fl["flux"] = f32(lum * area * f32(math.pi))
+                fl["averageRadiance"] = rgb
+                flux.append(fl)
+        etris = np.stack(etris) if etris else np.zeros(0, L.emissive_triangle_dtype)
+        flux = np.stack(flux) if flux else np.zeros(0, L.emissive_flux_dtype)
+        if len(etris):
+            alias, wsum = generate_alias_table(flux["flux"])
+            inv_sum = float(f32(1.0) / f32(wsum))
+        else:
+            alias, inv_sum = np.zeros((0, 2), np.uint32), 0.0
+        arrays = dict(
+            vertices=np.concatenate(verts) if verts else np.zeros(0, L.packed_vertex_dtype),
+            indexData=np.concatenate(idx).astype(np.uint32) if idx else np.zeros(0, np.uint32),
+            geometryInstances=np.stack(insts) if insts else np.zeros(0, L.geometry_instance_dtype),
+            meshes=np.stack(mds) if mds else np.zeros(0, L.mesh_desc_dtype),
+            worldMatrices=np.ascontiguousarray(world), inverseTransposeWorldMatrices=np.ascontiguousarray(invT),
+            materialData=materials, spectralProfiles=profiles,
+            lights=np.stack(self.lights) if self.lights else np.zeros(0, L.light_data_dtype),
+            emissiveTriangles=etris, emissiveFlux=flux, activeTriangles=np.arange(len(etris), dtype=np.uint32),
+            perMeshInstanceOffset=offsets, triangleAliasTable=alias,
+        )
+        scalars = dict(
+            vertexCount=vb, indexDataBytes=ib * 4, instanceCount=len(insts), meshCount=len(mds), matrixCount=len(mats),
+            materialCount=len(materials), profileCount=len(profiles), lightCount=len(self.lights),
+            emissiveTriangleCount=len(etris), invWeightsSum=inv_sum, triangleCount=tri_total,
+            instanceIDBits=_alloc_bits(len(insts)), primitiveIndexBits=_alloc_bits(max_prims),
+        )
+        return SceneBuffers(arrays, scalars)
+
+
+# ----------------------------------------------------------------------------------------------- camera
+def halton(index, base):
+    result, factor = f32(0.0), f32(1.0)
+    while index > 0:
+        factor = f32(factor / f32(base))
+        result = f32(result + factor * f32(index % base))
+        index //= base
+    return result
+
+
+def halton_jitter(frame, width, height, sample_count=16):
+    """Camera jitter GBufferRT sets for frame `frame` (HaltonSamplePattern.cpp:59-67 * 1/frameDim)."""
+    i = frame % sample_count if sample_count else frame
+    v = np.array([halton(i, 2), halton(i, 3)], f32)
+    v = (v + f32(0.5)) - np.floor(v + f32(0.5)) - f32(0.5)
+    return float(f32(v[0]) / f32(width)), float(f32(v[1]) / f32(height))
+
+
+def make_camera(pos, target, up=(0, 1, 0), focal_length=21.0, frame_height=24.0, aspect=16.0 / 9.0, focal_distance=10000.0,
+                jitter=(0.0, 0.0), polarizer=0.0, polarizer_theta=0.0) -> L.PltptCameraData:
+    """Camera::calculateCameraParameters (Camera.cpp:111-196): cameraU/V/W, view matrix (glm::lookAt, RH)."""
+    cam = L.PltptCameraData()
+    pos, target, up = (np.asarray(v, np.float64) for v in (pos, target, up))
+    fovY = 2.0 * math.atan(0.5 * frame_height / focal_length)
+    W = (target - pos) / np.linalg.norm(target - pos) * focal_distance
+    U = np.cross(W, up)
+    U /= np.linalg.norm(U)
+    V = np.cross(U, W)
+    V /= np.linalg.norm(V)
+    U *= focal_distance * math.tan(fovY * 0.5) * aspect
+    V *= focal_distance * math.tan(fovY * 0.5)
+    f = (target - pos) / np.linalg.norm(target - pos)
+    s = np.cross(f, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    view = np.eye(4)
+    view[0, :3], view[1, :3], view[2, :3] = s, u, -f
+    view[0, 3], view[1, 3], view[2, 3] = -s @ pos, -u @ pos, f @ pos
+    for i, x in enumerate(view.astype(f32).reshape(-1)):
+        cam.viewMat[i] = x
+        cam.prevViewMat[i] = x
+    for name, v in (("posW", pos), ("prevPosW", pos), ("up", up), ("target", target), ("cameraU", U), ("cameraV", V), ("cameraW", W)):
+        for i in range(3):
+            getattr(cam, name)[i] = float(f32(v[i]))
+    cam.focalLength, cam.aspectRatio, cam.nearZ, cam.farZ = focal_length, aspect, 0.1, 1000.0
+    cam.jitterX, cam.jitterY = jitter
+    cam.frameHeight, cam.frameWidth, cam.focalDistance = frame_height, frame_height * aspect, focal_distance
+    cam.shutterSpeed, cam.ISOSpeed = 0.004, 100.0
+    cam.polarizer, cam.polarizerTheta = polarizer, polarizer_theta
+    return cam
+
+
+def with_jitter(cam: L.PltptCameraData, frame, width, height) -> L.PltptCameraData:
+    c = L.PltptCameraData.from_buffer_copy(bytes(cam))
+    c.jitterX, c.jitterY = halton_jitter(frame, width, height)
+    return c
+
+
+# ----------------------------------------------------------------------------------------------- named scenes
+LAMP = "2475_INC_A19_domestic-use_softwhite-color_Rona-brand_100W_130V_2450K"
+
+
+def cornell_box(aspect=16.0 / 9.0, dielectric_roughness=0.1, conductor_roughness=0.3, emission_scale=1.0):
+    """BASELINE config 2: Cornell box, PLTDiffuse walls, rough Dielectric box, rough Au Conductor box, ceiling area
+    emitter with an LSPDD spectral profile."""
+    b = SceneBuilder()
+    au = b.add_ior_profiles("Au")
+    lamp = b.add_emission_profile(LAMP, emission_scale)
+    white = b.add_diffuse((0.73, 0.73, 0.73))
+    red = b.add_diffuse((0.65, 0.05, 0.05))
+    green = b.add_diffuse((0.12, 0.45, 0.15))
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    glass = b.add_dielectric(ior=1.5, roughness=dielectric_roughness)
+    gold = b.add_conductor(au, roughness=conductor_roughness, gamma=3.0)
+    # room: x in [-X,X] (16:9-shaped so that every pixel sees the interior), y in [0,2], z in [-1,1]; camera looks down -z
+    X = 1.6
+    b.add_mesh(quad([-X, 0, 1], [X, 0, 1], [X, 0, -1], [-X, 0, -1]), white)       # floor (normal +y)
+    b.add_mesh(quad([-X, 2, -1], [X, 2, -1], [X, 2, 1], [-X, 2, 1]), white)       # ceiling (normal -y)
+    b.add_mesh(quad([-X, 0, -1], [X, 0, -1], [X, 2, -1], [-X, 2, -1]), white)     # back wall (normal +z)
+    b.add_mesh(quad([-X, 0, 1], [-X, 0, -1], [-X, 2, -1], [-X, 2, 1]), red)       # left wall (normal +x)
+    b.add_mesh(quad([X, 0, -1], [X, 0, 1], [X, 2, 1], [X, 2, -1]), green)         # right wall (normal -x)
+    b.add_mesh(quad([-0.3, 1.995, -0.3], [0.3, 1.995, -0.3], [0.3, 1.995, 0.3], [-0.3, 1.995, 0.3]), light)  # emitter (normal -y)
+    b.add_mesh(box([-0.6, 0.6, -0.3], [0.3, 0.6, 0.3], rot_y=0.3), gold)
+    b.add_mesh(box([0.6, 0.3, 0.3], [0.3, 0.3, 0.3], rot_y=-0.25), glass)
+    cam = make_camera([0.0, 1.0, 3.5], [0.0, 1.0, 0.0], focal_length=35.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def sweep_scene(dielectric_roughness=0.1, conductor_roughness=0.3):
+    """BASELINE config 1 materials: 0 = rough Dielectric (IoR 1.5), 1 = rough Au Conductor (γ = 3); plus one of each
+    remaining PLT material for the wider BSDF parity tests."""
+    b = SceneBuilder()
+    au, cu = b.add_ior_profiles("Au"), b.add_ior_profiles("Cu")
+    lamp = b.add_emission_profile(LAMP)
+    ids = dict(
+        dielectric=b.add_dielectric(1.5, dielectric_roughness),
+        conductor=b.add_conductor(au, conductor_roughness, 3.0),
+        diffuse=b.add_diffuse((0.6, 0.4, 0.2)),
+        opaque=b.add_opaque_dielectric((0.3, 0.5, 0.7), 0.05),
+        thin=b.add_thin_dielectric(1.5, 0.3, birefringence=0.1),
+        coated_conductor=b.add_coated_conductor(cu, 0.05, tau_um=3.0, coat_ior=1.5),
+        coated_opaque=b.add_coated_opaque_dielectric((0.7, 0.2, 0.2), 0.05, tau_um=3.0, coat_ior=1.5),
+        grated_conductor=b.add_grated_conductor(au, (3.0, 0.0), q=0.5 * 0.3, lobes=3),
+        grated_opaque=b.add_grated_opaque_dielectric((0.5, 0.5, 0.5), (2.0, 2.0), q=0.2, gtype=1, lobes=4),
+        stack=b.add_multilayered_stack((1, 1, 1), layers=6),
+        smooth_dielectric=b.add_dielectric(1.5, 0.0, dispersion_b=0.01),
+        smooth_conductor=b.add_conductor(au, 0.0),
+        emitter=b.add_diffuse((0, 0, 0), emission_profile=lamp),
+    )
+    b.add_mesh(quad([-1, 0, 1], [1, 0, 1], [1, 0, -1], [-1, 0, -1]), ids["diffuse"])
+    return b.finalize(), ids
