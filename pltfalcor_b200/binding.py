@@ -1,0 +1,145 @@
+"""ctypes binding of libpltpt.so (include/pltpt.h).  Used by tests/, bench.py and __graft_entry__: the product is the
+C-ABI library, this file only moves pointers.  There is no fallback: a missing library or a failing call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layouts as L
+from .build import LIB
+
+_lib = None
+
+# every symbol include/pltpt.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "pltpt_default_options", "pltpt_create", "pltpt_destroy", "pltpt_last_error", "pltpt_version", "pltpt_set_options", "pltpt_set_scene",
+    "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
+    "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats",
+]
+
+
+class PltptError(RuntimeError):
+    """Non-zero PltptStatus (the Falcor shell throws Falcor::RuntimeError for the same codes, PLTPT.cpp:409)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"pltpt status {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"{LIB} is missing: build it with `python -m pltfalcor_b200.build` (there is no CPU fallback for the PLTPT path)")
+        _lib = C.CDLL(LIB)
+        _lib.pltpt_last_error.restype = C.c_char_p
+        _lib.pltpt_version.restype = C.c_char_p
+        vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
+        _lib.pltpt_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        _lib.pltpt_destroy.argtypes = [vp]
+        _lib.pltpt_set_options.argtypes = [vp, vp]
+        _lib.pltpt_set_scene.argtypes = [vp, vp]
+        _lib.pltpt_render_frame.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp]
+        _lib.pltpt_render_accumulate.argtypes = [vp, u32, u32, u32, vp, u32, u32, vp, vp]
+        _lib.pltpt_render_frame_host.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
+        _lib.pltpt_sample_stage_host.argtypes = [vp, u32, vp, u32, u32, vp]
+        _lib.pltpt_trace_closest.argtypes = [vp, u32, vp, vp, vp, vp]
+        _lib.pltpt_trace_any.argtypes = [vp, u32, vp, vp, vp]
+        _lib.pltpt_bsdf_eval_mueller.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]
+        _lib.pltpt_bsdf_sample.argtypes = [vp, u32, u32, u32, vp, vp, u32, vp, vp]
+        _lib.pltpt_get_stats.argtypes = [vp, vp]
+        _lib.pltpt_reset_stats.argtypes = [vp]
+    return _lib
+
+
+def _check(code):
+    if code != 0:
+        raise PltptError(code, lib().pltpt_last_error().decode())
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+class Pltpt:
+    """One PltptHandle. `options` are the 24 PLTPT pass properties (PLTPT.cpp:102-136)."""
+
+    def __init__(self, device=0, **options):
+        self.h = C.c_void_p()
+        self.options = L.make_options(**options)
+        _check(lib().pltpt_create(C.byref(self.options), int(device), C.byref(self.h)))
+        self.device = device
+        self._scene_keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pltpt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, **options):
+        vals = {k: getattr(self.options, k) for k, _ in L.PltptOptions._fields_}
+        vals.update(options)
+        self.options = L.make_options(**vals)
+        _check(lib().pltpt_set_options(self.h, C.byref(self.options)))
+
+    def set_scene(self, buffers, device_tensors=None):
+        """buffers: scene.SceneBuffers (host numpy). If device_tensors = buffers.to_device(torch) is given the
+        interop path (device pointers) is exercised instead."""
+        desc = device_tensors[1] if device_tensors else buffers.desc()
+        self._scene_keep = (buffers, device_tensors, desc)
+        _check(lib().pltpt_set_scene(self.h, C.byref(desc)))
+
+    def stats(self):
+        s = L.PltptStats()
+        _check(lib().pltpt_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.PltptStats._fields_}
+
+    def reset_stats(self):
+        _check(lib().pltpt_reset_stats(self.h))
+
+    # ---- rendering -------------------------------------------------------------------------------------------
+    def render_frame_host(self, cam, frame, width, height, want_guides=True):
+        color = np.zeros((height, width, 4), np.float32)
+        albedo = np.zeros((height, width, 4), np.float32) if want_guides else None
+        normal = np.zeros((height, width, 4), np.float32) if want_guides else None
+        _check(lib().pltpt_render_frame_host(self.h, frame, C.byref(cam), width, height, _hp(color), _hp(albedo), _hp(normal)))
+        return dict(color=color, albedo=albedo, normal=normal)
+
+    def sample_stage_host(self, cam, frame, width, height):
+        bounces = np.zeros((height, width, self.options.maxBounces + 1), L.bounce_dtype)
+        _check(lib().pltpt_sample_stage_host(self.h, frame, C.byref(cam), width, height, _hp(bounces)))
+        return bounces
+
+    def render_frame(self, cam, frame, width, height, color, albedo=None, normal=None, stream=None):
+        """color/albedo/normal: torch float32 CUDA tensors of width*height*4."""
+        _check(lib().pltpt_render_frame(self.h, frame, C.byref(cam), width, height, _dp(color), _dp(albedo), _dp(normal), stream))
+
+    def render_accumulate(self, cam, first_frame, frame_step, frame_count, width, height, accum, stream=None):
+        """accum: torch float64 CUDA tensor of width*height*4 (RGB sums + sample count)."""
+        _check(lib().pltpt_render_accumulate(self.h, first_frame, frame_step, frame_count, C.byref(cam), width, height, _dp(accum), stream))
+
+    # ---- ray queries ------------------------------------------------------------------------------------------
+    def trace_closest(self, rays, hits, hit_t=None, stream=None):
+        _check(lib().pltpt_trace_closest(self.h, rays.shape[0], _dp(rays), _dp(hits), _dp(hit_t), stream))
+
+    def trace_any(self, rays, occluded, stream=None):
+        _check(lib().pltpt_trace_any(self.h, rays.shape[0], _dp(rays), _dp(occluded), stream))
+
+    # ---- BSDF sweeps ------------------------------------------------------------------------------------------
+    def bsdf_eval_mueller(self, material_id, lobe, wi, wo, hero, out, stream=None):
+        """wi, wo: (n,3); hero: (groups,n); out: (n,groups,HWSS,4,4) — torch CUDA float32 tensors."""
+        groups, n = hero.shape
+        _check(lib().pltpt_bsdf_eval_mueller(self.h, material_id, lobe, n, groups, _dp(wi), _dp(wo), _dp(hero), _dp(out), stream))
+
+    def bsdf_sample(self, material_id, lobe_mask, wi, wavelengths, seed, out, stream=None):
+        _check(lib().pltpt_bsdf_sample(self.h, material_id, lobe_mask, wi.shape[0], _dp(wi), _dp(wavelengths), seed, _dp(out), stream))

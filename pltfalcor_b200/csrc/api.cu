@@ -73,6 +73,7 @@ extern "C" int pltpt_set_options(PltptHandle h, const PltptOptions* opts) {
 }
 extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
     if (!h || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int r = syncFrameStats(h)) return r;
     *out = h->stats;
     return PLTPT_OK;
 }

@@ -1,0 +1,403 @@
+// bvh.cu — GPU BVH builder (replaces the driver BLAS/TLAS build, reference Source/Falcor/Scene/Scene.cpp:3092-3760)
+// and the standalone ray-query kernels behind pltpt_trace_closest / pltpt_trace_any (replace TraceRay,
+// pltpt_sample.rt.slang:174-183, ShadowRays.slangh:68-77,115-124).
+//
+// Build pipeline (all on the device; B200 has no RT cores so there is no driver structure to lean on):
+//   1. k_world_tris    : instance transform -> world-space triangles with the contract's rounding, AABBs, scene bounds
+//   2. k_morton        : 63-bit Morton code of the AABB centre; CUB radix sort (key, triangle)
+//   3. k_radix_tree    : Karras 2012 binary radix tree over the sorted codes (one thread per internal node)
+//   4. k_fit           : bottom-up AABB fit with per-node arrival counters
+//   5. k_collapse      : level-synchronous collapse of the binary tree into 8-wide nodes. Children are opened greedily
+//                        by surface area (the SAH term: expected traversal cost ~ area), subtrees of <= 3 triangles
+//                        become leaf slots; child boxes are quantised to 8 bits on a per-node power-of-two grid
+//                        (80 B nodes, Ylitie et al. 2017) with conservative rounding verified in the kernel.
+// Flat world-space BVH: static instances are pre-transformed exactly like Falcor does for static meshes
+// (Scene.cpp:2712-2717), so one traversal handles BLAS+TLAS.
+#include "bvh_traverse.cuh"
+#include <cub/cub.cuh>
+#include <cfloat>
+
+namespace plt {
+namespace {
+
+constexpr uint32_t kMaxLeafTris = 3;
+constexpr uint32_t kLeafBit = 0x80000000u;
+
+// order-preserving float <-> uint mapping for atomicMin/Max
+PLT_D uint32_t floatFlip(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+PLT_D float floatUnflip(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+PLT_D void fetchIndices(const DevScene& sc, uint32_t instanceID, uint32_t tri, uint32_t idx[3]) {  // Scene.slang getLocalIndices/getIndices
+    const PltptGeometryInstance inst = sc.instances[instanceID];
+    const PltptMeshDesc mesh = sc.meshes[inst.geometryID];
+    if (mesh.indexCount == 0) { idx[0] = tri * 3 + inst.vbOffset; idx[1] = idx[0] + 1; idx[2] = idx[0] + 2; return; }
+    const uint8_t* base = sc.indexData + size_t(inst.ibOffset) * 4;
+    if (inst.flags & PLTPT_INSTANCE_FLAG_USE_16BIT_INDICES) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(base + size_t(tri) * 6);
+        idx[0] = uint32_t(p[0]) + inst.vbOffset; idx[1] = uint32_t(p[1]) + inst.vbOffset; idx[2] = uint32_t(p[2]) + inst.vbOffset;
+    } else {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(base + size_t(tri) * 12);
+        idx[0] = p[0] + inst.vbOffset; idx[1] = p[1] + inst.vbOffset; idx[2] = p[2] + inst.vbOffset;
+    }
+}
+
+// Intersection contract: p_w = ((m0*x + m1*y) + m2*z) + m3 per row, every operation rounded to fp32.
+PLT_D float3 worldPoint(const float* __restrict__ M, const float* __restrict__ P) {
+    float r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        r[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4 * i + 0], P[0]), __fmul_rn(M[4 * i + 1], P[1])), __fmul_rn(M[4 * i + 2], P[2])), M[4 * i + 3]);
+    return mk3(r[0], r[1], r[2]);
+}
+
+__global__ void k_world_tris(DevScene sc, BvhTri* __restrict__ tris, float4* __restrict__ boxLo, float4* __restrict__ boxHi, uint32_t* __restrict__ sceneBounds) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= sc.triCount) return;
+    // instance of global triangle g: last i with instTriOffset[i] <= g
+    uint32_t lo = 0, hi = sc.instanceCount;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sc.instTriOffset[mid] <= g) lo = mid; else hi = mid; }
+    const uint32_t inst = lo, prim = g - sc.instTriOffset[inst];
+    uint32_t idx[3];
+    fetchIndices(sc, inst, prim, idx);
+    const float* M = sc.world + 16 * size_t(sc.instances[inst].globalMatrixID);
+    const float3 v0 = worldPoint(M, sc.vertices[idx[0]].position), v1 = worldPoint(M, sc.vertices[idx[1]].position), v2 = worldPoint(M, sc.vertices[idx[2]].position);
+    BvhTri t;
+    t.v0x = v0.x; t.v0y = v0.y; t.v0z = v0.z; t.instanceID = inst;
+    t.v1x = v1.x; t.v1y = v1.y; t.v1z = v1.z; t.primitiveIndex = prim;
+    t.v2x = v2.x; t.v2y = v2.y; t.v2z = v2.z; t.globalIndex = g;
+    tris[g] = t;
+    const float3 bl = vmin(v0, vmin(v1, v2)), bh = vmax(v0, vmax(v1, v2));
+    boxLo[g] = mk4(bl.x, bl.y, bl.z, 0.f);
+    boxHi[g] = mk4(bh.x, bh.y, bh.z, 0.f);
+    atomicMin(sceneBounds + 0, floatFlip(bl.x)); atomicMin(sceneBounds + 1, floatFlip(bl.y)); atomicMin(sceneBounds + 2, floatFlip(bl.z));
+    atomicMax(sceneBounds + 3, floatFlip(bh.x)); atomicMax(sceneBounds + 4, floatFlip(bh.y)); atomicMax(sceneBounds + 5, floatFlip(bh.z));
+}
+
+PLT_D uint64_t expandBits21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void k_morton(uint32_t n, const float4* __restrict__ boxLo, const float4* __restrict__ boxHi, const uint32_t* __restrict__ sceneBounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const float3 slo = mk3(floatUnflip(sceneBounds[0]), floatUnflip(sceneBounds[1]), floatUnflip(sceneBounds[2]));
+    const float3 shi = mk3(floatUnflip(sceneBounds[3]), floatUnflip(sceneBounds[4]), floatUnflip(sceneBounds[5]));
+    const float4 l = boxLo[g], h = boxHi[g];
+    const float3 c = mk3(.5f * (l.x + h.x), .5f * (l.y + h.y), .5f * (l.z + h.z));
+    const float3 e = vmax(shi - slo, mk3(1e-30f));
+    const float s = 2097151.f;
+    const uint32_t qx = uint32_t(fminf(fmaxf((c.x - slo.x) / e.x, 0.f), 1.f) * s), qy = uint32_t(fminf(fmaxf((c.y - slo.y) / e.y, 0.f), 1.f) * s),
+                   qz = uint32_t(fminf(fmaxf((c.z - slo.z) / e.z, 0.f), 1.f) * s);
+    keys[g] = (expandBits21(qx) << 2) | (expandBits21(qy) << 1) | expandBits21(qz);
+    vals[g] = g;
+}
+
+// ---- Karras 2012: "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees" ----------------------
+PLT_D int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    return a == b ? 64 + __clz(uint32_t(i) ^ uint32_t(j)) : __clzll((long long)(a ^ b));
+}
+// refs: internal node i -> i ; leaf (sorted position p) -> p | kLeafBit
+__global__ void k_radix_tree(int n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ left, uint32_t* __restrict__ right, uint32_t* __restrict__ first,
+                             uint32_t* __restrict__ last, uint32_t* __restrict__ parentInner, uint32_t* __restrict__ parentLeaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const uint32_t L = lo == gamma ? (uint32_t(gamma) | kLeafBit) : uint32_t(gamma);
+    const uint32_t R = hi == gamma + 1 ? (uint32_t(gamma + 1) | kLeafBit) : uint32_t(gamma + 1);
+    left[i] = L; right[i] = R; first[i] = uint32_t(lo); last[i] = uint32_t(hi);
+    if (L & kLeafBit) parentLeaf[gamma] = uint32_t(i); else parentInner[gamma] = uint32_t(i);
+    if (R & kLeafBit) parentLeaf[gamma + 1] = uint32_t(i); else parentInner[gamma + 1] = uint32_t(i);
+    if (i == 0) parentInner[0] = 0xffffffffu;
+}
+
+// node boxes: index i (internal) in [0, n-1); leaves read the triangle boxes through `sorted`.
+__global__ void k_fit(int n, const uint32_t* __restrict__ sorted, const float4* __restrict__ triLo, const float4* __restrict__ triHi, const uint32_t* __restrict__ left,
+                      const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentInner, const uint32_t* __restrict__ parentLeaf, float4* __restrict__ nodeLo,
+                      float4* __restrict__ nodeHi, uint32_t* __restrict__ arrivals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t node = parentLeaf[p];
+    while (node != 0xffffffffu) {
+        __threadfence();
+        if (atomicAdd(arrivals + node, 1u) == 0u) return;  // the sibling subtree is not finished yet
+        __threadfence();
+        float4 lo[2], hi[2];
+        const uint32_t c[2] = {left[node], right[node]};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (c[k] & kLeafBit) { const uint32_t t = sorted[c[k] & ~kLeafBit]; lo[k] = triLo[t]; hi[k] = triHi[t]; }
+            else { lo[k] = __ldcg(nodeLo + c[k]); hi[k] = __ldcg(nodeHi + c[k]); }
+        }
+        __stcg(nodeLo + node, mk4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f));
+        __stcg(nodeHi + node, mk4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f));
+        node = parentInner[node];
+    }
+}
+
+struct CollapseItem { uint32_t bin, wide; };
+struct TreeView {
+    const uint32_t *left, *right, *first, *last, *sorted;
+    const float4 *nodeLo, *nodeHi, *triLo, *triHi;
+    PLT_D uint32_t count(uint32_t ref) const { return (ref & kLeafBit) ? 1u : last[ref] - first[ref] + 1u; }
+    PLT_D uint32_t firstPos(uint32_t ref) const { return (ref & kLeafBit) ? (ref & ~kLeafBit) : first[ref]; }
+    PLT_D void box(uint32_t ref, float3& lo, float3& hi) const {
+        float4 l, h;
+        if (ref & kLeafBit) { const uint32_t t = sorted[ref & ~kLeafBit]; l = triLo[t]; h = triHi[t]; }
+        else { l = nodeLo[ref]; h = nodeHi[ref]; }
+        lo = mk3(l.x, l.y, l.z); hi = mk3(h.x, h.y, h.z);
+    }
+    PLT_D float area(uint32_t ref) const {
+        float3 lo, hi;
+        box(ref, lo, hi);
+        const float3 e = hi - lo;
+        return e.x * e.y + e.y * e.z + e.z * e.x;
+    }
+};
+
+// smallest biased exponent eb with origin + 255 * 2^(eb-127) >= hi (checked in fp32 exactly as the traversal dequantises)
+PLT_D uint32_t gridExponent(float origin, float hi) {
+    const float ext = hi - origin;
+    int e = 0;
+    if (ext > 0.f) frexpf(ext / 255.f, &e);  // ext/255 = m * 2^e, m in [0.5,1)  =>  2^e >= ext/255
+    else e = -126;
+    int eb = min(max(e + 127, 1), 254);
+    while (eb < 254 && origin + 255.f * __uint_as_float(uint32_t(eb) << 23) < hi) ++eb;
+    return uint32_t(eb);
+}
+PLT_D uint32_t quantLo(float origin, float s, float v) {
+    int q = int(floorf((v - origin) / s));
+    q = min(max(q, 0), 255);
+    while (q > 0 && origin + float(q) * s > v) --q;
+    return uint32_t(q);
+}
+PLT_D uint32_t quantHi(float origin, float s, float v) {
+    int q = int(ceilf((v - origin) / s));
+    q = min(max(q, 0), 255);
+    while (q < 255 && origin + float(q) * s < v) ++q;
+    return uint32_t(q);
+}
+
+__global__ void k_collapse(const CollapseItem* __restrict__ items, uint32_t nItems, CollapseItem* __restrict__ nextItems, uint32_t* __restrict__ counters /*0 nodes,1 tris,2 next*/,
+                           TreeView tv, const BvhTri* __restrict__ srcTris, BvhNode* __restrict__ outNodes, BvhTri* __restrict__ outTris, uint32_t rootIsLeaf) {
+    const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= nItems) return;
+    const CollapseItem item = items[it];
+    uint32_t c[8];
+    int cnt;
+    if (rootIsLeaf) { c[0] = item.bin; cnt = 1; }
+    else { c[0] = tv.left[item.bin]; c[1] = tv.right[item.bin]; cnt = 2; }
+    while (cnt < 8) {
+        int best = -1;
+        float bestA = -1.f;
+        for (int i = 0; i < cnt; ++i) {
+            if ((c[i] & kLeafBit) || tv.count(c[i]) <= kMaxLeafTris) continue;
+            const float a = tv.area(c[i]);
+            if (a > bestA) { bestA = a; best = i; }
+        }
+        if (best < 0) break;
+        const uint32_t b = c[best];
+        c[best] = tv.left[b];
+        c[cnt++] = tv.right[b];
+    }
+    float3 nlo, nhi;
+    tv.box(item.bin, nlo, nhi);
+    uint32_t nInner = 0, nTris = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const uint32_t k = tv.count(c[i]);
+        if (k > kMaxLeafTris) ++nInner; else nTris += k;
+    }
+    const uint32_t childBase = nInner ? atomicAdd(counters + 0, nInner) : 0u;
+    const uint32_t triBase = nTris ? atomicAdd(counters + 1, nTris) : 0u;
+    const uint32_t nextBase = nInner ? atomicAdd(counters + 2, nInner) : 0u;
+
+    BvhNode node;
+    node.px = nlo.x; node.py = nlo.y; node.pz = nlo.z;
+    const uint32_t ex = gridExponent(nlo.x, nhi.x), ey = gridExponent(nlo.y, nhi.y), ez = gridExponent(nlo.z, nhi.z);
+    node.ex = uint8_t(ex); node.ey = uint8_t(ey); node.ez = uint8_t(ez);
+    const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+    node.childBase = childBase; node.triBase = triBase;
+    uint32_t imask = 0, innerSeen = 0, triOff = 0;
+    for (int i = 0; i < 8; ++i) {
+        node.meta[i] = 0;
+        node.qlox[i] = node.qloy[i] = node.qloz[i] = 0;
+        node.qhix[i] = node.qhiy[i] = node.qhiz[i] = 0;
+        if (i >= cnt) continue;
+        float3 lo, hi;
+        tv.box(c[i], lo, hi);
+        node.qlox[i] = uint8_t(quantLo(nlo.x, sx, lo.x)); node.qhix[i] = uint8_t(quantHi(nlo.x, sx, hi.x));
+        node.qloy[i] = uint8_t(quantLo(nlo.y, sy, lo.y)); node.qhiy[i] = uint8_t(quantHi(nlo.y, sy, hi.y));
+        node.qloz[i] = uint8_t(quantLo(nlo.z, sz, lo.z)); node.qhiz[i] = uint8_t(quantHi(nlo.z, sz, hi.z));
+        const uint32_t k = tv.count(c[i]);
+        if (k > kMaxLeafTris) {
+            imask |= 1u << i;
+            node.meta[i] = uint8_t(0x20u | (24u + uint32_t(i)));
+            nextItems[nextBase + innerSeen] = CollapseItem{c[i], childBase + innerSeen};
+            ++innerSeen;
+        } else {
+            node.meta[i] = uint8_t((k << 5) | triOff);
+            const uint32_t fp = tv.firstPos(c[i]);
+            for (uint32_t t = 0; t < k; ++t) outTris[triBase + triOff + t] = srcTris[tv.sorted[fp + t]];
+            triOff += k;
+        }
+    }
+    node.imask = uint8_t(imask);
+    outNodes[item.wide] = node;
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, uint32_t n, const float* __restrict__ rays, uint32_t* __restrict__ out,
+                                               float* __restrict__ outT, uint32_t* __restrict__ overflow) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i)), b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
+        Hit h;
+        const bool hit = traverseBvh<ANY>(nodes, tris, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, h, overflow);
+        if (ANY) out[i] = hit ? 1u : 0u;
+        else {
+            reinterpret_cast<uint4*>(out)[i] = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+            if (outT) outT[i] = hit ? h.t : 0.f;
+        }
+    }
+}
+
+inline uint32_t blocksFor(uint64_t n, uint32_t threads) { return uint32_t((n + threads - 1) / threads); }
+
+}  // namespace
+
+int buildBvh(PltptContext* c, cudaStream_t s) {
+    DevScene& sc = c->scene;
+    const uint32_t n = sc.triCount;
+    cudaEventRecord(c->evA, s);
+    DevBuf& srcTris = c->bvhScratch[0];
+    DevBuf& triLo = c->bvhScratch[1];
+    DevBuf& triHi = c->bvhScratch[2];
+    DevBuf& keys = c->bvhScratch[3];   // keys in | keys out | vals in | vals out
+    DevBuf& tree = c->bvhScratch[4];   // left,right,first,last,parentInner,arrivals (n each) + parentLeaf (n)
+    DevBuf& nodeBox = c->bvhScratch[5];
+    DevBuf& queue = c->bvhScratch[6];
+    DevBuf& misc = c->bvhScratch[7];   // scene bounds (6) + counters (3) + overflow (1)
+    PLT_CUDA(srcTris.ensure(size_t(n) * sizeof(BvhTri)));
+    PLT_CUDA(triLo.ensure(size_t(n) * 16));
+    PLT_CUDA(triHi.ensure(size_t(n) * 16));
+    PLT_CUDA(keys.ensure(size_t(n) * (8 + 8 + 4 + 4)));
+    PLT_CUDA(tree.ensure(size_t(n) * 7 * 4));
+    PLT_CUDA(nodeBox.ensure(size_t(n) * 32));
+    PLT_CUDA(queue.ensure(size_t(n) * 2 * sizeof(CollapseItem) + 16));
+    PLT_CUDA(misc.ensure(64));
+    PLT_CUDA(c->bvhTris.ensure(size_t(n) * sizeof(BvhTri)));
+    // a wide node has >= 2 children unless it is the root of a <=3-triangle scene, so #nodes <= max(1, n - 1)
+    PLT_CUDA(c->bvhNodes.ensure(size_t(n) * sizeof(BvhNode)));
+
+    uint32_t* miscU = misc.as<uint32_t>();
+    const uint32_t initMisc[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, /*counters*/ 1u, 0u, 0u, /*overflow*/ 0u, 0, 0, 0, 0, 0, 0};
+    PLT_CUDA(cudaMemcpyAsync(miscU, initMisc, sizeof(initMisc), cudaMemcpyHostToDevice, s));
+    uint32_t* counters = miscU + 6;
+
+    k_world_tris<<<blocksFor(n, 256), 256, 0, s>>>(sc, srcTris.as<BvhTri>(), triLo.as<float4>(), triHi.as<float4>(), miscU);
+    uint64_t* keysIn = keys.as<uint64_t>();
+    uint64_t* keysOut = keysIn + n;
+    uint32_t* valsIn = reinterpret_cast<uint32_t*>(keysOut + n);
+    uint32_t* valsOut = valsIn + n;
+    k_morton<<<blocksFor(n, 256), 256, 0, s>>>(n, triLo.as<float4>(), triHi.as<float4>(), miscU, keysIn, valsIn);
+    size_t tempBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keysIn, keysOut, valsIn, valsOut, int(n), 0, 63, s);
+    PLT_CUDA(c->work[23].ensure(tempBytes));
+    PLT_CUDA(cub::DeviceRadixSort::SortPairs(c->work[23].p, tempBytes, keysIn, keysOut, valsIn, valsOut, int(n), 0, 63, s));
+    c->stats.kernelLaunches += 2;
+
+    uint32_t* left = tree.as<uint32_t>();
+    uint32_t* right = left + n;
+    uint32_t* first = right + n;
+    uint32_t* last = first + n;
+    uint32_t* parentInner = last + n;
+    uint32_t* arrivals = parentInner + n;
+    uint32_t* parentLeaf = arrivals + n;
+    float4* nodeLo = nodeBox.as<float4>();
+    float4* nodeHi = nodeLo + n;
+    CollapseItem* q0 = queue.as<CollapseItem>();
+    CollapseItem* q1 = q0 + n;
+    TreeView tv{left, right, first, last, valsOut, nodeLo, nodeHi, triLo.as<float4>(), triHi.as<float4>()};
+
+    uint32_t levels = 0;
+    if (n == 1) {
+        // no internal binary node exists: the root wide node gets the single triangle as its only leaf slot
+        const CollapseItem root{0u | kLeafBit, 0u};
+        PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+        k_collapse<<<1, 32, 0, s>>>(q0, 1, q1, counters, tv, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 1u);
+        c->stats.kernelLaunches++;
+        levels = 1;
+    } else {
+        k_radix_tree<<<blocksFor(n - 1, 256), 256, 0, s>>>(int(n), keysOut, left, right, first, last, parentInner, parentLeaf);
+        PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(n) * 4, s));
+        k_fit<<<blocksFor(n, 256), 256, 0, s>>>(int(n), valsOut, triLo.as<float4>(), triHi.as<float4>(), left, right, parentInner, parentLeaf, nodeLo, nodeHi, arrivals);
+        c->stats.kernelLaunches += 4;
+        const CollapseItem root{0u, 0u};
+        PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+        uint32_t nItems = 1;
+        while (nItems > 0) {
+            PLT_CUDA(cudaMemsetAsync(counters + 2, 0, 4, s));
+            k_collapse<<<blocksFor(nItems, 128), 128, 0, s>>>(q0, nItems, q1, counters, tv, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 0u);
+            c->stats.kernelLaunches++;
+            PLT_CUDA(cudaMemcpyAsync(&nItems, counters + 2, 4, cudaMemcpyDeviceToHost, s));
+            PLT_CUDA(cudaStreamSynchronize(s));
+            std::swap(q0, q1);
+            if (++levels > 4096) { setError("BVH collapse did not terminate"); return PLTPT_ERR_CUDA; }
+        }
+    }
+    uint32_t finalCounters[3] = {0, 0, 0};
+    PLT_CUDA(cudaMemcpyAsync(finalCounters, counters, 12, cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(c->evB, s);
+    PLT_CUDA(cudaStreamSynchronize(s));
+    PLT_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->evA, c->evB);
+    if (finalCounters[1] != n) { setError("BVH build lost triangles: " + std::to_string(finalCounters[1]) + " of " + std::to_string(n)); return PLTPT_ERR_CUDA; }
+    c->stats.bvhBuildMs = ms;
+    c->stats.bvhNodes = finalCounters[0];
+    c->stats.bvhLeafTriangles = finalCounters[1];
+    c->stats.triangleCount = n;
+    sc.bvhNodes = c->bvhNodes.as<BvhNode>();
+    sc.bvhTris = c->bvhTris.as<BvhTri>();
+    // build scratch is only needed again on the next set_scene
+    for (int i = 0; i < 7; ++i) c->bvhScratch[i].release();
+    return PLTPT_OK;
+}
+
+static int traceLaunch(PltptContext* c, bool any, uint32_t n, const float* rays, uint32_t* out, float* outT, cudaStream_t s) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const uint32_t grid = std::min<uint32_t>(blocksFor(n, 128), uint32_t(sms) * 16);
+    uint32_t* overflow = c->bvhScratch[7].as<uint32_t>() + 9;
+    if (any) k_trace<true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);
+    else k_trace<false><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, overflow);
+    c->stats.kernelLaunches++;
+    (any ? c->stats.raysAny : c->stats.raysClosest) += n;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+int traceClosest(PltptContext* c, uint32_t n, const float* rays, uint32_t* hits, float* hitT, cudaStream_t s) { return traceLaunch(c, false, n, rays, hits, hitT, s); }
+int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded, cudaStream_t s) { return traceLaunch(c, true, n, rays, occluded, nullptr, s); }
+
+}  // namespace plt

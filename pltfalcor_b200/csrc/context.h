@@ -86,6 +86,8 @@ struct PltptContext {
     uint32_t workW = 0, workH = 0, workBounces = 0;
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};
+    bool statsDirty = false;
+    uint64_t traversalOverflows = 0, mneeIterations = 0;
     cudaEvent_t evA = nullptr, evB = nullptr;
 };
 
@@ -102,4 +104,5 @@ int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded,
 int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
                 double* accum, bool solve, cudaStream_t s);
 int copyBounces(PltptContext* c, PltptBounce* host, uint32_t w, uint32_t h);
+int syncFrameStats(PltptContext* c);
 }  // namespace plt

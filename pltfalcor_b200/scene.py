@@ -747,3 +747,60 @@ def sweep_scene(dielectric_roughness=0.1, conductor_roughness=0.3):
     )
     b.add_mesh(quad([-1, 0, 1], [1, 0, 1], [1, 0, -1], [-1, 0, -1]), ids["diffuse"])
     return b.finalize(), ids
+
+
+def grating_sphere_scene(aspect=16.0 / 9.0, n_lat=64, n_lon=128):
+    """BASELINE config 3: ground plane = sinusoidal diffraction-grated Au conductor (pitch 3 um, 3 lobes, q-scale 0.5),
+    a tessellated smooth Dielectric sphere (MNEE refracts through it), a small area emitter and one distant light."""
+    b = SceneBuilder()
+    au = b.add_ior_profiles("Au")
+    lamp = b.add_emission_profile(LAMP, 4.0)
+    led = b.add_emission_profile("2499_LED_Encaster_Calculite_domestic-use_softwhite-color_Philips_brand_22W_1500lm_7inch_3000K", 0.02)
+    grated = b.add_grated_conductor(au, (3.0, 0.0), q=0.3, q_scale=0.5, roughness=0.05, lobes=3)
+    glass = b.add_dielectric(ior=1.5, roughness=0.0)
+    wall = b.add_diffuse((0.6, 0.6, 0.6))
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    b.add_mesh(grid_plane(0.0, -3.0, 3.0, -3.0, 3.0, 8, 8), grated)
+    b.add_mesh(uv_sphere([0.0, 0.75, 0.0], 0.6, n_lat, n_lon), glass)
+    b.add_mesh(quad([-3, 0, -3], [3, 0, -3], [3, 4, -3], [-3, 4, -3]), wall)                                  # back wall (normal +z)
+    b.add_mesh(quad([-0.25, 2.6, -0.25], [0.25, 2.6, -0.25], [0.25, 2.6, 0.25], [-0.25, 2.6, 0.25]), light)   # emitter facing down
+    b.add_distant_light(led, direction=(-0.4, -1.0, -0.3), half_angle=math.radians(0.5))
+    cam = make_camera([0.0, 1.6, 4.0], [0.0, 0.6, 0.0], focal_length=35.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def layered_stress_scene(aspect=16.0 / 9.0):
+    """BASELINE config 4: coated conductors, coated opaque dielectric, birefringent thin dielectric and alternating
+    multilayer stacks (2..20 layers) as spheres / plates over a diffuse floor, under one area emitter."""
+    b = SceneBuilder()
+    au, cu, al = b.add_ior_profiles("Au"), b.add_ior_profiles("Cu"), b.add_ior_profiles("Al")
+    lamp = b.add_emission_profile(LAMP, 6.0)
+    floor = b.add_diffuse((0.55, 0.55, 0.55))
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    mats = [
+        b.add_coated_conductor(cu, 0.05, tau_um=3.0, coat_ior=1.5),
+        b.add_coated_conductor(au, 0.15, tau_um=1.0, coat_ior=1.38),
+        b.add_coated_opaque_dielectric((0.7, 0.2, 0.2), 0.05, tau_um=3.0, coat_ior=1.5),
+        b.add_coated_opaque_dielectric((0.2, 0.3, 0.7), 0.1, tau_um=0.5, coat_ior=1.6),
+        b.add_thin_dielectric(1.5, 0.3, birefringence=0.1),
+        b.add_multilayered_stack((1, 1, 1), layers=2),
+        b.add_multilayered_stack((1, 1, 1), layers=8),
+        b.add_multilayered_stack((1, 1, 1), layers=20),
+        b.add_conductor(al, 0.1),
+        b.add_opaque_dielectric((0.3, 0.5, 0.7), 0.05),
+    ]
+    b.add_mesh(grid_plane(0.0, -4.0, 4.0, -3.0, 3.0, 4, 4), floor)
+    b.add_mesh(quad([-4, 0, -3], [4, 0, -3], [4, 4, -3], [-4, 4, -3]), floor)
+    k = 0
+    for row in range(2):
+        for col in range(8):
+            m = mats[k % len(mats)]
+            k += 1
+            c = [-3.15 + col * 0.9, 0.36 + row * 0.0, -1.2 + row * 1.6]
+            if m == mats[4]:  # thin dielectric as an upright plate
+                b.add_mesh(quad([c[0] - 0.35, 0.02, c[2]], [c[0] + 0.35, 0.02, c[2]], [c[0] + 0.35, 0.9, c[2]], [c[0] - 0.35, 0.9, c[2]]), m)
+            else:
+                b.add_mesh(uv_sphere(c, 0.34, 24, 48), m)
+    b.add_mesh(quad([-1.0, 3.2, -1.0], [1.0, 3.2, -1.0], [1.0, 3.2, 1.0], [-1.0, 3.2, 1.0]), light)
+    cam = make_camera([0.0, 2.2, 5.5], [0.0, 0.4, 0.0], focal_length=35.0, aspect=aspect)
+    return b.finalize(), cam
