@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — PLT paths/s of the PLTPT hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (default N=1, K=32, W=3)
+  python bench.py --impl reference ...                          the reference's CPU path (oracle port) on the host cores
+
+Workload (config.workload): BASELINE configs[1] — procedural Cornell box (PLTDiffuse walls, rough PLT Dielectric box,
+rough Au PLT Conductor box, LSPDD area emitter), 1920x1080, max depth 8, HWSS 4, NEE + MIS + MNEE on.  One "step" = one
+frame = one sample per pixel over the whole image (= one PLTPT::execute, PLTPT.cpp:357-499) = 2 073 600 paths.
+With N GPUs every rank renders its own frame indices {rank, rank+N, ...} (sample-index partitioning; scene replicated) and
+the per-GPU fp64 accumulation buffers are summed onto rank 0 with one NCCL reduce inside the timed region ("weak" scaling:
+K frames per GPU).
+
+Numbers:
+  value  device-resident throughput: K frames through pltpt_render_accumulate, scene and accumulators in HBM, CUDA events.
+  e2e    the same metric through the host-buffer C-ABI call a Falcor shell makes without shared surfaces
+         (pltpt_render_frame_host): camera struct H2D and the three RGBA32F RenderData images D2H (pinned) every step.
+  roofline  dominant kernel (solve stage) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the CPU oracle (a restatement of the reference's Slang path; `kind: port`) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, MAX_BOUNCES = 1920, 1080, 8
+WORKLOAD = "cornell_box_plt_dielectric_conductor_lspdd_emitter_1920x1080_depth8 (BASELINE configs[1]; 1 spp per step)"
+# SURVEY §8(d) algorithmic bytes of the rendering path
+F_VERTEX_FETCH = 396   # indices 12 + 3 vertices 96 + instance 32 + matrices 128 + material 128
+R_BOUNCE = 40          # bounce record
+LIGHT_FETCH = 88       # alias 8 + flux 16 + emissive triangle 64
+NODE_BYTES, TRI_BYTES = 80, 48
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene():
+    from pltfalcor_b200 import scene
+    return scene.cornell_box(aspect=WIDTH / HEIGHT)
+
+
+def path_bytes(stats, frames, paths):
+    """per-path algorithmic bytes of the two stages from the measured path statistics."""
+    L = stats["totalPathVertices"] / paths                      # mean recorded vertices per path
+    replay = stats["totalReplaySteps"] / paths                  # mean sum_{p<L} p
+    bvh = (stats["traversalNodesVisited"] * NODE_BYTES + stats["traversalTrianglesTested"] * TRI_BYTES) / paths
+    sample_b = L * (F_VERTEX_FETCH + R_BOUNCE)
+    solve_b = L * (R_BOUNCE + F_VERTEX_FETCH + LIGHT_FETCH) + replay * (R_BOUNCE + F_VERTEX_FETCH) + 48
+    return dict(mean_vertices=L, mean_replay_steps=replay, sample_bytes=sample_b, solve_bytes=solve_b, bvh_bytes=bvh, total=sample_b + solve_b + bvh)
+
+
+def cpu_baseline_sample(buffers, cam, opts, seconds=10.0):
+    """Times the oracle (CPU restatement of the reference path) on all host cores on a bounded sample of the workload."""
+    from oracle import binding as ob
+    from pltfalcor_b200 import scene
+    osc = ob.OracleScene(buffers)
+    threads = ob.hardware_threads()
+    w, h = WIDTH // 2, HEIGHT // 2
+    osc.render_frame(opts, scene.with_jitter(cam, 0, w, h), 0, w, h, threads=threads)  # warm-up (page in, thread pool)
+    t0, frames = time.perf_counter(), 0
+    while True:
+        osc.render_frame(opts, scene.with_jitter(cam, 1 + frames, w, h), 1 + frames, w, h, threads=threads)
+        frames += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or frames >= 64:
+            break
+    return {"value": w * h * frames / dt, "unit": "paths/s", "cores": threads, "kind": "port",
+            "sample": f"{frames} frames of the same Cornell-box workload at {w}x{h} (1/4 of the pixels), depth {MAX_BOUNCES}, {dt:.1f} s wall, oracle/liboracle.so"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. slangc is not available, so the Slang modules cannot
+    be compiled for the CPU; the oracle port (C++ restatement, all host threads) stands in (DESIGN.md 'Oracle')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    from pltfalcor_b200 import layouts as L, scene
+    buffers, cam = build_scene()
+    opts = L.make_options(maxBounces=MAX_BOUNCES)
+    osc = ob.OracleScene(buffers)
+    threads = ob.hardware_threads()
+    w, h = WIDTH // 4, HEIGHT // 4  # bounded sample per step: 1/16 of the frame's pixels, same camera and scene
+    for f in range(args.warmup):
+        osc.render_frame(opts, scene.with_jitter(cam, f, w, h), f, w, h, threads=threads)
+    t0 = time.perf_counter()
+    for f in range(args.steps):
+        osc.render_frame(opts, scene.with_jitter(cam, 100 + f, w, h), 100 + f, w, h, threads=threads)
+    dt = time.perf_counter() - t0
+    value = w * h * args.steps / dt
+    sample = f"each step = one frame at {w}x{h} (1/16 of the 1920x1080 pixels, same scene/camera/options)"
+    print(json.dumps({
+        "impl": "reference", "metric": "plt_paths_per_s", "value": value, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "max_bounces": MAX_BOUNCES, "hwss": 4, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def bsdf_sweep(torch, p, ids, hbm_peak):
+    """BASELINE configs[0] on the GPU: rough dielectric + rough Au conductor, 2^20 random wi/wo x 16 wavelengths, Mueller output."""
+    n, groups = 1 << 20, 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    wi = torch.nn.functional.normalize(torch.randn((n, 3), device="cuda", generator=g), dim=1)
+    wi[:, 2].abs_()
+    wo = torch.nn.functional.normalize(torch.randn((n, 3), device="cuda", generator=g), dim=1)
+    hero = 380 + 340 * torch.rand((groups, n), device="cuda", generator=g)
+    out = torch.empty((n, groups, 4, 4, 4), device="cuda")  # 1.07 GB > L2
+    res = {}
+    for key in ("dielectric", "conductor"):
+        for _ in range(2):
+            p.bsdf_eval_mueller(ids[key], 0x33, wi, wo, hero, out)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        reps = 5
+        for _ in range(reps):
+            p.bsdf_eval_mueller(ids[key], 0x33, wi, wo, hero, out)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        evals = n * groups * 4
+        gbs = evals * 66.5 / (ms * 1e-3) / 1e9  # 66.5 algorithmic bytes per BSDF eval
+        res[key] = {"evals_per_s": evals / (ms * 1e-3), "ms": ms, "achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from pltfalcor_b200 import binding, build, layouts as L, scene
+    if build.needs_build():
+        raise SystemExit("libpltpt.so is stale or missing: run `python -c 'import __graft_entry__ as g; g.build()'` first (no JIT on the bench path)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the PLTPT path has no CPU fallback")
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    W, K = max(args.warmup, 3), args.steps
+    hbm_peak, peak_src = peaks()
+
+    buffers, cam = build_scene()
+    p = binding.Pltpt(device=local, maxBounces=MAX_BOUNCES)
+    p.set_scene(buffers)
+    build_stats = p.stats()
+    accum = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    # ---- device-resident timing -------------------------------------------------------------------------------------
+    p.render_accumulate(cam, rank, world, W, WIDTH, HEIGHT, accum, stream=sptr)  # warm-up frames (also sizes the work buffers)
+    accum.zero_()
+    if world > 1:
+        dist.reduce(accum, dst=0)  # warm-up of the NCCL communicator
+        accum.zero_()
+    torch.cuda.synchronize()
+    p.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    first = W * world + rank
+    p.render_accumulate(cam, first, world, K, WIDTH, HEIGHT, accum, stream=sptr)
+    if world > 1:
+        dist.reduce(accum, dst=0)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    stats = p.stats()
+    paths_per_gpu = WIDTH * HEIGHT * K
+    value = paths_per_gpu * world / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------------
+    host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+    e2e_steps = max(4, min(K, 16))
+
+    def e2e_step(f):
+        c = scene.with_jitter(cam, f, WIDTH, HEIGHT)
+        binding._check(binding.lib().pltpt_render_frame_host(p.h, f, C.byref(c), WIDTH, HEIGHT, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr()))
+
+    for f in range(3):
+        e2e_step(rank + f * world)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(e2e_steps):
+        e2e_step(1000 + rank + f * world)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = WIDTH * HEIGHT * e2e_steps * world / float(e2e_t.item())
+    checksum = float(host[0][..., :3].double().mean())
+
+    if rank == 0:
+        pb = path_bytes(stats, K, paths_per_gpu)
+        solve_ms = stats["solveStageMs"] / max(stats["framesRendered"], 1)
+        sample_ms = stats["sampleStageMs"] / max(stats["framesRendered"], 1)
+        paths_per_launch = WIDTH * HEIGHT
+        solve_gbs = pb["solve_bytes"] * paths_per_launch / (solve_ms * 1e-3) / 1e9
+        out = {
+            "metric": "plt_paths_per_s", "value": value, "unit": "paths/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "max_bounces": MAX_BOUNCES, "hwss": 4, "nee": True, "mis": True, "mnee": True, "russian_roulette": True,
+                       "paths_per_step_per_gpu": WIDTH * HEIGHT, "partition": "frame index modulo n_gpus; fp64 accumulators summed by one NCCL reduce inside the timed region",
+                       "l2": "inputs larger than L2: every frame rewrites and re-reads its %.0f MB bounce buffer (126 MB L2)" % ((MAX_BOUNCES + 1) * WIDTH * HEIGHT * 40 / 1e6),
+                       "triangles": int(build_stats["triangleCount"]), "bvh_nodes": int(build_stats["bvhNodes"]), "bvh_build_ms": build_stats["bvhBuildMs"]},
+            "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": C.sizeof(L.PltptCameraData), "d2h_bytes_per_step": 3 * WIDTH * HEIGHT * 16, "steps": e2e_steps,
+                    "api": "pltpt_render_frame_host (camera in, color/albedo/normal RGBA32F out, pinned host buffers)", "checksum_mean_rgb": checksum},
+            "gpu_launches": int(stats["kernelLaunches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_solve_stage", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": solve_gbs / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": solve_ms, "share_of_step": solve_ms / (solve_ms + sample_ms),
+                         "algorithmic_bytes_per_path": pb["solve_bytes"], "paths_per_launch": paths_per_launch,
+                         "other_kernels": {"k_sample_stage": {"kernel_ms": sample_ms, "algorithmic_bytes_per_path": pb["sample_bytes"] + pb["bvh_bytes"],
+                                                              "achieved": (pb["sample_bytes"] + pb["bvh_bytes"]) * paths_per_launch / (sample_ms * 1e-3) / 1e9}}},
+            "path_stats": {"mean_vertices": pb["mean_vertices"], "mean_replay_steps": pb["mean_replay_steps"], "bsdf_evals_per_path": stats["totalBsdfEvals"] / paths_per_gpu,
+                           "bsdf_evals_per_s": stats["totalBsdfEvals"] * world / (total_ms * 1e-3), "bvh_nodes_per_path": stats["traversalNodesVisited"] / paths_per_gpu,
+                           "bvh_triangles_per_path": stats["traversalTrianglesTested"] / paths_per_gpu, "algorithmic_bytes_per_path": pb["total"]},
+        }
+        if world == 1:
+            sw_buffers, ids = scene.sweep_scene()
+            q = binding.Pltpt(device=local)
+            q.set_scene(sw_buffers)
+            out["bsdf_sweep"] = bsdf_sweep(torch, q, ids, hbm_peak)
+            q.close()
+            if not args.no_cpu_baseline:
+                out["cpu_baseline"] = cpu_baseline_sample(buffers, cam, p.options)
+        print(json.dumps(out))
+    p.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

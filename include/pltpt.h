@@ -366,6 +366,15 @@ typedef struct PltptStats {
     uint64_t pathVertices;       /* recorded bounce vertices of the last frame */
     uint64_t bsdfEvals;          /* IMaterialInstance.eval calls x wavelengths of the last frame (if counted) */
     double   bvhBuildMs;
+    uint64_t traversalStackOverflows; /* rays whose traversal stack overflowed since create (must stay 0) */
+    uint64_t mneeIterations;          /* manifold-walk proposal rays of the last frame */
+    /* accumulated since the last pltpt_reset_stats (device timers: CUDA events on the launching stream) */
+    uint64_t framesRendered;
+    double   sampleStageMs, solveStageMs;      /* summed kernel durations of the two stages */
+    uint64_t totalPathVertices;                /* sum over paths of L (recorded vertices) */
+    uint64_t totalReplaySteps;                 /* sum over paths of L(L-1)/2: forward-replay vertex fetches of the NEE connections */
+    uint64_t totalBsdfEvals;                   /* eval calls x wavelengths */
+    uint64_t traversalNodesVisited, traversalTrianglesTested; /* BVH work of both stages */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);

@@ -13,6 +13,10 @@ enum Lobe : uint32_t {
 };
 static constexpr int LobeTypeMaterialSpecificOffset = 8;
 static constexpr float QcutoffForMS = .15f;  // IMaterialInstance.slang:44
+// exp() of the delta-lobe energies `alpha`: the BSDFs go on to form 1 - alpha, which cancels catastrophically for
+// near-smooth surfaces, so a 1-ulp difference between two exp implementations becomes an O(1) relative difference.
+// The oracle therefore DEFINES this exp as the correctly rounded fp32 value (evaluated in double); the CUDA path does the same.
+inline float exp_cr(float x) { return float(std::exp(double(x))); }
 
 // IMaterialInstance.slang:50-95
 struct BSDFProperties {
@@ -120,7 +124,7 @@ struct FractalSurface {
     explicit FractalSurface(float PSDroughness, float g = 3.f) : T(roughnessToT(PSDroughness)), gamma(std::max(1.1f, g)) {}
     float roughness() const { return 1.f / std::sqrt(1.f + 4.f * sqr(kMeanK) * T); }
     float q() const { return roughness() * 1.f; }
-    float alpha(float3 wi, float3 wo, float k) const { return std::exp(-sqr((std::fabs(wi.z) + std::fabs(wo.z)) * q() * k)); }
+    float alpha(float3 wi, float3 wo, float k) const { return exp_cr(-sqr((std::fabs(wi.z) + std::fabs(wo.z)) * q() * k)); }
     hwss_t alpha(float3 wi, float3 wo, hwss_t k) const { hwss_t r; for (int j = 0; j < 4; ++j) r[j] = alpha(wi, wo, k[j]); return r; }
     float alpha(float3 wi, float k) const { return alpha(wi, wi, k); }
     bool isDeltaOnly() const { return q() == .0f; }
@@ -170,7 +174,7 @@ struct GaussianSurface {
     bool isDeltaOnly() const { return q == .0f; }
     float alpha(float3 wi, float3 wo, float k) const {
         const float a = sqr((std::fabs(wi.z) + std::fabs(wo.z)) * q * k);
-        return isDeltaOnly() ? 1.f : std::exp(-a);
+        return isDeltaOnly() ? 1.f : exp_cr(-a);
     }
     hwss_t alpha(float3 wi, float3 wo, hwss_t k) const { hwss_t r; for (int j = 0; j < 4; ++j) r[j] = alpha(wi, wo, k[j]); return r; }
     float alpha(float3 wi, float k) const { return alpha(wi, wi, k); }
@@ -332,7 +336,7 @@ struct DiffractionGrating {
         intensityMultiplier = intensityMult;
     }
     bool is1DGrating() const { return invPitch.y == .0f; }
-    float alpha(float3 wi, float k) const { return std::exp(-sqr(wi.z * q * k)); }
+    float alpha(float3 wi, float k) const { return exp_cr(-sqr(wi.z * q * k)); }
     hwss_t alpha(float3 wi, hwss_t k) const { hwss_t r; for (int j = 0; j < 4; ++j) r[j] = alpha(wi, k[j]); return r; }
     ShadingData localGratingShadingFrame(const ShadingData& sd) const {
         ShadingData g;  // only T,B,N are set, as in the reference (DiffractionGrating.slang:84-91)

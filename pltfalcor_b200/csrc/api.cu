@@ -60,6 +60,7 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     if (!h) return PLTPT_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (auto e : h->timerEvents) cudaEventDestroy(e);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
     delete h;
@@ -79,9 +80,11 @@ extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
 }
 extern "C" int pltpt_reset_stats(PltptHandle h) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int r = syncFrameStats(h)) return r;
     const double b = h->stats.bvhBuildMs;
-    const uint64_t n = h->stats.bvhNodes, l = h->stats.bvhLeafTriangles, t = h->stats.triangleCount;
+    const uint64_t n = h->stats.bvhNodes, l = h->stats.bvhLeafTriangles, t = h->stats.triangleCount, ov = h->stats.traversalStackOverflows;
     h->stats = PltptStats{};
+    h->stats.traversalStackOverflows = ov;
     h->stats.bvhBuildMs = b; h->stats.bvhNodes = n; h->stats.bvhLeafTriangles = l; h->stats.triangleCount = t;
     return PLTPT_OK;
 }

@@ -69,8 +69,10 @@ constexpr int kTraversalStack = 160;
 
 // Walks the compressed wide BVH for one ray.  ANY = true: returns at the first accepted triangle.
 // `overflow` (optional) counts rays whose traversal stack overflowed (must stay 0; checked by the tests).
+struct TraversalCounters { uint32_t nodes, tris; };
 template <bool ANY>
-PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr) {
+PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr,
+                       TraversalCounters* tc = nullptr) {
     best.instanceID = 0xffffffffu;
     best.t = tmax;
     const RayPrep rp = prepRay(o, d);
@@ -78,39 +80,46 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
     const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
     const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
     const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
     uint32_t stack[kTraversalStack];
     int sp = 0;
     stack[sp++] = 0;
     while (sp > 0) {
         const uint32_t ni = stack[--sp];
+        if (tc) ++tc->nodes;
         const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
         const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-        const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
-        const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
         const uint32_t imask = n0.w >> 24;
         const uint32_t childBase = n1.x, triBase = n1.y;
         const uint32_t metaLo = n1.z, metaHi = n1.w;
-        // quantised planes: n2 = qlox[0..7] (x,y) qloy[0..7] (z,w); n3 = qloz, qhix; n4 = qhiy, qhiz
+        // Slab distances in one FMA per plane: t = q * (s * id) + (p - o) * id.  The library is built with -fmad=false
+        // (fp32 parity of the shading math with the oracle), so the traversal asks for its FMAs explicitly.
+        // Error bound of a plane distance: 4u (|(p-o) id| + 255 |s id|), u = 2^-24; it is folded into the two per-axis
+        // offsets (near planes pulled in, far planes pushed out), so the test stays conservative at no per-child cost.
+        const float sxi = __uint_as_float((n0.w & 0xffu) << 23) * idx, syi = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * idy, szi = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * idz;
+        const float pxi = (__uint_as_float(n0.x) - o.x) * idx, pyi = (__uint_as_float(n0.y) - o.y) * idy, pzi = (__uint_as_float(n0.z) - o.z) * idz;
+        const float ex = 3e-7f * fmaf(255.f, fabsf(sxi), fabsf(pxi)), ey = 3e-7f * fmaf(255.f, fabsf(syi), fabsf(pyi)), ez = 3e-7f * fmaf(255.f, fabsf(szi), fabsf(pzi));
+        const float pxn = pxi - ex, pxf = pxi + ex, pyn = pyi - ey, pyf = pyi + ey, pzn = pzi - ez, pzf = pzi + ez;
+        // quantised planes: n2 = qlox[0..7] (x,y) qloy[0..7] (z,w); n3 = qloz, qhix; n4 = qhiy, qhiz.  Per axis the plane
+        // the ray enters through is `lo` for a positive direction component and `hi` for a negative one.
+        const uint32_t nxA = negx ? n3.z : n2.x, nxB = negx ? n3.w : n2.y, fxA = negx ? n2.x : n3.z, fxB = negx ? n2.y : n3.w;
+        const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
+        const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
         float nearT[8];
         uint32_t innerHits = 0;
-        // the slab test is done against the ray segment [tmin, best.t] widened by a few ulps (conservative)
-        const float tfarLimit = best.t * 1.0000004f;
+        // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
+        const float tfarLimit = best.t * 1.000002f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xffu;
             const bool inner = (imask >> i) & 1u;
             if (meta == 0 && !inner) continue;
             const int sh = (i & 3) * 8;
-            const uint32_t wlx = i < 4 ? n2.x : n2.y, wly = i < 4 ? n2.z : n2.w, wlz = i < 4 ? n3.x : n3.y;
-            const uint32_t whx = i < 4 ? n3.z : n3.w, why = i < 4 ? n4.x : n4.y, whz = i < 4 ? n4.z : n4.w;
-            const float lox = px + float((wlx >> sh) & 0xffu) * sx, hix = px + float((whx >> sh) & 0xffu) * sx;
-            const float loy = py + float((wly >> sh) & 0xffu) * sy, hiy = py + float((why >> sh) & 0xffu) * sy;
-            const float loz = pz + float((wlz >> sh) & 0xffu) * sz, hiz = pz + float((whz >> sh) & 0xffu) * sz;
-            const float ax = (lox - o.x) * idx, bx = (hix - o.x) * idx;
-            const float ay = (loy - o.y) * idy, by = (hiy - o.y) * idy;
-            const float az = (loz - o.z) * idz, bz = (hiz - o.z) * idz;
-            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin)) * 0.9999996f;
-            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tfarLimit)) * 1.0000004f;
+            const float tnx = fmaf(float(((i < 4 ? nxA : nxB) >> sh) & 0xffu), sxi, pxn), tfx = fmaf(float(((i < 4 ? fxA : fxB) >> sh) & 0xffu), sxi, pxf);
+            const float tny = fmaf(float(((i < 4 ? nyA : nyB) >> sh) & 0xffu), syi, pyn), tfy = fmaf(float(((i < 4 ? fyA : fyB) >> sh) & 0xffu), syi, pyf);
+            const float tnz = fmaf(float(((i < 4 ? nzA : nzB) >> sh) & 0xffu), szi, pzn), tfz = fmaf(float(((i < 4 ? fzA : fzB) >> sh) & 0xffu), szi, pzf);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
             if (!(tn <= tf)) continue;
             if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
             else {
@@ -119,6 +128,7 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
                     const float4* tp = reinterpret_cast<const float4*>(tris + first + k);
                     const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                     float t, u, v;
+                    if (tc) ++tc->tris;
                     if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
                     if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
                     const uint32_t g = __float_as_uint(q2.w);

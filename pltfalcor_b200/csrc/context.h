@@ -87,7 +87,10 @@ struct PltptContext {
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};
     bool statsDirty = false;
-    uint64_t traversalOverflows = 0, mneeIterations = 0;
+    static constexpr uint32_t kTimerRing = 256;
+    std::vector<cudaEvent_t> timerEvents;  // kTimerRing x {start, after sample stage, after solve stage}
+    uint32_t timerCount = 0;
+    cudaStream_t timerStream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
 };
 

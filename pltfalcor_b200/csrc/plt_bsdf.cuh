@@ -244,10 +244,14 @@ PLT_D Beam sourceBeamArea(float3 posW, float3 dir, float A, float dist, float4 L
 }
 
 // ---- surfaces ------------------------------------------------------------------------------
+// Delta-lobe energies `alpha = exp(-x)` feed `1 - alpha`, which cancels catastrophically for near-smooth surfaces: a 1-ulp
+// difference in exp becomes an O(1) relative difference of the scattered lobe.  Parity therefore needs the correctly rounded
+// fp32 value here (double-precision exp rounded once); every other exp in the path uses the fast fp32 expf.
+PLT_D float exp_cr(float x) { return float(exp(double(x))); }
 // FractalSurface.slang:38-135 with T, gamma, q pre-evaluated
 struct Fractal {
     float T, gamma, q;
-    PLT_D float alpha(float3 wi, float3 wo, float k) const { return expf(-sqr((fabsf(wi.z) + fabsf(wo.z)) * q * k)); }
+    PLT_D float alpha(float3 wi, float3 wo, float k) const { return exp_cr(-sqr((fabsf(wi.z) + fabsf(wo.z)) * q * k)); }
     PLT_D float4 alpha4(float3 wi, float3 wo, float4 k) const { return mk4(alpha(wi, wo, k.x), alpha(wi, wo, k.y), alpha(wi, wo, k.z), alpha(wi, wo, k.w)); }
     PLT_D bool isDeltaOnly() const { return q == .0f; }
     PLT_D float pGF(float2 z) const { return k1_2Pi * (gamma - 1) * T * (1.f / powf(1 + T * dot(z, z), (gamma + 1.f) / 2.f)); }
@@ -275,7 +279,7 @@ struct Fractal {
 struct Gaussian {
     float sigma2, q;
     PLT_D bool isDeltaOnly() const { return q == .0f; }
-    PLT_D float alpha(float3 wi, float3 wo, float k) const { return isDeltaOnly() ? 1.f : expf(-sqr((fabsf(wi.z) + fabsf(wo.z)) * q * k)); }
+    PLT_D float alpha(float3 wi, float3 wo, float k) const { return isDeltaOnly() ? 1.f : exp_cr(-sqr((fabsf(wi.z) + fabsf(wo.z)) * q * k)); }
     PLT_D float4 alpha4(float3 wi, float3 wo, float4 k) const { return mk4(alpha(wi, wo, k.x), alpha(wi, wo, k.y), alpha(wi, wo, k.z), alpha(wi, wo, k.w)); }
     PLT_D float3 sample(float3 wi, Rng& sg, float k, float& pdf) const {
         const float s2 = (1.f / sigma2) / sqr(k);
@@ -781,7 +785,7 @@ struct Grating {
     int lobeCount;
     uint32_t type;
     PLT_D bool is1D() const { return invPitch.y == .0f; }
-    PLT_D float alpha(float3 wi, float k) const { return expf(-sqr(wi.z * q * k)); }
+    PLT_D float alpha(float3 wi, float k) const { return exp_cr(-sqr(wi.z * q * k)); }
     PLT_D float4 alpha4(float3 wi, float4 k) const { return mk4(alpha(wi, k.x), alpha(wi, k.y), alpha(wi, k.z), alpha(wi, k.w)); }
     PLT_D float intensity1(int l, float a) const {
         const uint32_t gt = type & 0xF;

@@ -28,7 +28,8 @@ struct FrameParams {
     float4* albedo;
     float4* normal;
     double* accum;     // RGBA64F running sums (may be null)
-    unsigned long long* counters;  // [0] bsdf evals x wavelengths, [1] recorded vertices, [2] traversal stack overflows, [3] mnee iterations
+    unsigned long long* counters;  // [0] bsdf evals x wavelengths, [1] recorded vertices, [2] traversal stack overflows, [3] mnee iterations,
+                                   // [4] sum L(L-1)/2, [5] BVH nodes visited, [6] triangles tested
     // derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
     bool useEmissive, useAnalytic, doNEE, doMS, doMIS, perTileSG;
 };
@@ -60,16 +61,16 @@ PLT_D Bounce readBounce(const FrameParams& P, uint32_t pixel, int p) {
 
 // ---- rays ------------------------------------------------------------------------------------------------------
 constexpr float kShadowRayTMin = 1e-4f;
-PLT_D bool traceClosestHit(const FrameParams& P, float3 o, float3 d, float tmin, float tmax, TriHit& th, float& t) {
+PLT_D bool traceClosestHit(const FrameParams& P, TraversalCounters& tc, float3 o, float3 d, float tmin, float tmax, TriHit& th, float& t) {
     Hit h;
-    const bool hit = traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, tmin, tmax, h, reinterpret_cast<uint32_t*>(P.counters + 2));
+    const bool hit = traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, tmin, tmax, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
     th.instanceID = h.instanceID; th.primitiveIndex = h.primitiveIndex; th.u = h.u; th.v = h.v;
     t = h.t;
     return hit;
 }
-PLT_D bool occluded(const FrameParams& P, float3 o, float3 d, float tmin, float tmax) {
+PLT_D bool occluded(const FrameParams& P, TraversalCounters& tc, float3 o, float3 d, float tmin, float tmax) {
     Hit h;
-    return traverseBvh<true>(P.sc.bvhNodes, P.sc.bvhTris, o, d, tmin, tmax, h, reinterpret_cast<uint32_t*>(P.counters + 2));
+    return traverseBvh<true>(P.sc.bvhNodes, P.sc.bvhTris, o, d, tmin, tmax, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
 }
 // ShadowRays.slangh:50-52
 PLT_D float3 shadowRayOrigin(const SD& sd, float3 rayDir) { return computeRayOrigin(sd.posW, dot(sd.faceN, rayDir) >= .0f ? sd.faceN : -sd.faceN); }
@@ -82,6 +83,7 @@ struct PathState {  // Path.slang:146-196
     uint32_t flags;
     int length;
     float lastNonDeltaPdf;
+    TraversalCounters tc;
 };
 // Camera.slang:46-78 (computeRayPinhole)
 PLT_D void cameraRay(const FrameParams& P, uint32_t px, uint32_t py, float3& origin, float3& dir) {
@@ -145,9 +147,10 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     path.dir = bs.wo;
 }
 // pltpt_sample.rt.slang:146-185 (raygen)
-PLT_D void samplePixel(const FrameParams& P, uint32_t px, uint32_t py) {
+PLT_D TraversalCounters samplePixel(const FrameParams& P, uint32_t px, uint32_t py) {
     const uint32_t pixel = py * P.width + px;
     PathState path;
+    path.tc.nodes = path.tc.tris = 0;
     path.sg = Rng::seed(px, py, P.frameCount);
     path.wavelength = sampleHeroWavelength(path.sg.next1D());
     if (P.normal) P.normal[pixel] = mk4(0.f);
@@ -160,11 +163,12 @@ PLT_D void samplePixel(const FrameParams& P, uint32_t px, uint32_t py) {
     for (path.length = 0; path.length < int(P.opt.maxBounces) + 1 && (path.flags & (RF_Miss | RF_Terminated)) == 0 && guard < 4096; ++guard) {
         TriHit th;
         float t;
-        if (!traceClosestHit(P, path.origin, path.dir, 0.f, kFltMax, th, t)) {
+        if (!traceClosestHit(P, path.tc, path.origin, path.dir, 0.f, kFltMax, th, t)) {
             path.flags |= RF_Miss;
             writeBounce(P, pixel, path.length, make_uint4(0, 0, 0, 0), -path.dir, 0u, path.flags, 1.f / (path.pdf * path.thp), path.lastNonDeltaPdf);
         } else scatterClosestHit(P, pixel, path, th);
     }
+    return path.tc;
 }
 
 // ---- light sampling (LightSampling.slangh, Rendering/Lights/*.slang) ---------------------------------------------
@@ -414,6 +418,7 @@ struct SolveState {
     float3 Lrgb, pathOrigin;
     float wavelength;
     uint32_t evals;
+    TraversalCounters tc;
 };
 // pltpt_solve.rt.slang:48-66 (forwardUnwindStep)
 PLT_D void forwardUnwindStep(const FrameParams& P, SolveState& st, const VertexData& v, uint32_t materialID, float3 wo, uint32_t lobe, Beam& beam) {
@@ -512,12 +517,12 @@ PLT_D bool manifoldSampleVertex(uint4 hitInfo, const SD& sd, const DevMaterial& 
     return true;
 }
 // Manifolds.slangh:110-160
-PLT_D bool traceMNEEOccluders(const FrameParams& P, float3 rayOrigin, float3 rayDir, float rayTMin, float rayTMax, Rng& sg, int maxMSBounces, ManifoldSampleData& data) {
+PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float3 rayOrigin, float3 rayDir, float rayTMin, float rayTMax, Rng& sg, int maxMSBounces, ManifoldSampleData& data) {
     const float3 wi = -rayDir;
     for (;;) {
         TriHit th;
         float t;
-        if (!traceClosestHit(P, rayOrigin, rayDir, rayTMin, rayTMax, th, t)) return true;
+        if (!traceClosestHit(P, tc, rayOrigin, rayDir, rayTMin, rayTMax, th, t)) return true;
         if (data.hitCount >= int(P.opt.MNEEMaxOccluders) || data.hitCount >= maxMSBounces) return false;
         uint32_t materialID;
         VertexData v = getVertexData(P.sc, th, materialID);
@@ -559,9 +564,9 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
 }
 // Manifolds.slangh:165-281.  Kept out of line: its data-dependent Newton loop must not inflate the register budget of
 // the straight NEE path.
-__device__ __noinline__ bool manifoldNEESample(const FrameParams& P, float3 visOrigin, float3 visDir, float visTMax, float3 origin, float3 lightPos, float3 lightDir,
+__device__ __noinline__ bool manifoldNEESample(const FrameParams& P, TraversalCounters& tc, float3 visOrigin, float3 visDir, float visTMax, float3 origin, float3 lightPos, float3 lightDir,
                                                bool isDistantLight, int maxMSBounces, Rng& sg, ManifoldSampleData& data) {
-    if (!traceMNEEOccluders(P, visOrigin, visDir, 0.f, visTMax, sg, maxMSBounces, data)) return false;
+    if (!traceMNEEOccluders(P, tc, visOrigin, visDir, 0.f, visTMax, sg, maxMSBounces, data)) return false;
     if (data.hitCount == 0) return true;
     float beta[kMaxMSHits];
     for (int i = 0; i < kMaxMSHits; ++i) beta[i] = 1.f;
@@ -599,7 +604,7 @@ __device__ __noinline__ bool manifoldNEESample(const FrameParams& P, float3 visO
                 dirToProposal /= dist;
                 TriHit ph;
                 float pt;
-                const bool isHit = traceClosestHit(P, p0, dirToProposal, fmaxf(kShadowRayTMin, .99f * dist), 1.01f * dist, ph, pt);
+                const bool isHit = traceClosestHit(P, tc, p0, dirToProposal, fmaxf(kShadowRayTMin, .99f * dist), 1.01f * dist, ph, pt);
                 if (!isHit || th.instanceID != ph.instanceID) { beta[idx] /= 4.f; continue; }
                 data.hits[idx].hit = packHit(P.sc, ph);
                 data.hits[idx].posW = p0 + dirToProposal * pt;
@@ -614,7 +619,7 @@ __device__ __noinline__ bool manifoldNEESample(const FrameParams& P, float3 visO
     if (!isDistantLight) { dir = lightPos - p; dist = length(dir); dir /= dist; }
     else { dir = lightDir; dist = kFltMax; }
     data.woLastHitToLight = dir;
-    return !occluded(P, p, dir, kShadowRayTMin, dist);
+    return !occluded(P, tc, p, dir, kShadowRayTMin, dist);
 }
 // Manifolds.slangh:80-93
 PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const ManifoldSampleData& r, float3 origin, Beam& beam) {
@@ -643,7 +648,7 @@ PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceI
     bool evalCurrentVertex = true;
     const int maxMSBounces = int(P.opt.maxBounces) - bounceIdx;
     if (!P.doMS || maxMSBounces <= 0) {
-        if (occluded(P, ls.origin, ls.dir, .0f, ls.distance)) return;
+        if (occluded(P, st.tc, ls.origin, ls.dir, .0f, ls.distance)) return;
         if (doMis) ls.beam.scale(misWeight(ls.pdf, bsdfPdf(m, sd, ls.dir, ls.beam.wl.x)));
     } else {
         const float3 lightDir = -ls.beam.r;
@@ -657,7 +662,7 @@ PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceI
             if (!manifoldSampleVertex(bounce.hit, sd, m, lightDir, st.sg, ms) || (ms.hits[0].lobe & L_Reflection) == 0) return;
         }
         const float3 origin = !currentVertexMS ? V.posW : st.pathOrigin;
-        const bool ok = manifoldNEESample(P, ls.origin, ls.dir, ls.distance, origin, ls.beam.posW, lightDir, ls.beam.distant, maxMSBounces, st.sg, ms);
+        const bool ok = manifoldNEESample(P, st.tc, ls.origin, ls.dir, ls.distance, origin, ls.beam.posW, lightDir, ls.beam.distant, maxMSBounces, st.sg, ms);
         if (P.counters && ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)ms.iterations);
         if (!ok || ms.pdf < 1e-6f) return;
         if (ms.hitCount > 0) {
@@ -691,7 +696,7 @@ PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceI
 }
 
 // pltpt_solve.rt.slang:401-476 (raygen).  Returns the number of recorded vertices; `evals` = eval calls x wavelengths.
-PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32_t& evals) {
+PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32_t& evals, TraversalCounters& tc) {
     const uint32_t pixel = py * P.width + px;
     SolveState st;
     st.sg = Rng::seed(px, py, P.frameCount);
@@ -700,6 +705,7 @@ PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32
     st.Lrgb = mk3(0.f);
     st.pathOrigin = P.camPos;
     st.evals = 0;
+    st.tc.nodes = st.tc.tris = 0;
     int p = 0;
     for (;; ++p) {
         const Bounce bounce = readBounce(P, pixel, p);
@@ -720,6 +726,7 @@ PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32
         a[0] += double(st.Lrgb.x); a[1] += double(st.Lrgb.y); a[2] += double(st.Lrgb.z); a[3] += 1.0;
     }
     evals = st.evals;
+    tc = st.tc;
     return uint32_t(p);
 }
 

@@ -151,4 +151,8 @@ class PltptStats(C.Structure):
         ("kernelLaunches", C.c_uint64), ("raysClosest", C.c_uint64), ("raysAny", C.c_uint64),
         ("bvhNodes", C.c_uint64), ("bvhLeafTriangles", C.c_uint64), ("triangleCount", C.c_uint64),
         ("pathVertices", C.c_uint64), ("bsdfEvals", C.c_uint64), ("bvhBuildMs", C.c_double),
+        ("traversalStackOverflows", C.c_uint64), ("mneeIterations", C.c_uint64),
+        ("framesRendered", C.c_uint64), ("sampleStageMs", C.c_double), ("solveStageMs", C.c_double),
+        ("totalPathVertices", C.c_uint64), ("totalReplaySteps", C.c_uint64), ("totalBsdfEvals", C.c_uint64),
+        ("traversalNodesVisited", C.c_uint64), ("traversalTrianglesTested", C.c_uint64),
     ]

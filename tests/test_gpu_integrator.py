@@ -1,0 +1,222 @@
+"""Integrator parity (north-star level 3 and the wavefront stages): bounce records of the sample stage, single-frame RGB of
+the solve stage, guide buffers, and converged images (3 sigma against an independent high-spp oracle render, relMSE stated)."""
+import numpy as np
+import pytest
+
+from pltfalcor_b200 import layouts as L
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(name):
+    from pltfalcor_b200 import scene
+    return {"cornell": scene.cornell_box, "grating_sphere": scene.grating_sphere_scene, "layered": scene.layered_stress_scene}[name]()
+
+
+@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered"])
+def loaded(request, torch_cuda, oracle):
+    from pltfalcor_b200 import binding
+    buffers, cam = _scene(request.param)
+    p = binding.Pltpt(maxBounces=8)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    yield request.param, buffers, cam, p, osc
+    p.close()
+
+
+W, H = 96, 54
+
+
+def test_sample_stage_bounce_records(loaded):
+    """Hit IDs, lobes and flags identical for (nearly) every path; floats of identical paths within fp32 noise.
+    Paths may legitimately fork where a random number falls within rounding of a branch threshold."""
+    from pltfalcor_b200 import scene
+    name, buffers, cam, p, osc = loaded
+    for frame in (0, 5):
+        c = scene.with_jitter(cam, frame, W, H)
+        gpu = p.sample_stage_host(c, frame, W, H)
+        cpu = osc.render_frame(p.options, c, frame, W, H, solve=False, want_bounces=True)["bounces"]
+        m, same = parity.compare_bounces(gpu, cpu)
+        assert m["identical_paths"] >= 0.97, (name, m)
+        assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3, (name, m)
+        assert m["max_contribution_rel"] <= 5e-3, (name, m)
+    assert p.stats()["traversalStackOverflows"] == 0
+
+
+def test_single_frame_rgb_and_guides(loaded):
+    from pltfalcor_b200 import scene
+    name, buffers, cam, p, osc = loaded
+    frame = 2
+    c = scene.with_jitter(cam, frame, W, H)
+    gpu_b = p.sample_stage_host(c, frame, W, H)
+    gpu = p.render_frame_host(c, frame, W, H)
+    cpu = osc.render_frame(p.options, c, frame, W, H, want_bounces=True)
+    _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
+    m = parity.compare_color(gpu["color"], cpu["color"], same)
+    assert m["nonfinite_gpu"] == 0
+    assert (gpu["color"][..., 3] == 1).all() and (gpu["color"][..., :3] >= 0).all()
+    # per-path radiance is a product of up to ~40 BSDF evaluations each good to 1e-4; MNEE paths amplify rounding further
+    assert m["frac_pixels_within_1e-2"] >= 0.97, (name, m)
+    assert m["mean_rel_diff"] <= 0.02, (name, m)
+    # guide buffers: albedo / view-space normal at the first non-delta vertex
+    for k in ("albedo", "normal"):
+        d = np.abs(gpu[k] - cpu[k]).max(axis=-1)
+        assert (d[same] <= 2e-3).mean() >= 0.995, (name, k)
+    s = p.stats()
+    assert s["pathVertices"] > 0 and s["bsdfEvals"] > 0
+    assert abs(s["bsdfEvals"] - cpu["evals"]) <= 0.03 * cpu["evals"], (s["bsdfEvals"], cpu["evals"])
+
+
+@pytest.mark.parametrize("opts", [
+    dict(doMNEE=False), dict(doMIS=False), dict(doNEE=False), dict(HWSSDoMIS=False), dict(HWSS=1), dict(doRussianRoulette=False),
+    dict(emissiveSampler=0), dict(doImportanceSampleEmitters=False), dict(useDirectLights=False), dict(NEEUsePerTileSG=True, tileSize=16), dict(maxBounces=3),
+])
+def test_option_variants_match_oracle(torch_cuda, oracle, opts):
+    """Every pass property that changes the light transport is honoured the same way (cornell box, one frame)."""
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = _scene("cornell")
+    kw = dict(maxBounces=6)
+    kw.update(opts)
+    p = binding.Pltpt(**kw)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    w, h, frame = 64, 36, 1
+    c = scene.with_jitter(cam, frame, w, h)
+    gpu_b = p.sample_stage_host(c, frame, w, h)
+    gpu = p.render_frame_host(c, frame, w, h)
+    cpu = osc.render_frame(p.options, c, frame, w, h, want_bounces=True)
+    _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
+    m = parity.compare_color(gpu["color"], cpu["color"], same)
+    assert same.mean() >= 0.97, (opts, same.mean())
+    assert m["frac_pixels_within_1e-2"] >= 0.97 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    p.close()
+
+
+def test_polarizing_camera(torch_cuda, oracle):
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = _scene("cornell")
+    cam = L.PltptCameraData.from_buffer_copy(bytes(cam))
+    cam.polarizer, cam.polarizerTheta = 0.8, 0.6
+    p = binding.Pltpt(maxBounces=4)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    gpu = p.render_frame_host(cam, 0, 64, 36)
+    cpu = osc.render_frame(p.options, cam, 0, 64, 36)
+    m = parity.compare_color(gpu["color"], cpu["color"], np.ones((36, 64), bool))
+    assert m["frac_pixels_within_1e-2"] >= 0.95 and m["mean_rel_diff"] <= 0.03, m
+    p.close()
+
+
+def test_converged_image_within_3_sigma(loaded, torch_cuda):
+    """GPU render (frames 0..N-1) vs an INDEPENDENT oracle render (frames 1000..1000+M-1): per pixel, the means must agree
+    within 3 sigma of the combined standard error; relMSE (ImageCompare.cpp:198-207) is reported."""
+    from pltfalcor_b200 import scene
+    name, buffers, cam, p, osc = loaded
+    w, h = 48, 27
+    n_gpu, n_cpu = 512, 192
+    torch = torch_cuda
+    col = torch.zeros((h, w, 4), device="cuda")
+    s1 = np.zeros((h, w, 3)); s2 = np.zeros((h, w, 3))
+    for f in range(n_gpu):
+        p.render_frame(scene.with_jitter(cam, f, w, h), f, w, h, col)
+        x = col[..., :3].double().cpu().numpy()
+        s1 += x; s2 += x * x
+    mean_g = s1 / n_gpu
+    var_g = np.maximum(s2 / n_gpu - mean_g ** 2, 0) * n_gpu / (n_gpu - 1)
+    t1 = np.zeros((h, w, 3)); t2 = np.zeros((h, w, 3))
+    for f in range(1000, 1000 + n_cpu):
+        x = osc.render_frame(p.options, scene.with_jitter(cam, f, w, h), f, w, h)["color"][..., :3].astype(np.float64)
+        t1 += x; t2 += x * x
+    mean_c = t1 / n_cpu
+    var_c = np.maximum(t2 / n_cpu - mean_c ** 2, 0) * n_cpu / (n_cpu - 1)
+    sigma = np.sqrt(var_g / n_gpu + var_c / n_cpu)
+    # firefly-dominated pixels have unreliable variance estimates at these sample counts: floor sigma at 2 % of the image mean
+    sigma = np.maximum(sigma, 0.02 * mean_c.mean())
+    z = np.abs(mean_g - mean_c) / sigma
+    frac = float((z <= 3.0).mean())
+    relmse = parity.rel_mse(mean_g, mean_c)
+    print(f"[{name}] within-3sigma fraction {frac:.4f}, relMSE {relmse:.4e}, mean gpu {mean_g.mean():.5f} cpu {mean_c.mean():.5f}")
+    assert frac >= 0.985, (name, frac, relmse)
+    assert abs(mean_g.mean() - mean_c.mean()) <= 0.05 * mean_c.mean() + 3 * np.sqrt((sigma ** 2).mean() / sigma.size), (name, mean_g.mean(), mean_c.mean())
+
+
+def test_frames_are_deterministic_and_partitionable(torch_cuda, cornell):
+    """Sample-index partitioning: frames {0..7} == frames {0,2,4,6} + {1,3,5,7}; same frame twice == same bits."""
+    from pltfalcor_b200 import binding
+    torch = torch_cuda
+    buffers, cam = cornell
+    p = binding.Pltpt(maxBounces=8)
+    p.set_scene(buffers)
+    w, h = 128, 72
+    a = torch.zeros((h, w, 4), device="cuda"); b = torch.zeros_like(a)
+    p.render_frame(cam, 7, w, h, a); p.render_frame(cam, 7, w, h, b)
+    assert torch.equal(a, b)
+    full = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    even = torch.zeros_like(full); odd = torch.zeros_like(full)
+    p.render_accumulate(cam, 0, 1, 8, w, h, full)
+    p.render_accumulate(cam, 0, 2, 4, w, h, even)
+    p.render_accumulate(cam, 1, 2, 4, w, h, odd)
+    torch.cuda.synchronize()
+    assert (full[..., 3] == 8).all()
+    assert torch.allclose(full, even + odd, rtol=1e-12, atol=0)
+    # accumulate of one frame == that frame (with the Halton jitter GBufferRT would set)
+    from pltfalcor_b200 import scene
+    one = torch.zeros_like(full)
+    p.render_accumulate(cam, 3, 1, 1, w, h, one)
+    p.render_frame(scene.with_jitter(cam, 3, w, h), 3, w, h, a)
+    assert torch.equal(one[..., :3].float(), a[..., :3])
+    p.close()
+
+
+def test_full_hd_frame_properties(torch_cuda, cornell):
+    """BASELINE config 2 size (1920x1080, depth 8): size-independent properties — finite, non-negative, alpha 1, every pixel's
+    first record is a hit or a miss, bounce chains are well formed, mean radiance agrees with a low-res render of the same frame set."""
+    from pltfalcor_b200 import binding, scene
+    torch = torch_cuda
+    buffers, cam = cornell
+    p = binding.Pltpt(maxBounces=8)
+    p.set_scene(buffers)
+    w, h = 1920, 1080
+    acc = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 4, w, h, acc)
+    torch.cuda.synchronize()
+    img = (acc[..., :3] / 4).cpu().numpy()
+    assert np.isfinite(img).all() and (img >= 0).all() and (acc[..., 3] == 4).all()
+    small = torch.zeros((135, 240, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 64, 240, 135, small)
+    ms = float((small[..., :3] / 64).mean())
+    assert abs(img.mean() - ms) <= 0.1 * ms, (img.mean(), ms)
+    s = p.stats()
+    assert s["traversalStackOverflows"] == 0
+    assert 1.0 <= s["pathVertices"] / (240 * 135) <= 9.0
+    b = p.sample_stage_host(cam, 0, 320, 180)
+    ended = (b["flags"] & 0x30) != 0
+    assert ended.any(-1).all(), "every path must end with a miss or a terminated record within maxBounces+1 records"
+    p.close()
+
+
+def test_render_errors(torch_cuda, cornell):
+    from pltfalcor_b200 import binding
+    buffers, cam = cornell
+    p = binding.Pltpt()
+    col = torch_cuda.zeros((4, 4, 4), device="cuda")
+    with pytest.raises(binding.PltptError) as e:
+        p.render_frame(cam, 0, 4, 4, col)
+    assert e.value.code == 4
+    p.set_scene(buffers)
+    with pytest.raises(binding.PltptError) as e:
+        p.render_frame(cam, 0, 0, 4, col)
+    assert e.value.code == 1
+    with pytest.raises(binding.PltptError) as e:
+        p.render_frame(cam, 0, 4, 4, None)
+    assert e.value.code == 1
+    # textured material handles are rejected loudly (Uniform handles only)
+    bad = type(buffers)(dict(buffers.arrays), dict(buffers.scalars))
+    mats = buffers.arrays["materialData"].copy()
+    mats["tex"][0, 0] = 1 << 29
+    bad.arrays["materialData"] = mats
+    with pytest.raises(binding.PltptError) as e:
+        p.set_scene(bad)
+    assert e.value.code == 3
+    p.close()
