@@ -375,6 +375,7 @@ typedef struct PltptStats {
     uint64_t totalReplaySteps;                 /* sum over paths of L(L-1)/2: forward-replay vertex fetches of the NEE connections */
     uint64_t totalBsdfEvals;                   /* eval calls x wavelengths */
     uint64_t traversalNodesVisited, traversalTrianglesTested; /* BVH work of both stages */
+    uint64_t droppedConnections;               /* connection jobs that did not fit the job buffer (must stay 0) */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);

@@ -18,7 +18,7 @@ inline void fresnel_dielectric(float cosThetaI_, float eta, float& rs, float& rp
     eta = (cosThetaI_ > 0) ? eta : 1 / eta;
     const float cosThetaI = std::fabs(cosThetaI_);
     const float cosThetaTSqr = 1 - (1 - sqr(cosThetaI)) / sqr(eta);
-    cosThetaT = std::sqrt(std::max(.0f, cosThetaTSqr));
+    cosThetaT = std::sqrt(hlsl_max(.0f, cosThetaTSqr));
     rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
     rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
     const float imp = std::sqrt(eta * cosThetaT / cosThetaI);
@@ -242,13 +242,13 @@ struct PLTBeam {
 
 // PLT.slang:253-290
 inline PLTBeam pltSourceBeamDistant(float3 dir, float solidAngle, hwss_t Le, hwss_t wavelengths, float maxBeamOmega, bool forceFullyCoherent, uint32_t comps) {
-    solidAngle = std::min(solidAngle, maxBeamOmega);
+    solidAngle = hlsl_min(solidAngle, maxBeamOmega);
     const float2x2 Diffusivity = forceFullyCoherent ? 1e-9f * ident2() : solidAngle * ident2();
     return PLTBeam(Le, Diffusivity, float3(.0f), dir, perp_stark(dir), wavelengths, true, comps);
 }
 inline PLTBeam pltSourceBeamArea(float3 posW, float3 dir, float A, float dist, hwss_t Le, hwss_t wavelengths, float maxBeamOmega, bool forceFullyCoherent, uint32_t comps) {
     const float r2 = sqr(dist * 1e+3f);
-    A = std::min(A, maxBeamOmega * r2);
+    A = hlsl_min(A, maxBeamOmega * r2);
     const float2x2 Diffusivity = forceFullyCoherent ? 1e-7f * ident2() : A * ident2();
     return PLTBeam(Le, Diffusivity, posW, dir, perp_stark(dir), wavelengths, false, comps);
 }

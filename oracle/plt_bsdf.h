@@ -97,7 +97,7 @@ inline float3kpdv refractDerivatives(float3pdv wi, float3pdv n, float eta, float
     const float eta2 = sqr(eta);
     const float dwdun = dot(wi.ddu, n.v), dwdvn = dot(wi.ddv, n.v);
     const float dnduw = dot(n.ddu, wi.v), dndvw = dot(n.ddv, wi.v);
-    const float root = std::sqrt(std::max(.0f, 1.f - eta2 * (1.0f - sqr(wn))));
+    const float root = std::sqrt(hlsl_max(.0f, 1.f - eta2 * (1.0f - sqr(wn))));
     if (root == .0f) return float3kpdv();
     const float dRoot_dLambda = -(1.0f - sqr(wn)) * eta * dEdl / root;
     const float a = eta - eta2 * wn / root;
@@ -118,10 +118,10 @@ struct FractalSurface {
     static float roughnessToT(float alpha) {
         const float maxAlpha = .75f, maxT = 5000.f;
         const float alpha2 = sqr(clampf(alpha, .0f, maxAlpha));
-        return std::min(maxT, (1 - alpha2) / (4.f * sqr(kMeanK) * alpha2));
+        return hlsl_min(maxT, (1 - alpha2) / (4.f * sqr(kMeanK) * alpha2));
     }
     FractalSurface() = default;
-    explicit FractalSurface(float PSDroughness, float g = 3.f) : T(roughnessToT(PSDroughness)), gamma(std::max(1.1f, g)) {}
+    explicit FractalSurface(float PSDroughness, float g = 3.f) : T(roughnessToT(PSDroughness)), gamma(hlsl_max(1.1f, g)) {}
     float roughness() const { return 1.f / std::sqrt(1.f + 4.f * sqr(kMeanK) * T); }
     float q() const { return roughness() * 1.f; }
     float alpha(float3 wi, float3 wo, float k) const { return exp_cr(-sqr((std::fabs(wi.z) + std::fabs(wo.z)) * q() * k)); }
@@ -134,7 +134,7 @@ struct FractalSurface {
     }
     // Holzschuch & Pacanowski 2017 sampling (FractalSurface.slang:97-124); 4 random numbers
     float3 sample(float3 wi, SampleGenerator& sg, float k, float& pdf) const {
-        const float s = std::sqrt(std::max(.0f, 1 - sqr(wi.z)));
+        const float s = std::sqrt(hlsl_max(.0f, 1 - sqr(wi.z)));
         const float phi_i = s > 0 ? std::atan2(wi.y, wi.x) : .0f;
         const float sqrtT = std::sqrt(T);
         const float2 u2d1 = sampleNext2D(sg);
@@ -147,7 +147,7 @@ struct FractalSurface {
         const float2 vf = f * float2(std::cos(phi_f), std::sin(phi_f));
         const float2 zeta = vf;
         const float2 wo = zeta / k - float2(wi.x, wi.y);
-        const float z = std::sqrt(std::max(.0f, 1 - dot(wo, wo)));
+        const float z = std::sqrt(hlsl_max(.0f, 1 - dot(wo, wo)));
         pdf = kPi / phi_max * z * pGF(zeta);
         return float3(wo, signf(wi.z) * z);
     }
@@ -169,7 +169,7 @@ struct GaussianSurface {
         const float s2max = roughnessToSigma2(0.1f);
         const float s2r0 = roughnessToSigma2(.0f);
         q = lerpf(.0f, 1.f, (s2r0 - s2) / (s2r0 - s2max));
-        sigma2 = std::min(s2max, s2);
+        sigma2 = hlsl_min(s2max, s2);
     }
     bool isDeltaOnly() const { return q == .0f; }
     float alpha(float3 wi, float3 wo, float k) const {
@@ -183,7 +183,7 @@ struct GaussianSurface {
         const float s2 = w / sqr(k);
         const float2 mean = -wi.xy();
         const float2 wo = sample_boxmueller_truncated(sampleNext2D(sg), mean, s2, pdf);
-        const float z = std::sqrt(std::max(0.f, 1.f - dot(wo, wo)));
+        const float z = std::sqrt(hlsl_max(0.f, 1.f - dot(wo, wo)));
         return float3(wo, signf(wi.z) * z);
     }
     float pdf(float3 wi, float3 wo, float k) const {
@@ -207,8 +207,8 @@ inline hwss_t phaseShift(float eta, float dist, hwss_t ks) { return vsin(dist * 
 inline float4 interfere(float4 SP1, float4 SP2, float phasor_s, float phasor_p, float coh) {
     const float S1 = (SP1.x + SP1.y) / 2.f, P1 = (SP1.x - SP1.y) / 2.f;
     const float S2 = (SP2.x + SP2.y) / 2.f, P2 = (SP2.x - SP2.y) / 2.f;
-    const float S = S1 + S2 + 2 * std::sqrt(std::max(.0f, S1 * S2)) * phasor_s * coh;
-    const float P = P1 + P2 + 2 * std::sqrt(std::max(.0f, P1 * P2)) * phasor_p * coh;
+    const float S = S1 + S2 + 2 * std::sqrt(hlsl_max(.0f, S1 * S2)) * phasor_s * coh;
+    const float P = P1 + P2 + 2 * std::sqrt(hlsl_max(.0f, P1 * P2)) * phasor_p * coh;
     const float n = SP1.x + SP2.x > 1e-6f ? (S + P) / (SP1.x + SP2.x) : .0f;
     return float4(S + P, S - P, (SP1.z + SP2.z) * n, (SP1.w + SP2.w) * n);
 }
@@ -216,7 +216,7 @@ inline float4 interfere(float4 SP1, float4 SP2, float phasor_s, float phasor_p, 
 inline float3 reflectZ(float3 wi) { return float3(-wi.x, -wi.y, wi.z); }
 inline float2x2 scatterCoherenceTransform(float3 woLocal, uint32_t lobe) {
     const bool isDirect = (lobe & L_Delta) != 0;
-    const float cosTheta = std::sqrt(std::max(1e-2f, std::fabs(woLocal.z)));
+    const float cosTheta = std::sqrt(hlsl_max(1e-2f, std::fabs(woLocal.z)));
     return isDirect ? ident2() : float2x2(cosTheta, .0f, .0f, 1.f / cosTheta);
 }
 inline hwss_t waveNumbers(hwss_t wavelengths) { return k2Pi / (1e-3f * wavelengths); }
@@ -230,7 +230,7 @@ inline float2 qe(float eo, float ee, float3 A, float K) {
     const float e = sqr(ee) - sqr(eo);
     const float k = 1, a = A.x, b = A.y, c = A.z;
     const float G = sqr(b) * e + sqr(eo);
-    const float root = std::sqrt(std::max(0.f, sqr(K) * (sqr(a) * e - sqr(ee)) + sqr(k) * sqr(ee) * G));
+    const float root = std::sqrt(hlsl_max(0.f, sqr(K) * (sqr(a) * e - sqr(ee)) + sqr(k) * sqr(ee) * G));
     return float2((eo * root + c * b * K * e) / G, (-eo * root + c * b * K * e) / G);
 }
 inline float3 E_e(float eo, float3 A, float K, float q) {
@@ -306,8 +306,8 @@ inline void vectors_in_slab(float3 I, float ei, float eo, float ee, float3 A, fl
     Ie = Poynting(qem, Eem, K);
     Ie2 = Poynting(qep, Eep, K);
     const float3 We = normalize(float3(0, qem, -K)), We2 = normalize(float3(0, qep, -K));
-    e_eff = K / std::sqrt(std::max(.0f, 1.f - sqr(We.y)));
-    e_eff2 = K / std::sqrt(std::max(.0f, 1.f - sqr(We2.y)));
+    e_eff = K / std::sqrt(hlsl_max(.0f, 1.f - sqr(We.y)));
+    e_eff2 = K / std::sqrt(hlsl_max(.0f, 1.f - sqr(We2.y)));
 }
 }  // namespace Birefringence
 
@@ -358,7 +358,7 @@ struct DiffractionGrating {
         }
         int lo[2];
         for (int i = 0; i < 2; ++i) {
-            lo[i] = std::min(std::max((int)(l[i] + signf(l[i]) * .5f), -int(lobeCount)), int(lobeCount));
+            lo[i] = hlsl_min(hlsl_max((int)(l[i] + signf(l[i]) * .5f), -int(lobeCount)), int(lobeCount));
             lo[i] = (alpha == .0f && lo[i] == 0) ? int(signf(l[i])) : lo[i];
         }
         lobe.x = lo[0];
@@ -422,7 +422,7 @@ struct DiffractionGrating {
         const float m = (sqr(a) - 1) / (sqr(a * b) - 1);
         const float qq = 1 - sqr(b) * m;
         return (std::fabs(sino.x) <= 1.f && std::fabs(sino.y) <= 1.f)
-                   ? float3(a * std::sqrt(std::max(.0f, qq)), b * std::sqrt(m), std::sqrt(std::max(.0f, 1 - sqr(a) * qq - sqr(b) * m)))
+                   ? float3(a * std::sqrt(hlsl_max(.0f, qq)), b * std::sqrt(m), std::sqrt(hlsl_max(.0f, 1 - sqr(a) * qq - sqr(b) * m)))
                    : float3(.0f);
     }
     float3pdv gratingXpdv(const DifferentialShadingGeometry& dsg) const {
@@ -446,7 +446,7 @@ struct DiffractionGrating {
         const float2 sini = float2(x, y) * invp;
         const float2 sino = lambda * lp - sini;
         const float a = sino.x;
-        const float oneMinusA2 = std::max(.0f, 1 - sqr(a));
+        const float oneMinusA2 = hlsl_max(.0f, 1 - sqr(a));
         const float b = sino.y;
         const float m = -oneMinusA2 / (sqr(a * b) - 1);
         const float qq = 1 - sqr(b) * m;
@@ -465,7 +465,7 @@ struct DiffractionGrating {
         const float dmdv = 2 * a * (a * b * oneMinusA2 * dbdv - dadv * (1 - sqr(b))) / den;
         const float dmdl = 2 * a * (a * b * oneMinusA2 * dbdl - dadl * (1 - sqr(b))) / den;
         float3kpdv ret;
-        ret.v = X.v * (a * sqrtOneM) + Y * (b * sqrtM) + n.v * std::sqrt(std::max(.0f, 1 - sqr(a) * qq - sqr(b) * m));
+        ret.v = X.v * (a * sqrtOneM) + Y * (b * sqrtM) + n.v * std::sqrt(hlsl_max(.0f, 1 - sqr(a) * qq - sqr(b) * m));
         auto deriv = [&](float da, float db, float dm) {
             return X.v * ((qq * da - a * b * (b * dm / 2.f + m * db)) / sqrtOneM) + Y * ((b * dm / 2.f + m * db) / sqrtM) +
                    n.v * ((-2 * a * da * qq - b * (b * dm + 2.f * m * db) + sqr(a) * b * (b * dm + 2.f * m * db)) * c);
@@ -499,7 +499,7 @@ struct DiffuseBxDF {  // PLTDiffuseBSDF.slang:39-95
     float pdf(float3, float3 woLocal, float) const { return cosine_hemisphere_concentric_pdf(woLocal); }
     hwss_t lambdaPdf(float3, float3, uint32_t, const PLTBeam&, hwss_t) const { return hwss_t(1.f); }
     float2x2 coherenceTransform(float3, float3 woLocal, uint32_t) const {
-        const float cosTheta = std::sqrt(std::max(1e-2f, std::fabs(woLocal.z)));
+        const float cosTheta = std::sqrt(hlsl_max(1e-2f, std::fabs(woLocal.z)));
         return float2x2(cosTheta, .0f, .0f, 1.f / cosTheta);
     }
 };
@@ -518,7 +518,7 @@ struct ConductorBxDF {  // PLTConductorBSDF.slang:44-170
         const hwss_t m00 = SpectrumUtils::rgbToSpectrum(specular, beam.wavelengths);
         const float3 h = toLight + toEye;
         const float3 m = normalize(h);
-        const float LdotH = std::max(.0f, dot(toLight, m));
+        const float LdotH = hlsl_max(.0f, dot(toLight, m));
         const hwss_t iorN = prof->evalSpectrum(etaN, beam.wavelengths), iorK = prof->evalSpectrum(etaK, beam.wavelengths);
         for (uint32_t j = 0; j < beam.hwss_comps; ++j) {
             const float4 SP = beam.getSP(j);
@@ -594,7 +594,7 @@ struct DielectricBxDF {  // PLTDielectricBSDF.slang:43-270
         const float scale = wo.z > 0 ? 1 / eta : eta;
         const float2 xy = wo.xy() * scale;
         const float l2 = dot(xy, xy);
-        return l2 > 1 ? float3(.0f) : float3(xy, -signf(wo.z) * std::sqrt(std::max(0.f, 1 - l2)));
+        return l2 > 1 ? float3(.0f) : float3(xy, -signf(wo.z) * std::sqrt(hlsl_max(0.f, 1 - l2)));
     }
     void eval(float3 toLight, float3 toEye, uint32_t lobe, PLTBeam& beam) const {
         const bool isReflection = toLight.z * toEye.z > .0f;
@@ -612,7 +612,7 @@ struct DielectricBxDF {  // PLTDielectricBSDF.slang:43-270
         if (isScatter) {
             const float3 h = toLight + toEyeUp;
             const float3 m = normalize(h);
-            const float LdotH = std::max(0.f, dot(toLight, m));
+            const float LdotH = hlsl_max(0.f, dot(toLight, m));
             const float2x2 Q = beam.Q();
             const float2x2 invTheta = beam.invTheta(1.f);
             for (uint32_t j = 0; j < beam.hwss_comps; ++j) {
@@ -773,7 +773,7 @@ struct ThinDielectricBxDF {  // PLTThinDielectricBSDF.slang:43-200
     float etaAvg = 1.5f, tau = 0, birefringence = 0;
     float3 opticAxis() const {
         const float2 xy = opticAxis_xy;
-        return float3(xy, std::sqrt(std::max(.0f, 1.f - dot(xy, xy))));
+        return float3(xy, std::sqrt(hlsl_max(.0f, 1.f - dot(xy, xy))));
     }
     void handle_birefringence(PLTBeam& beam, float3 wi, hwss_t k) const {
         const float3 OA = opticAxis();
@@ -892,7 +892,7 @@ struct CoatedBxDF {
         const hwss_t m00 = SpectrumUtils::rgbToSpectrum(specular, beam.wavelengths);
         const float3 h = wiIn + woIn;
         const float3 m = normalize(h);
-        const float LdotH = std::max(0.f, dot(wiIn, m));
+        const float LdotH = hlsl_max(0.f, dot(wiIn, m));
         const float3 Z = beam.toLocal(float3(0, 0, 1));
         const hwss_t mutual_coh = beam.mutualCoherence(k, tau * Z);
         const float4x4 MiT = MuellerFresnelTDielectric(toLight.z, eta1);
@@ -1007,7 +1007,7 @@ struct GratedBxDF {
     DiffractionGrating grating;
     static void encodeLobeType(int2 lobe, uint32_t& bsdfLobe) {
         const int sx = lobe.x < 0 ? 0 : 1, sy = lobe.y < 0 ? 0 : 1;
-        const int lx = std::min(std::abs(lobe.x), 7), ly = std::min(std::abs(lobe.y), 7);
+        const int lx = hlsl_min(std::abs(lobe.x), 7), ly = hlsl_min(std::abs(lobe.y), 7);
         bsdfLobe &= ~uint32_t(L_MaterialSpecific);
         bsdfLobe += uint32_t((ly << 3) + lx + (sy << 7) + (sx << 6)) << LobeTypeMaterialSpecificOffset;
     }
@@ -1123,7 +1123,9 @@ struct MultiLayeredStackBxDF {  // PLTMultiLayeredStackBSDF.slang:42-140
     uint32_t layers = 0;
     static float2 phasor(float cosThetaT, float thickness, float eta, float k) {
         const float d = 2.f * thickness / cosThetaT * k * eta;
-        return float2(std::cos(d), std::sin(d));
+        // Airy summation over the layers is an interference sum: near anti-reflection the result cancels to ~1e-4 of its terms,
+        // so the phase factor is DEFINED as the correctly rounded fp32 cos/sin (evaluated in double), like exp_cr above.
+        return float2(float(std::cos(double(d))), float(std::sin(double(d))));
     }
     void eval(float3 toLight, float3 toEye, uint32_t lobe, PLTBeam& beam) const {
         const bool isReflection = toLight.z * toEye.z > .0f;
@@ -1217,7 +1219,7 @@ struct MaterialInstance {
                 const float dispersionB = (tran.x > .0f || tran.y > .0f || tran.z > .0f) ? spec.x : .0f;
                 dielectric.specular = base.xyz(); dielectric.transmission = tran;
                 dielectric.gfs = GaussianSurface(spec.y);
-                dielectric.etaInt = std::max(1.f, IoR - 2.897f * dispersionB);
+                dielectric.etaInt = hlsl_max(1.f, IoR - 2.897f * dispersionB);
                 dielectric.etaExt = spec.w; dielectric.dispersionB = dispersionB;
                 break;
             }
@@ -1239,7 +1241,7 @@ struct MaterialInstance {
                 const float2 invPitch(pitch.x > .0f ? 1.f / pitch.x : .0f, pitch.y > .0f ? 1.f / pitch.y : .0f);
                 const float q = data2.x * spec.x, powerMult = spec.y, roughness = data2.y;
                 const uint32_t typeAndLobes = m.data1[3];
-                const uint32_t lobes = std::min(std::max(typeAndLobes & 0xFFu, 1u), 8u);
+                const uint32_t lobes = hlsl_min(hlsl_max(typeAndLobes & 0xFFu, 1u), 8u);
                 const uint32_t gtype = typeAndLobes >> 8;
                 grated.conductor = type == PLTPT_MATERIAL_GRATED_CONDUCTOR;
                 grated.baseC.specular = base.xyz(); grated.baseC.gfs = FractalSurface(roughness);

@@ -244,7 +244,7 @@ struct Integrator {
         const float3 b = sample_triangle(u);
         ls.posW = tri.posW[0] * b[0] + tri.posW[1] * b[1] + tri.posW[2] * b[2];
         float3 toLight = ls.posW - posW;
-        const float distSqr = std::max(FLT_MINf, dot(toLight, toLight));
+        const float distSqr = hlsl_max(FLT_MINf, dot(toLight, toLight));
         ls.distance = std::sqrt(distSqr);
         ls.dir = toLight / ls.distance;
         ls.normalW = tri.normal;
@@ -252,7 +252,7 @@ struct Integrator {
         if (cosTheta <= 0.f) return false;
         ls.Le = hwss_t(.0f);
         materialEvalEmissive(tri.materialID, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
-        float denom = std::max(FLT_MINf, cosTheta * tri.area);
+        float denom = hlsl_max(FLT_MINf, cosTheta * tri.area);
         ls.pdf = distSqr / denom;
         return true;
     }
@@ -263,7 +263,7 @@ struct Integrator {
             if (d.emissiveTriangleCount == 0) return false;
             float uLight = sampleNext1D(sg);
             uint32_t triangleCount = d.emissiveTriangleCount;
-            uint32_t triangleIndex = std::min((uint32_t)(uLight * triangleCount), triangleCount - 1);
+            uint32_t triangleIndex = hlsl_min((uint32_t)(uLight * triangleCount), triangleCount - 1);
             const uint32_t px = d.triangleAliasTable[2 * triangleIndex], py = d.triangleAliasTable[2 * triangleIndex + 1];
             float threshold = f16tof32(px >> 16u);
             uint32_t selectAbove = ((px & 0xFFFFu) << 8u) | ((py >> 24u) & 0xFFu);
@@ -277,7 +277,7 @@ struct Integrator {
             if (d.activeTriangleCount == 0) return false;
             float uLight = sampleNext1D(sg);
             uint32_t triangleCount = d.activeTriangleCount;
-            uint32_t idx = std::min((uint32_t)(uLight * triangleCount), triangleCount - 1);
+            uint32_t idx = hlsl_min((uint32_t)(uLight * triangleCount), triangleCount - 1);
             uint32_t triangleIndex = d.activeTriangles[idx];
             float triangleSelectionPdf = 1.f / (float)triangleCount;
             if (!sampleTriangle(posW, triangleIndex, sg, wavelength, importanceSample, ls)) return false;
@@ -298,7 +298,7 @@ struct Integrator {
         float3 L = toLight / std::sqrt(distSqr);
         float cosTheta = dot(hitNormalW, -L);
         if (cosTheta <= 0.f) return 0.f;
-        float denom = std::max(FLT_MINf, cosTheta * getEmissiveTriangle(triangleIndex).area);
+        float denom = hlsl_max(FLT_MINf, cosTheta * getEmissiveTriangle(triangleIndex).area);
         return sel * (distSqr / denom);
     }
     // LightSampling.slangh:104-126
@@ -325,7 +325,7 @@ struct Integrator {
     struct AnalyticLightSample { float3 posW, normalW, dir; float distance = 0; hwss_t Li, wavelengths; float pdf = 0; };
     bool finalizeAreaLightSample(float3 shadingPosW, const PltptLightData& light, SampleGenerator& sg, float wavelength, bool importanceSample, AnalyticLightSample& ls) const {
         float3 toLight = ls.posW - shadingPosW;
-        float distSqr = std::max(dot(toLight, toLight), 1e-9f);
+        float distSqr = hlsl_max(dot(toLight, toLight), 1e-9f);
         ls.distance = std::sqrt(distSqr);
         ls.dir = toLight / ls.distance;
         float cosTheta = dot(ls.normalW, -ls.dir);
@@ -343,7 +343,7 @@ struct Integrator {
                 ls.posW = lightPos;
                 ls.normalW = lightDir;
                 float3 toLight = ls.posW - shadingPosW;
-                float distSqr = std::max(dot(toLight, toLight), 1e-9f);
+                float distSqr = hlsl_max(dot(toLight, toLight), 1e-9f);
                 ls.distance = std::sqrt(distSqr);
                 ls.dir = toLight / ls.distance;
                 float cosTheta = -dot(ls.dir, lightDir);
@@ -397,7 +397,7 @@ struct Integrator {
         ls = LightSample();
         uint32_t lightCount = scene->d.lightCount;
         if (!kUseAnalyticLights() || lightCount == 0) return false;
-        uint32_t lightIndex = std::min(uint32_t(sampleNext1D(sg) * lightCount), lightCount - 1);
+        uint32_t lightIndex = hlsl_min(uint32_t(sampleNext1D(sg) * lightCount), lightCount - 1);
         const PltptLightData& light = scene->d.lights[lightIndex];
         AnalyticLightSample lightSample;
         if (!sampleAnalyticLight(sd.posW, light, sg, wavelength, importanceSample, lightSample)) return false;
@@ -603,7 +603,7 @@ struct Integrator {
         const float2 C(dt, dp);
         lenC = length(C);
         auto deriv = [](float3 v, float3 ddu, float3 ddv) {
-            const float dAcos = -1.f / std::sqrt(std::max(.0f, 1.f - sqr(v.z)));
+            const float dAcos = -1.f / std::sqrt(hlsl_max(.0f, 1.f - sqr(v.z)));
             const float invNorm = 1.f / dot(v.xy(), v.xy());
             return float2x2(dAcos * ddu.z, dAcos * ddv.z, invNorm * (v.x * ddu.y - v.y * ddu.x), invNorm * (v.x * ddv.y - v.y * ddv.x));
         };
@@ -655,7 +655,7 @@ struct Integrator {
                     float3 dirToProposal = proposal - p0;
                     const float dist = length(dirToProposal);
                     dirToProposal /= dist;
-                    const RayHit closestHit = shadowRay(p0, dirToProposal, 1.01f * dist, std::max(kShadowRayTMin, .99f * dist));
+                    const RayHit closestHit = shadowRay(p0, dirToProposal, 1.01f * dist, hlsl_max(kShadowRayTMin, .99f * dist));
                     // (reference unpacks the hit before testing isHit; a miss unpacks to instance 0)
                     const uint32_t propInst = closestHit.hit.valid() ? closestHit.hit.instanceID : 0u;
                     if (!closestHit.hit.valid() || scene->unpackHit(data.hits[idx].hit).instanceID != propInst) {
@@ -664,7 +664,7 @@ struct Integrator {
                     }
                     scene->packHit(closestHit.hit, data.hits[idx].hit);
                     data.hits[idx].posW = p0 + dirToProposal * closestHit.t;
-                    beta[idx] = std::min(1.0f, 2.f * beta[idx]);
+                    beta[idx] = hlsl_min(1.0f, 2.f * beta[idx]);
                     break;
                 }
             }

@@ -13,6 +13,20 @@
 
 namespace orc {
 
+// HLSL / DXIL min and max return the non-NaN operand (IEEE 754-2008 minNum / maxNum), exactly like CUDA fminf / fmaxf and
+// unlike std::min / std::max.  Every min / max of the restated Slang code goes through these.
+inline float hlsl_max(float a, float b) { return std::fmax(a, b); }
+inline float hlsl_min(float a, float b) { return std::fmin(a, b); }
+inline double hlsl_max(double a, double b) { return std::fmax(a, b); }
+inline double hlsl_min(double a, double b) { return std::fmin(a, b); }
+inline int hlsl_max(int a, int b) { return a < b ? b : a; }
+inline int hlsl_min(int a, int b) { return b < a ? b : a; }
+inline uint32_t hlsl_max(uint32_t a, uint32_t b) { return a < b ? b : a; }
+inline uint32_t hlsl_min(uint32_t a, uint32_t b) { return b < a ? b : a; }
+inline size_t hlsl_max(size_t a, size_t b) { return a < b ? b : a; }
+inline size_t hlsl_min(size_t a, size_t b) { return b < a ? b : a; }
+
+
 static constexpr float kPi = 3.14159265358979323846f;
 static constexpr float k2Pi = 6.28318530717958647693f;
 static constexpr float k4Pi = 12.5663706143591729539f;
@@ -74,8 +88,8 @@ struct float4 {
     inline T& operator/=(T& a, float s) { a = a / s; return a; }                                               \
     inline float dot(T a, T b) { float r = a[0] * b[0]; for (int i = 1; i < N; ++i) r += a[i] * b[i]; return r; } \
     inline T vabs(T a) { T r; for (int i = 0; i < N; ++i) r[i] = std::fabs(a[i]); return r; }                  \
-    inline T vmax(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::max(a[i], b[i]); return r; }        \
-    inline T vmin(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::min(a[i], b[i]); return r; }        \
+    inline T vmax(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = hlsl_max(a[i], b[i]); return r; }        \
+    inline T vmin(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = hlsl_min(a[i], b[i]); return r; }        \
     inline T vsqrt(T a) { T r; for (int i = 0; i < N; ++i) r[i] = std::sqrt(a[i]); return r; }                 \
     inline T vexp(T a) { T r; for (int i = 0; i < N; ++i) r[i] = std::exp(a[i]); return r; }                   \
     inline T vsin(T a) { T r; for (int i = 0; i < N; ++i) r[i] = std::sin(a[i]); return r; }                   \
@@ -95,7 +109,7 @@ inline float3 cross(float3 a, float3 b) {
 inline float sqr(float v) { return v * v; }
 inline float2 sqr(float2 v) { return v * v; }
 inline float4 sqr(float4 v) { return v * v; }
-inline float clampf(float v, float lo, float hi) { return std::min(std::max(v, lo), hi); }
+inline float clampf(float v, float lo, float hi) { return hlsl_min(hlsl_max(v, lo), hi); }
 inline float lerpf(float a, float b, float t) { return a + (b - a) * t; }  // HLSL lerp: x + s*(y-x)
 inline float4 lerp4(float4 a, float4 b, float4 t) { return a + (b - a) * t; }
 inline float signf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }  // HLSL sign()
@@ -216,8 +230,8 @@ inline float cnorm2(float2 z) { return dot(z, z); }
 inline float cabs(float2 z) { return std::sqrt(cnorm2(z)); }
 inline float2 csqrt(float2 z) {
     const float r = cabs(z);
-    const float a = std::sqrt(std::max(.0f, r + z.x) / 2.f);
-    const float b = std::sqrt(std::max(.0f, r - z.x) / 2.f);
+    const float a = std::sqrt(hlsl_max(.0f, r + z.x) / 2.f);
+    const float b = std::sqrt(hlsl_max(.0f, r - z.x) / 2.f);
     return c_t(a, signf(z.y) * b);
 }
 inline float2 cconj(float2 z) { return c_t(z.x, -z.y); }
@@ -264,7 +278,7 @@ inline float3 oct_to_ndir_equal_area_snorm(float2 p) {
 // Utils/Math/FormatConversion.slang unpackSnorm2x16 / packSnorm2x16 (used by decodeNormal2x16, PackedFormats.slang:50-62)
 inline float unpackSnorm16(uint32_t v) {
     int32_t i = int32_t(int16_t(v & 0xffff));
-    return std::max(float(i) / 32767.f, -1.f);
+    return hlsl_max(float(i) / 32767.f, -1.f);
 }
 inline uint32_t packSnorm16(float v) {
     v = std::isnan(v) ? 0.f : clampf(v, -1.f, 1.f);
@@ -292,7 +306,7 @@ inline float3 sample_cone(float2 u, float cosTheta) {
 inline float3 sample_sphere(float2 u) {
     float phi = k2Pi * u.y;
     float cosTheta = 1.0f - 2.0f * u.x;
-    float sinTheta = std::sqrt(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+    float sinTheta = std::sqrt(hlsl_max(0.0f, 1.0f - cosTheta * cosTheta));
     return float3(sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta);
 }
 inline float2 sample_disk_concentric(float2 u) {
@@ -305,7 +319,7 @@ inline float2 sample_disk_concentric(float2 u) {
 }
 inline float3 sample_cosine_hemisphere_concentric(float2 u, float& pdf) {
     float2 d = sample_disk_concentric(u);
-    float z = std::sqrt(std::max(0.f, 1.f - dot(d, d)));
+    float z = std::sqrt(hlsl_max(0.f, 1.f - dot(d, d)));
     pdf = z * k1_Pi;
     return float3(d, z);
 }
@@ -317,11 +331,11 @@ inline float3 sample_triangle(float2 u) {
 }
 // Truncated Box-Mueller — MathHelpers.slang:416-449
 inline float2 sample_boxmueller_truncated(float2 sample, float2 mean, float sigma2, float& pdf) {
-    const float l = std::sqrt(std::min(1.f, dot(mean, mean)));
-    const float coso = std::sqrt(std::max(.0f, 1 - dot(mean, mean)));
+    const float l = std::sqrt(hlsl_min(1.f, dot(mean, mean)));
+    const float coso = std::sqrt(hlsl_max(.0f, 1 - dot(mean, mean)));
     const float phi_i = (mean.x != .0f || mean.y != .0f) ? std::atan2(mean.y, mean.x) : .0f;
     const float s = std::exp(-.5f * sqr(1 + l) / sigma2);
-    const float x = (1.f - s) * std::max(FLT_EPS, sample.x) + s;
+    const float x = (1.f - s) * hlsl_max(FLT_EPS, sample.x) + s;
     const float r = std::sqrt(-2 * sigma2 * std::log(x));
     const float max_phi = (r < FLT_EPS || l < FLT_EPS) ? kPi : std::acos(clampf((sqr(r) + sqr(l) - 1) / (2.f * r * l), -1.f, 1.f));
     const float phi = phi_i + kPi + max_phi * (2.f * sample.y - 1.f);
@@ -330,8 +344,8 @@ inline float2 sample_boxmueller_truncated(float2 sample, float2 mean, float sigm
     return p + mean;
 }
 inline float boxmueller_truncated_pdf(float2 wo, float2 mean, float sigma2) {
-    const float l = std::sqrt(std::min(1.f, dot(mean, mean)));
-    const float coso = std::sqrt(std::max(.0f, 1 - dot(mean, mean)));
+    const float l = std::sqrt(hlsl_min(1.f, dot(mean, mean)));
+    const float coso = std::sqrt(hlsl_max(.0f, 1 - dot(mean, mean)));
     wo -= mean;
     const float r2 = dot(wo, wo);
     const float x = std::exp(-.5f * r2 / sigma2);
@@ -364,7 +378,7 @@ inline float BesselJ(int nu, float x) {
     float interp = cutoff / 10.f;
     float laa = BesselJ_laa(nu, x);
     float saa = BesselJ_saa(nu, x);
-    return (nu >= 7 || std::fabs(x) >= cutoff + interp) ? laa * t : lerpf(saa, laa, std::max(.0f, std::min(1.f, .5f * (x - cutoff - interp) / interp))) * t;
+    return (nu >= 7 || std::fabs(x) >= cutoff + interp) ? laa * t : lerpf(saa, laa, hlsl_max(.0f, hlsl_min(1.f, .5f * (x - cutoff - interp) / interp))) * t;
 }
 
 // GeometryHelpers.slang:47-61 (Wächter & Binder, Ray Tracing Gems ch. 6)

@@ -342,7 +342,7 @@ struct Scene {
             if (a > b) std::swap(a, b);
             a -= 1e-5 * std::fabs(a) + 1e-9;
             b += 1e-5 * std::fabs(b) + 1e-9;
-            t0 = std::max(t0, a); t1 = std::min(t1, b);
+            t0 = hlsl_max(t0, a); t1 = hlsl_min(t1, b);
         }
         return t0 <= t1;
     }

@@ -84,7 +84,7 @@ inline float wavelengthToD65(float lambda) {
     const int wavelength_b = int(std::floor(wavelengthResize) + .5f);
     const float weight = wavelengthResize - wavelength_b;
     // (index clamp is an oracle-only guard; the integrator only produces wavelengths in [380,720])
-    return D65_5nm[std::min(std::max(wavelength_t, 0), 68)] * weight + D65_5nm[std::min(std::max(wavelength_b, 0), 68)] * (1.0f - weight);
+    return D65_5nm[hlsl_min(hlsl_max(wavelength_t, 0), 68)] * weight + D65_5nm[hlsl_min(hlsl_max(wavelength_b, 0), 68)] * (1.0f - weight);
 }
 // ColorHelpers.slang:61-70
 inline float3 XYZtoRGB_Rec709(float3 c) {
@@ -170,8 +170,8 @@ struct ProfileTable {
         const float i = std::floor(x);
         const float w = x - i;
         if (lambda < minl || lambda > maxl) return .0f;
-        const int i0 = std::max(0, std::min(int(bins) - 1, int(i)));
-        const int i1 = std::max(0, std::min(int(bins) - 1, int(i + 1)));
+        const int i0 = hlsl_max(0, hlsl_min(int(bins) - 1, int(i)));
+        const int i1 = hlsl_max(0, hlsl_min(int(bins) - 1, int(i + 1)));
         return sp.intensity * lerpf(sp.pdf[i0], sp.pdf[i1], w);
     }
     hwss_t evalSpectrum(uint32_t id, hwss_t lambdas) const {
@@ -219,7 +219,7 @@ struct PiecewiseLinearSpectrum {
     }
     float leastBinSize() const {
         float size = wavelengths.back() - wavelengths.front();
-        for (size_t i = 1; i < wavelengths.size(); ++i) size = std::min(size, wavelengths[i] - wavelengths[i - 1]);
+        for (size_t i = 1; i < wavelengths.size(); ++i) size = hlsl_min(size, wavelengths[i] - wavelengths[i - 1]);
         return size;
     }
 };
@@ -230,7 +230,7 @@ struct SampledSpectrum {
     SampledSpectrum(float a, float b, std::vector<float> v) : lambdaStart(a), lambdaEnd(b), samples(std::move(v)) {}
     // SampledSpectrum.h:57-68
     explicit SampledSpectrum(const PiecewiseLinearSpectrum& pls, float lambdaBinMinSize = 5.f) : lambdaStart(pls.wavelengths.front()), lambdaEnd(pls.wavelengths.back()) {
-        const float binSize = std::max(lambdaBinMinSize, pls.leastBinSize() / 2.f);
+        const float binSize = hlsl_max(lambdaBinMinSize, pls.leastBinSize() / 2.f);
         samples.resize(std::max<size_t>(1, size_t((lambdaEnd - lambdaStart) / float(binSize) + .5f)));
         for (size_t idx = 0; idx < samples.size(); ++idx) samples[idx] = pls.eval(lambdaStart + (lambdaEnd - lambdaStart) / float(samples.size() - 1) * idx);
     }
@@ -249,8 +249,8 @@ inline PltptSpectralProfile genSpectralProfile(const SampledSpectrum& ss, bool c
     PltptSpectralProfile sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.intensity = 1.f;
-    sp.minWavelength = std::max(ss.lambdaStart, SpectrumUtils::minWavelength);
-    sp.maxWavelength = std::min(ss.lambdaEnd, SpectrumUtils::maxWavelength);
+    sp.minWavelength = hlsl_max(ss.lambdaStart, SpectrumUtils::minWavelength);
+    sp.maxWavelength = hlsl_min(ss.lambdaEnd, SpectrumUtils::maxWavelength);
     sp.bins = std::min<uint32_t>(128u, uint32_t(ss.samples.size() * (sp.maxWavelength - sp.minWavelength) / (ss.lambdaEnd - ss.lambdaStart) + .5f));
     if (sp.bins == 0) return sp;
     const float r = sp.bins > 1 ? 1.f / float(sp.bins - 1) : 1.f;
@@ -266,7 +266,7 @@ inline PltptSpectralProfile genSpectralProfile(const SampledSpectrum& ss, bool c
     for (size_t pdfi = 0, icdfi = 0; icdfi < sp.bins; ++icdfi) {
         const float cdf = icdfi * r;
         while (cdf >= cdfb && pdfi + 1 < sp.bins) { cdfa = cdfb; ++pdfi; cdfb += sp.pdf[pdfi]; }
-        const float l = std::min(1.f, (cdf - cdfa) / (cdfb - cdfa));
+        const float l = hlsl_min(1.f, (cdf - cdfa) / (cdfb - cdfa));
         sp.icdf[icdfi] = lerpf((float)std::max<uint32_t>(1, uint32_t(pdfi)) - 1.f, (float)pdfi, l) * r;
     }
     return sp;

@@ -524,6 +524,5 @@ extern "C" int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const
     PLT_CUDA(h->outColor.ensure(bytes));
     PLT_CUDA(h->outAlbedo.ensure(bytes));
     PLT_CUDA(h->outNormal.ensure(bytes));
-    if (int r = renderFrame(h, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, false, 0)) return r;
-    return copyBounces(h, bouncesHost, w, hgt);
+    return sampleStageToHost(h, frameCount, cam, w, hgt, h->outAlbedo.as<float>(), h->outNormal.as<float>(), bouncesHost);
 }

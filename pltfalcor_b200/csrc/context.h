@@ -106,6 +106,6 @@ int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded,
 // integrator.cu
 int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
                 double* accum, bool solve, cudaStream_t s);
-int copyBounces(PltptContext* c, PltptBounce* host, uint32_t w, uint32_t h);
+int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host);
 int syncFrameStats(PltptContext* c);
 }  // namespace plt

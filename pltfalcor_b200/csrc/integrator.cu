@@ -1,68 +1,20 @@
-// integrator.cu — the two stages of PLTPT::execute (reference Source/RenderPasses/PLTPT/PLTPT.cpp:487-495): the sample
-// stage records a backward path per pixel, the solve stage sources generalized rays at the lights and replays them forward.
+// integrator.cu — host side of PLTPT::execute's tile loop (reference Source/RenderPasses/PLTPT/PLTPT.cpp:487-495):
+// per row tile, the sample stage records a backward path per pixel, then the solve stage runs as a wavefront
+// (connect -> [sort, step] x (maxBounces+1) -> resolve).  Buffer sizing, statistics and the parity dump live here.
 #include "plt_integrator.cuh"
+#include <algorithm>
 
 namespace plt {
+
 namespace {
-
-constexpr int kStageThreads = 128;
-
-// Pixels are assigned to threads in 8x4 tiles per warp so that a warp's primary rays (and its bounce-record lines) stay coherent.
-PLT_D bool pixelOfThread(const FrameParams& P, uint32_t& px, uint32_t& py) {
-    const uint32_t tilesX = (P.width + 7) / 8;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    px = (warp % tilesX) * 8 + (lane & 7);
-    py = (warp / tilesX) * 4 + (lane >> 3);
-    return px < P.width && py < P.height;
+// worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
+size_t workBytesPerPixel(uint32_t records) {
+    return size_t(records) * (16 + 16 + 8 + 64 + 1) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16;
 }
-
-PLT_D void warpAdd(unsigned long long* dst, uint32_t v) {  // all 32 lanes must call
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
-}
-
-__global__ void __launch_bounds__(kStageThreads) k_sample_stage(const __grid_constant__ FrameParams P) {
-    uint32_t px, py;
-    TraversalCounters tc = {0, 0};
-    if (pixelOfThread(P, px, py)) tc = samplePixel(P, px, py);
-    warpAdd(P.counters + 5, tc.nodes);
-    warpAdd(P.counters + 6, tc.tris);
-}
-
-__global__ void __launch_bounds__(kStageThreads) k_solve_stage(const __grid_constant__ FrameParams P) {
-    uint32_t px, py;
-    uint32_t evals = 0, verts = 0;
-    TraversalCounters tc = {0, 0};
-    if (pixelOfThread(P, px, py)) verts = solvePixel(P, px, py, evals, tc);
-    // warp-aggregated statistics (all lanes reach this point)
-    warpAdd(P.counters + 0, evals);
-    warpAdd(P.counters + 1, verts);
-    warpAdd(P.counters + 4, verts * (verts - (verts ? 1u : 0u)) / 2u);
-    warpAdd(P.counters + 5, tc.nodes);
-    warpAdd(P.counters + 6, tc.tris);
-}
-
-// Re-assembles the reference's 40 B AoS bounce records (pixel-major, pltpt.slangh:132-136) from the SoA planes.
-__global__ void k_gather_bounces(FrameParams P, PltptBounce* __restrict__ out, uint32_t records) {
-    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= P.pixelCount) return;
-    for (uint32_t p = 0; p < records; ++p) {
-        const size_t o = size_t(p) * P.pixelCount + pixel;
-        const uint4 h = P.bHit[o];
-        const float4 d = P.bDir[o];
-        const float2 q = P.bPdf[o];
-        PltptBounce b;
-        b.hit[0] = h.x; b.hit[1] = h.y; b.hit[2] = h.z; b.hit[3] = h.w;
-        b.encodedWi[0] = d.x; b.encodedWi[1] = d.y;
-        b.sampledBsdfLobe = __float_as_uint(d.z); b.flags = __float_as_uint(d.w);
-        b.pathContribution = q.x; b.lastNonDeltaPdf = q.y;
-        out[size_t(pixel) * records + p] = b;
-    }
-}
-
+constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
 
-static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h) {
+static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, uint32_t& tileRows) {
     P.sc = c->scene;
     P.opt = c->opt;
     P.camPos = mk3(cam->posW[0], cam->posW[1], cam->posW[2]);
@@ -72,17 +24,42 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     P.jitterX = cam->jitterX; P.jitterY = cam->jitterY;
     P.polarizer = cam->polarizer; P.polarizerTheta = cam->polarizerTheta;
     for (int i = 0; i < 3; ++i) { P.viewRow0[i] = cam->viewMat[i]; P.viewRow1[i] = cam->viewMat[4 + i]; P.viewRow2[i] = cam->viewMat[8 + i]; }
-    P.frameCount = frameCount; P.width = w; P.height = h; P.pixelCount = w * h;
-    const size_t records = size_t(c->opt.maxBounces + 1) * P.pixelCount;
+    P.frameCount = frameCount; P.width = w; P.height = h;
+    const uint32_t recordsPerPixel = c->opt.maxBounces + 1;
+    const size_t perRow = workBytesPerPixel(recordsPerPixel) * w;
+    tileRows = uint32_t(std::min<size_t>(h, std::max<size_t>(4, (kWorkBudgetBytes / perRow) & ~size_t(3))));
+    const uint32_t tilePixels = tileRows * w;
+    P.pixelCount = tilePixels;
+    const size_t records = size_t(recordsPerPixel) * tilePixels;
+    const size_t jobCapacity = 2 * records;
+    if (jobCapacity >= (size_t(1) << 32)) { setError("tile too large for 32-bit job ids"); return PLTPT_ERR_INVALID_ARGUMENT; }
     PLT_CUDA(c->work[0].ensure(records * sizeof(uint4)));
     PLT_CUDA(c->work[1].ensure(records * sizeof(float4)));
     PLT_CUDA(c->work[2].ensure(records * sizeof(float2)));
     PLT_CUDA(c->work[3].ensure(16 * sizeof(unsigned long long)));
+    for (int k = 0; k < 4; ++k) PLT_CUDA(c->work[5 + k].ensure(records * sizeof(float4)));
+    PLT_CUDA(c->work[9].ensure(records));
+    PLT_CUDA(c->work[10].ensure(jobCapacity * kJobPlanes * sizeof(float4)));
+    PLT_CUDA(c->work[11].ensure(jobCapacity * 4));
+    PLT_CUDA(c->work[12].ensure(jobCapacity));
+    PLT_CUDA(c->work[13].ensure(jobCapacity * 4));
+    PLT_CUDA(c->work[14].ensure(64 * 4));
+    PLT_CUDA(c->work[15].ensure(jobCapacity * sizeof(float4)));  // contrib: 2 * records float4
     P.bHit = c->work[0].as<uint4>();
     P.bDir = c->work[1].as<float4>();
     P.bPdf = c->work[2].as<float2>();
     P.counters = c->work[3].as<unsigned long long>();
-    c->workW = w; c->workH = h; c->workBounces = c->opt.maxBounces + 1;
+    P.vc0 = c->work[5].as<float4>(); P.vc1 = c->work[6].as<float4>(); P.vc2 = c->work[7].as<float4>(); P.vc3 = c->work[8].as<float4>();
+    P.vMatType = c->work[9].as<uint8_t>();
+    P.job = c->work[10].as<float4>();
+    P.jobCapacity = uint32_t(jobCapacity);
+    P.pending = c->work[11].as<uint32_t>();
+    P.pendingType = c->work[12].as<uint8_t>();
+    P.sorted = c->work[13].as<uint32_t>();
+    P.queueCount = c->work[14].as<uint32_t>();
+    P.jobCount = P.queueCount + 32;
+    P.contrib = c->work[15].as<float4>();
+    c->workW = w; c->workH = h; c->workBounces = recordsPerPixel;
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
     P.doNEE = c->opt.doNEE != 0;
@@ -92,11 +69,45 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     return PLTPT_OK;
 }
 
+// One frame = one sample per pixel.  `bouncesOut` (device, optional) receives the reference-layout bounce records.
+static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool solve, PltptBounce* bouncesOut, cudaStream_t s) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const uint32_t persistentGrid = uint32_t(sms) * 8;
+    for (uint32_t y0 = 0; y0 < P.height; y0 += tileRows) {
+        P.tileY0 = y0;
+        P.tileRows = std::min(tileRows, P.height - y0);
+        P.outOffset = y0 * P.width;
+        P.pixelCount = P.tileRows * P.width;
+        const uint32_t warps = ((P.width + 7) / 8) * ((P.tileRows + 3) / 4);
+        const uint32_t blocks = (warps * 32 + kStageThreads - 1) / kStageThreads;
+        cudaEvent_t* ev = &c->timerEvents[3 * c->timerCount];
+        const bool timed = y0 == 0;  // stage timers cover the first tile of a frame (the only one unless the frame is tiled)
+        if (timed) cudaEventRecord(ev[0], s);
+        launchSampleStage(P, blocks, s);
+        c->stats.kernelLaunches++;
+        if (timed) cudaEventRecord(ev[1], s);
+        if (bouncesOut) { launchGatherBounces(P, bouncesOut, c->opt.maxBounces + 1, s); c->stats.kernelLaunches++; }
+        if (solve) {
+            PLT_CUDA(cudaMemsetAsync(P.queueCount, 0, 64 * 4, s));
+            launchConnectStage(P, blocks, s);
+            c->stats.kernelLaunches++;
+            for (uint32_t it = 0; it <= c->opt.maxBounces; ++it) { launchUnwindIteration(P, persistentGrid, s); c->stats.kernelLaunches += 3; }
+            launchResolve(P, s);
+            c->stats.kernelLaunches++;
+        }
+        if (timed) cudaEventRecord(ev[2], s);
+    }
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+
 int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, double* accum,
                 bool solve, cudaStream_t s) {
     FrameParams P{};
     const bool fresh = c->work[3].p == nullptr;
-    if (int r = fillParams(c, P, frameCount, cam, w, h)) return r;
+    uint32_t tileRows = 0;
+    if (int r = fillParams(c, P, frameCount, cam, w, h, tileRows)) return r;
     P.color = reinterpret_cast<float4*>(color);
     P.albedo = reinterpret_cast<float4*>(albedo);
     P.normal = reinterpret_cast<float4*>(normal);
@@ -104,27 +115,15 @@ int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam
     if (fresh) PLT_CUDA(cudaMemsetAsync(P.counters, 0, 16 * sizeof(unsigned long long), s));
     // snapshot of the cumulative counters before this frame, so that "last frame" statistics can be formed at sync time
     PLT_CUDA(cudaMemcpyAsync(P.counters + 8, P.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-    const uint32_t warps = ((w + 7) / 8) * ((h + 3) / 4);
-    const uint32_t blocks = (warps * 32 + kStageThreads - 1) / kStageThreads;
     // device timers: one event triple per frame from a ring, read back in syncFrameStats()
     if (c->timerEvents.empty()) {
         c->timerEvents.resize(3 * PltptContext::kTimerRing);
         for (auto& e : c->timerEvents) PLT_CUDA(cudaEventCreate(&e));
     }
     if (c->timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
-    cudaEvent_t* ev = &c->timerEvents[3 * c->timerCount];
-    cudaEventRecord(ev[0], s);
-    k_sample_stage<<<blocks, kStageThreads, 0, s>>>(P);
-    cudaEventRecord(ev[1], s);
-    c->stats.kernelLaunches++;
-    if (solve) {
-        k_solve_stage<<<blocks, kStageThreads, 0, s>>>(P);
-        c->stats.kernelLaunches++;
-    }
-    cudaEventRecord(ev[2], s);
+    if (int r = renderTiles(c, P, tileRows, solve, nullptr, s)) return r;
     c->timerCount++;
     c->timerStream = s;
-    PLT_CUDA(cudaGetLastError());
     c->statsDirty = true;
     return PLTPT_OK;
 }
@@ -145,6 +144,9 @@ int syncFrameStats(PltptContext* c) {
         c->stats.traversalNodesVisited += host[5];
         c->stats.traversalTrianglesTested += host[6];
         PLT_CUDA(cudaMemset(c->work[3].p, 0, 16 * sizeof(unsigned long long)));
+        uint32_t dropped = 0;
+        PLT_CUDA(cudaMemcpy(&dropped, c->work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
+        c->stats.droppedConnections += dropped;
         for (uint32_t i = 0; i < c->timerCount; ++i) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, c->timerEvents[3 * i], c->timerEvents[3 * i + 1]);
@@ -165,16 +167,24 @@ int syncFrameStats(PltptContext* c) {
     return PLTPT_OK;
 }
 
-int copyBounces(PltptContext* c, PltptBounce* host, uint32_t w, uint32_t h) {
+// Sample stage only; writes the reference-layout bounce records of the whole frame to host memory (parity checks).
+int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host) {
     FrameParams P{};
-    P.pixelCount = w * h;
-    P.bHit = c->work[0].as<uint4>(); P.bDir = c->work[1].as<float4>(); P.bPdf = c->work[2].as<float2>();
+    const bool fresh = c->work[3].p == nullptr;
+    uint32_t tileRows = 0;
+    if (int r = fillParams(c, P, frameCount, cam, w, h, tileRows)) return r;
+    P.albedo = reinterpret_cast<float4*>(albedo);
+    P.normal = reinterpret_cast<float4*>(normal);
+    if (fresh) PLT_CUDA(cudaMemset(P.counters, 0, 16 * sizeof(unsigned long long)));
+    if (c->timerEvents.empty()) {
+        c->timerEvents.resize(3 * PltptContext::kTimerRing);
+        for (auto& e : c->timerEvents) PLT_CUDA(cudaEventCreate(&e));
+    }
+    if (c->timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
     const uint32_t records = c->opt.maxBounces + 1;
-    const size_t bytes = size_t(P.pixelCount) * records * sizeof(PltptBounce);
+    const size_t bytes = size_t(w) * h * records * sizeof(PltptBounce);
     PLT_CUDA(c->work[4].ensure(bytes));
-    k_gather_bounces<<<(P.pixelCount + 127) / 128, 128>>>(P, c->work[4].as<PltptBounce>(), records);
-    c->stats.kernelLaunches++;
-    PLT_CUDA(cudaGetLastError());
+    if (int r = renderTiles(c, P, tileRows, false, c->work[4].as<PltptBounce>(), 0)) return r;
     PLT_CUDA(cudaMemcpy(host, c->work[4].p, bytes, cudaMemcpyDeviceToHost));
     c->work[4].release();
     return PLTPT_OK;

@@ -965,8 +965,11 @@ PLT_D void stackEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_
         for (uint32_t l = 0; l < layers; ++l) {
             const bool odd = (l & 1) != 0;
             const float d = 2.f * (odd ? m.f3 : m.f2) / (odd ? ct1 : ct0) * lane(k, j) * (odd ? m.f1 : m.f0);
-            float sd, cd;
-            sincosf(d, &sd, &cd);
+            // interference sum: near anti-reflection it cancels to ~1e-4 of its terms, so the phase factor is the correctly
+            // rounded fp32 cos/sin (evaluated in double), as in the oracle
+            double sdd, cdd;
+            sincos(double(d), &sdd, &cdd);
+            const float sd = float(sdd), cd = float(cdd);
             const float R = l == layers - 1 ? Rout : (odd ? r1 : r0);
             G = cmul(G, mk2(cd, sd));
             G = cdiv(mk2(R + G.x, G.y), mk2(1.f + R * G.x, R * G.y));

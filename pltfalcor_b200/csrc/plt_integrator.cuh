@@ -24,6 +24,23 @@ struct FrameParams {
     uint4* bHit;       // PackedHitInfo
     float4* bDir;      // encodedWi.xy, asfloat(lobe), asfloat(flags)
     float2* bPdf;      // pathContribution, lastNonDeltaPdf
+    // per-vertex shading cache written by the sample stage so that the O(L^2) forward replay never re-fetches geometry:
+    // vc0 = posW.xyz | materialID, vc1 = normalW.xyz | uv.x, vc2 = faceNormalW.xyz | uv.y, vc3 = tangentW
+    float4 *vc0, *vc1, *vc2, *vc3;
+    uint8_t* vMatType;  // MaterialType of every recorded vertex (queue binning key)
+    // connection jobs (one per NEE / emissive light connection): 10 float4 planes [plane][job]
+    float4* job;
+    uint32_t jobCapacity;
+    uint32_t* jobCount;      // [0] allocated jobs, [1] dropped (capacity overflow; must stay 0)
+    // replay queues: the step kernel appends surviving job ids (+ the MaterialType of their next vertex) to `pending`, a
+    // counting-sort scatter then writes them to `sorted` grouped by type, which is what the next step kernel walks.
+    uint32_t* pending;       // [jobCapacity] job ids in completion order
+    uint8_t* pendingType;    // [jobCapacity]
+    uint32_t* sorted;        // [jobCapacity] job ids grouped by material type
+    uint32_t* queueCount;    // [0..kQueueTypes) per-type counts of `pending`, [kQueueTypes] total, [kQueueTypes+1 ..] scatter cursors,
+                             // [2*kQueueTypes+2] number of entries of `sorted`
+    uint32_t tileY0, tileRows, outOffset;  // row tile of the frame processed by this launch sequence (work buffers are tile-local)
+    float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection, summed in fixed order by the resolve kernel
     float4* color;     // RGBA32F (may be null when accum is used)
     float4* albedo;
     float4* normal;
@@ -33,6 +50,9 @@ struct FrameParams {
     // derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
     bool useEmissive, useAnalytic, doNEE, doMS, doMIS, perTileSG;
 };
+
+constexpr int kQueueTypes = 12;  // MaterialType values 0..11
+constexpr int kJobPlanes = 10;
 
 struct Bounce {
     uint4 hit;
@@ -57,6 +77,25 @@ PLT_D Bounce readBounce(const FrameParams& P, uint32_t pixel, int p) {
     b.lobe = __float_as_uint(d.z); b.flags = __float_as_uint(d.w);
     b.pathContribution = q.x; b.lastNonDeltaPdf = q.y;
     return b;
+}
+
+PLT_D void writeVertexCache(const FrameParams& P, uint32_t pixel, int p, const VertexData& v, uint32_t materialID, uint32_t materialType) {
+    const size_t o = size_t(p) * P.pixelCount + pixel;
+    P.vc0[o] = mk4(v.posW.x, v.posW.y, v.posW.z, __uint_as_float(materialID));
+    P.vc1[o] = mk4(v.normalW.x, v.normalW.y, v.normalW.z, v.texC.x);
+    P.vc2[o] = mk4(v.faceNormalW.x, v.faceNormalW.y, v.faceNormalW.z, v.texC.y);
+    P.vc3[o] = v.tangentW;
+    P.vMatType[o] = uint8_t(materialType);
+}
+PLT_D VertexData readVertexCache(const FrameParams& P, uint32_t pixel, int p, uint32_t& materialID) {
+    const size_t o = size_t(p) * P.pixelCount + pixel;
+    const float4 a = __ldcs(P.vc0 + o), b = __ldcs(P.vc1 + o), c = __ldcs(P.vc2 + o), d = __ldcs(P.vc3 + o);
+    VertexData v;
+    v.posW = mk3(a.x, a.y, a.z); materialID = __float_as_uint(a.w);
+    v.normalW = mk3(b.x, b.y, b.z); v.faceNormalW = mk3(c.x, c.y, c.z);
+    v.texC = mk2(b.w, c.w);
+    v.tangentW = d;
+    return v;
 }
 
 // ---- rays ------------------------------------------------------------------------------------------------------
@@ -122,11 +161,12 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     const bool isDelta = (bs.lobe & L_Delta) != 0, isDispersive = (bs.lobe & L_DispersiveDelta) != 0, isReflection = (bs.lobe & L_Reflection) != 0;
     const bool isMSCompatible = (isReflection && (m.propFlags & P_CanMSReflective)) || (!isReflection && (m.propFlags & P_CanMSTransmissive));
     if (!isDelta && (path.flags & RF_OnlyDelta)) {
-        if (P.albedo) P.albedo[pixel] = mk4(m.albx, m.alby, m.albz, 1.f);
+        if (P.albedo) P.albedo[P.outOffset + pixel] = mk4(m.albx, m.alby, m.albz, 1.f);
         if (P.normal)
-            P.normal[pixel] = mk4(P.viewRow0[0] * sd.N.x + P.viewRow0[1] * sd.N.y + P.viewRow0[2] * sd.N.z, P.viewRow1[0] * sd.N.x + P.viewRow1[1] * sd.N.y + P.viewRow1[2] * sd.N.z,
+            P.normal[P.outOffset + pixel] = mk4(P.viewRow0[0] * sd.N.x + P.viewRow0[1] * sd.N.y + P.viewRow0[2] * sd.N.z, P.viewRow1[0] * sd.N.x + P.viewRow1[1] * sd.N.y + P.viewRow1[2] * sd.N.z,
                                   P.viewRow2[0] * sd.N.x + P.viewRow2[1] * sd.N.y + P.viewRow2[2] * sd.N.z, 1.f);
     }
+    writeVertexCache(P, pixel, path.length, v, materialID, m.type);
     if (shouldEndPath) {
         path.flags |= RF_Terminated;
         writeBounce(P, pixel, path.length, hitInfo, wi, 0u, path.flags, 1.f / (path.pdf * path.thp), path.lastNonDeltaPdf);
@@ -148,13 +188,13 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
 }
 // pltpt_sample.rt.slang:146-185 (raygen)
 PLT_D TraversalCounters samplePixel(const FrameParams& P, uint32_t px, uint32_t py) {
-    const uint32_t pixel = py * P.width + px;
+    const uint32_t pixel = (py - P.tileY0) * P.width + px;
     PathState path;
     path.tc.nodes = path.tc.tris = 0;
     path.sg = Rng::seed(px, py, P.frameCount);
     path.wavelength = sampleHeroWavelength(path.sg.next1D());
-    if (P.normal) P.normal[pixel] = mk4(0.f);
-    if (P.albedo) P.albedo[pixel] = mk4(0.f);
+    if (P.normal) P.normal[P.outOffset + pixel] = mk4(0.f);
+    if (P.albedo) P.albedo[P.outOffset + pixel] = mk4(0.f);
     cameraRay(P, px, py, path.origin, path.dir);
     path.weight = path.pdf = path.thp = 1.f;
     path.flags = RF_OnlyDelta;
@@ -413,36 +453,81 @@ PLT_D bool generateLightSample(const FrameParams& P, const SD& sd, bool sampleRe
 }
 
 // ---- solve stage ---------------------------------------------------------------------------------------------
+// The solve stage is a wavefront (DESIGN.md "Solve stage"):
+//   connect : one thread per path walks its recorded vertices in order (the random-number order of pltpt_solve.rt.slang:420-464
+//             is sequential per pixel), samples the light, traces the shadow ray / manifold walk, applies MIS and EMITS one
+//             connection job per surviving light connection instead of replaying it;
+//   unwind  : every job is a generalized ray that still has to be pushed through vertices q, q-1, ... 0 of its path.  Jobs are
+//             binned by the MaterialType of the vertex they evaluate next, so a warp runs ONE BSDF; one launch = one replay step;
+//   resolve : sums the measured RGB of a pixel's connections in the reference's order (deterministic, no float atomics).
 struct SolveState {
     Rng sg, tilesg;
-    float3 Lrgb, pathOrigin;
+    float3 pathOrigin;
     float wavelength;
     uint32_t evals;
     TraversalCounters tc;
 };
+enum : uint32_t { JOB_Q_MASK = 0xffu, JOB_COMPS_SHIFT = 8, JOB_DISTANT = 1u << 11, JOB_FIRST_IS_CURRENT = 1u << 12, JOB_BOUNCE_SHIFT = 16, JOB_KIND_SHIFT = 24 };
+struct JobHeader { uint32_t pixel, q, bounceIdx, kind; bool firstIsCurrent; float pathContribution; };
+
+PLT_D void storeJob(const FrameParams& P, uint32_t id, const Beam& b, const JobHeader& h) {
+    float4* J = P.job + id;
+    const size_t st = P.jobCapacity;
+    const uint32_t packed = (h.q & JOB_Q_MASK) | (uint32_t(b.comps) << JOB_COMPS_SHIFT) | (b.distant ? JOB_DISTANT : 0u) | (h.firstIsCurrent ? JOB_FIRST_IS_CURRENT : 0u) |
+                            (h.bounceIdx << JOB_BOUNCE_SHIFT) | (h.kind << JOB_KIND_SHIFT);
+    J[0 * st] = b.L; J[1 * st] = b.L1; J[2 * st] = b.L2; J[3 * st] = b.L3; J[4 * st] = b.wl; J[5 * st] = b.spdf;
+    J[6 * st] = mk4(b.Dxx, b.Dxy, b.Dyy, b.r_m);
+    J[7 * st] = mk4(b.posW.x, b.posW.y, b.posW.z, b.r.x);
+    J[8 * st] = mk4(b.r.y, b.r.z, b.t.x, b.t.y);
+    J[9 * st] = mk4(b.t.z, h.pathContribution, __uint_as_float(h.pixel), __uint_as_float(packed));
+}
+PLT_D void loadJob(const FrameParams& P, uint32_t id, Beam& b, JobHeader& h) {
+    const float4* J = P.job + id;
+    const size_t st = P.jobCapacity;
+    b.L = J[0 * st]; b.L1 = J[1 * st]; b.L2 = J[2 * st]; b.L3 = J[3 * st]; b.wl = J[4 * st]; b.spdf = J[5 * st];
+    const float4 c = J[6 * st], d = J[7 * st], e = J[8 * st], f = J[9 * st];
+    b.Dxx = c.x; b.Dxy = c.y; b.Dyy = c.z; b.r_m = c.w;
+    b.posW = mk3(d.x, d.y, d.z); b.r = mk3(d.w, e.x, e.y); b.t = mk3(e.z, e.w, f.x);
+    const uint32_t packed = __float_as_uint(f.w);
+    h.pathContribution = f.y; h.pixel = __float_as_uint(f.z);
+    h.q = packed & JOB_Q_MASK; b.comps = int((packed >> JOB_COMPS_SHIFT) & 7u); b.distant = (packed & JOB_DISTANT) != 0;
+    h.firstIsCurrent = (packed & JOB_FIRST_IS_CURRENT) != 0; h.bounceIdx = (packed >> JOB_BOUNCE_SHIFT) & 0xffu; h.kind = packed >> JOB_KIND_SHIFT;
+}
+// Appends `id` to the pending list of the next replay iteration (warp-aggregated: one atomic per warp for the slot, one per
+// material type for the histogram).
+PLT_D void enqueueJob(const FrameParams& P, uint32_t type, uint32_t id) {
+    const uint32_t active = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(P.queueCount + kQueueTypes, uint32_t(__popc(active)));
+    base = __shfl_sync(active, base, leader);
+    const uint32_t slot = base + __popc(active & ((1u << lane) - 1u));
+    P.pending[slot] = id;
+    P.pendingType[slot] = uint8_t(type);
+    const uint32_t peers = __match_any_sync(active, type);
+    if (lane == __ffs(peers) - 1) atomicAdd(P.queueCount + type, uint32_t(__popc(peers)));
+}
+PLT_D uint32_t allocJob(const FrameParams& P) {
+    const uint32_t active = __activemask();
+    const int leader = __ffs(active) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(P.jobCount, uint32_t(__popc(active)));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & ((1u << lane) - 1u));
+}
+
 // pltpt_solve.rt.slang:48-66 (forwardUnwindStep)
-PLT_D void forwardUnwindStep(const FrameParams& P, SolveState& st, const VertexData& v, uint32_t materialID, float3 wo, uint32_t lobe, Beam& beam) {
-    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+PLT_D void forwardUnwindStep(const FrameParams& P, uint32_t& evals, const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 wo, uint32_t lobe, Beam& beam) {
     const SD sd = prepareShadingData(v, materialID, m, -beam.r);
     beam.propagate(sd.posW);
     const BsdfCtx cx = {P.sc.profiles, int(P.opt.HWSS)};
     bsdfEval(m, cx, sd, wo, lobe, beam);
-    st.evals += uint32_t(beam.comps);
+    evals += uint32_t(beam.comps);
     if (P.opt.HWSSDoMIS) beam.spdf *= bsdfLambdaPdf(m, cx, sd, wo, lobe, beam, beam.wl);
 }
-// pltpt_solve.rt.slang:68-79
-PLT_D void forwardUnwind(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceIdx, Beam& beam) {
-    for (int p = bounceIdx - 1; p >= 0; --p) {
-        const Bounce b = readBounce(P, pixel, p);
-        const TriHit th = unpackHit(P.sc, b.hit);
-        uint32_t materialID;
-        const VertexData v = getVertexData(P.sc, th, materialID);
-        forwardUnwindStep(P, st, v, materialID, b.wi, b.lobe, beam);
-    }
-}
-// pltpt_solve.rt.slang:96-147
-PLT_D void measure(const FrameParams& P, SolveState& st, int bounceIdx, float pathContribution, Beam& beam) {
-    if (!P.opt.useDirectLights && bounceIdx <= 1) return;
+// pltpt_solve.rt.slang:96-147: returns the RGB contribution of one connection
+PLT_D float3 measure(const FrameParams& P, int bounceIdx, float pathContribution, Beam& beam) {
+    if (!P.opt.useDirectLights && bounceIdx <= 1) return mk3(0.f);
     beam.propagate(P.camPos);
     if (P.polarizer > .0f) {
         beam.rotateFrame(normalize(P.camU), -normalize(P.camW));
@@ -462,7 +547,21 @@ PLT_D void measure(const FrameParams& P, SolveState& st, int bounceIdx, float pa
         pathContribution *= sum > kFltEps ? beam.spdf.x / sum : .0f;
     } else pathContribution *= 1.f / float(beam.comps);
     const float3 Lrgb = vmax(mk3(.0f), spectrumToRgb(beam.L, beam.wl, beam.comps) * pathContribution);
-    if (isfinite(Lrgb.x) && isfinite(Lrgb.y) && isfinite(Lrgb.z)) st.Lrgb += Lrgb;
+    return (isfinite(Lrgb.x) && isfinite(Lrgb.y) && isfinite(Lrgb.z)) ? Lrgb : mk3(0.f);
+}
+PLT_D void writeContribution(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float3 rgb) {
+    P.contrib[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = mk4(rgb.x, rgb.y, rgb.z, 0.f);
+}
+// Hands a sourced beam over to the unwind kernels (or measures it at once when nothing is left to replay).
+PLT_D void emitConnection(const FrameParams& P, uint32_t pixel, int bounceIdx, uint32_t kind, bool evalCurrentVertex, float pathContribution, Beam& beam) {
+    if (!evalCurrentVertex && bounceIdx == 0) { writeContribution(P, pixel, bounceIdx, kind, measure(P, bounceIdx, pathContribution, beam)); return; }
+    const uint32_t id = allocJob(P);
+    if (id >= P.jobCapacity) { atomicAdd(P.jobCount + 1, 1u); writeContribution(P, pixel, bounceIdx, kind, mk3(0.f)); return; }
+    JobHeader h;
+    h.pixel = pixel; h.bounceIdx = uint32_t(bounceIdx); h.kind = kind; h.firstIsCurrent = evalCurrentVertex; h.pathContribution = pathContribution;
+    h.q = uint32_t(evalCurrentVertex ? bounceIdx : bounceIdx - 1);
+    storeJob(P, id, beam, h);
+    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + pixel], id);
 }
 // pltpt_solve.rt.slang:205-217
 PLT_D bool wasNEEAvailable(const FrameParams& P, int bounceIdx, uint32_t flags) {
@@ -473,7 +572,7 @@ PLT_D float misWeight(float p0, float p1) { return p0 / (p0 + p1); }
 // pltpt_solve.rt.slang:152-200
 PLT_D void evalEmissive(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceIdx, const Bounce& bounce, const DevMaterial& m, const SD& sd, const TriHit& th) {
     const bool didNEE = wasNEEAvailable(P, bounceIdx, bounce.flags);
-    if (!(P.useEmissive && (m.propFlags & P_IsEmissive) && (P.doMIS || !didNEE))) return;
+    if (!(P.useEmissive && (m.propFlags & P_IsEmissive) && (P.doMIS || !didNEE))) { writeContribution(P, pixel, bounceIdx, 1, mk3(0.f)); return; }
     const bool needMIS = P.doMIS && didNEE;
     const uint32_t triIdx = getEmissiveTriangleIndex(P.sc, th.instanceID, th.primitiveIndex);
     const float3 hitN = sd.frontFacing ? sd.faceN : -sd.faceN;
@@ -484,12 +583,11 @@ PLT_D void evalEmissive(const FrameParams& P, SolveState& st, uint32_t pixel, in
     float4 wl = mk4(.0f);
     float4 Le = sampleSpectrum(P.sc.profiles, m.emissionId, st.wavelength, st.sg, P.opt.doImportanceSampleEmitters != 0, int(P.opt.HWSS), wl);
     Le *= w * rgbToSpectrum4(mk3(1.f), wl);
-    if (!anyPositive(Le, int(P.opt.HWSS))) return;
+    if (!anyPositive(Le, int(P.opt.HWSS))) { writeContribution(P, pixel, bounceIdx, 1, mk3(0.f)); return; }
     const float dist = length(st.pathOrigin - sd.posW);
     Beam beam = sourceBeamArea(sd.posW, bounce.wi, P.opt.sourcingAreaFromEmissiveGeometry, dist, Le, wl, P.opt.sourcingMaxBeamOmega, int(P.opt.HWSS));
     if (!P.opt.HWSSDoMIS && (bounce.flags & RF_HasDispersiveDeltaSegment)) beam.comps = 1;
-    forwardUnwind(P, st, pixel, bounceIdx, beam);
-    measure(P, st, bounceIdx, bounce.pathContribution, beam);
+    emitConnection(P, pixel, bounceIdx, 1, false, bounce.pathContribution, beam);
 }
 
 // ---- MNEE (Manifolds.slangh) ------------------------------------------------------------------------------------
@@ -564,7 +662,7 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
 }
 // Manifolds.slangh:165-281.  Kept out of line: its data-dependent Newton loop must not inflate the register budget of
 // the straight NEE path.
-__device__ __noinline__ bool manifoldNEESample(const FrameParams& P, TraversalCounters& tc, float3 visOrigin, float3 visDir, float visTMax, float3 origin, float3 lightPos, float3 lightDir,
+static __device__ __noinline__ bool manifoldNEESample(const FrameParams& P, TraversalCounters& tc, float3 visOrigin, float3 visDir, float visTMax, float3 origin, float3 lightPos, float3 lightDir,
                                                bool isDistantLight, int maxMSBounces, Rng& sg, ManifoldSampleData& data) {
     if (!traceMNEEOccluders(P, tc, visOrigin, visDir, 0.f, visTMax, sg, maxMSBounces, data)) return false;
     if (data.hitCount == 0) return true;
@@ -629,26 +727,27 @@ PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const Man
         VertexData v = getVertexData(P.sc, th, materialID);
         v.posW = r.hits[idx].posW;
         const float3 p2 = idx == 0 ? origin : r.hits[idx - 1].posW;
-        forwardUnwindStep(P, st, v, materialID, normalize(p2 - v.posW), r.hits[idx].lobe, beam);
+        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+        forwardUnwindStep(P, st.evals, v, materialID, m, normalize(p2 - v.posW), r.hits[idx].lobe, beam);
     }
 }
 
-// pltpt_solve.rt.slang:219-366 (NEE + evalNEE)
-PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceIdx, const Bounce& bounce, const SD& sd, const VertexData& V, const DevMaterial& m) {
+// pltpt_solve.rt.slang:245-366 (NEE).  Returns false when the connection carries nothing; otherwise `ls.beam` is the
+// MIS-weighted beam arriving at the vertex and `evalCurrentVertex` tells whether the vertex's own BSDF is still to be applied.
+PLT_D bool neeConnect(const FrameParams& P, SolveState& st, int bounceIdx, const Bounce& bounce, const SD& sd, const VertexData& V, const DevMaterial& m, LightSample& ls, bool& evalCurrentVertex) {
     const uint32_t lobes = m.lobes;
     const bool allowMSOnCurrentVertex = P.doMS && bounceIdx > 0 && !(bounce.flags & RF_LastBounceWasDelta) && (m.propFlags & P_CanMSReflective);
     const bool sampleReflection = (lobes & L_NonDeltaReflection) != 0 || allowMSOnCurrentVertex;
     const bool sampleTransmission = (lobes & L_NonDeltaTransmission) != 0;
-    if (!sampleReflection && !sampleTransmission) return;
-    LightSample ls;
+    if (!sampleReflection && !sampleTransmission) return false;
     const bool valid = generateLightSample(P, sd, sampleReflection, sampleTransmission, st.sg, st.tilesg, st.wavelength, P.opt.doImportanceSampleEmitters != 0, ls);
-    if (!valid || !anyPositive(ls.beam.L, int(P.opt.HWSS))) return;
+    if (!valid || !anyPositive(ls.beam.L, int(P.opt.HWSS))) return false;
     if (!P.opt.HWSSDoMIS && (bounce.flags & RF_HasDispersiveDeltaSegment)) ls.beam.comps = 1;
     const bool doMis = P.doMIS && ls.lightType != LT_Analytic;
-    bool evalCurrentVertex = true;
+    evalCurrentVertex = true;
     const int maxMSBounces = int(P.opt.maxBounces) - bounceIdx;
     if (!P.doMS || maxMSBounces <= 0) {
-        if (occluded(P, st.tc, ls.origin, ls.dir, .0f, ls.distance)) return;
+        if (occluded(P, st.tc, ls.origin, ls.dir, .0f, ls.distance)) return false;
         if (doMis) ls.beam.scale(misWeight(ls.pdf, bsdfPdf(m, sd, ls.dir, ls.beam.wl.x)));
     } else {
         const float3 lightDir = -ls.beam.r;
@@ -659,12 +758,12 @@ PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceI
         const bool isReflection = dot(sd.N, lightDir) * dot(sd.N, sd.V) > .0f;
         const bool currentVertexMS = isReflection && allowMSOnCurrentVertex;
         if (currentVertexMS) {
-            if (!manifoldSampleVertex(bounce.hit, sd, m, lightDir, st.sg, ms) || (ms.hits[0].lobe & L_Reflection) == 0) return;
+            if (!manifoldSampleVertex(bounce.hit, sd, m, lightDir, st.sg, ms) || (ms.hits[0].lobe & L_Reflection) == 0) return false;
         }
         const float3 origin = !currentVertexMS ? V.posW : st.pathOrigin;
         const bool ok = manifoldNEESample(P, st.tc, ls.origin, ls.dir, ls.distance, origin, ls.beam.posW, lightDir, ls.beam.distant, maxMSBounces, st.sg, ms);
         if (P.counters && ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)ms.iterations);
-        if (!ok || ms.pdf < 1e-6f) return;
+        if (!ok || ms.pdf < 1e-6f) return false;
         if (ms.hitCount > 0) {
             if (!P.opt.HWSSDoMIS && ms.dispersive) ls.beam.comps = 1;
             if (!ls.beam.distant) {
@@ -681,28 +780,17 @@ PLT_D void nee(const FrameParams& P, SolveState& st, uint32_t pixel, int bounceI
             ls.beam.scale(misWeight(ls.pdf, MISBsdfPdf * ms.pdf));
         }
     }
-    // evalNEE (pltpt_solve.rt.slang:219-243)
-    Beam& beam = ls.beam;
-    if (evalCurrentVertex) {
-        const SD forwardSd = prepareShadingData(V, sd.materialID, m, -beam.r);
-        beam.propagate(forwardSd.posW);
-        const BsdfCtx cx = {P.sc.profiles, int(P.opt.HWSS)};
-        bsdfEval(m, cx, forwardSd, bounce.wi, L_NonDelta, beam);
-        st.evals += uint32_t(beam.comps);
-        if (P.opt.HWSSDoMIS) beam.spdf *= bsdfLambdaPdf(m, cx, forwardSd, bounce.wi, L_NonDelta, beam, beam.wl);
-    }
-    forwardUnwind(P, st, pixel, bounceIdx, beam);
-    measure(P, st, bounceIdx, bounce.pathContribution, beam);
+    return true;
 }
 
-// pltpt_solve.rt.slang:401-476 (raygen).  Returns the number of recorded vertices; `evals` = eval calls x wavelengths.
-PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32_t& evals, TraversalCounters& tc) {
-    const uint32_t pixel = py * P.width + px;
+// pltpt_solve.rt.slang:401-476 (raygen), connection half: walks the recorded vertices of one path and emits its connection jobs.
+// Returns the number of recorded vertices.
+PLT_D uint32_t connectPixel(const FrameParams& P, uint32_t px, uint32_t py, uint32_t& evals, TraversalCounters& tc) {
+    const uint32_t pixel = (py - P.tileY0) * P.width + px;
     SolveState st;
     st.sg = Rng::seed(px, py, P.frameCount);
     st.tilesg = Rng::seed(px / P.opt.tileSize, py / P.opt.tileSize, P.frameCount << 2);
     st.wavelength = sampleHeroWavelength(st.sg.next1D());
-    st.Lrgb = mk3(0.f);
     st.pathOrigin = P.camPos;
     st.evals = 0;
     st.tc.nodes = st.tc.tris = 0;
@@ -712,22 +800,88 @@ PLT_D uint32_t solvePixel(const FrameParams& P, uint32_t px, uint32_t py, uint32
         if (bounce.flags & RF_Miss) break;  // onMiss handles env maps only (pltpt_solve.rt.slang:371-396); no env map support yet
         const TriHit th = unpackHit(P.sc, bounce.hit);
         uint32_t materialID;
-        const VertexData v = getVertexData(P.sc, th, materialID);
+        const VertexData v = readVertexCache(P, pixel, p, materialID);
         const DevMaterial m = loadMaterial(P.sc.materials, materialID);
         const SD sd = prepareShadingData(v, materialID, m, bounce.wi);
-        if (P.doNEE) nee(P, st, pixel, p, bounce, sd, v, m);
+        bool connected = false;
+        if (P.doNEE) {
+            LightSample ls;
+            bool evalCurrentVertex = true;
+            connected = neeConnect(P, st, p, bounce, sd, v, m, ls, evalCurrentVertex);
+            if (connected) emitConnection(P, pixel, p, 0, evalCurrentVertex, bounce.pathContribution, ls.beam);
+        }
+        if (!connected) writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
         evalEmissive(P, st, pixel, p, bounce, m, sd, th);
         if ((bounce.flags & RF_Terminated) || p == int(P.opt.maxBounces)) { ++p; break; }
         st.pathOrigin = v.posW;
-    }
-    if (P.color) P.color[pixel] = mk4(st.Lrgb.x, st.Lrgb.y, st.Lrgb.z, 1.f);
-    if (P.accum) {
-        double* a = P.accum + 4 * size_t(pixel);
-        a[0] += double(st.Lrgb.x); a[1] += double(st.Lrgb.y); a[2] += double(st.Lrgb.z); a[3] += 1.0;
     }
     evals = st.evals;
     tc = st.tc;
     return uint32_t(p);
 }
+
+// One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head).
+// Returns true while the job has further vertices to go through.
+PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t& evals, uint32_t& nextType) {
+    Beam beam;
+    JobHeader h;
+    loadJob(P, id, beam, h);
+    uint32_t materialID;
+    const VertexData v = readVertexCache(P, h.pixel, int(h.q), materialID);
+    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+    const float4 d = __ldcs(P.bDir + size_t(h.q) * P.pixelCount + h.pixel);
+    const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
+    const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
+    forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);
+    if (h.q == 0) {
+        writeContribution(P, h.pixel, h.bounceIdx, h.kind, measure(P, int(h.bounceIdx), h.pathContribution, beam));
+        return false;
+    }
+    h.q -= 1; h.firstIsCurrent = false;
+    storeJob(P, id, beam, h);
+    nextType = P.vMatType[size_t(h.q) * P.pixelCount + h.pixel];
+    return true;
+}
+
+// Sums a pixel's connections in the order the reference adds them (bounce ascending, NEE before emissive).
+PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
+    float3 L = mk3(0.f);
+    for (int p = 0; p <= int(P.opt.maxBounces); ++p) {
+        const uint32_t flags = __float_as_uint(P.bDir[size_t(p) * P.pixelCount + pixel].w);
+        if (flags & RF_Miss) break;
+        const float4 a = __ldcs(P.contrib + size_t(2 * p) * P.pixelCount + pixel), b = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel);
+        L += mk3(a.x, a.y, a.z);
+        L += mk3(b.x, b.y, b.z);
+        if (flags & RF_Terminated) break;
+    }
+    if (P.color) P.color[P.outOffset + pixel] = mk4(L.x, L.y, L.z, 1.f);
+    if (P.accum) {
+        double* a = P.accum + 4 * size_t(P.outOffset + pixel);
+        a[0] += double(L.x); a[1] += double(L.y); a[2] += double(L.z); a[3] += 1.0;
+    }
+}
+
+// ---- kernel-side helpers shared by the stage translation units --------------------------------------------------------
+constexpr int kStageThreads = 128;
+// Pixels are assigned to threads in 8x4 tiles per warp so that a warp's primary rays (and its bounce-record lines) stay coherent.
+PLT_D bool pixelOfThread(const FrameParams& P, uint32_t& px, uint32_t& py) {
+    const uint32_t tilesX = (P.width + 7) / 8;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    px = (warp % tilesX) * 8 + (lane & 7);
+    const uint32_t ly = (warp / tilesX) * 4 + (lane >> 3);
+    py = P.tileY0 + ly;
+    return px < P.width && ly < P.tileRows;
+}
+PLT_D void warpAdd(unsigned long long* dst, uint32_t v) {  // all 32 lanes must call
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// stage launchers (stage_sample.cu, stage_connect.cu, stage_unwind.cu)
+void launchSampleStage(const FrameParams& P, uint32_t blocks, cudaStream_t s);
+void launchConnectStage(const FrameParams& P, uint32_t blocks, cudaStream_t s);
+void launchUnwindIteration(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchResolve(const FrameParams& P, cudaStream_t s);
+void launchGatherBounces(const FrameParams& P, PltptBounce* out, uint32_t records, cudaStream_t s);
 
 }  // namespace plt

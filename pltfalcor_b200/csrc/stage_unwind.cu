@@ -1,0 +1,66 @@
+// stage_unwind.cu — second half of the solve stage: the forward replay (reference forwardUnwind, pltpt_solve.rt.slang:48-79,
+// evalNEE :219-243, measure :96-147) as a wavefront.  One launch of k_unwind_step advances every live connection job by ONE
+// recorded vertex; jobs are walked in MaterialType order, 128 same-type jobs per CTA, so a warp executes one BSDF.
+#include "plt_integrator.cuh"
+
+namespace plt {
+namespace {
+// Counting-sort scatter of the pending list into material-type order.  Runs between two step launches; it also publishes the
+// number of sorted entries and clears the histogram for the next iteration (last block done).
+__global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ FrameParams P) {
+    __shared__ uint32_t offs[kQueueTypes];
+    uint32_t* qc = P.queueCount;
+    const uint32_t total = qc[kQueueTypes];
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < kQueueTypes; ++t) { offs[t] = run; run += qc[t]; }
+    }
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t type = P.pendingType[i];
+        // warp-aggregated cursor bump per type
+        const uint32_t active = __activemask();
+        const uint32_t peers = __match_any_sync(active, type);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(qc + kQueueTypes + 1 + type, uint32_t(__popc(peers)));
+        base = __shfl_sync(peers, base, leader);
+        P.sorted[offs[type] + base + __popc(peers & ((1u << lane) - 1u))] = P.pending[i];
+    }
+}
+// Publishes the sorted count and resets histogram / cursors / pending count (single thread; stream-ordered after k_sort_queue).
+__global__ void k_flip_queue(const __grid_constant__ FrameParams P) {
+    uint32_t* qc = P.queueCount;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        qc[2 * kQueueTypes + 2] = qc[kQueueTypes];
+        for (int t = 0; t <= 2 * kQueueTypes + 1; ++t) qc[t] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_unwind_step(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.queueCount[2 * kQueueTypes + 2];
+    uint32_t evals = 0;
+    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < n) {
+            uint32_t nextType = 0;
+            const uint32_t id = P.sorted[i];
+            if (unwindStep(P, id, evals, nextType)) enqueueJob(P, nextType, id);
+        }
+    }
+    warpAdd(P.counters + 0, evals);
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FrameParams P) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel < P.pixelCount) resolvePixel(P, pixel);
+}
+}  // namespace
+
+void launchUnwindIteration(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    k_sort_queue<<<grid, 256, 0, s>>>(P);
+    k_flip_queue<<<1, 32, 0, s>>>(P);
+    k_unwind_step<<<grid, kStageThreads, 0, s>>>(P);
+}
+void launchResolve(const FrameParams& P, cudaStream_t s) { k_resolve<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
+}  // namespace plt

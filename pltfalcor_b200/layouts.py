@@ -154,5 +154,5 @@ class PltptStats(C.Structure):
         ("traversalStackOverflows", C.c_uint64), ("mneeIterations", C.c_uint64),
         ("framesRendered", C.c_uint64), ("sampleStageMs", C.c_double), ("solveStageMs", C.c_double),
         ("totalPathVertices", C.c_uint64), ("totalReplaySteps", C.c_uint64), ("totalBsdfEvals", C.c_uint64),
-        ("traversalNodesVisited", C.c_uint64), ("traversalTrianglesTested", C.c_uint64),
+        ("traversalNodesVisited", C.c_uint64), ("traversalTrianglesTested", C.c_uint64), ("droppedConnections", C.c_uint64),
     ]
