@@ -82,7 +82,7 @@ struct PltptContext {
     std::vector<uint32_t> hInstTriOffset;
     uint32_t emissiveTriangleCount = 0, lightCount = 0;
     // per-frame work buffers (integrator.cu)
-    plt::DevBuf work[24];
+    plt::DevBuf work[32];
     uint32_t workW = 0, workH = 0, workBounces = 0;
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};

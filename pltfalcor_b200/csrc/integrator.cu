@@ -9,7 +9,7 @@ namespace plt {
 namespace {
 // worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
 size_t workBytesPerPixel(uint32_t records) {
-    return size_t(records) * (16 + 16 + 8 + 64 + 1) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16;
+    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16 + 6 * 16 + 4;
 }
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
@@ -43,8 +43,11 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     PLT_CUDA(c->work[11].ensure(jobCapacity * 4));
     PLT_CUDA(c->work[12].ensure(jobCapacity));
     PLT_CUDA(c->work[13].ensure(jobCapacity * 4));
-    PLT_CUDA(c->work[14].ensure(64 * 4));
+    PLT_CUDA(c->work[14].ensure(256 * 4));
     PLT_CUDA(c->work[15].ensure(jobCapacity * sizeof(float4)));  // contrib: 2 * records float4
+    for (int k = 0; k < 7; ++k) PLT_CUDA(c->work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
+    PLT_CUDA(c->work[4].ensure(size_t(tilePixels) * 4));                                    // trace queue
+    PLT_CUDA(c->work[23].ensure(records * 4));                                               // per-bounce type-sorted hit lists
     P.bHit = c->work[0].as<uint4>();
     P.bDir = c->work[1].as<float4>();
     P.bPdf = c->work[2].as<float2>();
@@ -59,6 +62,11 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     P.queueCount = c->work[14].as<uint32_t>();
     P.jobCount = P.queueCount + 32;
     P.contrib = c->work[15].as<float4>();
+    P.psRng = c->work[16].as<uint4>(); P.psOrigin = c->work[17].as<float4>(); P.psDir = c->work[18].as<float4>(); P.psPdf = c->work[19].as<float4>();
+    P.psHit = c->work[20].as<uint4>(); P.ssRng = c->work[21].as<uint4>(); P.ssTileRng = c->work[22].as<uint4>();
+    P.traceQueue = c->work[4].as<uint32_t>();
+    P.vertexList = c->work[23].as<uint32_t>();
+    P.levelCount = P.queueCount + 64;
     c->workW = w; c->workH = h; c->workBounces = recordsPerPixel;
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
@@ -79,20 +87,36 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
         P.tileRows = std::min(tileRows, P.height - y0);
         P.outOffset = y0 * P.width;
         P.pixelCount = P.tileRows * P.width;
-        const uint32_t warps = ((P.width + 7) / 8) * ((P.tileRows + 3) / 4);
-        const uint32_t blocks = (warps * 32 + kStageThreads - 1) / kStageThreads;
         cudaEvent_t* ev = &c->timerEvents[3 * c->timerCount];
         const bool timed = y0 == 0;  // stage timers cover the first tile of a frame (the only one unless the frame is tiled)
+        const uint32_t maxB = c->opt.maxBounces;
+        if (maxB > 63) { setError("maxBounces > 63 is not supported by the wavefront queues"); return PLTPT_ERR_INVALID_ARGUMENT; }
         if (timed) cudaEventRecord(ev[0], s);
-        launchSampleStage(P, blocks, s);
+        // ---- sample stage
+        PLT_CUDA(cudaMemsetAsync(P.queueCount, 0, 256 * 4, s));
+        launchRaygen(P, s);
         c->stats.kernelLaunches++;
+        for (uint32_t b = 0; b <= maxB; ++b) {
+            P.level = b;
+            launchTrace(P, persistentGrid, s);
+            launchSortFlip(P, SortView{P.vertexList + size_t(b) * P.pixelCount, P.levelCount + b}, true, persistentGrid, s);
+            launchShade(P, persistentGrid, s);
+            c->stats.kernelLaunches += 4;
+        }
         if (timed) cudaEventRecord(ev[1], s);
-        if (bouncesOut) { launchGatherBounces(P, bouncesOut, c->opt.maxBounces + 1, s); c->stats.kernelLaunches++; }
+        if (bouncesOut) { launchGatherBounces(P, bouncesOut, maxB + 1, s); c->stats.kernelLaunches++; }
         if (solve) {
-            PLT_CUDA(cudaMemsetAsync(P.queueCount, 0, 64 * 4, s));
-            launchConnectStage(P, blocks, s);
-            c->stats.kernelLaunches++;
-            for (uint32_t it = 0; it <= c->opt.maxBounces; ++it) { launchUnwindIteration(P, persistentGrid, s); c->stats.kernelLaunches += 3; }
+            // ---- solve stage: connect per vertex index, then the replay wavefront, then the deterministic per-pixel sum
+            for (uint32_t b = 0; b <= maxB; ++b) {
+                P.level = b;
+                launchConnect(P, persistentGrid, s);
+                c->stats.kernelLaunches++;
+            }
+            for (uint32_t it = 0; it <= maxB; ++it) {
+                launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2}, false, persistentGrid, s);
+                launchUnwindStep(P, persistentGrid, s);
+                c->stats.kernelLaunches += 3;
+            }
             launchResolve(P, s);
             c->stats.kernelLaunches++;
         }
@@ -183,10 +207,10 @@ int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraDat
     if (c->timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
     const uint32_t records = c->opt.maxBounces + 1;
     const size_t bytes = size_t(w) * h * records * sizeof(PltptBounce);
-    PLT_CUDA(c->work[4].ensure(bytes));
-    if (int r = renderTiles(c, P, tileRows, false, c->work[4].as<PltptBounce>(), 0)) return r;
-    PLT_CUDA(cudaMemcpy(host, c->work[4].p, bytes, cudaMemcpyDeviceToHost));
-    c->work[4].release();
+    PLT_CUDA(c->work[25].ensure(bytes));
+    if (int r = renderTiles(c, P, tileRows, false, c->work[25].as<PltptBounce>(), 0)) return r;
+    PLT_CUDA(cudaMemcpy(host, c->work[25].p, bytes, cudaMemcpyDeviceToHost));
+    c->work[25].release();
     return PLTPT_OK;
 }
 

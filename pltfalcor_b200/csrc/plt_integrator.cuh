@@ -40,6 +40,19 @@ struct FrameParams {
     uint32_t* queueCount;    // [0..kQueueTypes) per-type counts of `pending`, [kQueueTypes] total, [kQueueTypes+1 ..] scatter cursors,
                              // [2*kQueueTypes+2] number of entries of `sorted`
     uint32_t tileY0, tileRows, outOffset;  // row tile of the frame processed by this launch sequence (work buffers are tile-local)
+    // sample-stage wavefront: per-path state (SoA, one float4 plane each) and the closest hit of the current bounce
+    uint4* psRng;            // xoshiro128** state of the path
+    float4* psOrigin;        // origin.xyz | hero wavelength
+    float4* psDir;           // dir.xyz | weight
+    float4* psPdf;           // pdf, thp_modifier, lastNonDeltaPdf, asfloat(flags | length << 8)   (flags use bits 0-5 and 16-31)
+    uint4* psHit;            // instanceID, primitiveIndex, asuint(u), asuint(v)
+    uint32_t* traceQueue;    // paths whose next ray is to be traced (appended by the shade kernel)
+    uint32_t* vertexList;    // [(maxBounces+1)][pixelCount] paths with a recorded hit at bounce b, grouped by MaterialType
+    uint32_t* levelCount;    // [0 .. maxBounces] entries of vertexList per bounce; [64] trace-queue count
+    // solve-stage per-path state
+    uint4* ssRng;            // random-number state of the solve stage (continues from vertex to vertex)
+    uint4* ssTileRng;        // per-tile generator (NEEUsePerTileSG)
+    uint32_t level;          // bounce / vertex index the current launch works on
     float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection, summed in fixed order by the resolve kernel
     float4* color;     // RGBA32F (may be null when accum is used)
     float4* albedo;
@@ -122,7 +135,6 @@ struct PathState {  // Path.slang:146-196
     uint32_t flags;
     int length;
     float lastNonDeltaPdf;
-    TraversalCounters tc;
 };
 // Camera.slang:46-78 (computeRayPinhole)
 PLT_D void cameraRay(const FrameParams& P, uint32_t px, uint32_t py, float3& origin, float3& dir) {
@@ -138,7 +150,8 @@ PLT_D float russianRoulette(float rrVal, float u) {
     return u < p ? .0f : 1.f - p;
 }
 // pltpt_sample.rt.slang:63-141 (scatterTriangleMeshClosestHit)
-PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& path, const TriHit& th) {
+// Returns true when the hit was alpha-masked: the origin moved behind the surface and the same ray has to be re-traced.
+PLT_D bool scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& path, const TriHit& th) {
     const uint4 hitInfo = packHit(P.sc, th);
     uint32_t materialID;
     const VertexData v = getVertexData(P.sc, th, materialID);
@@ -147,7 +160,7 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     const SD sd = prepareShadingData(v, materialID, m, wi);
     if (P.opt.alphaMasking && m.opacity == .0f) {
         path.origin = sd.computeNewRayOrigin(false);
-        return;
+        return true;
     }
     const float rcp_thp = P.opt.doRussianRoulette ? russianRoulette(1.f - path.weight, path.sg.next1D()) : 1.f;
     bool shouldEndPath = path.length == int(P.opt.maxBounces) || (rcp_thp == .0f && path.length > 0);
@@ -170,7 +183,7 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     if (shouldEndPath) {
         path.flags |= RF_Terminated;
         writeBounce(P, pixel, path.length, hitInfo, wi, 0u, path.flags, 1.f / (path.pdf * path.thp), path.lastNonDeltaPdf);
-        return;
+        return false;
     }
     path.weight *= bs.weight;
     path.thp *= rcp_thp;
@@ -185,12 +198,40 @@ PLT_D void scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     if (!isDelta) path.flags &= ~RF_OnlyDelta;
     path.origin = sd.computeNewRayOrigin(isReflection);
     path.dir = bs.wo;
+    return false;
 }
-// pltpt_sample.rt.slang:146-185 (raygen)
-PLT_D TraversalCounters samplePixel(const FrameParams& P, uint32_t px, uint32_t py) {
-    const uint32_t pixel = (py - P.tileY0) * P.width + px;
+// ---- sample-stage wavefront ---------------------------------------------------------------------------------------------
+// raygen -> [trace -> sort by hit material -> shade] per bounce.  A path lives in the ps* planes between kernels.
+PLT_D void storePath(const FrameParams& P, uint32_t pixel, const PathState& path) {
+    P.psRng[pixel] = make_uint4(path.sg.s0, path.sg.s1, path.sg.s2, path.sg.s3);
+    P.psOrigin[pixel] = mk4(path.origin.x, path.origin.y, path.origin.z, path.wavelength);
+    P.psDir[pixel] = mk4(path.dir.x, path.dir.y, path.dir.z, path.weight);
+    P.psPdf[pixel] = mk4(path.pdf, path.thp, path.lastNonDeltaPdf, __uint_as_float(path.flags | (uint32_t(path.length) << 8)));
+}
+PLT_D void loadPath(const FrameParams& P, uint32_t pixel, PathState& path) {
+    const uint4 r = P.psRng[pixel];
+    const float4 o = P.psOrigin[pixel], d = P.psDir[pixel], q = P.psPdf[pixel];
+    path.sg = Rng{r.x, r.y, r.z, r.w};
+    path.origin = mk3(o.x, o.y, o.z); path.wavelength = o.w;
+    path.dir = mk3(d.x, d.y, d.z); path.weight = d.w;
+    path.pdf = q.x; path.thp = q.y; path.lastNonDeltaPdf = q.z;
+    const uint32_t fl = __float_as_uint(q.w);
+    path.flags = fl & ~0xff00u; path.length = int((fl >> 8) & 0xffu);
+}
+PLT_D void pixelCoords(const FrameParams& P, uint32_t pixel, uint32_t& px, uint32_t& py) { px = pixel % P.width; py = P.tileY0 + pixel / P.width; }
+// i-th entry of the implicit bounce-0 trace queue: pixels in 8x4 tiles so that a warp's primary rays stay coherent
+PLT_D bool primaryPixel(const FrameParams& P, uint32_t i, uint32_t& pixel) {
+    const uint32_t tilesX = (P.width + 7) / 8;
+    const uint32_t warp = i >> 5, lane = i & 31;
+    const uint32_t lx = (warp % tilesX) * 8 + (lane & 7), ly = (warp / tilesX) * 4 + (lane >> 3);
+    pixel = ly * P.width + lx;
+    return lx < P.width && ly < P.tileRows;
+}
+// pltpt_sample.rt.slang:146-166 (raygen up to the first TraceRay)
+PLT_D void raygenPixel(const FrameParams& P, uint32_t pixel) {
+    uint32_t px, py;
+    pixelCoords(P, pixel, px, py);
     PathState path;
-    path.tc.nodes = path.tc.tris = 0;
     path.sg = Rng::seed(px, py, P.frameCount);
     path.wavelength = sampleHeroWavelength(path.sg.next1D());
     if (P.normal) P.normal[P.outOffset + pixel] = mk4(0.f);
@@ -199,16 +240,45 @@ PLT_D TraversalCounters samplePixel(const FrameParams& P, uint32_t px, uint32_t 
     path.weight = path.pdf = path.thp = 1.f;
     path.flags = RF_OnlyDelta;
     path.lastNonDeltaPdf = 0.f;
-    int guard = 0;  // bound on alpha-mask pass-throughs, which do not advance `length`
-    for (path.length = 0; path.length < int(P.opt.maxBounces) + 1 && (path.flags & (RF_Miss | RF_Terminated)) == 0 && guard < 4096; ++guard) {
-        TriHit th;
+    path.length = 0;
+    storePath(P, pixel, path);
+}
+// TraceRay + scatterMiss (pltpt_sample.rt.slang:55-61,174-183).  Returns the MaterialType of the hit (0 = miss, path ended).
+PLT_D uint32_t tracePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc) {
+    const float4 o = P.psOrigin[pixel], d = P.psDir[pixel];
+    TriHit th;
+    float t;
+    if (!traceClosestHit(P, tc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.f, kFltMax, th, t)) {
+        const float4 q = P.psPdf[pixel];
+        const uint32_t fl = __float_as_uint(q.w);
+        const uint32_t flags = (fl & ~0xff00u) | RF_Miss;
+        writeBounce(P, pixel, int((fl >> 8) & 0xffu), make_uint4(0, 0, 0, 0), mk3(-d.x, -d.y, -d.z), 0u, flags, 1.f / (q.x * q.y), q.z);
+        return 0u;
+    }
+    P.psHit[pixel] = make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v));
+    const uint32_t materialID = __ldg(&P.sc.instances[th.instanceID].materialID);
+    return __ldg(&P.sc.materials[materialID].type);
+}
+// scatterTriangleMeshClosestHit on the stored hit; returns true when the path continues with a new ray.
+PLT_D bool shadePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc) {
+    PathState path;
+    loadPath(P, pixel, path);
+    const uint4 h = P.psHit[pixel];
+    TriHit th;
+    th.instanceID = h.x; th.primitiveIndex = h.y; th.u = __uint_as_float(h.z); th.v = __uint_as_float(h.w);
+    // Alpha-masked hits do not count as a bounce (pltpt_sample.rt.slang:83-87): the ray is re-traced at once from behind the
+    // surface.  (Rare: kept inline instead of a round trip through the queues; bounded like the oracle's pass-through guard.)
+    for (int guard = 0; scatterClosestHit(P, pixel, path, th); ++guard) {
         float t;
-        if (!traceClosestHit(P, path.tc, path.origin, path.dir, 0.f, kFltMax, th, t)) {
+        if (guard >= 4096 || !traceClosestHit(P, tc, path.origin, path.dir, 0.f, kFltMax, th, t)) {
             path.flags |= RF_Miss;
             writeBounce(P, pixel, path.length, make_uint4(0, 0, 0, 0), -path.dir, 0u, path.flags, 1.f / (path.pdf * path.thp), path.lastNonDeltaPdf);
-        } else scatterClosestHit(P, pixel, path, th);
+            return false;
+        }
     }
-    return path.tc;
+    if (path.flags & (RF_Miss | RF_Terminated)) return false;
+    storePath(P, pixel, path);
+    return true;
 }
 
 // ---- light sampling (LightSampling.slangh, Rendering/Lights/*.slang) ---------------------------------------------
@@ -783,41 +853,50 @@ PLT_D bool neeConnect(const FrameParams& P, SolveState& st, int bounceIdx, const
     return true;
 }
 
-// pltpt_solve.rt.slang:401-476 (raygen), connection half: walks the recorded vertices of one path and emits its connection jobs.
-// Returns the number of recorded vertices.
-PLT_D uint32_t connectPixel(const FrameParams& P, uint32_t px, uint32_t py, uint32_t& evals, TraversalCounters& tc) {
-    const uint32_t pixel = (py - P.tileY0) * P.width + px;
+// pltpt_solve.rt.slang:401-476 (raygen), connection half, for ONE recorded vertex of one path (vertex index P.level).  The
+// random-number state of the path's solve stage is carried from vertex to vertex in ssRng (the reference consumes it sequentially).
+PLT_D void connectVertex(const FrameParams& P, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
+    const int p = int(P.level);
+    uint32_t px, py;
+    pixelCoords(P, pixel, px, py);
     SolveState st;
-    st.sg = Rng::seed(px, py, P.frameCount);
-    st.tilesg = Rng::seed(px / P.opt.tileSize, py / P.opt.tileSize, P.frameCount << 2);
-    st.wavelength = sampleHeroWavelength(st.sg.next1D());
-    st.pathOrigin = P.camPos;
     st.evals = 0;
     st.tc.nodes = st.tc.tris = 0;
-    int p = 0;
-    for (;; ++p) {
-        const Bounce bounce = readBounce(P, pixel, p);
-        if (bounce.flags & RF_Miss) break;  // onMiss handles env maps only (pltpt_solve.rt.slang:371-396); no env map support yet
-        const TriHit th = unpackHit(P.sc, bounce.hit);
-        uint32_t materialID;
-        const VertexData v = readVertexCache(P, pixel, p, materialID);
-        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-        const SD sd = prepareShadingData(v, materialID, m, bounce.wi);
-        bool connected = false;
-        if (P.doNEE) {
-            LightSample ls;
-            bool evalCurrentVertex = true;
-            connected = neeConnect(P, st, p, bounce, sd, v, m, ls, evalCurrentVertex);
-            if (connected) emitConnection(P, pixel, p, 0, evalCurrentVertex, bounce.pathContribution, ls.beam);
-        }
-        if (!connected) writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
-        evalEmissive(P, st, pixel, p, bounce, m, sd, th);
-        if ((bounce.flags & RF_Terminated) || p == int(P.opt.maxBounces)) { ++p; break; }
-        st.pathOrigin = v.posW;
+    uint32_t materialID;
+    const VertexData v = readVertexCache(P, pixel, p, materialID);
+    if (p == 0) {
+        st.sg = Rng::seed(px, py, P.frameCount);
+        st.wavelength = sampleHeroWavelength(st.sg.next1D());
+        st.pathOrigin = P.camPos;
+        if (P.perTileSG) st.tilesg = Rng::seed(px / P.opt.tileSize, py / P.opt.tileSize, P.frameCount << 2);
+    } else {
+        const uint4 r = P.ssRng[pixel];
+        st.sg = Rng{r.x, r.y, r.z, r.w};
+        st.wavelength = P.psOrigin[pixel].w;  // hero wavelength: the first draw of both stages' generators (pltpt_solve.rt.slang:415)
+        const float4 prev = P.vc0[size_t(p - 1) * P.pixelCount + pixel];
+        st.pathOrigin = mk3(prev.x, prev.y, prev.z);
+        if (P.perTileSG) { const uint4 tr = P.ssTileRng[pixel]; st.tilesg = Rng{tr.x, tr.y, tr.z, tr.w}; }
+    }
+    if (!P.perTileSG) st.tilesg = st.sg;
+    const Bounce bounce = readBounce(P, pixel, p);
+    const TriHit th = unpackHit(P.sc, bounce.hit);
+    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+    const SD sd = prepareShadingData(v, materialID, m, bounce.wi);
+    bool connected = false;
+    if (P.doNEE) {
+        LightSample ls;
+        bool evalCurrentVertex = true;
+        connected = neeConnect(P, st, p, bounce, sd, v, m, ls, evalCurrentVertex);
+        if (connected) emitConnection(P, pixel, p, 0, evalCurrentVertex, bounce.pathContribution, ls.beam);
+    }
+    if (!connected) writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+    evalEmissive(P, st, pixel, p, bounce, m, sd, th);
+    if (!(bounce.flags & RF_Terminated) && p < int(P.opt.maxBounces)) {
+        P.ssRng[pixel] = make_uint4(st.sg.s0, st.sg.s1, st.sg.s2, st.sg.s3);
+        if (P.perTileSG) P.ssTileRng[pixel] = make_uint4(st.tilesg.s0, st.tilesg.s1, st.tilesg.s2, st.tilesg.s3);
     }
     evals = st.evals;
     tc = st.tc;
-    return uint32_t(p);
 }
 
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head).
@@ -877,10 +956,17 @@ PLT_D void warpAdd(unsigned long long* dst, uint32_t v) {  // all 32 lanes must 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
+// Counting-sort view: `pending`/`pendingType`/`hist` are filled by a producer kernel; k_sort_queue scatters the ids into
+// `dst` grouped by type and k_flip_queue publishes the count in *dstCount and clears the histogram (stage_unwind.cu).
+struct SortView { uint32_t* dst; uint32_t* dstCount; };
+
 // stage launchers (stage_sample.cu, stage_connect.cu, stage_unwind.cu)
-void launchSampleStage(const FrameParams& P, uint32_t blocks, cudaStream_t s);
-void launchConnectStage(const FrameParams& P, uint32_t blocks, cudaStream_t s);
-void launchUnwindIteration(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchRaygen(const FrameParams& P, cudaStream_t s);
+void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnect(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
+void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchResolve(const FrameParams& P, cudaStream_t s);
 void launchGatherBounces(const FrameParams& P, PltptBounce* out, uint32_t records, cudaStream_t s);
 

@@ -5,9 +5,8 @@
 
 namespace plt {
 namespace {
-// Counting-sort scatter of the pending list into material-type order.  Runs between two step launches; it also publishes the
-// number of sorted entries and clears the histogram for the next iteration (last block done).
-__global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ FrameParams P) {
+// Counting-sort scatter of the pending list into material-type order (dst).  Runs between a producer and a consumer launch.
+__global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ FrameParams P, SortView view) {
     __shared__ uint32_t offs[kQueueTypes];
     uint32_t* qc = P.queueCount;
     const uint32_t total = qc[kQueueTypes];
@@ -25,15 +24,16 @@ __global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ Fram
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(qc + kQueueTypes + 1 + type, uint32_t(__popc(peers)));
         base = __shfl_sync(peers, base, leader);
-        P.sorted[offs[type] + base + __popc(peers & ((1u << lane) - 1u))] = P.pending[i];
+        view.dst[offs[type] + base + __popc(peers & ((1u << lane) - 1u))] = P.pending[i];
     }
 }
 // Publishes the sorted count and resets histogram / cursors / pending count (single thread; stream-ordered after k_sort_queue).
-__global__ void k_flip_queue(const __grid_constant__ FrameParams P) {
+__global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView view, bool resetTraceQueue) {
     uint32_t* qc = P.queueCount;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        qc[2 * kQueueTypes + 2] = qc[kQueueTypes];
+        *view.dstCount = qc[kQueueTypes];
         for (int t = 0; t <= 2 * kQueueTypes + 1; ++t) qc[t] = 0;
+        if (resetTraceQueue) P.levelCount[64] = 0;
     }
 }
 
@@ -57,10 +57,10 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FramePa
 }
 }  // namespace
 
-void launchUnwindIteration(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    k_sort_queue<<<grid, 256, 0, s>>>(P);
-    k_flip_queue<<<1, 32, 0, s>>>(P);
-    k_unwind_step<<<grid, kStageThreads, 0, s>>>(P);
+void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s) {
+    k_sort_queue<<<grid, 256, 0, s>>>(P, v);
+    k_flip_queue<<<1, 32, 0, s>>>(P, v, resetTraceQueue);
 }
+void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_unwind_step<<<grid, kStageThreads, 0, s>>>(P); }
 void launchResolve(const FrameParams& P, cudaStream_t s) { k_resolve<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
 }  // namespace plt
