@@ -9,7 +9,7 @@ namespace plt {
 namespace {
 // worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
 size_t workBytesPerPixel(uint32_t records) {
-    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16 + 6 * 16 + 4;
+    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * sizeof(MneeItem) + sizeof(ConnItem) + 32 + 16 + 4;
 }
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
@@ -48,6 +48,11 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     for (int k = 0; k < 7; ++k) PLT_CUDA(c->work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
     PLT_CUDA(c->work[4].ensure(size_t(tilePixels) * 4));                                    // trace queue
     PLT_CUDA(c->work[23].ensure(records * 4));                                               // per-bounce type-sorted hit lists
+    PLT_CUDA(c->work[26].ensure(size_t(2) * tilePixels * sizeof(MneeItem)));                 // parked manifold walks
+    PLT_CUDA(c->work[27].ensure(size_t(tilePixels) * sizeof(ConnItem)));
+    PLT_CUDA(c->work[28].ensure(size_t(tilePixels) * 32));
+    PLT_CUDA(c->work[29].ensure(size_t(tilePixels) * 16));
+    PLT_CUDA(c->work[30].ensure(size_t(tilePixels) * 4));
     P.bHit = c->work[0].as<uint4>();
     P.bDir = c->work[1].as<float4>();
     P.bPdf = c->work[2].as<float2>();
@@ -67,6 +72,13 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     P.traceQueue = c->work[4].as<uint32_t>();
     P.vertexList = c->work[23].as<uint32_t>();
     P.levelCount = P.queueCount + 64;
+    P.mneeItems = c->work[26].as<MneeItem>();
+    P.mneeCount = P.queueCount + 34;
+    P.mneeCapacity = 2 * tilePixels;
+    P.connItems = c->work[27].as<ConnItem>();
+    P.shadowRays = c->work[28].as<float4>();
+    P.shadowHits = c->work[29].as<uint4>();
+    P.shadowT = c->work[30].as<float>();
     c->workW = w; c->workH = h; c->workBounces = recordsPerPixel;
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
@@ -109,9 +121,10 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
             // ---- solve stage: connect per vertex index, then the replay wavefront, then the deterministic per-pixel sum
             for (uint32_t b = 0; b <= maxB; ++b) {
                 P.level = b;
-                launchConnect(P, persistentGrid, s);
-                c->stats.kernelLaunches++;
+                launchConnectLevel(P, persistentGrid, s);
+                c->stats.kernelLaunches += 3;
             }
+            if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches++; }
             for (uint32_t it = 0; it <= maxB; ++it) {
                 launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2}, false, persistentGrid, s);
                 launchUnwindStep(P, persistentGrid, s);

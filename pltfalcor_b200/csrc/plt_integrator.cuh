@@ -13,6 +13,7 @@ namespace plt {
 // Path.slang:47-109
 enum : uint32_t { RF_LastBounceWasDelta = 0x1, RF_HasDispersiveDeltaSegment = 0x2, RF_OnlyDelta = 0x4, RF_Miss = 0x10, RF_Terminated = 0x20, RF_MSMask = 0xffff0000u };
 
+struct MneeItem;
 struct FrameParams {
     DevScene sc;
     PltptOptions opt;
@@ -53,6 +54,13 @@ struct FrameParams {
     uint4* ssRng;            // random-number state of the solve stage (continues from vertex to vertex)
     uint4* ssTileRng;        // per-tile generator (NEEUsePerTileSG)
     uint32_t level;          // bounce / vertex index the current launch works on
+    MneeItem* mneeItems;     // connections parked for the manifold-walk kernel
+    struct ConnItem* connItems;  // [pixelCount] hand-over between the two connect halves, indexed like the level's work list
+    float4* shadowRays;      // [2 * pixelCount] origin|tmin, dir|tmax of the NEE shadow rays
+    uint4* shadowHits;       // [pixelCount] instanceID (0xffffffff = nothing hit), primitiveIndex, asuint(u), asuint(v)
+    float* shadowT;          // [pixelCount]
+    uint32_t* mneeCount;
+    uint32_t mneeCapacity;
     float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection, summed in fixed order by the resolve kernel
     float4* color;     // RGBA32F (may be null when accum is used)
     float4* albedo;
@@ -685,12 +693,15 @@ PLT_D bool manifoldSampleVertex(uint4 hitInfo, const SD& sd, const DevMaterial& 
     return true;
 }
 // Manifolds.slangh:110-160
-PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float3 rayOrigin, float3 rayDir, float rayTMin, float rayTMax, Rng& sg, int maxMSBounces, ManifoldSampleData& data) {
+// `first` (optional): the closest hit of the first segment, already found by the shadow-ray trace kernel.
+PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float3 rayOrigin, float3 rayDir, float rayTMin, float rayTMax, Rng& sg, int maxMSBounces, ManifoldSampleData& data,
+                              const TriHit* first = nullptr, float firstT = 0.f) {
     const float3 wi = -rayDir;
-    for (;;) {
+    for (bool useFirst = first != nullptr;; useFirst = false) {
         TriHit th;
         float t;
-        if (!traceClosestHit(P, tc, rayOrigin, rayDir, rayTMin, rayTMax, th, t)) return true;
+        if (useFirst) { th = *first; t = firstT; }
+        else if (!traceClosestHit(P, tc, rayOrigin, rayDir, rayTMin, rayTMax, th, t)) return true;
         if (data.hitCount >= int(P.opt.MNEEMaxOccluders) || data.hitCount >= maxMSBounces) return false;
         uint32_t materialID;
         VertexData v = getVertexData(P.sc, th, materialID);
@@ -730,12 +741,10 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
     positionStepDir = p.ddu * dX.x + p.ddv * dX.y;
     return true;
 }
-// Manifolds.slangh:165-281.  Kept out of line: its data-dependent Newton loop must not inflate the register budget of
-// the straight NEE path.
-static __device__ __noinline__ bool manifoldNEESample(const FrameParams& P, TraversalCounters& tc, float3 visOrigin, float3 visDir, float visTMax, float3 origin, float3 lightPos, float3 lightDir,
-                                               bool isDistantLight, int maxMSBounces, Rng& sg, ManifoldSampleData& data) {
-    if (!traceMNEEOccluders(P, tc, visOrigin, visDir, 0.f, visTMax, sg, maxMSBounces, data)) return false;
-    if (data.hitCount == 0) return true;
+// Manifolds.slangh:165-281 after the occluder chain has been collected (traceMNEEOccluders): the Newton / line-search walk
+// and the final visibility test.  It consumes no random numbers, so it runs in its own kernel (k_mnee) where its data-dependent
+// iteration count cannot stall the coherent NEE work.
+PLT_D bool manifoldWalk(const FrameParams& P, TraversalCounters& tc, float3 origin, float3 lightPos, float3 lightDir, bool isDistantLight, ManifoldSampleData& data) {
     float beta[kMaxMSHits];
     for (int i = 0; i < kMaxMSHits; ++i) beta[i] = 1.f;
     bool success = false;
@@ -802,101 +811,252 @@ PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const Man
     }
 }
 
-// pltpt_solve.rt.slang:245-366 (NEE).  Returns false when the connection carries nothing; otherwise `ls.beam` is the
-// MIS-weighted beam arriving at the vertex and `evalCurrentVertex` tells whether the vertex's own BSDF is still to be applied.
-PLT_D bool neeConnect(const FrameParams& P, SolveState& st, int bounceIdx, const Bounce& bounce, const SD& sd, const VertexData& V, const DevMaterial& m, LightSample& ls, bool& evalCurrentVertex) {
-    const uint32_t lobes = m.lobes;
-    const bool allowMSOnCurrentVertex = P.doMS && bounceIdx > 0 && !(bounce.flags & RF_LastBounceWasDelta) && (m.propFlags & P_CanMSReflective);
-    const bool sampleReflection = (lobes & L_NonDeltaReflection) != 0 || allowMSOnCurrentVertex;
-    const bool sampleTransmission = (lobes & L_NonDeltaTransmission) != 0;
-    if (!sampleReflection && !sampleTransmission) return false;
-    const bool valid = generateLightSample(P, sd, sampleReflection, sampleTransmission, st.sg, st.tilesg, st.wavelength, P.opt.doImportanceSampleEmitters != 0, ls);
-    if (!valid || !anyPositive(ls.beam.L, int(P.opt.HWSS))) return false;
-    if (!P.opt.HWSSDoMIS && (bounce.flags & RF_HasDispersiveDeltaSegment)) ls.beam.comps = 1;
-    const bool doMis = P.doMIS && ls.lightType != LT_Analytic;
-    evalCurrentVertex = true;
-    const int maxMSBounces = int(P.opt.maxBounces) - bounceIdx;
-    if (!P.doMS || maxMSBounces <= 0) {
-        if (occluded(P, st.tc, ls.origin, ls.dir, .0f, ls.distance)) return false;
-        if (doMis) ls.beam.scale(misWeight(ls.pdf, bsdfPdf(m, sd, ls.dir, ls.beam.wl.x)));
-    } else {
-        const float3 lightDir = -ls.beam.r;
-        float MISBsdfPdf = 0.f;
-        ManifoldSampleData ms;
-        ms.hitCount = 0; ms.iterations = 0; ms.pdf = 1.f; ms.dispersive = false; ms.woLastHitToLight = mk3(0.f);
-        ms.wavelength = ls.beam.wl.x;
-        const bool isReflection = dot(sd.N, lightDir) * dot(sd.N, sd.V) > .0f;
-        const bool currentVertexMS = isReflection && allowMSOnCurrentVertex;
-        if (currentVertexMS) {
-            if (!manifoldSampleVertex(bounce.hit, sd, m, lightDir, st.sg, ms) || (ms.hits[0].lobe & L_Reflection) == 0) return false;
-        }
-        const float3 origin = !currentVertexMS ? V.posW : st.pathOrigin;
-        const bool ok = manifoldNEESample(P, st.tc, ls.origin, ls.dir, ls.distance, origin, ls.beam.posW, lightDir, ls.beam.distant, maxMSBounces, st.sg, ms);
-        if (P.counters && ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)ms.iterations);
-        if (!ok || ms.pdf < 1e-6f) return false;
-        if (ms.hitCount > 0) {
-            if (!P.opt.HWSSDoMIS && ms.dispersive) ls.beam.comps = 1;
-            if (!ls.beam.distant) {
-                ls.dir = ms.woLastHitToLight;
-                ls.beam.r = -ms.woLastHitToLight;
-                ls.beam.t = perp_stark(ls.beam.r);
-            }
-            ls.beam.scale(1.f / ms.pdf);
-            manifoldForwardUnwind(P, st, ms, origin, ls.beam);
-            if (currentVertexMS) { evalCurrentVertex = false; MISBsdfPdf = bounce.lastNonDeltaPdf; }
-        }
-        if (doMis) {
-            if (ms.hitCount == 0 || !currentVertexMS) MISBsdfPdf = bsdfPdf(m, sd, ls.dir, ls.beam.wl.x);
-            ls.beam.scale(misWeight(ls.pdf, MISBsdfPdf * ms.pdf));
-        }
-    }
-    return true;
-}
+// Deferred manifold walk: everything k_mnee needs to finish one NEE connection whose shadow ray crossed delta occluders.
+struct alignas(16) MneeItem {
+    uint4 hit[kMaxMSHits - 1];
+    float4 posLobe[kMaxMSHits - 1];  // posW.xyz | asfloat(lobe)
+    float4 originPdf;                // manifold origin.xyz | ms.pdf
+    float4 lightPosWl;               // light position.xyz | hero wavelength of the sampled beam
+    float4 lightDirLsPdf;            // direction towards the light.xyz | ls.pdf
+    uint32_t pixel, bounceIdx, jobId, flags;  // flags: hitCount[0:3] dispersive 4 distant 5 currentVertexMS 6 doMis 7
+};
+enum : uint32_t { MI_DISPERSIVE = 1u << 4, MI_DISTANT = 1u << 5, MI_CURRENT_VERTEX_MS = 1u << 6, MI_DO_MIS = 1u << 7 };
 
-// pltpt_solve.rt.slang:401-476 (raygen), connection half, for ONE recorded vertex of one path (vertex index P.level).  The
-// random-number state of the path's solve stage is carried from vertex to vertex in ssRng (the reference consumes it sequentially).
-PLT_D void connectVertex(const FrameParams& P, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
-    const int p = int(P.level);
-    uint32_t px, py;
-    pixelCoords(P, pixel, px, py);
+// Second half of an MNEE connection (Manifolds.slangh:165-281 walk, pltpt_solve.rt.slang:320-361): Newton walk, final visibility,
+// replay of the beam through the found specular chain, MIS; then the connection joins the unwind queues like any other.
+PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals, TraversalCounters& tc) {
+    ManifoldSampleData ms;
+    ms.hitCount = int(it.flags & 0xfu); ms.iterations = 0; ms.pdf = it.originPdf.w; ms.dispersive = (it.flags & MI_DISPERSIVE) != 0;
+    ms.wavelength = it.lightPosWl.w; ms.woLastHitToLight = mk3(0.f);
+    for (int i = 0; i < ms.hitCount; ++i) {
+        ms.hits[i].hit = it.hit[i];
+        ms.hits[i].posW = mk3(it.posLobe[i].x, it.posLobe[i].y, it.posLobe[i].z);
+        ms.hits[i].lobe = __float_as_uint(it.posLobe[i].w);
+    }
+    const float3 origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z), lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
+    const float3 lightDir = mk3(it.lightDirLsPdf.x, it.lightDirLsPdf.y, it.lightDirLsPdf.z);
+    const bool distant = (it.flags & MI_DISTANT) != 0, currentVertexMS = (it.flags & MI_CURRENT_VERTEX_MS) != 0;
+    const bool ok = manifoldWalk(P, tc, origin, lightPos, lightDir, distant, ms);
+    if (P.counters && ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)ms.iterations);
+    if (!ok) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
+    Beam beam;
+    JobHeader h;
+    loadJob(P, it.jobId, beam, h);
+    float3 lsDir = -beam.r;
+    if (!P.opt.HWSSDoMIS && ms.dispersive) beam.comps = 1;
+    if (!beam.distant) {
+        lsDir = ms.woLastHitToLight;
+        beam.r = -ms.woLastHitToLight;
+        beam.t = perp_stark(beam.r);
+    }
+    beam.scale(1.f / ms.pdf);
     SolveState st;
     st.evals = 0;
-    st.tc.nodes = st.tc.tris = 0;
+    manifoldForwardUnwind(P, st, ms, origin, beam);
+    evals += st.evals;
+    if (it.flags & MI_DO_MIS) {
+        float misBsdfPdf;
+        if (currentVertexMS) misBsdfPdf = P.bPdf[size_t(it.bounceIdx) * P.pixelCount + it.pixel].y;  // bounce.lastNonDeltaPdf
+        else {
+            uint32_t materialID;
+            const VertexData v = readVertexCache(P, it.pixel, int(it.bounceIdx), materialID);
+            const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+            const float4 d = P.bDir[size_t(it.bounceIdx) * P.pixelCount + it.pixel];
+            const SD sd = prepareShadingData(v, materialID, m, oct_to_ndir_equal_area_snorm(mk2(d.x, d.y)));
+            misBsdfPdf = bsdfPdf(m, sd, lsDir, beam.wl.x);
+        }
+        beam.scale(misWeight(it.lightDirLsPdf.w, misBsdfPdf * ms.pdf));
+    }
+    h.firstIsCurrent = !currentVertexMS;
+    h.q = h.firstIsCurrent ? it.bounceIdx : it.bounceIdx - 1u;
+    storeJob(P, it.jobId, beam, h);
+    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + it.pixel], it.jobId);
+}
+
+// ---- connect wavefront: A (light sampling) -> shadow-ray trace kernel -> B (visibility, MIS, emit) per vertex index ------------
+// Per work-list entry (one recorded vertex of one path) the two halves hand over through a ConnItem, a ray and a job slot that
+// already holds the sourced beam.
+struct ConnItem { float4 dirPdf; uint4 info; };  // ls.dir.xyz | ls.pdf ; jobId, flags, asuint(ms.pdf), lobe of the current-vertex delta sample
+enum : uint32_t { CI_TRACE = 1u, CI_ANY_HIT = 2u, CI_DO_MIS = 4u, CI_CURRENT_MS = 8u, CI_DISPERSIVE = 16u };
+
+struct ConnectCtx {  // what both halves rebuild for a vertex
+    SolveState st;
+    VertexData v;
+    Bounce bounce;
+    DevMaterial m;
+    SD sd;
     uint32_t materialID;
-    const VertexData v = readVertexCache(P, pixel, p, materialID);
-    if (p == 0) {
-        st.sg = Rng::seed(px, py, P.frameCount);
-        st.wavelength = sampleHeroWavelength(st.sg.next1D());
-        st.pathOrigin = P.camPos;
-        if (P.perTileSG) st.tilesg = Rng::seed(px / P.opt.tileSize, py / P.opt.tileSize, P.frameCount << 2);
+};
+PLT_D void connectSetup(const FrameParams& P, uint32_t pixel, int p, bool freshRng, ConnectCtx& c) {
+    uint32_t px, py;
+    pixelCoords(P, pixel, px, py);
+    c.st.evals = 0;
+    c.st.tc.nodes = c.st.tc.tris = 0;
+    c.v = readVertexCache(P, pixel, p, c.materialID);
+    if (p == 0) c.st.pathOrigin = P.camPos;
+    else { const float4 prev = P.vc0[size_t(p - 1) * P.pixelCount + pixel]; c.st.pathOrigin = mk3(prev.x, prev.y, prev.z); }
+    if (freshRng) {  // pltpt_solve.rt.slang:410-415
+        c.st.sg = Rng::seed(px, py, P.frameCount);
+        c.st.wavelength = sampleHeroWavelength(c.st.sg.next1D());
+        if (P.perTileSG) c.st.tilesg = Rng::seed(px / P.opt.tileSize, py / P.opt.tileSize, P.frameCount << 2);
     } else {
         const uint4 r = P.ssRng[pixel];
-        st.sg = Rng{r.x, r.y, r.z, r.w};
-        st.wavelength = P.psOrigin[pixel].w;  // hero wavelength: the first draw of both stages' generators (pltpt_solve.rt.slang:415)
-        const float4 prev = P.vc0[size_t(p - 1) * P.pixelCount + pixel];
-        st.pathOrigin = mk3(prev.x, prev.y, prev.z);
-        if (P.perTileSG) { const uint4 tr = P.ssTileRng[pixel]; st.tilesg = Rng{tr.x, tr.y, tr.z, tr.w}; }
+        c.st.sg = Rng{r.x, r.y, r.z, r.w};
+        c.st.wavelength = P.psOrigin[pixel].w;  // hero wavelength: the first draw of both stages' generators
+        if (P.perTileSG) { const uint4 tr = P.ssTileRng[pixel]; c.st.tilesg = Rng{tr.x, tr.y, tr.z, tr.w}; }
     }
-    if (!P.perTileSG) st.tilesg = st.sg;
-    const Bounce bounce = readBounce(P, pixel, p);
-    const TriHit th = unpackHit(P.sc, bounce.hit);
-    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-    const SD sd = prepareShadingData(v, materialID, m, bounce.wi);
-    bool connected = false;
+    if (!P.perTileSG) c.st.tilesg = c.st.sg;
+    c.bounce = readBounce(P, pixel, p);
+    c.m = loadMaterial(P.sc.materials, c.materialID);
+    c.sd = prepareShadingData(c.v, c.materialID, c.m, c.bounce.wi);
+}
+PLT_D void storeSolveRng(const FrameParams& P, uint32_t pixel, const SolveState& st) {
+    P.ssRng[pixel] = make_uint4(st.sg.s0, st.sg.s1, st.sg.s2, st.sg.s3);
+    if (P.perTileSG) P.ssTileRng[pixel] = make_uint4(st.tilesg.s0, st.tilesg.s1, st.tilesg.s2, st.tilesg.s3);
+}
+// tail of the per-vertex loop body of pltpt_solve.rt.slang:420-464: emissive hit, then hand the generator to the next vertex
+PLT_D void connectTail(const FrameParams& P, uint32_t pixel, int p, ConnectCtx& c) {
+    evalEmissive(P, c.st, pixel, p, c.bounce, c.m, c.sd, unpackHit(P.sc, c.bounce.hit));
+    if (!(c.bounce.flags & RF_Terminated) && p < int(P.opt.maxBounces)) storeSolveRng(P, pixel, c.st);
+}
+
+// Half A (pltpt_solve.rt.slang:245-300): light sample, beam sourcing, delta sample of the current vertex; posts the shadow ray.
+PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
+    const int p = int(P.level);
+    ConnectCtx c;
+    connectSetup(P, pixel, p, p == 0, c);
+    ConnItem item;
+    item.dirPdf = mk4(0.f); item.info = make_uint4(0, 0, 0, 0);
+    bool pending = false;
     if (P.doNEE) {
-        LightSample ls;
-        bool evalCurrentVertex = true;
-        connected = neeConnect(P, st, p, bounce, sd, v, m, ls, evalCurrentVertex);
-        if (connected) emitConnection(P, pixel, p, 0, evalCurrentVertex, bounce.pathContribution, ls.beam);
+        const uint32_t lobes = c.m.lobes;
+        const bool allowMSOnCurrentVertex = P.doMS && p > 0 && !(c.bounce.flags & RF_LastBounceWasDelta) && (c.m.propFlags & P_CanMSReflective);
+        const bool sampleReflection = (lobes & L_NonDeltaReflection) != 0 || allowMSOnCurrentVertex;
+        const bool sampleTransmission = (lobes & L_NonDeltaTransmission) != 0;
+        if (sampleReflection || sampleTransmission) {
+            LightSample ls;
+            const bool valid = generateLightSample(P, c.sd, sampleReflection, sampleTransmission, c.st.sg, c.st.tilesg, c.st.wavelength, P.opt.doImportanceSampleEmitters != 0, ls);
+            if (valid && anyPositive(ls.beam.L, int(P.opt.HWSS))) {
+                if (!P.opt.HWSSDoMIS && (c.bounce.flags & RF_HasDispersiveDeltaSegment)) ls.beam.comps = 1;
+                uint32_t flags = CI_TRACE | ((P.doMIS && ls.lightType != LT_Analytic) ? CI_DO_MIS : 0u);
+                float msPdf = 1.f;
+                uint32_t lobe0 = 0;
+                bool alive = true;
+                if (!P.doMS || int(P.opt.maxBounces) - p <= 0) flags |= CI_ANY_HIT;
+                else {
+                    const float3 lightDir = -ls.beam.r;
+                    const bool isReflection = dot(c.sd.N, lightDir) * dot(c.sd.N, c.sd.V) > .0f;
+                    if (isReflection && allowMSOnCurrentVertex) {
+                        ManifoldSampleData ms;
+                        ms.hitCount = 0; ms.iterations = 0; ms.pdf = 1.f; ms.dispersive = false; ms.wavelength = ls.beam.wl.x;
+                        alive = manifoldSampleVertex(c.bounce.hit, c.sd, c.m, lightDir, c.st.sg, ms) && (ms.hits[0].lobe & L_Reflection) != 0;
+                        flags |= CI_CURRENT_MS | (ms.dispersive ? CI_DISPERSIVE : 0u);
+                        msPdf = ms.pdf; lobe0 = ms.hits[0].lobe;
+                    }
+                }
+                if (alive) {
+                    const uint32_t id = allocJob(P);
+                    if (id < P.jobCapacity) {
+                        JobHeader h;
+                        h.pixel = pixel; h.bounceIdx = uint32_t(p); h.kind = 0; h.firstIsCurrent = true; h.pathContribution = c.bounce.pathContribution; h.q = uint32_t(p);
+                        storeJob(P, id, ls.beam, h);
+                        item.dirPdf = mk4(ls.dir.x, ls.dir.y, ls.dir.z, ls.pdf);
+                        item.info = make_uint4(id, flags, __float_as_uint(msPdf), lobe0);
+                        P.shadowRays[2 * size_t(slot)] = mk4(ls.origin.x, ls.origin.y, ls.origin.z, 0.f);
+                        P.shadowRays[2 * size_t(slot) + 1] = mk4(ls.dir.x, ls.dir.y, ls.dir.z, ls.distance);
+                        pending = true;
+                    } else atomicAdd(P.jobCount + 1, 1u);
+                }
+            }
+        }
     }
-    if (!connected) writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
-    evalEmissive(P, st, pixel, p, bounce, m, sd, th);
-    if (!(bounce.flags & RF_Terminated) && p < int(P.opt.maxBounces)) {
-        P.ssRng[pixel] = make_uint4(st.sg.s0, st.sg.s1, st.sg.s2, st.sg.s3);
-        if (P.perTileSG) P.ssTileRng[pixel] = make_uint4(st.tilesg.s0, st.tilesg.s1, st.tilesg.s2, st.tilesg.s3);
+    P.connItems[slot] = item;
+    if (pending) storeSolveRng(P, pixel, c.st);  // half B continues the stream (occluder samples, emissive hit)
+    else {
+        writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+        connectTail(P, pixel, p, c);
     }
-    evals = st.evals;
-    tc = st.tc;
+    evals += c.st.evals;
+    tc.nodes += c.st.tc.nodes; tc.tris += c.st.tc.tris;
+}
+
+// Half B (pltpt_solve.rt.slang:283-361): visibility / occluder chain, MIS weight, hand-over to the unwind queues (or to k_mnee).
+PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
+    const ConnItem item = P.connItems[slot];
+    const uint32_t flags = item.info.y;
+    if (!(flags & CI_TRACE)) return;
+    const int p = int(P.level);
+    ConnectCtx c;
+    connectSetup(P, pixel, p, false, c);
+    const uint32_t jobId = item.info.x;
+    const float3 lsDir = mk3(item.dirPdf.x, item.dirPdf.y, item.dirPdf.z);
+    const float lsPdf = item.dirPdf.w;
+    const uint4 hit = P.shadowHits[slot];
+    const bool blocked = hit.x != 0xffffffffu;
+    bool connected = false;
+    float misScale = 1.f;
+    if (flags & CI_ANY_HIT) {
+        if (!blocked) {
+            connected = true;
+            if (flags & CI_DO_MIS) misScale = misWeight(lsPdf, bsdfPdf(c.m, c.sd, lsDir, P.job[size_t(4) * P.jobCapacity + jobId].x));
+        }
+    } else {
+        ManifoldSampleData ms;
+        ms.hitCount = 0; ms.iterations = 0; ms.pdf = __uint_as_float(item.info.z); ms.dispersive = (flags & CI_DISPERSIVE) != 0; ms.woLastHitToLight = mk3(0.f);
+        const float heroWl = P.job[size_t(4) * P.jobCapacity + jobId].x;  // beam.wl.x
+        ms.wavelength = heroWl;
+        const bool currentVertexMS = (flags & CI_CURRENT_MS) != 0;
+        if (currentVertexMS) { ms.hits[0].hit = c.bounce.hit; ms.hits[0].posW = c.sd.posW; ms.hits[0].lobe = item.info.w; ms.hitCount = 1; }
+        const float3 origin = !currentVertexMS ? c.v.posW : c.st.pathOrigin;
+        const float4 r0 = P.shadowRays[2 * size_t(slot)], r1 = P.shadowRays[2 * size_t(slot) + 1];
+        bool ok = true;
+        if (blocked) {
+            TriHit th;
+            th.instanceID = hit.x; th.primitiveIndex = hit.y; th.u = __uint_as_float(hit.z); th.v = __uint_as_float(hit.w);
+            ok = traceMNEEOccluders(P, c.st.tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.f, r1.w, c.st.sg, int(P.opt.maxBounces) - p, ms, &th, P.shadowT[slot]);
+        }
+        if (ok && ms.hitCount > 0) {
+            // a manifold walk is needed: park the connection for k_mnee (it owns the contribution slot from here on)
+            connected = true;
+            if (ms.pdf < 1e-6f) connected = false;
+            else {
+                const uint32_t mslot = atomicAdd(P.mneeCount, 1u);
+                if (mslot >= P.mneeCapacity) { atomicAdd(P.jobCount + 1, 1u); connected = false; }
+                else {
+                    MneeItem& it = P.mneeItems[mslot];
+                    for (int i = 0; i < kMaxMSHits - 1; ++i) {
+                        it.hit[i] = i < ms.hitCount ? ms.hits[i].hit : make_uint4(0, 0, 0, 0);
+                        it.posLobe[i] = i < ms.hitCount ? mk4(ms.hits[i].posW.x, ms.hits[i].posW.y, ms.hits[i].posW.z, __uint_as_float(ms.hits[i].lobe)) : mk4(0.f);
+                    }
+                    const float4 bp = P.job[size_t(7) * P.jobCapacity + jobId];  // beam.posW
+                    it.originPdf = mk4(origin.x, origin.y, origin.z, ms.pdf);
+                    it.lightPosWl = mk4(bp.x, bp.y, bp.z, heroWl);
+                    it.lightDirLsPdf = mk4(lsDir.x, lsDir.y, lsDir.z, lsPdf);
+                    it.pixel = pixel; it.bounceIdx = uint32_t(p); it.jobId = jobId;
+                    const bool distant = (__float_as_uint(P.job[size_t(9) * P.jobCapacity + jobId].w) & JOB_DISTANT) != 0;
+                    it.flags = uint32_t(ms.hitCount) | (ms.dispersive ? MI_DISPERSIVE : 0u) | (distant ? MI_DISTANT : 0u) | (currentVertexMS ? MI_CURRENT_VERTEX_MS : 0u) | ((flags & CI_DO_MIS) ? MI_DO_MIS : 0u);
+                }
+            }
+            if (!connected) writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+            connectTail(P, pixel, p, c);
+            evals += c.st.evals;
+            tc.nodes += c.st.tc.nodes; tc.tris += c.st.tc.tris;
+            return;
+        }
+        if (ok) {
+            connected = true;
+            if (flags & CI_DO_MIS) misScale = misWeight(lsPdf, bsdfPdf(c.m, c.sd, lsDir, heroWl) * ms.pdf);
+        }
+    }
+    if (connected) {
+        if (flags & CI_DO_MIS) {  // beam.scale(w) on the parked beam
+            for (int k = 0; k < 4; ++k) { float4* q = P.job + size_t(k) * P.jobCapacity + jobId; *q = *q * misScale; }
+        }
+        enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId);
+    } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+    connectTail(P, pixel, p, c);
+    evals += c.st.evals;
+    tc.nodes += c.st.tc.nodes; tc.tris += c.st.tc.tris;
 }
 
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head).
@@ -964,7 +1124,8 @@ struct SortView { uint32_t* dst; uint32_t* dstCount; };
 void launchRaygen(const FrameParams& P, cudaStream_t s);
 void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s);
-void launchConnect(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnectLevel(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchResolve(const FrameParams& P, cudaStream_t s);

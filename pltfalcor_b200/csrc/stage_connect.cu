@@ -1,32 +1,84 @@
 // stage_connect.cu — first half of the solve stage (reference pltpt_solve.rt.slang:401-476, NEE :245-366, evalEmissive :152-200,
-// MNEE Manifolds.slangh).  One launch per recorded-vertex index p: every path that has a hit at vertex p samples the light,
-// traces the shadow ray / manifold walk, applies MIS and emits one connection job per surviving light connection.  The work list
-// is the sample stage's type-sorted hit list of bounce p, so a warp evaluates one material's pdf / delta sampling.
+// MNEE Manifolds.slangh) as a wavefront.  Per recorded-vertex index p (the work list is the sample stage's type-sorted hit list
+// of bounce p, so a warp evaluates one material):
+//   k_connect_a    : light sample + beam sourcing (+ delta sample of the current vertex for MNEE); posts one shadow ray
+//   k_shadow_trace : closest-hit (MNEE on: the first occluder matters) or any-hit traversal of the posted rays
+//   k_connect_b    : visibility / delta-occluder chain, MIS weight, emissive hit; hands the connection to the unwind queues
+// and once per tile
+//   k_mnee         : manifold walk (Newton + line search, data-dependent trip count) of the connections that crossed delta
+//                    occluders — isolated so that it cannot stall the coherent NEE work (north-star (d)).
 #include "plt_integrator.cuh"
 
 namespace plt {
 namespace {
-__global__ void __launch_bounds__(kStageThreads) k_connect(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     uint32_t evals = 0, verts = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
-        if (i < n) {
-            uint32_t e = 0;
-            TraversalCounters t = {0, 0};
-            connectVertex(P, list[i], e, t);
-            evals += e; tc.nodes += t.nodes; tc.tris += t.tris; ++verts;
-        }
+        if (i < n) { connectA(P, i, list[i], evals, tc); ++verts; }
     }
     // warp-aggregated statistics (all lanes reach this point)
-    warpAdd(P.counters + 0, evals);
     warpAdd(P.counters + 1, verts);
     warpAdd(P.counters + 4, verts * P.level);  // sum over paths of L(L-1)/2 == sum over recorded vertices of their index
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_shadow_trace(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.levelCount[P.level];
+    TraversalCounters tc = {0, 0};
+    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
+        const uint32_t i = base + threadIdx.x;
+        if (i >= n) continue;
+        const uint32_t flags = P.connItems[i].info.y;
+        if (!(flags & CI_TRACE)) continue;
+        const float4 r0 = P.shadowRays[2 * size_t(i)], r1 = P.shadowRays[2 * size_t(i) + 1];
+        const float3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+        if (flags & CI_ANY_HIT) P.shadowHits[i] = make_uint4(occluded(P, tc, o, d, r0.w, r1.w) ? 0u : 0xffffffffu, 0u, 0u, 0u);
+        else {
+            TriHit th;
+            float t;
+            const bool hit = traceClosestHit(P, tc, o, d, r0.w, r1.w, th, t);
+            P.shadowHits[i] = hit ? make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+            P.shadowT[i] = t;
+        }
+    }
+    warpAdd(P.counters + 5, tc.nodes);
+    warpAdd(P.counters + 6, tc.tris);
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.levelCount[P.level];
+    const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
+    uint32_t evals = 0;
+    TraversalCounters tc = {0, 0};
+    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < n) connectB(P, i, list[i], evals, tc);
+    }
+    warpAdd(P.counters + 5, tc.nodes);
+    warpAdd(P.counters + 6, tc.tris);
+}
+
+// Manifold-walk kernel: one thread per parked connection.  Runs once per tile after all connect launches.
+__global__ void __launch_bounds__(kStageThreads) k_mnee(const __grid_constant__ FrameParams P) {
+    const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
+    uint32_t evals = 0;
+    TraversalCounters tc = {0, 0};
+    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < n) mneeFinish(P, P.mneeItems[i], evals, tc);
+    }
+    warpAdd(P.counters + 0, evals);
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
 }
 }  // namespace
-void launchConnect(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect<<<grid, kStageThreads, 0, s>>>(P); }
+void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_mnee<<<grid, kStageThreads, 0, s>>>(P); }
+void launchConnectLevel(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    k_connect_a<<<grid, kStageThreads, 0, s>>>(P);
+    k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P);
+    k_connect_b<<<grid, kStageThreads, 0, s>>>(P);
+}
 }  // namespace plt
