@@ -67,7 +67,7 @@ typedef struct PltptOptions {
     uint32_t alphaMasking;                      /* 1 */
     uint32_t doNEE;                             /* 1 */
     uint32_t doMIS;                             /* 1 */
-    uint32_t emissiveSampler;                   /* 1 = Power, 0 = Uniform (EmissiveLightSamplerType) */
+    uint32_t emissiveSampler;                   /* EmissiveLightSamplerType (EmissiveLightSamplerType.slangh:37-44): 2 = Power (default), 0 = Uniform; others rejected */
     uint32_t doRussianRoulette;                 /* 1 */
     uint32_t NEEUsePerTileSG;                   /* 0 */
     uint32_t doImportanceSampleEmitters;        /* 1 */
@@ -76,6 +76,11 @@ typedef struct PltptOptions {
     uint32_t MNEEMaxIterations;                 /* 60 */
     float    MNEESolverThreshold;               /* 5e-5 */
 } PltptOptions;
+
+/* EmissiveLightSamplerType values the pass offers (PLTPT.cpp:80-83; LightBVH = 1 is not offered and is rejected
+ * with "Unknown emissive light sampler type" like PLTPT.cpp:409). */
+#define PLTPT_EMISSIVE_SAMPLER_UNIFORM 0u
+#define PLTPT_EMISSIVE_SAMPLER_POWER 2u
 
 /* Fills *opts with the reference defaults (PLTPT.h:74-108). */
 PLTPT_API void pltpt_default_options(PltptOptions* opts);

@@ -259,7 +259,7 @@ struct Integrator {
     // EmissivePowerSampler.slang:64-90 / EmissiveUniformSampler.slang:56-72
     bool emissiveSampleLight(float3 posW, SampleGenerator& sg, float wavelength, bool importanceSample, TriangleLightSample& ls) const {
         const PltptSceneDesc& d = scene->d;
-        if (opt.emissiveSampler == 1) {
+        if (opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER) {
             if (d.emissiveTriangleCount == 0) return false;
             float uLight = sampleNext1D(sg);
             uint32_t triangleCount = d.emissiveTriangleCount;
@@ -290,7 +290,7 @@ struct Integrator {
         const PltptSceneDesc& d = scene->d;
         if (triangleIndex == 0xffffffffu) return 0.f;
         float sel;
-        if (opt.emissiveSampler == 1) sel = d.emissiveFlux[triangleIndex].flux * d.invWeightsSum;
+        if (opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER) sel = d.emissiveFlux[triangleIndex].flux * d.invWeightsSum;
         else sel = d.activeTriangleCount > 0 ? 1.f / (float)d.activeTriangleCount : 0.f;
         float3 toLight = hitPosW - posW;
         const float distSqr = dot(toLight, toLight);

@@ -64,5 +64,35 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(_HERE, "host")
+PLUGIN = os.path.join(_HERE, "libPLTPT.so")       # the drop-in render-pass plugin (host/PLTPT.cpp), exports registerPlugin
+HOST_EXE = os.path.join(_HERE, "pltpt_host")      # Mogwai stand-in that loads the plugin (host/pltpt_host.cpp)
+
+
+def _cuda_home():
+    nv = _nvcc()
+    return os.path.dirname(os.path.dirname(nv)) if os.path.isabs(nv) else "/usr/local/cuda"
+
+
+def build_host(force=False):
+    """Compiles the C++ host shell: libPLTPT.so (plugin, links libpltpt.so) and pltpt_host.  g++ only; no GPU code here."""
+    srcs = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [os.path.join(_HERE, "..", "include", "pltpt.h"), LIB]
+    stale = lambda out: force or not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in srcs)
+    cuda = _cuda_home()
+    common = ["-std=c++17", "-O2", "-Wall", "-I" + os.path.join(_HERE, "..", "include"), "-I" + os.path.join(cuda, "include")]
+    libs = ["-L" + os.path.join(cuda, "lib64"), "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    cmds = []
+    if stale(PLUGIN):
+        cmds.append(["g++", *common, "-fPIC", "-shared", os.path.join(HOST, "PLTPT.cpp"), "-o", PLUGIN, "-L" + _HERE, "-lpltpt", *libs, "-Wl,-rpath,$ORIGIN"])
+    if stale(HOST_EXE):
+        cmds.append(["g++", *common, "-rdynamic", os.path.join(HOST, "pltpt_host.cpp"), "-o", HOST_EXE, *libs])
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return PLUGIN, HOST_EXE
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

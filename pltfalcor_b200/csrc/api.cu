@@ -22,13 +22,13 @@ static int fail(int code, const std::string& msg) { setError(msg); return code; 
 // ------------------------------------------------------------------------------------------------ options
 extern "C" void pltpt_default_options(PltptOptions* o) {  // PLTPT.h:74-108
     if (!o) return;
-    *o = PltptOptions{32, 512, 4, 1, 1, 0, 1.f, 1.f, .025f, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 2, 60, 5e-5f};
+    *o = PltptOptions{32, 512, 4, 1, 1, 0, 1.f, 1.f, .025f, 1, 1, 1, 1, 1, 1, 1, PLTPT_EMISSIVE_SAMPLER_POWER, 1, 0, 1, 1, 2, 60, 5e-5f};
 }
 static int validateOptions(const PltptOptions& o) {
     if (o.HWSS < 1 || o.HWSS > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "HWSS must be in 1..4");
     if (o.tileSize == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "tileSize must be > 0");
     if (o.maxBounces > 255) return fail(PLTPT_ERR_INVALID_ARGUMENT, "maxBounces must be <= 255");
-    if (o.emissiveSampler > 1) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Unknown emissive light sampler type");  // PLTPT.cpp:409
+    if (o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_UNIFORM && o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_POWER) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Unknown emissive light sampler type");  // PLTPT.cpp:409
     if (o.sampleGenerator != 1) return fail(PLTPT_ERR_UNSUPPORTED, "only SAMPLE_GENERATOR_UNIFORM (1) is supported");
     if (o.MNEEMaxOccluders > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "MNEEMaxOccluders must be <= 4");
     return PLTPT_OK;
@@ -346,7 +346,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     h->emissiveTriangleCount = s->emissiveTriangleCount;
     h->lightCount = s->lightCount;
     if (d.etriCount > 0 && (!d.etris || !d.eflux || !d.perMeshInstanceOffset)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "emissive triangles present but light-collection buffers missing");
-    if (d.etriCount > 0 && h->opt.emissiveSampler == 1 && !d.alias) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table");
+    if (d.etriCount > 0 && h->opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER && !d.alias) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table");
     if (d.triCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no triangles");
 
     if (int r = buildBvh(h, 0)) return r;

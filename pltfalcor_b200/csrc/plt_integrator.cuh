@@ -362,7 +362,7 @@ PLT_D bool emissiveSampleLight(const FrameParams& P, float3 posW, Rng& sg, float
     const DevScene& sc = P.sc;
     uint32_t triangleIndex;
     float selectionPdf;
-    if (P.opt.emissiveSampler == 1) {
+    if (P.opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER) {
         if (sc.etriCount == 0) return false;
         const float uLight = sg.next1D();
         triangleIndex = min(uint32_t(uLight * sc.etriCount), sc.etriCount - 1);
@@ -387,7 +387,7 @@ PLT_D bool emissiveSampleLight(const FrameParams& P, float3 posW, Rng& sg, float
 PLT_D float emissiveEvalPdf(const FrameParams& P, float3 posW, uint32_t triangleIndex, float3 hitPosW, float3 hitNormalW) {
     const DevScene& sc = P.sc;
     if (triangleIndex == 0xffffffffu) return 0.f;
-    const float sel = P.opt.emissiveSampler == 1 ? __ldg(&sc.eflux[triangleIndex].flux) * sc.invWeightsSum : (sc.activeTriCount > 0 ? 1.f / float(sc.activeTriCount) : 0.f);
+    const float sel = P.opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER ? __ldg(&sc.eflux[triangleIndex].flux) * sc.invWeightsSum : (sc.activeTriCount > 0 ? 1.f / float(sc.activeTriCount) : 0.f);
     const float3 toLight = hitPosW - posW;
     const float distSqr = dot(toLight, toLight);
     if (distSqr <= kFltMin) return 0.f;

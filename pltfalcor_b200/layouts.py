@@ -86,7 +86,7 @@ class PltptOptions(C.Structure):
 OPTION_DEFAULTS = dict(
     maxBounces=32, tileSize=512, HWSS=4, HWSSDoMIS=True, sampleGenerator=1, debugView=0, debugViewIntensity=1.0,
     sourcingAreaFromEmissiveGeometry=1.0, sourcingMaxBeamOmega=0.025, useDirectLights=True, useEnvLights=True,
-    useEmissiveLights=True, useAnalyticLights=True, alphaMasking=True, doNEE=True, doMIS=True, emissiveSampler=1,
+    useEmissiveLights=True, useAnalyticLights=True, alphaMasking=True, doNEE=True, doMIS=True, emissiveSampler=2,
     doRussianRoulette=True, NEEUsePerTileSG=False, doImportanceSampleEmitters=True, doMNEE=True, MNEEMaxOccluders=2,
     MNEEMaxIterations=60, MNEESolverThreshold=5e-5,
 )

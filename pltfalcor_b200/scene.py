@@ -369,6 +369,25 @@ class SceneBuffers:
     def triangle_count(self):
         return self.scalars["triangleCount"]
 
+    BLOB_ORDER = ("vertices", "indexData", "geometryInstances", "meshes", "worldMatrices", "inverseTransposeWorldMatrices", "materialData", "spectralProfiles",
+                  "lights", "emissiveTriangles", "emissiveFlux", "activeTriangles", "perMeshInstanceOffset", "triangleAliasTable")
+
+    def save(self, path, cam):
+        """Writes the buffers, byte for byte, plus the camera block to the scene file host/pltpt_host.cpp reads."""
+        s = self.scalars
+        head = np.array([s["vertexCount"], s["indexDataBytes"], s["instanceCount"], s["meshCount"], s["matrixCount"], s["materialCount"], s["profileCount"],
+                         s["lightCount"], s["emissiveTriangleCount"], s["emissiveTriangleCount"], 3, s["instanceIDBits"], s["primitiveIndexBits"], 0], np.uint64)
+        with open(path, "wb") as f:
+            f.write(b"PLTSCN1\0")
+            f.write(head.tobytes())
+            f.write(np.array([s["invWeightsSum"], 0.0], np.float32).tobytes())
+            f.write(bytes(cam))
+            for name in self.BLOB_ORDER:
+                a = self.arrays.get(name)
+                raw = b"" if a is None or a.size == 0 else np.ascontiguousarray(a).tobytes()
+                f.write(np.uint64(len(raw)).tobytes())
+                f.write(raw)
+
 
 def _alloc_bits(count):
     return 0 if count <= 1 else int(count - 1).bit_length()  # HitInfo.cpp allocateBits
