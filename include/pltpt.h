@@ -364,6 +364,10 @@ PLTPT_API int pltpt_bsdf_sample(PltptHandle h, uint32_t materialID, uint32_t lob
 /* ------------------------------------------------------------------------------------------
  * Counters (kernel launches, rays traced, BVH nodes visited ...) for bench.py / DESIGN.md.
  * ---------------------------------------------------------------------------------------- */
+enum PltptKernelClass {
+    PLTPT_K_RAYGEN = 0, PLTPT_K_TRACE, PLTPT_K_SORT, PLTPT_K_SHADE, PLTPT_K_CONNECT_A, PLTPT_K_SHADOW_TRACE, PLTPT_K_CONNECT_B,
+    PLTPT_K_MNEE, PLTPT_K_UNWIND_STEP, PLTPT_K_RESOLVE, PLTPT_K_OTHER, PLTPT_KERNEL_CLASS_COUNT
+};
 typedef struct PltptStats {
     uint64_t kernelLaunches;     /* launches of our kernels since the last reset */
     uint64_t raysClosest, raysAny;
@@ -381,9 +385,16 @@ typedef struct PltptStats {
     uint64_t totalBsdfEvals;                   /* eval calls x wavelengths */
     uint64_t traversalNodesVisited, traversalTrianglesTested; /* BVH work of both stages */
     uint64_t droppedConnections;               /* connection jobs that did not fit the job buffer (must stay 0) */
+    /* per-kernel device time, filled only while pltpt_set_profiling(h, 1) is in effect: one CUDA event after every launch on the
+     * launching stream; the time between consecutive events is booked to the kernel that ran between them. */
+    double   kernelMs[PLTPT_KERNEL_CLASS_COUNT];
+    uint64_t kernelLaunchCount[PLTPT_KERNEL_CLASS_COUNT];
+    uint64_t unwindJobSteps;                   /* work items of k_unwind_step: one generalized ray pushed through one recorded vertex */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);
+/* Per-kernel timers on/off (default off).  Costs one cudaEventRecord per launch; no effect on results. */
+PLTPT_API int pltpt_set_profiling(PltptHandle h, int enable);
 
 #ifdef __cplusplus
 }

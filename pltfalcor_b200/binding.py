@@ -14,7 +14,7 @@ _lib = None
 EXPORTS = [
     "pltpt_default_options", "pltpt_create", "pltpt_destroy", "pltpt_last_error", "pltpt_version", "pltpt_set_options", "pltpt_set_scene",
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
-    "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats",
+    "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
 ]
 
 
@@ -49,6 +49,7 @@ def lib():
         _lib.pltpt_bsdf_sample.argtypes = [vp, u32, u32, u32, vp, vp, u32, vp, vp]
         _lib.pltpt_get_stats.argtypes = [vp, vp]
         _lib.pltpt_reset_stats.argtypes = [vp]
+        _lib.pltpt_set_profiling.argtypes = [vp, C.c_int]
     return _lib
 
 
@@ -102,7 +103,14 @@ class Pltpt:
     def stats(self):
         s = L.PltptStats()
         _check(lib().pltpt_get_stats(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in L.PltptStats._fields_}
+        out = {k: getattr(s, k) for k, _ in L.PltptStats._fields_}
+        out["kernelMs"] = dict(zip(L.KERNEL_CLASSES, list(s.kernelMs)))
+        out["kernelLaunchCount"] = dict(zip(L.KERNEL_CLASSES, list(s.kernelLaunchCount)))
+        return out
+
+    def set_profiling(self, enable):
+        """Per-kernel device timers (one CUDA event per launch) on/off."""
+        _check(lib().pltpt_set_profiling(self.h, 1 if enable else 0))
 
     def reset_stats(self):
         _check(lib().pltpt_reset_stats(self.h))

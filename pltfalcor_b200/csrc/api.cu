@@ -61,6 +61,7 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto e : h->timerEvents) cudaEventDestroy(e);
+    for (auto e : h->kernelEvents) cudaEventDestroy(e);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
     delete h;
@@ -76,6 +77,12 @@ extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
     if (!h || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (int r = syncFrameStats(h)) return r;
     *out = h->stats;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int r = syncFrameStats(h)) return r;
+    h->profiling = enable != 0;
     return PLTPT_OK;
 }
 extern "C" int pltpt_reset_stats(PltptHandle h) {

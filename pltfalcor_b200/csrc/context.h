@@ -92,6 +92,17 @@ struct PltptContext {
     uint32_t timerCount = 0;
     cudaStream_t timerStream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
+    // per-kernel timers (pltpt_set_profiling): event after every launch, tagged with the kernel class that precedes it (0xff = frame start)
+    bool profiling = false;
+    std::vector<cudaEvent_t> kernelEvents;
+    std::vector<uint8_t> kernelEventClass;
+    uint32_t kernelEventCount = 0;
+    void markKernel(uint8_t cls, cudaStream_t s) {
+        if (!profiling) return;
+        if (kernelEventCount == kernelEvents.size()) { cudaEvent_t e; cudaEventCreate(&e); kernelEvents.push_back(e); kernelEventClass.push_back(0); }
+        kernelEventClass[kernelEventCount] = cls;
+        cudaEventRecord(kernelEvents[kernelEventCount++], s);
+    }
 };
 
 namespace plt {

@@ -106,31 +106,44 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
         if (timed) cudaEventRecord(ev[0], s);
         // ---- sample stage
         PLT_CUDA(cudaMemsetAsync(P.queueCount, 0, 256 * 4, s));
+        c->markKernel(0xff, s);
         launchRaygen(P, s);
+        c->markKernel(PLTPT_K_RAYGEN, s);
         c->stats.kernelLaunches++;
         for (uint32_t b = 0; b <= maxB; ++b) {
             P.level = b;
             launchTrace(P, persistentGrid, s);
+            c->markKernel(PLTPT_K_TRACE, s);
             launchSortFlip(P, SortView{P.vertexList + size_t(b) * P.pixelCount, P.levelCount + b}, true, persistentGrid, s);
+            c->markKernel(PLTPT_K_SORT, s);
             launchShade(P, persistentGrid, s);
+            c->markKernel(PLTPT_K_SHADE, s);
             c->stats.kernelLaunches += 4;
         }
         if (timed) cudaEventRecord(ev[1], s);
-        if (bouncesOut) { launchGatherBounces(P, bouncesOut, maxB + 1, s); c->stats.kernelLaunches++; }
+        if (bouncesOut) { launchGatherBounces(P, bouncesOut, maxB + 1, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_OTHER, s); }
         if (solve) {
             // ---- solve stage: connect per vertex index, then the replay wavefront, then the deterministic per-pixel sum
             for (uint32_t b = 0; b <= maxB; ++b) {
                 P.level = b;
-                launchConnectLevel(P, persistentGrid, s);
+                launchConnectA(P, persistentGrid, s);
+                c->markKernel(PLTPT_K_CONNECT_A, s);
+                launchShadowTrace(P, persistentGrid, s);
+                c->markKernel(PLTPT_K_SHADOW_TRACE, s);
+                launchConnectB(P, persistentGrid, s);
+                c->markKernel(PLTPT_K_CONNECT_B, s);
                 c->stats.kernelLaunches += 3;
             }
-            if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches++; }
+            if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_MNEE, s); }
             for (uint32_t it = 0; it <= maxB; ++it) {
                 launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2}, false, persistentGrid, s);
+                c->markKernel(PLTPT_K_SORT, s);
                 launchUnwindStep(P, persistentGrid, s);
+                c->markKernel(PLTPT_K_UNWIND_STEP, s);
                 c->stats.kernelLaunches += 3;
             }
             launchResolve(P, s);
+            c->markKernel(PLTPT_K_RESOLVE, s);
             c->stats.kernelLaunches++;
         }
         if (timed) cudaEventRecord(ev[2], s);
@@ -157,7 +170,7 @@ int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam
         c->timerEvents.resize(3 * PltptContext::kTimerRing);
         for (auto& e : c->timerEvents) PLT_CUDA(cudaEventCreate(&e));
     }
-    if (c->timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
+    if (c->timerCount == PltptContext::kTimerRing || c->kernelEventCount > 60000) { if (int r = syncFrameStats(c)) return r; }
     if (int r = renderTiles(c, P, tileRows, solve, nullptr, s)) return r;
     c->timerCount++;
     c->timerStream = s;
@@ -180,6 +193,7 @@ int syncFrameStats(PltptContext* c) {
         c->stats.totalReplaySteps += host[4];
         c->stats.traversalNodesVisited += host[5];
         c->stats.traversalTrianglesTested += host[6];
+        c->stats.unwindJobSteps += host[7];
         PLT_CUDA(cudaMemset(c->work[3].p, 0, 16 * sizeof(unsigned long long)));
         uint32_t dropped = 0;
         PLT_CUDA(cudaMemcpy(&dropped, c->work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
@@ -192,6 +206,15 @@ int syncFrameStats(PltptContext* c) {
             c->stats.solveStageMs += b;
         }
         c->stats.framesRendered += c->timerCount;
+        for (uint32_t i = 1; i < c->kernelEventCount; ++i) {
+            const uint8_t cls = c->kernelEventClass[i];
+            if (cls >= PLTPT_KERNEL_CLASS_COUNT) continue;  // 0xff: first event of a tile, nothing precedes it
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->kernelEvents[i - 1], c->kernelEvents[i]);
+            c->stats.kernelMs[cls] += ms;
+            c->stats.kernelLaunchCount[cls]++;
+        }
+        c->kernelEventCount = 0;
         c->timerCount = 0;
         c->statsDirty = false;
     }

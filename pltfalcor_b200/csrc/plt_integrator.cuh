@@ -67,7 +67,7 @@ struct FrameParams {
     float4* normal;
     double* accum;     // RGBA64F running sums (may be null)
     unsigned long long* counters;  // [0] bsdf evals x wavelengths, [1] recorded vertices, [2] traversal stack overflows, [3] mnee iterations,
-                                   // [4] sum L(L-1)/2, [5] BVH nodes visited, [6] triangles tested
+                                   // [4] sum L(L-1)/2, [5] BVH nodes visited, [6] triangles tested, [7] unwind job steps
     // derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
     bool useEmissive, useAnalytic, doNEE, doMS, doMIS, perTileSG;
 };
@@ -1124,7 +1124,9 @@ struct SortView { uint32_t* dst; uint32_t* dstCount; };
 void launchRaygen(const FrameParams& P, cudaStream_t s);
 void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s);
-void launchConnectLevel(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);

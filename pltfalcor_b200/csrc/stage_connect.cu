@@ -76,9 +76,7 @@ __global__ void __launch_bounds__(kStageThreads) k_mnee(const __grid_constant__ 
 }
 }  // namespace
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_mnee<<<grid, kStageThreads, 0, s>>>(P); }
-void launchConnectLevel(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    k_connect_a<<<grid, kStageThreads, 0, s>>>(P);
-    k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P);
-    k_connect_b<<<grid, kStageThreads, 0, s>>>(P);
-}
+void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_a<<<grid, kStageThreads, 0, s>>>(P); }
+void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P); }
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_b<<<grid, kStageThreads, 0, s>>>(P); }
 }  // namespace plt

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kStageThreads) k_unwind_step(const __grid_cons
         }
     }
     warpAdd(P.counters + 0, evals);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);
 }
 
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FrameParams P) {

@@ -146,6 +146,11 @@ class PltptSceneDesc(C.Structure):
     ]
 
 
+# enum PltptKernelClass (include/pltpt.h)
+KERNEL_CLASSES = ("raygen", "trace", "sort", "shade", "connect_a", "shadow_trace", "connect_b", "mnee", "unwind_step", "resolve", "other")
+KERNEL_CLASS_COUNT = len(KERNEL_CLASSES)
+
+
 class PltptStats(C.Structure):
     _fields_ = [
         ("kernelLaunches", C.c_uint64), ("raysClosest", C.c_uint64), ("raysAny", C.c_uint64),
@@ -155,4 +160,5 @@ class PltptStats(C.Structure):
         ("framesRendered", C.c_uint64), ("sampleStageMs", C.c_double), ("solveStageMs", C.c_double),
         ("totalPathVertices", C.c_uint64), ("totalReplaySteps", C.c_uint64), ("totalBsdfEvals", C.c_uint64),
         ("traversalNodesVisited", C.c_uint64), ("traversalTrianglesTested", C.c_uint64), ("droppedConnections", C.c_uint64),
+        ("kernelMs", C.c_double * KERNEL_CLASS_COUNT), ("kernelLaunchCount", C.c_uint64 * KERNEL_CLASS_COUNT), ("unwindJobSteps", C.c_uint64),
     ]
