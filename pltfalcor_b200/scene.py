@@ -432,6 +432,7 @@ def generate_alias_table(weights):
 class SceneBuilder:
     def __init__(self):
         self.meshes = []  # (P, N, UV, I, material, matrix)
+        self.extra_instances = []  # (mesh index, material, matrix): further instances of an already added mesh
         self.materials = []
         self.profiles = []
         self.lights = []
@@ -544,6 +545,10 @@ class SceneBuilder:
                             material, np.eye(4, dtype=f32) if matrix is None else np.asarray(matrix, f32)))
         return len(self.meshes) - 1
 
+    def add_instance(self, mesh_index, material, matrix):
+        """Another GeometryInstanceData of an existing mesh (same geometryID, own matrix and material)."""
+        self.extra_instances.append((mesh_index, material, np.asarray(matrix, f32)))
+
     # -- analytic lights (Light.cpp:366-401 for areas; LightData.slang:49-72)
     def add_rect_light(self, profile, center, normal, half_x, half_y):
         n = np.asarray(normal, np.float64) / np.linalg.norm(normal)
@@ -579,31 +584,39 @@ class SceneBuilder:
 
     def finalize(self) -> SceneBuffers:
         verts, idx, insts, mds, mats = [], [], [], [], []
-        vb, ib, tri_total, max_prims = 0, 0, 0, 0
+        vb, ib, max_prims = 0, 0, 0
+        mesh_offsets = []
         for i, (P, N, UV, I, material, M) in enumerate(self.meshes):
             verts.append(pack_vertices(P, N, UV))
             idx.append(I)
             md = np.zeros((), L.mesh_desc_dtype)
             md["vbOffset"], md["ibOffset"], md["vertexCount"], md["indexCount"], md["materialID"] = vb, ib, len(P), len(I), material
             mds.append(md)
-            gi = np.zeros((), L.geometry_instance_dtype)
-            gi["flags"] = 1 << 29  # GeometryType::TriangleMesh in the top 3 bits, 32-bit indices, CCW front faces
-            gi["globalMatrixID"], gi["materialID"], gi["geometryID"], gi["vbOffset"], gi["ibOffset"] = i, material, i, vb, ib
-            gi["instanceIndex"], gi["geometryIndex"] = i, 0
-            insts.append(gi)
-            mats.append(M)
+            mesh_offsets.append((vb, ib))
             vb += len(P)
             ib += len(I)
-            tri_total += len(I) // 3
             max_prims = max(max_prims, len(I) // 3)
+        # instances: one per mesh (in mesh order), then the extra instances
+        inst_list = [(i, m[4], m[5]) for i, m in enumerate(self.meshes)] + list(self.extra_instances)
+        tri_total = 0
+        for k, (mi, material, M) in enumerate(inst_list):
+            gi = np.zeros((), L.geometry_instance_dtype)
+            gi["flags"] = 1 << 29  # GeometryType::TriangleMesh in the top 3 bits, 32-bit indices, CCW front faces
+            gi["globalMatrixID"], gi["materialID"], gi["geometryID"] = k, material, mi
+            gi["vbOffset"], gi["ibOffset"] = mesh_offsets[mi]
+            gi["instanceIndex"], gi["geometryIndex"] = k, 0
+            insts.append(gi)
+            mats.append(M)
+            tri_total += len(self.meshes[mi][3]) // 3
         world = np.stack(mats).astype(f32) if mats else np.zeros((0, 4, 4), f32)
         invT = np.stack([np.linalg.inv(m.astype(np.float64)).T for m in mats]).astype(f32) if mats else world
         materials = np.stack(self.materials) if self.materials else np.zeros(0, L.material_blob_dtype)
         profiles = np.stack(self.profiles) if self.profiles else np.zeros(0, L.spectral_profile_dtype)
 
         # LightCollection (BuildTriangleList.cs.slang, FinalizeIntegration.cs.slang:64-110)
-        etris, flux, offsets = [], [], np.full(len(self.meshes), 0xFFFFFFFF, np.uint32)
-        for i, (P, N, UV, I, material, M) in enumerate(self.meshes):
+        etris, flux, offsets = [], [], np.full(len(inst_list), 0xFFFFFFFF, np.uint32)
+        for i, (mi, material, M) in enumerate(inst_list):
+            P, N, UV, I = self.meshes[mi][:4]
             if materials[material]["emissionSpectralId"] == L.NO_SPECTRAL_PROFILE:
                 continue
             offsets[i] = len(etris)
@@ -822,4 +835,101 @@ def layered_stress_scene(aspect=16.0 / 9.0):
                 b.add_mesh(uv_sphere(c, 0.34, 24, 48), m)
     b.add_mesh(quad([-1.0, 3.2, -1.0], [1.0, 3.2, -1.0], [1.0, 3.2, 1.0], [-1.0, 3.2, 1.0]), light)
     cam = make_camera([0.0, 2.2, 5.5], [0.0, 0.4, 0.0], focal_length=35.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def _value_noise(X, Z, seed, octaves=5):
+    """Seeded value noise (bilinear interpolation of a hashed lattice, summed over octaves), vectorised."""
+    def hash01(ix, iz, k):
+        h = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) ^ (iz.astype(np.uint64) + np.uint64(seed * 7919 + k)) * np.uint64(0xC2B2AE3D27D4EB4F))
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+        return (h & np.uint64(0xFFFFFF)).astype(np.float64) / float(1 << 24)
+    out = np.zeros_like(X, dtype=np.float64)
+    amp, freq = 1.0, 1.0
+    for k in range(octaves):
+        x, z = X * freq, Z * freq
+        ix, iz = np.floor(x).astype(np.int64), np.floor(z).astype(np.int64)
+        fx, fz = x - ix, z - iz
+        fx, fz = fx * fx * (3 - 2 * fx), fz * fz * (3 - 2 * fz)
+        ix, iz = ix + (1 << 20), iz + (1 << 20)
+        v00, v10, v01, v11 = hash01(ix, iz, k), hash01(ix + 1, iz, k), hash01(ix, iz + 1, k), hash01(ix + 1, iz + 1, k)
+        out += amp * ((v00 * (1 - fx) + v10 * fx) * (1 - fz) + (v01 * (1 - fx) + v11 * fx) * fz)
+        amp *= 0.5
+        freq *= 2.0
+    return out
+
+
+def _boxes_mesh(centers, halves):
+    """Many axis-aligned boxes merged into one mesh (24 vertices / 12 triangles each), vectorised."""
+    c, h = np.asarray(centers, np.float64), np.asarray(halves, np.float64)
+    sgn = np.array([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1],      # +z
+                    [1, -1, -1], [-1, -1, -1], [-1, 1, -1], [1, 1, -1],  # -z
+                    [1, -1, 1], [1, -1, -1], [1, 1, -1], [1, 1, 1],      # +x
+                    [-1, -1, -1], [-1, -1, 1], [-1, 1, 1], [-1, 1, -1],  # -x
+                    [-1, 1, 1], [1, 1, 1], [1, 1, -1], [-1, 1, -1],      # +y
+                    [-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1]], np.float64)  # -y
+    nrm = np.repeat(np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], np.float64), 4, axis=0)
+    P = (c[:, None, :] + sgn[None] * h[:, None, :]).reshape(-1, 3)
+    N = np.tile(nrm, (len(c), 1))
+    UV = np.tile(np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float64), (6 * len(c), 1))
+    quad_idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    I = (np.arange(6 * len(c), dtype=np.uint32)[:, None] * 4 + quad_idx[None]).reshape(-1)
+    return P.astype(f32), N.astype(f32), UV.astype(f32), I
+
+
+def city_scene(target_triangles=10_000_000, aspect=16.0 / 9.0, seed=1):
+    """BASELINE config 5: large synthetic scene with mixed PLT materials — a seeded value-noise terrain (80 % of the triangles),
+    box "buildings" merged into one unique mesh per material (12 %) and an instanced tessellated sphere (8 %), lit by an
+    area emitter and a distant light.  Material of a mesh = hash(mesh index) % 10 over the ten PLT types."""
+    b = SceneBuilder()
+    au, cu, al = b.add_ior_profiles("Au"), b.add_ior_profiles("Cu"), b.add_ior_profiles("Al")
+    lamp = b.add_emission_profile(LAMP, 40.0)
+    sun = b.add_emission_profile("2499_LED_Encaster_Calculite_domestic-use_softwhite-color_Philips_brand_22W_1500lm_7inch_3000K", 0.05)
+    mats = [
+        b.add_diffuse((0.55, 0.5, 0.45)),
+        b.add_conductor(al, 0.2),
+        b.add_dielectric(1.5, 0.1),
+        b.add_opaque_dielectric((0.3, 0.5, 0.7), 0.1),
+        b.add_thin_dielectric(1.5, 0.3, birefringence=0.1),
+        b.add_coated_conductor(cu, 0.05, tau_um=3.0, coat_ior=1.5),
+        b.add_coated_opaque_dielectric((0.7, 0.2, 0.2), 0.05, tau_um=3.0, coat_ior=1.5),
+        b.add_grated_conductor(au, (3.0, 0.0), q=0.3, q_scale=0.5, roughness=0.05, lobes=3),
+        b.add_grated_opaque_dielectric((0.5, 0.5, 0.5), (2.0, 2.0), q=0.2, gtype=1, lobes=4),
+        b.add_multilayered_stack((1, 1, 1), layers=6),
+    ]
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    rng = np.random.default_rng(seed)
+    E = 60.0  # half extent of the terrain in metres
+    n = max(4, int(math.sqrt(0.8 * target_triangles / 2)))
+    height = lambda X, Z: 2.5 * _value_noise((X + E) * 0.05, (Z + E) * 0.05, seed) - 2.0
+    b.add_mesh(grid_plane(0.0, -E, E, -E, E, n, n, height_fn=height), mats[0])
+    n_boxes = max(10, int(0.12 * target_triangles / 12))
+    centers = np.stack([rng.uniform(-E * 0.9, E * 0.9, n_boxes), np.zeros(n_boxes), rng.uniform(-E * 0.9, E * 0.9, n_boxes)], -1)
+    halves = np.stack([rng.uniform(0.05, 0.4, n_boxes), rng.uniform(0.2, 3.0, n_boxes), rng.uniform(0.05, 0.4, n_boxes)], -1)
+    centers[:, 1] = height(centers[:, 0], centers[:, 2]) + halves[:, 1] - 0.1
+    group = (np.arange(n_boxes) * 2654435761 >> 7) % 10
+    for g in range(10):
+        sel = group == g
+        if sel.any():
+            b.add_mesh(_boxes_mesh(centers[sel], halves[sel]), mats[(g * 7 + 3) % 10])
+    sphere = uv_sphere([0, 0, 0], 1.0, 48, 96) if target_triangles >= 2_000_000 else uv_sphere([0, 0, 0], 1.0, 12, 24)
+    n_inst = max(1, int(0.08 * target_triangles / (len(sphere[3]) // 3)))
+    first = None
+    for k in range(n_inst):
+        r = rng.uniform(0.3, 1.2)
+        x, z = rng.uniform(-E * 0.8, E * 0.8, 2)
+        y = float(height(np.array([x]), np.array([z]))[0]) + r + rng.uniform(0.0, 2.0)
+        M = np.eye(4, dtype=f32)
+        M[0, 0] = M[1, 1] = M[2, 2] = r
+        M[:3, 3] = [x, y, z]
+        m = mats[(k * 2654435761 >> 5) % 10]
+        if first is None:
+            first = b.add_mesh(sphere, m, M)
+        else:
+            b.add_instance(first, m, M)
+    b.add_mesh(quad([-6.0, 25.0, -6.0], [6.0, 25.0, -6.0], [6.0, 25.0, 6.0], [-6.0, 25.0, 6.0]), light)
+    b.add_distant_light(sun, direction=(-0.4, -1.0, -0.3), half_angle=math.radians(0.5))
+    cam = make_camera([0.0, 14.0, 58.0], [0.0, 0.0, 0.0], focal_length=28.0, aspect=aspect)
     return b.finalize(), cam

@@ -10,10 +10,11 @@ pytestmark = pytest.mark.gpu
 
 def _scenes():
     from pltfalcor_b200 import scene
-    return {"cornell": scene.cornell_box, "grating_sphere": scene.grating_sphere_scene, "layered": scene.layered_stress_scene}
+    return {"cornell": scene.cornell_box, "grating_sphere": scene.grating_sphere_scene, "layered": scene.layered_stress_scene,
+            "city": lambda: scene.city_scene(40_000)}  # BASELINE config 5 generator at a size the brute-force oracle finishes in seconds (instanced spheres, all ten PLT materials)
 
 
-@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered"])
+@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered", "city"])
 def loaded(request, torch_cuda, oracle):
     from pltfalcor_b200 import binding
     buffers, cam = _scenes()[request.param]()
