@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 def _scene(name):
     from pltfalcor_b200 import scene
     return {"cornell": scene.cornell_box, "grating_sphere": scene.grating_sphere_scene, "layered": scene.layered_stress_scene,
-            "city": lambda: scene.city_scene(40_000)}  # BASELINE config 5 generator at a size the brute-force oracle finishes in seconds (instanced spheres, all ten PLT materials)[name]()
+            # BASELINE config 5 generator at a size the brute-force oracle finishes in seconds (instanced spheres, all ten PLT materials)
+            "city": lambda: scene.city_scene(40_000)}[name]()
 
 
 @pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered", "city"])
