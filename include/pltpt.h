@@ -226,6 +226,14 @@ typedef struct PltptEmissiveFlux {
     float averageRadiance[3];
 } PltptEmissiveFlux;
 
+/* EnvMapData, 112 B — Source/Falcor/Scene/Lights/EnvMapData.slang:36-43. float3x4 row-major (3 rows of 4). */
+typedef struct PltptEnvMapData {
+    float transform[12];    /* local to world */
+    float invTransform[12]; /* world to local */
+    float tint[3];
+    float intensity;
+} PltptEnvMapData;
+
 /* CameraData, 656 B — Source/Falcor/Scene/Camera/CameraData.slang:36-69. Matrices row-major. */
 typedef struct PltptCameraData {
     float viewMat[16], prevViewMat[16], projMat[16], viewProjMat[16];
@@ -278,6 +286,12 @@ typedef struct PltptSceneDesc {
     /* HitInfo bit allocation (scene defines, Source/Falcor/Scene/HitInfo.cpp:52-90) */
     uint32_t hitInfoTypeBits, hitInfoInstanceIDBits, hitInfoPrimitiveIndexBits;
     uint32_t pointersAreDevice;
+    /* Environment map (Source/Falcor/Scene/Lights/EnvMap.slang:36-52): lat-long RGBA32F texels, row-major, sampled with
+     * bilinear filtering, wrap in u / clamp in v (EnvMap.cpp:121-126).  NULL = the scene has no env map
+     * (Scene::useEnvLight() false).  pltpt_set_scene builds the hierarchical importance map itself
+     * (replaces EnvMapSampler::createImportanceMap, EnvMapSampler.cpp:82-121: 512x512 texels, 64 samples per texel). */
+    const float*                 envMapTexels;        uint32_t envMapWidth, envMapHeight;
+    PltptEnvMapData              envMap;
 } PltptSceneDesc;
 
 /* ------------------------------------------------------------------------------------------

@@ -92,6 +92,23 @@ class OracleScene:
         lib().oracle_bsdf_sample(self.h, C.c_uint32(material_id), C.c_uint32(lobe_mask), C.c_uint32(n), _p(wi), _p(wavelengths), C.c_uint32(seed), _p(out), C.c_int(hwss), C.c_int(threads))
         return out
 
+    def envmap_eval(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        out = np.zeros((len(dirs), 4), np.float32)
+        lib().oracle_envmap_eval(self.h, C.c_uint32(len(dirs)), _p(dirs), _p(out))
+        return out
+
+    def envmap_sample(self, rnd):
+        rnd = np.ascontiguousarray(rnd, np.float32)
+        out = np.zeros((len(rnd), 8), np.float32)
+        lib().oracle_envmap_sample(self.h, C.c_uint32(len(rnd)), _p(rnd), _p(out))
+        return out
+
+    def envmap_importance(self):
+        out = np.zeros((512, 512), np.float32)
+        lib().oracle_envmap_importance(self.h, _p(out))
+        return out
+
     def render_frame(self, opts, cam, frame, width, height, solve=True, want_bounces=False, threads=8):
         from pltfalcor_b200 import layouts as L
         color = np.zeros((height, width, 4), np.float32)

@@ -218,6 +218,30 @@ uint64_t oracle_render_frame(void* sp, const PltptOptions* opt, const PltptCamer
     return evals.load();
 }
 
+// ---- environment map (plt_envmap.h): dirs float3 -> out float4 {eval rgb, evalPdf}; rnd float2 -> out float8 {dir, pdf, Le rgb, 0}
+void oracle_envmap_eval(void* sp, uint32_t n, const float* dirs, float* out) {
+    const Scene& sc = *(Scene*)sp;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float3 d(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        const float3 c = sc.env.eval(d);
+        out[4 * i] = c.x; out[4 * i + 1] = c.y; out[4 * i + 2] = c.z; out[4 * i + 3] = sc.env.evalPdf(d);
+    }
+}
+void oracle_envmap_sample(void* sp, uint32_t n, const float* rnd, float* out) {
+    const Scene& sc = *(Scene*)sp;
+    for (uint32_t i = 0; i < n; ++i) {
+        EnvMap::Sample s;
+        sc.env.sample(float2(rnd[2 * i], rnd[2 * i + 1]), s);
+        float* o = out + 8 * i;
+        o[0] = s.dir.x; o[1] = s.dir.y; o[2] = s.dir.z; o[3] = s.pdf; o[4] = s.Le.x; o[5] = s.Le.y; o[6] = s.Le.z; o[7] = 0.f;
+    }
+}
+void oracle_envmap_importance(void* sp, float* out) {
+    const Scene& sc = *(Scene*)sp;
+    if (!sc.env.valid()) return;
+    std::memcpy(out, sc.env.mips[0].data(), sc.env.mips[0].size() * sizeof(float));
+}
+
 int oracle_hardware_threads() { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

@@ -47,7 +47,7 @@ struct Integrator {
 
     // ---- derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
     bool kUseEmissiveLights() const { return opt.useEmissiveLights && scene->d.emissiveTriangleCount > 0; }
-    bool kUseEnvLight() const { return false; }  // env maps: not yet restated
+    bool kUseEnvLight() const { return opt.useEnvLights && scene->env.valid(); }  // PLTPT.cpp:235
     bool kUseAnalyticLights() const { return opt.useAnalyticLights && scene->d.lightCount > 0; }
     bool kDoNEE() const { return opt.doNEE; }
     bool kDoMSonNEE() const { return opt.doNEE && opt.doMNEE; }
@@ -301,6 +301,22 @@ struct Integrator {
         float denom = hlsl_max(FLT_MINf, cosTheta * getEmissiveTriangle(triangleIndex).area);
         return sel * (distSqr / denom);
     }
+    // LightSampling.slangh:86-102
+    bool generateEnvMapSample(const ShadingData& sd, SampleGenerator& sg, float wavelength, LightSample& ls) const {
+        ls = LightSample();
+        if (!kUseEnvLight()) return false;
+        EnvMap::Sample lightSample;
+        if (!scene->env.sample(sampleNext2D(sg), lightSample)) return false;
+        const hwss_t wavelengths = SpectrumSampler::hwssWavelengths(wavelength);
+        const hwss_t Le = SpectrumUtils::rgbToSpectrum(lightSample.Le, wavelengths);
+        const hwss_t L = lightSample.pdf > 0.f ? Le / lightSample.pdf : hwss_t(.0f);
+        ls.beam = pltSourceBeamDistant(-lightSample.dir, opt.sourcingMaxBeamOmega, L, wavelengths, opt.sourcingMaxBeamOmega, false, hwss_samples());
+        ls.pdf = lightSample.pdf;
+        ls.origin = computeNewRayOrigin(sd, lightSample.dir);
+        ls.distance = FLT_MAXf;  // kRayTMax
+        ls.dir = lightSample.dir;
+        return anyPositive(L);
+    }
     // LightSampling.slangh:104-126
     bool generateEmissiveSample(const ShadingData& sd, SampleGenerator& sg, float wavelength, bool importanceSample, LightSample& ls) const {
         ls = LightSample();
@@ -422,6 +438,7 @@ struct Integrator {
         const bool success = kNEEUsePerTileSG() ? selectLightType(lightType, selectionPdf, tilesg) : selectLightType(lightType, selectionPdf, sg);
         if (!success) return false;
         bool valid = false;
+        if (kUseEnvLight() && lightType == LT_EnvMap) valid = generateEnvMapSample(sd, sg, wavelength, ls);
         if (kUseEmissiveLights() && lightType == LT_Emissive) valid = generateEmissiveSample(sd, sg, wavelength, importanceSample, ls);
         if (kUseAnalyticLights() && lightType == LT_Analytic) valid = generateAnalyticLightSample(sd, sg, wavelength, importanceSample, ls);
         ls.lightType = lightType;
@@ -494,6 +511,26 @@ struct Integrator {
                 forwardUnwind(bounceIdx, px, py, beam);
                 measure(solveData, bounceIdx, bounce.pathContribution, beam);
             }
+        }
+    }
+
+    // pltpt_solve.rt.slang:371-396
+    void onMiss(PLTSolve& solveData, int bounceIdx, const PltptBounce& bounce, uint32_t px, uint32_t py) {
+        const float3 wo = bounceWi(bounce);
+        RayFlags bf; bf.flags = bounce.flags;
+        const bool didNEE = wasNEEAvailable(bounceIdx, bf);
+        if (kUseEnvLight() && (kDoMIS() || !didNEE)) {
+            const bool needMIS = kDoMIS() && didNEE;
+            float p[3];
+            lightTypeProbabilities(p);
+            const float lightPdf = p[0] * scene->env.evalPdf(-wo);
+            const float misWeight = needMIS ? MISWeight(bounce.lastNonDeltaPdf, lightPdf) : 1.f;
+            const hwss_t wavelengths = SpectrumSampler::hwssWavelengths(solveData.wavelength);
+            const hwss_t Le = misWeight * SpectrumUtils::rgbToSpectrum(scene->env.eval(-wo), wavelengths);
+            PLTBeam beam = pltSourceBeamDistant(wo, opt.sourcingMaxBeamOmega, Le, wavelengths, opt.sourcingMaxBeamOmega, false, hwss_samples());
+            if (!opt.HWSSDoMIS && bf.dispersiveDeltaSegment()) beam.collapseToHeroWavelengthOnly();
+            forwardUnwind(bounceIdx, px, py, beam);
+            measure(solveData, bounceIdx, bounce.pathContribution, beam);
         }
     }
 
@@ -772,7 +809,7 @@ struct Integrator {
         for (int p = 0;; ++p) {
             const PltptBounce bounce = bounceAt(px, py, p);
             RayFlags bf; bf.flags = bounce.flags;
-            if (bf.miss()) break;  // onMiss: env light only (pltpt_solve.rt.slang:371-396); no env map support yet
+            if (bf.miss()) { onMiss(solveData, p, bounce, px, py); break; }
             const TriangleHit triangleHit = scene->unpackHit(bounce.hit);
             const VertexData v = scene->getVertexData(triangleHit);
             const uint32_t materialID = scene->getMaterialID(triangleHit.instanceID);

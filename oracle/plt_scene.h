@@ -12,6 +12,7 @@
 // A brute-force loop and a binary BVH (same leaf test; validated against brute force) are provided.
 #pragma once
 #include "plt_bsdf.h"
+#include "plt_envmap.h"
 #include <vector>
 #include <numeric>
 
@@ -42,6 +43,7 @@ struct RayHit { float t = 0; TriangleHit hit; };
 struct Scene {
     PltptSceneDesc d{};
     ProfileTable profiles;
+    EnvMap env;
     // derived
     std::vector<uint32_t> instTriOffset;  // first global triangle of each instance
     std::vector<WorldTri> tris;           // world-space triangles, instance-major
@@ -80,6 +82,7 @@ struct Scene {
             }
         }
         buildBVH();
+        env.init(d);
     }
 
     // Scene.slang getLocalIndices / getIndices

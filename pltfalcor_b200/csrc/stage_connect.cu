@@ -9,9 +9,21 @@
 //                    occluders — isolated so that it cannot stall the coherent NEE work (north-star (d)).
 #include "plt_integrator.cuh"
 
+#ifndef PLT_MINB_CONNECT_A
+#define PLT_MINB_CONNECT_A 1
+#endif
+#ifndef PLT_MINB_SHADOW_TRACE
+#define PLT_MINB_SHADOW_TRACE 1
+#endif
+#ifndef PLT_MINB_CONNECT_B
+#define PLT_MINB_CONNECT_B 1
+#endif
+#ifndef PLT_MINB_MNEE
+#define PLT_MINB_MNEE 1
+#endif
 namespace plt {
 namespace {
-__global__ void __launch_bounds__(kStageThreads) k_connect_a(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     uint32_t evals = 0, verts = 0;
@@ -25,7 +37,7 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_a(const __grid_consta
     warpAdd(P.counters + 4, verts * P.level);  // sum over paths of L(L-1)/2 == sum over recorded vertices of their index
 }
 
-__global__ void __launch_bounds__(kStageThreads) k_shadow_trace(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
@@ -48,7 +60,7 @@ __global__ void __launch_bounds__(kStageThreads) k_shadow_trace(const __grid_con
     warpAdd(P.counters + 6, tc.tris);
 }
 
-__global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     uint32_t evals = 0;
@@ -62,7 +74,7 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_consta
 }
 
 // Manifold-walk kernel: one thread per parked connection.  Runs once per tile after all connect launches.
-__global__ void __launch_bounds__(kStageThreads) k_mnee(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee(const __grid_constant__ FrameParams P) {
     const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};

@@ -8,6 +8,12 @@
 // connect kernel for vertex b.
 #include "plt_integrator.cuh"
 
+#ifndef PLT_MINB_SHADE
+#define PLT_MINB_SHADE 1
+#endif
+#ifndef PLT_MINB_TRACE
+#define PLT_MINB_TRACE 1
+#endif
 namespace plt {
 namespace {
 __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ FrameParams P) {
@@ -15,7 +21,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ FramePar
     if (pixel < P.pixelCount) raygenPixel(P, pixel);
 }
 
-__global__ void __launch_bounds__(kStageThreads) k_trace(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const __grid_constant__ FrameParams P) {
     const bool primary = P.level == 0;
     // bounce 0 walks the implicit queue of all pixels (8x4 tiles per warp, padded), later bounces the queue the shade kernel filled
     const uint32_t tilesX = (P.width + 7) / 8, tilesY = (P.tileRows + 3) / 4;
@@ -34,7 +40,7 @@ __global__ void __launch_bounds__(kStageThreads) k_trace(const __grid_constant__
     warpAdd(P.counters + 6, tc.tris);
 }
 
-__global__ void __launch_bounds__(kStageThreads) k_shade(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADE) k_shade(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     TraversalCounters tc = {0, 0};

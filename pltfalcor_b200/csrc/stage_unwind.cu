@@ -3,6 +3,9 @@
 // recorded vertex; jobs are walked in MaterialType order, 128 same-type jobs per CTA, so a warp executes one BSDF.
 #include "plt_integrator.cuh"
 
+#ifndef PLT_MINB_UNWIND_STEP
+#define PLT_MINB_UNWIND_STEP 1
+#endif
 namespace plt {
 namespace {
 // Counting-sort scatter of the pending list into material-type order (dst).  Runs between a producer and a consumer launch.
@@ -37,7 +40,7 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
     }
 }
 
-__global__ void __launch_bounds__(kStageThreads) k_unwind_step(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[2 * kQueueTypes + 2];
     uint32_t evals = 0;
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {

@@ -126,6 +126,14 @@ assert C.sizeof(PltptCameraData) == 656
 assert C.sizeof(PltptOptions) == 96
 
 
+class PltptEnvMapData(C.Structure):
+    """EnvMapData, Source/Falcor/Scene/Lights/EnvMapData.slang:36-43 (112 B); float3x4 row-major."""
+    _fields_ = [("transform", C.c_float * 12), ("invTransform", C.c_float * 12), ("tint", C.c_float * 3), ("intensity", C.c_float)]
+
+
+assert C.sizeof(PltptEnvMapData) == 112
+
+
 class PltptSceneDesc(C.Structure):
     _fields_ = [
         ("vertices", C.c_void_p), ("vertexCount", C.c_uint32),
@@ -143,6 +151,8 @@ class PltptSceneDesc(C.Structure):
         ("triangleAliasTable", C.c_void_p), ("invWeightsSum", C.c_float),
         ("hitInfoTypeBits", C.c_uint32), ("hitInfoInstanceIDBits", C.c_uint32), ("hitInfoPrimitiveIndexBits", C.c_uint32),
         ("pointersAreDevice", C.c_uint32),
+        ("envMapTexels", C.c_void_p), ("envMapWidth", C.c_uint32), ("envMapHeight", C.c_uint32),
+        ("envMap", PltptEnvMapData),
     ]
 
 

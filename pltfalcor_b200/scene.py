@@ -354,6 +354,14 @@ class SceneBuffers:
         d.triangleAliasTable, d.invWeightsSum = ptr("triangleAliasTable"), s["invWeightsSum"]
         d.hitInfoTypeBits, d.hitInfoInstanceIDBits, d.hitInfoPrimitiveIndexBits = 3, s["instanceIDBits"], s["primitiveIndexBits"]
         d.pointersAreDevice = 1 if device else 0
+        d.envMapTexels = ptr("envMapTexels")
+        if d.envMapTexels:
+            d.envMapWidth, d.envMapHeight = s["envMapWidth"], s["envMapHeight"]
+            e = s["envMap"]
+            d.envMap.transform[:] = [float(x) for x in np.asarray(e["transform"], np.float32).reshape(-1)]
+            d.envMap.invTransform[:] = [float(x) for x in np.asarray(e["invTransform"], np.float32).reshape(-1)]
+            d.envMap.tint[:] = [float(x) for x in e["tint"]]
+            d.envMap.intensity = float(e["intensity"])
         return d
 
     def to_device(self, torch, device="cuda:0"):
@@ -387,6 +395,12 @@ class SceneBuffers:
                 raw = b"" if a is None or a.size == 0 else np.ascontiguousarray(a).tobytes()
                 f.write(np.uint64(len(raw)).tobytes())
                 f.write(raw)
+            env = self.arrays.get("envMapTexels")  # optional trailing section: u64 texel bytes, then w, h (u32), EnvMapData (112 B), texels
+            f.write(np.uint64(0 if env is None else env.nbytes).tobytes())
+            if env is not None:
+                f.write(np.array([s["envMapWidth"], s["envMapHeight"]], np.uint32).tobytes())
+                f.write(bytes(self.desc().envMap))
+                f.write(np.ascontiguousarray(env).tobytes())
 
 
 def _alloc_bits(count):
@@ -436,6 +450,15 @@ class SceneBuilder:
         self.materials = []
         self.profiles = []
         self.lights = []
+        self.env = None  # (texels HxWx4 f32, EnvMapData dict)
+
+    def set_env_map(self, texels, intensity=1.0, tint=(1.0, 1.0, 1.0), rot_y=0.0):
+        """EnvMap (Scene/Lights/EnvMap.cpp:60-110): lat-long RGBA32F texels; `rot_y` (radians) is the env map's rotation about +y
+        (EnvMap::setRotation builds transform = rotation, invTransform = its inverse)."""
+        c, s_ = math.cos(rot_y), math.sin(rot_y)
+        R = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0]], f32)
+        Ri = np.array([[c, 0, -s_, 0], [0, 1, 0, 0], [s_, 0, c, 0]], f32)
+        self.env = (np.ascontiguousarray(texels, f32), dict(transform=R, invTransform=Ri, tint=tuple(tint), intensity=float(intensity)))
 
     # -- spectral profiles (SceneBuilder::addSpectralProfile*, SceneBuilder.cpp:962-999)
     def add_profile(self, wavelengths, values, compute_icdf=True, scale=1.0):
@@ -665,7 +688,30 @@ class SceneBuilder:
             emissiveTriangleCount=len(etris), invWeightsSum=inv_sum, triangleCount=tri_total,
             instanceIDBits=_alloc_bits(len(insts)), primitiveIndexBits=_alloc_bits(max_prims),
         )
+        if self.env is not None:
+            arrays["envMapTexels"] = self.env[0]
+            scalars.update(envMapWidth=self.env[0].shape[1], envMapHeight=self.env[0].shape[0], envMap=self.env[1])
         return SceneBuffers(arrays, scalars)
+
+
+def procedural_sky(width=256, height=128, sun_dir=(0.4, 0.6, 0.5), sun_radiance=60.0, seed=3):
+    """Synthetic lat-long environment map (no asset files offline): horizon-to-zenith gradient, a dim ground, a soft sun lobe
+    and low-amplitude seeded noise so that neighbouring texels differ (exercises the bilinear filter and the importance map)."""
+    v = (np.arange(height, dtype=np.float64) + 0.5) / height
+    u = (np.arange(width, dtype=np.float64) + 0.5) / width
+    U, V = np.meshgrid(u, v)
+    phi, theta = math.pi * (2.0 * U - 1.0), math.pi * V            # latlong_map_to_world (MathHelpers.slang:120-129)
+    d = np.stack([np.sin(theta) * np.sin(phi), np.cos(theta), -np.sin(theta) * np.cos(phi)], -1)
+    up = np.clip(d[..., 1], 0.0, 1.0)
+    sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.35 * (1 - up), 0.55 + 0.3 * (1 - up)], -1)
+    ground = np.array([0.12, 0.10, 0.08])
+    rgb = np.where(d[..., 1:2] >= 0.0, sky, ground)
+    sd = np.asarray(sun_dir, np.float64)
+    sd /= np.linalg.norm(sd)
+    rgb = rgb + sun_radiance * np.array([1.0, 0.9, 0.75]) * np.exp(-(1.0 - np.clip(d @ sd, -1, 1)) / 0.004)[..., None]
+    rng = np.random.default_rng(seed)
+    rgb = rgb * (1.0 + 0.1 * (rng.random((height, width, 1)) - 0.5))
+    return np.concatenate([rgb, np.ones((height, width, 1))], -1).astype(f32)
 
 
 # ----------------------------------------------------------------------------------------------- camera
@@ -753,6 +799,31 @@ def cornell_box(aspect=16.0 / 9.0, dielectric_roughness=0.1, conductor_roughness
     b.add_mesh(box([-0.6, 0.6, -0.3], [0.3, 0.6, 0.3], rot_y=0.3), gold)
     b.add_mesh(box([0.6, 0.3, 0.3], [0.3, 0.3, 0.3], rot_y=-0.25), glass)
     cam = make_camera([0.0, 1.0, 3.5], [0.0, 1.0, 0.0], focal_length=35.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def env_scene(aspect=16.0 / 9.0, with_emitter=True):
+    """Environment-lit scene (EnvMapSampler NEE + onMiss): open ground plane, a rough Au conductor sphere, a smooth
+    Dielectric sphere (MNEE towards the distant env light), a coated sphere and a diffuse box under a procedural sky rotated by
+    0.7 rad; optionally a small area emitter so that the light-type selection mixes env and emissive sampling."""
+    b = SceneBuilder()
+    au, cu = b.add_ior_profiles("Au"), b.add_ior_profiles("Cu")
+    lamp = b.add_emission_profile(LAMP, 2.0)
+    ground = b.add_diffuse((0.5, 0.5, 0.45))
+    gold = b.add_conductor(au, roughness=0.2, gamma=3.0)
+    glass = b.add_dielectric(ior=1.5, roughness=0.0)
+    coated = b.add_coated_conductor(cu, 0.05, tau_um=2.0, coat_ior=1.5)
+    red = b.add_diffuse((0.65, 0.1, 0.1))
+    b.add_mesh(grid_plane(0.0, -6.0, 6.0, -6.0, 6.0, 4, 4), ground)
+    b.add_mesh(uv_sphere([-1.3, 0.6, 0.0], 0.6, 32, 64), gold)
+    b.add_mesh(uv_sphere([0.0, 0.6, 0.4], 0.6, 32, 64), glass)
+    b.add_mesh(uv_sphere([1.3, 0.6, 0.0], 0.6, 32, 64), coated)
+    b.add_mesh(box([0.0, 0.4, -1.6], [0.9, 0.4, 0.3], rot_y=0.2), red)
+    if with_emitter:
+        light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+        b.add_mesh(quad([-0.4, 2.8, -0.4], [0.4, 2.8, -0.4], [0.4, 2.8, 0.4], [-0.4, 2.8, 0.4]), light)
+    b.set_env_map(procedural_sky(), intensity=1.5, tint=(1.0, 0.95, 0.9), rot_y=0.7)
+    cam = make_camera([0.0, 1.5, 4.5], [0.0, 0.6, 0.0], focal_length=30.0, aspect=aspect)
     return b.finalize(), cam
 
 

@@ -34,7 +34,7 @@ for path in sys.argv[2:]:
         return v * UNIT.get(units[col[name]], 1.0) if scale else v
 
     for r in rows[2:]:
-        k = r[col["Kernel Name"]].split("(")[0].replace("plt::<unnamed>::", "")
+        k = r[col["Kernel Name"]].split("(")[0].split("::")[-1]  # "plt::<unnamed>::k_x(FrameParams)" (ncu may print "unnamed>::k_x") -> "k_x"
         a = acc[k]
         rd, wr = get(r, "dram__bytes_read.sum"), get(r, "dram__bytes_write.sum")
         if rd is not None and wr is not None:

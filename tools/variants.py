@@ -1,0 +1,98 @@
+"""Builds experimental variants of libpltpt.so (extra nvcc flags per source) under pltfalcor_b200/build/variants/<name>/ and times
+them on the bench workload.  Development tool: the product build is pltfalcor_b200/build.py.
+
+  python tools/variants.py build            # here (cross-compile)
+  python tools/variants.py bench [frames]   # on the GPU box: per-kernel ms of one 1080p Cornell frame for every built variant
+  python tools/variants.py one <lib> [frames]
+"""
+import json
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from pltfalcor_b200 import build as B  # noqa: E402
+
+VDIR = os.path.join(B._HERE, "build", "variants")
+VARIANTS = {
+    "base": {},
+    "u3": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=3"]},
+    "u4": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=4"]},
+    "u3fm": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=3", "-fmad=true"]},
+    "s4": {"stage_sample.cu": ["-DPLT_MINB_SHADE=4"]},
+    "s4c4": {"stage_sample.cu": ["-DPLT_MINB_SHADE=4"], "stage_connect.cu": ["-DPLT_MINB_CONNECT_B=4"]},
+}
+
+
+def build_variant(name, flags):
+    d = os.path.join(VDIR, name)
+    os.makedirs(d, exist_ok=True)
+    nvcc = B._nvcc()
+
+    def one(src):
+        obj = os.path.join(d, src.replace(".cu", ".o"))
+        extra = flags.get(src, [])
+        base = [f for f in B.NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in extra)]
+        if not extra:  # unchanged source: reuse the product object when it is fresh
+            prod = os.path.join(B._HERE, "build", src.replace(".cu", ".o"))
+            if os.path.exists(prod) and all(os.path.getmtime(x) <= os.path.getmtime(prod) for x in B._deps()):
+                return prod
+        r = subprocess.run([nvcc, *base, *extra, "-c", os.path.join(B.CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(len(B.SOURCES)) as ex:
+        objs = list(ex.map(one, B.SOURCES))
+    lib = os.path.join(d, "libpltpt.so")
+    r = subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-lcudart_static", "-Xlinker", "--no-undefined"], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError(r.stderr)
+    return lib
+
+
+def bench_one(lib, frames):
+    import torch
+    from pltfalcor_b200 import binding, layouts as L, scene
+    binding.LIB = lib
+    W, H = 1920, 1080
+    buffers, cam = scene.cornell_box(aspect=W / H)
+    p = binding.Pltpt(maxBounces=8)
+    p.set_scene(buffers)
+    acc = torch.zeros((H, W, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 3, W, H, acc)
+    torch.cuda.synchronize()
+    acc.zero_()
+    p.reset_stats()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    p.render_accumulate(cam, 3, 1, frames, W, H, acc)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / frames
+    p.set_profiling(True)
+    p.reset_stats()
+    p.render_accumulate(cam, 3, 1, frames, W, H, acc)
+    torch.cuda.synchronize()
+    s = p.stats()
+    k = {n: round(s["kernelMs"][n] / frames, 3) for n in L.KERNEL_CLASSES if s["kernelLaunchCount"][n]}
+    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "ms_per_frame": round(ms, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean()) / (2 * frames), "kernels": k}))
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "build"
+    if cmd == "build":
+        B.build()
+        names = sys.argv[2:] or list(VARIANTS)
+        for n in names:
+            print(n, build_variant(n, VARIANTS[n]))
+    elif cmd == "bench":
+        frames = sys.argv[2] if len(sys.argv) > 2 else "16"
+        for n in sorted(os.listdir(VDIR)):
+            lib = os.path.join(VDIR, n, "libpltpt.so")
+            if os.path.exists(lib):
+                subprocess.run([sys.executable, os.path.abspath(__file__), "one", lib, frames])
+    elif cmd == "one":
+        bench_one(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 16)
