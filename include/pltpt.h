@@ -340,6 +340,14 @@ PLTPT_API int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const 
                                       uint32_t width, uint32_t height, PltptBounce* bouncesHost);
 
 /* ------------------------------------------------------------------------------------------
+ * Environment-map queries (parity checks of EnvMap.eval, EnvMap.slang:57-74, and EnvMapSampler.sample / evalPdf,
+ * EnvMapSampler.slang:71-162).  Device pointers.  eval: n world directions float3 -> float4 {radiance rgb, pdf};
+ * sample: n random pairs float2 -> 2 x float4 {dir xyz, pdf}, {Le rgb, 0}.  Fails when the scene has no env map.
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_envmap_eval(PltptHandle h, uint32_t n, const float* dirs, float* rgbPdf, void* stream);
+PLTPT_API int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Ray queries against the scene BVH (replaces TraceRay, pltpt_sample.rt.slang:174-183,
  * ShadowRays.slangh:68-77,115-124).  Rays are float[8] {ox,oy,oz,tmin,dx,dy,dz,tmax}.
  * Closest hit writes uint4 {instanceID, primitiveIndex, asuint(u), asuint(v)} + t;

@@ -15,6 +15,7 @@ EXPORTS = [
     "pltpt_default_options", "pltpt_create", "pltpt_destroy", "pltpt_last_error", "pltpt_version", "pltpt_set_options", "pltpt_set_scene",
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
+    "pltpt_envmap_eval", "pltpt_envmap_sample",
 ]
 
 
@@ -50,6 +51,8 @@ def lib():
         _lib.pltpt_get_stats.argtypes = [vp, vp]
         _lib.pltpt_reset_stats.argtypes = [vp]
         _lib.pltpt_set_profiling.argtypes = [vp, C.c_int]
+        _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
+        _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
     return _lib
 
 
@@ -142,6 +145,15 @@ class Pltpt:
 
     def trace_any(self, rays, occluded, stream=None):
         _check(lib().pltpt_trace_any(self.h, rays.shape[0], _dp(rays), _dp(occluded), stream))
+
+    # ---- environment map ------------------------------------------------------------------------------------
+    def envmap_eval(self, dirs, out, stream=None):
+        """dirs: (n,3) world directions; out: (n,4) {radiance rgb, pdf} — torch CUDA float32 tensors."""
+        _check(lib().pltpt_envmap_eval(self.h, dirs.shape[0], _dp(dirs), _dp(out), stream))
+
+    def envmap_sample(self, rnd, out, stream=None):
+        """rnd: (n,2) in [0,1); out: (n,8) {dir xyz, pdf, Le rgb, 0}."""
+        _check(lib().pltpt_envmap_sample(self.h, rnd.shape[0], _dp(rnd), _dp(out), stream))
 
     # ---- BSDF sweeps ------------------------------------------------------------------------------------------
     def bsdf_eval_mueller(self, material_id, lobe, wi, wo, hero, out, stream=None):

@@ -275,6 +275,100 @@ int upload(DevBuf& buf, const void* src, size_t bytes, bool device) {
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ environment map
+namespace {
+// EnvMapSamplerSetup.cs.slang:47-75: one thread per importance-map texel, 8x8 bilinear luminance samples of the lat-long map
+__global__ void __launch_bounds__(256) k_env_importance(DevEnvMap e, float* __restrict__ out) {
+    const uint32_t px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (px >= kEnvImportanceDim || py >= kEnvImportanceDim) return;
+    const float invSamples = 1.f / float(kEnvImportanceSamples * kEnvImportanceSamples);
+    float L = 0.f;
+    for (uint32_t y = 0; y < kEnvImportanceSamples; ++y)
+        for (uint32_t x = 0; x < kEnvImportanceSamples; ++x) {
+            const float2 p = mk2((float(px * kEnvImportanceSamples + x) + 0.5f) / float(kEnvImportanceDim * kEnvImportanceSamples),
+                                 (float(py * kEnvImportanceSamples + y) + 0.5f) / float(kEnvImportanceDim * kEnvImportanceSamples));
+            L += luminance709(envSampleBilinear(e, world_to_latlong_map(oct_to_ndir_equal_area_unorm(p))));
+        }
+    out[size_t(py) * kEnvImportanceDim + px] = L * invSamples;
+}
+// Texture::generateMips: 2x2 box filter, one launch per mip level
+__global__ void __launch_bounds__(256) k_env_mip(const float* __restrict__ src, float* __restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n) return;
+    const uint32_t x = i % n, y = i / n;
+    const size_t o = size_t(2 * y) * (2 * n) + 2 * x;
+    dst[i] = ((src[o] + src[o + 1]) + (src[o + 2 * n] + src[o + 2 * n + 1])) * 0.25f;
+}
+__global__ void k_env_eval(DevEnvMap e, uint32_t n, const float* __restrict__ dirs, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 d = mk3(dirs[3 * size_t(i)], dirs[3 * size_t(i) + 1], dirs[3 * size_t(i) + 2]);
+    const float3 c = envEval(e, d);
+    out[i] = mk4(c.x, c.y, c.z, envEvalPdf(e, d));
+}
+__global__ void k_env_sample(DevEnvMap e, uint32_t n, const float2* __restrict__ rnd, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvSample s;
+    envSample(e, rnd[i], s);
+    out[2 * size_t(i)] = mk4(s.dir.x, s.dir.y, s.dir.z, s.pdf);
+    out[2 * size_t(i) + 1] = mk4(s.Le.x, s.Le.y, s.Le.z, 0.f);
+}
+
+// Replaces EnvMap::setShaderData + EnvMapSampler::createImportanceMap (EnvMapSampler.cpp:82-121)
+int buildEnvMap(PltptContext* h, const PltptSceneDesc* s, bool dev) {
+    DevEnvMap& e = h->scene.env;
+    e = DevEnvMap{};
+    h->envTexels.release();
+    h->envImportance.release();
+    if (!s->envMapTexels) return PLTPT_OK;
+    if (s->envMapWidth == 0 || s->envMapHeight == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "environment map has zero extent");
+    if (int r = upload(h->envTexels, s->envMapTexels, size_t(s->envMapWidth) * s->envMapHeight * 16, dev)) return r;
+    PLT_CUDA(h->envImportance.ensure(size_t(kEnvImportanceFloats) * sizeof(float)));
+    e.texels = h->envTexels.as<float4>();
+    e.importance = h->envImportance.as<float>();
+    e.width = s->envMapWidth; e.height = s->envMapHeight;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { e.toWorld[3 * r + c] = s->envMap.transform[4 * r + c]; e.toLocal[3 * r + c] = s->envMap.invTransform[4 * r + c]; }
+    e.intensity = mk3(s->envMap.tint[0] * s->envMap.intensity, s->envMap.tint[1] * s->envMap.intensity, s->envMap.tint[2] * s->envMap.intensity);
+    float* imp = h->envImportance.as<float>();
+    k_env_importance<<<dim3(kEnvImportanceDim / 16, kEnvImportanceDim / 16), 256>>>(e, imp);
+    for (uint32_t mip = 1; mip <= kEnvImportanceBaseMip; ++mip) {
+        const uint32_t n = kEnvImportanceDim >> mip;
+        k_env_mip<<<(n * n + 255) / 256, 256>>>(imp + envMipOffset(mip - 1), imp + envMipOffset(mip), n);
+    }
+    h->stats.kernelLaunches += 1 + kEnvImportanceBaseMip;
+    PLT_CUDA(cudaDeviceSynchronize());
+    return PLTPT_OK;
+}
+}  // namespace
+
+/* Environment-map queries for the parity checks (EnvMap.eval + EnvMapSampler.evalPdf; EnvMapSampler.sample). Device pointers. */
+extern "C" int pltpt_envmap_eval(PltptHandle h, uint32_t n, const float* dirs, float* rgbPdf, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (!h->scene.env.texels) return fail(PLTPT_ERR_INVALID_ARGUMENT, "the scene has no environment map");
+    if (n == 0) return PLTPT_OK;
+    if (!dirs || !rgbPdf) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    k_env_eval<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->scene.env, n, dirs, reinterpret_cast<float4*>(rgbPdf));
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+extern "C" int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, float* out, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (!h->scene.env.texels) return fail(PLTPT_ERR_INVALID_ARGUMENT, "the scene has no environment map");
+    if (n == 0) return PLTPT_OK;
+    if (!rnd || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    k_env_sample<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->scene.env, n, reinterpret_cast<const float2*>(rnd), reinterpret_cast<float4*>(out));
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+
 extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     PLT_CUDA(cudaSetDevice(h->device));
@@ -357,6 +451,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (d.triCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no triangles");
 
     if (int r = buildBvh(h, 0)) return r;
+    if (int r = buildEnvMap(h, s, dev)) return r;
     h->hasScene = true;
     return PLTPT_OK;
 }

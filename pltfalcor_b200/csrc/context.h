@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 #include "plt_bsdf.cuh"
+#include "plt_envmap.cuh"
 
 namespace plt {
 
@@ -49,6 +50,7 @@ struct DevScene {
     uint32_t instanceCount, lightCount, etriCount, activeTriCount, triCount;
     float invWeightsSum;
     uint32_t hitTypeBits, hitInstBits, hitPrimBits;
+    DevEnvMap env;  // env.texels == nullptr: the scene has no environment map
 };
 
 struct DevBuf {
@@ -76,6 +78,7 @@ struct PltptContext {
     // owned device copies
     plt::DevBuf vertices, indexData, instances, meshes, world, worldIT, materials, profiles, lights, etris, eflux, activeTris, perMeshOffset, alias, instTriOffset;
     plt::DevBuf bvhNodes, bvhTris, bvhScratch[8];
+    plt::DevBuf envTexels, envImportance;
     // host mirrors needed by the host logic
     std::vector<PltptGeometryInstance> hInstances;
     std::vector<PltptMeshDesc> hMeshes;

@@ -9,7 +9,7 @@ namespace plt {
 namespace {
 // worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
 size_t workBytesPerPixel(uint32_t records) {
-    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * sizeof(MneeItem) + sizeof(ConnItem) + 32 + 16 + 4;
+    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4 + 8) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * sizeof(MneeItem) + sizeof(ConnItem) + 32 + 16 + 4;
 }
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
@@ -37,12 +37,14 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     PLT_CUDA(c->work[1].ensure(records * sizeof(float4)));
     PLT_CUDA(c->work[2].ensure(records * sizeof(float2)));
     PLT_CUDA(c->work[3].ensure(16 * sizeof(unsigned long long)));
-    for (int k = 0; k < 4; ++k) PLT_CUDA(c->work[5 + k].ensure(records * sizeof(float4)));
+    PLT_CUDA(c->work[5].ensure(records * 4 * sizeof(float4)));
     PLT_CUDA(c->work[9].ensure(records));
     PLT_CUDA(c->work[10].ensure(jobCapacity * kJobPlanes * sizeof(float4)));
     PLT_CUDA(c->work[11].ensure(jobCapacity * 4));
     PLT_CUDA(c->work[12].ensure(jobCapacity));
     PLT_CUDA(c->work[13].ensure(jobCapacity * 4));
+    PLT_CUDA(c->work[6].ensure(jobCapacity * 4));
+    PLT_CUDA(c->work[7].ensure(jobCapacity * 4));
     PLT_CUDA(c->work[14].ensure(256 * 4));
     PLT_CUDA(c->work[15].ensure(jobCapacity * sizeof(float4)));  // contrib: 2 * records float4
     for (int k = 0; k < 7; ++k) PLT_CUDA(c->work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
@@ -57,13 +59,15 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     P.bDir = c->work[1].as<float4>();
     P.bPdf = c->work[2].as<float2>();
     P.counters = c->work[3].as<unsigned long long>();
-    P.vc0 = c->work[5].as<float4>(); P.vc1 = c->work[6].as<float4>(); P.vc2 = c->work[7].as<float4>(); P.vc3 = c->work[8].as<float4>();
+    P.vc = c->work[5].as<float4>();
     P.vMatType = c->work[9].as<uint8_t>();
     P.job = c->work[10].as<float4>();
     P.jobCapacity = uint32_t(jobCapacity);
     P.pending = c->work[11].as<uint32_t>();
     P.pendingType = c->work[12].as<uint8_t>();
     P.sorted = c->work[13].as<uint32_t>();
+    P.pendingAux = c->work[6].as<uint32_t>();
+    P.sortedAux = c->work[7].as<uint32_t>();
     P.queueCount = c->work[14].as<uint32_t>();
     P.jobCount = P.queueCount + 32;
     P.contrib = c->work[15].as<float4>();
@@ -75,6 +79,10 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     P.mneeItems = c->work[26].as<MneeItem>();
     P.mneeCount = P.queueCount + 34;
     P.mneeCapacity = 2 * tilePixels;
+    PLT_CUDA(c->work[24].ensure(size_t(tilePixels) * 4));
+    P.missList = c->work[24].as<uint32_t>();
+    P.missCount = P.queueCount + 36;
+    if (tilePixels >= (1u << 26)) { setError("tile too large for the packed miss list"); return PLTPT_ERR_INVALID_ARGUMENT; }
     P.connItems = c->work[27].as<ConnItem>();
     P.shadowRays = c->work[28].as<float4>();
     P.shadowHits = c->work[29].as<uint4>();
@@ -82,6 +90,7 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     c->workW = w; c->workH = h; c->workBounces = recordsPerPixel;
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
+    P.useEnv = c->opt.useEnvLights && c->scene.env.texels != nullptr;  // PLTPT.cpp:235
     P.doNEE = c->opt.doNEE != 0;
     P.doMS = P.doNEE && c->opt.doMNEE;
     P.doMIS = P.doNEE && c->opt.doMIS;
@@ -114,7 +123,7 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
             P.level = b;
             launchTrace(P, persistentGrid, s);
             c->markKernel(PLTPT_K_TRACE, s);
-            launchSortFlip(P, SortView{P.vertexList + size_t(b) * P.pixelCount, P.levelCount + b}, true, persistentGrid, s);
+            launchSortFlip(P, SortView{P.vertexList + size_t(b) * P.pixelCount, P.levelCount + b, nullptr}, true, persistentGrid, s);
             c->markKernel(PLTPT_K_SORT, s);
             launchShade(P, persistentGrid, s);
             c->markKernel(PLTPT_K_SHADE, s);
@@ -134,9 +143,10 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
                 c->markKernel(PLTPT_K_CONNECT_B, s);
                 c->stats.kernelLaunches += 3;
             }
+            if (P.useEnv) { launchConnectMiss(P, persistentGrid, s); c->markKernel(PLTPT_K_CONNECT_A, s); c->stats.kernelLaunches++; }
             if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_MNEE, s); }
             for (uint32_t it = 0; it <= maxB; ++it) {
-                launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2}, false, persistentGrid, s);
+                launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2, P.sortedAux}, false, persistentGrid, s);
                 c->markKernel(PLTPT_K_SORT, s);
                 launchUnwindStep(P, persistentGrid, s);
                 c->markKernel(PLTPT_K_UNWIND_STEP, s);

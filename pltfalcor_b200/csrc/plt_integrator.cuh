@@ -25,19 +25,23 @@ struct FrameParams {
     uint4* bHit;       // PackedHitInfo
     float4* bDir;      // encodedWi.xy, asfloat(lobe), asfloat(flags)
     float2* bPdf;      // pathContribution, lastNonDeltaPdf
-    // per-vertex shading cache written by the sample stage so that the O(L^2) forward replay never re-fetches geometry:
-    // vc0 = posW.xyz | materialID, vc1 = normalW.xyz | uv.x, vc2 = faceNormalW.xyz | uv.y, vc3 = tangentW
-    float4 *vc0, *vc1, *vc2, *vc3;
+    // per-vertex shading cache written by the sample stage so that the O(L^2) forward replay never re-fetches geometry: one
+    // 64 B record (two full 32 B sectors) per vertex at [(bounce * pixelCount + pixel) * 4]:
+    // [0] = posW.xyz | materialID, [1] = normalW.xyz | uv.x, [2] = faceNormalW.xyz | uv.y, [3] = tangentW
+    float4* vc;
     uint8_t* vMatType;  // MaterialType of every recorded vertex (queue binning key)
-    // connection jobs (one per NEE / emissive light connection): 10 float4 planes [plane][job]
+    // connection jobs (one per NEE / emissive light connection): one 160 B record (five full 32 B sectors) per job, [job][10]
     float4* job;
     uint32_t jobCapacity;
     uint32_t* jobCount;      // [0] allocated jobs, [1] dropped (capacity overflow; must stay 0)
     // replay queues: the step kernel appends surviving job ids (+ the MaterialType of their next vertex) to `pending`, a
     // counting-sort scatter then writes them to `sorted` grouped by type, which is what the next step kernel walks.
     uint32_t* pending;       // [jobCapacity] job ids in completion order
+    uint32_t* pendingAux;    // [jobCapacity] pixel | next vertex index << 26 of the job: the step kernel can fetch the job record and
+                             //               the vertex record at once instead of one after the other
     uint8_t* pendingType;    // [jobCapacity]
     uint32_t* sorted;        // [jobCapacity] job ids grouped by material type
+    uint32_t* sortedAux;     // [jobCapacity]
     uint32_t* queueCount;    // [0..kQueueTypes) per-type counts of `pending`, [kQueueTypes] total, [kQueueTypes+1 ..] scatter cursors,
                              // [2*kQueueTypes+2] number of entries of `sorted`
     uint32_t tileY0, tileRows, outOffset;  // row tile of the frame processed by this launch sequence (work buffers are tile-local)
@@ -69,7 +73,10 @@ struct FrameParams {
     unsigned long long* counters;  // [0] bsdf evals x wavelengths, [1] recorded vertices, [2] traversal stack overflows, [3] mnee iterations,
                                    // [4] sum L(L-1)/2, [5] BVH nodes visited, [6] triangles tested, [7] unwind job steps
     // derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
-    bool useEmissive, useAnalytic, doNEE, doMS, doMIS, perTileSG;
+    bool useEmissive, useAnalytic, useEnv, doNEE, doMS, doMIS, perTileSG;
+    // environment-lit scenes: paths that left the scene, in the order the trace kernels found them (each pixel misses at most once)
+    uint32_t* missList;      // [pixelCount] pixel | vertex index << 26
+    uint32_t* missCount;
 };
 
 constexpr int kQueueTypes = 12;  // MaterialType values 0..11
@@ -102,15 +109,16 @@ PLT_D Bounce readBounce(const FrameParams& P, uint32_t pixel, int p) {
 
 PLT_D void writeVertexCache(const FrameParams& P, uint32_t pixel, int p, const VertexData& v, uint32_t materialID, uint32_t materialType) {
     const size_t o = size_t(p) * P.pixelCount + pixel;
-    P.vc0[o] = mk4(v.posW.x, v.posW.y, v.posW.z, __uint_as_float(materialID));
-    P.vc1[o] = mk4(v.normalW.x, v.normalW.y, v.normalW.z, v.texC.x);
-    P.vc2[o] = mk4(v.faceNormalW.x, v.faceNormalW.y, v.faceNormalW.z, v.texC.y);
-    P.vc3[o] = v.tangentW;
+    float4* r = P.vc + 4 * o;
+    r[0] = mk4(v.posW.x, v.posW.y, v.posW.z, __uint_as_float(materialID));
+    r[1] = mk4(v.normalW.x, v.normalW.y, v.normalW.z, v.texC.x);
+    r[2] = mk4(v.faceNormalW.x, v.faceNormalW.y, v.faceNormalW.z, v.texC.y);
+    r[3] = v.tangentW;
     P.vMatType[o] = uint8_t(materialType);
 }
 PLT_D VertexData readVertexCache(const FrameParams& P, uint32_t pixel, int p, uint32_t& materialID) {
-    const size_t o = size_t(p) * P.pixelCount + pixel;
-    const float4 a = __ldcs(P.vc0 + o), b = __ldcs(P.vc1 + o), c = __ldcs(P.vc2 + o), d = __ldcs(P.vc3 + o);
+    const float4* r = P.vc + 4 * (size_t(p) * P.pixelCount + pixel);
+    const float4 a = r[0], b = r[1], c = r[2], d = r[3];
     VertexData v;
     v.posW = mk3(a.x, a.y, a.z); materialID = __float_as_uint(a.w);
     v.normalW = mk3(b.x, b.y, b.z); v.faceNormalW = mk3(c.x, c.y, c.z);
@@ -251,6 +259,15 @@ PLT_D void raygenPixel(const FrameParams& P, uint32_t pixel) {
     path.length = 0;
     storePath(P, pixel, path);
 }
+// Records a path that left the scene for the solve stage's onMiss (warp-aggregated append).
+PLT_D void appendMiss(const FrameParams& P, uint32_t pixel, uint32_t vertexIndex) {
+    const uint32_t active = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(P.missCount, uint32_t(__popc(active)));
+    base = __shfl_sync(active, base, leader);
+    P.missList[base + __popc(active & ((1u << lane) - 1u))] = pixel | (vertexIndex << 26);
+}
 // TraceRay + scatterMiss (pltpt_sample.rt.slang:55-61,174-183).  Returns the MaterialType of the hit (0 = miss, path ended).
 PLT_D uint32_t tracePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc) {
     const float4 o = P.psOrigin[pixel], d = P.psDir[pixel];
@@ -261,6 +278,7 @@ PLT_D uint32_t tracePath(const FrameParams& P, uint32_t pixel, TraversalCounters
         const uint32_t fl = __float_as_uint(q.w);
         const uint32_t flags = (fl & ~0xff00u) | RF_Miss;
         writeBounce(P, pixel, int((fl >> 8) & 0xffu), make_uint4(0, 0, 0, 0), mk3(-d.x, -d.y, -d.z), 0u, flags, 1.f / (q.x * q.y), q.z);
+        if (P.useEnv) appendMiss(P, pixel, (fl >> 8) & 0xffu);
         return 0u;
     }
     P.psHit[pixel] = make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v));
@@ -281,6 +299,7 @@ PLT_D bool shadePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc
         if (guard >= 4096 || !traceClosestHit(P, tc, path.origin, path.dir, 0.f, kFltMax, th, t)) {
             path.flags |= RF_Miss;
             writeBounce(P, pixel, path.length, make_uint4(0, 0, 0, 0), -path.dir, 0u, path.flags, 1.f / (path.pdf * path.thp), path.lastNonDeltaPdf);
+            if (P.useEnv) appendMiss(P, pixel, uint32_t(path.length));
             return false;
         }
     }
@@ -300,9 +319,9 @@ struct LightSample {
     uint32_t lightType;
 };
 PLT_D bool anyPositive(float4 L, int hwss) { return L.x > 0.f || (hwss > 1 && L.y > 0.f) || (hwss > 2 && L.z > 0.f) || (hwss > 3 && L.w > 0.f); }
-// LightSampling.slangh:40-76 (env maps are not supported: §8f rank 3)
+// LightSampling.slangh:40-76
 PLT_D void lightTypeProbabilities(const FrameParams& P, float p[3]) {
-    p[0] = 0.f; p[1] = P.useEmissive ? 1.f : 0.f; p[2] = P.useAnalytic ? 1.f : 0.f;
+    p[0] = P.useEnv ? 1.f : 0.f; p[1] = P.useEmissive ? 1.f : 0.f; p[2] = P.useAnalytic ? 1.f : 0.f;
     const float sum = p[0] + p[1] + p[2];
     if (sum == 0.f) return;
     const float invSum = 1.f / sum;
@@ -396,6 +415,21 @@ PLT_D float emissiveEvalPdf(const FrameParams& P, float3 posW, uint32_t triangle
     if (cosTheta <= 0.f) return 0.f;
     const float area = __uint_as_float(__ldg(&sc.etris[triangleIndex].area));
     return sel * (distSqr / fmaxf(kFltMin, cosTheta * area));
+}
+// LightSampling.slangh:86-102
+PLT_D bool generateEnvMapSample(const FrameParams& P, const SD& sd, Rng& sg, float wavelength, LightSample& ls) {
+    if (!P.useEnv) return false;
+    EnvSample s;
+    envSample(P.sc.env, sg.next2D(), s);
+    const float4 wl = hwssWavelengths(wavelength, int(P.opt.HWSS));
+    const float4 Le = rgbToSpectrum4(s.Le, wl);
+    const float4 L = s.pdf > 0.f ? Le / s.pdf : mk4(.0f);
+    ls.beam = sourceBeamDistant(-s.dir, P.opt.sourcingMaxBeamOmega, L, wl, P.opt.sourcingMaxBeamOmega, int(P.opt.HWSS));
+    ls.pdf = s.pdf;
+    ls.origin = shadowRayOrigin(sd, s.dir);
+    ls.distance = kFltMax;  // kRayTMax
+    ls.dir = s.dir;
+    return anyPositive(L, int(P.opt.HWSS));
 }
 // LightSampling.slangh:104-126
 PLT_D bool generateEmissiveSample(const FrameParams& P, const SD& sd, Rng& sg, float wavelength, bool importanceSample, LightSample& ls) {
@@ -521,6 +555,7 @@ PLT_D bool generateLightSample(const FrameParams& P, const SD& sd, bool sampleRe
     const bool success = P.perTileSG ? selectLightType(P, lightType, selectionPdf, tilesg) : selectLightType(P, lightType, selectionPdf, sg);
     if (!success) return false;
     bool valid = false;
+    if (P.useEnv && lightType == LT_EnvMap) valid = generateEnvMapSample(P, sd, sg, wavelength, ls);
     if (P.useEmissive && lightType == LT_Emissive) valid = generateEmissiveSample(P, sd, sg, wavelength, importanceSample, ls);
     if (P.useAnalytic && lightType == LT_Analytic) valid = generateAnalyticLightSample(P, sd, sg, wavelength, importanceSample, ls);
     ls.lightType = lightType;
@@ -548,9 +583,11 @@ struct SolveState {
 enum : uint32_t { JOB_Q_MASK = 0xffu, JOB_COMPS_SHIFT = 8, JOB_DISTANT = 1u << 11, JOB_FIRST_IS_CURRENT = 1u << 12, JOB_BOUNCE_SHIFT = 16, JOB_KIND_SHIFT = 24 };
 struct JobHeader { uint32_t pixel, q, bounceIdx, kind; bool firstIsCurrent; float pathContribution; };
 
+PLT_D float4* jobField(const FrameParams& P, uint32_t id, int k) { return P.job + size_t(id) * kJobPlanes + k; }
+PLT_D uint32_t jobAux(uint32_t pixel, uint32_t q) { return pixel | (q << 26); }
 PLT_D void storeJob(const FrameParams& P, uint32_t id, const Beam& b, const JobHeader& h) {
-    float4* J = P.job + id;
-    const size_t st = P.jobCapacity;
+    float4* J = P.job + size_t(id) * kJobPlanes;
+    constexpr size_t st = 1;
     const uint32_t packed = (h.q & JOB_Q_MASK) | (uint32_t(b.comps) << JOB_COMPS_SHIFT) | (b.distant ? JOB_DISTANT : 0u) | (h.firstIsCurrent ? JOB_FIRST_IS_CURRENT : 0u) |
                             (h.bounceIdx << JOB_BOUNCE_SHIFT) | (h.kind << JOB_KIND_SHIFT);
     J[0 * st] = b.L; J[1 * st] = b.L1; J[2 * st] = b.L2; J[3 * st] = b.L3; J[4 * st] = b.wl; J[5 * st] = b.spdf;
@@ -560,8 +597,8 @@ PLT_D void storeJob(const FrameParams& P, uint32_t id, const Beam& b, const JobH
     J[9 * st] = mk4(b.t.z, h.pathContribution, __uint_as_float(h.pixel), __uint_as_float(packed));
 }
 PLT_D void loadJob(const FrameParams& P, uint32_t id, Beam& b, JobHeader& h) {
-    const float4* J = P.job + id;
-    const size_t st = P.jobCapacity;
+    const float4* J = P.job + size_t(id) * kJobPlanes;
+    constexpr size_t st = 1;
     b.L = J[0 * st]; b.L1 = J[1 * st]; b.L2 = J[2 * st]; b.L3 = J[3 * st]; b.wl = J[4 * st]; b.spdf = J[5 * st];
     const float4 c = J[6 * st], d = J[7 * st], e = J[8 * st], f = J[9 * st];
     b.Dxx = c.x; b.Dxy = c.y; b.Dyy = c.z; b.r_m = c.w;
@@ -573,7 +610,8 @@ PLT_D void loadJob(const FrameParams& P, uint32_t id, Beam& b, JobHeader& h) {
 }
 // Appends `id` to the pending list of the next replay iteration (warp-aggregated: one atomic per warp for the slot, one per
 // material type for the histogram).
-PLT_D void enqueueJob(const FrameParams& P, uint32_t type, uint32_t id) {
+template <bool kAux = true>
+PLT_D void enqueueJob(const FrameParams& P, uint32_t type, uint32_t id, uint32_t aux = 0) {
     const uint32_t active = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
     uint32_t base = 0;
@@ -581,6 +619,7 @@ PLT_D void enqueueJob(const FrameParams& P, uint32_t type, uint32_t id) {
     base = __shfl_sync(active, base, leader);
     const uint32_t slot = base + __popc(active & ((1u << lane) - 1u));
     P.pending[slot] = id;
+    if (kAux) P.pendingAux[slot] = aux;
     P.pendingType[slot] = uint8_t(type);
     const uint32_t peers = __match_any_sync(active, type);
     if (lane == __ffs(peers) - 1) atomicAdd(P.queueCount + type, uint32_t(__popc(peers)));
@@ -639,7 +678,7 @@ PLT_D void emitConnection(const FrameParams& P, uint32_t pixel, int bounceIdx, u
     h.pixel = pixel; h.bounceIdx = uint32_t(bounceIdx); h.kind = kind; h.firstIsCurrent = evalCurrentVertex; h.pathContribution = pathContribution;
     h.q = uint32_t(evalCurrentVertex ? bounceIdx : bounceIdx - 1);
     storeJob(P, id, beam, h);
-    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + pixel], id);
+    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + pixel], id, jobAux(pixel, h.q));
 }
 // pltpt_solve.rt.slang:205-217
 PLT_D bool wasNEEAvailable(const FrameParams& P, int bounceIdx, uint32_t flags) {
@@ -666,6 +705,24 @@ PLT_D void evalEmissive(const FrameParams& P, SolveState& st, uint32_t pixel, in
     Beam beam = sourceBeamArea(sd.posW, bounce.wi, P.opt.sourcingAreaFromEmissiveGeometry, dist, Le, wl, P.opt.sourcingMaxBeamOmega, int(P.opt.HWSS));
     if (!P.opt.HWSSDoMIS && (bounce.flags & RF_HasDispersiveDeltaSegment)) beam.comps = 1;
     emitConnection(P, pixel, bounceIdx, 1, false, bounce.pathContribution, beam);
+}
+
+// pltpt_solve.rt.slang:371-396 (onMiss): the environment seen by a path that left the scene at vertex index `p`
+PLT_D void onMiss(const FrameParams& P, uint32_t pixel, int p) {
+    const Bounce bounce = readBounce(P, pixel, p);
+    const float3 wo = bounce.wi;
+    const bool didNEE = wasNEEAvailable(P, p, bounce.flags);
+    if (!(P.useEnv && (P.doMIS || !didNEE))) { writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f)); return; }
+    const bool needMIS = P.doMIS && didNEE;
+    float prob[3];
+    lightTypeProbabilities(P, prob);
+    const float lightPdf = prob[0] * envEvalPdf(P.sc.env, -wo);
+    const float w = needMIS ? misWeight(bounce.lastNonDeltaPdf, lightPdf) : 1.f;
+    const float4 wl = hwssWavelengths(P.psOrigin[pixel].w, int(P.opt.HWSS));  // hero wavelength of the path
+    const float4 Le = rgbToSpectrum4(envEval(P.sc.env, -wo), wl) * w;
+    Beam beam = sourceBeamDistant(wo, P.opt.sourcingMaxBeamOmega, Le, wl, P.opt.sourcingMaxBeamOmega, int(P.opt.HWSS));
+    if (!P.opt.HWSSDoMIS && (bounce.flags & RF_HasDispersiveDeltaSegment)) beam.comps = 1;
+    emitConnection(P, pixel, p, 1, false, bounce.pathContribution, beam);
 }
 
 // ---- MNEE (Manifolds.slangh) ------------------------------------------------------------------------------------
@@ -870,7 +927,7 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
     h.firstIsCurrent = !currentVertexMS;
     h.q = h.firstIsCurrent ? it.bounceIdx : it.bounceIdx - 1u;
     storeJob(P, it.jobId, beam, h);
-    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + it.pixel], it.jobId);
+    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + it.pixel], it.jobId, jobAux(it.pixel, h.q));
 }
 
 // ---- connect wavefront: A (light sampling) -> shadow-ray trace kernel -> B (visibility, MIS, emit) per vertex index ------------
@@ -894,7 +951,7 @@ PLT_D void connectSetup(const FrameParams& P, uint32_t pixel, int p, bool freshR
     c.st.tc.nodes = c.st.tc.tris = 0;
     c.v = readVertexCache(P, pixel, p, c.materialID);
     if (p == 0) c.st.pathOrigin = P.camPos;
-    else { const float4 prev = P.vc0[size_t(p - 1) * P.pixelCount + pixel]; c.st.pathOrigin = mk3(prev.x, prev.y, prev.z); }
+    else { const float4 prev = P.vc[4 * (size_t(p - 1) * P.pixelCount + pixel)]; c.st.pathOrigin = mk3(prev.x, prev.y, prev.z); }
     if (freshRng) {  // pltpt_solve.rt.slang:410-415
         c.st.sg = Rng::seed(px, py, P.frameCount);
         c.st.wavelength = sampleHeroWavelength(c.st.sg.next1D());
@@ -998,12 +1055,12 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
     if (flags & CI_ANY_HIT) {
         if (!blocked) {
             connected = true;
-            if (flags & CI_DO_MIS) misScale = misWeight(lsPdf, bsdfPdf(c.m, c.sd, lsDir, P.job[size_t(4) * P.jobCapacity + jobId].x));
+            if (flags & CI_DO_MIS) misScale = misWeight(lsPdf, bsdfPdf(c.m, c.sd, lsDir, jobField(P, jobId, 4)->x));
         }
     } else {
         ManifoldSampleData ms;
         ms.hitCount = 0; ms.iterations = 0; ms.pdf = __uint_as_float(item.info.z); ms.dispersive = (flags & CI_DISPERSIVE) != 0; ms.woLastHitToLight = mk3(0.f);
-        const float heroWl = P.job[size_t(4) * P.jobCapacity + jobId].x;  // beam.wl.x
+        const float heroWl = jobField(P, jobId, 4)->x;  // beam.wl.x
         ms.wavelength = heroWl;
         const bool currentVertexMS = (flags & CI_CURRENT_MS) != 0;
         if (currentVertexMS) { ms.hits[0].hit = c.bounce.hit; ms.hits[0].posW = c.sd.posW; ms.hits[0].lobe = item.info.w; ms.hitCount = 1; }
@@ -1028,12 +1085,12 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                         it.hit[i] = i < ms.hitCount ? ms.hits[i].hit : make_uint4(0, 0, 0, 0);
                         it.posLobe[i] = i < ms.hitCount ? mk4(ms.hits[i].posW.x, ms.hits[i].posW.y, ms.hits[i].posW.z, __uint_as_float(ms.hits[i].lobe)) : mk4(0.f);
                     }
-                    const float4 bp = P.job[size_t(7) * P.jobCapacity + jobId];  // beam.posW
+                    const float4 bp = *jobField(P, jobId, 7);  // beam.posW
                     it.originPdf = mk4(origin.x, origin.y, origin.z, ms.pdf);
                     it.lightPosWl = mk4(bp.x, bp.y, bp.z, heroWl);
                     it.lightDirLsPdf = mk4(lsDir.x, lsDir.y, lsDir.z, lsPdf);
                     it.pixel = pixel; it.bounceIdx = uint32_t(p); it.jobId = jobId;
-                    const bool distant = (__float_as_uint(P.job[size_t(9) * P.jobCapacity + jobId].w) & JOB_DISTANT) != 0;
+                    const bool distant = (__float_as_uint(jobField(P, jobId, 9)->w) & JOB_DISTANT) != 0;
                     it.flags = uint32_t(ms.hitCount) | (ms.dispersive ? MI_DISPERSIVE : 0u) | (distant ? MI_DISTANT : 0u) | (currentVertexMS ? MI_CURRENT_VERTEX_MS : 0u) | ((flags & CI_DO_MIS) ? MI_DO_MIS : 0u);
                 }
             }
@@ -1050,9 +1107,9 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
     }
     if (connected) {
         if (flags & CI_DO_MIS) {  // beam.scale(w) on the parked beam
-            for (int k = 0; k < 4; ++k) { float4* q = P.job + size_t(k) * P.jobCapacity + jobId; *q = *q * misScale; }
+            for (int k = 0; k < 4; ++k) { float4* q = jobField(P, jobId, k); *q = *q * misScale; }
         }
-        enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId);
+        enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId, jobAux(pixel, uint32_t(p)));
     } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
     connectTail(P, pixel, p, c);
     evals += c.st.evals;
@@ -1061,14 +1118,16 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
 
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head).
 // Returns true while the job has further vertices to go through.
-PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t& evals, uint32_t& nextType) {
+PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
+    // the queue entry names the vertex: the job record, the vertex record and the bounce direction are independent loads
+    const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
+    uint32_t materialID;
+    const VertexData v = readVertexCache(P, pixel, int(q), materialID);
+    const float4 d = P.bDir[size_t(q) * P.pixelCount + pixel];
     Beam beam;
     JobHeader h;
     loadJob(P, id, beam, h);
-    uint32_t materialID;
-    const VertexData v = readVertexCache(P, h.pixel, int(h.q), materialID);
     const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-    const float4 d = __ldcs(P.bDir + size_t(h.q) * P.pixelCount + h.pixel);
     const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
     forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);
@@ -1077,8 +1136,9 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t& evals, uint32
         return false;
     }
     h.q -= 1; h.firstIsCurrent = false;
-    storeJob(P, id, beam, h);
     nextType = P.vMatType[size_t(h.q) * P.pixelCount + h.pixel];
+    nextAux = jobAux(h.pixel, h.q);
+    storeJob(P, id, beam, h);
     return true;
 }
 
@@ -1087,7 +1147,10 @@ PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
     float3 L = mk3(0.f);
     for (int p = 0; p <= int(P.opt.maxBounces); ++p) {
         const uint32_t flags = __float_as_uint(P.bDir[size_t(p) * P.pixelCount + pixel].w);
-        if (flags & RF_Miss) break;
+        if (flags & RF_Miss) {
+            if (P.useEnv) { const float4 e = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel); L += mk3(e.x, e.y, e.z); }
+            break;
+        }
         const float4 a = __ldcs(P.contrib + size_t(2 * p) * P.pixelCount + pixel), b = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel);
         L += mk3(a.x, a.y, a.z);
         L += mk3(b.x, b.y, b.z);
@@ -1118,13 +1181,14 @@ PLT_D void warpAdd(unsigned long long* dst, uint32_t v) {  // all 32 lanes must 
 
 // Counting-sort view: `pending`/`pendingType`/`hist` are filled by a producer kernel; k_sort_queue scatters the ids into
 // `dst` grouped by type and k_flip_queue publishes the count in *dstCount and clears the histogram (stage_unwind.cu).
-struct SortView { uint32_t* dst; uint32_t* dstCount; };
+struct SortView { uint32_t* dst; uint32_t* dstCount; uint32_t* dstAux; };  // dstAux: null when the producer wrote no aux words
 
 // stage launchers (stage_sample.cu, stage_connect.cu, stage_unwind.cu)
 void launchRaygen(const FrameParams& P, cudaStream_t s);
 void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s);

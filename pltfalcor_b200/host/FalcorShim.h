@@ -226,7 +226,7 @@ class Scene {
 public:
     using SharedPtr = std::shared_ptr<Scene>;
     enum class UpdateFlags : uint32_t { None = 0 };
-    Scene(const PltptSceneDesc& d, bool hasEnvMap = false) : mDesc(d), mpCamera(std::make_shared<Camera>()), mHasEnvMap(hasEnvMap) {}
+    Scene(const PltptSceneDesc& d) : mDesc(d), mpCamera(std::make_shared<Camera>()), mHasEnvMap(d.envMapTexels != nullptr) {}
     const PltptSceneDesc& getPltptSceneDesc() const { return mDesc; }
     const Camera::SharedPtr& getCamera() const { return mpCamera; }
     bool useEmissiveLights() const { return mDesc.emissiveTriangleCount > 0; }  // Scene.h: render settings && light collection non-empty

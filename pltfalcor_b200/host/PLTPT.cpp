@@ -162,11 +162,6 @@ void PLTPT::execute(RenderContext* pRenderContext, const RenderData& renderData)
     }
     if (!mSceneUploaded) uploadScene();
 
-    if (mOptions.useEnvLights && mpScene->useEnvLight()) {
-        static bool warned = false;
-        if (!warned) logWarning("PLTPT (CUDA): environment-map lighting is not implemented yet; the env map is ignored.");
-        warned = true;
-    }
     const bool useDOF = mpScene->getCamera()->getApertureRadius() > 0.f;  // PLTPT.cpp:419-423
     if (useDOF && renderData[kInputViewDir] == nullptr) logWarning(std::string("Depth-of-field requires the '") + kInputViewDir + "' input. Expect incorrect shading.");
 

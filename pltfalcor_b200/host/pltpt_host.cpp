@@ -67,6 +67,15 @@ bool loadScene(const std::string& path, SceneFile& s) {
     d.invWeightsSum = fw[0];
     d.hitInfoTypeBits = uint32_t(sc[10]); d.hitInfoInstanceIDBits = uint32_t(sc[11]); d.hitInfoPrimitiveIndexBits = uint32_t(sc[12]);
     d.pointersAreDevice = 0;
+    // optional trailing section: uint64 texel bytes, then width, height (uint32), EnvMapData (112 B), RGBA32F texels
+    uint64_t envBytes = 0;
+    if (readExact(f, &envBytes, 8) && envBytes) {
+        uint32_t wh[2];
+        s.blobs.emplace_back(envBytes);
+        if (!readExact(f, wh, sizeof wh) || !readExact(f, &d.envMap, sizeof d.envMap) || !readExact(f, s.blobs.back().data(), envBytes)) return false;
+        d.envMapTexels = reinterpret_cast<const float*>(s.blobs.back().data());
+        d.envMapWidth = wh[0]; d.envMapHeight = wh[1];
+    }
     return true;
 }
 

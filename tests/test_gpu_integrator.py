@@ -13,10 +13,12 @@ def _scene(name):
     from pltfalcor_b200 import scene
     return {"cornell": scene.cornell_box, "grating_sphere": scene.grating_sphere_scene, "layered": scene.layered_stress_scene,
             # BASELINE config 5 generator at a size the brute-force oracle finishes in seconds (instanced spheres, all ten PLT materials)
-            "city": lambda: scene.city_scene(40_000)}[name]()
+            "city": lambda: scene.city_scene(40_000),
+            # environment-lit scene: EnvMapSampler NEE + onMiss, mixed with an emissive quad
+            "env": scene.env_scene}[name]()
 
 
-@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered", "city"])
+@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered", "city", "env"])
 def loaded(request, torch_cuda, oracle):
     from pltfalcor_b200 import binding
     buffers, cam = _scene(request.param)
@@ -92,6 +94,31 @@ def test_option_variants_match_oracle(torch_cuda, oracle, opts):
     m = parity.compare_color(gpu["color"], cpu["color"], same)
     assert same.mean() >= 0.97, (opts, same.mean())
     assert m["frac_pixels_within_1e-2"] >= 0.97 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    p.close()
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(useEnvLights=False), dict(useEmissiveLights=False), dict(doMIS=False), dict(doNEE=False), dict(doMNEE=False), dict(HWSSDoMIS=False)])
+def test_env_lit_option_variants_match_oracle(torch_cuda, oracle, opts):
+    """Environment lighting (LightSampling.slangh:86-102, pltpt_solve.rt.slang:371-396) under the options that change how it is mixed."""
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.env_scene()
+    kw = dict(maxBounces=6)
+    kw.update(opts)
+    p = binding.Pltpt(**kw)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    w, h, frame = 64, 36, 3
+    c = scene.with_jitter(cam, frame, w, h)
+    gpu_b = p.sample_stage_host(c, frame, w, h)
+    gpu = p.render_frame_host(c, frame, w, h)
+    cpu = osc.render_frame(p.options, c, frame, w, h, want_bounces=True)
+    _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
+    m = parity.compare_color(gpu["color"], cpu["color"], same)
+    assert same.mean() >= 0.97, (opts, same.mean())
+    assert m["nonfinite_gpu"] == 0
+    assert m["frac_pixels_within_1e-2"] >= 0.97 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    if opts.get("useEnvLights", True):  # sky pixels see the map directly: they must not be black
+        assert (gpu["color"][:4, :, :3].sum(-1) > 0).mean() > 0.9
     p.close()
 
 

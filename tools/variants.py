@@ -18,11 +18,11 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
-    "u3": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=3"]},
+    "a5": {"stage_connect.cu": ["-DPLT_MINB_CONNECT_A=5"]},
+    "t6": {"stage_sample.cu": ["-DPLT_MINB_TRACE=6"], "stage_connect.cu": ["-DPLT_MINB_SHADOW_TRACE=6"]},
+    "s5": {"stage_sample.cu": ["-DPLT_MINB_SHADE=5"]},
+    "c5": {"stage_connect.cu": ["-DPLT_MINB_CONNECT_B=5"]},
     "u4": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=4"]},
-    "u3fm": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=3", "-fmad=true"]},
-    "s4": {"stage_sample.cu": ["-DPLT_MINB_SHADE=4"]},
-    "s4c4": {"stage_sample.cu": ["-DPLT_MINB_SHADE=4"], "stage_connect.cu": ["-DPLT_MINB_CONNECT_B=4"]},
 }
 
 
