@@ -328,6 +328,12 @@ PLTPT_API int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32
                                       const PltptCameraData* camera, uint32_t width, uint32_t height,
                                       double* accum, void* stream);
 
+/* Frames pltpt_render_accumulate keeps in flight (ours; frames are independent, pltpt_sample.rt.slang:154): 0 = the default
+ * (every lane the library was built with, each a CUDA stream with private work buffers), 1 = strictly sequential on the
+ * caller's stream, n = n frames.
+ * The sum is the same set of frames either way; only the fp64 summation order differs. */
+PLTPT_API int pltpt_set_frame_overlap(PltptHandle h, int frames);
+
 /* Host-buffer convenience used by the Falcor shell when no shared CUDA surface exists:
  * renders one frame and copies RGBA32F results to host memory (any of the three may be NULL). */
 PLTPT_API int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,

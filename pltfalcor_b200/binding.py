@@ -15,7 +15,7 @@ EXPORTS = [
     "pltpt_default_options", "pltpt_create", "pltpt_destroy", "pltpt_last_error", "pltpt_version", "pltpt_set_options", "pltpt_set_scene",
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
-    "pltpt_envmap_eval", "pltpt_envmap_sample",
+    "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
 ]
 
 
@@ -51,6 +51,7 @@ def lib():
         _lib.pltpt_get_stats.argtypes = [vp, vp]
         _lib.pltpt_reset_stats.argtypes = [vp]
         _lib.pltpt_set_profiling.argtypes = [vp, C.c_int]
+        _lib.pltpt_set_frame_overlap.argtypes = [vp, C.c_int]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
     return _lib
@@ -114,6 +115,10 @@ class Pltpt:
     def set_profiling(self, enable):
         """Per-kernel device timers (one CUDA event per launch) on/off."""
         _check(lib().pltpt_set_profiling(self.h, 1 if enable else 0))
+
+    def set_frame_overlap(self, frames):
+        """Frames render_accumulate keeps in flight: 2 (default) or 1."""
+        _check(lib().pltpt_set_frame_overlap(self.h, int(frames)))
 
     def reset_stats(self):
         _check(lib().pltpt_reset_stats(self.h))

@@ -60,7 +60,12 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     if (!h) return PLTPT_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto e : h->timerEvents) cudaEventDestroy(e);
+    for (auto& ln : h->lanes) {
+        for (auto e : ln.timerEvents) cudaEventDestroy(e);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    if (h->evFork) cudaEventDestroy(h->evFork);
     for (auto e : h->kernelEvents) cudaEventDestroy(e);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
@@ -77,6 +82,13 @@ extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
     if (!h || !out) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (int r = syncFrameStats(h)) return r;
     *out = h->stats;
+    return PLTPT_OK;
+}
+/* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 or 2 = two (default). */
+extern "C" int pltpt_set_frame_overlap(PltptHandle h, int frames) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (frames < 0 || frames > PltptContext::kLanes) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame overlap out of range (0 = default, 1 .. lanes built in)");
+    h->frameOverlap = frames == 0 ? PltptContext::kLanes : frames;
     return PLTPT_OK;
 }
 extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {
@@ -587,15 +599,38 @@ static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, ui
 extern "C" int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* color, float* albedo, float* normal, void* stream) {
     if (int r = checkRender(h, cam, w, hgt)) return r;
     if (!color) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
-    return renderFrame(h, frameCount, cam, w, hgt, color, albedo, normal, nullptr, true, (cudaStream_t)stream);
+    return renderFrame(h, 0, frameCount, cam, w, hgt, color, albedo, normal, nullptr, true, (cudaStream_t)stream);
 }
+namespace {
+__global__ void __launch_bounds__(256) k_accum_add(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+}  // namespace
 extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
                                        double* accum, void* stream) {
     if (int r = checkRender(h, cam, w, hgt)) return r;
     if (!accum) return fail(PLTPT_ERR_INVALID_ARGUMENT, "accum output is null");
     if (frameStep == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep must be > 0");
+    cudaStream_t user = (cudaStream_t)stream;
+    // Two frames in flight (context.h "Frame lanes") unless per-kernel timers are on (they need one stream) or there is one frame.
+    const int lanes = h->profiling ? 1 : int(std::min<uint32_t>(frameCount, uint32_t(h->frameOverlap)));
+    const size_t accumBytes = size_t(w) * hgt * 4 * sizeof(double);
+    if (lanes > 1) {
+        if (!h->evFork) PLT_CUDA(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+        PLT_CUDA(cudaEventRecord(h->evFork, user));
+        for (int l = 1; l < lanes; ++l) {
+            PltptContext::Lane& ln = h->lanes[l];
+            if (!ln.stream) PLT_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+            if (!ln.done) PLT_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+            PLT_CUDA(ln.accum.ensure(accumBytes));
+            PLT_CUDA(cudaStreamWaitEvent(ln.stream, h->evFork, 0));
+            PLT_CUDA(cudaMemsetAsync(ln.accum.p, 0, accumBytes, ln.stream));
+        }
+    }
     for (uint32_t i = 0; i < frameCount; ++i) {
         const uint32_t f = firstFrame + i * frameStep;
+        const int l = int(i % uint32_t(lanes));
         PltptCameraData c = *cam;
         // GBufferRT Halton-16 jitter (HaltonSamplePattern.cpp:37-67, GBufferBase.cpp:212-228)
         auto halton = [](uint32_t index, uint32_t base) { float result = 0.f, factor = 1.f; for (; index > 0; index /= base) { factor /= base; result += factor * (index % base); } return result; };
@@ -603,8 +638,17 @@ extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint3
         float jx = halton(k, 2) + 0.5f, jy = halton(k, 3) + 0.5f;
         jx = (jx - std::floor(jx)) - 0.5f; jy = (jy - std::floor(jy)) - 0.5f;
         c.jitterX = jx / float(w); c.jitterY = jy / float(hgt);
-        if (int r = renderFrame(h, f, &c, w, hgt, nullptr, nullptr, nullptr, accum, true, (cudaStream_t)stream)) return r;
+        if (int r = renderFrame(h, l, f, &c, w, hgt, nullptr, nullptr, nullptr, l == 0 ? accum : h->lanes[l].accum.as<double>(), true, l == 0 ? user : h->lanes[l].stream)) return r;
     }
+    for (int l = 1; l < lanes; ++l) {  // join: the caller's stream waits for the lane, then folds the lane's sums into `accum`
+        PltptContext::Lane& ln = h->lanes[l];
+        PLT_CUDA(cudaEventRecord(ln.done, ln.stream));
+        PLT_CUDA(cudaStreamWaitEvent(user, ln.done, 0));
+        const size_t n = size_t(w) * hgt * 4;
+        k_accum_add<<<uint32_t((n + 255) / 256), 256, 0, user>>>(accum, ln.accum.as<double>(), n);
+        h->stats.kernelLaunches++;
+    }
+    PLT_CUDA(cudaGetLastError());
     return PLTPT_OK;
 }
 extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* colorHost, float* albedoHost, float* normalHost) {
@@ -613,7 +657,7 @@ extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const
     PLT_CUDA(h->outColor.ensure(bytes));
     PLT_CUDA(h->outAlbedo.ensure(bytes));
     PLT_CUDA(h->outNormal.ensure(bytes));
-    if (int r = renderFrame(h, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0)) return r;
+    if (int r = renderFrame(h, 0, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0)) return r;
     if (colorHost) PLT_CUDA(cudaMemcpy(colorHost, h->outColor.p, bytes, cudaMemcpyDeviceToHost));
     if (albedoHost) PLT_CUDA(cudaMemcpy(albedoHost, h->outAlbedo.p, bytes, cudaMemcpyDeviceToHost));
     if (normalHost) PLT_CUDA(cudaMemcpy(normalHost, h->outNormal.p, bytes, cudaMemcpyDeviceToHost));

@@ -323,8 +323,8 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
     k_morton<<<blocksFor(n, 256), 256, 0, s>>>(n, triLo.as<float4>(), triHi.as<float4>(), miscU, keysIn, valsIn);
     size_t tempBytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keysIn, keysOut, valsIn, valsOut, int(n), 0, 63, s);
-    PLT_CUDA(c->work[24].ensure(tempBytes));
-    PLT_CUDA(cub::DeviceRadixSort::SortPairs(c->work[24].p, tempBytes, keysIn, keysOut, valsIn, valsOut, int(n), 0, 63, s));
+    PLT_CUDA(c->lanes[0].work[24].ensure(tempBytes));
+    PLT_CUDA(cub::DeviceRadixSort::SortPairs(c->lanes[0].work[24].p, tempBytes, keysIn, keysOut, valsIn, valsOut, int(n), 0, 63, s));
     c->stats.kernelLaunches += 2;
 
     uint32_t* left = tree.as<uint32_t>();

@@ -70,6 +70,9 @@ struct DevBuf {
 
 }  // namespace plt
 
+#ifndef PLT_LANES
+#define PLT_LANES 2
+#endif
 struct PltptContext {
     int device = 0;
     PltptOptions opt{};
@@ -84,16 +87,25 @@ struct PltptContext {
     std::vector<PltptMeshDesc> hMeshes;
     std::vector<uint32_t> hInstTriOffset;
     uint32_t emissiveTriangleCount = 0, lightCount = 0;
-    // per-frame work buffers (integrator.cu)
-    plt::DevBuf work[32];
-    uint32_t workW = 0, workH = 0, workBounces = 0;
+    // Frame lanes: frames are independent (every random number derives from (pixel, frameCount), pltpt_sample.rt.slang:154), so
+    // pltpt_render_accumulate keeps two frames in flight on two streams, each with its own work buffers, counters and timers: the
+    // under-filled late bounces of one frame overlap the wide early bounces of the other.  Lane 0 runs on the caller's stream.
+    static constexpr uint32_t kTimerRing = 256;
+    static constexpr int kLanes = PLT_LANES;
+    struct Lane {
+        plt::DevBuf work[32];                  // per-frame work buffers (integrator.cu)
+        plt::DevBuf accum;                     // lane-private RGBA64F sums (lanes >= 1), merged into the caller's buffer at the end
+        cudaStream_t stream = nullptr;         // own non-blocking stream (lanes >= 1)
+        cudaEvent_t done = nullptr;
+        bool statsDirty = false;
+        std::vector<cudaEvent_t> timerEvents;  // kTimerRing x {start, after sample stage, after solve stage}
+        uint32_t timerCount = 0;
+        cudaStream_t timerStream = nullptr;
+    } lanes[kLanes];
+    cudaEvent_t evFork = nullptr;
+    int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};
-    bool statsDirty = false;
-    static constexpr uint32_t kTimerRing = 256;
-    std::vector<cudaEvent_t> timerEvents;  // kTimerRing x {start, after sample stage, after solve stage}
-    uint32_t timerCount = 0;
-    cudaStream_t timerStream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
     // per-kernel timers (pltpt_set_profiling): event after every launch, tagged with the kernel class that precedes it (0xff = frame start)
     bool profiling = false;
@@ -118,7 +130,7 @@ int buildBvh(PltptContext* c, cudaStream_t s);
 int traceClosest(PltptContext* c, uint32_t n, const float* rays, uint32_t* hits, float* hitT, cudaStream_t s);
 int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded, cudaStream_t s);
 // integrator.cu
-int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
+int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
                 double* accum, bool solve, cudaStream_t s);
 int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host);
 int syncFrameStats(PltptContext* c);

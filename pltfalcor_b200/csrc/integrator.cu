@@ -14,7 +14,7 @@ size_t workBytesPerPixel(uint32_t records) {
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
 
-static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, uint32_t& tileRows) {
+static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, uint32_t& tileRows) {
     P.sc = c->scene;
     P.opt = c->opt;
     P.camPos = mk3(cam->posW[0], cam->posW[1], cam->posW[2]);
@@ -33,61 +33,60 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
     const size_t records = size_t(recordsPerPixel) * tilePixels;
     const size_t jobCapacity = 2 * records;
     if (jobCapacity >= (size_t(1) << 32)) { setError("tile too large for 32-bit job ids"); return PLTPT_ERR_INVALID_ARGUMENT; }
-    PLT_CUDA(c->work[0].ensure(records * sizeof(uint4)));
-    PLT_CUDA(c->work[1].ensure(records * sizeof(float4)));
-    PLT_CUDA(c->work[2].ensure(records * sizeof(float2)));
-    PLT_CUDA(c->work[3].ensure(16 * sizeof(unsigned long long)));
-    PLT_CUDA(c->work[5].ensure(records * 4 * sizeof(float4)));
-    PLT_CUDA(c->work[9].ensure(records));
-    PLT_CUDA(c->work[10].ensure(jobCapacity * kJobPlanes * sizeof(float4)));
-    PLT_CUDA(c->work[11].ensure(jobCapacity * 4));
-    PLT_CUDA(c->work[12].ensure(jobCapacity));
-    PLT_CUDA(c->work[13].ensure(jobCapacity * 4));
-    PLT_CUDA(c->work[6].ensure(jobCapacity * 4));
-    PLT_CUDA(c->work[7].ensure(jobCapacity * 4));
-    PLT_CUDA(c->work[14].ensure(256 * 4));
-    PLT_CUDA(c->work[15].ensure(jobCapacity * sizeof(float4)));  // contrib: 2 * records float4
-    for (int k = 0; k < 7; ++k) PLT_CUDA(c->work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
-    PLT_CUDA(c->work[4].ensure(size_t(tilePixels) * 4));                                    // trace queue
-    PLT_CUDA(c->work[23].ensure(records * 4));                                               // per-bounce type-sorted hit lists
-    PLT_CUDA(c->work[26].ensure(size_t(2) * tilePixels * sizeof(MneeItem)));                 // parked manifold walks
-    PLT_CUDA(c->work[27].ensure(size_t(tilePixels) * sizeof(ConnItem)));
-    PLT_CUDA(c->work[28].ensure(size_t(tilePixels) * 32));
-    PLT_CUDA(c->work[29].ensure(size_t(tilePixels) * 16));
-    PLT_CUDA(c->work[30].ensure(size_t(tilePixels) * 4));
-    P.bHit = c->work[0].as<uint4>();
-    P.bDir = c->work[1].as<float4>();
-    P.bPdf = c->work[2].as<float2>();
-    P.counters = c->work[3].as<unsigned long long>();
-    P.vc = c->work[5].as<float4>();
-    P.vMatType = c->work[9].as<uint8_t>();
-    P.job = c->work[10].as<float4>();
+    PLT_CUDA(ln.work[0].ensure(records * sizeof(uint4)));
+    PLT_CUDA(ln.work[1].ensure(records * sizeof(float4)));
+    PLT_CUDA(ln.work[2].ensure(records * sizeof(float2)));
+    PLT_CUDA(ln.work[3].ensure(16 * sizeof(unsigned long long)));
+    PLT_CUDA(ln.work[5].ensure(records * 4 * sizeof(float4)));
+    PLT_CUDA(ln.work[9].ensure(records));
+    PLT_CUDA(ln.work[10].ensure(jobCapacity * kJobPlanes * sizeof(float4)));
+    PLT_CUDA(ln.work[11].ensure(jobCapacity * 4));
+    PLT_CUDA(ln.work[12].ensure(jobCapacity));
+    PLT_CUDA(ln.work[13].ensure(jobCapacity * 4));
+    PLT_CUDA(ln.work[6].ensure(jobCapacity * 4));
+    PLT_CUDA(ln.work[7].ensure(jobCapacity * 4));
+    PLT_CUDA(ln.work[14].ensure(256 * 4));
+    PLT_CUDA(ln.work[15].ensure(jobCapacity * sizeof(float4)));  // contrib: 2 * records float4
+    for (int k = 0; k < 7; ++k) PLT_CUDA(ln.work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
+    PLT_CUDA(ln.work[4].ensure(size_t(tilePixels) * 4));                                    // trace queue
+    PLT_CUDA(ln.work[23].ensure(records * 4));                                               // per-bounce type-sorted hit lists
+    PLT_CUDA(ln.work[26].ensure(size_t(2) * tilePixels * sizeof(MneeItem)));                 // parked manifold walks
+    PLT_CUDA(ln.work[27].ensure(size_t(tilePixels) * sizeof(ConnItem)));
+    PLT_CUDA(ln.work[28].ensure(size_t(tilePixels) * 32));
+    PLT_CUDA(ln.work[29].ensure(size_t(tilePixels) * 16));
+    PLT_CUDA(ln.work[30].ensure(size_t(tilePixels) * 4));
+    P.bHit = ln.work[0].as<uint4>();
+    P.bDir = ln.work[1].as<float4>();
+    P.bPdf = ln.work[2].as<float2>();
+    P.counters = ln.work[3].as<unsigned long long>();
+    P.vc = ln.work[5].as<float4>();
+    P.vMatType = ln.work[9].as<uint8_t>();
+    P.job = ln.work[10].as<float4>();
     P.jobCapacity = uint32_t(jobCapacity);
-    P.pending = c->work[11].as<uint32_t>();
-    P.pendingType = c->work[12].as<uint8_t>();
-    P.sorted = c->work[13].as<uint32_t>();
-    P.pendingAux = c->work[6].as<uint32_t>();
-    P.sortedAux = c->work[7].as<uint32_t>();
-    P.queueCount = c->work[14].as<uint32_t>();
+    P.pending = ln.work[11].as<uint32_t>();
+    P.pendingType = ln.work[12].as<uint8_t>();
+    P.sorted = ln.work[13].as<uint32_t>();
+    P.pendingAux = ln.work[6].as<uint32_t>();
+    P.sortedAux = ln.work[7].as<uint32_t>();
+    P.queueCount = ln.work[14].as<uint32_t>();
     P.jobCount = P.queueCount + 32;
-    P.contrib = c->work[15].as<float4>();
-    P.psRng = c->work[16].as<uint4>(); P.psOrigin = c->work[17].as<float4>(); P.psDir = c->work[18].as<float4>(); P.psPdf = c->work[19].as<float4>();
-    P.psHit = c->work[20].as<uint4>(); P.ssRng = c->work[21].as<uint4>(); P.ssTileRng = c->work[22].as<uint4>();
-    P.traceQueue = c->work[4].as<uint32_t>();
-    P.vertexList = c->work[23].as<uint32_t>();
+    P.contrib = ln.work[15].as<float4>();
+    P.psRng = ln.work[16].as<uint4>(); P.psOrigin = ln.work[17].as<float4>(); P.psDir = ln.work[18].as<float4>(); P.psPdf = ln.work[19].as<float4>();
+    P.psHit = ln.work[20].as<uint4>(); P.ssRng = ln.work[21].as<uint4>(); P.ssTileRng = ln.work[22].as<uint4>();
+    P.traceQueue = ln.work[4].as<uint32_t>();
+    P.vertexList = ln.work[23].as<uint32_t>();
     P.levelCount = P.queueCount + 64;
-    P.mneeItems = c->work[26].as<MneeItem>();
+    P.mneeItems = ln.work[26].as<MneeItem>();
     P.mneeCount = P.queueCount + 34;
     P.mneeCapacity = 2 * tilePixels;
-    PLT_CUDA(c->work[24].ensure(size_t(tilePixels) * 4));
-    P.missList = c->work[24].as<uint32_t>();
+    PLT_CUDA(ln.work[24].ensure(size_t(tilePixels) * 4));
+    P.missList = ln.work[24].as<uint32_t>();
     P.missCount = P.queueCount + 36;
     if (tilePixels >= (1u << 26)) { setError("tile too large for the packed miss list"); return PLTPT_ERR_INVALID_ARGUMENT; }
-    P.connItems = c->work[27].as<ConnItem>();
-    P.shadowRays = c->work[28].as<float4>();
-    P.shadowHits = c->work[29].as<uint4>();
-    P.shadowT = c->work[30].as<float>();
-    c->workW = w; c->workH = h; c->workBounces = recordsPerPixel;
+    P.connItems = ln.work[27].as<ConnItem>();
+    P.shadowRays = ln.work[28].as<float4>();
+    P.shadowHits = ln.work[29].as<uint4>();
+    P.shadowT = ln.work[30].as<float>();
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
     P.useEnv = c->opt.useEnvLights && c->scene.env.texels != nullptr;  // PLTPT.cpp:235
@@ -99,7 +98,7 @@ static int fillParams(PltptContext* c, FrameParams& P, uint32_t frameCount, cons
 }
 
 // One frame = one sample per pixel.  `bouncesOut` (device, optional) receives the reference-layout bounce records.
-static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool solve, PltptBounce* bouncesOut, cudaStream_t s) {
+static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, uint32_t tileRows, bool solve, PltptBounce* bouncesOut, cudaStream_t s) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const uint32_t persistentGrid = uint32_t(sms) * 8;
@@ -108,7 +107,7 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
         P.tileRows = std::min(tileRows, P.height - y0);
         P.outOffset = y0 * P.width;
         P.pixelCount = P.tileRows * P.width;
-        cudaEvent_t* ev = &c->timerEvents[3 * c->timerCount];
+        cudaEvent_t* ev = &ln.timerEvents[3 * ln.timerCount];
         const bool timed = y0 == 0;  // stage timers cover the first tile of a frame (the only one unless the frame is tiled)
         const uint32_t maxB = c->opt.maxBounces;
         if (maxB > 63) { setError("maxBounces > 63 is not supported by the wavefront queues"); return PLTPT_ERR_INVALID_ARGUMENT; }
@@ -162,12 +161,21 @@ static int renderTiles(PltptContext* c, FrameParams& P, uint32_t tileRows, bool 
     return PLTPT_OK;
 }
 
-int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, double* accum,
+static int ensureTimers(PltptContext::Lane& ln) {
+    if (ln.timerEvents.empty()) {
+        ln.timerEvents.resize(3 * PltptContext::kTimerRing);
+        for (auto& e : ln.timerEvents) PLT_CUDA(cudaEventCreate(&e));
+    }
+    return PLTPT_OK;
+}
+
+int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, double* accum,
                 bool solve, cudaStream_t s) {
+    PltptContext::Lane& ln = c->lanes[lane];
     FrameParams P{};
-    const bool fresh = c->work[3].p == nullptr;
+    const bool fresh = ln.work[3].p == nullptr;
     uint32_t tileRows = 0;
-    if (int r = fillParams(c, P, frameCount, cam, w, h, tileRows)) return r;
+    if (int r = fillParams(c, ln, P, frameCount, cam, w, h, tileRows)) return r;
     P.color = reinterpret_cast<float4*>(color);
     P.albedo = reinterpret_cast<float4*>(albedo);
     P.normal = reinterpret_cast<float4*>(normal);
@@ -176,24 +184,24 @@ int renderFrame(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam
     // snapshot of the cumulative counters before this frame, so that "last frame" statistics can be formed at sync time
     PLT_CUDA(cudaMemcpyAsync(P.counters + 8, P.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     // device timers: one event triple per frame from a ring, read back in syncFrameStats()
-    if (c->timerEvents.empty()) {
-        c->timerEvents.resize(3 * PltptContext::kTimerRing);
-        for (auto& e : c->timerEvents) PLT_CUDA(cudaEventCreate(&e));
-    }
-    if (c->timerCount == PltptContext::kTimerRing || c->kernelEventCount > 60000) { if (int r = syncFrameStats(c)) return r; }
-    if (int r = renderTiles(c, P, tileRows, solve, nullptr, s)) return r;
-    c->timerCount++;
-    c->timerStream = s;
-    c->statsDirty = true;
+    if (int r = ensureTimers(ln)) return r;
+    if (ln.timerCount == PltptContext::kTimerRing || c->kernelEventCount > 60000) { if (int r = syncFrameStats(c)) return r; }
+    if (int r = renderTiles(c, ln, P, tileRows, solve, nullptr, s)) return r;
+    ln.timerCount++;
+    ln.timerStream = s;
+    ln.statsDirty = true;
     return PLTPT_OK;
 }
 
 int syncFrameStats(PltptContext* c) {
     PLT_CUDA(cudaSetDevice(c->device));
-    if (c->statsDirty && c->work[3].p) {
-        PLT_CUDA(cudaStreamSynchronize(c->timerStream));
+    bool any = false;
+    for (auto& ln : c->lanes) {
+        if (!(ln.statsDirty && ln.work[3].p)) continue;
+        any = true;
+        PLT_CUDA(cudaStreamSynchronize(ln.timerStream));
         unsigned long long host[16];
-        PLT_CUDA(cudaMemcpy(host, c->work[3].p, sizeof(host), cudaMemcpyDeviceToHost));
+        PLT_CUDA(cudaMemcpy(host, ln.work[3].p, sizeof(host), cudaMemcpyDeviceToHost));
         c->stats.bsdfEvals = host[0] - host[8];       // last frame
         c->stats.pathVertices = host[1] - host[9];
         c->stats.mneeIterations = host[3] - host[11];
@@ -204,18 +212,22 @@ int syncFrameStats(PltptContext* c) {
         c->stats.traversalNodesVisited += host[5];
         c->stats.traversalTrianglesTested += host[6];
         c->stats.unwindJobSteps += host[7];
-        PLT_CUDA(cudaMemset(c->work[3].p, 0, 16 * sizeof(unsigned long long)));
+        PLT_CUDA(cudaMemset(ln.work[3].p, 0, 16 * sizeof(unsigned long long)));
         uint32_t dropped = 0;
-        PLT_CUDA(cudaMemcpy(&dropped, c->work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
+        PLT_CUDA(cudaMemcpy(&dropped, ln.work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
         c->stats.droppedConnections += dropped;
-        for (uint32_t i = 0; i < c->timerCount; ++i) {
+        for (uint32_t i = 0; i < ln.timerCount; ++i) {
             float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, c->timerEvents[3 * i], c->timerEvents[3 * i + 1]);
-            cudaEventElapsedTime(&b, c->timerEvents[3 * i + 1], c->timerEvents[3 * i + 2]);
+            cudaEventElapsedTime(&a, ln.timerEvents[3 * i], ln.timerEvents[3 * i + 1]);
+            cudaEventElapsedTime(&b, ln.timerEvents[3 * i + 1], ln.timerEvents[3 * i + 2]);
             c->stats.sampleStageMs += a;
             c->stats.solveStageMs += b;
         }
-        c->stats.framesRendered += c->timerCount;
+        c->stats.framesRendered += ln.timerCount;
+        ln.timerCount = 0;
+        ln.statsDirty = false;
+    }
+    if (any) {  // per-kernel timers are only recorded on lane 0 (profiling disables the frame overlap)
         for (uint32_t i = 1; i < c->kernelEventCount; ++i) {
             const uint8_t cls = c->kernelEventClass[i];
             if (cls >= PLTPT_KERNEL_CLASS_COUNT) continue;  // 0xff: first event of a tile, nothing precedes it
@@ -225,8 +237,6 @@ int syncFrameStats(PltptContext* c) {
             c->stats.kernelLaunchCount[cls]++;
         }
         c->kernelEventCount = 0;
-        c->timerCount = 0;
-        c->statsDirty = false;
     }
     if (c->bvhScratch[7].p) {  // overflow counter of the standalone ray-query kernels (bvh.cu)
         uint32_t* ov = c->bvhScratch[7].as<uint32_t>() + 9;
@@ -239,24 +249,22 @@ int syncFrameStats(PltptContext* c) {
 
 // Sample stage only; writes the reference-layout bounce records of the whole frame to host memory (parity checks).
 int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host) {
+    PltptContext::Lane& ln = c->lanes[0];
     FrameParams P{};
-    const bool fresh = c->work[3].p == nullptr;
+    const bool fresh = ln.work[3].p == nullptr;
     uint32_t tileRows = 0;
-    if (int r = fillParams(c, P, frameCount, cam, w, h, tileRows)) return r;
+    if (int r = fillParams(c, ln, P, frameCount, cam, w, h, tileRows)) return r;
     P.albedo = reinterpret_cast<float4*>(albedo);
     P.normal = reinterpret_cast<float4*>(normal);
     if (fresh) PLT_CUDA(cudaMemset(P.counters, 0, 16 * sizeof(unsigned long long)));
-    if (c->timerEvents.empty()) {
-        c->timerEvents.resize(3 * PltptContext::kTimerRing);
-        for (auto& e : c->timerEvents) PLT_CUDA(cudaEventCreate(&e));
-    }
-    if (c->timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
+    if (int r = ensureTimers(ln)) return r;
+    if (ln.timerCount == PltptContext::kTimerRing) { if (int r = syncFrameStats(c)) return r; }
     const uint32_t records = c->opt.maxBounces + 1;
     const size_t bytes = size_t(w) * h * records * sizeof(PltptBounce);
-    PLT_CUDA(c->work[25].ensure(bytes));
-    if (int r = renderTiles(c, P, tileRows, false, c->work[25].as<PltptBounce>(), 0)) return r;
-    PLT_CUDA(cudaMemcpy(host, c->work[25].p, bytes, cudaMemcpyDeviceToHost));
-    c->work[25].release();
+    PLT_CUDA(ln.work[25].ensure(bytes));
+    if (int r = renderTiles(c, ln, P, tileRows, false, ln.work[25].as<PltptBounce>(), 0)) return r;
+    PLT_CUDA(cudaMemcpy(host, ln.work[25].p, bytes, cudaMemcpyDeviceToHost));
+    ln.work[25].release();
     return PLTPT_OK;
 }
 

@@ -301,7 +301,10 @@ __device__ const float kRgbBasis[7][11] = {
 
 PLT_D float xyzG(float x, float lambda, float s1, float s2) {
     const float t = (x - lambda) * (x < lambda ? s1 : s2);
-    return expf(-0.5f * t * t);
+    // ex2.approx: 28 of these per measured connection (7 lobes x 4 wavelengths) were 12 % of k_unwind_step's instructions with the
+    // full-precision expf (profiles/r1e_unwind_lines.txt); its ~2e-6 relative error is far inside the 1e-4 colour tolerance and
+    // the fit itself is only good to ~1e-2 of the CIE curves (SpectrumUtilsTests.cpp:40-80)
+    return __expf(-0.5f * t * t);
 }
 PLT_D float3 wavelengthToXYZ(float l) {
     return mk3(0.362f * xyzG(l, 442.0f, 0.0624f, 0.0374f) + 1.056f * xyzG(l, 599.8f, 0.0264f, 0.0323f) - 0.065f * xyzG(l, 501.1f, 0.0490f, 0.0382f),
@@ -328,28 +331,41 @@ PLT_D float3 spectrumToRgb(float4 spectrum, float4 wavelengths, int samples) {
     }
     return result / 10.5670762f;
 }
-PLT_D float rgbToSpectrum(float3 rgb, float wavelength) {
-    const int b = (int)(clampf((wavelength - kMinWavelength) / (kMaxWavelength - kMinWavelength), .0f, 1.f) * 10.f);
-    const float white = kRgbBasis[0][b], cyan = kRgbBasis[1][b], magenta = kRgbBasis[2][b], yellow = kRgbBasis[3][b];
-    const float red = kRgbBasis[4][b], green = kRgbBasis[5][b], blue = kRgbBasis[6][b];
+// SpectrumUtils.slang:106-160.  Which two chromatic basis spectra an RGB triple mixes depends on the ordering of r, g, b only, so
+// it is resolved once per triple; per wavelength that leaves three table reads (white + two) instead of seven.  The sum keeps the
+// reference's operation order ((white * w + first * c1) + second * c2), so the result is bit-identical to the seven-read form.
+struct RgbBasisSel { int i1, i2; float w, c1, c2; };
+PLT_D RgbBasisSel rgbBasisSelect(float3 rgb) {
     const float r = rgb.x, g = rgb.y, bl = rgb.z;
-    float sd = 0.f;
+    RgbBasisSel s;
     if (r <= g && r <= bl) {
-        sd += white * r;
-        if (g <= bl) { sd += cyan * (g - r); sd += blue * (bl - g); }
-        else { sd += cyan * (bl - r); sd += green * (g - bl); }
+        s.w = r; s.i1 = 1;                                        // cyan
+        if (g <= bl) { s.c1 = g - r; s.i2 = 6; s.c2 = bl - g; }   // blue
+        else { s.c1 = bl - r; s.i2 = 5; s.c2 = g - bl; }          // green
     } else if (g <= r && g <= bl) {
-        sd += white * g;
-        if (r <= bl) { sd += magenta * (r - g); sd += blue * (bl - r); }
-        else { sd += magenta * (bl - g); sd += red * (r - bl); }
+        s.w = g; s.i1 = 2;                                        // magenta
+        if (r <= bl) { s.c1 = r - g; s.i2 = 6; s.c2 = bl - r; }
+        else { s.c1 = bl - g; s.i2 = 4; s.c2 = r - bl; }          // red
     } else {
-        sd += white * bl;
-        if (r <= g) { sd += yellow * (r - bl); sd += green * (g - r); }
-        else { sd += yellow * (g - bl); sd += red * (r - g); }
+        s.w = bl; s.i1 = 3;                                       // yellow
+        if (r <= g) { s.c1 = r - bl; s.i2 = 5; s.c2 = g - r; }
+        else { s.c1 = g - bl; s.i2 = 4; s.c2 = r - g; }
     }
+    return s;
+}
+PLT_D float rgbBasisEval(const RgbBasisSel& s, float wavelength) {
+    const int b = (int)(clampf((wavelength - kMinWavelength) / (kMaxWavelength - kMinWavelength), .0f, 1.f) * 10.f);
+    float sd = 0.f;
+    sd += kRgbBasis[0][b] * s.w;
+    sd += kRgbBasis[s.i1][b] * s.c1;
+    sd += kRgbBasis[s.i2][b] * s.c2;
     return sd;
 }
-PLT_D float4 rgbToSpectrum4(float3 rgb, float4 wl) { return mk4(rgbToSpectrum(rgb, wl.x), rgbToSpectrum(rgb, wl.y), rgbToSpectrum(rgb, wl.z), rgbToSpectrum(rgb, wl.w)); }
+PLT_D float rgbToSpectrum(float3 rgb, float wavelength) { return rgbBasisEval(rgbBasisSelect(rgb), wavelength); }
+PLT_D float4 rgbToSpectrum4(float3 rgb, float4 wl) {
+    const RgbBasisSel s = rgbBasisSelect(rgb);
+    return mk4(rgbBasisEval(s, wl.x), rgbBasisEval(s, wl.y), rgbBasisEval(s, wl.z), rgbBasisEval(s, wl.w));
+}
 PLT_D float sampleHeroWavelength(float u) { return kMinWavelength + u * (kMaxWavelength - kMinWavelength); }
 PLT_D float4 hwssWavelengths(float hero, int hwss) {
     const float span = kMaxWavelength - kMinWavelength;

@@ -4,7 +4,7 @@
 #include "plt_integrator.cuh"
 
 #ifndef PLT_MINB_UNWIND_STEP
-#define PLT_MINB_UNWIND_STEP 3  // 164 registers, no spills: 12 resident warps per SM instead of 8 (profiles/r1b: -13% kernel time)
+#define PLT_MINB_UNWIND_STEP 4  // 128 registers (196 B of spills): 16 resident warps per SM instead of 8 (profiles/r1_variants*.log: -20% kernel time)
 #endif
 namespace plt {
 namespace {

@@ -189,6 +189,17 @@ def test_frames_are_deterministic_and_partitionable(torch_cuda, cornell):
     torch.cuda.synchronize()
     assert (full[..., 3] == 8).all()
     assert torch.allclose(full, even + odd, rtol=1e-12, atol=0)
+    # two frames in flight on two streams (default) against strictly sequential frames: same samples, fp64 summation order only
+    seq = torch.zeros_like(full)
+    p.set_frame_overlap(1)
+    p.render_accumulate(cam, 0, 1, 8, w, h, seq)
+    p.set_frame_overlap(0)
+    torch.cuda.synchronize()
+    assert (seq[..., 3] == 8).all() and torch.allclose(full, seq, rtol=1e-12, atol=0)
+    again = torch.zeros_like(full)
+    p.render_accumulate(cam, 0, 1, 8, w, h, again)
+    torch.cuda.synchronize()
+    assert torch.equal(full, again)
     # accumulate of one frame == that frame (with the Halton jitter GBufferRT would set)
     from pltfalcor_b200 import scene
     one = torch.zeros_like(full)

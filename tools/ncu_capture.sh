@@ -9,8 +9,9 @@ cap() {  # name regex skip count
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/${tag}_$1 python tools/profile_frame.py 2 > $out/${tag}_$1.log 2>&1
   ncu -i /tmp/${tag}_$1.ncu-rep --page raw --csv > $out/${tag}_$1_raw.csv 2>>$out/${tag}_$1.log
   ncu -i /tmp/${tag}_$1.ncu-rep --page source --csv 2>>$out/${tag}_$1.log | gzip -9 > $out/${tag}_$1_source.csv.gz
+  ncu -i /tmp/${tag}_$1.ncu-rep --page source --print-source cuda,sass --csv 2>>$out/${tag}_$1.log | gzip -9 > $out/${tag}_$1_cuda.csv.gz
 }
-cap unwind "k_unwind_step" 9 2
+cap unwind "k_unwind_step" 9 9   # all nine replay steps of the second frame: per-launch averages comparable with bench.py's live timers
 cap sample "k_shade|k_trace" 18 4
 cap connect "k_connect_a|k_shadow_trace|k_connect_b" 27 6
 # gpurun only merges gpurun_out/ back when it is below 64 MiB in total: the .ncu-rep files stay on the box

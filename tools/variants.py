@@ -18,11 +18,8 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
-    "a5": {"stage_connect.cu": ["-DPLT_MINB_CONNECT_A=5"]},
-    "t6": {"stage_sample.cu": ["-DPLT_MINB_TRACE=6"], "stage_connect.cu": ["-DPLT_MINB_SHADOW_TRACE=6"]},
-    "s5": {"stage_sample.cu": ["-DPLT_MINB_SHADE=5"]},
-    "c5": {"stage_connect.cu": ["-DPLT_MINB_CONNECT_B=5"]},
-    "u4": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=4"]},
+    "lanes3": {s: ["-DPLT_LANES=3"] for s in B.SOURCES},
+    "lanes4": {s: ["-DPLT_LANES=4"] for s in B.SOURCES},
 }
 
 
@@ -66,19 +63,28 @@ def bench_one(lib, frames):
     torch.cuda.synchronize()
     acc.zero_()
     p.reset_stats()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    p.render_accumulate(cam, 3, 1, frames, W, H, acc)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / frames
+    def timed():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        p.render_accumulate(cam, 3, 1, frames, W, H, acc)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / frames
+
+    timed()  # sizes the second lane's buffers
+    ms = timed()
+    ms_seq = None
+    if hasattr(binding.lib(), "pltpt_set_frame_overlap"):
+        p.set_frame_overlap(1)
+        ms_seq = timed()
+        p.set_frame_overlap(0)
     p.set_profiling(True)
     p.reset_stats()
     p.render_accumulate(cam, 3, 1, frames, W, H, acc)
     torch.cuda.synchronize()
     s = p.stats()
     k = {n: round(s["kernelMs"][n] / frames, 3) for n in L.KERNEL_CLASSES if s["kernelLaunchCount"][n]}
-    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "ms_per_frame": round(ms, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean()) / (2 * frames), "kernels": k}))
+    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "ms_per_frame": round(ms, 3), "ms_sequential": ms_seq and round(ms_seq, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean() / acc[..., 3].mean()), "kernels": k}))
 
 
 if __name__ == "__main__":
