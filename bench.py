@@ -212,6 +212,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the PLTPT path has no CPU fallback")
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     W, K = max(args.warmup, 3), args.steps
@@ -233,7 +234,6 @@ def main():
         accum.zero_()
     torch.cuda.synchronize()
     p.reset_stats()
-    p.set_profiling(not args.no_kernel_timers)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -254,10 +254,31 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
-    stats = p.stats()
-    p.set_profiling(False)
+    timed_stats = p.stats()
     paths_per_gpu = WIDTH * HEIGHT * K
     value = paths_per_gpu * world / (total_ms * 1e-3)
+
+    # ---- per-kernel durations: the same K frames again with a CUDA event after every launch on the launching stream.  The timed
+    # region above keeps two frames in flight on two streams (kernels of different frames share the SMs, so a per-launch duration
+    # taken there would include the other frame's work); this pass runs the frames one after the other so that every kernel is
+    # timed alone, which is what a roofline fraction needs.  Its frame time is reported as `sequential_ms_per_step`.
+    stats = timed_stats
+    seq_ms = None
+    if rank == 0 and not args.no_kernel_timers:
+        scratch = torch.zeros_like(accum)
+        p.reset_stats()
+        p.set_profiling(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        p.render_accumulate(cam, first, step, count, WIDTH, HEIGHT, scratch, stream=sptr)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        seq_ms = s0.elapsed_time(s1) / K
+        stats = p.stats()
+        p.set_profiling(False)
+        del scratch
+    if world > 1:
+        dist.barrier()
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------------
     host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(3)]
@@ -298,7 +319,7 @@ def main():
             k_ms_total, k_launches, units = kms["unwind_step"], kcount["unwind_step"], stats["unwindJobSteps"]
             roof = {"kernel": "k_unwind_step", "kernel_ms": k_ms_total / k_launches, "launches": int(k_launches), "units_per_launch": units / k_launches,
                     "algorithmic_bytes_per_unit": unit_bytes, "achieved": units * unit_bytes / (k_ms_total * 1e-3) / 1e9, "share_of_step": kernels["unwind_step"]["share_of_step"],
-                    "timer": "CUDA events after every launch on the launching stream, inside the timed region"}
+                    "timer": "CUDA events after every launch on the launching stream; same K frames as the timed region, run one frame at a time (sequential_ms_per_step) so that the kernel is timed alone"}
         else:  # --no-kernel-timers: whole solve stage from the stage timers
             roof = {"kernel": "solve stage (k_connect_*, k_shadow_trace, k_mnee, k_sort_queue, k_unwind_step, k_resolve)", "kernel_ms": solve_ms, "launches": int(frames),
                     "units_per_launch": WIDTH * HEIGHT, "algorithmic_bytes_per_unit": pb["solve_bytes"], "achieved": pb["solve_bytes"] * WIDTH * HEIGHT / (solve_ms * 1e-3) / 1e9,
@@ -307,13 +328,14 @@ def main():
         out = {
             "metric": "plt_paths_per_s", "value": value, "unit": "paths/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "max_bounces": MAX_BOUNCES, "hwss": 4, "nee": True, "mis": True, "mnee": True, "russian_roulette": True,
+            "config": {"workload": WORKLOAD, "max_bounces": MAX_BOUNCES, "hwss": 4, "nee": True, "mis": True, "mnee": True, "russian_roulette": True, "frames_in_flight": 2,
                        "paths_per_step_per_gpu": WIDTH * HEIGHT, "partition": "frame index modulo n_gpus; fp64 accumulators summed by one NCCL reduce inside the timed region",
                        "l2": "inputs larger than L2: every frame rewrites and re-reads its %.0f MB bounce buffer (126 MB L2)" % ((MAX_BOUNCES + 1) * WIDTH * HEIGHT * 40 / 1e6),
                        "triangles": int(build_stats["triangleCount"]), "bvh_nodes": int(build_stats["bvhNodes"]), "bvh_build_ms": build_stats["bvhBuildMs"]},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": C.sizeof(L.PltptCameraData), "d2h_bytes_per_step": 3 * WIDTH * HEIGHT * 16, "steps": e2e_steps,
                     "api": "pltpt_render_frame_host (camera in, color/albedo/normal RGBA32F out, pinned host buffers)", "checksum_mean_rgb": checksum},
-            "gpu_launches": int(stats["kernelLaunches"]),
+            "gpu_launches": int(timed_stats["kernelLaunches"]),
+            "sequential_ms_per_step": seq_ms,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": roof["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": roof["achieved"] / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, **{k: v for k, v in roof.items() if k != "achieved"},

@@ -66,6 +66,8 @@ extern "C" int pltpt_destroy(PltptHandle h) {
         if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->guidesReady) cudaEventDestroy(h->guidesReady);
+    if (h->copyStream) cudaStreamDestroy(h->copyStream);
     for (auto e : h->kernelEvents) cudaEventDestroy(e);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
@@ -657,10 +659,25 @@ extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const
     PLT_CUDA(h->outColor.ensure(bytes));
     PLT_CUDA(h->outAlbedo.ensure(bytes));
     PLT_CUDA(h->outNormal.ensure(bytes));
-    if (int r = renderFrame(h, 0, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0)) return r;
-    if (colorHost) PLT_CUDA(cudaMemcpy(colorHost, h->outColor.p, bytes, cudaMemcpyDeviceToHost));
-    if (albedoHost) PLT_CUDA(cudaMemcpy(albedoHost, h->outAlbedo.p, bytes, cudaMemcpyDeviceToHost));
-    if (normalHost) PLT_CUDA(cudaMemcpy(normalHost, h->outNormal.p, bytes, cudaMemcpyDeviceToHost));
+    // albedo and normal leave for the host on a copy stream as soon as the sample stage has written them (under the solve stage);
+    // color follows on the render stream.  Host buffers should be pinned for the copies to overlap.
+    const bool guides = albedoHost || normalHost;
+    if (guides) {
+        if (!h->copyStream) PLT_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+        if (!h->guidesReady) PLT_CUDA(cudaEventCreateWithFlags(&h->guidesReady, cudaEventDisableTiming));
+    }
+    h->armGuides = guides;  // renderTiles records guidesReady after the last tile's sample stage
+    const int rr = renderFrame(h, 0, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0);
+    h->armGuides = false;
+    if (rr) return rr;
+    if (guides) {
+        PLT_CUDA(cudaStreamWaitEvent(h->copyStream, h->guidesReady, 0));
+        if (albedoHost) PLT_CUDA(cudaMemcpyAsync(albedoHost, h->outAlbedo.p, bytes, cudaMemcpyDeviceToHost, h->copyStream));
+        if (normalHost) PLT_CUDA(cudaMemcpyAsync(normalHost, h->outNormal.p, bytes, cudaMemcpyDeviceToHost, h->copyStream));
+    }
+    if (colorHost) PLT_CUDA(cudaMemcpyAsync(colorHost, h->outColor.p, bytes, cudaMemcpyDeviceToHost, 0));
+    PLT_CUDA(cudaStreamSynchronize(0));
+    if (guides) PLT_CUDA(cudaStreamSynchronize(h->copyStream));
     return PLTPT_OK;
 }
 extern "C" int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, PltptBounce* bouncesHost) {

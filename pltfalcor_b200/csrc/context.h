@@ -103,6 +103,9 @@ struct PltptContext {
         cudaStream_t timerStream = nullptr;
     } lanes[kLanes];
     cudaEvent_t evFork = nullptr;
+    cudaEvent_t guidesReady = nullptr, copyDone = nullptr;  // pltpt_render_frame_host: guide-buffer copies run on copyStream under the solve stage
+    cudaStream_t copyStream = nullptr;
+    bool armGuides = false;
     int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};

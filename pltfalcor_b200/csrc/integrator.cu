@@ -129,6 +129,9 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
             c->stats.kernelLaunches += 4;
         }
         if (timed) cudaEventRecord(ev[1], s);
+        // guide buffers (albedo, normal) are final once the last tile's sample stage has run: the host-buffer path starts their
+        // device-to-host copies here, under the solve stage
+        if (c->armGuides && y0 + tileRows >= P.height) cudaEventRecord(c->guidesReady, s);
         if (bouncesOut) { launchGatherBounces(P, bouncesOut, maxB + 1, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_OTHER, s); }
         if (solve) {
             // ---- solve stage: connect per vertex index, then the replay wavefront, then the deterministic per-pixel sum

@@ -6,8 +6,12 @@
 #ifndef PLT_MINB_UNWIND_STEP
 #define PLT_MINB_UNWIND_STEP 4  // 128 registers (196 B of spills): 16 resident warps per SM instead of 8 (profiles/r1_variants*.log: -20% kernel time)
 #endif
+#ifndef PLT_UNWIND_PREFETCH
+#define PLT_UNWIND_PREFETCH 0  // measured on B200 (profiles/r1_variants6_prefetch.log): 1.92 ms with, 1.71 ms without -- left off
+#endif
 namespace plt {
 namespace {
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Counting-sort scatter of the pending list into material-type order (dst).  Runs between a producer and a consumer launch.
 __global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ FrameParams P, SortView view) {
     __shared__ uint32_t offs[kQueueTypes];
@@ -45,13 +49,28 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[2 * kQueueTypes + 2];
     uint32_t evals = 0;
-    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
-        const uint32_t i = base + threadIdx.x;
-        if (i < n) {
-            uint32_t nextType = 0, nextAux = 0;
-            const uint32_t id = P.sorted[i];
-            if (unwindStep(P, id, P.sortedAux[i], evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
+    const uint32_t stride = gridDim.x * kStageThreads;
+    uint32_t i = blockIdx.x * kStageThreads + threadIdx.x;
+    uint32_t id = 0, aux = 0;
+    if (i < n) { id = P.sorted[i]; aux = P.sortedAux[i]; }
+    for (; i < n; i += stride) {  // (tail threads of the last CTA-row simply skip: no block-wide barrier in this kernel)
+        // optional software prefetch of this thread's NEXT item (job 160 B, vertex 64 B, bounce direction 16 B) into L2; an
+        // experiment that lost (see PLT_UNWIND_PREFETCH above): the queue entries of the next item are still read one iteration early
+        const uint32_t j = i + stride;
+        uint32_t nid = 0, naux = 0;
+        if (j < n) {
+            nid = P.sorted[j]; naux = P.sortedAux[j];
+#if PLT_UNWIND_PREFETCH
+            const uint32_t npx = naux & 0x3ffffffu, nq = naux >> 26;
+            const char* jr = reinterpret_cast<const char*>(P.job + size_t(nid) * kJobPlanes);
+            prefetchL2(jr); prefetchL2(jr + 128);
+            prefetchL2(P.vc + 4 * (size_t(nq) * P.pixelCount + npx));
+            prefetchL2(P.bDir + size_t(nq) * P.pixelCount + npx);
+#endif
         }
+        uint32_t nextType = 0, nextAux = 0;
+        if (unwindStep(P, id, aux, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
+        id = nid; aux = naux;
     }
     warpAdd(P.counters + 0, evals);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);

@@ -18,8 +18,7 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
-    "lanes3": {s: ["-DPLT_LANES=3"] for s in B.SOURCES},
-    "lanes4": {s: ["-DPLT_LANES=4"] for s in B.SOURCES},
+    "nopf": {"stage_unwind.cu": ["-DPLT_UNWIND_PREFETCH=0"]},
 }
 
 
