@@ -933,8 +933,11 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
 // ---- connect wavefront: A (light sampling) -> shadow-ray trace kernel -> B (visibility, MIS, emit) per vertex index ------------
 // Per work-list entry (one recorded vertex of one path) the two halves hand over through a ConnItem, a ray and a job slot that
 // already holds the sourced beam.
-struct ConnItem { float4 dirPdf; uint4 info; };  // ls.dir.xyz | ls.pdf ; jobId, flags, asuint(ms.pdf), lobe of the current-vertex delta sample
-enum : uint32_t { CI_TRACE = 1u, CI_ANY_HIT = 2u, CI_DO_MIS = 4u, CI_CURRENT_MS = 8u, CI_DISPERSIVE = 16u };
+// ls.dir.xyz | ls.pdf ; jobId, flags, asuint(ms.pdf), CI_CURRENT_MS ? lobe of the current-vertex delta sample : asuint(MIS weight of
+// the unoccluded connection) — half A already knows that weight (it does not depend on visibility), so for the common outcome
+// "shadow ray answered, nothing special about the vertex" half B finishes from this item alone, without rebuilding the vertex.
+struct ConnItem { float4 dirPdf; uint4 info; };
+enum : uint32_t { CI_TRACE = 1u, CI_ANY_HIT = 2u, CI_DO_MIS = 4u, CI_CURRENT_MS = 8u, CI_DISPERSIVE = 16u, CI_EMISSIVE = 32u };
 
 struct ConnectCtx {  // what both halves rebuild for a vertex
     SolveState st;
@@ -1012,6 +1015,8 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                     }
                 }
                 if (alive) {
+                    if ((flags & CI_DO_MIS) && !(flags & CI_CURRENT_MS)) lobe0 = __float_as_uint(misWeight(ls.pdf, bsdfPdf(c.m, c.sd, ls.dir, ls.beam.wl.x)));
+                    if (P.useEmissive && (c.m.propFlags & P_IsEmissive)) flags |= CI_EMISSIVE;
                     const uint32_t id = allocJob(P);
                     if (id < P.jobCapacity) {
                         JobHeader h;
@@ -1038,18 +1043,42 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
 }
 
 // Half B (pltpt_solve.rt.slang:283-361): visibility / occluder chain, MIS weight, hand-over to the unwind queues (or to k_mnee).
+// Returns true when the entry needs the full half B (connectB): it is then queued for k_connect_b_slow, so that the few entries
+// with an occluder chain / delta sample / emissive hit run densely packed instead of stalling 31 finished lanes each.
+PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
+    const ConnItem item = P.connItems[slot];
+    const uint32_t flags = item.info.y;
+    if (!(flags & CI_TRACE)) return false;
+    const int p = int(P.level);
+    const uint32_t jobId = item.info.x;
+    const bool blocked = P.shadowHits[slot].x != 0xffffffffu;
+    // Fast path (pltpt_solve.rt.slang:283-300 with nothing else to do at this vertex): plain visibility answer, no delta sample
+    // of the current vertex, no emissive hit.  MIS weight from half A; the emissive slot of a non-emissive vertex is zero; the
+    // generator state half A stored is already the one the next vertex continues from (this half would draw nothing).
+    if (!(flags & (CI_CURRENT_MS | CI_EMISSIVE)) && ((flags & CI_ANY_HIT) || !blocked)) {
+        if (!blocked) {
+            if (flags & CI_DO_MIS) {
+                const float w = __uint_as_float(item.info.w);
+                for (int k = 0; k < 4; ++k) { float4* q = jobField(P, jobId, k); *q = *q * w; }
+            }
+            enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId, jobAux(pixel, uint32_t(p)));
+        } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+        writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f));
+        return false;
+    }
+    return true;
+}
 PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
     const ConnItem item = P.connItems[slot];
     const uint32_t flags = item.info.y;
-    if (!(flags & CI_TRACE)) return;
     const int p = int(P.level);
-    ConnectCtx c;
-    connectSetup(P, pixel, p, false, c);
     const uint32_t jobId = item.info.x;
-    const float3 lsDir = mk3(item.dirPdf.x, item.dirPdf.y, item.dirPdf.z);
-    const float lsPdf = item.dirPdf.w;
     const uint4 hit = P.shadowHits[slot];
     const bool blocked = hit.x != 0xffffffffu;
+    ConnectCtx c;
+    connectSetup(P, pixel, p, false, c);
+    const float3 lsDir = mk3(item.dirPdf.x, item.dirPdf.y, item.dirPdf.z);
+    const float lsPdf = item.dirPdf.w;
     bool connected = false;
     float misScale = 1.f;
     if (flags & CI_ANY_HIT) {
@@ -1190,7 +1219,7 @@ void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
-void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s);
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s);  // fast pass + dense pass over the deferred entries
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);

@@ -26,6 +26,7 @@ namespace {
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.levelCount[64] = 0;  // deferred-entry count of this level's half B
     uint32_t evals = 0, verts = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
@@ -70,14 +71,32 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
     warpAdd(P.counters + 6, tc.tris);
 }
 
-__global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b(const __grid_constant__ FrameParams P) {
+// Half B, pass 1: every entry whose shadow-ray answer settles it (connectBFast); the others are appended to the deferred list
+// (the sample stage's trace queue is idle during the solve stage and is reused for it; k_connect_a of this level zeroed its count).
+__global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
+    const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
+    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < n && connectBFast(P, i, list[i])) {
+            const uint32_t active = __activemask();
+            const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+            uint32_t at = 0;
+            if (lane == leader) at = atomicAdd(P.levelCount + 64, uint32_t(__popc(active)));
+            at = __shfl_sync(active, at, leader) + __popc(active & ((1u << lane) - 1u));
+            P.traceQueue[at] = i;
+        }
+    }
+}
+// Half B, pass 2: the deferred entries, densely packed.
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b_slow(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.levelCount[64];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
-        const uint32_t i = base + threadIdx.x;
-        if (i < n) connectB(P, i, list[i], evals, tc);
+        const uint32_t k = base + threadIdx.x;
+        if (k < n) { const uint32_t i = P.traceQueue[k]; connectB(P, i, list[i], evals, tc); }
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
@@ -101,5 +120,8 @@ void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_mnee<<<
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }
 void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_a<<<grid, kStageThreads, 0, s>>>(P); }
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P); }
-void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_b<<<grid, kStageThreads, 0, s>>>(P); }
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    k_connect_b<<<grid, kStageThreads, 0, s>>>(P);
+    k_connect_b_slow<<<grid, kStageThreads, 0, s>>>(P);
+}
 }  // namespace plt

@@ -18,7 +18,6 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
-    "nopf": {"stage_unwind.cu": ["-DPLT_UNWIND_PREFETCH=0"]},
 }
 
 
