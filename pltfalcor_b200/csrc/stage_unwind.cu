@@ -13,27 +13,44 @@ namespace plt {
 namespace {
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Counting-sort scatter of the pending list into material-type order (dst).  Runs between a producer and a consumer launch.
-__global__ void __launch_bounds__(256) k_sort_queue(const __grid_constant__ FrameParams P, SortView view) {
-    __shared__ uint32_t offs[kQueueTypes];
+// Each CTA takes chunks of kSortChunk entries: a shared-memory histogram of the chunk, ONE global cursor bump per type per chunk
+// (the per-warp version serialised ~65k atomics on the cursor of the dominant type), then the scatter with shared-memory cursors.
+constexpr int kSortThreads = 256, kSortItems = 8, kSortChunk = kSortThreads * kSortItems;
+__global__ void __launch_bounds__(kSortThreads) k_sort_queue(const __grid_constant__ FrameParams P, SortView view) {
+    __shared__ uint32_t offs[kQueueTypes], hist[kQueueTypes], base[kQueueTypes];
     uint32_t* qc = P.queueCount;
     const uint32_t total = qc[kQueueTypes];
     if (threadIdx.x == 0) {
         uint32_t run = 0;
         for (int t = 0; t < kQueueTypes; ++t) { offs[t] = run; run += qc[t]; }
     }
-    __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t type = P.pendingType[i];
-        // warp-aggregated cursor bump per type
-        const uint32_t active = __activemask();
-        const uint32_t peers = __match_any_sync(active, type);
-        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(qc + kQueueTypes + 1 + type, uint32_t(__popc(peers)));
-        base = __shfl_sync(peers, base, leader);
-        const uint32_t pos = offs[type] + base + __popc(peers & ((1u << lane) - 1u));
-        view.dst[pos] = P.pending[i];
-        if (view.dstAux) view.dstAux[pos] = P.pendingAux[i];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t chunk = blockIdx.x * kSortChunk; chunk < total; chunk += gridDim.x * kSortChunk) {
+        if (threadIdx.x < kQueueTypes) hist[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t type[kSortItems], rank[kSortItems];
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const uint32_t i = chunk + k * kSortThreads + threadIdx.x;
+            type[k] = i < total ? P.pendingType[i] : 0xffu;
+            // warp-aggregated rank within the chunk's per-type run
+            const uint32_t peers = __match_any_sync(0xffffffffu, type[k]);
+            uint32_t r = 0;
+            if (type[k] != 0xffu && lane == __ffs(peers) - 1) r = atomicAdd(&hist[type[k]], uint32_t(__popc(peers)));
+            rank[k] = __shfl_sync(0xffffffffu, r, __ffs(peers) - 1) + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < kQueueTypes) base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(qc + kQueueTypes + 1 + threadIdx.x, hist[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const uint32_t i = chunk + k * kSortThreads + threadIdx.x;
+            if (type[k] == 0xffu) continue;
+            const uint32_t pos = offs[type[k]] + base[type[k]] + rank[k];
+            view.dst[pos] = P.pending[i];
+            if (view.dstAux) view.dstAux[pos] = P.pendingAux[i];
+        }
+        __syncthreads();
     }
 }
 // Publishes the sorted count and resets histogram / cursors / pending count (single thread; stream-ordered after k_sort_queue).
@@ -83,7 +100,7 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FramePa
 }  // namespace
 
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s) {
-    k_sort_queue<<<grid, 256, 0, s>>>(P, v);
+    k_sort_queue<<<grid, kSortThreads, 0, s>>>(P, v);
     k_flip_queue<<<1, 32, 0, s>>>(P, v, resetTraceQueue);
 }
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_unwind_step<<<grid, kStageThreads, 0, s>>>(P); }
