@@ -479,7 +479,10 @@ __device__ __forceinline__ SD canonicalSd(uint32_t materialID, float3 V) {
     return sd;
 }
 
-constexpr int kSweepThreads = 128;
+#ifndef PLT_SWEEP_UNROLL
+#define PLT_SWEEP_UNROLL 1
+#endif
+constexpr int kSweepThreads = 128, kSweepUnroll = PLT_SWEEP_UNROLL;
 // One thread per (query, hero group): evaluates the BSDF on the four basis Stokes vectors; results are staged in
 // shared memory (stride 65 words: conflict-free) and written out as fully coalesced 128 B lines.
 __global__ void __launch_bounds__(kSweepThreads) k_bsdf_eval_mueller(DevScene sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups,
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_bsdf_eval_mueller(DevScene sc
             const float4 wl = hwssWavelengths(__ldg(hero + size_t(g) * n + i), hwss);
             const SD sd = canonicalSd(materialID, Wi);
             float* my = stage + threadIdx.x * stride;
-#pragma unroll 1
+#pragma unroll kSweepUnroll
             for (int c = 0; c < 4; ++c) {
                 Beam beam = sourceBeamArea(Wi, -Wi, 1.f, 1.f, mk4(1.f), wl, maxBeamOmega, hwss);
                 const float4 e = mk4(c == 0 ? 1.f : 0.f, c == 1 ? 1.f : 0.f, c == 2 ? 1.f : 0.f, c == 3 ? 1.f : 0.f);

@@ -18,6 +18,7 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
+    "sweep4": {"api.cu": ["-DPLT_SWEEP_UNROLL=4"]},
 }
 
 
@@ -82,7 +83,12 @@ def bench_one(lib, frames):
     torch.cuda.synchronize()
     s = p.stats()
     k = {n: round(s["kernelMs"][n] / frames, 3) for n in L.KERNEL_CLASSES if s["kernelLaunchCount"][n]}
-    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "ms_per_frame": round(ms, 3), "ms_sequential": ms_seq and round(ms_seq, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean() / acc[..., 3].mean()), "kernels": k}))
+    import bench
+    sb, ids = scene.sweep_scene()
+    q = binding.Pltpt()
+    q.set_scene(sb)
+    sweep = {k: round(v["evals_per_s"] / 1e9, 3) for k, v in bench.bsdf_sweep(torch, q, ids, 6543.7).items()}
+    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "sweep_Gevals_s": sweep, "ms_per_frame": round(ms, 3), "ms_sequential": ms_seq and round(ms_seq, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean() / acc[..., 3].mean()), "kernels": k}))
 
 
 if __name__ == "__main__":
