@@ -133,6 +133,28 @@ def cpu_baseline_sample(buffers, cam, opts, seconds=10.0):
             "sample": f"{frames} frames of the same Cornell-box workload at {w}x{h} (1/4 of the pixels), depth {MAX_BOUNCES}, {dt:.1f} s wall, oracle/liboracle.so"}
 
 
+def cpu_bsdf_sweep_sample(ids, sw_buffers, seconds=4.0):
+    """BASELINE configs[0] on the CPU oracle: BSDF evals/s (one eval = one wavelength's Mueller matrix) on a bounded sample."""
+    from oracle import binding as ob
+    osc = ob.OracleScene(sw_buffers)
+    threads = ob.hardware_threads()
+    rng = np.random.default_rng(1)
+    n, groups = 1 << 15, 4
+    wi = rng.normal(size=(n, 3)).astype(np.float32); wi /= np.linalg.norm(wi, axis=1, keepdims=True); wi[:, 2] = np.abs(wi[:, 2])
+    wo = rng.normal(size=(n, 3)).astype(np.float32); wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    hero = (380 + 340 * rng.random((groups, n))).astype(np.float32)
+    out = {}
+    for key in ("dielectric", "conductor"):
+        osc.bsdf_eval_mueller(ids[key], 0x33, wi[:1024], wo[:1024], hero[:, :1024], threads=threads)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds / 2:
+            osc.bsdf_eval_mueller(ids[key], 0x33, wi, wo, hero, threads=threads)
+            reps += 1
+        dt = time.perf_counter() - t0
+        out[key] = {"evals_per_s": reps * n * groups * 4 / dt, "cores": threads, "sample": f"{reps} x 2^15 queries x 16 wavelengths, {dt:.1f} s wall"}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path. slangc is not available, so the Slang modules cannot
     be compiled for the CPU; the oracle port (C++ restatement, all host threads) stands in (DESIGN.md 'Oracle')."""
@@ -355,6 +377,10 @@ def main():
             q.close()
             if not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_baseline_sample(buffers, cam, p.options)
+                cpu_sw = cpu_bsdf_sweep_sample(ids, sw_buffers)
+                for key, v in cpu_sw.items():
+                    out["bsdf_sweep"][key]["cpu_oracle"] = v
+                    out["bsdf_sweep"][key]["gpu_over_cpu"] = out["bsdf_sweep"][key]["evals_per_s"] / v["evals_per_s"]
         print(json.dumps(out))
     p.close()
     if world > 1:

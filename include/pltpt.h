@@ -418,6 +418,7 @@ typedef struct PltptStats {
     double   kernelMs[PLTPT_KERNEL_CLASS_COUNT];
     uint64_t kernelLaunchCount[PLTPT_KERNEL_CLASS_COUNT];
     uint64_t unwindJobSteps;                   /* work items of k_unwind_step: one generalized ray pushed through one recorded vertex */
+    uint64_t mneeWalks;                        /* manifold walks parked for k_mnee in the last tile of the last frame */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);

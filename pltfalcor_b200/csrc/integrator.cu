@@ -146,7 +146,7 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
                 c->stats.kernelLaunches += 4;
             }
             if (P.useEnv) { launchConnectMiss(P, persistentGrid, s); c->markKernel(PLTPT_K_CONNECT_A, s); c->stats.kernelLaunches++; }
-            if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_MNEE, s); }
+            if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches += 2; c->markKernel(PLTPT_K_MNEE, s); }
             for (uint32_t it = 0; it <= maxB; ++it) {
                 launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2, P.sortedAux}, false, persistentGrid, s);
                 c->markKernel(PLTPT_K_SORT, s);
@@ -219,6 +219,9 @@ int syncFrameStats(PltptContext* c) {
         uint32_t dropped = 0;
         PLT_CUDA(cudaMemcpy(&dropped, ln.work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
         c->stats.droppedConnections += dropped;
+        uint32_t walks = 0;
+        PLT_CUDA(cudaMemcpy(&walks, ln.work[14].as<uint32_t>() + 34, 4, cudaMemcpyDeviceToHost));
+        c->stats.mneeWalks = walks;
         for (uint32_t i = 0; i < ln.timerCount; ++i) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, ln.timerEvents[3 * i], ln.timerEvents[3 * i + 1]);

@@ -798,62 +798,74 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
     positionStepDir = p.ddu * dX.x + p.ddv * dX.y;
     return true;
 }
-// Manifolds.slangh:165-281 after the occluder chain has been collected (traceMNEEOccluders): the Newton / line-search walk
-// and the final visibility test.  It consumes no random numbers, so it runs in its own kernel (k_mnee) where its data-dependent
-// iteration count cannot stall the coherent NEE work.
-PLT_D bool manifoldWalk(const FrameParams& P, TraversalCounters& tc, float3 origin, float3 lightPos, float3 lightDir, bool isDistantLight, ManifoldSampleData& data) {
+// Manifolds.slangh:165-281 after the occluder chain has been collected (traceMNEEOccluders): the Newton / line-search walk.
+// It consumes no random numbers, so it runs in its own kernel (k_mnee_walk).  The reference's nested loops
+//     while (!success) { success = true; for (idx ...) { newton step; if (|C| < eps) continue; success = false; for (;;) { trial ray ... } } }
+// are unrolled into a resumable state machine whose unit of work ("trip") is at most one Newton step (phase A) followed by at
+// most one line-search trial ray (phase B): every lane of a warp then executes the same code for a different walk, and a lane
+// whose walk has ended takes the next parked walk at once instead of idling until the longest walk of its warp is over
+// (walk lengths range from 1 to MNEEMaxIterations trial rays).  Arithmetic and its order are the reference's.
+struct WalkState {
+    ManifoldSampleData ms;
     float beta[kMaxMSHits];
-    for (int i = 0; i < kMaxMSHits; ++i) beta[i] = 1.f;
-    bool success = false;
-    while (!success) {
-        success = true;
-        for (int idx = 0; idx < data.hitCount; ++idx) {
-            const TriHit th = unpackHit(P.sc, data.hits[idx].hit);
-            uint32_t materialID;
-            const VertexData v = getVertexData(P.sc, th, materialID);
-            const DiffGeom dsg = differentialShadingGeometry(P.sc, th);
-            const float3 p0 = idx == 0 ? origin : data.hits[idx - 1].posW;
-            const V3pdv pdvp0 = dsg.pdw(p0);
-            const float3 p2 = idx + 1 == data.hitCount ? lightPos : data.hits[idx + 1].posW;
-            V3pdv pdvp2;
-            pdvp2.v = lightDir; pdvp2.ddu = pdvp2.ddv = mk3(0.f);
-            if (!isDistantLight) pdvp2 = dsg.pdw(p2);
-            const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
-            const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
-            const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
-            const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-            const SD sd = prepareShadingData(v, materialID, m, wiP.v);
-            const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, data.hits[idx].lobe, data.wavelength);
-            float lenC;
-            float3 positionStepDir;
-            if (allZero(wos.v)) return false;
-            if (!manifoldOneStep(woP, wos, dsg.p, lenC, positionStepDir)) return false;
-            if (lenC < P.opt.MNEESolverThreshold) continue;
-            success = false;
-            for (;;) {
-                if (++data.iterations > P.opt.MNEEMaxIterations) return false;
-                const float3 proposal = data.hits[idx].posW - beta[idx] * positionStepDir;
-                float3 dirToProposal = proposal - p0;
-                const float dist = length(dirToProposal);
-                dirToProposal /= dist;
-                TriHit ph;
-                float pt;
-                const bool isHit = traceClosestHit(P, tc, p0, dirToProposal, fmaxf(kShadowRayTMin, .99f * dist), 1.01f * dist, ph, pt);
-                if (!isHit || th.instanceID != ph.instanceID) { beta[idx] /= 4.f; continue; }
-                data.hits[idx].hit = packHit(P.sc, ph);
-                data.hits[idx].posW = p0 + dirToProposal * pt;
-                beta[idx] = fminf(1.0f, 2.f * beta[idx]);
-                break;
-            }
+    float3 origin, lightPos, lightDir, stepDir;
+    uint32_t hitInstance;   // instance of the vertex the current line search moves (th.instanceID at Newton time)
+    int idx;                // vertex of the chain the current pass is at
+    bool distant, passSuccess, lineSearch;
+};
+enum { WALK_CONTINUE = 0, WALK_CONVERGED = 1, WALK_FAILED = -1 };
+PLT_D int manifoldWalkTrip(const FrameParams& P, TraversalCounters& tc, WalkState& w) {
+    ManifoldSampleData& data = w.ms;
+    if (!w.lineSearch) {  // ---- phase A: Newton step at vertex idx
+        if (w.idx == data.hitCount) {  // a pass over the chain is complete
+            if (w.passSuccess) return WALK_CONVERGED;
+            w.passSuccess = true; w.idx = 0;
         }
+        const int idx = w.idx;
+        const TriHit th = unpackHit(P.sc, data.hits[idx].hit);
+        uint32_t materialID;
+        const VertexData v = getVertexData(P.sc, th, materialID);
+        const DiffGeom dsg = differentialShadingGeometry(P.sc, th);
+        const float3 p0 = idx == 0 ? w.origin : data.hits[idx - 1].posW;
+        const V3pdv pdvp0 = dsg.pdw(p0);
+        const float3 p2 = idx + 1 == data.hitCount ? w.lightPos : data.hits[idx + 1].posW;
+        V3pdv pdvp2;
+        pdvp2.v = w.lightDir; pdvp2.ddu = pdvp2.ddv = mk3(0.f);
+        if (!w.distant) pdvp2 = dsg.pdw(p2);
+        const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
+        const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
+        const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
+        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+        const SD sd = prepareShadingData(v, materialID, m, wiP.v);
+        const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, data.hits[idx].lobe, data.wavelength);
+        float lenC;
+        float3 positionStepDir;
+        if (allZero(wos.v)) return WALK_FAILED;
+        if (!manifoldOneStep(woP, wos, dsg.p, lenC, positionStepDir)) return WALK_FAILED;
+        if (lenC < P.opt.MNEESolverThreshold) { w.idx = idx + 1; return WALK_CONTINUE; }
+        w.passSuccess = false;
+        w.lineSearch = true;
+        w.stepDir = positionStepDir;
+        w.hitInstance = th.instanceID;
     }
-    const float3 p = data.hits[data.hitCount - 1].posW;
-    float3 dir;
-    float dist;
-    if (!isDistantLight) { dir = lightPos - p; dist = length(dir); dir /= dist; }
-    else { dir = lightDir; dist = kFltMax; }
-    data.woLastHitToLight = dir;
-    return !occluded(P, tc, p, dir, kShadowRayTMin, dist);
+    // ---- phase B: one trial ray of the line search at vertex idx
+    const int idx = w.idx;
+    if (++data.iterations > P.opt.MNEEMaxIterations) return WALK_FAILED;
+    const float3 p0 = idx == 0 ? w.origin : data.hits[idx - 1].posW;
+    const float3 proposal = data.hits[idx].posW - w.beta[idx] * w.stepDir;
+    float3 dirToProposal = proposal - p0;
+    const float dist = length(dirToProposal);
+    dirToProposal /= dist;
+    TriHit ph;
+    float pt;
+    const bool isHit = traceClosestHit(P, tc, p0, dirToProposal, fmaxf(kShadowRayTMin, .99f * dist), 1.01f * dist, ph, pt);
+    if (!isHit || w.hitInstance != ph.instanceID) { w.beta[idx] /= 4.f; return WALK_CONTINUE; }
+    data.hits[idx].hit = packHit(P.sc, ph);
+    data.hits[idx].posW = p0 + dirToProposal * pt;
+    w.beta[idx] = fminf(1.0f, 2.f * w.beta[idx]);
+    w.lineSearch = false;
+    w.idx = idx + 1;
+    return WALK_CONTINUE;
 }
 // Manifolds.slangh:80-93
 PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const ManifoldSampleData& r, float3 origin, Beam& beam) {
@@ -879,23 +891,54 @@ struct alignas(16) MneeItem {
 };
 enum : uint32_t { MI_DISPERSIVE = 1u << 4, MI_DISTANT = 1u << 5, MI_CURRENT_VERTEX_MS = 1u << 6, MI_DO_MIS = 1u << 7 };
 
-// Second half of an MNEE connection (Manifolds.slangh:165-281 walk, pltpt_solve.rt.slang:320-361): Newton walk, final visibility,
-// replay of the beam through the found specular chain, MIS; then the connection joins the unwind queues like any other.
-PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals, TraversalCounters& tc) {
-    ManifoldSampleData ms;
+enum : uint32_t { MI_WALK_OK = 1u << 8 };
+PLT_D void mneeUnpack(const MneeItem& it, ManifoldSampleData& ms) {
     ms.hitCount = int(it.flags & 0xfu); ms.iterations = 0; ms.pdf = it.originPdf.w; ms.dispersive = (it.flags & MI_DISPERSIVE) != 0;
     ms.wavelength = it.lightPosWl.w; ms.woLastHitToLight = mk3(0.f);
-    for (int i = 0; i < ms.hitCount; ++i) {
+    for (int i = 0; i < kMaxMSHits - 1; ++i) {
         ms.hits[i].hit = it.hit[i];
         ms.hits[i].posW = mk3(it.posLobe[i].x, it.posLobe[i].y, it.posLobe[i].z);
         ms.hits[i].lobe = __float_as_uint(it.posLobe[i].w);
     }
+}
+// k_mnee_walk, start of a parked walk
+PLT_D void mneeWalkInit(const MneeItem& it, WalkState& w) {
+    mneeUnpack(it, w.ms);
+    for (int i = 0; i < kMaxMSHits; ++i) w.beta[i] = 1.f;
+    w.origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z);
+    w.lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
+    w.lightDir = mk3(it.lightDirLsPdf.x, it.lightDirLsPdf.y, it.lightDirLsPdf.z);
+    w.stepDir = mk3(0.f); w.hitInstance = 0;
+    w.idx = 0; w.distant = (it.flags & MI_DISTANT) != 0; w.passSuccess = true; w.lineSearch = false;
+}
+// k_mnee_walk, end of a walk: the converged chain goes back into the item for k_mnee_finish; a failed walk contributes nothing
+PLT_D void mneeWalkStore(const FrameParams& P, MneeItem& it, const WalkState& w, bool converged) {
+    if (P.counters && w.ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)w.ms.iterations);
+    if (!converged) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
+    for (int i = 0; i < w.ms.hitCount; ++i) {
+        it.hit[i] = w.ms.hits[i].hit;
+        it.posLobe[i] = mk4(w.ms.hits[i].posW.x, w.ms.hits[i].posW.y, w.ms.hits[i].posW.z, __uint_as_float(w.ms.hits[i].lobe));
+    }
+    it.flags |= MI_WALK_OK;
+}
+
+// k_mnee_finish (Manifolds.slangh:270-281, pltpt_solve.rt.slang:320-361): final visibility of the converged chain, replay of the
+// beam through the found specular vertices, MIS; then the connection joins the unwind queues like any other.
+PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals, TraversalCounters& tc) {
+    ManifoldSampleData ms;
+    mneeUnpack(it, ms);
     const float3 origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z), lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
     const float3 lightDir = mk3(it.lightDirLsPdf.x, it.lightDirLsPdf.y, it.lightDirLsPdf.z);
     const bool distant = (it.flags & MI_DISTANT) != 0, currentVertexMS = (it.flags & MI_CURRENT_VERTEX_MS) != 0;
-    const bool ok = manifoldWalk(P, tc, origin, lightPos, lightDir, distant, ms);
-    if (P.counters && ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)ms.iterations);
-    if (!ok) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
+    {
+        const float3 p = ms.hits[ms.hitCount - 1].posW;
+        float3 dir;
+        float dist;
+        if (!distant) { dir = lightPos - p; dist = length(dir); dir /= dist; }
+        else { dir = lightDir; dist = kFltMax; }
+        ms.woLastHitToLight = dir;
+        if (occluded(P, tc, p, dir, kShadowRayTMin, dist)) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
+    }
     Beam beam;
     JobHeader h;
     loadJob(P, it.jobId, beam, h);

@@ -102,21 +102,63 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b
     warpAdd(P.counters + 6, tc.tris);
 }
 
-// Manifold-walk kernel: one thread per parked connection.  Runs once per tile after all connect launches.
-__global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee(const __grid_constant__ FrameParams P) {
+// Manifold walks (Manifolds.slangh:165-281).  Pass 1: persistent lanes; a lane that has no walk takes the next parked one (one
+// warp-aggregated cursor bump per refill), then every lane runs ONE trip of its walk (manifoldWalkTrip).  Converged walks are
+// listed for pass 2.  The cursor and the list count live in queueCount[37..38] (zeroed per tile); the list reuses `sorted`, which
+// is idle until the first replay sort.
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(const __grid_constant__ FrameParams P) {
     const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
+    uint32_t* cursor = P.queueCount + 38;
+    uint32_t* doneCount = P.queueCount + 37;
+    const int lane = threadIdx.x & 31;
+    TraversalCounters tc = {0, 0};
+    WalkState w;
+    uint32_t item = 0;
+    bool have = false, exhausted = n == 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(cursor, uint32_t(__popc(idle)));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) { item = i; mneeWalkInit(P.mneeItems[i], w); have = true; }
+            }
+            exhausted = base + __popc(idle) >= n;  // warp-uniform
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            const int r = manifoldWalkTrip(P, tc, w);
+            if (r != WALK_CONTINUE) {
+                mneeWalkStore(P, P.mneeItems[item], w, r == WALK_CONVERGED);
+                if (r == WALK_CONVERGED) P.sorted[atomicAdd(doneCount, 1u)] = item;
+                have = false;
+            }
+        }
+    }
+    warpAdd(P.counters + 5, tc.nodes);
+    warpAdd(P.counters + 6, tc.tris);
+}
+// Pass 2: converged walks, densely packed: final visibility, replay through the specular chain, MIS, hand-over to the unwind queues.
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.queueCount[37];
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
-        if (i < n) mneeFinish(P, P.mneeItems[i], evals, tc);
+        if (i < n) mneeFinish(P, P.mneeItems[P.sorted[i]], evals, tc);
     }
     warpAdd(P.counters + 0, evals);
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
 }
 }  // namespace
-void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_mnee<<<grid, kStageThreads, 0, s>>>(P); }
+void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    k_mnee_walk<<<grid, kStageThreads, 0, s>>>(P);
+    k_mnee_finish<<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }
 void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_a<<<grid, kStageThreads, 0, s>>>(P); }
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P); }
