@@ -82,10 +82,13 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
     const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
     const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
     uint32_t stack[kTraversalStack];
+    float stackT[ANY ? 1 : kTraversalStack];  // entry distance of the pushed node: a closer hit found meanwhile culls it at pop time
     int sp = 0;
     stack[sp++] = 0;
+    if (!ANY) stackT[0] = tmin;
     while (sp > 0) {
         const uint32_t ni = stack[--sp];
+        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit below: exact-t ties are still visited)
         if (tc) ++tc->nodes;
         const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
         const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -149,8 +152,10 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
                     if (((innerHits >> i) & 1u) && (far < 0 || nearT[i] > ft)) { far = i; ft = nearT[i]; }
             }
             innerHits &= ~(1u << far);
-            if (sp < kTraversalStack) stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
-            else if (overflow) atomicAdd(overflow, 1u);
+            if (sp < kTraversalStack) {
+                if (!ANY) stackT[sp] = ft;
+                stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
+            } else if (overflow) atomicAdd(overflow, 1u);
         }
     }
     return best.valid();

@@ -9,7 +9,7 @@ namespace plt {
 namespace {
 // worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
 size_t workBytesPerPixel(uint32_t records) {
-    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4 + 8) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * sizeof(MneeItem) + sizeof(ConnItem) + 32 + 16 + 4;
+    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4 + 8) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * (sizeof(MneeItem) + sizeof(MneeWalk) + 12) + sizeof(ConnItem) + 32 + 16 + 4;
 }
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
@@ -79,6 +79,10 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.mneeItems = ln.work[26].as<MneeItem>();
     P.mneeCount = P.queueCount + 34;
     P.mneeCapacity = 2 * tilePixels;
+    PLT_CUDA(ln.work[8].ensure(size_t(2) * tilePixels * sizeof(MneeWalk)));
+    PLT_CUDA(ln.work[31].ensure(size_t(3) * 2 * tilePixels * 4));
+    P.mneeWalks = ln.work[8].as<MneeWalk>();
+    P.mneeLists = ln.work[31].as<uint32_t>();
     PLT_CUDA(ln.work[24].ensure(size_t(tilePixels) * 4));
     P.missList = ln.work[24].as<uint32_t>();
     P.missCount = P.queueCount + 36;

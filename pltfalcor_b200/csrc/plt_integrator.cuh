@@ -59,6 +59,8 @@ struct FrameParams {
     uint4* ssTileRng;        // per-tile generator (NEEUsePerTileSG)
     uint32_t level;          // bounce / vertex index the current launch works on
     MneeItem* mneeItems;     // connections parked for the manifold-walk kernel
+    struct MneeWalk* mneeWalks;  // their walk state between rounds
+    uint32_t* mneeLists;     // [3][mneeCapacity]: two ping-pong lists of live walks + the list of converged walks
     struct ConnItem* connItems;  // [pixelCount] hand-over between the two connect halves, indexed like the level's work list
     float4* shadowRays;      // [2 * pixelCount] origin|tmin, dir|tmax of the NEE shadow rays
     uint4* shadowHits;       // [pixelCount] instanceID (0xffffffff = nothing hit), primitiveIndex, asuint(u), asuint(v)
@@ -798,75 +800,6 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
     positionStepDir = p.ddu * dX.x + p.ddv * dX.y;
     return true;
 }
-// Manifolds.slangh:165-281 after the occluder chain has been collected (traceMNEEOccluders): the Newton / line-search walk.
-// It consumes no random numbers, so it runs in its own kernel (k_mnee_walk).  The reference's nested loops
-//     while (!success) { success = true; for (idx ...) { newton step; if (|C| < eps) continue; success = false; for (;;) { trial ray ... } } }
-// are unrolled into a resumable state machine whose unit of work ("trip") is at most one Newton step (phase A) followed by at
-// most one line-search trial ray (phase B): every lane of a warp then executes the same code for a different walk, and a lane
-// whose walk has ended takes the next parked walk at once instead of idling until the longest walk of its warp is over
-// (walk lengths range from 1 to MNEEMaxIterations trial rays).  Arithmetic and its order are the reference's.
-struct WalkState {
-    ManifoldSampleData ms;
-    float beta[kMaxMSHits];
-    float3 origin, lightPos, lightDir, stepDir;
-    uint32_t hitInstance;   // instance of the vertex the current line search moves (th.instanceID at Newton time)
-    int idx;                // vertex of the chain the current pass is at
-    bool distant, passSuccess, lineSearch;
-};
-enum { WALK_CONTINUE = 0, WALK_CONVERGED = 1, WALK_FAILED = -1 };
-PLT_D int manifoldWalkTrip(const FrameParams& P, TraversalCounters& tc, WalkState& w) {
-    ManifoldSampleData& data = w.ms;
-    if (!w.lineSearch) {  // ---- phase A: Newton step at vertex idx
-        if (w.idx == data.hitCount) {  // a pass over the chain is complete
-            if (w.passSuccess) return WALK_CONVERGED;
-            w.passSuccess = true; w.idx = 0;
-        }
-        const int idx = w.idx;
-        const TriHit th = unpackHit(P.sc, data.hits[idx].hit);
-        uint32_t materialID;
-        const VertexData v = getVertexData(P.sc, th, materialID);
-        const DiffGeom dsg = differentialShadingGeometry(P.sc, th);
-        const float3 p0 = idx == 0 ? w.origin : data.hits[idx - 1].posW;
-        const V3pdv pdvp0 = dsg.pdw(p0);
-        const float3 p2 = idx + 1 == data.hitCount ? w.lightPos : data.hits[idx + 1].posW;
-        V3pdv pdvp2;
-        pdvp2.v = w.lightDir; pdvp2.ddu = pdvp2.ddv = mk3(0.f);
-        if (!w.distant) pdvp2 = dsg.pdw(p2);
-        const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
-        const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
-        const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
-        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-        const SD sd = prepareShadingData(v, materialID, m, wiP.v);
-        const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, data.hits[idx].lobe, data.wavelength);
-        float lenC;
-        float3 positionStepDir;
-        if (allZero(wos.v)) return WALK_FAILED;
-        if (!manifoldOneStep(woP, wos, dsg.p, lenC, positionStepDir)) return WALK_FAILED;
-        if (lenC < P.opt.MNEESolverThreshold) { w.idx = idx + 1; return WALK_CONTINUE; }
-        w.passSuccess = false;
-        w.lineSearch = true;
-        w.stepDir = positionStepDir;
-        w.hitInstance = th.instanceID;
-    }
-    // ---- phase B: one trial ray of the line search at vertex idx
-    const int idx = w.idx;
-    if (++data.iterations > P.opt.MNEEMaxIterations) return WALK_FAILED;
-    const float3 p0 = idx == 0 ? w.origin : data.hits[idx - 1].posW;
-    const float3 proposal = data.hits[idx].posW - w.beta[idx] * w.stepDir;
-    float3 dirToProposal = proposal - p0;
-    const float dist = length(dirToProposal);
-    dirToProposal /= dist;
-    TriHit ph;
-    float pt;
-    const bool isHit = traceClosestHit(P, tc, p0, dirToProposal, fmaxf(kShadowRayTMin, .99f * dist), 1.01f * dist, ph, pt);
-    if (!isHit || w.hitInstance != ph.instanceID) { w.beta[idx] /= 4.f; return WALK_CONTINUE; }
-    data.hits[idx].hit = packHit(P.sc, ph);
-    data.hits[idx].posW = p0 + dirToProposal * pt;
-    w.beta[idx] = fminf(1.0f, 2.f * w.beta[idx]);
-    w.lineSearch = false;
-    w.idx = idx + 1;
-    return WALK_CONTINUE;
-}
 // Manifolds.slangh:80-93
 PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const ManifoldSampleData& r, float3 origin, Beam& beam) {
     for (int idx = r.hitCount - 1; idx >= 0; --idx) {
@@ -901,25 +834,100 @@ PLT_D void mneeUnpack(const MneeItem& it, ManifoldSampleData& ms) {
         ms.hits[i].lobe = __float_as_uint(it.posLobe[i].w);
     }
 }
-// k_mnee_walk, start of a parked walk
-PLT_D void mneeWalkInit(const MneeItem& it, WalkState& w) {
-    mneeUnpack(it, w.ms);
-    for (int i = 0; i < kMaxMSHits; ++i) w.beta[i] = 1.f;
-    w.origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z);
-    w.lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
-    w.lightDir = mk3(it.lightDirLsPdf.x, it.lightDirLsPdf.y, it.lightDirLsPdf.z);
-    w.stepDir = mk3(0.f); w.hitInstance = 0;
-    w.idx = 0; w.distant = (it.flags & MI_DISTANT) != 0; w.passSuccess = true; w.lineSearch = false;
-}
-// k_mnee_walk, end of a walk: the converged chain goes back into the item for k_mnee_finish; a failed walk contributes nothing
-PLT_D void mneeWalkStore(const FrameParams& P, MneeItem& it, const WalkState& w, bool converged) {
-    if (P.counters && w.ms.iterations) atomicAdd(P.counters + 3, (unsigned long long)w.ms.iterations);
-    if (!converged) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
-    for (int i = 0; i < w.ms.hitCount; ++i) {
-        it.hit[i] = w.ms.hits[i].hit;
-        it.posLobe[i] = mk4(w.ms.hits[i].posW.x, w.ms.hits[i].posW.y, w.ms.hits[i].posW.z, __uint_as_float(w.ms.hits[i].lobe));
+// ---- the manifold walk as a wavefront (k_mnee_walk) -------------------------------------------------------------------------
+// Manifolds.slangh:165-281 after the occluder chain has been collected (traceMNEEOccluders).  It consumes no random numbers, so
+// it runs in its own kernel.  The reference's nested loops
+//     while (!success) { success = true; for (idx ...) { newton step; if (|C| < eps) continue; success = false; for (;;) { trial ray ... } } }
+// are cut at the trial ray: mneeWalkAdvance() consumes the answer of the previous trial ray (accept / shrink the step), runs Newton
+// steps until the next trial ray is due, and posts it; the rays of all live walks are then traced together.  One round = one
+// trial ray per live walk, so every warp executes either Newton steps or traversal, never a mix, and walks that ended drop
+// out of the list (walk lengths range from 1 to MNEEMaxIterations trial rays).  Arithmetic and its order are the reference's.
+struct alignas(16) MneeWalk {
+    float4 beta;        // line-search step scale per chain vertex
+    float4 stepInst;    // positionStepDir.xyz | asfloat(instance of the vertex the line search moves)
+    float4 ray0, ray1;  // posted trial ray: p0 | tmin, direction | tmax
+    uint4 hit;          // its closest hit: instanceID (0xffffffff = none), primitiveIndex, asuint(u), asuint(v)
+    float t;
+    uint32_t state;     // idx[0:3] | passSuccess << 4
+    uint32_t iterations, pad;
+};
+enum { WALK_CONTINUE = 0, WALK_CONVERGED = 1, WALK_FAILED = -1 };
+PLT_D float betaGet(const float4& b, int i) { return lane(b, i); }
+PLT_D int mneeWalkAdvance(const FrameParams& P, MneeItem& it, MneeWalk& w, bool first) {
+    const int hitCount = int(it.flags & 0xfu);
+    const float3 origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z), lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
+    const float3 lightDir = mk3(it.lightDirLsPdf.x, it.lightDirLsPdf.y, it.lightDirLsPdf.z);
+    const bool distant = (it.flags & MI_DISTANT) != 0;
+    const float wavelength = it.lightPosWl.w;
+    int idx;
+    bool passSuccess, lineSearch = false;
+    float4 beta;
+    float3 stepDir = mk3(0.f);
+    uint32_t hitInstance = 0, iterations;
+    if (first) { idx = 0; passSuccess = true; beta = mk4(1.f); iterations = 0; }
+    else {
+        idx = int(w.state & 0xfu); passSuccess = (w.state & 16u) != 0; beta = w.beta; iterations = w.iterations;
+        stepDir = mk3(w.stepInst.x, w.stepInst.y, w.stepInst.z); hitInstance = __float_as_uint(w.stepInst.w);
+        // answer of the posted trial ray (Manifolds.slangh:236-250)
+        const uint4 ph = w.hit;
+        if (ph.x == 0xffffffffu || hitInstance != ph.x) { setLane(beta, idx, betaGet(beta, idx) / 4.f); lineSearch = true; }
+        else {
+            TriHit th;
+            th.instanceID = ph.x; th.primitiveIndex = ph.y; th.u = __uint_as_float(ph.z); th.v = __uint_as_float(ph.w);
+            const float3 p0 = mk3(w.ray0.x, w.ray0.y, w.ray0.z), dir = mk3(w.ray1.x, w.ray1.y, w.ray1.z);
+            const float3 np = p0 + dir * w.t;
+            it.hit[idx] = packHit(P.sc, th);
+            it.posLobe[idx] = mk4(np.x, np.y, np.z, it.posLobe[idx].w);
+            setLane(beta, idx, fminf(1.0f, 2.f * betaGet(beta, idx)));
+            idx += 1;
+        }
     }
-    it.flags |= MI_WALK_OK;
+    while (!lineSearch) {  // Newton steps until a vertex has to move
+        if (idx == hitCount) {  // a pass over the chain is complete
+            if (passSuccess) { w.iterations = iterations; return WALK_CONVERGED; }
+            passSuccess = true; idx = 0;
+        }
+        const TriHit th = unpackHit(P.sc, it.hit[idx]);
+        uint32_t materialID;
+        const VertexData v = getVertexData(P.sc, th, materialID);
+        const DiffGeom dsg = differentialShadingGeometry(P.sc, th);
+        const float4 prevP = it.posLobe[idx > 0 ? idx - 1 : 0], nextP = it.posLobe[idx + 1 < hitCount ? idx + 1 : idx];
+        const float3 p0 = idx == 0 ? origin : mk3(prevP.x, prevP.y, prevP.z);
+        const V3pdv pdvp0 = dsg.pdw(p0);
+        const float3 p2 = idx + 1 == hitCount ? lightPos : mk3(nextP.x, nextP.y, nextP.z);
+        V3pdv pdvp2;
+        pdvp2.v = lightDir; pdvp2.ddu = pdvp2.ddv = mk3(0.f);
+        if (!distant) pdvp2 = dsg.pdw(p2);
+        const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
+        const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
+        const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
+        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+        const SD sd = prepareShadingData(v, materialID, m, wiP.v);
+        const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, __float_as_uint(it.posLobe[idx].w), wavelength);
+        float lenC;
+        float3 positionStepDir;
+        if (allZero(wos.v) || !manifoldOneStep(woP, wos, dsg.p, lenC, positionStepDir)) { w.iterations = iterations; return WALK_FAILED; }
+        if (lenC < P.opt.MNEESolverThreshold) { idx += 1; continue; }
+        passSuccess = false;
+        lineSearch = true;
+        stepDir = positionStepDir;
+        hitInstance = th.instanceID;
+    }
+    // next trial ray of the line search at vertex idx (Manifolds.slangh:226-235)
+    if (++iterations > P.opt.MNEEMaxIterations) { w.iterations = iterations; return WALK_FAILED; }
+    const float4 prevP = it.posLobe[idx > 0 ? idx - 1 : 0], curP = it.posLobe[idx];
+    const float3 p0 = idx == 0 ? origin : mk3(prevP.x, prevP.y, prevP.z);
+    const float3 proposal = mk3(curP.x, curP.y, curP.z) - betaGet(beta, idx) * stepDir;
+    float3 dirToProposal = proposal - p0;
+    const float dist = length(dirToProposal);
+    dirToProposal /= dist;
+    w.beta = beta;
+    w.stepInst = mk4(stepDir.x, stepDir.y, stepDir.z, __uint_as_float(hitInstance));
+    w.ray0 = mk4(p0.x, p0.y, p0.z, fmaxf(kShadowRayTMin, .99f * dist));
+    w.ray1 = mk4(dirToProposal.x, dirToProposal.y, dirToProposal.z, 1.01f * dist);
+    w.state = uint32_t(idx) | (passSuccess ? 16u : 0u);
+    w.iterations = iterations;
+    return WALK_CONTINUE;
 }
 
 // k_mnee_finish (Manifolds.slangh:270-281, pltpt_solve.rt.slang:320-361): final visibility of the converged chain, replay of the

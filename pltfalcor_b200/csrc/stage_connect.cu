@@ -8,6 +8,8 @@
 //   k_mnee         : manifold walk (Newton + line search, data-dependent trip count) of the connections that crossed delta
 //                    occluders — isolated so that it cannot stall the coherent NEE work (north-star (d)).
 #include "plt_integrator.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #ifndef PLT_MINB_CONNECT_A
 #define PLT_MINB_CONNECT_A 1
@@ -102,53 +104,78 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b
     warpAdd(P.counters + 6, tc.tris);
 }
 
-// Manifold walks (Manifolds.slangh:165-281).  Pass 1: persistent lanes; a lane that has no walk takes the next parked one (one
-// warp-aggregated cursor bump per refill), then every lane runs ONE trip of its walk (manifoldWalkTrip).  Converged walks are
-// listed for pass 2.  The cursor and the list count live in queueCount[37..38] (zeroed per tile); the list reuses `sorted`, which
-// is idle until the first replay sort.
+// Manifold walks (Manifolds.slangh:165-281), pass 1: ONE cooperative launch that loops over rounds on the device (grid-wide
+// barriers instead of ~2 x MNEEMaxIterations host launches that would mostly be empty).  Round = { advance: consume the previous
+// trial ray's answer, Newton steps, post the next trial ray (mneeWalkAdvance) | barrier | trace the posted rays | barrier }.
+// Live walks are kept in two ping-pong lists, converged ones are listed for pass 2; the three list counts rotate through
+// queueCount[37..39] (zeroed per tile; the count two rounds back is re-zeroed by thread 0 while nobody reads it), the number
+// of converged walks is queueCount[40].
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(const __grid_constant__ FrameParams P) {
+    cg::grid_group grid = cg::this_grid();
     const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
-    uint32_t* cursor = P.queueCount + 38;
-    uint32_t* doneCount = P.queueCount + 37;
+    if (n == 0) return;  // grid-uniform
+    uint32_t* counts = P.queueCount + 37;
+    uint32_t* doneCount = P.queueCount + 40;
+    uint32_t* doneList = P.mneeLists + 2 * size_t(P.mneeCapacity);
+    const uint32_t tid = blockIdx.x * kStageThreads + threadIdx.x, stride = gridDim.x * kStageThreads;
     const int lane = threadIdx.x & 31;
     TraversalCounters tc = {0, 0};
-    WalkState w;
-    uint32_t item = 0;
-    bool have = false, exhausted = n == 0;
-    for (;;) {
-        const uint32_t idle = __ballot_sync(0xffffffffu, !have);
-        if (idle && !exhausted) {
-            const int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(cursor, uint32_t(__popc(idle)));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!have) {
-                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-                if (i < n) { item = i; mneeWalkInit(P.mneeItems[i], w); have = true; }
+    unsigned long long iterations = 0;
+    for (uint32_t round = 0;; ++round) {
+        const uint32_t* cur = P.mneeLists + size_t(round & 1u) * P.mneeCapacity;
+        uint32_t* next = P.mneeLists + size_t((round + 1u) & 1u) * P.mneeCapacity;
+        const uint32_t nCur = round == 0 ? n : counts[round % 3u];
+        uint32_t* nextCount = counts + (round + 1u) % 3u;
+        if (tid == 0) counts[(round + 2u) % 3u] = 0;
+        for (uint32_t base = blockIdx.x * kStageThreads; base < nCur; base += stride) {  // ---- advance
+            const uint32_t k = base + threadIdx.x;
+            int r = WALK_FAILED;
+            uint32_t item = 0;
+            const bool valid = k < nCur;
+            if (valid) {
+                item = round == 0 ? k : cur[k];
+                r = mneeWalkAdvance(P, P.mneeItems[item], P.mneeWalks[item], round == 0);
+                if (r != WALK_CONTINUE) {
+                    iterations += P.mneeWalks[item].iterations;
+                    if (r == WALK_FAILED) writeContribution(P, P.mneeItems[item].pixel, P.mneeItems[item].bounceIdx, 0, mk3(0.f));
+                }
             }
-            exhausted = base + __popc(idle) >= n;  // warp-uniform
+            // warp-aggregated appends to the two lists
+            const uint32_t go = __ballot_sync(0xffffffffu, valid && r == WALK_CONTINUE), ok = __ballot_sync(0xffffffffu, valid && r == WALK_CONVERGED);
+            uint32_t b0 = 0, b1 = 0;
+            if (lane == 0) { if (go) b0 = atomicAdd(nextCount, uint32_t(__popc(go))); if (ok) b1 = atomicAdd(doneCount, uint32_t(__popc(ok))); }
+            b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
+            const uint32_t below = (1u << lane) - 1u;
+            if (valid && r == WALK_CONTINUE) next[b0 + __popc(go & below)] = item;
+            if (valid && r == WALK_CONVERGED) doneList[b1 + __popc(ok & below)] = item;
         }
-        if (!__any_sync(0xffffffffu, have)) break;
-        if (have) {
-            const int r = manifoldWalkTrip(P, tc, w);
-            if (r != WALK_CONTINUE) {
-                mneeWalkStore(P, P.mneeItems[item], w, r == WALK_CONVERGED);
-                if (r == WALK_CONVERGED) P.sorted[atomicAdd(doneCount, 1u)] = item;
-                have = false;
-            }
+        grid.sync();
+        const uint32_t nNext = *nextCount;
+        if (nNext == 0) break;  // grid-uniform: every thread reads the same count after the barrier
+        for (uint32_t k = tid; k < nNext; k += stride) {  // ---- trace the posted trial rays
+            MneeWalk& w = P.mneeWalks[next[k]];
+            const float4 r0 = w.ray0, r1 = w.ray1;
+            TriHit th;
+            float t;
+            const bool hit = traceClosestHit(P, tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), r0.w, r1.w, th, t);
+            w.hit = hit ? make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+            w.t = t;
         }
+        grid.sync();
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
+    if (iterations) atomicAdd(P.counters + 3, iterations);
 }
 // Pass 2: converged walks, densely packed: final visibility, replay through the specular chain, MIS, hand-over to the unwind queues.
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(const __grid_constant__ FrameParams P) {
-    const uint32_t n = P.queueCount[37];
+    const uint32_t n = P.queueCount[40];
+    const uint32_t* doneList = P.mneeLists + 2 * size_t(P.mneeCapacity);
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
-        if (i < n) mneeFinish(P, P.mneeItems[P.sorted[i]], evals, tc);
+        if (i < n) mneeFinish(P, P.mneeItems[doneList[i]], evals, tc);
     }
     warpAdd(P.counters + 0, evals);
     warpAdd(P.counters + 5, tc.nodes);
@@ -156,7 +183,18 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(co
 }
 }  // namespace
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    k_mnee_walk<<<grid, kStageThreads, 0, s>>>(P);
+    // cooperative launch: every CTA must be resident, so the grid is what the device can hold of this kernel
+    static int perSm = 0, sms = 0;
+    if (!perSm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mnee_walk, kStageThreads, 0);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (perSm < 1) perSm = 1;
+    }
+    FrameParams Pc = P;
+    void* args[] = {&Pc};
+    cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk), dim3(uint32_t(perSm * sms)), dim3(kStageThreads), args, 0, s);
     k_mnee_finish<<<grid, kStageThreads, 0, s>>>(P);
 }
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }
