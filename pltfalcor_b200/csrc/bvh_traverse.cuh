@@ -67,29 +67,34 @@ struct Hit {
 
 constexpr int kTraversalStack = 160;
 
-// Walks the compressed wide BVH for one ray.  ANY = true: returns at the first accepted triangle.
-// `overflow` (optional) counts rays whose traversal stack overflowed (must stay 0; checked by the tests).
+// Traversal of the compressed wide BVH.  processNode() handles ONE popped node (children slab tests, leaf triangles, ordered push
+// of the inner children).  traverseBvh() runs a ray to completion in the calling thread; the trace kernels of non-trivial scenes
+// drive the same code through travPersistent(), where a lane whose ray has finished takes the next ray of the queue instead
+// of idling until the slowest ray of its warp is done.
+// ANY = true: finishes at the first accepted triangle.  `overflow` (optional) counts stack overflows (must stay 0; tests check).
 struct TraversalCounters { uint32_t nodes, tris; };
-template <bool ANY>
-PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr,
-                       TraversalCounters* tc = nullptr) {
-    best.instanceID = 0xffffffffu;
-    best.t = tmax;
-    const RayPrep rp = prepRay(o, d);
+struct RayConst {
+    RayPrep rp;
+    float3 o;
+    float idx, idy, idz, tmin, tmax;
+};
+PLT_D void rayConstInit(RayConst& R, float3 o, float3 d, float tmin, float tmax) {
+    R.rp = prepRay(o, d);
     const float tiny = 1e-30f;
-    const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    R.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+    R.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+    R.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    R.o = o; R.tmin = tmin; R.tmax = tmax;
+}
+// Returns true when ANY and a triangle was accepted.
+template <bool ANY>
+PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, const RayConst& R, uint32_t ni, Hit& best, uint32_t* stack, float* stackT, int& sp,
+                       uint32_t* overflow, TraversalCounters* tc) {
+    const float3 o = R.o;
+    const float idx = R.idx, idy = R.idy, idz = R.idz, tmin = R.tmin, tmax = R.tmax;
+    const RayPrep& rp = R.rp;
     const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
-    uint32_t stack[kTraversalStack];
-    float stackT[ANY ? 1 : kTraversalStack];  // entry distance of the pushed node: a closer hit found meanwhile culls it at pop time
-    int sp = 0;
-    stack[sp++] = 0;
-    if (!ANY) stackT[0] = tmin;
-    while (sp > 0) {
-        const uint32_t ni = stack[--sp];
-        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit below: exact-t ties are still visited)
-        if (tc) ++tc->nodes;
+    if (tc) ++tc->nodes;
         const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
         const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
         const uint32_t imask = n0.w >> 24;
@@ -157,8 +162,92 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
                 stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
             } else if (overflow) atomicAdd(overflow, 1u);
         }
+    return false;
+}
+template <bool ANY>
+PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr,
+                       TraversalCounters* tc = nullptr) {
+    best.instanceID = 0xffffffffu;
+    best.t = tmax;
+    RayConst R;
+    rayConstInit(R, o, d, tmin, tmax);
+    uint32_t stack[kTraversalStack];
+    float stackT[ANY ? 1 : kTraversalStack];  // entry distance of the pushed node: a closer hit found meanwhile culls it at pop time
+    int sp = 0;
+    stack[sp++] = 0;
+    if (!ANY) stackT[0] = tmin;
+    while (sp > 0) {
+        const uint32_t ni = stack[--sp];
+        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit: exact-t ties are still visited)
+        if (processNode<ANY>(nodes, tris, R, ni, best, stack, stackT, sp, overflow, tc)) return true;
     }
     return best.valid();
+}
+
+// Resumable form of the same loop for travPersistent().
+template <bool ANY>
+struct Trav {
+    RayConst R;
+    Hit best;
+    int sp;
+    uint32_t stack[kTraversalStack];
+    float stackT[ANY ? 1 : kTraversalStack];
+};
+template <bool ANY>
+PLT_D void travInit(Trav<ANY>& T, float3 o, float3 d, float tmin, float tmax) {
+    T.best.instanceID = 0xffffffffu;
+    T.best.t = tmax;
+    rayConstInit(T.R, o, d, tmin, tmax);
+    T.sp = 0;
+    T.stack[T.sp++] = 0;
+    if (!ANY) T.stackT[0] = tmin;
+}
+// One node; returns true when the ray is finished (stack empty, or ANY and a triangle was accepted).
+template <bool ANY>
+PLT_D bool travStep(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, Trav<ANY>& T, uint32_t* overflow, TraversalCounters* tc) {
+    if (T.sp <= 0) return true;
+    const uint32_t ni = T.stack[--T.sp];
+    if (!ANY && T.stackT[T.sp] > T.best.t * 1.000002f) return T.sp == 0;
+    if (processNode<ANY>(nodes, tris, T.R, ni, T.best, T.stack, T.stackT, T.sp, overflow, tc)) { T.sp = 0; return true; }
+    return T.sp == 0;
+}
+
+// Persistent-lane driver for a queue of `n` rays (Aila & Laine 2009, "Understanding the Efficiency of Ray Traversal on GPUs",
+// dynamic fetch): fetch(i, o, d, tmin, tmax) loads ray i (false: nothing to trace for this entry), commit(i, hit, best) consumes its
+// result.  Idle lanes refill from `cursor` (one warp-aggregated bump) once at least kRefillLanes lanes are idle; between refills
+// every lane with a ray processes kStepsPerRound nodes.  All 32 lanes of a warp must call this together.
+constexpr int kRefillLanes = 8, kStepsPerRound = 4;
+template <bool ANY, class Fetch, class Commit>
+PLT_D void travPersistent(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, uint32_t n, uint32_t* cursor, uint32_t* overflow, TraversalCounters* tc,
+                          Fetch fetch, Commit commit) {
+    const int lane = threadIdx.x & 31;
+    Trav<ANY> T;
+    T.sp = 0;
+    uint32_t item = 0;
+    bool have = false, exhausted = n == 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        if (!exhausted && (__popc(idle) >= kRefillLanes)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(cursor, uint32_t(__popc(idle)));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    float3 o, d;
+                    float tmin, tmax;
+                    if (fetch(i, o, d, tmin, tmax)) { item = i; travInit(T, o, d, tmin, tmax); have = true; }
+                }
+            }
+            exhausted = base + __popc(idle) >= n;  // warp-uniform
+        }
+        if (!__any_sync(0xffffffffu, have)) { if (exhausted) break; else continue; }
+#pragma unroll 1
+        for (int s = 0; s < kStepsPerRound; ++s) {
+            if (have && travStep(nodes, tris, T, overflow, tc)) { commit(item, T.best.valid(), T.best); have = false; }
+        }
+    }
 }
 
 }  // namespace plt

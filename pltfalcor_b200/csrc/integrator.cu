@@ -94,6 +94,7 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.useEmissive = c->opt.useEmissiveLights && c->emissiveTriangleCount > 0;
     P.useAnalytic = c->opt.useAnalyticLights && c->lightCount > 0;
     P.useEnv = c->opt.useEnvLights && c->scene.env.texels != nullptr;  // PLTPT.cpp:235
+    P.tinyScene = c->stats.bvhNodes < 256;
     P.doNEE = c->opt.doNEE != 0;
     P.doMS = P.doNEE && c->opt.doMNEE;
     P.doMIS = P.doNEE && c->opt.doMIS;

@@ -76,6 +76,7 @@ struct FrameParams {
                                    // [4] sum L(L-1)/2, [5] BVH nodes visited, [6] triangles tested, [7] unwind job steps
     // derived switches: pltpt.slangh:100-122 + PLTPT::getDefines (PLTPT.cpp:216-256)
     bool useEmissive, useAnalytic, useEnv, doNEE, doMS, doMIS, perTileSG;
+    bool tinyScene;          // BVH of a few nodes: the trace kernels skip the persistent-lane refill logic
     // environment-lit scenes: paths that left the scene, in the order the trace kernels found them (each pixel misses at most once)
     uint32_t* missList;      // [pixelCount] pixel | vertex index << 26
     uint32_t* missCount;
@@ -270,12 +271,11 @@ PLT_D void appendMiss(const FrameParams& P, uint32_t pixel, uint32_t vertexIndex
     base = __shfl_sync(active, base, leader);
     P.missList[base + __popc(active & ((1u << lane) - 1u))] = pixel | (vertexIndex << 26);
 }
-// TraceRay + scatterMiss (pltpt_sample.rt.slang:55-61,174-183).  Returns the MaterialType of the hit (0 = miss, path ended).
-PLT_D uint32_t tracePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc) {
-    const float4 o = P.psOrigin[pixel], d = P.psDir[pixel];
-    TriHit th;
-    float t;
-    if (!traceClosestHit(P, tc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.f, kFltMax, th, t)) {
+// TraceRay + scatterMiss (pltpt_sample.rt.slang:55-61,174-183), after the traversal: records the closest hit of the path's ray, or
+// ends the path with a miss record.  Returns the MaterialType of the hit (0 = miss, path ended).
+PLT_D uint32_t tracePathCommit(const FrameParams& P, uint32_t pixel, bool hit, const Hit& h) {
+    if (!hit) {
+        const float4 d = P.psDir[pixel];
         const float4 q = P.psPdf[pixel];
         const uint32_t fl = __float_as_uint(q.w);
         const uint32_t flags = (fl & ~0xff00u) | RF_Miss;
@@ -283,8 +283,8 @@ PLT_D uint32_t tracePath(const FrameParams& P, uint32_t pixel, TraversalCounters
         if (P.useEnv) appendMiss(P, pixel, (fl >> 8) & 0xffu);
         return 0u;
     }
-    P.psHit[pixel] = make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v));
-    const uint32_t materialID = __ldg(&P.sc.instances[th.instanceID].materialID);
+    P.psHit[pixel] = make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v));
+    const uint32_t materialID = __ldg(&P.sc.instances[h.instanceID].materialID);
     return __ldg(&P.sc.materials[materialID].type);
 }
 // scatterTriangleMeshClosestHit on the stored hit; returns true when the path continues with a new ray.

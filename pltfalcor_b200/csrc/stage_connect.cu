@@ -28,7 +28,7 @@ namespace {
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.levelCount[64] = 0;  // deferred-entry count of this level's half B
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.levelCount[64] = 0; P.queueCount[42] = 0; }  // deferred-entry count of this level's half B; shadow-trace fetch cursor
     uint32_t evals = 0, verts = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_miss(const __grid_con
     }
 }
 
-__global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace(const __grid_constant__ FrameParams P) {
+// Tiny scenes: one ray per thread per grid-stride iteration (see k_trace_simple).
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace_simple(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
@@ -68,6 +69,32 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
             P.shadowHits[i] = hit ? make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
             P.shadowT[i] = t;
         }
+    }
+    warpAdd(P.counters + 5, tc.nodes);
+    warpAdd(P.counters + 6, tc.tris);
+}
+
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace(const __grid_constant__ FrameParams P) {
+    const uint32_t n = P.levelCount[P.level];
+    TraversalCounters tc = {0, 0};
+    uint32_t* cursor = P.queueCount + 42;  // zeroed by k_connect_a of this level
+    uint32_t* overflow = reinterpret_cast<uint32_t*>(P.counters + 2);
+    auto fetch = [&](uint32_t i, float3& o, float3& d, float& tmin, float& tmax) {
+        if (!(P.connItems[i].info.y & CI_TRACE)) return false;
+        const float4 r0 = P.shadowRays[2 * size_t(i)], r1 = P.shadowRays[2 * size_t(i) + 1];
+        o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z); tmin = r0.w; tmax = r1.w;
+        return true;
+    };
+    // half A posts any-hit rays when no manifold walk can follow (MNEE off, or no bounce left for an occluder chain): uniform per launch
+    if (!P.doMS || int(P.opt.maxBounces) - int(P.level) <= 0) {
+        travPersistent<true>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch,
+            [&](uint32_t i, bool hit, const Hit&) { P.shadowHits[i] = make_uint4(hit ? 0u : 0xffffffffu, 0u, 0u, 0u); });
+    } else {
+        travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch,
+            [&](uint32_t i, bool hit, const Hit& h) {
+                P.shadowHits[i] = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+                P.shadowT[i] = h.t;
+            });
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
@@ -199,7 +226,10 @@ void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) {
 }
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }
 void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_a<<<grid, kStageThreads, 0, s>>>(P); }
-void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P); }
+void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.tinyScene) k_shadow_trace_simple<<<grid, kStageThreads, 0, s>>>(P);
+    else k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     k_connect_b<<<grid, kStageThreads, 0, s>>>(P);
     k_connect_b_slow<<<grid, kStageThreads, 0, s>>>(P);

@@ -21,9 +21,10 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ FramePar
     if (pixel < P.pixelCount) raygenPixel(P, pixel);
 }
 
-__global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const __grid_constant__ FrameParams P) {
+// Tiny scenes (a handful of BVH nodes: every ray of a warp walks the same two or three nodes) are faster without the refill
+// logic: one ray per thread per grid-stride iteration (Cornell box 1.27 vs 1.61 ms per frame; profiles/r1_kernel_times_scenes*.log).
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace_simple(const __grid_constant__ FrameParams P) {
     const bool primary = P.level == 0;
-    // bounce 0 walks the implicit queue of all pixels (8x4 tiles per warp, padded), later bounces the queue the shade kernel filled
     const uint32_t tilesX = (P.width + 7) / 8, tilesY = (P.tileRows + 3) / 4;
     const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[64];
     TraversalCounters tc = {0, 0};
@@ -32,10 +33,39 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const _
         uint32_t pixel = 0;
         const bool live = i < n && (primary ? primaryPixel(P, i, pixel) : (pixel = P.traceQueue[i], true));
         if (live) {
-            const uint32_t type = tracePath(P, pixel, tc);
+            const float4 o = P.psOrigin[pixel], d = P.psDir[pixel];
+            Hit h;
+            const bool hit = traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.f, kFltMax, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
+            const uint32_t type = tracePathCommit(P, pixel, hit, h);
             if (type != 0u) enqueueJob<false>(P, type, pixel);
         }
     }
+    warpAdd(P.counters + 5, tc.nodes);
+    warpAdd(P.counters + 6, tc.tris);
+}
+
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const __grid_constant__ FrameParams P) {
+    const bool primary = P.level == 0;
+    // bounce 0 walks the implicit queue of all pixels (8x4 tiles per warp, padded), later bounces the queue the shade kernel filled
+    const uint32_t tilesX = (P.width + 7) / 8, tilesY = (P.tileRows + 3) / 4;
+    const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[64];
+    TraversalCounters tc = {0, 0};
+    auto pixelOf = [&](uint32_t i, uint32_t& pixel) { return primary ? primaryPixel(P, i, pixel) : (pixel = P.traceQueue[i], true); };
+    // persistent lanes: a lane whose ray is done takes the next queue entry (cursor queueCount[41], re-zeroed by k_flip_queue)
+    travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, P.queueCount + 41, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
+        [&](uint32_t i, float3& o, float3& d, float& tmin, float& tmax) {
+            uint32_t pixel;
+            if (!pixelOf(i, pixel)) return false;
+            const float4 ro = P.psOrigin[pixel], rd = P.psDir[pixel];
+            o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z); tmin = 0.f; tmax = kFltMax;
+            return true;
+        },
+        [&](uint32_t i, bool hit, const Hit& h) {
+            uint32_t pixel;
+            pixelOf(i, pixel);
+            const uint32_t type = tracePathCommit(P, pixel, hit, h);
+            if (type != 0u) enqueueJob<false>(P, type, pixel);
+        });
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
 }
@@ -87,7 +117,10 @@ __global__ void k_gather_bounces(FrameParams P, PltptBounce* __restrict__ out, u
 }  // namespace
 
 void launchRaygen(const FrameParams& P, cudaStream_t s) { k_raygen<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
-void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_trace<<<grid, kStageThreads, 0, s>>>(P); }
+void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.tinyScene) k_trace_simple<<<grid, kStageThreads, 0, s>>>(P);
+    else k_trace<<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shade<<<grid, kStageThreads, 0, s>>>(P); }
 void launchGatherBounces(const FrameParams& P, PltptBounce* out, uint32_t records, cudaStream_t s) {
     k_gather_bounces<<<(P.pixelCount + 127) / 128, 128, 0, s>>>(P, out, records);

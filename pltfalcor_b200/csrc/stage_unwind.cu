@@ -59,7 +59,7 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *view.dstCount = qc[kQueueTypes];
         for (int t = 0; t <= 2 * kQueueTypes + 1; ++t) qc[t] = 0;
-        if (resetTraceQueue) P.levelCount[64] = 0;
+        if (resetTraceQueue) { P.levelCount[64] = 0; qc[41] = 0; }  // trace queue of the next bounce and the trace kernel's fetch cursor
     }
 }
 
