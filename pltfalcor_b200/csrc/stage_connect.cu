@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         uint32_t* next = P.mneeLists + size_t((round + 1u) & 1u) * P.mneeCapacity;
         const uint32_t nCur = round == 0 ? n : counts[round % 3u];
         uint32_t* nextCount = counts + (round + 1u) % 3u;
-        if (tid == 0) counts[(round + 2u) % 3u] = 0;
+        if (tid == 0) { counts[(round + 2u) % 3u] = 0; P.queueCount[43 + (round + 2u) % 3u] = 0; }
         for (uint32_t base = blockIdx.x * kStageThreads; base < nCur; base += stride) {  // ---- advance
             const uint32_t k = base + threadIdx.x;
             int r = WALK_FAILED;
@@ -179,15 +179,19 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         grid.sync();
         const uint32_t nNext = *nextCount;
         if (nNext == 0) break;  // grid-uniform: every thread reads the same count after the barrier
-        for (uint32_t k = tid; k < nNext; k += stride) {  // ---- trace the posted trial rays
-            MneeWalk& w = P.mneeWalks[next[k]];
-            const float4 r0 = w.ray0, r1 = w.ray1;
-            TriHit th;
-            float t;
-            const bool hit = traceClosestHit(P, tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), r0.w, r1.w, th, t);
-            w.hit = hit ? make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-            w.t = t;
-        }
+        // ---- trace the posted trial rays (persistent lanes; the fetch cursors rotate through queueCount[43..45] like the counts)
+        travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, nNext, P.queueCount + 43 + round % 3u, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
+            [&](uint32_t k, float3& o, float3& d, float& tmin, float& tmax) {
+                const MneeWalk& w = P.mneeWalks[next[k]];
+                const float4 r0 = w.ray0, r1 = w.ray1;
+                o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z); tmin = r0.w; tmax = r1.w;
+                return true;
+            },
+            [&](uint32_t k, bool hit, const Hit& h) {
+                MneeWalk& w = P.mneeWalks[next[k]];
+                w.hit = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+                w.t = h.t;
+            });
         grid.sync();
     }
     warpAdd(P.counters + 5, tc.nodes);
