@@ -242,6 +242,10 @@ void oracle_envmap_importance(void* sp, float* out) {
     std::memcpy(out, sc.env.mips[0].data(), sc.env.mips[0].size() * sizeof(float));
 }
 
+void oracle_colour_map(int which, uint32_t n, const float* vals, float* out) {  // 0 = ccMagma, 1 = ccInferno (plt_debug.h)
+    for (uint32_t i = 0; i < n; ++i) { const float3 c = which == 0 ? ccMagma(vals[i]) : ccInferno(vals[i]); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
+}
+
 int oracle_hardware_threads() { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 //   LightSampling.slangh, ShadowRays.slangh, Manifolds.slangh}
 #pragma once
 #include "plt_scene.h"
+#include "plt_debug.h"
 
 namespace orc {
 
@@ -172,7 +173,24 @@ struct Integrator {
         SampleGenerator sg, tilesg;
         float3 Lrgb, pathOrigin, pathNormal;
         float wavelength = 0;
+        float4 debugOutput = float4(0.f);  // Path.slang:204-220 (DO_DEBUG_VIEW)
     };
+    // pltpt_debug.slangh:19-29
+    void writeDebugOutput(uint32_t type, PLTSolve& solveData, float3 val) const {
+        if (opt.debugView == type && all_finite(val)) solveData.debugOutput += float4(val.x, val.y, val.z, 1.f);
+    }
+    // pltpt_debug.slangh:31-51
+    void markDebug(PLTSolve& solveData, int bounceIdx, const PLTBeam& beam) const {
+        if (std::isnan(solveData.Lrgb.x) || std::isnan(solveData.Lrgb.y) || std::isnan(solveData.Lrgb.z)) writeDebugOutput(DV_NaNs, solveData, float3(5, 0, 3));
+        if (std::isinf(solveData.Lrgb.x) || std::isinf(solveData.Lrgb.y) || std::isinf(solveData.Lrgb.z)) writeDebugOutput(DV_Inf, solveData, float3(2, 0, 5));
+        writeDebugOutput(DV_PathLength, solveData, ccMagma(bounceIdx / float(int(maxBounces()) - 1)));
+        writeDebugOutput(DV_HwssComps, solveData, ccMagma(beam.hwss_comps / float(hwss_samples())));
+        const float4 S(beam.L[0], beam.L1[0], beam.L2[0], beam.L3[0]);
+        const float cp = std::sqrt(sqr(S.w)) / S.x;
+        const float lp = std::sqrt(sqr(S.y) + sqr(S.z)) / S.x;
+        const float lpd = .5f * std::atan2(S.z, S.y);
+        writeDebugOutput(DV_Polarization, solveData, lp * float3(sqr(std::cos(lpd)), 0, sqr(std::sin(lpd))) + cp * float3(0, 1, 0));
+    }
     struct LightSample {  // LightsSamplingUtils.slang
         float pdf = 0;
         float3 origin;
@@ -469,6 +487,13 @@ struct Integrator {
     // pltpt_solve.rt.slang:96-147
     void measure(PLTSolve& solveData, int bounceIdx, float pathContribution, PLTBeam& beam) const {
         if (!opt.useDirectLights && bounceIdx <= 1) return;
+        if (opt.debugView) {  // pltpt_solve.rt.slang:100-106: coherence views before the propagation to the camera
+            const float k = k2Pi / (1e-3f * beam.wavelengths.x);
+            writeDebugOutput(DV_CoherenceArea, solveData, ccMagma(std::sqrt(beam.coherenceArea(k)) / 150.f));
+            float2x2 U, S;
+            svd_symmetric(beam.Theta.toInvCoherenceMat(k), U, S);
+            writeDebugOutput(DV_CoherenceAnisotropy, solveData, ccInferno(1.f - S.m[0][0] / S.m[1][1]));
+        }
         beam.propagate(camPos());
         if (cam.polarizer > .0f) {
             beam.rotateFrame(normalize(camU()), -normalize(camW()));
@@ -482,6 +507,7 @@ struct Integrator {
         } else pathContribution *= 1.f / float(beam.hwss_comps);
         const float3 Lrgb = vmax(float3(.0f), SpectrumUtils::spectrumToRgb(beam.L, beam.wavelengths, beam.hwss_comps) * pathContribution);
         if (all_finite(Lrgb)) solveData.Lrgb += Lrgb;
+        if (opt.debugView) markDebug(solveData, bounceIdx, beam);
     }
     // pltpt_solve.rt.slang:205-217
     bool wasNEEAvailable(int bounceIdx, RayFlags f) const {
@@ -775,6 +801,10 @@ struct Integrator {
             }
             const float3 origin = !currentVertexMS ? V.posW : solveData.pathOrigin;
             const bool mneeOk = manifoldNEESample(ls.origin, ls.dir, .0f, ls.distance, origin, ls.beam.posW, lightDir, ls.beam.distant, maxMSBounces, solveData.sg, msresult);
+            if (opt.debugView) {  // pltpt_solve.rt.slang:318-326
+                writeDebugOutput(DV_MneeIterations, solveData, ccInferno(msresult.iterations / float(opt.MNEEMaxIterations)));
+                if (msresult.hitCount > 0 && mneeOk) writeDebugOutput(DV_MneeBounces, solveData, msresult.hitCount == 1 ? float3(0, 0.3f, 1) : float3(1, 0, 0));
+            }
             if (!mneeOk || msresult.pdf < 1e-6f) return;
             if (msresult.hitCount > 0) {
                 if (!opt.HWSSDoMIS && msresult.dispersive) ls.beam.collapseToHeroWavelengthOnly();
@@ -818,12 +848,24 @@ struct Integrator {
             const BSDFProperties bsdfProp = bsdf.getProperties();
             if (kDoNEE()) NEE(solveData, p, bounce, px, py, triangleHit, sd, v, bsdf, bsdfProp);
             evalEmissive(solveData, p, bounce, px, py, bsdfProp, sd, triangleHit, opt.doImportanceSampleEmitters);
+            if (opt.debugView && p == 0) {  // pltpt_solve.rt.slang:450-457
+                writeDebugOutput(DV_Normals, solveData, sd.N);
+                writeDebugOutput(DV_Albedo, solveData, bsdfProp.albedo);
+                writeDebugOutput(DV_Roughness, solveData, float3(bsdfProp.roughness));
+                writeDebugOutput(DV_UVs, solveData, float3(sd.uv.x, 0, sd.uv.y));
+            }
             if (bf.terminated() || p == int(maxBounces())) break;
             solveData.pathOrigin = v.posW;
             solveData.pathNormal = sd.N;
         }
         const size_t o = (size_t(py) * width + px) * 4;
-        outColor[o] = solveData.Lrgb.x; outColor[o + 1] = solveData.Lrgb.y; outColor[o + 2] = solveData.Lrgb.z; outColor[o + 3] = 1.f;
+        float3 out = solveData.Lrgb;
+        if (opt.debugView) {  // pltpt_solve.rt.slang:470-475
+            const float4 dbg = solveData.debugOutput;
+            const float3 dv = dbg.w > .0f ? float3(dbg.x, dbg.y, dbg.z) / dbg.w : float3(.0f);
+            out = out + (dv - out) * opt.debugViewIntensity;
+        }
+        outColor[o] = out.x; outColor[o + 1] = out.y; outColor[o + 2] = out.z; outColor[o + 3] = 1.f;
     }
 };
 

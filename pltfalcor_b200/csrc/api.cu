@@ -31,6 +31,7 @@ static int validateOptions(const PltptOptions& o) {
     if (o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_UNIFORM && o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_POWER) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Unknown emissive light sampler type");  // PLTPT.cpp:409
     if (o.sampleGenerator != 1) return fail(PLTPT_ERR_UNSUPPORTED, "only SAMPLE_GENERATOR_UNIFORM (1) is supported");
     if (o.MNEEMaxOccluders > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "MNEEMaxOccluders must be <= 4");
+    if (o.debugView >= 14) return fail(PLTPT_ERR_INVALID_ARGUMENT, "debugView must be a DebugViewType (0..13)");  // DebugViewType.slangh:5-20
     return PLTPT_OK;
 }
 

@@ -93,7 +93,7 @@ struct PltptContext {
     static constexpr uint32_t kTimerRing = 256;
     static constexpr int kLanes = PLT_LANES;
     struct Lane {
-        plt::DevBuf work[32];                  // per-frame work buffers (integrator.cu)
+        plt::DevBuf work[40];                  // per-frame work buffers (integrator.cu)
         plt::DevBuf accum;                     // lane-private RGBA64F sums (lanes >= 1), merged into the caller's buffer at the end
         cudaStream_t stream = nullptr;         // own non-blocking stream (lanes >= 1)
         cudaEvent_t done = nullptr;

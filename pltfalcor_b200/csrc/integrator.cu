@@ -71,6 +71,13 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.queueCount = ln.work[14].as<uint32_t>();
     P.jobCount = P.queueCount + 32;
     P.contrib = ln.work[15].as<float4>();
+    P.debugView = c->opt.debugView;
+    P.debugIntensity = c->opt.debugViewIntensity;
+    P.debug = nullptr;
+    if (P.debugView) {  // debug views only: one event slot per connection slot
+        PLT_CUDA(ln.work[32].ensure(jobCapacity * sizeof(float4)));
+        P.debug = ln.work[32].as<float4>();
+    }
     P.psRng = ln.work[16].as<uint4>(); P.psOrigin = ln.work[17].as<float4>(); P.psDir = ln.work[18].as<float4>(); P.psPdf = ln.work[19].as<float4>();
     P.psHit = ln.work[20].as<uint4>(); P.ssRng = ln.work[21].as<uint4>(); P.ssTileRng = ln.work[22].as<uint4>();
     P.traceQueue = ln.work[4].as<uint32_t>();
@@ -119,6 +126,7 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
         if (timed) cudaEventRecord(ev[0], s);
         // ---- sample stage
         PLT_CUDA(cudaMemsetAsync(P.queueCount, 0, 256 * 4, s));
+        if (P.debug) PLT_CUDA(cudaMemsetAsync(P.debug, 0, size_t(P.jobCapacity) * sizeof(float4), s));  // slots without an event must read as none
         c->markKernel(0xff, s);
         launchRaygen(P, s);
         c->markKernel(PLTPT_K_RAYGEN, s);

@@ -7,6 +7,7 @@
 #pragma once
 #include "bvh_traverse.cuh"
 #include "plt_scene.cuh"
+#include "plt_debug.cuh"
 
 namespace plt {
 
@@ -67,7 +68,10 @@ struct FrameParams {
     float* shadowT;          // [pixelCount]
     uint32_t* mneeCount;
     uint32_t mneeCapacity;
-    float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection, summed in fixed order by the resolve kernel
+    float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection (w = 1: measure() ran), summed in fixed order by the resolve kernel
+    float4* debug;           // same shape: the debug-view event of that connection slot (value.rgb, 1); allocated and zeroed only when debugView != 0
+    uint32_t debugView;      // DebugViewType (0 = off), pltpt_debug.slangh
+    float debugIntensity;
     float4* color;     // RGBA32F (may be null when accum is used)
     float4* albedo;
     float4* normal;
@@ -644,9 +648,24 @@ PLT_D void forwardUnwindStep(const FrameParams& P, uint32_t& evals, const Vertex
     evals += uint32_t(beam.comps);
     if (P.opt.HWSSDoMIS) beam.spdf *= bsdfLambdaPdf(m, cx, sd, wo, lobe, beam, beam.wl);
 }
-// pltpt_solve.rt.slang:96-147: returns the RGB contribution of one connection
-PLT_D float3 measure(const FrameParams& P, int bounceIdx, float pathContribution, Beam& beam) {
-    if (!P.opt.useDirectLights && bounceIdx <= 1) return mk3(0.f);
+PLT_D bool finite3(float3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
+PLT_D void debugEvent(float4* dbg, float3 val) { if (dbg && finite3(val)) *dbg = mk4(val.x, val.y, val.z, 1.f); }  // writeDebugOutput, pltpt_debug.slangh:20-23
+// pltpt_solve.rt.slang:96-147: returns the RGB contribution of one connection (w = 1 unless the direct-light switch skipped it).
+// `dbg` (debug views on): receives the event of the selected view that measure() / markDebug() raise for this connection.
+PLT_D float4 measure(const FrameParams& P, int bounceIdx, float pathContribution, Beam& beam, float4* dbg = nullptr) {
+    if (dbg) *dbg = mk4(0.f);
+    if (!P.opt.useDirectLights && bounceIdx <= 1) return mk4(0.f);
+    if (dbg && (P.debugView == DV_CoherenceArea || P.debugView == DV_CoherenceAnisotropy)) {  // :100-106, before the propagation to the camera
+        const float k = k2Pi / (1e-3f * beam.wl.x);
+        const M22 iT = beam.invThetaK(k);
+        if (P.debugView == DV_CoherenceArea) debugEvent(dbg, ccMagma(sqrtf(kPi * sqrtf(1.f / (iT.a * iT.d - iT.b * iT.c))) / 150.f));
+        else {  // 1 - S00 / S11 of svd_symmetric (MathHelpers.slang:498-520)
+            const float a2 = sqr(iT.a), b2 = sqr(iT.c), c2 = sqr(iT.b), d2 = sqr(iT.d);
+            const float y = 2 * iT.a * iT.b + 2 * iT.c * iT.d, x = a2 + b2 - c2 - d2;
+            const float s1 = a2 + b2 + c2 + d2, s2 = sqrtf(sqr(x) + sqr(y));
+            debugEvent(dbg, ccInferno(1.f - sqrtf((s1 + s2) / 2.f) / sqrtf((s1 - s2) / 2.f)));
+        }
+    }
     beam.propagate(P.camPos);
     if (P.polarizer > .0f) {
         beam.rotateFrame(normalize(P.camU), -normalize(P.camW));
@@ -666,14 +685,33 @@ PLT_D float3 measure(const FrameParams& P, int bounceIdx, float pathContribution
         pathContribution *= sum > kFltEps ? beam.spdf.x / sum : .0f;
     } else pathContribution *= 1.f / float(beam.comps);
     const float3 Lrgb = vmax(mk3(.0f), spectrumToRgb(beam.L, beam.wl, beam.comps) * pathContribution);
-    return (isfinite(Lrgb.x) && isfinite(Lrgb.y) && isfinite(Lrgb.z)) ? Lrgb : mk3(0.f);
+    if (dbg) {  // markDebug, pltpt_debug.slangh:31-51 (the NaN / inf views need the running pixel sum: k_resolve raises them)
+        if (P.debugView == DV_PathLength) debugEvent(dbg, ccMagma(float(bounceIdx) / float(int(P.opt.maxBounces) - 1)));
+        else if (P.debugView == DV_HwssComps) debugEvent(dbg, ccMagma(float(beam.comps) / float(P.opt.HWSS)));
+        else if (P.debugView == DV_Polarization) {
+            const float4 S = mk4(beam.L.x, beam.L1.x, beam.L2.x, beam.L3.x);
+            const float cp = sqrtf(sqr(S.w)) / S.x, lp = sqrtf(sqr(S.y) + sqr(S.z)) / S.x, lpd = .5f * atan2f(S.z, S.y);
+            debugEvent(dbg, mk3(lp * sqr(cosf(lpd)), cp, lp * sqr(sinf(lpd))));
+        }
+    }
+    return finite3(Lrgb) ? mk4(Lrgb.x, Lrgb.y, Lrgb.z, 1.f) : mk4(0.f, 0.f, 0.f, 1.f);
 }
 PLT_D void writeContribution(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float3 rgb) {
     P.contrib[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = mk4(rgb.x, rgb.y, rgb.z, 0.f);
 }
+PLT_D void writeDebug(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float4 ev) {
+    if (ev.w != 0.f) P.debug[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = ev;
+}
+// measure() of a finished connection into its contribution (and debug) slot
+PLT_D void measureInto(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float pathContribution, Beam& beam) {
+    float4 ev;
+    const float4 c = measure(P, int(bounceIdx), pathContribution, beam, P.debugView ? &ev : nullptr);
+    P.contrib[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = c;
+    if (P.debugView) writeDebug(P, pixel, bounceIdx, kind, ev);
+}
 // Hands a sourced beam over to the unwind kernels (or measures it at once when nothing is left to replay).
 PLT_D void emitConnection(const FrameParams& P, uint32_t pixel, int bounceIdx, uint32_t kind, bool evalCurrentVertex, float pathContribution, Beam& beam) {
-    if (!evalCurrentVertex && bounceIdx == 0) { writeContribution(P, pixel, bounceIdx, kind, measure(P, bounceIdx, pathContribution, beam)); return; }
+    if (!evalCurrentVertex && bounceIdx == 0) { measureInto(P, pixel, uint32_t(bounceIdx), kind, pathContribution, beam); return; }
     const uint32_t id = allocJob(P);
     if (id >= P.jobCapacity) { atomicAdd(P.jobCount + 1, 1u); writeContribution(P, pixel, bounceIdx, kind, mk3(0.f)); return; }
     JobHeader h;
@@ -946,6 +984,7 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
         else { dir = lightDir; dist = kFltMax; }
         ms.woLastHitToLight = dir;
         if (occluded(P, tc, p, dir, kShadowRayTMin, dist)) { writeContribution(P, it.pixel, it.bounceIdx, 0, mk3(0.f)); return; }
+        if (P.debugView == DV_MneeBounces) { float4 ev = mk4(0.f); debugEvent(&ev, ms.hitCount == 1 ? mk3(0.f, 0.3f, 1.f) : mk3(1.f, 0.f, 0.f)); writeDebug(P, it.pixel, it.bounceIdx, 0, ev); }
     }
     Beam beam;
     JobHeader h;
@@ -1036,6 +1075,14 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
     const int p = int(P.level);
     ConnectCtx c;
     connectSetup(P, pixel, p, p == 0, c);
+    if (P.debugView && p == 0) {  // geometry views of the first vertex, pltpt_solve.rt.slang:450-457
+        float4 ev = mk4(0.f);
+        if (P.debugView == DV_Normals) debugEvent(&ev, c.sd.N);
+        else if (P.debugView == DV_Albedo) debugEvent(&ev, mk3(c.m.albx, c.m.alby, c.m.albz));
+        else if (P.debugView == DV_Roughness) debugEvent(&ev, mk3(c.m.roughnessProp));
+        else if (P.debugView == DV_UVs) debugEvent(&ev, mk3(c.sd.uv.x, 0.f, c.sd.uv.y));
+        writeDebug(P, pixel, 0, 1, ev);
+    }
     ConnItem item;
     item.dirPdf = mk4(0.f); item.info = make_uint4(0, 0, 0, 0);
     bool pending = false;
@@ -1115,6 +1162,8 @@ PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
             enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId, jobAux(pixel, uint32_t(p)));
         } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
         writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f));
+        // manifoldNEESample ran with nothing in the way: 0 iterations (pltpt_solve.rt.slang:318-322)
+        if (P.debugView == DV_MneeIterations && !(flags & CI_ANY_HIT)) { float4 ev = mk4(0.f); debugEvent(&ev, ccInferno(0.f)); writeDebug(P, pixel, uint32_t(p), 0, ev); }
         return false;
     }
     return true;
@@ -1152,6 +1201,8 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
             th.instanceID = hit.x; th.primitiveIndex = hit.y; th.u = __uint_as_float(hit.z); th.v = __uint_as_float(hit.w);
             ok = traceMNEEOccluders(P, c.st.tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.f, r1.w, c.st.sg, int(P.opt.maxBounces) - p, ms, &th, P.shadowT[slot]);
         }
+        // debug view: a chain that needs no walk (or cannot be walked) reports 0 iterations; parked walks report at their end
+        if (P.debugView == DV_MneeIterations && !(ok && ms.hitCount > 0 && ms.pdf >= 1e-6f)) { float4 ev = mk4(0.f); debugEvent(&ev, ccInferno(0.f)); writeDebug(P, pixel, uint32_t(p), 0, ev); }
         if (ok && ms.hitCount > 0) {
             // a manifold walk is needed: park the connection for k_mnee (it owns the contribution slot from here on)
             connected = true;
@@ -1212,7 +1263,7 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
     forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);
     if (h.q == 0) {
-        writeContribution(P, h.pixel, h.bounceIdx, h.kind, measure(P, int(h.bounceIdx), h.pathContribution, beam));
+        measureInto(P, h.pixel, h.bounceIdx, h.kind, h.pathContribution, beam);
         return false;
     }
     h.q -= 1; h.firstIsCurrent = false;
@@ -1225,16 +1276,32 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
 // Sums a pixel's connections in the order the reference adds them (bounce ascending, NEE before emissive).
 PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
     float3 L = mk3(0.f);
+    float4 dbg = mk4(0.f);
+    // one connection slot: add its RGB; debug views: add its event, and raise the NaN / inf events on the running sum after
+    // every connection measure() ran for (markDebug, pltpt_debug.slangh:34-38)
+    auto slot = [&](int p, int kind) {
+        const size_t o = size_t(2 * p + kind) * P.pixelCount + pixel;
+        const float4 c = __ldcs(P.contrib + o);
+        L += mk3(c.x, c.y, c.z);
+        if (P.debugView) {
+            if (P.debugView == DV_NaNs) { if (c.w != 0.f && (isnan(L.x) || isnan(L.y) || isnan(L.z))) dbg += mk4(5.f, 0.f, 3.f, 1.f); }
+            else if (P.debugView == DV_Inf) { if (c.w != 0.f && (isinf(L.x) || isinf(L.y) || isinf(L.z))) dbg += mk4(2.f, 0.f, 5.f, 1.f); }
+            else dbg += P.debug[o];
+        }
+    };
     for (int p = 0; p <= int(P.opt.maxBounces); ++p) {
         const uint32_t flags = __float_as_uint(P.bDir[size_t(p) * P.pixelCount + pixel].w);
         if (flags & RF_Miss) {
-            if (P.useEnv) { const float4 e = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel); L += mk3(e.x, e.y, e.z); }
+            if (P.useEnv) slot(p, 1);
             break;
         }
-        const float4 a = __ldcs(P.contrib + size_t(2 * p) * P.pixelCount + pixel), b = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel);
-        L += mk3(a.x, a.y, a.z);
-        L += mk3(b.x, b.y, b.z);
+        slot(p, 0);
+        slot(p, 1);
         if (flags & RF_Terminated) break;
+    }
+    if (P.debugView) {  // pltpt_solve.rt.slang:470-475
+        const float3 dv = dbg.w > 0.f ? mk3(dbg.x, dbg.y, dbg.z) / dbg.w : mk3(0.f);
+        L = L + (dv - L) * P.debugIntensity;
     }
     if (P.color) P.color[P.outOffset + pixel] = mk4(L.x, L.y, L.z, 1.f);
     if (P.accum) {

@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
                 r = mneeWalkAdvance(P, P.mneeItems[item], P.mneeWalks[item], round == 0);
                 if (r != WALK_CONTINUE) {
                     iterations += P.mneeWalks[item].iterations;
+                    if (P.debugView == DV_MneeIterations) {  // pltpt_solve.rt.slang:318-322
+                        float4 ev = mk4(0.f);
+                        debugEvent(&ev, ccInferno(float(P.mneeWalks[item].iterations) / float(P.opt.MNEEMaxIterations)));
+                        writeDebug(P, P.mneeItems[item].pixel, P.mneeItems[item].bounceIdx, 0, ev);
+                    }
                     if (r == WALK_FAILED) writeContribution(P, P.mneeItems[item].pixel, P.mneeItems[item].bounceIdx, 0, mk3(0.f));
                 }
             }
