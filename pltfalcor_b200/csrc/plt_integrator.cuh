@@ -703,11 +703,17 @@ PLT_D void writeDebug(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, 
     if (ev.w != 0.f) P.debug[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = ev;
 }
 // measure() of a finished connection into its contribution (and debug) slot
-PLT_D void measureInto(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float pathContribution, Beam& beam) {
+// The debug-view variant is kept out of line: with `dbg == nullptr` known at compile time the inlined measure() of the hot path
+// carries none of the view code (inlined both ways it cost k_unwind_step 5 %).
+static __device__ __noinline__ void measureIntoDebug(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float pathContribution, Beam beam) {  // beam by value: the caller's copy never has its address taken
     float4 ev;
-    const float4 c = measure(P, int(bounceIdx), pathContribution, beam, P.debugView ? &ev : nullptr);
+    const float4 c = measure(P, int(bounceIdx), pathContribution, beam, &ev);
     P.contrib[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = c;
-    if (P.debugView) writeDebug(P, pixel, bounceIdx, kind, ev);
+    writeDebug(P, pixel, bounceIdx, kind, ev);
+}
+PLT_D void measureInto(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx, uint32_t kind, float pathContribution, Beam& beam) {
+    if (P.debugView) { measureIntoDebug(P, pixel, bounceIdx, kind, pathContribution, beam); return; }
+    P.contrib[size_t(2 * bounceIdx + kind) * P.pixelCount + pixel] = measure(P, int(bounceIdx), pathContribution, beam, nullptr);
 }
 // Hands a sourced beam over to the unwind kernels (or measures it at once when nothing is left to replay).
 PLT_D void emitConnection(const FrameParams& P, uint32_t pixel, int bounceIdx, uint32_t kind, bool evalCurrentVertex, float pathContribution, Beam& beam) {
@@ -1070,19 +1076,21 @@ PLT_D void connectTail(const FrameParams& P, uint32_t pixel, int p, ConnectCtx& 
     if (!(c.bounce.flags & RF_Terminated) && p < int(P.opt.maxBounces)) storeSolveRng(P, pixel, c.st);
 }
 
+// geometry views of the first vertex, pltpt_solve.rt.slang:450-457
+static __device__ __noinline__ void firstVertexDebugViews(const FrameParams& P, uint32_t pixel, float3 N, float3 albedo, float roughness, float2 uv) {
+    float4 ev = mk4(0.f);
+    if (P.debugView == DV_Normals) debugEvent(&ev, N);
+    else if (P.debugView == DV_Albedo) debugEvent(&ev, albedo);
+    else if (P.debugView == DV_Roughness) debugEvent(&ev, mk3(roughness));
+    else if (P.debugView == DV_UVs) debugEvent(&ev, mk3(uv.x, 0.f, uv.y));
+    writeDebug(P, pixel, 0, 1, ev);
+}
 // Half A (pltpt_solve.rt.slang:245-300): light sample, beam sourcing, delta sample of the current vertex; posts the shadow ray.
 PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
     const int p = int(P.level);
     ConnectCtx c;
     connectSetup(P, pixel, p, p == 0, c);
-    if (P.debugView && p == 0) {  // geometry views of the first vertex, pltpt_solve.rt.slang:450-457
-        float4 ev = mk4(0.f);
-        if (P.debugView == DV_Normals) debugEvent(&ev, c.sd.N);
-        else if (P.debugView == DV_Albedo) debugEvent(&ev, mk3(c.m.albx, c.m.alby, c.m.albz));
-        else if (P.debugView == DV_Roughness) debugEvent(&ev, mk3(c.m.roughnessProp));
-        else if (P.debugView == DV_UVs) debugEvent(&ev, mk3(c.sd.uv.x, 0.f, c.sd.uv.y));
-        writeDebug(P, pixel, 0, 1, ev);
-    }
+    if (P.debugView && p == 0) firstVertexDebugViews(P, pixel, c.sd.N, mk3(c.m.albx, c.m.alby, c.m.albz), c.m.roughnessProp, c.sd.uv);
     ConnItem item;
     item.dirPdf = mk4(0.f); item.info = make_uint4(0, 0, 0, 0);
     bool pending = false;
@@ -1165,6 +1173,18 @@ PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
         // manifoldNEESample ran with nothing in the way: 0 iterations (pltpt_solve.rt.slang:318-322)
         if (P.debugView == DV_MneeIterations && !(flags & CI_ANY_HIT)) { float4 ev = mk4(0.f); debugEvent(&ev, ccInferno(0.f)); writeDebug(P, pixel, uint32_t(p), 0, ev); }
         return false;
+    }
+    // Blocked in manifold mode: the occluder chain can only start at a vertex that transmits through a delta lobe
+    // (Manifolds.slangh:128-141: the first test after the hit, before any random number is drawn).  An opaque first occluder --
+    // the usual case -- ends the connection here, from two table reads, without rebuilding the current vertex.
+    if (!(flags & (CI_CURRENT_MS | CI_EMISSIVE)) && blocked) {
+        const uint32_t occluderMaterial = __ldg(&P.sc.instances[P.shadowHits[slot].x].materialID);
+        if (P.opt.MNEEMaxOccluders == 0 || !(__ldg(&P.sc.materials[occluderMaterial].propFlags) & P_CanMSTransmissive)) {
+            writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
+            writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f));
+            if (P.debugView == DV_MneeIterations) { float4 ev = mk4(0.f); debugEvent(&ev, ccInferno(0.f)); writeDebug(P, pixel, uint32_t(p), 0, ev); }
+            return false;
+        }
     }
     return true;
 }
@@ -1274,20 +1294,18 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
 }
 
 // Sums a pixel's connections in the order the reference adds them (bounce ascending, NEE before emissive).
-PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
+// debug views on: the pixel's events are averaged in the reference's order; the NaN / inf views are raised on the running sum after
+// every connection measure() ran for (markDebug, pltpt_debug.slangh:34-38); final mix pltpt_solve.rt.slang:470-475
+static __device__ __noinline__ float3 resolvePixelDebug(const FrameParams& P, uint32_t pixel) {
     float3 L = mk3(0.f);
     float4 dbg = mk4(0.f);
-    // one connection slot: add its RGB; debug views: add its event, and raise the NaN / inf events on the running sum after
-    // every connection measure() ran for (markDebug, pltpt_debug.slangh:34-38)
     auto slot = [&](int p, int kind) {
         const size_t o = size_t(2 * p + kind) * P.pixelCount + pixel;
-        const float4 c = __ldcs(P.contrib + o);
+        const float4 c = P.contrib[o];
         L += mk3(c.x, c.y, c.z);
-        if (P.debugView) {
-            if (P.debugView == DV_NaNs) { if (c.w != 0.f && (isnan(L.x) || isnan(L.y) || isnan(L.z))) dbg += mk4(5.f, 0.f, 3.f, 1.f); }
-            else if (P.debugView == DV_Inf) { if (c.w != 0.f && (isinf(L.x) || isinf(L.y) || isinf(L.z))) dbg += mk4(2.f, 0.f, 5.f, 1.f); }
-            else dbg += P.debug[o];
-        }
+        if (P.debugView == DV_NaNs) { if (c.w != 0.f && (isnan(L.x) || isnan(L.y) || isnan(L.z))) dbg += mk4(5.f, 0.f, 3.f, 1.f); }
+        else if (P.debugView == DV_Inf) { if (c.w != 0.f && (isinf(L.x) || isinf(L.y) || isinf(L.z))) dbg += mk4(2.f, 0.f, 5.f, 1.f); }
+        else dbg += P.debug[o];
     };
     for (int p = 0; p <= int(P.opt.maxBounces); ++p) {
         const uint32_t flags = __float_as_uint(P.bDir[size_t(p) * P.pixelCount + pixel].w);
@@ -1299,10 +1317,24 @@ PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
         slot(p, 1);
         if (flags & RF_Terminated) break;
     }
-    if (P.debugView) {  // pltpt_solve.rt.slang:470-475
-        const float3 dv = dbg.w > 0.f ? mk3(dbg.x, dbg.y, dbg.z) / dbg.w : mk3(0.f);
-        L = L + (dv - L) * P.debugIntensity;
-    }
+    const float3 dv = dbg.w > 0.f ? mk3(dbg.x, dbg.y, dbg.z) / dbg.w : mk3(0.f);
+    return L + (dv - L) * P.debugIntensity;
+}
+PLT_D void resolvePixel(const FrameParams& P, uint32_t pixel) {
+    float3 L = mk3(0.f);
+    if (P.debugView) L = resolvePixelDebug(P, pixel);
+    else
+        for (int p = 0; p <= int(P.opt.maxBounces); ++p) {
+            const uint32_t flags = __float_as_uint(P.bDir[size_t(p) * P.pixelCount + pixel].w);
+            if (flags & RF_Miss) {
+                if (P.useEnv) { const float4 e = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel); L += mk3(e.x, e.y, e.z); }
+                break;
+            }
+            const float4 a = __ldcs(P.contrib + size_t(2 * p) * P.pixelCount + pixel), b = __ldcs(P.contrib + size_t(2 * p + 1) * P.pixelCount + pixel);
+            L += mk3(a.x, a.y, a.z);
+            L += mk3(b.x, b.y, b.z);
+            if (flags & RF_Terminated) break;
+        }
     if (P.color) P.color[P.outOffset + pixel] = mk4(L.x, L.y, L.z, 1.f);
     if (P.accum) {
         double* a = P.accum + 4 * size_t(P.outOffset + pixel);

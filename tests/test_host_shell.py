@@ -117,6 +117,37 @@ def test_render_through_plugin_matches_direct_c_abi(host, tmp_path, cornell, tor
 
 
 @pytest.mark.gpu
+def test_plugin_renders_env_lit_scene_and_debug_view(host, tmp_path, torch_cuda):
+    """The scene file's environment-map section reaches the plugin (Scene::useEnvLight), `useEnvLights` and `debugView` are honoured."""
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.env_scene()
+    w, h, frames = 96, 54, 2
+    path = tmp_path / "env.pltscn"
+    buffers.save(str(path), cam)
+    plugin, exe = host
+
+    def run(tag, *props):
+        args = [exe, "--plugin", plugin, "--scene", str(path), "--width", str(w), "--height", str(h), "--frames", str(frames), "--out", str(tmp_path / tag), "--prop", "maxBounces=6"]
+        for pr in props:
+            args += ["--prop", pr]
+        r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        return np.fromfile(tmp_path / (tag + ".color.f64"), np.float64).reshape(h, w, 4)
+
+    lit, dark, normals = run("lit"), run("dark", "useEnvLights=false"), run("nrm", "debugView=5")
+    for opts, got in ((dict(), lit), (dict(useEnvLights=False), dark), (dict(debugView=5), normals)):
+        p = binding.Pltpt(device=0, maxBounces=6, **opts)
+        p.set_scene(buffers)
+        acc = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+        p.render_accumulate(cam, 0, 1, frames, w, h, acc)
+        torch.cuda.synchronize()
+        assert np.allclose(got[..., :3], acc.cpu().numpy()[..., :3], rtol=1e-12, atol=0), opts
+        p.close()
+    assert (lit[:4, :, :3] > 0).all() and (dark[:4, :, :3] == 0).all()  # the top rows look at the sky
+
+
+@pytest.mark.gpu
 def test_plugin_reports_library_errors_as_exceptions(host, tmp_path, cornell, torch_cuda):
     """A failing C-ABI call surfaces as Falcor::RuntimeError (exit code 1 of the harness), e.g. the LightBVH sampler the pass does
     not offer: 'Unknown emissive light sampler type' (PLTPT.cpp:409)."""
