@@ -346,6 +346,44 @@ PLTPT_API int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const 
                                       uint32_t width, uint32_t height, PltptBounce* bouncesHost);
 
 /* ------------------------------------------------------------------------------------------
+ * Scene ingestion without Falcor (ours): what SceneBuilder / LightCollection / EmissivePowerSampler do on the
+ * host and in compute passes, so that a shell can go from `.spd` tables, PLT material parameters and emissive meshes to the
+ * buffers pltpt_set_scene takes.  Host pointers.
+ * ---------------------------------------------------------------------------------------- */
+/* PiecewiseLinearSpectrum::fromFile (Source/Falcor/Utils/Color/Spectrum.cpp:89-112): `lambda value` rows, '#' comments, stops at
+ * the first malformed row.  *count receives the number of rows (call with capacity 0 to size the buffers). */
+PLTPT_API int pltpt_spd_load(const char* path, float* wavelengths, float* values, uint32_t capacity, uint32_t* count);
+/* SampledSpectrum(PiecewiseLinearSpectrum) + genSpectralProfile (SampledSpectrum.h:57-68, SceneBuilder.cpp:911-960);
+ * computeICdf = 1 for emitters (normalised pdf + inverse cdf), 0 for IOR tables (raw values). */
+PLTPT_API int pltpt_gen_spectral_profile(uint32_t n, const float* wavelengths, const float* values, float scale, int computeICdf,
+                                         PltptSpectralProfile* out);
+/* Parameters of the ten PLT materials (Source/Falcor/Scene/Material/PLT/ *Material.h setters); unused fields are ignored. */
+typedef struct PltptMaterialParams {
+    uint32_t type;                 /* PLTPT_MATERIAL_* (DIFFUSE .. MULTILAYERED_STACK) */
+    uint32_t doubleSided;
+    float    color[3];             /* albedo (diffuse, opaque, coated opaque, grated opaque, stack) or specular tint (conductors, dielectric) */
+    uint32_t emissionSpectralId;   /* diffuse emitters; PLTPT_NO_SPECTRAL_PROFILE otherwise */
+    uint32_t iorNSpectralId, iorKSpectralId; /* conductors */
+    float    roughness, gamma;     /* surface roughness; K-correlation exponent (conductor) */
+    float    ior, extEta, dispersionB;
+    float    transmission[3];      /* dielectric */
+    float    tau, coatIor;         /* coating thickness in um (coated) / plate thickness in mm (thin dielectric); coat IOR */
+    float    birefringence, birefringenceScale, opticAxis[2]; /* thin dielectric */
+    float    gratingPitch[2], gratingDirection, gratingQ, gratingQScale, gratingPowerMultiplier; /* pitch in um */
+    uint32_t gratingType, gratingLobes;
+    float    layerThickness[2], layerIor[2]; /* multilayered stack, thickness in um */
+    uint32_t layers;
+} PltptMaterialParams;
+PLTPT_API int pltpt_pack_material(const PltptMaterialParams* params, PltptMaterialBlob* out);
+/* LightCollection (BuildTriangleList.cs.slang, FinalizeIntegration.cs.slang:64-110; on the GPU) + EmissivePowerSampler alias table
+ * (EmissivePowerSampler.cpp:86-170, without the final random permutation) of the scene held by `h`; replaces whatever tables
+ * pltpt_set_scene was given (they may have been NULL).  pltpt_get_light_collection copies the installed tables to host memory
+ * (any pointer may be NULL; *count = emissive triangles; perMeshInstanceOffset has instanceCount entries). */
+PLTPT_API int pltpt_build_light_collection(PltptHandle h);
+PLTPT_API int pltpt_get_light_collection(PltptHandle h, PltptEmissiveTriangle* triangles, PltptEmissiveFlux* flux, uint32_t* perMeshInstanceOffset,
+                                         uint32_t* aliasTable, float* invWeightsSum, uint32_t capacity, uint32_t* count);
+
+/* ------------------------------------------------------------------------------------------
  * Environment-map queries (parity checks of EnvMap.eval, EnvMap.slang:57-74, and EnvMapSampler.sample / evalPdf,
  * EnvMapSampler.slang:71-162).  Device pointers.  eval: n world directions float3 -> float4 {radiance rgb, pdf};
  * sample: n random pairs float2 -> 2 x float4 {dir xyz, pdf}, {Le rgb, 0}.  Fails when the scene has no env map.

@@ -16,6 +16,7 @@ EXPORTS = [
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
+    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection",
 ]
 
 
@@ -52,6 +53,11 @@ def lib():
         _lib.pltpt_reset_stats.argtypes = [vp]
         _lib.pltpt_set_profiling.argtypes = [vp, C.c_int]
         _lib.pltpt_set_frame_overlap.argtypes = [vp, C.c_int]
+        _lib.pltpt_spd_load.argtypes = [C.c_char_p, vp, vp, u32, vp]
+        _lib.pltpt_gen_spectral_profile.argtypes = [u32, vp, vp, f32, C.c_int, vp]
+        _lib.pltpt_pack_material.argtypes = [vp, vp]
+        _lib.pltpt_build_light_collection.argtypes = [vp]
+        _lib.pltpt_get_light_collection.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
     return _lib
@@ -68,6 +74,39 @@ def _hp(a):
 
 def _dp(t):
     return None if t is None else t.data_ptr()
+
+
+# ---- scene ingestion without Falcor (host-side entry points; no handle, no GPU) -------------------------------------------------
+def spd_load(path):
+    n = C.c_uint32()
+    _check(lib().pltpt_spd_load(str(path).encode(), None, None, 0, C.byref(n)))
+    w, v = np.zeros(n.value, np.float32), np.zeros(n.value, np.float32)
+    _check(lib().pltpt_spd_load(str(path).encode(), _hp(w), _hp(v), n.value, C.byref(n)))
+    return w, v
+
+
+def gen_spectral_profile(wavelengths, values, compute_icdf=True, scale=1.0):
+    w, v = np.ascontiguousarray(wavelengths, np.float32), np.ascontiguousarray(values, np.float32)
+    out = np.zeros((), L.spectral_profile_dtype)
+    _check(lib().pltpt_gen_spectral_profile(len(w), _hp(w), _hp(v), scale, int(compute_icdf), out.ctypes.data))
+    return out
+
+
+def pack_material(**params):
+    p = L.PltptMaterialParams()
+    p.emissionSpectralId = p.iorNSpectralId = p.iorKSpectralId = L.NO_SPECTRAL_PROFILE
+    p.color[:] = [1.0, 1.0, 1.0]
+    p.transmission[:] = [1.0, 1.0, 1.0]
+    p.extEta, p.ior, p.gamma, p.gratingQScale, p.gratingPowerMultiplier, p.birefringenceScale = 1.0, 1.5, 3.0, 1.0, 1.0, 1.0
+    for k, v in params.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            cur[:] = [float(x) for x in v]
+        else:
+            setattr(p, k, type(cur)(v))
+    out = np.zeros((), L.material_blob_dtype)
+    _check(lib().pltpt_pack_material(C.byref(p), out.ctypes.data))
+    return out
 
 
 class Pltpt:
@@ -150,6 +189,20 @@ class Pltpt:
 
     def trace_any(self, rays, occluded, stream=None):
         _check(lib().pltpt_trace_any(self.h, rays.shape[0], _dp(rays), _dp(occluded), stream))
+
+    # ---- light collection built by the library -------------------------------------------------------------------
+    def build_light_collection(self):
+        _check(lib().pltpt_build_light_collection(self.h))
+
+    def get_light_collection(self, instance_count):
+        n, inv = C.c_uint32(), C.c_float()
+        _check(lib().pltpt_get_light_collection(self.h, None, None, None, None, None, 0, C.byref(n)))
+        tris = np.zeros(n.value, L.emissive_triangle_dtype)
+        flux = np.zeros(n.value, L.emissive_flux_dtype)
+        offs = np.zeros(instance_count, np.uint32)
+        alias = np.zeros((n.value, 2), np.uint32)
+        _check(lib().pltpt_get_light_collection(self.h, _hp(tris), _hp(flux), _hp(offs), _hp(alias), C.byref(inv), n.value, C.byref(n)))
+        return dict(emissiveTriangles=tris, emissiveFlux=flux, perMeshInstanceOffset=offs, triangleAliasTable=alias, invWeightsSum=inv.value)
 
     # ---- environment map ------------------------------------------------------------------------------------
     def envmap_eval(self, dirs, out, stream=None):

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libpltpt.so")
-SOURCES = ["api.cu", "bvh.cu", "integrator.cu", "stage_sample.cu", "stage_connect.cu", "stage_unwind.cu"]
+SOURCES = ["api.cu", "bvh.cu", "integrator.cu", "stage_sample.cu", "stage_connect.cu", "stage_unwind.cu", "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 

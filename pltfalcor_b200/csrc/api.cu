@@ -416,6 +416,14 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
         for (uint32_t id : {dmats[i].emissionId, dmats[i].etaN, dmats[i].etaK})
             if (id != PLTPT_NO_SPECTRAL_PROFILE && id >= s->profileCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "spectral profile id out of range");
     }
+    h->hMaterialEmission.assign(mats.size(), PLTPT_NO_SPECTRAL_PROFILE);
+    h->hMaterialRgb.assign(mats.size() * 3, 0.f);
+    for (size_t i = 0; i < mats.size(); ++i) {
+        const uint32_t id = mats[i].emissionSpectralId;
+        if (id == PLTPT_NO_SPECTRAL_PROFILE || id >= profiles.size()) continue;
+        h->hMaterialEmission[i] = id;
+        for (int c = 0; c < 3; ++c) h->hMaterialRgb[3 * i + c] = profiles[id].rgb[c];
+    }
     std::vector<DevProfile> dprofiles(profiles.size());
     for (size_t i = 0; i < profiles.size(); ++i) repackProfile(profiles[i], dprofiles[i]);
 

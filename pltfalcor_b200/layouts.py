@@ -126,6 +126,18 @@ assert C.sizeof(PltptCameraData) == 656
 assert C.sizeof(PltptOptions) == 96
 
 
+class PltptMaterialParams(C.Structure):
+    """Parameters of the ten PLT materials for pltpt_pack_material (include/pltpt.h)."""
+    _fields_ = [
+        ("type", C.c_uint32), ("doubleSided", C.c_uint32), ("color", C.c_float * 3), ("emissionSpectralId", C.c_uint32),
+        ("iorNSpectralId", C.c_uint32), ("iorKSpectralId", C.c_uint32), ("roughness", C.c_float), ("gamma", C.c_float),
+        ("ior", C.c_float), ("extEta", C.c_float), ("dispersionB", C.c_float), ("transmission", C.c_float * 3),
+        ("tau", C.c_float), ("coatIor", C.c_float), ("birefringence", C.c_float), ("birefringenceScale", C.c_float), ("opticAxis", C.c_float * 2),
+        ("gratingPitch", C.c_float * 2), ("gratingDirection", C.c_float), ("gratingQ", C.c_float), ("gratingQScale", C.c_float), ("gratingPowerMultiplier", C.c_float),
+        ("gratingType", C.c_uint32), ("gratingLobes", C.c_uint32), ("layerThickness", C.c_float * 2), ("layerIor", C.c_float * 2), ("layers", C.c_uint32),
+    ]
+
+
 class PltptEnvMapData(C.Structure):
     """EnvMapData, Source/Falcor/Scene/Lights/EnvMapData.slang:36-43 (112 B); float3x4 row-major."""
     _fields_ = [("transform", C.c_float * 12), ("invTransform", C.c_float * 12), ("tint", C.c_float * 3), ("intensity", C.c_float)]

@@ -1,0 +1,160 @@
+"""Scene ingestion without Falcor (include/pltpt.h): `.spd` loader, SpectralProfile builder and PLT material packers
+of the C ABI against the harness / oracle restatements (CPU; these entry points need no GPU), the GPU-built LightCollection and
+alias table against the harness tables (GPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pltfalcor_b200 import layouts as L
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "spd_tables.json")
+
+
+@pytest.fixture(scope="module")
+def tables():
+    return json.load(open(GOLDEN))
+
+
+def _all_tables(t):
+    for name, tab in t["emission"].items():
+        yield "emission/" + name, tab["wavelengths"], tab["values"], True
+    for name, nk in t["ior"].items():
+        for part in ("eta", "k"):
+            yield f"ior/{name}.{part}", nk[part]["wavelengths"], nk[part]["values"], False
+
+
+def test_spd_loader_reads_what_the_harness_reads(tmp_path, tables):
+    from pltfalcor_b200 import binding, scene
+    name, w, v, _ = next(_all_tables(tables))
+    path = tmp_path / "lamp.spd"
+    with open(path, "w") as f:
+        f.write("# Wavelength (A)   Value\n\n")
+        for a, b in zip(w, v):
+            f.write(f"{a:.6f}\t{b:.9g}\n")
+        f.write("garbage row stops the parser\n1 2\n")
+    gw, gv = binding.spd_load(path)
+    hw, hv = scene.load_spd(str(path))
+    assert np.array_equal(gw, hw) and np.array_equal(gv, hv) and len(gw) == len(w)
+    with pytest.raises(binding.PltptError):
+        binding.spd_load(tmp_path / "missing.spd")
+
+
+def test_spectral_profiles_match_harness_and_oracle(tables, oracle):
+    import ctypes as C
+    from pltfalcor_b200 import binding, scene
+    n = 0
+    for name, w, v, icdf in _all_tables(tables):
+        for scale in (1.0, 0.02):
+            got = binding.gen_spectral_profile(w, v, icdf, scale)
+            want = scene.gen_spectral_profile(w, v, icdf, scale)
+            for k in ("bins", "minWavelength", "maxWavelength", "intensity"):
+                assert got[k] == want[k], (name, k)
+            assert np.array_equal(got["pdf"], want["pdf"]) and np.array_equal(got["icdf"], want["icdf"]), name
+            assert np.allclose(got["rgb"], want["rgb"], rtol=2e-6, atol=1e-9), name
+            orc = np.zeros((), L.spectral_profile_dtype)
+            wa, va = np.asarray(w, np.float32), np.asarray(v, np.float32)
+            oracle.lib().oracle_gen_spectral_profile(C.c_uint32(len(wa)), wa.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p), C.c_float(scale), C.c_int(int(icdf)),
+                                                     orc.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(got["pdf"], orc["pdf"]) and np.array_equal(got["icdf"], orc["icdf"]) and got["bins"] == orc["bins"], name
+            n += 1
+    assert n >= 6
+
+
+def test_material_packers_are_byte_identical_to_the_harness():
+    from pltfalcor_b200 import binding, scene
+    b = scene.SceneBuilder()
+    T = L
+    cases = [
+        (b.add_diffuse((0.6, 0.4, 0.2)), dict(type=T.MATERIAL_DIFFUSE, color=(0.6, 0.4, 0.2))),
+        (b.add_diffuse((0, 0, 0), emission_profile=3, double_sided=True), dict(type=T.MATERIAL_DIFFUSE, color=(0, 0, 0), emissionSpectralId=3, doubleSided=1)),
+        (b.add_conductor((4, 5), 0.3, 3.0), dict(type=T.MATERIAL_CONDUCTOR, iorNSpectralId=4, iorKSpectralId=5, roughness=0.3, gamma=3.0)),
+        (b.add_dielectric(1.5, 0.1, dispersion_b=0.01, transmission=(0.9, 0.8, 0.7)), dict(type=T.MATERIAL_DIELECTRIC, ior=1.5, roughness=0.1, dispersionB=0.01, transmission=(0.9, 0.8, 0.7))),
+        (b.add_opaque_dielectric((0.3, 0.5, 0.7), 0.05), dict(type=T.MATERIAL_OPAQUE_DIELECTRIC, color=(0.3, 0.5, 0.7), roughness=0.05)),
+        (b.add_thin_dielectric(1.5, 0.3, birefringence=0.1), dict(type=T.MATERIAL_THIN_DIELECTRIC, ior=1.5, tau=0.3, birefringence=0.1, opticAxis=(0.15, 0.04))),
+        (b.add_coated_conductor((1, 2), 0.05, tau_um=3.0, coat_ior=1.5), dict(type=T.MATERIAL_COATED_CONDUCTOR, iorNSpectralId=1, iorKSpectralId=2, roughness=0.05, tau=3.0, coatIor=1.5)),
+        (b.add_coated_opaque_dielectric((0.7, 0.2, 0.2), 0.05, tau_um=3.0, coat_ior=1.5), dict(type=T.MATERIAL_COATED_OPAQUE_DIELECTRIC, color=(0.7, 0.2, 0.2), roughness=0.05, tau=3.0, coatIor=1.5)),
+        (b.add_grated_conductor((1, 2), (3.0, 0.0), q=0.15, q_scale=0.5, roughness=0.05, lobes=3),
+         dict(type=T.MATERIAL_GRATED_CONDUCTOR, iorNSpectralId=1, iorKSpectralId=2, gratingPitch=(3.0, 0.0), gratingQ=0.15, gratingQScale=0.5, roughness=0.05, gratingLobes=3)),
+        (b.add_grated_opaque_dielectric((0.5, 0.5, 0.5), (2.0, 2.0), q=0.2, gtype=1, lobes=4),
+         dict(type=T.MATERIAL_GRATED_OPAQUE_DIELECTRIC, color=(0.5, 0.5, 0.5), gratingPitch=(2.0, 2.0), gratingQ=0.2, gratingType=1, gratingLobes=4)),
+        (b.add_multilayered_stack((1, 1, 1), layers=6), dict(type=T.MATERIAL_MULTILAYERED_STACK, layers=6, layerThickness=(0.1, 0.15), layerIor=(1.38, 2.3))),
+    ]
+    for idx, params in cases:
+        want, got = b.materials[idx], binding.pack_material(**params)
+        assert got.tobytes() == want.tobytes(), (params, [(k, got[k], want[k]) for k in want.dtype.names if not np.array_equal(got[k], want[k])])
+    with pytest.raises(binding.PltptError):
+        binding.pack_material(type=1)  # MaterialType::Standard is not a PLT material
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell", "layered"])
+def test_gpu_light_collection_matches_the_harness_tables(name, torch_cuda):
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = {"cornell": scene.cornell_box, "layered": scene.layered_stress_scene}[name]()
+    n_inst = buffers.scalars["instanceCount"]
+    p = binding.Pltpt(maxBounces=4)
+    p.set_scene(buffers)
+    given = p.get_light_collection(n_inst)
+    w, h = 96, 54
+    ref = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 2, w, h, ref)
+    p.build_light_collection()
+    built = p.get_light_collection(n_inst)
+    assert len(built["emissiveTriangles"]) == len(given["emissiveTriangles"]) == buffers.scalars["emissiveTriangleCount"] > 0
+    assert np.array_equal(built["perMeshInstanceOffset"], given["perMeshInstanceOffset"])
+    a, b = built["emissiveTriangles"], given["emissiveTriangles"]
+    assert np.allclose(a["posAndTexCoords"][..., :3], b["posAndTexCoords"][..., :3], rtol=1e-6, atol=1e-6)  # fp32 transform (reference) vs the harness's fp64
+    assert np.array_equal(a["posAndTexCoords"][..., 3].view(np.uint32), b["posAndTexCoords"][..., 3].view(np.uint32))  # fp16 uv pairs
+    assert np.array_equal(a["materialID"], b["materialID"])
+    assert np.allclose(a["area"].view(np.float32), b["area"].view(np.float32), rtol=1e-5)
+    da, db = (a["normal"] & 0xffff).astype(np.int32), (b["normal"] & 0xffff).astype(np.int32)
+    assert np.abs(((da - db + 32768) % 65536) - 32768).max() <= 1  # 16-bit snorm octahedral, one quantisation step
+    assert np.allclose(built["emissiveFlux"]["flux"], given["emissiveFlux"]["flux"], rtol=1e-5)
+    assert built["invWeightsSum"] == pytest.approx(given["invWeightsSum"], rel=1e-5)
+    # the alias table induces the flux pdf (EmissivePowerSampler.slang:64-90): p(i) = (threshold_i + sum of redirected remainders) / N
+    t = built["triangleAliasTable"]
+    thr = (t[:, 0] >> 16).astype(np.uint16).view(np.float16).astype(np.float64)
+    redirect = ((t[:, 0] & 0xffff) << 8) | (t[:, 1] >> 24)
+    own = t[:, 1] & 0xffffff
+    N = len(t)
+    pdf = np.zeros(N)
+    np.add.at(pdf, own, thr / N)
+    np.add.at(pdf, redirect, (1 - thr) / N)
+    flux = built["emissiveFlux"]["flux"].astype(np.float64)
+    assert np.allclose(pdf, flux / flux.sum(), atol=2e-3)
+    # rendering with the tables the library built == rendering with the tables Falcor (the harness) would hand over
+    out = torch.zeros_like(ref)
+    p.render_accumulate(cam, 0, 1, 2, w, h, out)
+    torch.cuda.synchronize()
+    d = (out[..., :3] - ref[..., :3]).abs().cpu().numpy()
+    assert (d <= 1e-3 * np.maximum(ref[..., :3].cpu().numpy(), 1e-3)).mean() >= 0.97
+    p.close()
+
+
+@pytest.mark.gpu
+def test_gpu_scene_without_light_tables_gets_them_from_the_library(torch_cuda):
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.cornell_box()
+    bare = scene.SceneBuffers({k: (None if k in ("emissiveTriangles", "emissiveFlux", "activeTriangles", "perMeshInstanceOffset", "triangleAliasTable") else v)
+                               for k, v in buffers.arrays.items()}, dict(buffers.scalars, emissiveTriangleCount=0, invWeightsSum=0.0))
+    p = binding.Pltpt(maxBounces=4)
+    p.set_scene(bare)
+    w, h = 64, 36
+    dark = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 2, w, h, dark)
+    p.build_light_collection()
+    lit = torch.zeros_like(dark)
+    p.render_accumulate(cam, 0, 1, 2, w, h, lit)
+    torch.cuda.synchronize()
+    assert float(dark[..., :3].sum()) == 0.0 and float(lit[..., :3].mean()) > 0
+    full = binding.Pltpt(maxBounces=4)
+    full.set_scene(buffers)
+    ref = torch.zeros_like(dark)
+    full.render_accumulate(cam, 0, 1, 2, w, h, ref)
+    torch.cuda.synchronize()
+    assert abs(float(lit[..., :3].mean()) / float(ref[..., :3].mean()) - 1) < 0.02
+    p.close(); full.close()
