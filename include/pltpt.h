@@ -383,6 +383,12 @@ PLTPT_API int pltpt_build_light_collection(PltptHandle h);
 PLTPT_API int pltpt_get_light_collection(PltptHandle h, PltptEmissiveTriangle* triangles, PltptEmissiveFlux* flux, uint32_t* perMeshInstanceOffset,
                                          uint32_t* aliasTable, float* invWeightsSum, uint32_t capacity, uint32_t* count);
 
+/* Animated instance transforms: new world / inverse-transpose matrices (float4x4 row-major per matrixID, like PltptSceneDesc) for
+ * the scene held by `h`.  Replaces the TLAS refit / rebuild Falcor does on demand (Source/Falcor/Scene/Scene.cpp:3624-3700): the
+ * single world-space BVH is rebuilt on the GPU, and a library-built light collection is re-derived. */
+PLTPT_API int pltpt_update_transforms(PltptHandle h, const float* worldMatrices, const float* inverseTransposeWorldMatrices, uint32_t matrixCount,
+                                      uint32_t pointersAreDevice);
+
 /* ------------------------------------------------------------------------------------------
  * Environment-map queries (parity checks of EnvMap.eval, EnvMap.slang:57-74, and EnvMapSampler.sample / evalPdf,
  * EnvMapSampler.slang:71-162).  Device pointers.  eval: n world directions float3 -> float4 {radiance rgb, pdf};

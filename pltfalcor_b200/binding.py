@@ -16,7 +16,7 @@ EXPORTS = [
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
-    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection",
+    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms",
 ]
 
 
@@ -57,6 +57,7 @@ def lib():
         _lib.pltpt_gen_spectral_profile.argtypes = [u32, vp, vp, f32, C.c_int, vp]
         _lib.pltpt_pack_material.argtypes = [vp, vp]
         _lib.pltpt_build_light_collection.argtypes = [vp]
+        _lib.pltpt_update_transforms.argtypes = [vp, vp, vp, u32, u32]
         _lib.pltpt_get_light_collection.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
@@ -189,6 +190,11 @@ class Pltpt:
 
     def trace_any(self, rays, occluded, stream=None):
         _check(lib().pltpt_trace_any(self.h, rays.shape[0], _dp(rays), _dp(occluded), stream))
+
+    def update_transforms(self, world, world_it):
+        """world, world_it: (n,4,4) float32 host arrays (row-major), like SceneBuffers.arrays['worldMatrices']."""
+        world, world_it = np.ascontiguousarray(world, np.float32), np.ascontiguousarray(world_it, np.float32)
+        _check(lib().pltpt_update_transforms(self.h, _hp(world), _hp(world_it), len(world), 0))
 
     # ---- light collection built by the library -------------------------------------------------------------------
     def build_light_collection(self):

@@ -388,6 +388,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     PLT_CUDA(cudaSetDevice(h->device));
     h->hasScene = false;
+    h->ownLightCollection = false;
     const bool dev = s->pointersAreDevice != 0;
     if (s->instanceCount == 0 || s->vertexCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no geometry");
     if (s->hitInfoTypeBits == 0 || s->hitInfoTypeBits > 8) return fail(PLTPT_ERR_INVALID_ARGUMENT, "hitInfoTypeBits out of range");

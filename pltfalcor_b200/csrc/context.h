@@ -88,6 +88,7 @@ struct PltptContext {
     std::vector<uint32_t> hInstTriOffset;
     std::vector<uint32_t> hMaterialEmission;  // emissionSpectralId per material (pltpt_build_light_collection)
     std::vector<float> hMaterialRgb;           // rgb of that emission profile, 3 per material
+    bool ownLightCollection = false;           // the light collection was built by pltpt_build_light_collection
     uint32_t emissiveTriangleCount = 0, lightCount = 0;
     // Frame lanes: frames are independent (every random number derives from (pixel, frameCount), pltpt_sample.rt.slang:154), so
     // pltpt_render_accumulate keeps two frames in flight on two streams, each with its own work buffers, counters and timers: the

@@ -376,6 +376,28 @@ extern "C" int pltpt_build_light_collection(PltptHandle h) {
     h->scene.activeTris = h->activeTris.as<uint32_t>();
     h->scene.alias = h->alias.as<uint2>();
     h->scene.invWeightsSum = 1.0f / weightSum;
+    h->ownLightCollection = true;
+    return PLTPT_OK;
+}
+
+// Animated instance transforms (the reference refits / rebuilds its TLAS on demand, Source/Falcor/Scene/Scene.cpp:3624-3700; geometry
+// here lives in ONE world-space BVH, and a full GPU rebuild of 10 M triangles takes ~30 ms, so "refit" is a rebuild): new world and
+// inverse-transpose matrices for the scene held by `h`, BVH rebuilt, and -- when the library built the light collection itself --
+// the emissive triangles re-derived.  A light collection supplied by the caller is the caller's to refresh (pltpt_set_scene).
+extern "C" int pltpt_update_transforms(PltptHandle h, const float* worldMatrices, const float* inverseTransposeWorldMatrices, uint32_t matrixCount, uint32_t pointersAreDevice) {
+    if (!h || !worldMatrices || !inverseTransposeWorldMatrices) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->hasScene) return ifail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (size_t(matrixCount) * 64 != h->world.bytes && size_t(matrixCount) * 64 > h->world.bytes) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "matrixCount exceeds the scene's matrix table");
+    for (const auto& gi : h->hInstances)
+        if (gi.globalMatrixID >= matrixCount) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "an instance refers to a matrix beyond matrixCount");
+    PLT_CUDA(cudaSetDevice(h->device));
+    if (int r = syncFrameStats(h)) return r;  // frames in flight read the old BVH
+    PLT_CUDA(cudaDeviceSynchronize());
+    const cudaMemcpyKind kind = pointersAreDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    PLT_CUDA(cudaMemcpy(h->world.p, worldMatrices, size_t(matrixCount) * 64, kind));
+    PLT_CUDA(cudaMemcpy(h->worldIT.p, inverseTransposeWorldMatrices, size_t(matrixCount) * 64, kind));
+    if (int r = buildBvh(h, 0)) return r;
+    if (h->ownLightCollection) return pltpt_build_light_collection(h);
     return PLTPT_OK;
 }
 

@@ -123,3 +123,44 @@ def test_single_triangle_and_tiny_scenes(torch_cuda, oracle):
         assert np.array_equal(hits, ref_hits) and np.array_equal(t, ref_t), n_tris
         assert (hits[:, 0] != 0xFFFFFFFF).any()
         p.close()
+
+
+def binding_scene(binding, buffers):
+    h = binding.Pltpt(maxBounces=4)
+    h.set_scene(buffers)
+    return h
+
+
+def test_updated_transforms_equal_a_scene_built_with_them(torch_cuda, oracle):
+    """pltpt_update_transforms (animated instances; the reference refits its TLAS, Scene.cpp:3624-3700): after moving two meshes the
+    BVH answers exactly like the BVH of a scene created with the moved meshes, and the library-built light collection follows."""
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.cornell_box()
+    moved = np.array(buffers.arrays["worldMatrices"], copy=True)
+    moved[6, :3, 3] += np.float32([0.25, 0.1, -0.2])      # the gold box
+    moved[5, :3, 3] += np.float32([0.3, -0.4, 0.1])       # the emitter quad
+    moved_it = np.stack([np.linalg.inv(m.astype(np.float64)).T for m in moved]).astype(np.float32)
+    target = scene.SceneBuffers(dict(buffers.arrays, worldMatrices=moved, inverseTransposeWorldMatrices=moved_it), buffers.scalars)
+    rays = np.concatenate([parity.camera_rays(cam, 128, 72), parity.random_rays(np.random.default_rng(5), target, 8000)])
+    p, q = binding.Pltpt(maxBounces=4), binding.Pltpt(maxBounces=4)
+    p.set_scene(buffers)
+    p.build_light_collection()
+    p.update_transforms(moved, moved_it)
+    q.set_scene(target)
+    q.build_light_collection()
+    hp, tp, op = _trace_gpu(torch, p, rays)
+    hq, tq, oq = _trace_gpu(torch, q, rays)
+    assert np.array_equal(hp, hq) and np.array_equal(tp.view(np.uint32), tq.view(np.uint32)) and np.array_equal(op, oq)
+    ref_hits, ref_t = oracle.OracleScene(target).trace_closest(rays, brute=True)
+    assert np.array_equal(hp, ref_hits) and np.array_equal(tp.view(np.uint32), ref_t.view(np.uint32))
+    unmoved, _, _ = _trace_gpu(torch, binding_scene(binding, buffers), rays)
+    assert (unmoved != hp).any()  # the move is visible to the ray set
+    n = buffers.scalars["instanceCount"]
+    a, b = p.get_light_collection(n), q.get_light_collection(n)
+    assert a["emissiveTriangles"].tobytes() == b["emissiveTriangles"].tobytes() and a["triangleAliasTable"].tobytes() == b["triangleAliasTable"].tobytes()
+    img = [torch.zeros((54, 96, 4), dtype=torch.float64, device="cuda") for _ in range(2)]
+    p.render_accumulate(cam, 0, 1, 2, 96, 54, img[0]); q.render_accumulate(cam, 0, 1, 2, 96, 54, img[1])
+    torch.cuda.synchronize()
+    assert torch.equal(img[0], img[1])
+    p.close(); q.close()
