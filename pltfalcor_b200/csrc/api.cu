@@ -64,6 +64,7 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     for (auto& ln : h->lanes) {
         for (auto e : ln.timerEvents) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.guidesReady) cudaEventDestroy(ln.guidesReady);
         if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     if (h->evFork) cudaEventDestroy(h->evFork);
@@ -614,7 +615,8 @@ static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, ui
 extern "C" int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* color, float* albedo, float* normal, void* stream) {
     if (int r = checkRender(h, cam, w, hgt)) return r;
     if (!color) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
-    return renderFrame(h, 0, frameCount, cam, w, hgt, color, albedo, normal, nullptr, true, (cudaStream_t)stream);
+    h->splitGuides = false;
+    return renderFrameSplit(h, frameCount, cam, w, hgt, color, albedo, normal, (cudaStream_t)stream);
 }
 namespace {
 __global__ void __launch_bounds__(256) k_accum_add(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
@@ -680,11 +682,13 @@ extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const
         if (!h->guidesReady) PLT_CUDA(cudaEventCreateWithFlags(&h->guidesReady, cudaEventDisableTiming));
     }
     h->armGuides = guides;  // renderTiles records guidesReady after the last tile's sample stage
-    const int rr = renderFrame(h, 0, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), nullptr, true, 0);
+    h->splitGuides = false;
+    const int rr = renderFrameSplit(h, frameCount, cam, w, hgt, h->outColor.as<float>(), h->outAlbedo.as<float>(), h->outNormal.as<float>(), 0);
     h->armGuides = false;
     if (rr) return rr;
     if (guides) {
         PLT_CUDA(cudaStreamWaitEvent(h->copyStream, h->guidesReady, 0));
+        if (h->splitGuides) PLT_CUDA(cudaStreamWaitEvent(h->copyStream, h->lanes[1].guidesReady, 0));
         if (albedoHost) PLT_CUDA(cudaMemcpyAsync(albedoHost, h->outAlbedo.p, bytes, cudaMemcpyDeviceToHost, h->copyStream));
         if (normalHost) PLT_CUDA(cudaMemcpyAsync(normalHost, h->outNormal.p, bytes, cudaMemcpyDeviceToHost, h->copyStream));
     }

@@ -99,7 +99,8 @@ struct PltptContext {
         plt::DevBuf work[40];                  // per-frame work buffers (integrator.cu)
         plt::DevBuf accum;                     // lane-private RGBA64F sums (lanes >= 1), merged into the caller's buffer at the end
         cudaStream_t stream = nullptr;         // own non-blocking stream (lanes >= 1)
-        cudaEvent_t done = nullptr;
+        cudaEvent_t done = nullptr, guidesReady = nullptr;
+        uint32_t partialFrames = 0;            // lower halves of split frames among timerCount
         bool statsDirty = false;
         std::vector<cudaEvent_t> timerEvents;  // kTimerRing x {start, after sample stage, after solve stage}
         uint32_t timerCount = 0;
@@ -108,7 +109,7 @@ struct PltptContext {
     cudaEvent_t evFork = nullptr;
     cudaEvent_t guidesReady = nullptr, copyDone = nullptr;  // pltpt_render_frame_host: guide-buffer copies run on copyStream under the solve stage
     cudaStream_t copyStream = nullptr;
-    bool armGuides = false;
+    bool armGuides = false, splitGuides = false;  // splitGuides: the last frame was split over both lanes (both guidesReady events count)
     int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};
@@ -137,7 +138,8 @@ int traceClosest(PltptContext* c, uint32_t n, const float* rays, uint32_t* hits,
 int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded, cudaStream_t s);
 // integrator.cu
 int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal,
-                double* accum, bool solve, cudaStream_t s);
+                double* accum, bool solve, cudaStream_t s, uint32_t rowBegin = 0, uint32_t rowEnd = 0);
+int renderFrameSplit(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, cudaStream_t s);
 int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host);
 int syncFrameStats(PltptContext* c);
 }  // namespace plt

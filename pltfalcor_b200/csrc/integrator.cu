@@ -110,17 +110,17 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
 }
 
 // One frame = one sample per pixel.  `bouncesOut` (device, optional) receives the reference-layout bounce records.
-static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, uint32_t tileRows, bool solve, PltptBounce* bouncesOut, cudaStream_t s) {
+static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, uint32_t tileRows, uint32_t rowBegin, uint32_t rowEnd, bool solve, PltptBounce* bouncesOut, cudaStream_t s) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const uint32_t persistentGrid = uint32_t(sms) * 8;
-    for (uint32_t y0 = 0; y0 < P.height; y0 += tileRows) {
+    for (uint32_t y0 = rowBegin; y0 < rowEnd; y0 += tileRows) {
         P.tileY0 = y0;
-        P.tileRows = std::min(tileRows, P.height - y0);
+        P.tileRows = std::min(tileRows, rowEnd - y0);
         P.outOffset = y0 * P.width;
         P.pixelCount = P.tileRows * P.width;
         cudaEvent_t* ev = &ln.timerEvents[3 * ln.timerCount];
-        const bool timed = y0 == 0;  // stage timers cover the first tile of a frame (the only one unless the frame is tiled)
+        const bool timed = y0 == rowBegin;  // stage timers cover the first tile of a frame (the only one unless the frame is tiled)
         const uint32_t maxB = c->opt.maxBounces;
         if (maxB > 63) { setError("maxBounces > 63 is not supported by the wavefront queues"); return PLTPT_ERR_INVALID_ARGUMENT; }
         if (timed) cudaEventRecord(ev[0], s);
@@ -144,7 +144,7 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
         if (timed) cudaEventRecord(ev[1], s);
         // guide buffers (albedo, normal) are final once the last tile's sample stage has run: the host-buffer path starts their
         // device-to-host copies here, under the solve stage
-        if (c->armGuides && y0 + tileRows >= P.height) cudaEventRecord(c->guidesReady, s);
+        if (c->armGuides && y0 + tileRows >= rowEnd) cudaEventRecord(&ln == &c->lanes[0] ? c->guidesReady : ln.guidesReady, s);
         if (bouncesOut) { launchGatherBounces(P, bouncesOut, maxB + 1, s); c->stats.kernelLaunches++; c->markKernel(PLTPT_K_OTHER, s); }
         if (solve) {
             // ---- solve stage: connect per vertex index, then the replay wavefront, then the deterministic per-pixel sum
@@ -185,8 +185,10 @@ static int ensureTimers(PltptContext::Lane& ln) {
     return PLTPT_OK;
 }
 
+// Rows [rowBegin, rowEnd) of one frame on one lane (rowEnd = 0: the whole frame).
 int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, double* accum,
-                bool solve, cudaStream_t s) {
+                bool solve, cudaStream_t s, uint32_t rowBegin, uint32_t rowEnd) {
+    if (rowEnd == 0) rowEnd = h;
     PltptContext::Lane& ln = c->lanes[lane];
     FrameParams P{};
     const bool fresh = ln.work[3].p == nullptr;
@@ -202,10 +204,34 @@ int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCamer
     // device timers: one event triple per frame from a ring, read back in syncFrameStats()
     if (int r = ensureTimers(ln)) return r;
     if (ln.timerCount == PltptContext::kTimerRing || c->kernelEventCount > 60000) { if (int r = syncFrameStats(c)) return r; }
-    if (int r = renderTiles(c, ln, P, tileRows, solve, nullptr, s)) return r;
+    if (int r = renderTiles(c, ln, P, tileRows, rowBegin, rowEnd, solve, nullptr, s)) return r;
     ln.timerCount++;
     ln.timerStream = s;
     ln.statsDirty = true;
+    if (rowBegin != 0) ln.partialFrames++;  // the lower part of a split frame: not a frame of its own in the statistics
+    return PLTPT_OK;
+}
+
+// One frame for a caller that renders frame by frame (pltpt_render_frame, pltpt_render_frame_host): the two lanes take the upper
+// and the lower half of the image concurrently (rows are independent: seeds derive from absolute pixel coordinates), so that the
+// narrow late-bounce launches of one half share the GPU with the other half's.  `s` is the caller's stream; lane 1 forks from it
+// and joins it again.
+int renderFrameSplit(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, cudaStream_t s) {
+    const bool split = !c->profiling && c->frameOverlap >= 2 && PltptContext::kLanes >= 2 && h >= 128;
+    if (!split) return renderFrame(c, 0, frameCount, cam, w, h, color, albedo, normal, nullptr, true, s, 0, h);
+    PltptContext::Lane& l1 = c->lanes[1];
+    if (!c->evFork) PLT_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    if (!l1.stream) PLT_CUDA(cudaStreamCreateWithFlags(&l1.stream, cudaStreamNonBlocking));
+    if (!l1.done) PLT_CUDA(cudaEventCreateWithFlags(&l1.done, cudaEventDisableTiming));
+    if (!l1.guidesReady) PLT_CUDA(cudaEventCreateWithFlags(&l1.guidesReady, cudaEventDisableTiming));
+    const uint32_t mid = ((h / 2) + 3u) & ~3u;  // primary rays are traced in 8x4 pixel tiles per warp
+    PLT_CUDA(cudaEventRecord(c->evFork, s));
+    PLT_CUDA(cudaStreamWaitEvent(l1.stream, c->evFork, 0));
+    if (int r = renderFrame(c, 0, frameCount, cam, w, h, color, albedo, normal, nullptr, true, s, 0, mid)) return r;
+    if (int r = renderFrame(c, 1, frameCount, cam, w, h, color, albedo, normal, nullptr, true, l1.stream, mid, h)) return r;
+    PLT_CUDA(cudaEventRecord(l1.done, l1.stream));
+    PLT_CUDA(cudaStreamWaitEvent(s, l1.done, 0));
+    c->splitGuides = true;
     return PLTPT_OK;
 }
 
@@ -218,9 +244,15 @@ int syncFrameStats(PltptContext* c) {
         PLT_CUDA(cudaStreamSynchronize(ln.timerStream));
         unsigned long long host[16];
         PLT_CUDA(cudaMemcpy(host, ln.work[3].p, sizeof(host), cudaMemcpyDeviceToHost));
-        c->stats.bsdfEvals = host[0] - host[8];       // last frame
-        c->stats.pathVertices = host[1] - host[9];
-        c->stats.mneeIterations = host[3] - host[11];
+        if (ln.partialFrames) {  // lower half of a split frame: completes the upper half's "last frame" figures
+            c->stats.bsdfEvals += host[0] - host[8];
+            c->stats.pathVertices += host[1] - host[9];
+            c->stats.mneeIterations += host[3] - host[11];
+        } else {
+            c->stats.bsdfEvals = host[0] - host[8];       // last frame
+            c->stats.pathVertices = host[1] - host[9];
+            c->stats.mneeIterations = host[3] - host[11];
+        }
         c->stats.traversalStackOverflows += host[2] & 0xffffffffull;
         c->stats.totalBsdfEvals += host[0];
         c->stats.totalPathVertices += host[1];
@@ -234,7 +266,7 @@ int syncFrameStats(PltptContext* c) {
         c->stats.droppedConnections += dropped;
         uint32_t walks = 0;
         PLT_CUDA(cudaMemcpy(&walks, ln.work[14].as<uint32_t>() + 34, 4, cudaMemcpyDeviceToHost));
-        c->stats.mneeWalks = walks;
+        c->stats.mneeWalks = ln.partialFrames ? c->stats.mneeWalks + walks : walks;
         for (uint32_t i = 0; i < ln.timerCount; ++i) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, ln.timerEvents[3 * i], ln.timerEvents[3 * i + 1]);
@@ -242,7 +274,8 @@ int syncFrameStats(PltptContext* c) {
             c->stats.sampleStageMs += a;
             c->stats.solveStageMs += b;
         }
-        c->stats.framesRendered += ln.timerCount;
+        c->stats.framesRendered += ln.timerCount - std::min(ln.timerCount, ln.partialFrames);
+        ln.partialFrames = 0;
         ln.timerCount = 0;
         ln.statsDirty = false;
     }
@@ -281,7 +314,7 @@ int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraDat
     const uint32_t records = c->opt.maxBounces + 1;
     const size_t bytes = size_t(w) * h * records * sizeof(PltptBounce);
     PLT_CUDA(ln.work[25].ensure(bytes));
-    if (int r = renderTiles(c, ln, P, tileRows, false, ln.work[25].as<PltptBounce>(), 0)) return r;
+    if (int r = renderTiles(c, ln, P, tileRows, 0, h, false, ln.work[25].as<PltptBounce>(), 0)) return r;
     PLT_CUDA(cudaMemcpy(host, ln.work[25].p, bytes, cudaMemcpyDeviceToHost));
     ln.work[25].release();
     return PLTPT_OK;

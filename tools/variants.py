@@ -77,6 +77,20 @@ def bench_one(lib, frames):
         p.set_frame_overlap(1)
         ms_seq = timed()
         p.set_frame_overlap(0)
+    # frame-by-frame host-buffer call (what bench.py's e2e times)
+    host = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+    import ctypes as C
+    import time
+    def e2e(n, first):
+        for f in range(first, first + n):
+            c = scene.with_jitter(cam, f, W, H)
+            binding._check(binding.lib().pltpt_render_frame_host(p.h, f, C.byref(c), W, H, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr()))
+    e2e(3, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e(frames, 100)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / frames
     p.set_profiling(True)
     p.reset_stats()
     p.render_accumulate(cam, 3, 1, frames, W, H, acc)
@@ -88,7 +102,7 @@ def bench_one(lib, frames):
     q = binding.Pltpt()
     q.set_scene(sb)
     sweep = {k: round(v["evals_per_s"] / 1e9, 3) for k, v in bench.bsdf_sweep(torch, q, ids, 6543.7).items()}
-    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "sweep_Gevals_s": sweep, "ms_per_frame": round(ms, 3), "ms_sequential": ms_seq and round(ms_seq, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean() / acc[..., 3].mean()), "kernels": k}))
+    print(json.dumps({"lib": os.path.relpath(lib, ROOT), "sweep_Gevals_s": sweep, "ms_per_frame": round(ms, 3), "e2e_ms": round(e2e_ms, 3), "ms_sequential": ms_seq and round(ms_seq, 3), "Mpaths_s": round(W * H / ms / 1e3, 1), "mean_rgb": float(acc[..., :3].mean() / acc[..., 3].mean()), "kernels": k}))
 
 
 if __name__ == "__main__":
