@@ -225,7 +225,8 @@ private:
 class Scene {
 public:
     using SharedPtr = std::shared_ptr<Scene>;
-    enum class UpdateFlags : uint32_t { None = 0 };
+    enum class UpdateFlags : uint32_t { None = 0, GeometryMoved = 0x1, SceneGraphChanged = 0x80, LightCollectionChanged = 0x100, MaterialsChanged = 0x200, EnvMapChanged = 0x400,
+                                        GeometryChanged = 0x100000 };  // Scene/Scene.h:127-165 (the values the pass looks at)
     Scene(const PltptSceneDesc& d) : mDesc(d), mpCamera(std::make_shared<Camera>()), mHasEnvMap(d.envMapTexels != nullptr) {}
     const PltptSceneDesc& getPltptSceneDesc() const { return mDesc; }
     const Camera::SharedPtr& getCamera() const { return mpCamera; }

@@ -129,6 +129,23 @@ void PLTPT::setScene(RenderContext* pRenderContext, const std::shared_ptr<Scene>
     }
 }
 
+void PLTPT::onSceneUpdates(RenderContext* pRenderContext, Scene::UpdateFlags sceneUpdates) {
+    if (!mpScene || !mSceneUploaded) return;
+    const uint32_t u = uint32_t(sceneUpdates);
+    const uint32_t structural = uint32_t(Scene::UpdateFlags::GeometryChanged) | uint32_t(Scene::UpdateFlags::MaterialsChanged) | uint32_t(Scene::UpdateFlags::EnvMapChanged) |
+                                uint32_t(Scene::UpdateFlags::LightCollectionChanged);
+    const uint32_t moved = uint32_t(Scene::UpdateFlags::GeometryMoved) | uint32_t(Scene::UpdateFlags::SceneGraphChanged);
+    if (!(u & (structural | moved))) return;
+    if (pRenderContext) pRenderContext->flush(true);
+    if (u & structural) { uploadScene(); return; }
+#ifdef PLTPT_WITH_FALCOR
+    const PltptSceneDesc desc = pltptDescribeFalcorScene(*mpScene);
+#else
+    const PltptSceneDesc& desc = mpScene->getPltptSceneDesc();
+#endif
+    check(pltpt_update_transforms(mHandle, desc.worldMatrices, desc.inverseTransposeWorldMatrices, desc.matrixCount, desc.pointersAreDevice), "pltpt_update_transforms");
+}
+
 void PLTPT::uploadScene() {
     ensureHandle();
     check(pltpt_set_options(mHandle, &mOptions), "pltpt_set_options");

@@ -30,6 +30,9 @@ public:
     void execute(RenderContext* pRenderContext, const RenderData& renderData) override;
     void renderUI(Gui::Widgets& widget) override;
     void setScene(RenderContext* pRenderContext, const std::shared_ptr<Scene>& pScene) override;
+    // The reference leaves scene changes to the driver (Scene::raytrace refits / rebuilds the TLAS on demand, Scene.cpp:3624-3700); the
+    // CUDA library owns its BVH, so the pass forwards them: moved instances -> pltpt_update_transforms, anything structural -> re-upload.
+    void onSceneUpdates(RenderContext* pRenderContext, Scene::UpdateFlags sceneUpdates) override;
     bool onMouseEvent(const MouseEvent&) override { return false; }
     bool onKeyEvent(const KeyboardEvent&) override { return false; }
 
