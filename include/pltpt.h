@@ -334,6 +334,11 @@ PLTPT_API int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32
  * The sum is the same set of frames either way; only the fp64 summation order differs. */
 PLTPT_API int pltpt_set_frame_overlap(PltptHandle h, int frames);
 
+/* Work-buffer budget per lane in bytes (ours; 0 = the default 24 GB).  The reference bounds its bounce buffer with `tileSize`
+ * (512 x 512 pixel tiles, PLTPT.cpp:426-428); this library tiles by rows so that one tile's work buffers fit the budget
+ * (1080p and 4K at depth 8 need 9 GB and 37 GB untiled).  Results do not depend on the tiling. */
+PLTPT_API int pltpt_set_work_budget(PltptHandle h, uint64_t bytes);
+
 /* Host-buffer convenience used by the Falcor shell when no shared CUDA surface exists:
  * renders one frame and copies RGBA32F results to host memory (any of the three may be NULL). */
 PLTPT_API int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,

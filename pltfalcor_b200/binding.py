@@ -16,7 +16,7 @@ EXPORTS = [
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
-    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms",
+    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
 ]
 
 
@@ -53,6 +53,7 @@ def lib():
         _lib.pltpt_reset_stats.argtypes = [vp]
         _lib.pltpt_set_profiling.argtypes = [vp, C.c_int]
         _lib.pltpt_set_frame_overlap.argtypes = [vp, C.c_int]
+        _lib.pltpt_set_work_budget.argtypes = [vp, C.c_uint64]
         _lib.pltpt_spd_load.argtypes = [C.c_char_p, vp, vp, u32, vp]
         _lib.pltpt_gen_spectral_profile.argtypes = [u32, vp, vp, f32, C.c_int, vp]
         _lib.pltpt_pack_material.argtypes = [vp, vp]
@@ -159,6 +160,10 @@ class Pltpt:
     def set_frame_overlap(self, frames):
         """Frames render_accumulate keeps in flight: 2 (default) or 1."""
         _check(lib().pltpt_set_frame_overlap(self.h, int(frames)))
+
+    def set_work_budget(self, nbytes):
+        """Per-lane work-buffer budget (bytes; 0 = default): smaller budgets render a frame in more row tiles."""
+        _check(lib().pltpt_set_work_budget(self.h, int(nbytes)))
 
     def reset_stats(self):
         _check(lib().pltpt_reset_stats(self.h))

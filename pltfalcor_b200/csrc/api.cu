@@ -88,6 +88,13 @@ extern "C" int pltpt_get_stats(PltptHandle h, PltptStats* out) {
     *out = h->stats;
     return PLTPT_OK;
 }
+/* Per-lane work-buffer budget in bytes (0 = default): frames whose buffers would exceed it are rendered in row tiles. */
+extern "C" int pltpt_set_work_budget(PltptHandle h, uint64_t bytes) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int r = syncFrameStats(h)) return r;
+    h->workBudgetBytes = size_t(bytes);
+    return PLTPT_OK;
+}
 /* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 or 2 = two (default). */
 extern "C" int pltpt_set_frame_overlap(PltptHandle h, int frames) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");

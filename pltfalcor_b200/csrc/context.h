@@ -111,6 +111,7 @@ struct PltptContext {
     cudaStream_t copyStream = nullptr;
     bool armGuides = false, splitGuides = false;  // splitGuides: the last frame was split over both lanes (both guidesReady events count)
     int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
+    size_t workBudgetBytes = 0; // per-lane work-buffer budget that sizes the row tiles (0 = default 24 GB; pltpt_set_work_budget)
     plt::DevBuf outColor, outAlbedo, outNormal;
     PltptStats stats{};
     cudaEvent_t evA = nullptr, evB = nullptr;

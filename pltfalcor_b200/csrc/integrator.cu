@@ -27,7 +27,8 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.frameCount = frameCount; P.width = w; P.height = h;
     const uint32_t recordsPerPixel = c->opt.maxBounces + 1;
     const size_t perRow = workBytesPerPixel(recordsPerPixel) * w;
-    tileRows = uint32_t(std::min<size_t>(h, std::max<size_t>(4, (kWorkBudgetBytes / perRow) & ~size_t(3))));
+    const size_t budget = c->workBudgetBytes ? c->workBudgetBytes : kWorkBudgetBytes;
+    tileRows = uint32_t(std::min<size_t>(h, std::max<size_t>(4, (budget / perRow) & ~size_t(3))));
     const uint32_t tilePixels = tileRows * w;
     P.pixelCount = tilePixels;
     const size_t records = size_t(recordsPerPixel) * tilePixels;

@@ -209,6 +209,39 @@ def test_frames_are_deterministic_and_partitionable(torch_cuda, cornell):
     p.close()
 
 
+@pytest.mark.parametrize("name", ["cornell", "grating_sphere", "env"])
+def test_row_tiling_does_not_change_the_image(name, torch_cuda):
+    """Frames that exceed the work-buffer budget are rendered in row tiles (4K at depth 8 does); the image must not depend on it:
+    single frames through both lanes (split halves, each tiled) and accumulated frames, bit for bit."""
+    torch = torch_cuda
+    from pltfalcor_b200 import binding
+    buffers, cam = _scene(name)
+    p = binding.Pltpt(maxBounces=6)
+    p.set_scene(buffers)
+    w, h = 160, 144
+    whole, tiled = torch.zeros((h, w, 4), device="cuda"), torch.zeros((h, w, 4), device="cuda")
+    guides = [torch.zeros((h, w, 4), device="cuda") for _ in range(4)]
+    p.render_frame(cam, 3, w, h, whole, guides[0], guides[1])
+    acc_whole = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 3, w, h, acc_whole)
+    torch.cuda.synchronize()
+    per_row = 160 * 7 * 4600  # ~bytes of work buffers per image row at depth 6 (integrator.cu workBytesPerPixel)
+    p.set_work_budget(20 * per_row)  # => tiles of <= 20 rows: 4 tiles per half-frame, 8 per accumulated frame
+    p.render_frame(cam, 3, w, h, tiled, guides[2], guides[3])
+    acc_tiled = torch.zeros_like(acc_whole)
+    p.render_accumulate(cam, 0, 1, 3, w, h, acc_tiled)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, tiled) and torch.equal(guides[0], guides[2]) and torch.equal(guides[1], guides[3])
+    assert torch.equal(acc_whole, acc_tiled)
+    assert float(whole[..., :3].sum()) > 0
+    p.set_frame_overlap(1)  # one lane, no split: the same image again
+    single = torch.zeros_like(whole)
+    p.render_frame(cam, 3, w, h, single)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, single)
+    p.close()
+
+
 def test_full_hd_frame_properties(torch_cuda, cornell):
     """BASELINE config 2 size (1920x1080, depth 8): size-independent properties — finite, non-negative, alpha 1, every pixel's
     first record is a hit or a miss, bounce chains are well formed, mean radiance agrees with a low-res render of the same frame set."""
