@@ -114,7 +114,7 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
         const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
         const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
         float nearT[8];
-        uint32_t innerHits = 0;
+        uint32_t innerHits = 0, triMask = 0;
         // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
         const float tfarLimit = best.t * 1.000002f;
 #pragma unroll
@@ -130,21 +130,23 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
             if (!(tn <= tf)) continue;
             if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
-            else {
-                const uint32_t count = meta >> 5, first = triBase + (meta & 31u);
-                for (uint32_t k = 0; k < count; ++k) {
-                    const float4* tp = reinterpret_cast<const float4*>(tris + first + k);
-                    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                    float t, u, v;
-                    if (tc) ++tc->tris;
-                    if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
-                    if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
-                    const uint32_t g = __float_as_uint(q2.w);
-                    if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
-                    best.t = t; best.u = u; best.v = v;
-                    best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
-                }
-            }
+            else triMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);  // the leaf's triangles: slots [offset, offset + count) of this node's <= 24
+        }
+        // The triangles of all intersected leaf children in ONE loop after the slab tests: tested inside the unrolled child loop, every
+        // child was a separate divergence point (a lane with a leaf hit ran the triangle test while its 31 neighbours waited).
+        while (triMask) {
+            const uint32_t k = uint32_t(__ffs(int(triMask))) - 1u;
+            triMask &= triMask - 1u;
+            const float4* tp = reinterpret_cast<const float4*>(tris + triBase + k);
+            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            float t, u, v;
+            if (tc) ++tc->tris;
+            if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
+            if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
+            const uint32_t g = __float_as_uint(q2.w);
+            if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
+            best.t = t; best.u = u; best.v = v;
+            best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
         }
         // push the intersected inner children, farthest first, so the nearest is popped next
         while (innerHits) {
@@ -205,7 +207,7 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
         const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
         const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
         float nearT[8];
-        uint32_t innerHits = 0;
+        uint32_t innerHits = 0, triMask = 0;
         // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
         const float tfarLimit = best.t * 1.000002f;
 #pragma unroll
@@ -221,21 +223,23 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
             if (!(tn <= tf)) continue;
             if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
-            else {
-                const uint32_t count = meta >> 5, first = triBase + (meta & 31u);
-                for (uint32_t k = 0; k < count; ++k) {
-                    const float4* tp = reinterpret_cast<const float4*>(tris + first + k);
-                    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                    float t, u, v;
-                    if (tc) ++tc->tris;
-                    if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
-                    if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
-                    const uint32_t g = __float_as_uint(q2.w);
-                    if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
-                    best.t = t; best.u = u; best.v = v;
-                    best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
-                }
-            }
+            else triMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);  // the leaf's triangles: slots [offset, offset + count) of this node's <= 24
+        }
+        // The triangles of all intersected leaf children in ONE loop after the slab tests: tested inside the unrolled child loop, every
+        // child was a separate divergence point (a lane with a leaf hit ran the triangle test while its 31 neighbours waited).
+        while (triMask) {
+            const uint32_t k = uint32_t(__ffs(int(triMask))) - 1u;
+            triMask &= triMask - 1u;
+            const float4* tp = reinterpret_cast<const float4*>(tris + triBase + k);
+            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            float t, u, v;
+            if (tc) ++tc->tris;
+            if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
+            if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
+            const uint32_t g = __float_as_uint(q2.w);
+            if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
+            best.t = t; best.u = u; best.v = v;
+            best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
         }
         // push the intersected inner children, farthest first, so the nearest is popped next
         while (innerHits) {
