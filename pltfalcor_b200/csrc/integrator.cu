@@ -70,7 +70,7 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.pendingAux = ln.work[6].as<uint32_t>();
     P.sortedAux = ln.work[7].as<uint32_t>();
     P.queueCount = ln.work[14].as<uint32_t>();
-    P.jobCount = P.queueCount + 32;
+    P.jobCount = P.queueCount + QC_JobCount;
     P.contrib = ln.work[15].as<float4>();
     P.debugView = c->opt.debugView;
     P.debugIntensity = c->opt.debugViewIntensity;
@@ -83,9 +83,9 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.psHit = ln.work[20].as<uint4>(); P.ssRng = ln.work[21].as<uint4>(); P.ssTileRng = ln.work[22].as<uint4>();
     P.traceQueue = ln.work[4].as<uint32_t>();
     P.vertexList = ln.work[23].as<uint32_t>();
-    P.levelCount = P.queueCount + 64;
+    P.levelCount = P.queueCount + QC_LevelCount;
     P.mneeItems = ln.work[26].as<MneeItem>();
-    P.mneeCount = P.queueCount + 34;
+    P.mneeCount = P.queueCount + QC_MneeCount;
     P.mneeCapacity = 2 * tilePixels;
     PLT_CUDA(ln.work[8].ensure(size_t(2) * tilePixels * sizeof(MneeWalk)));
     PLT_CUDA(ln.work[31].ensure(size_t(3) * 2 * tilePixels * 4));
@@ -93,7 +93,7 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.mneeLists = ln.work[31].as<uint32_t>();
     PLT_CUDA(ln.work[24].ensure(size_t(tilePixels) * 4));
     P.missList = ln.work[24].as<uint32_t>();
-    P.missCount = P.queueCount + 36;
+    P.missCount = P.queueCount + QC_MissCount;
     if (tilePixels >= (1u << 26)) { setError("tile too large for the packed miss list"); return PLTPT_ERR_INVALID_ARGUMENT; }
     P.connItems = ln.work[27].as<ConnItem>();
     P.shadowRays = ln.work[28].as<float4>();
@@ -162,7 +162,7 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
             if (P.useEnv) { launchConnectMiss(P, persistentGrid, s); c->markKernel(PLTPT_K_CONNECT_A, s); c->stats.kernelLaunches++; }
             if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches += 2; c->markKernel(PLTPT_K_MNEE, s); }
             for (uint32_t it = 0; it <= maxB; ++it) {
-                launchSortFlip(P, SortView{P.sorted, P.queueCount + 2 * kQueueTypes + 2, P.sortedAux}, false, persistentGrid, s);
+                launchSortFlip(P, SortView{P.sorted, P.queueCount + QC_SortedCount, P.sortedAux}, false, persistentGrid, s);
                 c->markKernel(PLTPT_K_SORT, s);
                 launchUnwindStep(P, persistentGrid, s);
                 c->markKernel(PLTPT_K_UNWIND_STEP, s);
@@ -263,10 +263,10 @@ int syncFrameStats(PltptContext* c) {
         c->stats.unwindJobSteps += host[7];
         PLT_CUDA(cudaMemset(ln.work[3].p, 0, 16 * sizeof(unsigned long long)));
         uint32_t dropped = 0;
-        PLT_CUDA(cudaMemcpy(&dropped, ln.work[14].as<uint32_t>() + 33, 4, cudaMemcpyDeviceToHost));
+        PLT_CUDA(cudaMemcpy(&dropped, ln.work[14].as<uint32_t>() + QC_Dropped, 4, cudaMemcpyDeviceToHost));
         c->stats.droppedConnections += dropped;
         uint32_t walks = 0;
-        PLT_CUDA(cudaMemcpy(&walks, ln.work[14].as<uint32_t>() + 34, 4, cudaMemcpyDeviceToHost));
+        PLT_CUDA(cudaMemcpy(&walks, ln.work[14].as<uint32_t>() + QC_MneeCount, 4, cudaMemcpyDeviceToHost));
         c->stats.mneeWalks = ln.partialFrames ? c->stats.mneeWalks + walks : walks;
         for (uint32_t i = 0; i < ln.timerCount; ++i) {
             float a = 0.f, b = 0.f;

@@ -86,7 +86,28 @@ struct FrameParams {
     uint32_t* missCount;
 };
 
-constexpr int kQueueTypes = 12;  // MaterialType values 0..11
+constexpr int kQueueTypes = 32;  // MaterialType values 0..11, | kFinishingBin for replay jobs whose next step is their last (measure)
+constexpr uint32_t kFinishingBin = 16;
+// Slots of the per-lane counter block `queueCount` (256 x uint32, zeroed at the start of every tile).
+enum : uint32_t {
+    QC_Hist = 0,                            // [kQueueTypes] per-type counts of `pending`
+    QC_Total = kQueueTypes,                 // entries of `pending`
+    QC_Cursor = kQueueTypes + 1,            // [kQueueTypes] scatter cursors of k_sort_queue
+    QC_SortedCount = 2 * kQueueTypes + 2,   // entries of `sorted`
+    QC_JobCount = 70,                       // allocated connection jobs
+    QC_Dropped = 71,                        // connections dropped for lack of capacity (must stay 0)
+    QC_MneeCount = 72,                      // parked manifold walks
+    QC_MissCount = 73,                      // entries of missList
+    QC_MneeRound = 74,                      // [3] rotating live-walk counts of k_mnee_walk
+    QC_MneeDone = 77,                       // converged walks
+    QC_TraceCursor = 78,                    // fetch cursor of k_trace (re-zeroed by k_flip_queue)
+    QC_ShadowCursor = 79,                   // fetch cursor of k_shadow_trace (re-zeroed by k_connect_a)
+    QC_MneeTraceCursor = 80,                // [3] rotating fetch cursors of the trial-ray trace in k_mnee_walk
+    QC_LevelCount = 96,                     // [maxBounces + 1 <= 64] entries of vertexList per bounce
+    QC_TraceCount = QC_LevelCount + 64,     // entries of traceQueue (sample stage) / deferred entries of half B (solve stage)
+};
+static_assert(QC_SortedCount < QC_JobCount && QC_MneeTraceCursor + 3 <= QC_LevelCount && QC_TraceCount < 256, "queueCount slots overlap");
+constexpr uint32_t kTraceCountSlot = 64;  // levelCount[kTraceCountSlot] == queueCount[QC_TraceCount]
 constexpr int kJobPlanes = 10;
 
 struct Bounce {
@@ -621,14 +642,19 @@ PLT_D void enqueueJob(const FrameParams& P, uint32_t type, uint32_t id, uint32_t
     const uint32_t active = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(P.queueCount + kQueueTypes, uint32_t(__popc(active)));
+    if (lane == leader) base = atomicAdd(P.queueCount + QC_Total, uint32_t(__popc(active)));
     base = __shfl_sync(active, base, leader);
     const uint32_t slot = base + __popc(active & ((1u << lane) - 1u));
     P.pending[slot] = id;
     if (kAux) P.pendingAux[slot] = aux;
     P.pendingType[slot] = uint8_t(type);
     const uint32_t peers = __match_any_sync(active, type);
-    if (lane == __ffs(peers) - 1) atomicAdd(P.queueCount + type, uint32_t(__popc(peers)));
+    if (lane == __ffs(peers) - 1) atomicAdd(P.queueCount + QC_Hist + type, uint32_t(__popc(peers)));
+}
+// Queue bin of a replay job that evaluates vertex q of its path next: the vertex's MaterialType, and a separate set of bins for
+// q == 0, where the step ends in measure() instead of storing the job back: a warp then does one or the other, not both in turn.
+PLT_D uint32_t replayBin(const FrameParams& P, uint32_t pixel, uint32_t q) {
+    return uint32_t(P.vMatType[size_t(q) * P.pixelCount + pixel]) | (q == 0u ? kFinishingBin : 0u);
 }
 PLT_D uint32_t allocJob(const FrameParams& P) {
     const uint32_t active = __activemask();
@@ -719,12 +745,12 @@ PLT_D void measureInto(const FrameParams& P, uint32_t pixel, uint32_t bounceIdx,
 PLT_D void emitConnection(const FrameParams& P, uint32_t pixel, int bounceIdx, uint32_t kind, bool evalCurrentVertex, float pathContribution, Beam& beam) {
     if (!evalCurrentVertex && bounceIdx == 0) { measureInto(P, pixel, uint32_t(bounceIdx), kind, pathContribution, beam); return; }
     const uint32_t id = allocJob(P);
-    if (id >= P.jobCapacity) { atomicAdd(P.jobCount + 1, 1u); writeContribution(P, pixel, bounceIdx, kind, mk3(0.f)); return; }
+    if (id >= P.jobCapacity) { atomicAdd(P.queueCount + QC_Dropped, 1u); writeContribution(P, pixel, bounceIdx, kind, mk3(0.f)); return; }
     JobHeader h;
     h.pixel = pixel; h.bounceIdx = uint32_t(bounceIdx); h.kind = kind; h.firstIsCurrent = evalCurrentVertex; h.pathContribution = pathContribution;
     h.q = uint32_t(evalCurrentVertex ? bounceIdx : bounceIdx - 1);
     storeJob(P, id, beam, h);
-    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + pixel], id, jobAux(pixel, h.q));
+    enqueueJob(P, replayBin(P, pixel, h.q), id, jobAux(pixel, h.q));
 }
 // pltpt_solve.rt.slang:205-217
 PLT_D bool wasNEEAvailable(const FrameParams& P, int bounceIdx, uint32_t flags) {
@@ -1023,7 +1049,7 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
     h.firstIsCurrent = !currentVertexMS;
     h.q = h.firstIsCurrent ? it.bounceIdx : it.bounceIdx - 1u;
     storeJob(P, it.jobId, beam, h);
-    enqueueJob(P, P.vMatType[size_t(h.q) * P.pixelCount + it.pixel], it.jobId, jobAux(it.pixel, h.q));
+    enqueueJob(P, replayBin(P, it.pixel, h.q), it.jobId, jobAux(it.pixel, h.q));
 }
 
 // ---- connect wavefront: A (light sampling) -> shadow-ray trace kernel -> B (visibility, MIS, emit) per vertex index ------------
@@ -1133,7 +1159,7 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                         P.shadowRays[2 * size_t(slot)] = mk4(ls.origin.x, ls.origin.y, ls.origin.z, 0.f);
                         P.shadowRays[2 * size_t(slot) + 1] = mk4(ls.dir.x, ls.dir.y, ls.dir.z, ls.distance);
                         pending = true;
-                    } else atomicAdd(P.jobCount + 1, 1u);
+                    } else atomicAdd(P.queueCount + QC_Dropped, 1u);
                 }
             }
         }
@@ -1167,7 +1193,7 @@ PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
                 const float w = __uint_as_float(item.info.w);
                 for (int k = 0; k < 4; ++k) { float4* q = jobField(P, jobId, k); *q = *q * w; }
             }
-            enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId, jobAux(pixel, uint32_t(p)));
+            enqueueJob(P, replayBin(P, pixel, uint32_t(p)), jobId, jobAux(pixel, uint32_t(p)));
         } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
         writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f));
         // manifoldNEESample ran with nothing in the way: 0 iterations (pltpt_solve.rt.slang:318-322)
@@ -1229,7 +1255,7 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
             if (ms.pdf < 1e-6f) connected = false;
             else {
                 const uint32_t mslot = atomicAdd(P.mneeCount, 1u);
-                if (mslot >= P.mneeCapacity) { atomicAdd(P.jobCount + 1, 1u); connected = false; }
+                if (mslot >= P.mneeCapacity) { atomicAdd(P.queueCount + QC_Dropped, 1u); connected = false; }
                 else {
                     MneeItem& it = P.mneeItems[mslot];
                     for (int i = 0; i < kMaxMSHits - 1; ++i) {
@@ -1260,7 +1286,7 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
         if (flags & CI_DO_MIS) {  // beam.scale(w) on the parked beam
             for (int k = 0; k < 4; ++k) { float4* q = jobField(P, jobId, k); *q = *q * misScale; }
         }
-        enqueueJob(P, P.vMatType[size_t(p) * P.pixelCount + pixel], jobId, jobAux(pixel, uint32_t(p)));
+        enqueueJob(P, replayBin(P, pixel, uint32_t(p)), jobId, jobAux(pixel, uint32_t(p)));
     } else writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
     connectTail(P, pixel, p, c);
     evals += c.st.evals;
@@ -1287,7 +1313,7 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
         return false;
     }
     h.q -= 1; h.firstIsCurrent = false;
-    nextType = P.vMatType[size_t(h.q) * P.pixelCount + h.pixel];
+    nextType = replayBin(P, h.pixel, h.q);
     nextAux = jobAux(h.pixel, h.q);
     storeJob(P, id, beam, h);
     return true;

@@ -28,7 +28,7 @@ namespace {
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { P.levelCount[64] = 0; P.queueCount[42] = 0; }  // deferred-entry count of this level's half B; shadow-trace fetch cursor
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.levelCount[kTraceCountSlot] = 0; P.queueCount[QC_ShadowCursor] = 0; }  // deferred-entry count of this level's half B; shadow-trace fetch cursor
     uint32_t evals = 0, verts = 0;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     TraversalCounters tc = {0, 0};
-    uint32_t* cursor = P.queueCount + 42;  // zeroed by k_connect_a of this level
+    uint32_t* cursor = P.queueCount + QC_ShadowCursor;  // zeroed by k_connect_a of this level
     uint32_t* overflow = reinterpret_cast<uint32_t*>(P.counters + 2);
     auto fetch = [&](uint32_t i, float3& o, float3& d, float& tmin, float& tmax) {
         if (!(P.connItems[i].info.y & CI_TRACE)) return false;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_consta
             const uint32_t active = __activemask();
             const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
             uint32_t at = 0;
-            if (lane == leader) at = atomicAdd(P.levelCount + 64, uint32_t(__popc(active)));
+            if (lane == leader) at = atomicAdd(P.levelCount + kTraceCountSlot, uint32_t(__popc(active)));
             at = __shfl_sync(active, at, leader) + __popc(active & ((1u << lane) - 1u));
             P.traceQueue[at] = i;
         }
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_consta
 }
 // Half B, pass 2: the deferred entries, densely packed.
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b_slow(const __grid_constant__ FrameParams P) {
-    const uint32_t n = P.levelCount[64];
+    const uint32_t n = P.levelCount[kTraceCountSlot];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};
@@ -135,14 +135,14 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b
 // barriers instead of ~2 x MNEEMaxIterations host launches that would mostly be empty).  Round = { advance: consume the previous
 // trial ray's answer, Newton steps, post the next trial ray (mneeWalkAdvance) | barrier | trace the posted rays | barrier }.
 // Live walks are kept in two ping-pong lists, converged ones are listed for pass 2; the three list counts rotate through
-// queueCount[37..39] (zeroed per tile; the count two rounds back is re-zeroed by thread 0 while nobody reads it), the number
-// of converged walks is queueCount[40].
+// queueCount[QC_MneeRound ..+3) (zeroed per tile; the count two rounds back is re-zeroed by thread 0 while nobody reads it), the number
+// of converged walks is queueCount[QC_MneeDone].
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(const __grid_constant__ FrameParams P) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
     if (n == 0) return;  // grid-uniform
-    uint32_t* counts = P.queueCount + 37;
-    uint32_t* doneCount = P.queueCount + 40;
+    uint32_t* counts = P.queueCount + QC_MneeRound;
+    uint32_t* doneCount = P.queueCount + QC_MneeDone;
     uint32_t* doneList = P.mneeLists + 2 * size_t(P.mneeCapacity);
     const uint32_t tid = blockIdx.x * kStageThreads + threadIdx.x, stride = gridDim.x * kStageThreads;
     const int lane = threadIdx.x & 31;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         uint32_t* next = P.mneeLists + size_t((round + 1u) & 1u) * P.mneeCapacity;
         const uint32_t nCur = round == 0 ? n : counts[round % 3u];
         uint32_t* nextCount = counts + (round + 1u) % 3u;
-        if (tid == 0) { counts[(round + 2u) % 3u] = 0; P.queueCount[43 + (round + 2u) % 3u] = 0; }
+        if (tid == 0) { counts[(round + 2u) % 3u] = 0; P.queueCount[QC_MneeTraceCursor + (round + 2u) % 3u] = 0; }
         for (uint32_t base = blockIdx.x * kStageThreads; base < nCur; base += stride) {  // ---- advance
             const uint32_t k = base + threadIdx.x;
             int r = WALK_FAILED;
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         grid.sync();
         const uint32_t nNext = *nextCount;
         if (nNext == 0) break;  // grid-uniform: every thread reads the same count after the barrier
-        // ---- trace the posted trial rays (persistent lanes; the fetch cursors rotate through queueCount[43..45] like the counts)
-        travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, nNext, P.queueCount + 43 + round % 3u, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
+        // ---- trace the posted trial rays (persistent lanes; the fetch cursors rotate through queueCount[QC_MneeTraceCursor ..+3) like the counts)
+        travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, nNext, P.queueCount + QC_MneeTraceCursor + round % 3u, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
             [&](uint32_t k, float3& o, float3& d, float& tmin, float& tmax) {
                 const MneeWalk& w = P.mneeWalks[next[k]];
                 const float4 r0 = w.ray0, r1 = w.ray1;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
 }
 // Pass 2: converged walks, densely packed: final visibility, replay through the specular chain, MIS, hand-over to the unwind queues.
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(const __grid_constant__ FrameParams P) {
-    const uint32_t n = P.queueCount[40];
+    const uint32_t n = P.queueCount[QC_MneeDone];
     const uint32_t* doneList = P.mneeLists + 2 * size_t(P.mneeCapacity);
     uint32_t evals = 0;
     TraversalCounters tc = {0, 0};

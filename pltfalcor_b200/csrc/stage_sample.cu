@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ FramePar
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace_simple(const __grid_constant__ FrameParams P) {
     const bool primary = P.level == 0;
     const uint32_t tilesX = (P.width + 7) / 8, tilesY = (P.tileRows + 3) / 4;
-    const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[64];
+    const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[kTraceCountSlot];
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
@@ -48,11 +48,11 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const _
     const bool primary = P.level == 0;
     // bounce 0 walks the implicit queue of all pixels (8x4 tiles per warp, padded), later bounces the queue the shade kernel filled
     const uint32_t tilesX = (P.width + 7) / 8, tilesY = (P.tileRows + 3) / 4;
-    const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[64];
+    const uint32_t n = primary ? tilesX * tilesY * 32u : P.levelCount[kTraceCountSlot];
     TraversalCounters tc = {0, 0};
     auto pixelOf = [&](uint32_t i, uint32_t& pixel) { return primary ? primaryPixel(P, i, pixel) : (pixel = P.traceQueue[i], true); };
-    // persistent lanes: a lane whose ray is done takes the next queue entry (cursor queueCount[41], re-zeroed by k_flip_queue)
-    travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, P.queueCount + 41, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
+    // persistent lanes: a lane whose ray is done takes the next queue entry (cursor queueCount[QC_TraceCursor], re-zeroed by k_flip_queue)
+    travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, P.queueCount + QC_TraceCursor, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
         [&](uint32_t i, float3& o, float3& d, float& tmin, float& tmax) {
             uint32_t pixel;
             if (!pixelOf(i, pixel)) return false;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADE) k_shade(const _
                 const uint32_t active = __activemask();
                 const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
                 uint32_t slot = 0;
-                if (lane == leader) slot = atomicAdd(P.levelCount + 64, uint32_t(__popc(active)));
+                if (lane == leader) slot = atomicAdd(P.levelCount + kTraceCountSlot, uint32_t(__popc(active)));
                 slot = __shfl_sync(active, slot, leader) + __popc(active & ((1u << lane) - 1u));
                 P.traceQueue[slot] = pixel;
             }

@@ -19,10 +19,10 @@ constexpr int kSortThreads = 256, kSortItems = 8, kSortChunk = kSortThreads * kS
 __global__ void __launch_bounds__(kSortThreads) k_sort_queue(const __grid_constant__ FrameParams P, SortView view) {
     __shared__ uint32_t offs[kQueueTypes], hist[kQueueTypes], base[kQueueTypes];
     uint32_t* qc = P.queueCount;
-    const uint32_t total = qc[kQueueTypes];
+    const uint32_t total = qc[QC_Total];
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int t = 0; t < kQueueTypes; ++t) { offs[t] = run; run += qc[t]; }
+        for (int t = 0; t < kQueueTypes; ++t) { offs[t] = run; run += qc[QC_Hist + t]; }
     }
     const int lane = threadIdx.x & 31;
     for (uint32_t chunk = blockIdx.x * kSortChunk; chunk < total; chunk += gridDim.x * kSortChunk) {
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_queue(const __grid_consta
             rank[k] = __shfl_sync(0xffffffffu, r, __ffs(peers) - 1) + __popc(peers & ((1u << lane) - 1u));
         }
         __syncthreads();
-        if (threadIdx.x < kQueueTypes) base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(qc + kQueueTypes + 1 + threadIdx.x, hist[threadIdx.x]) : 0u;
+        if (threadIdx.x < kQueueTypes) base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(qc + QC_Cursor + threadIdx.x, hist[threadIdx.x]) : 0u;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
@@ -57,14 +57,14 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_queue(const __grid_consta
 __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView view, bool resetTraceQueue) {
     uint32_t* qc = P.queueCount;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        *view.dstCount = qc[kQueueTypes];
-        for (int t = 0; t <= 2 * kQueueTypes + 1; ++t) qc[t] = 0;
-        if (resetTraceQueue) { P.levelCount[64] = 0; qc[41] = 0; }  // trace queue of the next bounce and the trace kernel's fetch cursor
+        *view.dstCount = qc[QC_Total];
+        for (uint32_t t = QC_Hist; t < QC_SortedCount; ++t) qc[t] = 0;  // histogram, total, cursors
+        if (resetTraceQueue) { P.levelCount[kTraceCountSlot] = 0; qc[QC_TraceCursor] = 0; }  // trace queue of the next bounce and the trace kernel's fetch cursor
     }
 }
 
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
-    const uint32_t n = P.queueCount[2 * kQueueTypes + 2];
+    const uint32_t n = P.queueCount[QC_SortedCount];
     uint32_t evals = 0;
     const uint32_t stride = gridDim.x * kStageThreads;
     uint32_t i = blockIdx.x * kStageThreads + threadIdx.x;
