@@ -110,7 +110,8 @@ bool writeFile(const std::string& path, const void* data, size_t bytes) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string plugin, scenePath, out = "pltpt_host_out";
+    std::string plugin, scenePath, movedScenePath, out = "pltpt_host_out";
+    uint32_t moveAfter = 0;
     uint32_t width = 0, height = 0, frames = 1;
     int device = 0;
     bool describe = false;
@@ -120,6 +121,8 @@ int main(int argc, char** argv) {
         auto next = [&]() -> std::string { if (i + 1 >= argc) { std::fprintf(stderr, "missing value after %s\n", a.c_str()); std::exit(2); } return argv[++i]; };
         if (a == "--plugin") plugin = next();
         else if (a == "--scene") scenePath = next();
+        else if (a == "--moved-scene") movedScenePath = next();   // same scene with other instance transforms: animation keyframe
+        else if (a == "--move-after") moveAfter = uint32_t(std::stoul(next()));
         else if (a == "--width") width = uint32_t(std::stoul(next()));
         else if (a == "--height") height = uint32_t(std::stoul(next()));
         else if (a == "--frames") frames = uint32_t(std::stoul(next()));
@@ -200,7 +203,18 @@ int main(int argc, char** argv) {
         const size_t texels = size_t(width) * height;
         std::vector<double> sum(texels * 4, 0.0);
         std::vector<float> guideA(texels * 4, 0.f), guideN(texels * 4, 0.f), host(texels * 4);
+        SceneFile moved;
+        if (!movedScenePath.empty() && !loadScene(movedScenePath, moved)) { std::fprintf(stderr, "cannot read scene file %s\n", movedScenePath.c_str()); return 3; }
         for (uint32_t f = 0; f < frames; ++f) {
+            if (!movedScenePath.empty() && f == moveAfter) {
+                // the animation controller moved instances: Falcor rewrites the matrix buffers in place and raises SceneGraphChanged
+                // (Scene::update -> RenderGraph::onSceneUpdates); the accumulation restarts like AccumulatePass does on scene changes
+                if (moved.blobs[4].size() != sf.blobs[4].size()) { std::fprintf(stderr, "--moved-scene has another matrix count\n"); return 3; }
+                std::memcpy(sf.blobs[4].data(), moved.blobs[4].data(), sf.blobs[4].size());
+                std::memcpy(sf.blobs[5].data(), moved.blobs[5].data(), sf.blobs[5].size());
+                pass->onSceneUpdates(&ctx, Scene::UpdateFlags::SceneGraphChanged);
+                std::fill(sum.begin(), sum.end(), 0.0);
+            }
             // GBufferRT: Halton(2,3), 16 samples, offset by (0.5, 0.5) and wrapped into [-0.5, 0.5), in pixels
             const uint32_t k = f % 16u;
             float jx = halton(k, 2) + 0.5f, jy = halton(k, 3) + 0.5f;

@@ -148,6 +148,40 @@ def test_plugin_renders_env_lit_scene_and_debug_view(host, tmp_path, torch_cuda)
 
 
 @pytest.mark.gpu
+def test_plugin_follows_moved_instances(host, tmp_path, cornell, torch_cuda):
+    """RenderPass::onSceneUpdates(SceneGraphChanged) -> pltpt_update_transforms: after the animation keyframe the plugin renders what
+    a pass created on the moved scene renders (same frame indices), bit for bit."""
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = cornell
+    moved = np.array(buffers.arrays["worldMatrices"], copy=True)
+    moved[7, :3, 3] += np.float32([-0.4, 0.2, 0.3])  # the glass box
+    moved_it = np.stack([np.linalg.inv(m.astype(np.float64)).T for m in moved]).astype(np.float32)
+    target = scene.SceneBuffers(dict(buffers.arrays, worldMatrices=moved, inverseTransposeWorldMatrices=moved_it), buffers.scalars)
+    a, b = tmp_path / "a.pltscn", tmp_path / "b.pltscn"
+    buffers.save(str(a), cam); target.save(str(b), cam)
+    w, h, frames, after = 96, 54, 5, 2
+    plugin, exe = host
+    r = subprocess.run([exe, "--plugin", plugin, "--scene", str(a), "--moved-scene", str(b), "--move-after", str(after), "--width", str(w), "--height", str(h),
+                        "--frames", str(frames), "--out", str(tmp_path / "anim"), "--prop", "maxBounces=6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(tmp_path / "anim.color.f64", np.float64).reshape(h, w, 4)
+    p = binding.Pltpt(device=0, maxBounces=6)
+    p.set_scene(target)
+    acc = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, after, 1, frames - after, w, h, acc)
+    torch.cuda.synchronize()
+    assert np.allclose(got[..., :3], acc.cpu().numpy()[..., :3], rtol=1e-12, atol=0)
+    still = binding.Pltpt(device=0, maxBounces=6)
+    still.set_scene(buffers)
+    acc2 = torch.zeros_like(acc)
+    still.render_accumulate(cam, after, 1, frames - after, w, h, acc2)
+    torch.cuda.synchronize()
+    assert not np.allclose(got[..., :3], acc2.cpu().numpy()[..., :3], rtol=1e-6, atol=0)  # the move is visible
+    p.close(); still.close()
+
+
+@pytest.mark.gpu
 def test_plugin_reports_library_errors_as_exceptions(host, tmp_path, cornell, torch_cuda):
     """A failing C-ABI call surfaces as Falcor::RuntimeError (exit code 1 of the harness), e.g. the LightBVH sampler the pass does
     not offer: 'Unknown emissive light sampler type' (PLTPT.cpp:409)."""
