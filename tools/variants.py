@@ -18,8 +18,6 @@ from pltfalcor_b200 import build as B  # noqa: E402
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
     "base": {},
-    "a4": {"stage_connect.cu": ["-DPLT_MINB_CONNECT_A=4"]},
-    "t5": {"stage_sample.cu": ["-DPLT_MINB_TRACE=5"], "stage_connect.cu": ["-DPLT_MINB_SHADOW_TRACE=5"]},
 }
 
 
