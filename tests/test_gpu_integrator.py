@@ -269,6 +269,52 @@ def test_full_hd_frame_properties(torch_cuda, cornell):
     p.close()
 
 
+@pytest.mark.parametrize("w,h", [(37, 23), (8, 4), (1, 1), (131, 129)])
+def test_ragged_frame_sizes_match_oracle(w, h, torch_cuda, oracle, cornell):
+    """Widths / heights that are not multiples of the 8x4 primary-ray tiles, a single tile, a single pixel, and a frame just
+    over the split threshold (two lanes, ragged halves)."""
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = cornell
+    p = binding.Pltpt(maxBounces=5)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    c = scene.with_jitter(cam, 4, w, h)
+    gpu_b = p.sample_stage_host(c, 4, w, h)
+    gpu = p.render_frame_host(c, 4, w, h)
+    cpu = osc.render_frame(p.options, c, 4, w, h, want_bounces=True)
+    _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
+    m = parity.compare_color(gpu["color"], cpu["color"], same)
+    assert gpu["color"].shape == (h, w, 4) and m["nonfinite_gpu"] == 0
+    if w * h >= 32:
+        assert same.mean() >= 0.95 and m["frac_pixels_within_1e-2"] >= 0.95, (w, h, m)
+    p.close()
+
+
+@pytest.mark.parametrize("opts,expect_black", [
+    (dict(maxBounces=0), False),                                               # emission seen directly only (one recorded vertex per path)
+    (dict(useEmissiveLights=False, useAnalyticLights=False, useEnvLights=False), True),  # no light source enabled at all
+    (dict(maxBounces=1, doNEE=False, doRussianRoulette=False), False),
+])
+def test_degenerate_light_transport_settings(opts, expect_black, torch_cuda, oracle, cornell):
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = cornell
+    p = binding.Pltpt(**opts)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    w, h = 64, 36
+    c = scene.with_jitter(cam, 1, w, h)
+    gpu = p.render_frame_host(c, 1, w, h)["color"]
+    cpu = osc.render_frame(p.options, c, 1, w, h)["color"]
+    assert np.isfinite(gpu).all() and (gpu[..., 3] == 1).all()
+    if expect_black:
+        assert (gpu[..., :3] == 0).all() and (cpu[..., :3] == 0).all()
+    else:
+        assert gpu[..., :3].max() > 0
+        d = np.abs(gpu[..., :3] - cpu[..., :3]).max(-1)
+        assert (d <= 1e-2 * np.maximum(cpu[..., :3].max(-1), 1e-3)).mean() >= 0.97
+    p.close()
+
+
 def test_render_errors(torch_cuda, cornell):
     from pltfalcor_b200 import binding
     buffers, cam = cornell
