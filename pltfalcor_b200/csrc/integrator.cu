@@ -157,7 +157,7 @@ static int renderTiles(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, 
                 c->markKernel(PLTPT_K_SHADOW_TRACE, s);
                 launchConnectB(P, persistentGrid, s);
                 c->markKernel(PLTPT_K_CONNECT_B, s);
-                c->stats.kernelLaunches += 4;
+                c->stats.kernelLaunches += 3;
             }
             if (P.useEnv) { launchConnectMiss(P, persistentGrid, s); c->markKernel(PLTPT_K_CONNECT_A, s); c->stats.kernelLaunches++; }
             if (P.doMS) { launchMnee(P, persistentGrid, s); c->stats.kernelLaunches += 2; c->markKernel(PLTPT_K_MNEE, s); }

@@ -1177,13 +1177,11 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
 // Half B (pltpt_solve.rt.slang:283-361): visibility / occluder chain, MIS weight, hand-over to the unwind queues (or to k_mnee).
 // Returns true when the entry needs the full half B (connectB): it is then queued for k_connect_b_slow, so that the few entries
 // with an occluder chain / delta sample / emissive hit run densely packed instead of stalling 31 finished lanes each.
-PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
-    const ConnItem item = P.connItems[slot];
+// Called by the shadow-ray kernels right after the ray of `slot` has been traced (`blocked`, `occluderInstance`: its answer).
+PLT_D bool connectBFast(const FrameParams& P, uint32_t pixel, const ConnItem& item, bool blocked, uint32_t occluderInstance) {
     const uint32_t flags = item.info.y;
-    if (!(flags & CI_TRACE)) return false;
     const int p = int(P.level);
     const uint32_t jobId = item.info.x;
-    const bool blocked = P.shadowHits[slot].x != 0xffffffffu;
     // Fast path (pltpt_solve.rt.slang:283-300 with nothing else to do at this vertex): plain visibility answer, no delta sample
     // of the current vertex, no emissive hit.  MIS weight from half A; the emissive slot of a non-emissive vertex is zero; the
     // generator state half A stored is already the one the next vertex continues from (this half would draw nothing).
@@ -1204,7 +1202,7 @@ PLT_D bool connectBFast(const FrameParams& P, uint32_t slot, uint32_t pixel) {
     // (Manifolds.slangh:128-141: the first test after the hit, before any random number is drawn).  An opaque first occluder --
     // the usual case -- ends the connection here, from two table reads, without rebuilding the current vertex.
     if (!(flags & (CI_CURRENT_MS | CI_EMISSIVE)) && blocked) {
-        const uint32_t occluderMaterial = __ldg(&P.sc.instances[P.shadowHits[slot].x].materialID);
+        const uint32_t occluderMaterial = __ldg(&P.sc.instances[occluderInstance].materialID);
         if (P.opt.MNEEMaxOccluders == 0 || !(__ldg(&P.sc.materials[occluderMaterial].propFlags) & P_CanMSTransmissive)) {
             writeContribution(P, pixel, uint32_t(p), 0, mk3(0.f));
             writeContribution(P, pixel, uint32_t(p), 1, mk3(0.f));

@@ -1,12 +1,15 @@
 // stage_connect.cu — first half of the solve stage (reference pltpt_solve.rt.slang:401-476, NEE :245-366, evalEmissive :152-200,
 // MNEE Manifolds.slangh) as a wavefront.  Per recorded-vertex index p (the work list is the sample stage's type-sorted hit list
 // of bounce p, so a warp evaluates one material):
-//   k_connect_a    : light sample + beam sourcing (+ delta sample of the current vertex for MNEE); posts one shadow ray
-//   k_shadow_trace : closest-hit (MNEE on: the first occluder matters) or any-hit traversal of the posted rays
-//   k_connect_b    : visibility / delta-occluder chain, MIS weight, emissive hit; hands the connection to the unwind queues
+//   k_connect_a      : light sample + beam sourcing (+ delta sample of the current vertex for MNEE) + MIS weight of the unoccluded
+//                      connection; posts one shadow ray
+//   k_shadow_trace   : closest-hit (MNEE on: the first occluder matters) or any-hit traversal of the posted rays; a connection whose
+//                      answer settles it (visible / blocked by an opaque occluder, nothing else to do at the vertex) is finished right
+//                      here from the hand-over item: MIS scale, hand-over to the unwind queues
+//   k_connect_b_slow : the others, densely packed: delta-occluder chain, delta sample of the current vertex, emissive hit
 // and once per tile
-//   k_mnee         : manifold walk (Newton + line search, data-dependent trip count) of the connections that crossed delta
-//                    occluders — isolated so that it cannot stall the coherent NEE work (north-star (d)).
+//   k_mnee_walk / k_mnee_finish : manifold walks (Newton + line search, data-dependent trip count) of the connections that crossed
+//                      delta occluders, isolated so that they cannot stall the coherent NEE work (north-star (d)).
 #include "plt_integrator.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -50,25 +53,42 @@ __global__ void __launch_bounds__(kStageThreads) k_connect_miss(const __grid_con
     }
 }
 
+// Appends entry `i` of the level's work list to the deferred list of half B (warp-aggregated; the sample stage's trace queue is
+// idle during the solve stage and is reused for it; k_connect_a of this level zeroed its count).
+__device__ __forceinline__ void deferConnection(const FrameParams& P, uint32_t i) {
+    const uint32_t active = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+    uint32_t at = 0;
+    if (lane == leader) at = atomicAdd(P.levelCount + kTraceCountSlot, uint32_t(__popc(active)));
+    at = __shfl_sync(active, at, leader) + __popc(active & ((1u << lane) - 1u));
+    P.traceQueue[at] = i;
+}
+// After the shadow ray of entry `i` has been traced: settle the connection at once when the answer suffices (connectBFast: the
+// first half of what used to be a separate pass over the same items), otherwise publish the hit for k_connect_b_slow and defer.
+__device__ __forceinline__ void shadowAnswer(const FrameParams& P, const uint32_t* list, uint32_t i, const ConnItem& item, bool hit, const Hit& h) {
+    const bool anyHit = (item.info.y & CI_ANY_HIT) != 0;
+    if (!connectBFast(P, list[i], item, hit, anyHit ? 0u : h.instanceID)) return;
+    P.shadowHits[i] = (hit && !anyHit) ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(hit ? 0u : 0xffffffffu, 0u, 0u, 0u);
+    P.shadowT[i] = h.t;
+    deferConnection(P, i);
+}
+
 // Tiny scenes: one ray per thread per grid-stride iteration (see k_trace_simple).
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace_simple(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
+    const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
         if (i >= n) continue;
-        const uint32_t flags = P.connItems[i].info.y;
-        if (!(flags & CI_TRACE)) continue;
+        const ConnItem item = P.connItems[i];
+        if (!(item.info.y & CI_TRACE)) continue;
         const float4 r0 = P.shadowRays[2 * size_t(i)], r1 = P.shadowRays[2 * size_t(i) + 1];
         const float3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
-        if (flags & CI_ANY_HIT) P.shadowHits[i] = make_uint4(occluded(P, tc, o, d, r0.w, r1.w) ? 0u : 0xffffffffu, 0u, 0u, 0u);
-        else {
-            TriHit th;
-            float t;
-            const bool hit = traceClosestHit(P, tc, o, d, r0.w, r1.w, th, t);
-            P.shadowHits[i] = hit ? make_uint4(th.instanceID, th.primitiveIndex, __float_as_uint(th.u), __float_as_uint(th.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-            P.shadowT[i] = t;
-        }
+        Hit h;
+        const bool hit = (item.info.y & CI_ANY_HIT) ? traverseBvh<true>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc)
+                                                    : traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
+        shadowAnswer(P, list, i, item, hit, h);
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
@@ -76,6 +96,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
 
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow_trace(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
+    const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
     TraversalCounters tc = {0, 0};
     uint32_t* cursor = P.queueCount + QC_ShadowCursor;  // zeroed by k_connect_a of this level
     uint32_t* overflow = reinterpret_cast<uint32_t*>(P.counters + 2);
@@ -85,39 +106,16 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
         o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z); tmin = r0.w; tmax = r1.w;
         return true;
     };
+    auto commit = [&](uint32_t i, bool hit, const Hit& h) { shadowAnswer(P, list, i, P.connItems[i], hit, h); };
     // half A posts any-hit rays when no manifold walk can follow (MNEE off, or no bounce left for an occluder chain): uniform per launch
-    if (!P.doMS || int(P.opt.maxBounces) - int(P.level) <= 0) {
-        travPersistent<true>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch,
-            [&](uint32_t i, bool hit, const Hit&) { P.shadowHits[i] = make_uint4(hit ? 0u : 0xffffffffu, 0u, 0u, 0u); });
-    } else {
-        travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch,
-            [&](uint32_t i, bool hit, const Hit& h) {
-                P.shadowHits[i] = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-                P.shadowT[i] = h.t;
-            });
-    }
+    if (!P.doMS || int(P.opt.maxBounces) - int(P.level) <= 0) travPersistent<true>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch, commit);
+    else travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, n, cursor, overflow, &tc, fetch, commit);
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
 }
 
-// Half B, pass 1: every entry whose shadow-ray answer settles it (connectBFast); the others are appended to the deferred list
-// (the sample stage's trace queue is idle during the solve stage and is reused for it; k_connect_a of this level zeroed its count).
-__global__ void __launch_bounds__(kStageThreads) k_connect_b(const __grid_constant__ FrameParams P) {
-    const uint32_t n = P.levelCount[P.level];
-    const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
-    for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
-        const uint32_t i = base + threadIdx.x;
-        if (i < n && connectBFast(P, i, list[i])) {
-            const uint32_t active = __activemask();
-            const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
-            uint32_t at = 0;
-            if (lane == leader) at = atomicAdd(P.levelCount + kTraceCountSlot, uint32_t(__popc(active)));
-            at = __shfl_sync(active, at, leader) + __popc(active & ((1u << lane) - 1u));
-            P.traceQueue[at] = i;
-        }
-    }
-}
-// Half B, pass 2: the deferred entries, densely packed.
+// Half B for the entries the shadow-ray kernel could not settle (occluder chain, delta sample of the current vertex, emissive hit),
+// densely packed.
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b_slow(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[kTraceCountSlot];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
@@ -239,8 +237,5 @@ void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     if (P.tinyScene) k_shadow_trace_simple<<<grid, kStageThreads, 0, s>>>(P);
     else k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P);
 }
-void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    k_connect_b<<<grid, kStageThreads, 0, s>>>(P);
-    k_connect_b_slow<<<grid, kStageThreads, 0, s>>>(P);
-}
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_b_slow<<<grid, kStageThreads, 0, s>>>(P); }
 }  // namespace plt
