@@ -13,6 +13,6 @@ cap() {  # name regex skip count
 }
 cap unwind "k_unwind_step" 9 9   # all nine replay steps of the second frame: per-launch averages comparable with bench.py's live timers
 cap sample "k_shade|k_trace" 18 4
-cap connect "k_connect_a|k_shadow_trace|k_connect_b" 36 8   # four kernels per bounce (a, shadow, b, b_slow): bounces 0 and 1 of the second frame
+cap connect "k_connect_a|k_shadow_trace|k_connect_b" 27 6   # three kernels per bounce (a, shadow, b_slow): bounces 0 and 1 of the second frame
 # gpurun only merges gpurun_out/ back when it is below 64 MiB in total: the .ncu-rep files stay on the box
 du -sh $out; ls -la $out /tmp/*.ncu-rep
