@@ -213,3 +213,21 @@ def test_eval_spectrum_interpolates_gold(oracle):
         assert abs(got - ref) < 0.02 * max(1.0, abs(ref)), (lam, got, ref)  # table is resampled to <= 128 bins
     assert lib.oracle_eval_spectrum(prof.ctypes.data_as(C.c_void_p), C.c_float(300.0)) == 0.0
     assert lib.oracle_eval_spectrum(prof.ctypes.data_as(C.c_void_p), C.c_float(800.0)) == 0.0
+
+
+def test_oracle_frames_match_their_pinned_copies():
+    """tests/golden/oracle_frames.npz (tools/make_golden_oracle.py): the oracle's own small frames.  Not a reference image (none exists,
+    DESIGN §5) — a tripwire for accidental changes of the checker: discrete path records identical, floats to 1e-4 (libm may differ)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden_oracle", os.path.join(os.path.dirname(__file__), "..", "tools", "make_golden_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_frames.npz"))
+    for name in mod.CASES:
+        got = mod.render(name)
+        same = (got["hit"] == gold[f"{name}/hit"]).all(axis=(-1, -2)) & (got["lobe"] == gold[f"{name}/lobe"]).all(-1) & (got["flags"] == gold[f"{name}/flags"]).all(-1)
+        assert same.mean() >= 0.99, name  # a path may fork where a random number sits within an ulp of a branch threshold
+        for k in ("color", "albedo", "normal"):
+            d = np.abs(got[k] - gold[f"{name}/{k}"])[same]
+            assert (d <= 1e-4 * np.maximum(np.abs(gold[f"{name}/{k}"])[same], 1e-3)).mean() >= 0.995, (name, k, float(d.max()))
