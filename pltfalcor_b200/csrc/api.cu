@@ -497,13 +497,16 @@ __device__ __forceinline__ SD canonicalSd(uint32_t materialID, float3 V) {
     return sd;
 }
 
+#ifndef PLT_MINB_SWEEP
+#define PLT_MINB_SWEEP 4  // 128 registers, 16 resident warps per SM: 5.7 -> 8.2 G evals/s (profiles/r1_variants16_17_sweep_occupancy.log); 5, 6, 8 are slower again
+#endif
 #ifndef PLT_SWEEP_UNROLL
 #define PLT_SWEEP_UNROLL 1
 #endif
 constexpr int kSweepThreads = 128, kSweepUnroll = PLT_SWEEP_UNROLL;
 // One thread per (query, hero group): evaluates the BSDF on the four basis Stokes vectors; results are staged in
 // shared memory (stride 65 words: conflict-free) and written out as fully coalesced 128 B lines.
-__global__ void __launch_bounds__(kSweepThreads) k_bsdf_eval_mueller(DevScene sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups,
+__global__ void __launch_bounds__(kSweepThreads, PLT_MINB_SWEEP) k_bsdf_eval_mueller(DevScene sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups,
                                                                      const float* __restrict__ wi, const float* __restrict__ wo, const float* __restrict__ hero,
                                                                      float* __restrict__ out, int hwss, float maxBeamOmega) {
     extern __shared__ float stage[];  // kSweepThreads * (hwss*16 + 1)

@@ -17,7 +17,10 @@ from pltfalcor_b200 import build as B  # noqa: E402
 
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
-    "base": {},
+    "sw4": {"api.cu": ["-DPLT_MINB_SWEEP=4"]},
+    "sw5": {"api.cu": ["-DPLT_MINB_SWEEP=5"]},
+    "sw6": {"api.cu": ["-DPLT_MINB_SWEEP=6"]},
+    "sw8": {"api.cu": ["-DPLT_MINB_SWEEP=8"]},
 }
 
 
