@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 #define PLT_MINB_CONNECT_B 4  // 128 registers: 16 resident warps per SM instead of 12 (-19% kernel time)
 #endif
 #ifndef PLT_MINB_MNEE
-#define PLT_MINB_MNEE 1
+#define PLT_MINB_MNEE 4  // 128 registers: 21.2 vs 23.7 ms on the 10 M-triangle city, 5.98 vs 5.85 ms on the grating scene (profiles/r1_variants18_mnee_occupancy.log)
 #endif
 namespace plt {
 namespace {

@@ -8,6 +8,9 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from pltfalcor_b200 import binding, layouts as L, scene  # noqa: E402
 
+if os.environ.get("PLTPT_LIB"):
+    binding.LIB = os.environ["PLTPT_LIB"]  # a variant built by tools/variants.py
+
 name = sys.argv[1]
 w, h = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080)
 frames = int(sys.argv[4]) if len(sys.argv) > 4 else 4

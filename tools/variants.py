@@ -17,10 +17,9 @@ from pltfalcor_b200 import build as B  # noqa: E402
 
 VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {
-    "sw4": {"api.cu": ["-DPLT_MINB_SWEEP=4"]},
-    "sw5": {"api.cu": ["-DPLT_MINB_SWEEP=5"]},
-    "sw6": {"api.cu": ["-DPLT_MINB_SWEEP=6"]},
-    "sw8": {"api.cu": ["-DPLT_MINB_SWEEP=8"]},
+    "base": {},
+    "m3": {"stage_connect.cu": ["-DPLT_MINB_MNEE=3"]},
+    "m4": {"stage_connect.cu": ["-DPLT_MINB_MNEE=4"]},
 }
 
 
