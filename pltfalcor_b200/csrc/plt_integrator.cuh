@@ -1132,7 +1132,7 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                 if (!P.opt.HWSSDoMIS && (c.bounce.flags & RF_HasDispersiveDeltaSegment)) ls.beam.comps = 1;
                 uint32_t flags = CI_TRACE | ((P.doMIS && ls.lightType != LT_Analytic) ? CI_DO_MIS : 0u);
                 float msPdf = 1.f;
-                uint32_t lobe0 = 0;
+                uint32_t handover = 0;  // ConnItem::info.w: lobe of the current-vertex delta sample, or the MIS weight of the unoccluded connection
                 bool alive = true;
                 if (!P.doMS || int(P.opt.maxBounces) - p <= 0) flags |= CI_ANY_HIT;
                 else {
@@ -1143,11 +1143,11 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                         ms.hitCount = 0; ms.iterations = 0; ms.pdf = 1.f; ms.dispersive = false; ms.wavelength = ls.beam.wl.x;
                         alive = manifoldSampleVertex(c.bounce.hit, c.sd, c.m, lightDir, c.st.sg, ms) && (ms.hits[0].lobe & L_Reflection) != 0;
                         flags |= CI_CURRENT_MS | (ms.dispersive ? CI_DISPERSIVE : 0u);
-                        msPdf = ms.pdf; lobe0 = ms.hits[0].lobe;
+                        msPdf = ms.pdf; handover = ms.hits[0].lobe;
                     }
                 }
                 if (alive) {
-                    if ((flags & CI_DO_MIS) && !(flags & CI_CURRENT_MS)) lobe0 = __float_as_uint(misWeight(ls.pdf, bsdfPdf(c.m, c.sd, ls.dir, ls.beam.wl.x)));
+                    if ((flags & CI_DO_MIS) && !(flags & CI_CURRENT_MS)) handover = __float_as_uint(misWeight(ls.pdf, bsdfPdf(c.m, c.sd, ls.dir, ls.beam.wl.x)));
                     if (P.useEmissive && (c.m.propFlags & P_IsEmissive)) flags |= CI_EMISSIVE;
                     const uint32_t id = allocJob(P);
                     if (id < P.jobCapacity) {
@@ -1155,7 +1155,7 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
                         h.pixel = pixel; h.bounceIdx = uint32_t(p); h.kind = 0; h.firstIsCurrent = true; h.pathContribution = c.bounce.pathContribution; h.q = uint32_t(p);
                         storeJob(P, id, ls.beam, h);
                         item.dirPdf = mk4(ls.dir.x, ls.dir.y, ls.dir.z, ls.pdf);
-                        item.info = make_uint4(id, flags, __float_as_uint(msPdf), lobe0);
+                        item.info = make_uint4(id, flags, __float_as_uint(msPdf), handover);
                         P.shadowRays[2 * size_t(slot)] = mk4(ls.origin.x, ls.origin.y, ls.origin.z, 0.f);
                         P.shadowRays[2 * size_t(slot) + 1] = mk4(ls.dir.x, ls.dir.y, ls.dir.z, ls.distance);
                         pending = true;
