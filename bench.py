@@ -232,7 +232,10 @@ def main():
         # normally built beforehand by __graft_entry__.build(); a stale or missing library is rebuilt here (nvcc, about a minute)
         # rather than failing the run -- there is no other implementation to fall back to
         try:
-            build.build()
+            import fcntl
+            with open(build.LIB + ".lock", "w") as lock:  # under torchrun every rank gets here: one builds, the others wait and find it fresh
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                build.build()
         except Exception as e:  # noqa: BLE001
             raise SystemExit(f"libpltpt.so is stale or missing and could not be rebuilt ({e}): run `python -c 'import __graft_entry__ as g; g.build()'`")
     if not torch.cuda.is_available():
