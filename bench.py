@@ -13,8 +13,9 @@ K frames per GPU).
 
 Numbers:
   value  device-resident throughput: K frames through pltpt_render_accumulate, scene and accumulators in HBM, CUDA events.
-  e2e    the same metric through the host-buffer C-ABI call a Falcor shell makes without shared surfaces
-         (pltpt_render_frame_host): camera struct H2D and the three RGBA32F RenderData images D2H (pinned) every step.
+  e2e    the same metric through the host-buffer C-ABI calls a Falcor shell makes without shared surfaces: camera struct H2D and
+         the three RGBA32F RenderData images D2H (pinned) every step.  Queued (pltpt_render_frame_host_async + pltpt_host_wait,
+         two frames in flight) is the value; the synchronous call (pltpt_render_frame_host) is reported beside it.
   roofline  dominant kernel (k_unwind_step, the forward replay) against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
             its duration comes from CUDA events recorded after every launch on the launching stream inside the timed region.
   cpu_baseline  the CPU oracle (a restatement of the reference's Slang path; `kind: port`) on the box's host cores.
@@ -311,26 +312,40 @@ def main():
         dist.barrier()
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------------
-    host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+    # Two ways through the same entry-point family, both timed: the synchronous call (returns with the images on the host) and the
+    # queued one (pltpt_render_frame_host_async: the way PLTPT::execute records work and returns; two frames in flight, each with its
+    # own pinned image set, pltpt_host_wait inside the timed region).  The queued figure is the e2e value; the synchronous one is kept beside it.
+    host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(6)]
     e2e_steps = max(4, min(K, 16))
+    e2e_steps += e2e_steps & 1
 
-    def e2e_step(f):
+    def e2e_step(f, i, queued):
         c = scene.with_jitter(cam, f, WIDTH, HEIGHT)
-        binding._check(binding.lib().pltpt_render_frame_host(p.h, f, C.byref(c), WIDTH, HEIGHT, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr()))
+        fn = binding.lib().pltpt_render_frame_host_async if queued else binding.lib().pltpt_render_frame_host
+        b = 3 * (i & 1)
+        binding._check(fn(p.h, f, C.byref(c), WIDTH, HEIGHT, host[b].data_ptr(), host[b + 1].data_ptr(), host[b + 2].data_ptr()))
 
-    for f in range(3):
-        e2e_step(rank + f * world)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for f in range(e2e_steps):
-        e2e_step(1000 + rank + f * world)
-    torch.cuda.synchronize()
-    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = WIDTH * HEIGHT * e2e_steps * world / float(e2e_t.item())
+    def e2e_run(queued):
+        for f in range(4):
+            e2e_step(rank + f * world, f, queued)
+        binding._check(binding.lib().pltpt_host_wait(p.h))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for f in range(e2e_steps):
+            e2e_step(1000 + rank + f * world, f, queued)
+        binding._check(binding.lib().pltpt_host_wait(p.h))
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return WIDTH * HEIGHT * e2e_steps * world / float(t.item())
+
+    e2e_sync_value = e2e_run(False)
+    sync_image = host[3].clone()   # last synchronous frame (odd index -> second image set)
+    e2e_value = e2e_run(True)
+    e2e_queued_equals_sync = bool(torch.equal(sync_image, host[3]))  # same frame index, same jitter: must be the same bits
     checksum = float(host[0][..., :3].double().mean())
 
     if rank == 0:
@@ -363,7 +378,9 @@ def main():
                        "l2": "inputs larger than L2: every frame rewrites and re-reads its %.0f MB bounce buffer (126 MB L2)" % ((MAX_BOUNCES + 1) * WIDTH * HEIGHT * 40 / 1e6),
                        "triangles": int(build_stats["triangleCount"]), "bvh_nodes": int(build_stats["bvhNodes"]), "bvh_build_ms": build_stats["bvhBuildMs"]},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": C.sizeof(L.PltptCameraData), "d2h_bytes_per_step": 3 * WIDTH * HEIGHT * 16, "steps": e2e_steps,
-                    "api": "pltpt_render_frame_host (camera in, color/albedo/normal RGBA32F out, pinned host buffers)", "checksum_mean_rgb": checksum},
+                    "api": "pltpt_render_frame_host_async + pltpt_host_wait (camera in, color/albedo/normal RGBA32F out per frame into pinned host buffers, two frames in flight)",
+                    "synchronous_value": e2e_sync_value, "synchronous_api": "pltpt_render_frame_host (returns with the three images on the host)",
+                    "queued_equals_synchronous": e2e_queued_equals_sync, "checksum_mean_rgb": checksum},
             "gpu_launches": int(timed_stats["kernelLaunches"]),
             "sequential_ms_per_step": seq_ms,
             "clocks": clocks,

@@ -17,6 +17,7 @@ EXPORTS = [
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
+    "pltpt_render_frame_host_async", "pltpt_host_wait",
 ]
 
 
@@ -44,6 +45,8 @@ def lib():
         _lib.pltpt_render_frame.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp]
         _lib.pltpt_render_accumulate.argtypes = [vp, u32, u32, u32, vp, u32, u32, vp, vp]
         _lib.pltpt_render_frame_host.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
+        _lib.pltpt_render_frame_host_async.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
+        _lib.pltpt_host_wait.argtypes = [vp]
         _lib.pltpt_sample_stage_host.argtypes = [vp, u32, vp, u32, u32, vp]
         _lib.pltpt_trace_closest.argtypes = [vp, u32, vp, vp, vp, vp]
         _lib.pltpt_trace_any.argtypes = [vp, u32, vp, vp, vp]
@@ -175,6 +178,14 @@ class Pltpt:
         normal = np.zeros((height, width, 4), np.float32) if want_guides else None
         _check(lib().pltpt_render_frame_host(self.h, frame, C.byref(cam), width, height, _hp(color), _hp(albedo), _hp(normal)))
         return dict(color=color, albedo=albedo, normal=normal)
+
+    def render_frames_host_queued(self, cams_and_frames, width, height):
+        """pltpt_render_frame_host_async for every (camera, frame) pair, then pltpt_host_wait; returns the color images."""
+        out = [np.zeros((height, width, 4), np.float32) for _ in cams_and_frames]
+        for (cam, frame), color in zip(cams_and_frames, out):
+            _check(lib().pltpt_render_frame_host_async(self.h, frame, C.byref(cam), width, height, _hp(color), None, None))
+        _check(lib().pltpt_host_wait(self.h))
+        return out
 
     def sample_stage_host(self, cam, frame, width, height):
         bounces = np.zeros((height, width, self.options.maxBounces + 1), L.bounce_dtype)

@@ -70,6 +70,10 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->guidesReady) cudaEventDestroy(h->guidesReady);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
+    for (cudaStream_t hs : h->hostStream) if (hs) cudaStreamDestroy(hs);
+    if (h->hostCopyStream) cudaStreamDestroy(h->hostCopyStream);
+    for (auto& lane : h->hostFrameDone) for (cudaEvent_t e : lane) if (e) cudaEventDestroy(e);
+    for (auto& lane : h->hostCopyDone) for (cudaEvent_t e : lane) if (e) cudaEventDestroy(e);
     for (auto e : h->kernelEvents) cudaEventDestroy(e);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
@@ -395,6 +399,7 @@ extern "C" int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, 
 extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     PLT_CUDA(cudaSetDevice(h->device));
+    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
     h->hasScene = false;
     h->ownLightCollection = false;
     const bool dev = s->pointersAreDevice != 0;
@@ -620,6 +625,7 @@ static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, ui
     if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
     if (w == 0 || hgt == 0 || w > 65535 || hgt > 65535) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame dimensions must be in 1..65535 (path id packs the pixel in 16+16 bits, Path.slang:166)");
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(PLTPT_ERR_CUDA, "cudaSetDevice failed");
+    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");  // the lanes' work buffers are about to be reused
     return PLTPT_OK;
 }
 extern "C" int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* color, float* albedo, float* normal, void* stream) {
@@ -705,6 +711,44 @@ extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const
     if (colorHost) PLT_CUDA(cudaMemcpyAsync(colorHost, h->outColor.p, bytes, cudaMemcpyDeviceToHost, 0));
     PLT_CUDA(cudaStreamSynchronize(0));
     if (guides) PLT_CUDA(cudaStreamSynchronize(h->copyStream));
+    return PLTPT_OK;
+}
+extern "C" int pltpt_render_frame_host_async(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* colorHost, float* albedoHost, float* normalHost) {
+    if (!h || !cam) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    const bool pending = h->hostAsyncPending;
+    h->hostAsyncPending = false;  // checkRender would drain the queue
+    const int rc = checkRender(h, cam, w, hgt);
+    h->hostAsyncPending = pending;
+    if (rc) return rc;
+    if (!colorHost) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
+    const int lanes = (h->profiling || h->frameOverlap < 2) ? 1 : std::min(h->frameOverlap, int(PltptContext::kLanes));
+    const int l = int(h->hostAsyncNext++ % uint32_t(lanes));
+    if (!h->hostStream[l]) PLT_CUDA(cudaStreamCreateWithFlags(&h->hostStream[l], cudaStreamNonBlocking));
+    if (!h->hostCopyStream) PLT_CUDA(cudaStreamCreateWithFlags(&h->hostCopyStream, cudaStreamNonBlocking));
+    const cudaStream_t s = h->hostStream[l], cs = h->hostCopyStream;
+    const uint32_t k = h->hostSetNext[l]++ & 1u;
+    if (!h->hostFrameDone[l][k]) {
+        PLT_CUDA(cudaEventCreateWithFlags(&h->hostFrameDone[l][k], cudaEventDisableTiming));
+        PLT_CUDA(cudaEventCreateWithFlags(&h->hostCopyDone[l][k], cudaEventDisableTiming));
+    }
+    const size_t bytes = size_t(w) * hgt * 16;
+    plt::DevBuf* out = h->hostOut[l][k];
+    for (int i = 0; i < 3; ++i) PLT_CUDA(out[i].ensure(bytes));
+    h->hostAsyncPending = true;
+    PLT_CUDA(cudaStreamWaitEvent(s, h->hostCopyDone[l][k], 0));  // the set's previous frame must have left for the host (no-op the first time)
+    if (int r = renderFrame(h, l, frameCount, cam, w, hgt, out[0].as<float>(), out[1].as<float>(), out[2].as<float>(), nullptr, true, s)) return r;
+    PLT_CUDA(cudaEventRecord(h->hostFrameDone[l][k], s));
+    PLT_CUDA(cudaStreamWaitEvent(cs, h->hostFrameDone[l][k], 0));
+    PLT_CUDA(cudaMemcpyAsync(colorHost, out[0].p, bytes, cudaMemcpyDeviceToHost, cs));
+    if (albedoHost) PLT_CUDA(cudaMemcpyAsync(albedoHost, out[1].p, bytes, cudaMemcpyDeviceToHost, cs));
+    if (normalHost) PLT_CUDA(cudaMemcpyAsync(normalHost, out[2].p, bytes, cudaMemcpyDeviceToHost, cs));
+    PLT_CUDA(cudaEventRecord(h->hostCopyDone[l][k], cs));
+    return PLTPT_OK;
+}
+extern "C" int pltpt_host_wait(PltptHandle h) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(PLTPT_ERR_CUDA, "cudaSetDevice failed");
+    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
     return PLTPT_OK;
 }
 extern "C" int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, PltptBounce* bouncesHost) {

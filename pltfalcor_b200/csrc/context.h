@@ -113,6 +113,24 @@ struct PltptContext {
     int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
     size_t workBudgetBytes = 0; // per-lane work-buffer budget that sizes the row tiles (0 = default 24 GB; pltpt_set_work_budget)
     plt::DevBuf outColor, outAlbedo, outNormal;
+    // pltpt_render_frame_host_async: frame i runs whole on lane i % frameOverlap, on that lane's own stream, into one of that lane's
+    // two output image sets; its device-to-host copies run on hostCopyStream behind an event, so the lane starts its next frame
+    // (other image set) at once and only waits for a set's previous copy before overwriting that set
+    cudaStream_t hostStream[kLanes] = {};
+    cudaStream_t hostCopyStream = nullptr;
+    plt::DevBuf hostOut[kLanes][2][3];
+    cudaEvent_t hostFrameDone[kLanes][2] = {}, hostCopyDone[kLanes][2] = {};
+    uint32_t hostSetNext[kLanes] = {};
+    uint32_t hostAsyncNext = 0;
+    bool hostAsyncPending = false;
+    int waitHostAsync() {
+        if (!hostAsyncPending) return 0;
+        hostAsyncPending = false;
+        int bad = 0;
+        for (cudaStream_t s : hostStream) if (s && cudaStreamSynchronize(s) != cudaSuccess) bad = 1;
+        if (hostCopyStream && cudaStreamSynchronize(hostCopyStream) != cudaSuccess) bad = 1;
+        return bad;
+    }
     PltptStats stats{};
     cudaEvent_t evA = nullptr, evB = nullptr;
     // per-kernel timers (pltpt_set_profiling): event after every launch, tagged with the kernel class that precedes it (0xff = frame start)

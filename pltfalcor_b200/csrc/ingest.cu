@@ -391,6 +391,7 @@ extern "C" int pltpt_update_transforms(PltptHandle h, const float* worldMatrices
     for (const auto& gi : h->hInstances)
         if (gi.globalMatrixID >= matrixCount) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "an instance refers to a matrix beyond matrixCount");
     PLT_CUDA(cudaSetDevice(h->device));
+    if (h->waitHostAsync()) return ifail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
     if (int r = syncFrameStats(h)) return r;  // frames in flight read the old BVH
     PLT_CUDA(cudaDeviceSynchronize());
     const cudaMemcpyKind kind = pointersAreDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

@@ -339,3 +339,36 @@ def test_render_errors(torch_cuda, cornell):
         p.set_scene(bad)
     assert e.value.code == 3
     p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell", "grating_sphere"])
+def test_queued_host_frames_equal_the_synchronous_ones(name, torch_cuda):
+    """pltpt_render_frame_host_async + pltpt_host_wait: frames queued on alternating lanes, copies under the next frame's kernels;
+    every image must equal the one pltpt_render_frame_host returns, bit for bit, including guides, and a synchronous call made
+    while frames are queued must wait for them."""
+    import ctypes as C
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = _scene(name)
+    p = binding.Pltpt(maxBounces=6)
+    p.set_scene(buffers)
+    w, h = 176, 132
+    cams = [(scene.with_jitter(cam, f, w, h), f) for f in (0, 1, 2, 3, 4)]
+    want = [p.render_frame_host(c, f, w, h) for c, f in cams]
+    got = p.render_frames_host_queued(cams, w, h)
+    for a, b in zip(want, got):
+        assert np.array_equal(a["color"], b)
+    assert float(got[0][..., :3].sum()) > 0
+    # guides through pinned buffers, then a synchronous frame without an explicit wait in between
+    host = [torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True) for _ in range(6)]
+    for i, (c, f) in enumerate(cams[:2]):
+        binding._check(binding.lib().pltpt_render_frame_host_async(p.h, f, C.byref(c), w, h, host[3 * i].data_ptr(), host[3 * i + 1].data_ptr(), host[3 * i + 2].data_ptr()))
+    again = p.render_frame_host(*cams[2], w, h)   # drains the queue first
+    for i in range(2):
+        assert np.array_equal(host[3 * i].numpy(), want[i]["color"]) and np.array_equal(host[3 * i + 1].numpy(), want[i]["albedo"]) and np.array_equal(host[3 * i + 2].numpy(), want[i]["normal"])
+    assert np.array_equal(again["color"], want[2]["color"])
+    binding._check(binding.lib().pltpt_host_wait(p.h))  # nothing queued: returns at once
+    with pytest.raises(binding.PltptError):
+        binding._check(binding.lib().pltpt_render_frame_host_async(p.h, 0, C.byref(cam), w, h, None, None, None))
+    p.close()
