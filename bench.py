@@ -315,27 +315,32 @@ def main():
     # Two ways through the same entry-point family, both timed: the synchronous call (returns with the images on the host) and the
     # queued one (pltpt_render_frame_host_async: the way PLTPT::execute records work and returns; two frames in flight, each with its
     # own pinned image set, pltpt_host_wait inside the timed region).  The queued figure is the e2e value; the synchronous one is kept beside it.
-    host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(6)]
-    e2e_steps = max(4, min(K, 16))
-    e2e_steps += e2e_steps & 1
+    host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(9)]  # three image sets
+    e2e_steps = 3 * ((max(4, min(K, 16)) + 2) // 3)   # a multiple of the three image sets, so both runs end on the same set
+    wait = binding.lib().pltpt_host_wait
 
     def e2e_step(f, i, queued):
         c = scene.with_jitter(cam, f, WIDTH, HEIGHT)
-        fn = binding.lib().pltpt_render_frame_host_async if queued else binding.lib().pltpt_render_frame_host
-        b = 3 * (i & 1)
-        binding._check(fn(p.h, f, C.byref(c), WIDTH, HEIGHT, host[b].data_ptr(), host[b + 1].data_ptr(), host[b + 2].data_ptr()))
+        b = 3 * (i % 3)
+        if queued:
+            # the consumer pattern of include/pltpt.h: queue frame i, then wait until only two frames are on their way, i.e. frame
+            # i-2 is in its host buffers and its image set is free for frame i+1
+            binding._check(binding.lib().pltpt_render_frame_host_async(p.h, f, C.byref(c), WIDTH, HEIGHT, host[b].data_ptr(), host[b + 1].data_ptr(), host[b + 2].data_ptr()))
+            binding._check(wait(p.h, 2))
+        else:
+            binding._check(binding.lib().pltpt_render_frame_host(p.h, f, C.byref(c), WIDTH, HEIGHT, host[b].data_ptr(), host[b + 1].data_ptr(), host[b + 2].data_ptr()))
 
     def e2e_run(queued):
         for f in range(4):
             e2e_step(rank + f * world, f, queued)
-        binding._check(binding.lib().pltpt_host_wait(p.h))
+        binding._check(wait(p.h, 0))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for f in range(e2e_steps):
             e2e_step(1000 + rank + f * world, f, queued)
-        binding._check(binding.lib().pltpt_host_wait(p.h))
+        binding._check(wait(p.h, 0))
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -343,10 +348,10 @@ def main():
         return WIDTH * HEIGHT * e2e_steps * world / float(t.item())
 
     e2e_sync_value = e2e_run(False)
-    sync_image = host[3].clone()   # last synchronous frame (odd index -> second image set)
+    sync_image = host[6].clone()   # last synchronous frame (third image set)
     e2e_value = e2e_run(True)
-    e2e_queued_equals_sync = bool(torch.equal(sync_image, host[3]))  # same frame index, same jitter: must be the same bits
-    checksum = float(host[0][..., :3].double().mean())
+    e2e_queued_equals_sync = bool(torch.equal(sync_image, host[6]))  # same frame index, same jitter: must be the same bits
+    checksum = float(host[6][..., :3].double().mean())
 
     if rank == 0:
         pb = path_bytes(stats, K, paths_per_gpu)
@@ -378,7 +383,7 @@ def main():
                        "l2": "inputs larger than L2: every frame rewrites and re-reads its %.0f MB bounce buffer (126 MB L2)" % ((MAX_BOUNCES + 1) * WIDTH * HEIGHT * 40 / 1e6),
                        "triangles": int(build_stats["triangleCount"]), "bvh_nodes": int(build_stats["bvhNodes"]), "bvh_build_ms": build_stats["bvhBuildMs"]},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": C.sizeof(L.PltptCameraData), "d2h_bytes_per_step": 3 * WIDTH * HEIGHT * 16, "steps": e2e_steps,
-                    "api": "pltpt_render_frame_host_async + pltpt_host_wait (camera in, color/albedo/normal RGBA32F out per frame into pinned host buffers, two frames in flight)",
+                    "api": "pltpt_render_frame_host_async + pltpt_host_wait (camera in, color/albedo/normal RGBA32F out per frame into pinned host buffers, two frames in flight, pltpt_host_wait(h, 2) after every frame)",
                     "synchronous_value": e2e_sync_value, "synchronous_api": "pltpt_render_frame_host (returns with the three images on the host)",
                     "queued_equals_synchronous": e2e_queued_equals_sync, "checksum_mean_rgb": checksum},
             "gpu_launches": int(timed_stats["kernelLaunches"]),

@@ -349,14 +349,17 @@ PLTPT_API int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const 
  * its dispatches and returns (PLTPT.cpp:357-499; the frame is complete only after the render context's flush).  Consecutive
  * calls go to alternating frame lanes (pltpt_set_frame_overlap), each with its own stream and output images, so the copies of
  * one frame run under the kernels of the next.  The host buffers of a queued frame (pinned, or the copies serialise) must stay
- * untouched until pltpt_host_wait returns; with two frames in flight the caller alternates two sets.  colorHost is required.
+ * untouched until pltpt_host_wait says the frame has arrived.  colorHost is required.
  * Every other entry point that renders, changes the scene or destroys the handle waits for the queue first.  Pixel values are
  * those of pltpt_render_frame_host bit for bit. */
 PLTPT_API int pltpt_render_frame_host_async(PltptHandle h, uint32_t frameCount, const PltptCameraData* camera,
                                             uint32_t width, uint32_t height,
                                             float* colorHost, float* albedoHost, float* normalHost);
-/* Blocks until every frame queued by pltpt_render_frame_host_async is in its host buffers; reports a failed frame. */
-PLTPT_API int pltpt_host_wait(PltptHandle h);
+/* Blocks until at most `keepInFlight` of the frames queued by pltpt_render_frame_host_async are still on their way (frames
+ * complete in the order they were queued); 0 = every queued frame is in its host buffers.  A consumer that works on frame i-2
+ * while frames i-1 and i render calls pltpt_host_wait(h, 2) after queueing frame i and cycles three host image sets.  Reports a
+ * failed frame. */
+PLTPT_API int pltpt_host_wait(PltptHandle h, uint32_t keepInFlight);
 
 /* Sample-stage only; copies the bounce buffer ((maxBounces+1) records per pixel, pixel-major,
  * pltpt.slangh:132-136 with the tile spanning the whole frame) to host for parity checks. */

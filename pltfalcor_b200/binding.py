@@ -46,7 +46,7 @@ def lib():
         _lib.pltpt_render_accumulate.argtypes = [vp, u32, u32, u32, vp, u32, u32, vp, vp]
         _lib.pltpt_render_frame_host.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
         _lib.pltpt_render_frame_host_async.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
-        _lib.pltpt_host_wait.argtypes = [vp]
+        _lib.pltpt_host_wait.argtypes = [vp, u32]
         _lib.pltpt_sample_stage_host.argtypes = [vp, u32, vp, u32, u32, vp]
         _lib.pltpt_trace_closest.argtypes = [vp, u32, vp, vp, vp, vp]
         _lib.pltpt_trace_any.argtypes = [vp, u32, vp, vp, vp]
@@ -184,7 +184,7 @@ class Pltpt:
         out = [np.zeros((height, width, 4), np.float32) for _ in cams_and_frames]
         for (cam, frame), color in zip(cams_and_frames, out):
             _check(lib().pltpt_render_frame_host_async(self.h, frame, C.byref(cam), width, height, _hp(color), None, None))
-        _check(lib().pltpt_host_wait(self.h))
+        _check(lib().pltpt_host_wait(self.h, 0))
         return out
 
     def sample_stage_host(self, cam, frame, width, height):

@@ -743,12 +743,13 @@ extern "C" int pltpt_render_frame_host_async(PltptHandle h, uint32_t frameCount,
     if (albedoHost) PLT_CUDA(cudaMemcpyAsync(albedoHost, out[1].p, bytes, cudaMemcpyDeviceToHost, cs));
     if (normalHost) PLT_CUDA(cudaMemcpyAsync(normalHost, out[2].p, bytes, cudaMemcpyDeviceToHost, cs));
     PLT_CUDA(cudaEventRecord(h->hostCopyDone[l][k], cs));
+    h->hostSeqEvent[h->hostSeq++ % 8] = h->hostCopyDone[l][k];
     return PLTPT_OK;
 }
-extern "C" int pltpt_host_wait(PltptHandle h) {
+extern "C" int pltpt_host_wait(PltptHandle h, uint32_t keepInFlight) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(PLTPT_ERR_CUDA, "cudaSetDevice failed");
-    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    if (h->waitHostAsyncKeep(keepInFlight)) return fail(PLTPT_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
     return PLTPT_OK;
 }
 extern "C" int pltpt_sample_stage_host(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, PltptBounce* bouncesHost) {

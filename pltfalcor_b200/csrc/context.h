@@ -122,7 +122,16 @@ struct PltptContext {
     cudaEvent_t hostFrameDone[kLanes][2] = {}, hostCopyDone[kLanes][2] = {};
     uint32_t hostSetNext[kLanes] = {};
     uint32_t hostAsyncNext = 0;
+    uint64_t hostSeq = 0;                  // frames queued so far; the copy stream finishes them in this order
+    cudaEvent_t hostSeqEvent[8] = {};      // copy-done event of frame (seq % 8), borrowed from hostCopyDone
     bool hostAsyncPending = false;
+    // waits until at most `keep` queued frames are still on their way to the host
+    int waitHostAsyncKeep(uint32_t keep) {
+        if (keep == 0 || !hostAsyncPending) return waitHostAsync();
+        if (hostSeq <= keep) return 0;
+        cudaEvent_t e = hostSeqEvent[(hostSeq - keep - 1) % 8];  // a re-recorded event only makes the wait longer
+        return e && cudaEventSynchronize(e) != cudaSuccess ? 1 : 0;
+    }
     int waitHostAsync() {
         if (!hostAsyncPending) return 0;
         hostAsyncPending = false;

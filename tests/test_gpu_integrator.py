@@ -368,7 +368,15 @@ def test_queued_host_frames_equal_the_synchronous_ones(name, torch_cuda):
     for i in range(2):
         assert np.array_equal(host[3 * i].numpy(), want[i]["color"]) and np.array_equal(host[3 * i + 1].numpy(), want[i]["albedo"]) and np.array_equal(host[3 * i + 2].numpy(), want[i]["normal"])
     assert np.array_equal(again["color"], want[2]["color"])
-    binding._check(binding.lib().pltpt_host_wait(p.h))  # nothing queued: returns at once
+    # partial wait: with three frames queued, pltpt_host_wait(h, 1) returns once the first two have arrived
+    for i, (c, f) in enumerate(cams[:3]):
+        host[i].zero_()
+        binding._check(binding.lib().pltpt_render_frame_host_async(p.h, f, C.byref(c), w, h, host[i].data_ptr(), None, None))
+    binding._check(binding.lib().pltpt_host_wait(p.h, 1))
+    assert np.array_equal(host[0].numpy(), want[0]["color"]) and np.array_equal(host[1].numpy(), want[1]["color"])
+    binding._check(binding.lib().pltpt_host_wait(p.h, 0))
+    assert np.array_equal(host[2].numpy(), want[2]["color"])
+    binding._check(binding.lib().pltpt_host_wait(p.h, 0))  # nothing queued: returns at once
     with pytest.raises(binding.PltptError):
         binding._check(binding.lib().pltpt_render_frame_host_async(p.h, 0, C.byref(cam), w, h, None, None, None))
     p.close()
