@@ -177,13 +177,13 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = w * h * args.steps / dt
     sample = f"each step = one frame at {w}x{h} (1/16 of the 1920x1080 pixels, same scene/camera/options)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "plt_paths_per_s", "value": value, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "max_bounces": MAX_BOUNCES, "hwss": 4, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def bsdf_sweep(torch, p, ids, hbm_peak):
@@ -214,7 +214,29 @@ def bsdf_sweep(torch, p, ids, hbm_peak):
     return res
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly one JSON line on stdout, but libraries write there too (NCCL prints its version banner to fd 1 on the
+    first communicator, whatever NCCL_DEBUG_FILE says).  Keep the real stdout aside for the result and point fd 1 at stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(result):
+    line = (json.dumps(result) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=32)
@@ -411,7 +433,7 @@ def main():
                 for key, v in cpu_sw.items():
                     out["bsdf_sweep"][key]["cpu_oracle"] = v
                     out["bsdf_sweep"][key]["gpu_over_cpu"] = out["bsdf_sweep"][key]["evals_per_s"] / v["evals_per_s"]
-        print(json.dumps(out))
+        emit(out)
     p.close()
     if world > 1:
         dist.destroy_process_group()
