@@ -338,7 +338,7 @@ def main():
     # queued one (pltpt_render_frame_host_async: the way PLTPT::execute records work and returns; two frames in flight, each with its
     # own pinned image set, pltpt_host_wait inside the timed region).  The queued figure is the e2e value; the synchronous one is kept beside it.
     host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(9)]  # three image sets
-    e2e_steps = 3 * ((max(4, min(K, 16)) + 2) // 3)   # a multiple of the three image sets, so both runs end on the same set
+    e2e_steps = 3 * ((max(4, min(K, 64)) + 2) // 3)   # a multiple of the three image sets, so both runs end on the same set
     wait = binding.lib().pltpt_host_wait
 
     def e2e_step(f, i, queued):
