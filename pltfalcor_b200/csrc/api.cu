@@ -64,6 +64,7 @@ extern "C" int pltpt_destroy(PltptHandle h) {
     for (auto& ln : h->lanes) {
         for (auto e : ln.timerEvents) cudaEventDestroy(e);
         if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.lastUse) cudaEventDestroy(ln.lastUse);
         if (ln.guidesReady) cudaEventDestroy(ln.guidesReady);
         if (ln.stream) cudaStreamDestroy(ln.stream);
     }
@@ -620,12 +621,17 @@ extern "C" int pltpt_trace_any(PltptHandle h, uint32_t n, const float* rays, uin
 }
 
 // ------------------------------------------------------------------------------------------------ rendering
-static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, uint32_t hgt) {
+static int checkRenderArgs(PltptHandle h, const PltptCameraData* cam, uint32_t w, uint32_t hgt) {
     if (!h || !cam) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
     if (w == 0 || hgt == 0 || w > 65535 || hgt > 65535) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame dimensions must be in 1..65535 (path id packs the pixel in 16+16 bits, Path.slang:166)");
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(PLTPT_ERR_CUDA, "cudaSetDevice failed");
-    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");  // the lanes' work buffers are about to be reused
+    return PLTPT_OK;
+}
+// every entry point that renders outside the host-frame queue: the lanes' work buffers are about to be reused, so the queue drains first
+static int checkRender(PltptHandle h, const PltptCameraData* cam, uint32_t w, uint32_t hgt) {
+    if (int r = checkRenderArgs(h, cam, w, hgt)) return r;
+    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
     return PLTPT_OK;
 }
 extern "C" int pltpt_render_frame(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* color, float* albedo, float* normal, void* stream) {
@@ -714,12 +720,7 @@ extern "C" int pltpt_render_frame_host(PltptHandle h, uint32_t frameCount, const
     return PLTPT_OK;
 }
 extern "C" int pltpt_render_frame_host_async(PltptHandle h, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, float* colorHost, float* albedoHost, float* normalHost) {
-    if (!h || !cam) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
-    const bool pending = h->hostAsyncPending;
-    h->hostAsyncPending = false;  // checkRender would drain the queue
-    const int rc = checkRender(h, cam, w, hgt);
-    h->hostAsyncPending = pending;
-    if (rc) return rc;
+    if (int r = checkRenderArgs(h, cam, w, hgt)) return r;
     if (!colorHost) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
     const int lanes = (h->profiling || h->frameOverlap < 2) ? 1 : std::min(h->frameOverlap, int(PltptContext::kLanes));
     const int l = int(h->hostAsyncNext++ % uint32_t(lanes));
@@ -736,6 +737,8 @@ extern "C" int pltpt_render_frame_host_async(PltptHandle h, uint32_t frameCount,
     for (int i = 0; i < 3; ++i) PLT_CUDA(out[i].ensure(bytes));
     h->hostAsyncPending = true;
     PLT_CUDA(cudaStreamWaitEvent(s, h->hostCopyDone[l][k], 0));  // the set's previous frame must have left for the host (no-op the first time)
+    // work queued on this lane by another entry point (on the caller's stream) must finish before the lane's buffers are reused
+    if (h->lanes[l].lastUse) PLT_CUDA(cudaStreamWaitEvent(s, h->lanes[l].lastUse, 0));
     if (int r = renderFrame(h, l, frameCount, cam, w, hgt, out[0].as<float>(), out[1].as<float>(), out[2].as<float>(), nullptr, true, s)) return r;
     PLT_CUDA(cudaEventRecord(h->hostFrameDone[l][k], s));
     PLT_CUDA(cudaStreamWaitEvent(cs, h->hostFrameDone[l][k], 0));

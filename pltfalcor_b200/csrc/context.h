@@ -100,6 +100,7 @@ struct PltptContext {
         plt::DevBuf accum;                     // lane-private RGBA64F sums (lanes >= 1), merged into the caller's buffer at the end
         cudaStream_t stream = nullptr;         // own non-blocking stream (lanes >= 1)
         cudaEvent_t done = nullptr, guidesReady = nullptr;
+        cudaEvent_t lastUse = nullptr;         // recorded after every frame on the stream it ran on (orders the host-frame queue behind it)
         uint32_t partialFrames = 0;            // lower halves of split frames among timerCount
         bool statsDirty = false;
         std::vector<cudaEvent_t> timerEvents;  // kTimerRing x {start, after sample stage, after solve stage}

@@ -206,6 +206,8 @@ int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCamer
     if (int r = ensureTimers(ln)) return r;
     if (ln.timerCount == PltptContext::kTimerRing || c->kernelEventCount > 60000) { if (int r = syncFrameStats(c)) return r; }
     if (int r = renderTiles(c, ln, P, tileRows, rowBegin, rowEnd, solve, nullptr, s)) return r;
+    if (!ln.lastUse) PLT_CUDA(cudaEventCreateWithFlags(&ln.lastUse, cudaEventDisableTiming));
+    PLT_CUDA(cudaEventRecord(ln.lastUse, s));
     ln.timerCount++;
     ln.timerStream = s;
     ln.statsDirty = true;

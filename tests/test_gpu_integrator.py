@@ -368,6 +368,11 @@ def test_queued_host_frames_equal_the_synchronous_ones(name, torch_cuda):
     for i in range(2):
         assert np.array_equal(host[3 * i].numpy(), want[i]["color"]) and np.array_equal(host[3 * i + 1].numpy(), want[i]["albedo"]) and np.array_equal(host[3 * i + 2].numpy(), want[i]["normal"])
     assert np.array_equal(again["color"], want[2]["color"])
+    # frames queued right behind work another entry point left in flight on both lanes
+    acc = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 0, 1, 6, w, h, acc)
+    behind = p.render_frames_host_queued(cams[:2], w, h)
+    assert np.array_equal(behind[0], want[0]["color"]) and np.array_equal(behind[1], want[1]["color"])
     # partial wait: with three frames queued, pltpt_host_wait(h, 1) returns once the first two have arrived
     for i, (c, f) in enumerate(cams[:3]):
         host[i].zero_()
