@@ -149,3 +149,26 @@ def test_gold_mirror_follows_the_complex_fresnel_equations(osc):
     assert _close(np.hypot(M[:, 1, 3], M[:, 2, 3]), np.abs(cross.imag), **tol)        # retardance: linear -> circular
     assert np.median(np.abs(M[:, 0, 0] - (Rs + Rp) / 2)) < 3e-4 and np.median(np.abs(np.hypot(M[:, 1, 3], M[:, 2, 3]) - np.abs(cross.imag))) < 3e-4
     assert M[:, 0, 0].min() > 0.3 and M[:, 0, 0].max() < 1.0                           # gold: 35-40 % in the blue, > 95 % in the red
+
+
+def test_grating_lobes_obey_the_grating_equation(osc):
+    """1-D Au grating, pitch 3 um along x, incidence in the plane normal to the grooves: every sampled diffraction lobe leaves in that
+    plane with sin(theta_o) = m lambda / pitch - sin(theta_i), m = +-1..3 equal to the order encoded in bits 8-15 of the lobe word
+    (order in the low six bits, 0x40 = sign; PLTDiffractionGratedConductorMaterial.slang:54-66)."""
+    o, ids = osc
+    rng = np.random.default_rng(6)
+    n = 8192
+    th = rng.uniform(-1.3, 1.3, n)
+    wi = np.stack([np.sin(th), np.zeros(n), np.cos(th)], -1).astype(np.float32)
+    wl = rng.uniform(380, 720, n).astype(np.float32)
+    s = o.bsdf_sample(ids["grated_conductor"], L.LOBE_ALL, wi, wl, seed=3)
+    lobe = s[:, 4].copy().view(np.uint32)
+    ok = (s[:, 6] > 0) & ((lobe & L.LOBE_DISPERSIVE_DELTA_REFLECTION) != 0) & (np.abs(s[:, 0:3]).sum(axis=1) > 0)   # evanescent orders come back as a zero direction
+    assert ok.sum() > 3000
+    wo, w = s[ok, 0:3].astype(np.float64), wi[ok].astype(np.float64)
+    order = (wo[:, 0] + w[:, 0]) / (wl[ok].astype(np.float64) * 1e-3 / 3.0)   # wi points away from the surface: sin(theta_i) = -wi.x for the arriving ray
+    code = lobe[ok] >> 8
+    want = (code & 0x3F).astype(np.float64) * np.where(code & 0x40, 1.0, -1.0)
+    assert np.abs(order - want).max() < 2e-4, np.abs(order - want).max()
+    assert set(np.unique(np.abs(want))) == {1.0, 2.0, 3.0}
+    assert np.abs(wo[:, 1]).max() == 0 and np.abs(np.linalg.norm(wo, axis=1) - 1).max() < 1e-6 and (wo[:, 2] > 0).all()
