@@ -172,3 +172,21 @@ def test_grating_lobes_obey_the_grating_equation(osc):
     assert np.abs(order - want).max() < 2e-4, np.abs(order - want).max()
     assert set(np.unique(np.abs(want))) == {1.0, 2.0, 3.0}
     assert np.abs(wo[:, 1]).max() == 0 and np.abs(np.linalg.norm(wo, axis=1) - 1).max() < 1e-6 and (wo[:, 2] > 0).all()
+
+
+def test_diffuse_sampling_is_cosine_weighted(osc):
+    from tests import parity
+    o, ids = osc
+    rng = np.random.default_rng(11)
+    n = 1 << 16
+    wi = parity.random_dirs(rng, n, upper=True)
+    s = o.bsdf_sample(ids["diffuse"], L.LOBE_ALL, wi, rng.uniform(400, 700, n).astype(np.float32), seed=5)
+    ok = s[:, 6] > 0
+    assert ok.mean() > 0.999
+    wo, pdf = s[ok, 0:3].astype(np.float64), s[ok, 3].astype(np.float64)   # columns: wo, pdf, lobe bits, weight, valid, pdf() of the pair
+    assert np.abs(pdf - wo[:, 2] / np.pi).max() < 1e-6 and (wo[:, 2] > 0).all()
+    m = ok.sum()
+    assert abs(wo[:, 2].mean() - 2 / 3) < 4 * np.sqrt(1 / 18 / m)            # E[cos] = 2/3, Var[cos] = 1/18 under the cosine density
+    assert abs((wo[:, 2] ** 2).mean() - 0.5) < 4 * np.sqrt(1 / 12 / m)        # E[cos^2] = 1/2, Var = 1/12
+    phi = np.arctan2(wo[:, 1], wo[:, 0])
+    assert abs(np.cos(phi).mean()) < 4 * np.sqrt(0.5 / m) and abs(np.sin(2 * phi).mean()) < 4 * np.sqrt(0.5 / m)   # uniform azimuth
