@@ -1,0 +1,53 @@
+"""Radiometric laws the CPU oracle's integrator must reproduce (no reference render exists to compare with): direct lighting
+of a Lambertian plane by a small area emitter follows A cos(theta_l) cos(theta_s) / r^2 and scales with the albedo, and the radiance of
+a directly seen emitter does not depend on the viewing distance.  Ratios only, so that the emission spectrum and the colour conversion
+cancel.  Deterministic (seeds derive from pixel and frame index)."""
+import numpy as np
+import pytest
+
+from pltfalcor_b200 import layouts as L
+from pltfalcor_b200 import scene as S
+
+
+def _lit_plane(oracle, h, d, albedo, half=0.05, frames=48):
+    b = S.SceneBuilder()
+    lamp = b.add_emission_profile(S.LAMP)
+    ground = b.add_diffuse((albedo,) * 3)
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    b.add_mesh(S.quad([-10, 0, 10], [10, 0, 10], [10, 0, -10], [-10, 0, -10]), ground)                       # normal +y
+    b.add_mesh(S.quad([-half, h, -half], [half, h, -half], [half, h, half], [-half, h, half]), light)        # normal -y
+    cam = S.make_camera([d, 3.0, 4.0], [d, 0.0, 0.0], focal_length=2000.0, aspect=1.0)                       # ~0.7 degree field of view around (d, 0, 0)
+    osc = oracle.OracleScene(b.finalize())
+    opts = L.make_options(maxBounces=2)
+    w = 8
+    acc = np.zeros(3)
+    for f in range(frames):
+        acc += osc.render_frame(opts, S.with_jitter(cam, f, w, w), f, w, w)["color"][..., :3].reshape(-1, 3).mean(axis=0)
+    return acc / frames
+
+
+def test_direct_lighting_follows_the_inverse_square_and_cosine_laws(oracle):
+    d = 0.5
+    near, far = _lit_plane(oracle, 1.0, d, 0.5), _lit_plane(oracle, 2.0, d, 0.5)
+    geom = lambda h: h * h / (d * d + h * h) ** 2          # cos_l cos_s / r^2 with both cosines = h / r
+    assert near.min() > 0 and far.min() > 0
+    ratio = near / far
+    assert np.abs(ratio / (geom(1.0) / geom(2.0)) - 1).max() < 0.03, ratio   # 2.89 expected in every channel
+
+
+def test_direct_lighting_scales_with_the_albedo(oracle):
+    bright, dark = _lit_plane(oracle, 1.0, 0.5, 0.5), _lit_plane(oracle, 1.0, 0.5, 0.25)
+    assert np.abs(bright / dark / 2.0 - 1).max() < 0.03, bright / dark
+
+
+def test_radiance_of_a_seen_emitter_does_not_depend_on_distance(oracle):
+    def seen(dist):
+        b = S.SceneBuilder()
+        light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=b.add_emission_profile(S.LAMP))
+        b.add_mesh(S.quad([-1, 5, -1], [1, 5, -1], [1, 5, 1], [-1, 5, 1]), light)                               # normal -y
+        cam = S.make_camera([0.0, 5.0 - dist, 0.0], [0.0, 5.0, 0.0], up=(0, 0, 1), focal_length=400.0, aspect=1.0)
+        osc = oracle.OracleScene(b.finalize())
+        opts = L.make_options(maxBounces=1)
+        return np.mean([osc.render_frame(opts, cam, f, 8, 8)["color"][..., :3].reshape(-1, 3).mean(axis=0) for f in range(48)], axis=0)
+    a, c = seen(1.0), seen(4.0)
+    assert a.min() > 0 and np.abs(a / c - 1).max() < 0.03, (a, c)
