@@ -81,3 +81,33 @@ def test_light_sampling_and_bsdf_sampling_agree(oracle):
     assert nee_only.min() > 0
     assert np.abs(bsdf_only / nee_only - 1).max() < 0.04, bsdf_only / nee_only
     assert (mis > nee_only).all() and (mis < 1.5 * nee_only).all(), mis / nee_only
+
+
+def test_brewster_reflection_is_extinguished_by_the_camera_polariser(oracle):
+    """End-to-end polarisation chain (emitter -> Fresnel Mueller matrix of a smooth dielectric at Brewster's angle -> beam frame rotations ->
+    camera polariser, pltpt_solve.rt.slang:111-125): the reflected light is fully linearly polarised, so one polariser orientation
+    passes all of it, the opposite one extinguishes it, and opposite orientations always add up to the unpolarised reading.
+    The orientation scale is the reference's own: MuellerPolarizer (Mueller.slang:60-74) takes cos / sin of `polarizerTheta` itself and
+    MuellerT (:34-53) maps Q to U for aligned frames, which puts the extinction of s-polarised light at polarizerTheta = pi / 2."""
+    import math
+    b = S.SceneBuilder()
+    glass = b.add_dielectric(1.5, 0.0)
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=b.add_emission_profile(S.LAMP))
+    b.add_mesh(S.quad([-10, 0, 10], [10, 0, 10], [10, 0, -10], [-10, 0, -10]), glass)
+    b.add_mesh(S.quad([-30, 6, -30], [30, 6, -30], [30, 6, 30], [-30, 6, 30]), light)
+    osc = oracle.OracleScene(b.finalize())
+    opts = L.make_options(maxBounces=3, doRussianRoulette=False)
+
+    def reading(polarizer, theta):
+        cam = S.make_camera([0.0, 1.0, 1.5], [0.0, 0.0, 0.0], focal_length=2000.0, aspect=1.0, polarizer=polarizer, polarizer_theta=theta)   # tan(incidence) = 1.5 = eta
+        return np.mean([osc.render_frame(opts, cam, f, 8, 8)["color"][..., :3].reshape(-1, 3).mean(axis=0) for f in range(24)], axis=0)
+
+    plain = reading(0.0, 0.0)
+    blocked, passed = reading(1.0, math.pi / 2), reading(1.0, 3 * math.pi / 2)
+    assert plain.min() > 0
+    assert (blocked < 1e-3 * plain).all(), blocked / plain
+    assert np.abs(passed / plain - 1).max() < 2e-3, passed / plain
+    for theta in (0.0, 0.7):
+        assert np.abs((reading(1.0, theta) + reading(1.0, theta + math.pi)) / plain - 1).max() < 2e-3
+    half = reading(0.5, math.pi / 2)   # a half-strength polariser is the average of the plain and the polarised reading
+    assert np.abs(half / (0.5 * plain + 0.5 * blocked) - 1).max() < 2e-3
