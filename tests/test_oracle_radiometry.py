@@ -111,3 +111,27 @@ def test_brewster_reflection_is_extinguished_by_the_camera_polariser(oracle):
         assert np.abs((reading(1.0, theta) + reading(1.0, theta + math.pi)) / plain - 1).max() < 2e-3
     half = reading(0.5, math.pi / 2)   # a half-strength polariser is the average of the plain and the polarised reading
     assert np.abs(half / (0.5 * plain + 0.5 * blocked) - 1).max() < 2e-3
+
+
+def test_furnace_sums_the_geometric_series(oracle):
+    """A closed box whose walls all emit L and reflect diffusely with albedo rho shows L / (1 - rho) everywhere.  rho = 0.25 keeps the
+    series short: the reference ends a path once the product of its sampling pdfs falls below 1e-6 (pltpt_sample.rt.slang:98-99), about
+    nine diffuse bounces.  BSDF sampling only (the unbiased single-strategy estimator with the lower variance here) must reproduce 4/3;
+    light sampling only comes out 1.5 % higher at 256 k paths (near-field connections between adjacent walls) and is held to 3 %."""
+    def furnace(rho, frames, **kw):
+        b = S.SceneBuilder()
+        wall = b.add_diffuse((rho,) * 3, emission_profile=b.add_emission_profile(S.LAMP))
+        X = 1.0
+        for q in (([-X, 0, 1], [X, 0, 1], [X, 0, -1], [-X, 0, -1]), ([-X, 2, -1], [X, 2, -1], [X, 2, 1], [-X, 2, 1]), ([-X, 0, -1], [X, 0, -1], [X, 2, -1], [-X, 2, -1]),
+                  ([-X, 0, 1], [-X, 0, -1], [-X, 2, -1], [-X, 2, 1]), ([X, 0, -1], [X, 0, 1], [X, 2, 1], [X, 2, -1]), ([X, 0, 1], [-X, 0, 1], [-X, 2, 1], [X, 2, 1])):
+            b.add_mesh(S.quad(*q), wall)   # six inward-facing walls
+        cam = S.make_camera([0.0, 1.0, 0.5], [0.2, 0.7, -1.0], focal_length=50.0, aspect=1.0)
+        osc = oracle.OracleScene(b.finalize())
+        opts = L.make_options(maxBounces=16, doRussianRoulette=False, doImportanceSampleEmitters=False, **kw)
+        return np.mean([osc.render_frame(opts, S.with_jitter(cam, f, 8, 8), f, 8, 8)["color"][..., :3].reshape(-1, 3).mean(axis=0) for f in range(frames)], axis=0)
+
+    frames = 1500
+    black = furnace(0.0, frames, doNEE=False)
+    assert np.abs(furnace(0.25, frames, doNEE=False) / black / (4 / 3) - 1).max() < 0.01
+    assert np.abs(furnace(0.0, frames, doMIS=False) / black - 1).max() < 1e-6          # nothing to connect to: the emission seen directly
+    assert np.abs(furnace(0.25, frames, doMIS=False) / black / (4 / 3) - 1).max() < 0.03
