@@ -135,3 +135,47 @@ def test_furnace_sums_the_geometric_series(oracle):
     assert np.abs(furnace(0.25, frames, doNEE=False) / black / (4 / 3) - 1).max() < 0.01
     assert np.abs(furnace(0.0, frames, doMIS=False) / black - 1).max() < 1e-6          # nothing to connect to: the emission seen directly
     assert np.abs(furnace(0.25, frames, doMIS=False) / black / (4 / 3) - 1).max() < 0.03
+
+
+def test_glass_slab_transmits_the_incoherent_airy_sum(oracle):
+    """An emitter seen at normal incidence through a 0.2 m slab of smooth glass (eta 1.5, R = 4 % per face): the delta-lobe random walk
+    (reflect / transmit at every face, radiance scaled by eta^2 going in and 1 / eta^2 coming out) must add up to
+    T^2 (1 + R^2 + R^4 + ...) = (1 - R) / (1 + R) = 0.9231 of the unobstructed view.  MNEE is off so that only the sampled chains count."""
+    def view(with_slab, frames=300, **kw):
+        b = S.SceneBuilder()
+        light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=b.add_emission_profile(S.LAMP))
+        b.add_mesh(S.quad([-5, 0, 5], [5, 0, 5], [5, 0, -5], [-5, 0, -5]), light)   # normal +y
+        if with_slab:
+            b.add_mesh(S.box([0.0, 1.0, 0.0], [3.0, 0.1, 3.0]), b.add_dielectric(1.5, 0.0))
+        cam = S.make_camera([0.0, 3.0, 0.0], [0.0, 0.0, 0.0], up=(0, 0, 1), focal_length=2000.0, aspect=1.0)
+        osc = oracle.OracleScene(b.finalize())
+        opts = L.make_options(**dict(dict(maxBounces=10, doRussianRoulette=False, doImportanceSampleEmitters=False, doMNEE=False), **kw))
+        # the same frames (seeds, hence hero wavelengths) in both views: the spectral noise cancels in the ratio
+        return np.mean([osc.render_frame(opts, S.with_jitter(cam, f, 8, 8), f, 8, 8)["color"][..., :3].reshape(-1, 3).mean(axis=0) for f in range(frames)], axis=0)
+
+    ratio = view(True) / view(False)
+    assert np.abs(ratio / (0.96 / 1.04) - 1).max() < 0.015, ratio
+    # Reference behaviour with the default doMNEE = true (reproduced as it is): an emissive hit behind two or more manifold-compatible delta
+    # bounces counts as "NEE was available" (pltpt_solve.rt.slang:205-210), so it is MIS-weighted by lastNonDeltaPdf / (lastNonDeltaPdf + lightPdf)
+    # (:174); on a chain that starts at the camera no non-delta bounce has happened, lastNonDeltaPdf is still its initial 0
+    # (Path.slang:182) and no vertex exists to start the manifold walk from: the emitter behind the slab renders black.
+    assert view(True, frames=8, doMNEE=True).max() == 0
+
+
+def test_contribution_at_a_continuing_vertex_carries_that_vertex_sampling_pdf(oracle):
+    """Reference bookkeeping, pinned as it is: the bounce record stores 1 / path.pdf AFTER path.pdf was multiplied by the pdf
+    of the direction sampled at that vertex (pltpt_sample.rt.slang:126,130; pltpt.slangh:151), unless the path ends there (:115-119).
+    A diffuse emitter seen directly is therefore 2 pi brighter (the mean of 1 / pdf over the cosine lobe) when the path may continue
+    (maxBounces >= 1) than when its first vertex is terminal (maxBounces = 0)."""
+    b = S.SceneBuilder()
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=b.add_emission_profile(S.LAMP))
+    b.add_mesh(S.quad([-5, 0, 5], [5, 0, 5], [5, 0, -5], [-5, 0, -5]), light)
+    cam = S.make_camera([0.0, 3.0, 0.0], [0.0, 0.0, 0.0], up=(0, 0, 1), focal_length=2000.0, aspect=1.0)
+    osc = oracle.OracleScene(b.finalize())
+
+    def view(max_bounces):
+        opts = L.make_options(maxBounces=max_bounces, doRussianRoulette=False, doImportanceSampleEmitters=False)
+        return np.mean([osc.render_frame(opts, S.with_jitter(cam, f, 8, 8), f, 8, 8)["color"][..., :3].reshape(-1, 3).mean(axis=0) for f in range(200)], axis=0)
+
+    assert np.abs(view(0) / view(1) * 2 * np.pi - 1).max() < 0.02
+    assert np.abs(view(4) / view(1) - 1).max() < 1e-6
