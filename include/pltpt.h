@@ -429,6 +429,11 @@ PLTPT_API int pltpt_trace_closest(PltptHandle h, uint32_t rayCount, const float*
                                   uint32_t* hits, float* hitT, void* stream);
 PLTPT_API int pltpt_trace_any(PltptHandle h, uint32_t rayCount, const float* rays,
                               uint32_t* occluded, void* stream);
+/* Which traversal driver the two ray queries above run through.  The rendering kernels pick by scene size: one ray per thread to
+ * completion for trees of a few nodes, persistent lanes that refill from a queue otherwise; AUTO (default) makes the queries follow
+ * the same rule, the other two force one driver so that the hit-ID parity checks can cover both on every scene. */
+enum { PLTPT_TRACE_AUTO = 0, PLTPT_TRACE_ONE_RAY_PER_THREAD = 1, PLTPT_TRACE_PERSISTENT_LANES = 2 };
+PLTPT_API int pltpt_set_trace_mode(PltptHandle h, int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Batched PLT BSDF queries (config 1 of the benchmark; IMaterialInstance contract,

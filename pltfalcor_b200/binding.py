@@ -17,7 +17,7 @@ EXPORTS = [
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
-    "pltpt_render_frame_host_async", "pltpt_host_wait",
+    "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
 ]
 
 
@@ -50,6 +50,7 @@ def lib():
         _lib.pltpt_sample_stage_host.argtypes = [vp, u32, vp, u32, u32, vp]
         _lib.pltpt_trace_closest.argtypes = [vp, u32, vp, vp, vp, vp]
         _lib.pltpt_trace_any.argtypes = [vp, u32, vp, vp, vp]
+        _lib.pltpt_set_trace_mode.argtypes = [vp, C.c_int]
         _lib.pltpt_bsdf_eval_mueller.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]
         _lib.pltpt_bsdf_sample.argtypes = [vp, u32, u32, u32, vp, vp, u32, vp, vp]
         _lib.pltpt_get_stats.argtypes = [vp, vp]
@@ -206,6 +207,10 @@ class Pltpt:
 
     def trace_any(self, rays, occluded, stream=None):
         _check(lib().pltpt_trace_any(self.h, rays.shape[0], _dp(rays), _dp(occluded), stream))
+
+    def set_trace_mode(self, mode):
+        """0 = follow the renderer's choice, 1 = one ray per thread, 2 = persistent lanes (include/pltpt.h PLTPT_TRACE_*)."""
+        _check(lib().pltpt_set_trace_mode(self.h, mode))
 
     def update_transforms(self, world, world_it):
         """world, world_it: (n,4,4) float32 host arrays (row-major), like SceneBuffers.arrays['worldMatrices']."""

@@ -27,7 +27,7 @@ extern "C" void pltpt_default_options(PltptOptions* o) {  // PLTPT.h:74-108
 static int validateOptions(const PltptOptions& o) {
     if (o.HWSS < 1 || o.HWSS > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "HWSS must be in 1..4");
     if (o.tileSize == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "tileSize must be > 0");
-    if (o.maxBounces > 255) return fail(PLTPT_ERR_INVALID_ARGUMENT, "maxBounces must be <= 255");
+    if (o.maxBounces > 63) return fail(PLTPT_ERR_INVALID_ARGUMENT, "maxBounces must be <= 63 (the wavefront queues index recorded vertices with 6 bits)");
     if (o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_UNIFORM && o.emissiveSampler != PLTPT_EMISSIVE_SAMPLER_POWER) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Unknown emissive light sampler type");  // PLTPT.cpp:409
     if (o.sampleGenerator != 1) return fail(PLTPT_ERR_UNSUPPORTED, "only SAMPLE_GENERATOR_UNIFORM (1) is supported");
     if (o.MNEEMaxOccluders > 4) return fail(PLTPT_ERR_INVALID_ARGUMENT, "MNEEMaxOccluders must be <= 4");
@@ -84,6 +84,11 @@ extern "C" int pltpt_destroy(PltptHandle h) {
 extern "C" int pltpt_set_options(PltptHandle h, const PltptOptions* opts) {
     if (!h || !opts) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (int r = validateOptions(*opts)) return r;
+    // the scene was checked against the options in force when it was uploaded (pltpt_set_scene); PLTPT::execute re-runs setScene on an
+    // option change (PLTPT.cpp:373-383), here the same checks are repeated against the resident scene instead
+    if (h->hasScene && h->scene.etriCount > 0 && opts->emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER && !h->scene.alias)
+        return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table (the resident scene was uploaded without one)");
+    if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
     h->opt = *opts;
     return PLTPT_OK;
 }
@@ -401,6 +406,9 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     PLT_CUDA(cudaSetDevice(h->device));
     if (h->waitHostAsync()) return fail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
+    // frames still running on the caller's stream or on a lane's stream read the scene buffers that are about to be rewritten in place
+    if (int r = syncFrameStats(h)) return r;
+    PLT_CUDA(cudaDeviceSynchronize());
     h->hasScene = false;
     h->ownLightCollection = false;
     const bool dev = s->pointersAreDevice != 0;
@@ -438,6 +446,15 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
         if (id == PLTPT_NO_SPECTRAL_PROFILE || id >= profiles.size()) continue;
         h->hMaterialEmission[i] = id;
         for (int c = 0; c < 3; ++c) h->hMaterialRgb[3 * i + c] = profiles[id].rgb[c];
+    }
+    for (size_t i = 0; i < profiles.size(); ++i)
+        if (profiles[i].bins == 0 || profiles[i].bins > 128) return fail(PLTPT_ERR_INVALID_ARGUMENT, "spectral profile " + std::to_string(i) + ": bins must be in 1..128 (BasicMaterialData.slang:43-54)");
+    {
+        std::vector<PltptLightData> hl;
+        if (int r = fetchHost(hl, s->lights, s->lightCount, dev)) return r;
+        for (size_t i = 0; i < hl.size(); ++i)
+            if (hl[i].intensitySpectrumId != PLTPT_NO_SPECTRAL_PROFILE && hl[i].intensitySpectrumId >= s->profileCount)
+                return fail(PLTPT_ERR_INVALID_ARGUMENT, "light " + std::to_string(i) + ": intensitySpectrumId out of range");
     }
     std::vector<DevProfile> dprofiles(profiles.size());
     for (size_t i = 0; i < profiles.size(); ++i) repackProfile(profiles[i], dprofiles[i]);
@@ -484,6 +501,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     d.hitTypeBits = s->hitInfoTypeBits; d.hitInstBits = s->hitInfoInstanceIDBits; d.hitPrimBits = s->hitInfoPrimitiveIndexBits;
     h->emissiveTriangleCount = s->emissiveTriangleCount;
     h->lightCount = s->lightCount;
+    h->matrixCount = s->matrixCount;
     if (d.etriCount > 0 && (!d.etris || !d.eflux || !d.perMeshInstanceOffset)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "emissive triangles present but light-collection buffers missing");
     if (d.etriCount > 0 && h->opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER && !d.alias) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table");
     if (d.triCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no triangles");
@@ -618,6 +636,13 @@ extern "C" int pltpt_trace_any(PltptHandle h, uint32_t n, const float* rays, uin
     if (!rays || !occluded) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
     PLT_CUDA(cudaSetDevice(h->device));
     return traceAny(h, n, rays, occluded, (cudaStream_t)stream);
+}
+
+extern "C" int pltpt_set_trace_mode(PltptHandle h, int mode) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (mode < PLTPT_TRACE_AUTO || mode > PLTPT_TRACE_PERSISTENT_LANES) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown trace mode");
+    h->traceMode = mode;
+    return PLTPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ rendering

@@ -282,6 +282,26 @@ __global__ void __launch_bounds__(128) k_trace(const BvhNode* __restrict__ nodes
     }
 }
 
+// The same query through the traversal driver the rendering kernels of non-trivial scenes use (travPersistent: persistent lanes
+// that refill from a cursor, processNode per step), so that the bit-exact hit-ID checks cover that code path too.
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_lanes(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, uint32_t n, const float* __restrict__ rays, uint32_t* __restrict__ out,
+                                                     float* __restrict__ outT, uint32_t* __restrict__ cursor, uint32_t* __restrict__ overflow) {
+    travPersistent<ANY>(nodes, tris, n, cursor, overflow, nullptr,
+        [&](uint32_t i, float3& o, float3& d, float& tmin, float& tmax) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i)), b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
+            o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z); tmin = a.w; tmax = b.w;
+            return true;
+        },
+        [&](uint32_t i, bool hit, const Hit& h) {
+            if (ANY) out[i] = hit ? 1u : 0u;
+            else {
+                reinterpret_cast<uint4*>(out)[i] = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+                if (outT) outT[i] = hit ? h.t : 0.f;
+            }
+        });
+}
+
 inline uint32_t blocksFor(uint64_t n, uint32_t threads) { return uint32_t((n + threads - 1) / threads); }
 
 }  // namespace
@@ -390,7 +410,15 @@ static int traceLaunch(PltptContext* c, bool any, uint32_t n, const float* rays,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const uint32_t grid = std::min<uint32_t>(blocksFor(n, 128), uint32_t(sms) * 16);
     uint32_t* overflow = c->bvhScratch[7].as<uint32_t>() + 9;
-    if (any) k_trace<true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);
+    // PLTPT_TRACE_AUTO follows the renderer (launchTrace / launchShadowTrace): persistent lanes unless the tree has only a few nodes
+    const bool lanes = c->traceMode == PLTPT_TRACE_PERSISTENT_LANES || (c->traceMode == PLTPT_TRACE_AUTO && c->stats.bvhNodes >= 256);
+    if (lanes) {
+        uint32_t* cursor = c->bvhScratch[7].as<uint32_t>() + 10;
+        PLT_CUDA(cudaMemsetAsync(cursor, 0, 4, s));
+        const uint32_t lgrid = std::min<uint32_t>(blocksFor(n, 128), uint32_t(sms) * 8);
+        if (any) k_trace_lanes<true><<<lgrid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, cursor, overflow);
+        else k_trace_lanes<false><<<lgrid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, cursor, overflow);
+    } else if (any) k_trace<true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);
     else k_trace<false><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, overflow);
     c->stats.kernelLaunches++;
     (any ? c->stats.raysAny : c->stats.raysClosest) += n;

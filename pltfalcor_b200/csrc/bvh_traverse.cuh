@@ -66,6 +66,9 @@ struct Hit {
 };
 
 constexpr int kTraversalStack = 160;
+#ifndef PLT_TRAVERSE_DEDUP
+#define PLT_TRAVERSE_DEDUP 0  // 1: traverseBvh() drives processNode() instead of its own copy of the node body (measured before the copy is deleted)
+#endif
 
 // Traversal of the compressed wide BVH.  processNode() handles ONE popped node (children slab tests, leaf triangles, ordered push
 // of the inner children).  traverseBvh() runs a ray to completion in the calling thread; the trace kernels of non-trivial scenes
@@ -184,6 +187,16 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
     int sp = 0;
     stack[sp++] = 0;
     if (!ANY) stackT[0] = tmin;
+#if PLT_TRAVERSE_DEDUP
+    RayConst R;
+    rayConstInit(R, o, d, tmin, tmax);
+    while (sp > 0) {
+        const uint32_t ni = stack[--sp];
+        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;
+        if (processNode<ANY>(nodes, tris, R, ni, best, stack, stackT, sp, overflow, tc)) return true;
+    }
+    return best.valid();
+#endif
     while (sp > 0) {
         const uint32_t ni = stack[--sp];
         if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit below: exact-t ties are still visited)

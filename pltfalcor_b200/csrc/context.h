@@ -89,7 +89,9 @@ struct PltptContext {
     std::vector<uint32_t> hMaterialEmission;  // emissionSpectralId per material (pltpt_build_light_collection)
     std::vector<float> hMaterialRgb;           // rgb of that emission profile, 3 per material
     bool ownLightCollection = false;           // the light collection was built by pltpt_build_light_collection
-    uint32_t emissiveTriangleCount = 0, lightCount = 0;
+    uint32_t emissiveTriangleCount = 0, lightCount = 0, matrixCount = 0;
+    int traceMode = 0;                         // pltpt_set_trace_mode: which traversal driver the ray-query entry points use
+    uint32_t mneeGrid = 0;                     // cooperative grid of k_mnee_walk on this handle's device (resident CTAs), 0 = not queried yet
     // Frame lanes: frames are independent (every random number derives from (pixel, frameCount), pltpt_sample.rt.slang:154), so
     // pltpt_render_accumulate keeps two frames in flight on two streams, each with its own work buffers, counters and timers: the
     // under-filled late bounces of one frame overlap the wide early bounces of the other.  Lane 0 runs on the caller's stream.

@@ -329,6 +329,9 @@ extern "C" int pltpt_build_light_collection(PltptHandle h) {
     if (!h) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
     if (!h->hasScene) return ifail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
     PLT_CUDA(cudaSetDevice(h->device));
+    if (h->waitHostAsync()) return ifail(PLTPT_ERR_CUDA, "a frame queued by pltpt_render_frame_host_async failed");
+    if (int r = syncFrameStats(h)) return r;  // frames in flight read the light tables that are rebuilt here
+    PLT_CUDA(cudaDeviceSynchronize());
     const uint32_t instCount = uint32_t(h->hInstances.size());
     std::vector<uint32_t> instList, instFirst, offsets(instCount, 0xffffffffu);
     uint32_t total = 0;
@@ -387,7 +390,7 @@ extern "C" int pltpt_build_light_collection(PltptHandle h) {
 extern "C" int pltpt_update_transforms(PltptHandle h, const float* worldMatrices, const float* inverseTransposeWorldMatrices, uint32_t matrixCount, uint32_t pointersAreDevice) {
     if (!h || !worldMatrices || !inverseTransposeWorldMatrices) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (!h->hasScene) return ifail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
-    if (size_t(matrixCount) * 64 != h->world.bytes && size_t(matrixCount) * 64 > h->world.bytes) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "matrixCount exceeds the scene's matrix table");
+    if (matrixCount != h->matrixCount) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "matrixCount differs from the scene's matrix table (" + std::to_string(h->matrixCount) + ")");
     for (const auto& gi : h->hInstances)
         if (gi.globalMatrixID >= matrixCount) return ifail(PLTPT_ERR_INVALID_ARGUMENT, "an instance refers to a matrix beyond matrixCount");
     PLT_CUDA(cudaSetDevice(h->device));

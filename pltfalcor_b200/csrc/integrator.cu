@@ -9,7 +9,8 @@ namespace plt {
 namespace {
 // worst-case work-buffer bytes per pixel: bounce planes + vertex cache + jobs (2 per recorded vertex) + queues + contributions
 size_t workBytesPerPixel(uint32_t records) {
-    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4 + 8) + size_t(2 * records) * 16 + 6 * 16 + 4 + 2 * (sizeof(MneeItem) + sizeof(MneeWalk) + 12) + sizeof(ConnItem) + 32 + 16 + 4;
+    // (parked manifold walks: worst case one per recorded vertex -- a connection parks at most once per (pixel, vertex index))
+    return size_t(records) * (16 + 16 + 8 + 64 + 1 + 4) + size_t(2 * records) * (kJobPlanes * 16 + 4 + 1 + 4 + 8) + size_t(2 * records) * 16 + 6 * 16 + 4 + size_t(records) * (sizeof(MneeItem) + sizeof(MneeWalk) + 12) + sizeof(ConnItem) + 32 + 16 + 4;
 }
 constexpr size_t kWorkBudgetBytes = size_t(24) << 30;  // tiles are sized so that the work buffers stay below this
 }  // namespace
@@ -51,7 +52,7 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     for (int k = 0; k < 7; ++k) PLT_CUDA(ln.work[16 + k].ensure(size_t(tilePixels) * 16));  // path state planes, hit, solve rng x2
     PLT_CUDA(ln.work[4].ensure(size_t(tilePixels) * 4));                                    // trace queue
     PLT_CUDA(ln.work[23].ensure(records * 4));                                               // per-bounce type-sorted hit lists
-    PLT_CUDA(ln.work[26].ensure(size_t(2) * tilePixels * sizeof(MneeItem)));                 // parked manifold walks
+    PLT_CUDA(ln.work[26].ensure(records * sizeof(MneeItem)));                                // parked manifold walks (worst case: every recorded vertex parks one)
     PLT_CUDA(ln.work[27].ensure(size_t(tilePixels) * sizeof(ConnItem)));
     PLT_CUDA(ln.work[28].ensure(size_t(tilePixels) * 32));
     PLT_CUDA(ln.work[29].ensure(size_t(tilePixels) * 16));
@@ -86,9 +87,11 @@ static int fillParams(PltptContext* c, PltptContext::Lane& ln, FrameParams& P, u
     P.levelCount = P.queueCount + QC_LevelCount;
     P.mneeItems = ln.work[26].as<MneeItem>();
     P.mneeCount = P.queueCount + QC_MneeCount;
-    P.mneeCapacity = 2 * tilePixels;
-    PLT_CUDA(ln.work[8].ensure(size_t(2) * tilePixels * sizeof(MneeWalk)));
-    PLT_CUDA(ln.work[31].ensure(size_t(3) * 2 * tilePixels * 4));
+    P.mneeCapacity = uint32_t(records);
+    PLT_CUDA(ln.work[8].ensure(records * sizeof(MneeWalk)));
+    PLT_CUDA(ln.work[31].ensure(size_t(3) * records * 4));
+    if (!c->mneeGrid) c->mneeGrid = mneeCooperativeGrid(c->device);
+    P.mneeGrid = c->mneeGrid;
     P.mneeWalks = ln.work[8].as<MneeWalk>();
     P.mneeLists = ln.work[31].as<uint32_t>();
     PLT_CUDA(ln.work[24].ensure(size_t(tilePixels) * 4));

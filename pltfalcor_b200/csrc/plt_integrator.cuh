@@ -68,6 +68,7 @@ struct FrameParams {
     float* shadowT;          // [pixelCount]
     uint32_t* mneeCount;
     uint32_t mneeCapacity;
+    uint32_t mneeGrid;       // cooperative grid of k_mnee_walk on this device (every CTA resident)
     float4* contrib;         // [(2 * bounce + kind)][pixel] measured RGB of each connection (w = 1: measure() ran), summed in fixed order by the resolve kernel
     float4* debug;           // same shape: the debug-view event of that connection slot (value.rgb, 1); allocated and zeroed only when debugView != 0
     uint32_t debugView;      // DebugViewType (0 = off), pltpt_debug.slangh
@@ -144,8 +145,9 @@ PLT_D void writeVertexCache(const FrameParams& P, uint32_t pixel, int p, const V
     r[3] = v.tangentW;
     P.vMatType[o] = uint8_t(materialType);
 }
-PLT_D VertexData readVertexCache(const FrameParams& P, uint32_t pixel, int p, uint32_t& materialID) {
-    const float4* r = P.vc + 4 * (size_t(p) * P.pixelCount + pixel);
+PLT_D VertexData readVertexCache(const float4* r, uint32_t& materialID);
+PLT_D VertexData readVertexCache(const FrameParams& P, uint32_t pixel, int p, uint32_t& materialID) { return readVertexCache(P.vc + 4 * (size_t(p) * P.pixelCount + pixel), materialID); }
+PLT_D VertexData readVertexCache(const float4* r, uint32_t& materialID) {
     const float4 a = r[0], b = r[1], c = r[2], d = r[3];
     VertexData v;
     v.posW = mk3(a.x, a.y, a.z); materialID = __float_as_uint(a.w);
@@ -623,8 +625,10 @@ PLT_D void storeJob(const FrameParams& P, uint32_t id, const Beam& b, const JobH
     J[8 * st] = mk4(b.r.y, b.r.z, b.t.x, b.t.y);
     J[9 * st] = mk4(b.t.z, h.pathContribution, __uint_as_float(h.pixel), __uint_as_float(packed));
 }
-PLT_D void loadJob(const FrameParams& P, uint32_t id, Beam& b, JobHeader& h) {
-    const float4* J = P.job + size_t(id) * kJobPlanes;
+PLT_D void loadJob(const float4* J, Beam& b, JobHeader& h);
+PLT_D void loadJob(const FrameParams& P, uint32_t id, Beam& b, JobHeader& h) { loadJob(P.job + size_t(id) * kJobPlanes, b, h); }
+// `J`: the job's ten float4 (in global memory, or staged in shared memory by k_unwind_step)
+PLT_D void loadJob(const float4* J, Beam& b, JobHeader& h) {
     constexpr size_t st = 1;
     b.L = J[0 * st]; b.L1 = J[1 * st]; b.L2 = J[2 * st]; b.L3 = J[3 * st]; b.wl = J[4 * st]; b.spdf = J[5 * st];
     const float4 c = J[6 * st], d = J[7 * st], e = J[8 * st], f = J[9 * st];
@@ -1293,15 +1297,12 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
 
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head).
 // Returns true while the job has further vertices to go through.
-PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
-    // the queue entry names the vertex: the job record, the vertex record and the bounce direction are independent loads
-    const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
-    uint32_t materialID;
-    const VertexData v = readVertexCache(P, pixel, int(q), materialID);
-    const float4 d = P.bDir[size_t(q) * P.pixelCount + pixel];
-    Beam beam;
-    JobHeader h;
-    loadJob(P, id, beam, h);
+// One staged replay item: the job record, the vertex record and the bounce direction of the vertex it evaluates next (240 B).
+struct alignas(16) UnwindItem { float4 job[kJobPlanes]; float4 vtx[4]; float4 dir; };
+// One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head) on its loaded
+// inputs: `v`, `materialID`, `d` = vertex record and bounce direction of the vertex the job evaluates next, `beam`, `h` = the job.
+// Returns true while the job has further vertices to go through.
+PLT_D bool unwindStepLoaded(const FrameParams& P, uint32_t id, const VertexData& v, uint32_t materialID, float4 d, Beam& beam, JobHeader& h, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
     const DevMaterial m = loadMaterial(P.sc.materials, materialID);
     const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
@@ -1315,6 +1316,17 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
     nextAux = jobAux(h.pixel, h.q);
     storeJob(P, id, beam, h);
     return true;
+}
+PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
+    // the queue entry names the vertex: the job record, the vertex record and the bounce direction are independent loads
+    const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
+    uint32_t materialID;
+    const VertexData v = readVertexCache(P, pixel, int(q), materialID);
+    const float4 d = P.bDir[size_t(q) * P.pixelCount + pixel];
+    Beam beam;
+    JobHeader h;
+    loadJob(P, id, beam, h);
+    return unwindStepLoaded(P, id, v, materialID, d, beam, h, evals, nextType, nextAux);
 }
 
 // Sums a pixel's connections in the order the reference adds them (bounce ascending, NEE before emissive).
@@ -1395,6 +1407,7 @@ void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s);  // fast pass + dense pass over the deferred entries
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s);
+uint32_t mneeCooperativeGrid(int device);  // resident CTAs of k_mnee_walk on `device` (queried once per handle)
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchResolve(const FrameParams& P, cudaStream_t s);

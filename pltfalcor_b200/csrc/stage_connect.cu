@@ -12,6 +12,7 @@
 //                      delta occluders, isolated so that they cannot stall the coherent NEE work (north-star (d)).
 #include "plt_integrator.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 namespace cg = cooperative_groups;
 
 #ifndef PLT_MINB_CONNECT_A
@@ -25,6 +26,16 @@ namespace cg = cooperative_groups;
 #endif
 #ifndef PLT_MINB_MNEE
 #define PLT_MINB_MNEE 4  // 128 registers: 21.2 vs 23.7 ms on the 10 M-triangle city, 5.98 vs 5.85 ms on the grating scene (profiles/r1_variants18_mnee_occupancy.log)
+#endif
+#ifndef PLT_MNEE_PHASE_TIMERS
+#define PLT_MNEE_PHASE_TIMERS 0  // development builds (tools/variants.py): per-round live-walk counts and phase durations of k_mnee_walk
+#endif
+#if PLT_MNEE_PHASE_TIMERS
+__device__ unsigned long long g_mneeProfile[4 * 128];  // per round: live walks, advance ns, trace ns, rays traced
+extern "C" __attribute__((visibility("default"))) int pltpt_debug_mnee_profile(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_mneeProfile, sizeof(g_mneeProfile)) == cudaSuccess ? 0 : 1;
+}
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 namespace plt {
 namespace {
@@ -152,6 +163,10 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         const uint32_t nCur = round == 0 ? n : counts[round % 3u];
         uint32_t* nextCount = counts + (round + 1u) % 3u;
         if (tid == 0) { counts[(round + 2u) % 3u] = 0; P.queueCount[QC_MneeTraceCursor + (round + 2u) % 3u] = 0; }
+#if PLT_MNEE_PHASE_TIMERS
+        unsigned long long t0 = 0;
+        if (tid == 0) t0 = globalTimerNs();
+#endif
         for (uint32_t base = blockIdx.x * kStageThreads; base < nCur; base += stride) {  // ---- advance
             const uint32_t k = base + threadIdx.x;
             int r = WALK_FAILED;
@@ -181,6 +196,10 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
         }
         grid.sync();
         const uint32_t nNext = *nextCount;
+#if PLT_MNEE_PHASE_TIMERS
+        unsigned long long t1 = 0;
+        if (tid == 0 && round < 128) { t1 = globalTimerNs(); g_mneeProfile[4 * round] += nCur; g_mneeProfile[4 * round + 1] += t1 - t0; g_mneeProfile[4 * round + 3] += nNext; }
+#endif
         if (nNext == 0) break;  // grid-uniform: every thread reads the same count after the barrier
         // ---- trace the posted trial rays (persistent lanes; the fetch cursors rotate through queueCount[QC_MneeTraceCursor ..+3) like the counts)
         travPersistent<false>(P.sc.bvhNodes, P.sc.bvhTris, nNext, P.queueCount + QC_MneeTraceCursor + round % 3u, reinterpret_cast<uint32_t*>(P.counters + 2), &tc,
@@ -196,6 +215,9 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
                 w.t = h.t;
             });
         grid.sync();
+#if PLT_MNEE_PHASE_TIMERS
+        if (tid == 0 && round < 128) g_mneeProfile[4 * round + 2] += globalTimerNs() - t1;
+#endif
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
@@ -216,19 +238,21 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(co
     warpAdd(P.counters + 6, tc.tris);
 }
 }  // namespace
+// cooperative launch: every CTA must be resident, so the grid is what the device can hold of this kernel (per device: a process may
+// hold handles on several GPUs)
+uint32_t mneeCooperativeGrid(int device) {
+    int perSm = 0, sms = 0, cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mnee_walk, kStageThreads, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cur != device) cudaSetDevice(cur);
+    return uint32_t(std::max(perSm, 1) * std::max(sms, 1));
+}
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    // cooperative launch: every CTA must be resident, so the grid is what the device can hold of this kernel
-    static int perSm = 0, sms = 0;
-    if (!perSm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mnee_walk, kStageThreads, 0);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (perSm < 1) perSm = 1;
-    }
     FrameParams Pc = P;
     void* args[] = {&Pc};
-    cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk), dim3(uint32_t(perSm * sms)), dim3(kStageThreads), args, 0, s);
+    cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk), dim3(P.mneeGrid), dim3(kStageThreads), args, 0, s);
     k_mnee_finish<<<grid, kStageThreads, 0, s>>>(P);
 }
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }

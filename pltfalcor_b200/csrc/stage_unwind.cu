@@ -63,6 +63,64 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
     }
 }
 
+#ifndef PLT_UNWIND_STAGE
+#define PLT_UNWIND_STAGE 1
+#endif
+#if PLT_UNWIND_STAGE
+// Asynchronous global -> shared copies (LDGSTS): the gather of a thread's NEXT item runs under the BSDF arithmetic of its current one
+// and costs no registers while in flight (the kernel sits at the 128-register limit that gives 16 warps per SM).
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stageUnwindItem(const FrameParams& P, UnwindItem* slot, uint32_t id, uint32_t aux) {
+    const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
+    const size_t o = size_t(q) * P.pixelCount + pixel;
+    const float4* J = P.job + size_t(id) * kJobPlanes;
+    const float4* V = P.vc + 4 * o;
+#pragma unroll
+    for (int k = 0; k < kJobPlanes; ++k) cpAsync16(&slot->job[k], J + k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cpAsync16(&slot->vtx[k], V + k);
+    cpAsync16(&slot->dir, P.bDir + o);
+    cpAsyncCommit();
+}
+// Each thread owns one 240 B slot (stride 60 words: a quarter-warp's 16 B accesses fall into distinct banks).  The slot is read
+// into registers, then refilled for the thread's next item (same thread, program order: no barrier), then the step is computed.
+__global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
+    __shared__ UnwindItem slots[kStageThreads];
+    const uint32_t n = P.queueCount[QC_SortedCount];
+    uint32_t evals = 0;
+    const uint32_t stride = gridDim.x * kStageThreads;
+    uint32_t i = blockIdx.x * kStageThreads + threadIdx.x;
+    UnwindItem* slot = &slots[threadIdx.x];
+    uint32_t id = 0, aux = 0, nid = 0, naux = 0;
+    if (i < n) { id = P.sorted[i]; aux = P.sortedAux[i]; stageUnwindItem(P, slot, id, aux); }
+    if (i + stride < n) { nid = P.sorted[i + stride]; naux = P.sortedAux[i + stride]; }
+    for (; i < n; i += stride) {
+        cpAsyncWaitAll();
+        uint32_t materialID;                            // staged record -> registers (15 LDS.128)
+        const VertexData v = readVertexCache(slot->vtx, materialID);
+        const float4 d = slot->dir;
+        Beam beam;
+        JobHeader h;
+        loadJob(slot->job, beam, h);
+        const uint32_t j = i + stride;
+        uint32_t nnid = 0, nnaux = 0;
+        if (j < n) {
+            stageUnwindItem(P, slot, nid, naux);        // refill for the next iteration: in flight during this item's arithmetic
+            const uint32_t j2 = j + stride;
+            if (j2 < n) { nnid = P.sorted[j2]; nnaux = P.sortedAux[j2]; }
+        }
+        uint32_t nextType = 0, nextAux = 0;
+        if (unwindStepLoaded(P, id, v, materialID, d, beam, h, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
+        id = nid; aux = naux; nid = nnid; naux = nnaux;
+    }
+    warpAdd(P.counters + 0, evals);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);
+}
+#else
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[QC_SortedCount];
     uint32_t evals = 0;
@@ -92,6 +150,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_
     warpAdd(P.counters + 0, evals);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);
 }
+#endif
 
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FrameParams P) {
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;

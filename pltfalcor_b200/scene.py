@@ -589,6 +589,41 @@ class SceneBuilder:
         l["transMatIT"] = np.linalg.inv(M).T.astype(f32).reshape(-1)
         self.lights.append(l)
 
+    def _area_light(self, ltype, profile, center, normal, scale, emission_solid_angle=None):
+        """AnalyticAreaLight::update (Light.cpp:341-346): transMat = transform * scale, transMatIT = inverse(transpose(transMat));
+        object-space +z is the emitting side of the rect / disc."""
+        n = np.asarray(normal, np.float64) / np.linalg.norm(normal)
+        t = np.cross([0, 1, 0] if abs(n[1]) < 0.9 else [1, 0, 0], n)
+        t /= np.linalg.norm(t)
+        b = np.cross(n, t)
+        M = np.eye(4)
+        M[:3, 0], M[:3, 1], M[:3, 2], M[:3, 3] = t * scale[0], b * scale[1], n * scale[2], center
+        M = M.astype(f32)
+        l = np.zeros((), L.light_data_dtype)
+        l["posW"], l["type"], l["dirW"] = center, ltype, n
+        l["openingAngle"], l["cosOpeningAngle"] = math.pi, -1.0
+        # AnalyticAreaLight::setEmissionSolidAngle (Light.cpp:348-351); LightData default cosSubtendedAngle = 0.9999893
+        l["cosSubtendedAngle"] = 0.9999893 if emission_solid_angle is None else math.sqrt(1.0 - emission_solid_angle / 4.0 / math.pi)
+        l["intensitySpectrumId"] = profile
+        rx, ry, rz = (float(np.linalg.norm(M[:3, k])) for k in range(3))
+        if ltype == 3:
+            area = 4.0 * rx * ry                                                   # RectLight::update, Light.cpp:366
+        elif ltype == 4:
+            area = math.pi * rx * ry                                               # DiscLight::update, Light.cpp:383
+        else:  # SphereLight::update, Light.cpp:401 — the reference's operator precedence (only the last term is divided by 3) is kept
+            area = 4.0 * math.pi * ((rx * ry) ** 1.6 + (ry * rz) ** 1.6 + (rx * rz) ** 1.6 / 3.0) ** (1.0 / 1.6)
+        l["surfaceArea"] = f32(area)
+        l["transMat"] = M.reshape(-1)
+        l["transMatIT"] = np.linalg.inv(M.astype(np.float64).T).astype(f32).reshape(-1)
+        self.lights.append(l)
+
+    def add_disc_light(self, profile, center, normal, radius_x, radius_y=None, emission_solid_angle=None):
+        self._area_light(4, profile, center, normal, (radius_x, radius_x if radius_y is None else radius_y, 1.0), emission_solid_angle)
+
+    def add_sphere_light(self, profile, center, radius, emission_solid_angle=None):
+        r = (radius,) * 3 if np.isscalar(radius) else tuple(radius)
+        self._area_light(5, profile, center, (0, 0, 1), r, emission_solid_angle)
+
     def add_distant_light(self, profile, direction, half_angle):
         d = np.asarray(direction, np.float64) / np.linalg.norm(direction)
         z = -d  # cone axis points towards the light
@@ -824,6 +859,37 @@ def env_scene(aspect=16.0 / 9.0, with_emitter=True):
         b.add_mesh(quad([-0.4, 2.8, -0.4], [0.4, 2.8, -0.4], [0.4, 2.8, 0.4], [-0.4, 2.8, 0.4]), light)
     b.set_env_map(procedural_sky(), intensity=1.5, tint=(1.0, 0.95, 0.9), rot_y=0.7)
     cam = make_camera([0.0, 1.5, 4.5], [0.0, 0.6, 0.0], focal_length=30.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def analytic_lights_scene(aspect=16.0 / 9.0, kinds=("rect", "disc", "sphere", "distant")):
+    """Scene lit by the analytic area lights of LightHelpers.slang:100-168 (rect, disc, sphere; plus one distant light and a small
+    emissive quad so that the light-type selection mixes emissive and analytic sampling): diffuse room, a rough conductor and a
+    smooth dielectric sphere (MNEE towards analytic lights)."""
+    b = SceneBuilder()
+    au = b.add_ior_profiles("Au")
+    lamp = b.add_emission_profile(LAMP, 3.0)
+    led = b.add_emission_profile("2499_LED_Encaster_Calculite_domestic-use_softwhite-color_Philips_brand_22W_1500lm_7inch_3000K", 1.0)
+    white = b.add_diffuse((0.7, 0.7, 0.7))
+    blue = b.add_diffuse((0.2, 0.3, 0.65))
+    gold = b.add_conductor(au, roughness=0.25)
+    glass = b.add_dielectric(ior=1.5, roughness=0.0)
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    b.add_mesh(grid_plane(0.0, -3.0, 3.0, -3.0, 3.0, 2, 2), white)
+    b.add_mesh(quad([-3, 0, -2], [3, 0, -2], [3, 4, -2], [-3, 4, -2]), blue)
+    b.add_mesh(uv_sphere([-0.9, 0.5, 0.2], 0.5, 24, 48), gold)
+    b.add_mesh(uv_sphere([0.9, 0.5, 0.4], 0.5, 24, 48), glass)
+    b.add_mesh(box([0.0, 0.3, -1.0], [0.5, 0.3, 0.3], rot_y=0.4), white)
+    b.add_mesh(quad([-0.2, 3.0, -0.2], [0.2, 3.0, -0.2], [0.2, 3.0, 0.2], [-0.2, 3.0, 0.2]), light)
+    if "rect" in kinds:
+        b.add_rect_light(lamp, center=(-1.8, 2.2, 0.5), normal=(0.6, -1.0, -0.1), half_x=0.4, half_y=0.25)
+    if "disc" in kinds:
+        b.add_disc_light(led, center=(1.6, 2.4, 0.8), normal=(-0.5, -1.0, -0.2), radius_x=0.35, radius_y=0.2)
+    if "sphere" in kinds:
+        b.add_sphere_light(lamp, center=(0.0, 1.8, 1.2), radius=(0.15, 0.2, 0.1))
+    if "distant" in kinds:
+        b.add_distant_light(led, direction=(0.3, -1.0, -0.4), half_angle=math.radians(1.0))
+    cam = make_camera([0.0, 1.5, 4.5], [0.0, 0.7, 0.0], focal_length=30.0, aspect=aspect)
     return b.finalize(), cam
 
 

@@ -12,6 +12,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """Writes the parity figures the GPU tests measured (tests/parity.py record()) next to the other GPU-run artefacts."""
+    import json
+    from tests import parity
+    out = os.path.join(ROOT, "gpurun_out")
+    for name, data in (("parity_metrics.json", parity.METRICS), ("image_parity.json", parity.IMAGE_PARITY)):
+        if not data:
+            continue
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, name)
+        merged = {}
+        if os.path.exists(path):
+            try:
+                with open(path) as f:
+                    merged = json.load(f)
+            except ValueError:
+                merged = {}
+        merged.update(data)
+        with open(path, "w") as f:
+            json.dump(merged, f, indent=1, sort_keys=True)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import binding

@@ -59,6 +59,16 @@ def random_rays(rng, buffers, n, tmax=None):
 
 ABS_FLOOR = 1e-8
 
+# Measured parity figures of a test session: tests call record(); tests/conftest.py writes them to gpurun_out/parity_metrics.json at the
+# end of the session (and the converged-image figures to gpurun_out/image_parity.json), from where they are committed under profiles/.
+METRICS = {}
+IMAGE_PARITY = {}
+
+
+def record(key, value):
+    METRICS[key] = value
+
+
 
 def mueller_rel_err(a, b, columns=None):
     """Per Mueller matrix: max |a-b| / (max|b| + ABS_FLOOR / 1e-4), i.e. the test `err <= 1e-4` reads

@@ -15,10 +15,15 @@ def _scene(name):
             # BASELINE config 5 generator at a size the brute-force oracle finishes in seconds (instanced spheres, all ten PLT materials)
             "city": lambda: scene.city_scene(40_000),
             # environment-lit scene: EnvMapSampler NEE + onMiss, mixed with an emissive quad
-            "env": scene.env_scene}[name]()
+            "env": scene.env_scene,
+            # rect, disc and sphere analytic area lights (LightHelpers.slang:100-168) + a distant light + an emissive quad
+            "analytic": scene.analytic_lights_scene}[name]()
 
 
-@pytest.fixture(scope="module", params=["cornell", "grating_sphere", "layered", "city", "env"])
+SCENES = ["cornell", "grating_sphere", "layered", "city", "env", "analytic"]
+
+
+@pytest.fixture(scope="module", params=SCENES)
 def loaded(request, torch_cuda, oracle):
     from pltfalcor_b200 import binding
     buffers, cam = _scene(request.param)
@@ -31,6 +36,12 @@ def loaded(request, torch_cuda, oracle):
 
 W, H = 96, 54
 
+# Gates sit just above what is measured on B200 (profiles/parity_metrics.json is the record of the last run): a regression that
+# breaks one path in a hundred must fail.  Paths legitimately fork where a random number falls within rounding of a branch
+# threshold (delta/scatter pick, Russian roulette, Fresnel R/T) -- more often on scenes with many specular chains.
+MIN_IDENTICAL_PATHS = {"cornell": 0.995, "grating_sphere": 0.99, "layered": 0.99, "city": 0.99, "env": 0.99, "analytic": 0.995}
+MIN_PIXELS_WITHIN_1E3 = {"cornell": 0.995, "grating_sphere": 0.97, "layered": 0.985, "city": 0.985, "env": 0.985, "analytic": 0.99}
+
 
 def test_sample_stage_bounce_records(loaded):
     """Hit IDs, lobes and flags identical for (nearly) every path; floats of identical paths within fp32 noise.
@@ -42,10 +53,12 @@ def test_sample_stage_bounce_records(loaded):
         gpu = p.sample_stage_host(c, frame, W, H)
         cpu = osc.render_frame(p.options, c, frame, W, H, solve=False, want_bounces=True)["bounces"]
         m, same = parity.compare_bounces(gpu, cpu)
-        assert m["identical_paths"] >= 0.97, (name, m)
+        parity.record(f"bounces/{name}/frame{frame}", m)
+        assert m["identical_paths"] >= MIN_IDENTICAL_PATHS[name], (name, m)
         assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3, (name, m)
         assert m["max_contribution_rel"] <= 5e-3, (name, m)
-    assert p.stats()["traversalStackOverflows"] == 0
+    s = p.stats()
+    assert s["traversalStackOverflows"] == 0 and s["droppedConnections"] == 0
 
 
 def test_single_frame_rgb_and_guides(loaded):
@@ -58,17 +71,21 @@ def test_single_frame_rgb_and_guides(loaded):
     cpu = osc.render_frame(p.options, c, frame, W, H, want_bounces=True)
     _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
     m = parity.compare_color(gpu["color"], cpu["color"], same)
+    m["identical_paths"] = float(same.mean())
+    parity.record(f"single_frame/{name}", m)
     assert m["nonfinite_gpu"] == 0
     assert (gpu["color"][..., 3] == 1).all() and (gpu["color"][..., :3] >= 0).all()
     # per-path radiance is a product of up to ~40 BSDF evaluations each good to 1e-4; MNEE paths amplify rounding further
-    assert m["frac_pixels_within_1e-2"] >= 0.97, (name, m)
+    assert m["frac_pixels_within_1e-3"] >= MIN_PIXELS_WITHIN_1E3[name], (name, m)
+    assert m["frac_pixels_within_1e-2"] >= 0.995, (name, m)
+    # the frame means include the few forked paths (different, equally valid samples): bounded by their share, not by rounding
     assert m["mean_rel_diff"] <= 0.02, (name, m)
     # guide buffers: albedo / view-space normal at the first non-delta vertex
     for k in ("albedo", "normal"):
         d = np.abs(gpu[k] - cpu[k]).max(axis=-1)
         assert (d[same] <= 2e-3).mean() >= 0.995, (name, k)
     s = p.stats()
-    assert s["pathVertices"] > 0 and s["bsdfEvals"] > 0
+    assert s["pathVertices"] > 0 and s["bsdfEvals"] > 0 and s["droppedConnections"] == 0
     assert abs(s["bsdfEvals"] - cpu["evals"]) <= 0.03 * cpu["evals"], (s["bsdfEvals"], cpu["evals"])
 
 
@@ -92,8 +109,11 @@ def test_option_variants_match_oracle(torch_cuda, oracle, opts):
     cpu = osc.render_frame(p.options, c, frame, w, h, want_bounces=True)
     _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
     m = parity.compare_color(gpu["color"], cpu["color"], same)
-    assert same.mean() >= 0.97, (opts, same.mean())
-    assert m["frac_pixels_within_1e-2"] >= 0.97 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    m["identical_paths"] = float(same.mean())
+    parity.record("options/cornell/" + ",".join(f"{k}={v}" for k, v in opts.items()), m)
+    assert same.mean() >= 0.99, (opts, same.mean())
+    assert m["frac_pixels_within_1e-3"] >= 0.99 and m["frac_pixels_within_1e-2"] >= 0.995 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    assert p.stats()["droppedConnections"] == 0
     p.close()
 
 
@@ -114,9 +134,11 @@ def test_env_lit_option_variants_match_oracle(torch_cuda, oracle, opts):
     cpu = osc.render_frame(p.options, c, frame, w, h, want_bounces=True)
     _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
     m = parity.compare_color(gpu["color"], cpu["color"], same)
-    assert same.mean() >= 0.97, (opts, same.mean())
+    m["identical_paths"] = float(same.mean())
+    parity.record("options/env/" + ",".join(f"{k}={v}" for k, v in opts.items()), m)
+    assert same.mean() >= 0.985, (opts, same.mean())
     assert m["nonfinite_gpu"] == 0
-    assert m["frac_pixels_within_1e-2"] >= 0.97 and m["mean_rel_diff"] <= 0.03, (opts, m)
+    assert m["frac_pixels_within_1e-3"] >= 0.98 and m["frac_pixels_within_1e-2"] >= 0.99 and m["mean_rel_diff"] <= 0.03, (opts, m)
     if opts.get("useEnvLights", True):  # sky pixels see the map directly: they must not be black
         assert (gpu["color"][:4, :, :3].sum(-1) > 0).mean() > 0.9
     p.close()
@@ -137,37 +159,79 @@ def test_polarizing_camera(torch_cuda, oracle):
     p.close()
 
 
-def test_converged_image_within_3_sigma(loaded, torch_cuda):
-    """GPU render (frames 0..N-1) vs an INDEPENDENT oracle render (frames 1000..1000+M-1): per pixel, the means must agree
-    within 3 sigma of the combined standard error; relMSE (ImageCompare.cpp:198-207) is reported."""
+@pytest.mark.parametrize("kinds", [("rect",), ("disc",), ("sphere",), ("rect", "disc", "sphere", "distant")])
+@pytest.mark.parametrize("opts", [dict(), dict(useEmissiveLights=False, doMNEE=False)])
+def test_analytic_area_lights_match_oracle(torch_cuda, oracle, kinds, opts):
+    """Rect, disc and sphere analytic lights (sampleRectAreaLight / sampleDiscAreaLight / sampleSphereAreaLight +
+    finalizeAreaLightSample, LightHelpers.slang:70-168) one kind at a time and mixed, with and without the emissive quad."""
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.analytic_lights_scene(kinds=kinds)
+    kw = dict(maxBounces=5)
+    kw.update(opts)
+    p = binding.Pltpt(**kw)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    w, h, frame = 64, 36, 2
+    c = scene.with_jitter(cam, frame, w, h)
+    gpu_b = p.sample_stage_host(c, frame, w, h)
+    gpu = p.render_frame_host(c, frame, w, h)
+    cpu = osc.render_frame(p.options, c, frame, w, h, want_bounces=True)
+    _, same = parity.compare_bounces(gpu_b, cpu["bounces"])
+    m = parity.compare_color(gpu["color"], cpu["color"], same)
+    m["identical_paths"] = float(same.mean())
+    parity.record("analytic/" + "+".join(kinds) + "/" + ",".join(f"{k}={v}" for k, v in opts.items()), m)
+    assert same.mean() >= 0.99 and m["nonfinite_gpu"] == 0, (kinds, opts, m)
+    assert m["frac_pixels_within_1e-3"] >= 0.985 and m["frac_pixels_within_1e-2"] >= 0.995 and m["mean_rel_diff"] <= 0.03, (kinds, opts, m)
+    if not opts.get("useEmissiveLights", True):  # lit by the analytic lights alone: they must light the scene
+        assert gpu["color"][..., :3].mean() > 1e-4 and cpu["color"][..., :3].mean() > 1e-4
+    p.close()
+
+
+# converged-image check: (width, height, GPU spp, oracle spp) -- the Cornell box (BASELINE configs[1]) at the larger size
+CONVERGED = {"cornell": (240, 135, 4096, 1024)}
+CONVERGED_DEFAULT = (160, 90, 2048, 512)
+
+
+def test_converged_image_within_3_sigma(loaded, torch_cuda, oracle):
+    """GPU render (frames 0..N-1) vs an INDEPENDENT oracle render (frames 100000..100000+M-1): per pixel and channel the means must agree
+    within 3 sigma of the combined standard error; relMSE (ImageCompare.cpp:198-207) is recorded (gpurun_out/image_parity.json ->
+    profiles/image_parity.json)."""
     from pltfalcor_b200 import scene
     name, buffers, cam, p, osc = loaded
-    w, h = 48, 27
-    n_gpu, n_cpu = 512, 192
+    w, h, n_gpu, n_cpu = CONVERGED.get(name, CONVERGED_DEFAULT)
     torch = torch_cuda
+    threads = oracle.hardware_threads()
     col = torch.zeros((h, w, 4), device="cuda")
-    s1 = np.zeros((h, w, 3)); s2 = np.zeros((h, w, 3))
+    s1 = torch.zeros((h, w, 3), device="cuda", dtype=torch.float64); s2 = torch.zeros_like(s1)
     for f in range(n_gpu):
         p.render_frame(scene.with_jitter(cam, f, w, h), f, w, h, col)
-        x = col[..., :3].double().cpu().numpy()
+        x = col[..., :3].double()
         s1 += x; s2 += x * x
+    s1, s2 = s1.cpu().numpy(), s2.cpu().numpy()
     mean_g = s1 / n_gpu
     var_g = np.maximum(s2 / n_gpu - mean_g ** 2, 0) * n_gpu / (n_gpu - 1)
     t1 = np.zeros((h, w, 3)); t2 = np.zeros((h, w, 3))
-    for f in range(1000, 1000 + n_cpu):
-        x = osc.render_frame(p.options, scene.with_jitter(cam, f, w, h), f, w, h)["color"][..., :3].astype(np.float64)
+    for f in range(100000, 100000 + n_cpu):
+        x = osc.render_frame(p.options, scene.with_jitter(cam, f, w, h), f, w, h, threads=threads)["color"][..., :3].astype(np.float64)
         t1 += x; t2 += x * x
     mean_c = t1 / n_cpu
     var_c = np.maximum(t2 / n_cpu - mean_c ** 2, 0) * n_cpu / (n_cpu - 1)
-    sigma = np.sqrt(var_g / n_gpu + var_c / n_cpu)
-    # firefly-dominated pixels have unreliable variance estimates at these sample counts: floor sigma at 2 % of the image mean
-    sigma = np.maximum(sigma, 0.02 * mean_c.mean())
+    sigma_raw = np.sqrt(var_g / n_gpu + var_c / n_cpu)
+    # firefly-dominated pixels have unreliable variance estimates at these sample counts: floor sigma at 0.5 % of the image mean
+    sigma = np.maximum(sigma_raw, 0.005 * mean_c.mean())
     z = np.abs(mean_g - mean_c) / sigma
     frac = float((z <= 3.0).mean())
+    lit = sigma_raw > 0
+    frac_raw = float((np.abs(mean_g - mean_c)[lit] <= 3.0 * sigma_raw[lit]).mean()) if lit.any() else 1.0
     relmse = parity.rel_mse(mean_g, mean_c)
-    print(f"[{name}] within-3sigma fraction {frac:.4f}, relMSE {relmse:.4e}, mean gpu {mean_g.mean():.5f} cpu {mean_c.mean():.5f}")
-    assert frac >= 0.985, (name, frac, relmse)
-    assert abs(mean_g.mean() - mean_c.mean()) <= 0.05 * mean_c.mean() + 3 * np.sqrt((sigma ** 2).mean() / sigma.size), (name, mean_g.mean(), mean_c.mean())
+    parity.IMAGE_PARITY[name] = {"scene": name, "width": w, "height": h, "gpu_spp": n_gpu, "oracle_spp": n_cpu, "frac_within_3sigma": frac,
+                                 "frac_within_3sigma_no_floor": frac_raw, "sigma_floor": "0.5 % of the image mean", "relMSE": relmse,
+                                 "mean_gpu": float(mean_g.mean()), "mean_oracle": float(mean_c.mean()), "max_z": float(z.max()),
+                                 "dropped_connections": int(p.stats()["droppedConnections"])}
+    print(f"[{name}] within-3sigma fraction {frac:.4f} (no floor {frac_raw:.4f}), relMSE {relmse:.4e}, mean gpu {mean_g.mean():.5f} cpu {mean_c.mean():.5f}")
+    assert frac >= 0.99, (name, frac, frac_raw, relmse)
+    assert abs(mean_g.mean() - mean_c.mean()) <= 0.02 * mean_c.mean() + 3 * np.sqrt((sigma ** 2).mean() / sigma.size), (name, mean_g.mean(), mean_c.mean())
+    assert p.stats()["droppedConnections"] == 0
 
 
 def test_frames_are_deterministic_and_partitionable(torch_cuda, cornell):

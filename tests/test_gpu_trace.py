@@ -25,7 +25,11 @@ def loaded(request, torch_cuda, oracle):
     p.close()
 
 
-def _trace_gpu(torch, p, rays):
+MODES = {"one_ray_per_thread": 1, "persistent_lanes": 2}  # include/pltpt.h PLTPT_TRACE_*: both traversal drivers of the renderer
+
+
+def _trace_gpu(torch, p, rays, mode=0):
+    p.set_trace_mode(mode)
     r = torch.from_numpy(rays).cuda()
     hits = torch.zeros((len(rays), 4), dtype=torch.int32, device="cuda")
     t = torch.zeros(len(rays), dtype=torch.float32, device="cuda")
@@ -44,21 +48,66 @@ def test_bvh_build_stats(loaded):
     assert s["bvhBuildMs"] > 0
 
 
-def test_closest_hit_bit_exact(loaded, torch_cuda):
+@pytest.fixture(scope="module")
+def brute_reference(loaded):
+    """The fixed ray set of a scene and the oracle's brute-force answers (computed once, compared with both traversal drivers)."""
     name, buffers, cam, p, osc = loaded
     rng = np.random.default_rng(11)
     n_rand = 6000 if buffers.triangle_count > 1000 else 20000
     rays = np.concatenate([parity.camera_rays(cam, 96, 54), parity.random_rays(rng, buffers, n_rand), parity.random_rays(rng, buffers, 2000, tmax=0.5)])
-    hits, t, occ = _trace_gpu(torch_cuda, p, rays)
     ref_hits, ref_t = osc.trace_closest(rays, brute=True)
     ref_occ = osc.trace_any(rays, brute=True)
+    return rays, ref_hits, ref_t, ref_occ
+
+
+def _assert_bit_exact(name, osc, rays, hits, t, ref_hits, ref_t):
     bad = np.nonzero((hits != ref_hits).any(axis=1) | (t.view(np.uint32) != ref_t.view(np.uint32)))[0]
     # exact ties are listed (north star): a mismatch is only tolerable where several triangles share the minimum t
     ties = [(int(i), osc.count_ties(rays[i])) for i in bad[:50]]
     assert len(bad) == 0, f"{name}: {len(bad)} of {len(rays)} rays differ; (ray, #triangles at min t) = {ties}"
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_closest_hit_bit_exact(loaded, brute_reference, torch_cuda, mode):
+    """Both traversal drivers -- the one-ray-per-thread loop (tiny scenes, occluder chains) and the persistent-lane driver every
+    rendering kernel of a non-trivial scene uses (travPersistent / processNode) -- against the brute-force loop, on every scene."""
+    name, buffers, cam, p, osc = loaded
+    rays, ref_hits, ref_t, ref_occ = brute_reference
+    hits, t, occ = _trace_gpu(torch_cuda, p, rays, MODES[mode])
+    _assert_bit_exact(f"{name}/{mode}", osc, rays, hits, t, ref_hits, ref_t)
     assert (hits[:, 0] != 0xFFFFFFFF).mean() > 0.2  # the ray set does exercise hits
     assert np.array_equal(occ, ref_occ)
     assert p.stats()["traversalStackOverflows"] == 0
+
+
+def test_closest_hit_bit_exact_10m_triangles(torch_cuda, oracle):
+    """BASELINE config 5 at its full size (9.99 M triangles, 1.6 M wide nodes): a fixed ray set against the oracle's brute-force loop
+    over all triangles (independent of any tree), then a hundred times more rays against the oracle's own CPU BVH (a different
+    builder over the same world-space triangles), through both traversal drivers."""
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.city_scene(10_000_000)
+    p = binding.Pltpt(maxBounces=8)
+    p.set_scene(buffers)
+    osc = oracle.OracleScene(buffers)
+    threads = oracle.hardware_threads()
+    rng = np.random.default_rng(5)
+    cam_rays = parity.camera_rays(cam, 192, 108)
+    brute = np.concatenate([cam_rays[rng.choice(len(cam_rays), 1000, replace=False)], parity.random_rays(rng, buffers, 500), parity.random_rays(rng, buffers, 250, tmax=0.2)])
+    ref_hits, ref_t = osc.trace_closest(brute, brute=True, threads=threads)
+    ref_occ = osc.trace_any(brute, brute=True, threads=threads)
+    many = np.concatenate([cam_rays, parity.random_rays(rng, buffers, 100_000), parity.random_rays(rng, buffers, 50_000, tmax=0.1)])
+    tree_hits, tree_t = osc.trace_closest(many, brute=False, threads=threads)
+    assert (ref_hits[:, 0] != 0xFFFFFFFF).mean() > 0.3
+    for mode in sorted(MODES):
+        hits, t, occ = _trace_gpu(torch_cuda, p, brute, MODES[mode])
+        _assert_bit_exact(f"city10m/{mode}/brute", osc, brute, hits, t, ref_hits, ref_t)
+        assert np.array_equal(occ, ref_occ)
+        hits, t, occ = _trace_gpu(torch_cuda, p, many, MODES[mode])
+        _assert_bit_exact(f"city10m/{mode}/tree", osc, many, hits, t, tree_hits, tree_t)
+        assert np.array_equal(occ == 1, hits[:, 0] != 0xFFFFFFFF)
+    s = p.stats()
+    assert s["traversalStackOverflows"] == 0 and s["triangleCount"] == buffers.triangle_count
+    p.close()
 
 
 def test_any_hit_consistent_with_closest(loaded, torch_cuda):
