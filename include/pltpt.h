@@ -489,6 +489,8 @@ typedef struct PltptStats {
     uint64_t kernelLaunchCount[PLTPT_KERNEL_CLASS_COUNT];
     uint64_t unwindJobSteps;                   /* work items of k_unwind_step: one generalized ray pushed through one recorded vertex */
     uint64_t mneeWalks;                        /* manifold walks parked for k_mnee in the last tile of the last frame */
+    double   bvhSahCost;                       /* SAH cost of the wide BVH relative to the root area (c_node = 1, c_prim = 0.3): the
+                                                  minimum the collapse could reach on the binary tree (bvh.cu k_sah_costs) */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);

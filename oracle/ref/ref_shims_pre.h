@@ -1,0 +1,65 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// ref_shims_pre.h — what the transpiled reference modules (oracle/_ref/ref_gen.h) expect from the engine around them, declared before
+// them: the compile-time HWSS width, the sample-generator free functions, and the two engine structs the BSDF code reads.
+// Hand-written (engine plumbing, not PLT physics); every item cites the reference declaration it stands in for.
+#pragma once
+#include "slang_compat.h"
+
+namespace ref {
+
+// Utils/HWSS.slang:33-37 with HWSS_SAMPLES = 4 (PLTPT's default `HWSS`, PLTPT.h:87)
+static const uint hwss_samples = 4;
+typedef float4 hwss_t;
+
+// Utils/Sampling/SampleGeneratorInterface.slang:48-75: the generator only has to provide next() (32 random bits)
+template <class S> float sampleNext1D(S& sg) {
+    uint bits = sg.next();
+    return (bits >> 8) * 0x1p-24f;
+}
+template <class S> float2 sampleNext2D(S& sg) {
+    float2 sample;
+    sample.x = sampleNext1D(sg);
+    sample.y = sampleNext1D(sg);
+    return sample;
+}
+template <class S> float3 sampleNext3D(S& sg) {
+    float3 sample;
+    sample.x = sampleNext1D(sg);
+    sample.y = sampleNext1D(sg);
+    sample.z = sampleNext1D(sg);
+    return sample;
+}
+
+// Scene/ShadingData.slang:46-107: the fields and the two frame transforms the PLT BSDFs use
+struct ShadingData {
+    float3 posW, V, N, T, B, faceN;
+    float2 uv;
+    bool frontFacing = true;
+    uint materialID = 0;
+    float3 fromLocal(float3 v) const { return T * v.x + B * v.y + N * v.z; }
+    float3 toLocal(float3 v) const { return float3(dot(v, T), dot(v, B), dot(v, N)); }
+};
+
+// Rendering/Materials/LobeType.slang:36-68
+enum class LobeType : uint {
+    None = 0x00, DiffuseReflection = 0x01, ScatterReflection = 0x02, DeltaReflection = 0x04, DispersiveDeltaReflection = 0x08,
+    DiffuseTransmission = 0x10, ScatterTransmission = 0x20, DeltaTransmission = 0x40, DispersiveDeltaTransmission = 0x80,
+    Diffuse = 0x11, Scatter = 0x22, NonDispersiveDelta = 0x44, DispersiveDelta = 0x88, Delta = 0xCC, NonDelta = 0x33,
+    Reflection = 0x0f, Transmission = 0xf0, NonDeltaReflection = 0x03, NonDeltaTransmission = 0x30, ClientSide = 0xff, All = 0xffff, MaterialSpecifc = 0xff00,
+};
+static const uint LobeTypeMaterialSpecificOffset = 8;
+// Rendering/Materials/IMaterialInstance.slang:44-60
+enum class BSDFEvaluationFlags : uint { None = 0 };
+static const float QcutoffForMS = .15f;
+
+// Scene/Scene.slang:251-294 is transpiled (gScene.evalSpectrum); the table it reads is set by the caller of the comparison
+struct SpectralProfile {  // Scene/Material/BasicMaterialData.slang:43-54
+    float3 rgb;
+    float intensity;
+    uint bins;
+    float minWavelength, maxWavelength;
+    float pdf[128];
+    float icdf[128];
+};
+
+}  // namespace ref

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ref_transpile.py — compiles the reference's own PLT shader text for the CPU.
+
+`slangc` is not available offline, so the reference's Slang modules cannot be built with their own compiler.  Their
+physics core is, however, plain C-like code.  This script reads the modules listed in SOURCES from /root/reference where they lie,
+applies the purely TEXTUAL rewrite rules below (no statement of the reference is re-typed by hand, nothing is re-ordered inside a
+function), and writes the result to oracle/_ref/ref_gen.h (git-ignored: reference text never enters the repository).  Together with
+oracle/ref/slang_compat.h (HLSL vector / matrix types and intrinsics in C++) and oracle/ref/ref_shims.h (the few engine services
+the modules call: gScene.evalSpectrum on a caller-provided table, the sample generator, ShadingData) it is compiled by
+`make -C oracle ref` into oracle/_ref/ref_compare, which runs the oracle (namespace orc) and the transpiled reference
+(namespace ref) on the same random inputs and prints the largest deviation per function (tests/test_oracle_ref.py).
+
+Rewrite rules (all mechanical; each is a regular expression or a brace-matched block move):
+  R1  strip comments-only license headers, `import`, `__exported import`, `#include "*.slangh"`, `#pragma once`
+  R2  floating literals get an `f` suffix (Slang literals are fp32; C++ ones would silently compute in double)
+  R3  `__init(` -> constructor of the enclosing struct (+ a defaulted default constructor); `this.` -> `this->`
+  R4  `[mutating]`, `[unroll]`, `[ForceInline]`... attributes dropped; `no_diff` dropped
+  R5  `property NAME : T { get { BODY } }` -> `T NAME() { BODY }`; uses listed in PROPERTY_USES get `()`
+  R6  generics `RET NAME<S : ISampleGenerator>(` -> `template <class S> RET NAME(`
+  R7  `out T x` / `inout T x` parameters -> `T& x`
+  R8  multi-component swizzles `.xy` -> `.xy()` (read-only in these modules); `rgb.r/.g/.b` -> `.x/.y/.z`; `.x` on scalars dropped
+  R9  `A.B` static access -> `A::B` for the names in STATIC_SCOPES; `struct X : IFoo` loses the interface list
+  R10 `static const float` -> `static constexpr float`; struct-typed `const` locals / parameters lose `const` (Slang methods are
+      callable on them; C++ would need const-qualified methods), structs get their trailing `;`
+  R11 the handful of vector-condition ternaries (`c ? a : b` with bool2 `c`, DiffractionGrating.slang only) -> select(c, a, b); listed in PATCHES
+      with the exact source text they replace -- the script fails if a patch no longer matches.
+"""
+import os
+import re
+import sys
+
+REF = "/root/reference/Source/Falcor"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+
+# (path, None = whole file | list of top-level items to extract by name)
+SOURCES = [
+    ("Utils/Math/MathConstants.slangh", "defines"),
+    ("Utils/Math/MathHelpers.slang", ["sqr", "norm2", "factorial", "c_t", "cnorm2", "cabs", "csqrt", "cconj", "creal", "cimag", "cmul", "cdiv", "csqr", "carg", "sinc",
+                                      "sample_disk", "sample_cone", "sample_sphere", "sample_disk_concentric", "sample_cosine_hemisphere_concentric", "cosine_hemisphere_concentric_pdf",
+                                      "sample_triangle", "sample_boxmueller", "boxmueller_pdf", "sample_boxmueller_truncated", "boxmueller_truncated_pdf", "tryInvert", "inverse",
+                                      "diag2", "ident2", "svd_symmetric", "perp_stark", "BesselJ_saa", "BesselJ_laa", "BesselJ", "ndir_to_oct_equal_area_snorm", "oct_to_ndir_equal_area_snorm",
+                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm"]),
+    ("Utils/Color/ColorHelpers.slang", ["XYZtoRGB_Rec709"]),
+    ("Utils/Color/SpectrumUtils.slang", None),
+    ("Rendering/Materials/Fresnel.slang", None),
+    ("Rendering/Materials/PLT/Mueller.slang", None),
+    ("Rendering/PLT.slang", None),
+    ("Rendering/Materials/PLT/Interference.slang", None),
+    ("Rendering/Materials/PLT/FractalSurface.slang", None),
+    ("Rendering/Materials/PLT/GaussianSurface.slang", None),
+    ("Rendering/Materials/PLT/Birefringence.slang", None),
+]
+
+STATIC_SCOPES = ["SpectrumUtils", "Birefringence"]
+PROPERTY_USES = [r"gfs\.q", r"gfs\.roughness", r"surface\.q", r"surface\.roughness"]
+# exact-text patches: (file suffix, old, new, why)
+PATCHES = [
+    ("Utils/Math/MathHelpers.slang", "float1 sqr(float1 v) { return v*v; }", "", "float1 (1-vectors) are not modelled"),
+    ("Utils/Color/SpectrumUtils.slang", "static const float3 rgbWavelengths = float3(630,532,467);", "static inline const float3 rgbWavelengths = float3(630,532,467);",
+     "C++ needs `inline` for a class-type static data member defined in the class"),
+    ("Utils/Color/ColorHelpers.slang", "static const float3x3 M =\n    {", "static const float3x3 M =\n    float3x3{", "list-initialisation of the matrix type"),
+]
+
+
+def read(path):
+    with open(os.path.join(REF, path)) as f:
+        return f.read()
+
+
+def strip_comments_keep_lines(s):
+    """Block comments and line comments removed (reference prose does not need to travel into the generated file)."""
+    s = re.sub(r"/\*.*?\*/", lambda m: "\n" * m.group(0).count("\n"), s, flags=re.S)
+    s = re.sub(r"//[^\n]*", "", s)
+    return s
+
+
+def match_brace(s, i):
+    """index just past the brace block that opens at s[i] == '{'"""
+    depth = 0
+    for j in range(i, len(s)):
+        if s[j] == "{":
+            depth += 1
+        elif s[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return j + 1
+    raise ValueError("unbalanced braces")
+
+
+def extract_items(s, names):
+    """Top-level functions / structs with the given names (all overloads of a name in source order), emitted in the order of `names`
+    (Slang resolves names regardless of declaration order, C++ needs the callee first)."""
+    found = {n: [] for n in names}
+    pat = re.compile(r"^(?:static\s+)?(?:const\s+)?[\w<>,:]+\s+(\w+)\s*\([^;{]*\)\s*\{|^struct\s+(\w+)[^{;]*\{", re.M)
+    pos = 0
+    while True:
+        m = pat.search(s, pos)
+        if not m:
+            break
+        name = m.group(1) or m.group(2)
+        end = match_brace(s, m.end() - 1)
+        if name in found:
+            found[name].append(s[m.start():end] + (";" if m.group(2) else ""))
+        pos = end
+    missing = [n for n in names if not found[n]]
+    if missing:
+        raise SystemExit(f"items not found in the reference source: {missing}")
+    return "\n".join("\n".join(found[n]) for n in names)
+
+
+FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
+
+
+def rule_literals(s):
+    return FLOAT_LIT.sub(lambda m: m.group(1) + "f", s)
+
+
+def rule_defines(s):
+    """MathConstants.slangh: keep the #define lines of the shader branch, as fp32 literals."""
+    body = s[s.index("#else"):s.index("#endif // !HOST_CODE")]
+    out = []
+    for line in body.splitlines():
+        m = re.match(r"#define\s+(\w+)\s+(\S+)", line)
+        if m and (m.group(1).startswith("M_") or m.group(1).startswith("FLT_")):
+            val = m.group(2)
+            if re.fullmatch(r"[-+]?(\d+\.\d*|\.\d+)([eE][+-]?\d+)?", val):
+                val += "f"
+            out.append(f"#undef {m.group(1)}\n#define {m.group(1)} {val}")
+    return "\n".join(out)
+
+
+def rule_structs(s):
+    """R3, R5, R9 (interface lists), R10 (trailing ';'): per struct, brace matched."""
+    out, pos = [], 0
+    pat = re.compile(r"\bstruct\s+(\w+)\s*(:[^{]*)?\{")
+    while True:
+        m = pat.search(s, pos)
+        if not m:
+            out.append(s[pos:])
+            break
+        name = m.group(1)
+        end = match_brace(s, m.end() - 1)
+        body = s[m.end():end - 1]
+        had_init = "__init" in body
+        body = re.sub(r"\b__init\s*\(", name + "(", body)
+        if had_init:
+            body = f"\n    {name}() = default;" + body
+        # properties -> getters
+        def prop(pm):
+            pname, ptype = pm.group(1), pm.group(2)
+            b0 = body_ref[0].index("{", pm.end() - 1)
+            return None
+        body_ref = [body]
+        pp = re.compile(r"\bproperty\s+(\w+)\s*:\s*(\w+)\s*\{")
+        props = []
+        while True:
+            pm = pp.search(body)
+            if not pm:
+                break
+            pend = match_brace(body, pm.end() - 1)
+            inner = body[pm.end():pend - 1]
+            gm = re.search(r"\bget\s*\{", inner)
+            gend = match_brace(inner, gm.end() - 1)
+            getter = inner[gm.end():gend - 1]
+            body = body[:pm.start()] + f"{pm.group(2)} {pm.group(1)}() {{{getter}}}" + body[pend:]
+            props.append(pm.group(1))
+        for p in props:  # bare uses inside the struct: not a member access of something else, not already a call, not a declaration
+            body = re.sub(rf"(?<![\w.]){p}\b(?!\s*\()", p + "()", body)
+            body = re.sub(rf"\b(\w+)\s+{p}\(\)\(\)\s*\{{", rf"\1 {p}() {{", body)
+        body = rule_structs(body)  # nested structs
+        tail = s[end:end + 1]
+        out.append(s[pos:m.start()] + f"struct {name} {{" + body + "}" + ("" if tail == ";" else ";"))
+        pos = end
+    return "".join(out)
+
+
+def scalar_swizzles(s):
+    """R8c: `.x` applied to a variable declared as a plain float in the same function (`k.x` where `const float k`)."""
+    floats = set(re.findall(r"\b(?:const\s+)?float\s+(\w+)\s*(?:=|;|,|\))", s))
+    for name in floats:
+        # only if no vector declaration of the same name exists in the text unit
+        if re.search(rf"\b(?:float[234]|hwss_t|int2|uint2)\s+{name}\b", s):
+            continue
+        s = re.sub(rf"(?<![\w.]){name}\.x\b", name, s)
+    return s
+
+
+def per_function(s, fn):
+    """applies fn to every outermost brace block that follows a ')' (function bodies), leaving the rest untouched"""
+    out, pos = [], 0
+    for m in re.finditer(r"\)\s*(?:const\s*)?\{", s):
+        if m.start() < pos:
+            continue
+        b = m.end() - 1
+        e = match_brace(s, b)
+        # include the parameter list (walk back to the matching '(')
+        depth, a = 0, m.start()
+        while a >= 0:
+            if s[a] == ")":
+                depth += 1
+            elif s[a] == "(":
+                depth -= 1
+                if depth == 0:
+                    break
+            a -= 1
+        out.append(s[pos:a])
+        out.append(fn(s[a:e]))
+        pos = e
+    out.append(s[pos:])
+    return "".join(out)
+
+
+def transpile(path, s, struct_names):
+    for suffix, old, new, _why in PATCHES:
+        if path.endswith(suffix):
+            if old not in s:
+                raise SystemExit(f"patch for {path} no longer matches: {old[:60]!r}")
+            s = s.replace(old, new)
+    s = strip_comments_keep_lines(s)
+    # R1
+    s = re.sub(r"^\s*(__exported\s+)?import\s+[\w.]+\s*;\s*$", "", s, flags=re.M)
+    s = re.sub(r'^\s*#include\s+"[^"]*"\s*$', "", s, flags=re.M)
+    s = re.sub(r"^\s*#pragma once\s*$", "", s, flags=re.M)
+    # R4
+    s = re.sub(r"\[mutating\]\s*", "", s)
+    s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
+    s = re.sub(r"\bno_diff\s+", "", s)
+    # R2
+    s = rule_literals(s)
+    # R6
+    s = re.sub(r"^(\s*)((?:static\s+)?[\w:<>]+\s+)(\w+)\s*<\s*(\w+)\s*:\s*\w+\s*>\s*\(", r"\1template <class \4> \2\3(", s, flags=re.M)
+    # R7
+    s = re.sub(r"\b(?:in)?out\s+((?:const\s+)?[\w:]+)\s+(\w+)", r"\1& \2", s)
+    # R3 (this) + structs
+    s = re.sub(r"\bthis\.", "this->", s)
+    s = rule_structs(s)
+    # R9
+    for sc in STATIC_SCOPES:
+        s = re.sub(rf"\b{sc}\.(?=\w)", sc + "::", s)
+    s = re.sub(r"\b(\w+)\.Flags::", r"\1::Flags::", s)
+    # R8
+    s = re.sub(r"\brgb\.r\b", "rgb.x", s)
+    s = re.sub(r"\brgb\.g\b", "rgb.y", s)
+    s = re.sub(r"\brgb\.b\b", "rgb.z", s)
+    s = re.sub(r"\.([xyzw]{2,4})\b(?!\s*\()", r".\1()", s)
+    s = per_function(s, scalar_swizzles)
+    for pu in PROPERTY_USES:
+        s = re.sub(rf"\b({pu})\b(?!\s*\()", r"\1()", s)
+    # R10
+    s = re.sub(r"\bstatic\s+const\s+(float|int|uint|bool)\b", r"static constexpr \1", s)
+    if struct_names:
+        s = re.sub(r"\bconst\s+(" + "|".join(sorted(struct_names, key=len, reverse=True)) + r")\b", r"\1", s)
+    s = re.sub(r"\n{3,}", "\n\n", s)
+    return s
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("/root/reference is not present: oracle/_ref can only be (re)generated where the reference lies")
+    os.makedirs(OUT, exist_ok=True)
+    texts = []
+    for path, what in SOURCES:
+        raw = read(path)
+        if what == "defines":
+            texts.append((path, rule_defines(raw), True))
+            continue
+        if what is not None:
+            for suffix, old, new, _why in PATCHES:  # patches address the original text: apply before extraction
+                pass
+            raw_nc = raw
+            raw = extract_items(strip_comments_keep_lines(raw_nc) if False else raw_nc, what)
+        texts.append((path, raw, False))
+    struct_names = set()
+    for _p, t, _d in texts:
+        struct_names.update(re.findall(r"\bstruct\s+(\w+)", t))
+    struct_names.update(["ShadingData", "DifferentialShadingGeometry"])
+    parts = ["// GENERATED by oracle/ref_transpile.py from the reference's Slang sources under /root/reference -- not part of the repository.",
+             "#pragma once", '#include "../ref/slang_compat.h"', '#include "../ref/ref_shims_pre.h"', "namespace ref {"]
+    for path, t, is_def in texts:
+        parts.append(f"\n// ======== {path}")
+        parts.append(t if is_def else transpile(path, t, struct_names))
+    parts.append("}  // namespace ref")
+    out = os.path.join(OUT, "ref_gen.h")
+    with open(out, "w") as f:
+        f.write("\n".join(parts) + "\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,10 +121,11 @@ extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {
 extern "C" int pltpt_reset_stats(PltptHandle h) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (int r = syncFrameStats(h)) return r;
-    const double b = h->stats.bvhBuildMs;
+    const double b = h->stats.bvhBuildMs, sahCost = h->stats.bvhSahCost;
     const uint64_t n = h->stats.bvhNodes, l = h->stats.bvhLeafTriangles, t = h->stats.triangleCount, ov = h->stats.traversalStackOverflows;
     h->stats = PltptStats{};
     h->stats.traversalStackOverflows = ov;
+    h->stats.bvhSahCost = sahCost;
     h->stats.bvhBuildMs = b; h->stats.bvhNodes = n; h->stats.bvhLeafTriangles = l; h->stats.triangleCount = t;
     return PLTPT_OK;
 }

@@ -7,10 +7,15 @@
 //   2. k_morton        : 63-bit Morton code of the AABB centre; CUB radix sort (key, triangle)
 //   3. k_radix_tree    : Karras 2012 binary radix tree over the sorted codes (one thread per internal node)
 //   4. k_fit           : bottom-up AABB fit with per-node arrival counters
-//   5. k_collapse      : level-synchronous collapse of the binary tree into 8-wide nodes. Children are opened greedily
-//                        by surface area (the SAH term: expected traversal cost ~ area), subtrees of <= 3 triangles
-//                        become leaf slots; child boxes are quantised to 8 bits on a per-node power-of-two grid
-//                        (80 B nodes, Ylitie et al. 2017) with conservative rounding verified in the kernel.
+//   5. k_sah_costs     : bottom-up dynamic programme of Ylitie et al. 2017 (section 3.1) over the binary tree: C(n, i) = least SAH
+//                        cost of representing the subtree of n by at most i children of a wide node (i = 1..7), with the choices
+//                        "leaf of <= 3 triangles", "own wide node" (cost A_n c_node + best split of 8 slots) and the split of i
+//                        slots between the two binary children recorded per node
+//   6. k_collapse      : level-synchronous top-down pass that follows the recorded choices: every wide node takes the SAH-optimal
+//                        set of <= 8 descendants of its binary node as children, puts each into the slot of the octant it lies in,
+//                        and quantises the child boxes to 8 bits on a per-node power-of-two grid (80 B nodes) with conservative
+//                        rounding verified in the kernel.  The level loop runs on the device (rotating queue counters); the host
+//                        looks at the queue length once every 16 levels.
 // Flat world-space BVH: static instances are pre-transformed exactly like Falcor does for static meshes
 // (Scene.cpp:2712-2717), so one traversal handles BLAS+TLAS.
 #include "bvh_traverse.cuh"
@@ -157,6 +162,61 @@ __global__ void k_fit(int n, const uint32_t* __restrict__ sorted, const float4* 
     }
 }
 
+// ---- SAH-optimal collapse into wide nodes (Ylitie, Karras, Laine 2017, section 3.1) -------------------------------------------
+constexpr float kCostNode = 1.f, kCostPrim = .3f;
+// per binary internal node: cost[7] = C(n, 1..7); choice[8]: [0] = 1 when C(n,1) is the "own wide node" option (0 = leaf),
+// [i-1] for i = 2..7 = slots given to the left child when i slots are split (0 = use C(n, i-1) instead), [7] = the same for 8 slots
+struct SahTables { float* cost; uint8_t* choice; };
+PLT_D float boxArea(float4 l, float4 h) { const float ex = h.x - l.x, ey = h.y - l.y, ez = h.z - l.z; return ex * ey + ey * ez + ez * ex; }
+__global__ void k_sah_costs(int n, const uint32_t* __restrict__ sorted, const float4* __restrict__ triLo, const float4* __restrict__ triHi, const uint32_t* __restrict__ left,
+                            const uint32_t* __restrict__ right, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, const uint32_t* __restrict__ parentInner,
+                            const uint32_t* __restrict__ parentLeaf, const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, uint32_t* __restrict__ arrivals, SahTables sah) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t node = parentLeaf[p];
+    while (node != 0xffffffffu) {
+        __threadfence();
+        if (atomicAdd(arrivals + node, 1u) == 0u) return;  // the sibling subtree is not finished yet
+        __threadfence();
+        float C[2][8];  // C[side][i], i = 1..7
+        const uint32_t c[2] = {left[node], right[node]};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (c[k] & kLeafBit) {
+                const uint32_t t = sorted[c[k] & ~kLeafBit];
+                const float a = boxArea(triLo[t], triHi[t]) * kCostPrim;
+                for (int i = 1; i <= 7; ++i) C[k][i] = a;
+            } else
+                for (int i = 1; i <= 7; ++i) C[k][i] = __ldcg(sah.cost + size_t(c[k]) * 7 + (i - 1));
+        }
+        const float A = boxArea(nodeLo[node], nodeHi[node]);
+        const uint32_t N = last[node] - first[node] + 1u;
+        float D[9];
+        uint8_t Dk[9];
+        for (int j = 2; j <= 8; ++j) {
+            float best = FLT_MAX;
+            int bk = 1;
+            for (int k = (j - 7 > 1 ? j - 7 : 1); k <= j - 1 && k <= 7; ++k) {
+                const float v = C[0][k] + C[1][j - k];
+                if (v < best) { best = v; bk = k; }
+            }
+            D[j] = best; Dk[j] = uint8_t(bk);
+        }
+        float out[8];
+        uint8_t ch[8];
+        const float internal = A * kCostNode + D[8];
+        const float leaf = N <= kMaxLeafTris ? A * float(N) * kCostPrim : FLT_MAX;
+        out[1] = fminf(leaf, internal); ch[0] = internal < leaf ? 1 : 0; ch[7] = Dk[8];
+        for (int i = 2; i <= 7; ++i) {
+            if (D[i] < out[i - 1]) { out[i] = D[i]; ch[i - 1] = Dk[i]; }
+            else { out[i] = out[i - 1]; ch[i - 1] = 0; }
+        }
+        for (int i = 1; i <= 7; ++i) __stcg(sah.cost + size_t(node) * 7 + (i - 1), out[i]);
+        for (int i = 0; i < 8; ++i) sah.choice[size_t(node) * 8 + i] = ch[i];
+        node = parentInner[node];
+    }
+}
+
 struct CollapseItem { uint32_t bin, wide; };
 struct TreeView {
     const uint32_t *left, *right, *first, *last, *sorted;
@@ -200,38 +260,54 @@ PLT_D uint32_t quantHi(float origin, float s, float v) {
     return uint32_t(q);
 }
 
-__global__ void k_collapse(const CollapseItem* __restrict__ items, uint32_t nItems, CollapseItem* __restrict__ nextItems, uint32_t* __restrict__ counters /*0 nodes,1 tris,2 next*/,
-                           TreeView tv, const BvhTri* __restrict__ srcTris, BvhNode* __restrict__ outNodes, BvhTri* __restrict__ outTris, uint32_t rootIsLeaf) {
-    const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= nItems) return;
+// One level of the top-down pass: the items of this level are queue[level & 1][0 .. counts[level % 3]); inner children are appended to the
+// other queue under counts[(level + 1) % 3]; counts[(level + 2) % 3] is re-zeroed for the level after that (nobody reads it meanwhile).
+__global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ queues, uint32_t queueStride, uint32_t level, uint32_t* __restrict__ levelCounts,
+                                                  uint32_t* __restrict__ counters /*0 nodes,1 tris,2 max children seen*/, TreeView tv, SahTables sah, const BvhTri* __restrict__ srcTris,
+                                                  BvhNode* __restrict__ outNodes, BvhTri* __restrict__ outTris, uint32_t rootIsLeaf) {
+    const CollapseItem* items = queues + size_t(level & 1u) * queueStride;
+    CollapseItem* nextItems = queues + size_t((level + 1u) & 1u) * queueStride;
+    const uint32_t nItems = levelCounts[level % 3u];
+    uint32_t* nextCount = levelCounts + (level + 1u) % 3u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) levelCounts[(level + 2u) % 3u] = 0;
+  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
     const CollapseItem item = items[it];
+    // the SAH-optimal children of this wide node: follow the recorded slot splits down from the binary node
     uint32_t c[8];
-    int cnt;
-    if (rootIsLeaf) { c[0] = item.bin; cnt = 1; }
-    else { c[0] = tv.left[item.bin]; c[1] = tv.right[item.bin]; cnt = 2; }
-    while (cnt < 8) {
-        int best = -1;
-        float bestA = -1.f;
-        for (int i = 0; i < cnt; ++i) {
-            if ((c[i] & kLeafBit) || tv.count(c[i]) <= kMaxLeafTris) continue;
-            const float a = tv.area(c[i]);
-            if (a > bestA) { bestA = a; best = i; }
+    bool asLeaf[8];
+    int cnt = 0;
+    if (rootIsLeaf) { c[0] = item.bin; asLeaf[0] = true; cnt = 1; }
+    else {
+        uint32_t stRef[16];
+        uint8_t stSlots[16];
+        int sp = 0;
+        const uint32_t k8 = sah.choice[size_t(item.bin) * 8 + 7];
+        stRef[sp] = tv.right[item.bin]; stSlots[sp++] = uint8_t(8u - k8);
+        stRef[sp] = tv.left[item.bin]; stSlots[sp++] = uint8_t(k8);
+        while (sp > 0) {
+            const uint32_t ref = stRef[--sp];
+            uint32_t slots = stSlots[sp];
+            if (ref & kLeafBit) { c[cnt] = ref; asLeaf[cnt++] = true; continue; }
+            const uint8_t* ch = sah.choice + size_t(ref) * 8;
+            while (slots > 1 && ch[slots - 1] == 0) --slots;  // C(n, i) = C(n, i-1): fewer slots do as well
+            if (slots == 1) { c[cnt] = ref; asLeaf[cnt++] = ch[0] == 0; continue; }
+            const uint32_t k = ch[slots - 1];
+            stRef[sp] = tv.right[ref]; stSlots[sp++] = uint8_t(slots - k);
+            stRef[sp] = tv.left[ref]; stSlots[sp++] = uint8_t(k);
         }
-        if (best < 0) break;
-        const uint32_t b = c[best];
-        c[best] = tv.left[b];
-        c[cnt++] = tv.right[b];
     }
     float3 nlo, nhi;
     tv.box(item.bin, nlo, nhi);
+    for (int i = cnt; i < 8; ++i) c[i] = 0xffffffffu;  // empty slots
+    constexpr uint32_t kEmpty = 0xffffffffu;
     uint32_t nInner = 0, nTris = 0;
-    for (int i = 0; i < cnt; ++i) {
-        const uint32_t k = tv.count(c[i]);
-        if (k > kMaxLeafTris) ++nInner; else nTris += k;
+    for (int i = 0; i < 8; ++i) {
+        if (c[i] == kEmpty) continue;
+        if (!asLeaf[i]) ++nInner; else nTris += tv.count(c[i]);
     }
     const uint32_t childBase = nInner ? atomicAdd(counters + 0, nInner) : 0u;
     const uint32_t triBase = nTris ? atomicAdd(counters + 1, nTris) : 0u;
-    const uint32_t nextBase = nInner ? atomicAdd(counters + 2, nInner) : 0u;
+    const uint32_t nextBase = nInner ? atomicAdd(nextCount, nInner) : 0u;
 
     BvhNode node;
     node.px = nlo.x; node.py = nlo.y; node.pz = nlo.z;
@@ -244,14 +320,14 @@ __global__ void k_collapse(const CollapseItem* __restrict__ items, uint32_t nIte
         node.meta[i] = 0;
         node.qlox[i] = node.qloy[i] = node.qloz[i] = 0;
         node.qhix[i] = node.qhiy[i] = node.qhiz[i] = 0;
-        if (i >= cnt) continue;
+        if (c[i] == kEmpty) continue;
         float3 lo, hi;
         tv.box(c[i], lo, hi);
         node.qlox[i] = uint8_t(quantLo(nlo.x, sx, lo.x)); node.qhix[i] = uint8_t(quantHi(nlo.x, sx, hi.x));
         node.qloy[i] = uint8_t(quantLo(nlo.y, sy, lo.y)); node.qhiy[i] = uint8_t(quantHi(nlo.y, sy, hi.y));
         node.qloz[i] = uint8_t(quantLo(nlo.z, sz, lo.z)); node.qhiz[i] = uint8_t(quantHi(nlo.z, sz, hi.z));
         const uint32_t k = tv.count(c[i]);
-        if (k > kMaxLeafTris) {
+        if (!asLeaf[i]) {
             imask |= 1u << i;
             node.meta[i] = uint8_t(0x20u | (24u + uint32_t(i)));
             nextItems[nextBase + innerSeen] = CollapseItem{c[i], childBase + innerSeen};
@@ -265,6 +341,7 @@ __global__ void k_collapse(const CollapseItem* __restrict__ items, uint32_t nIte
     }
     node.imask = uint8_t(imask);
     outNodes[item.wide] = node;
+  }
 }
 
 template <bool ANY>
@@ -331,7 +408,7 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
     PLT_CUDA(c->bvhNodes.ensure(size_t(n) * sizeof(BvhNode)));
 
     uint32_t* miscU = misc.as<uint32_t>();
-    const uint32_t initMisc[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, /*counters*/ 1u, 0u, 0u, /*overflow*/ 0u, 0, 0, 0, 0, 0, 0};
+    const uint32_t initMisc[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, /*counters*/ 1u, 0u, 0u, /*overflow*/ 0u, /*query cursor*/ 0u, /*level counts*/ 0, 0, 0, 0, 0};
     PLT_CUDA(cudaMemcpyAsync(miscU, initMisc, sizeof(initMisc), cudaMemcpyHostToDevice, s));
     uint32_t* counters = miscU + 6;
 
@@ -356,35 +433,59 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
     uint32_t* parentLeaf = arrivals + n;
     float4* nodeLo = nodeBox.as<float4>();
     float4* nodeHi = nodeLo + n;
-    CollapseItem* q0 = queue.as<CollapseItem>();
-    CollapseItem* q1 = q0 + n;
+    CollapseItem* q0 = queue.as<CollapseItem>();  // two halves of n items: levels alternate between them
     TreeView tv{left, right, first, last, valsOut, nodeLo, nodeHi, triLo.as<float4>(), triHi.as<float4>()};
 
     uint32_t levels = 0;
+    // queue: two halves of n items each; level counts rotate through three words behind the build counters
+    uint32_t* levelCounts = miscU + 11;
+    const uint32_t levelInit[3] = {1u, 0u, 0u};
+    PLT_CUDA(cudaMemcpyAsync(levelCounts, levelInit, sizeof(levelInit), cudaMemcpyHostToDevice, s));
+    SahTables sah{nullptr, nullptr};
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     if (n == 1) {
         // no internal binary node exists: the root wide node gets the single triangle as its only leaf slot
         const CollapseItem root{0u | kLeafBit, 0u};
         PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
-        k_collapse<<<1, 32, 0, s>>>(q0, 1, q1, counters, tv, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 1u);
+        k_collapse<<<1, 128, 0, s>>>(q0, n, 0u, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 1u);
         c->stats.kernelLaunches++;
         levels = 1;
     } else {
         k_radix_tree<<<blocksFor(n - 1, 256), 256, 0, s>>>(int(n), keysOut, left, right, first, last, parentInner, parentLeaf);
         PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(n) * 4, s));
         k_fit<<<blocksFor(n, 256), 256, 0, s>>>(int(n), valsOut, triLo.as<float4>(), triHi.as<float4>(), left, right, parentInner, parentLeaf, nodeLo, nodeHi, arrivals);
-        c->stats.kernelLaunches += 4;
+        // SAH tables of the dynamic programme (7 costs + 8 choices per binary node), bottom-up like the box fit
+        DevBuf& sahBuf = c->lanes[0].work[25];
+        PLT_CUDA(sahBuf.ensure(size_t(n) * (7 * 4 + 8)));
+        sah.cost = sahBuf.as<float>();
+        sah.choice = reinterpret_cast<uint8_t*>(sah.cost + size_t(n) * 7);
+        PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(n) * 4, s));
+        k_sah_costs<<<blocksFor(n, 256), 256, 0, s>>>(int(n), valsOut, triLo.as<float4>(), triHi.as<float4>(), left, right, first, last, parentInner, parentLeaf, nodeLo, nodeHi, arrivals, sah);
+        c->stats.kernelLaunches += 6;
         const CollapseItem root{0u, 0u};
         PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
-        uint32_t nItems = 1;
-        while (nItems > 0) {
-            PLT_CUDA(cudaMemsetAsync(counters + 2, 0, 4, s));
-            k_collapse<<<blocksFor(nItems, 128), 128, 0, s>>>(q0, nItems, q1, counters, tv, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 0u);
-            c->stats.kernelLaunches++;
-            PLT_CUDA(cudaMemcpyAsync(&nItems, counters + 2, 4, cudaMemcpyDeviceToHost, s));
+        // top-down: one launch per level over a persistent grid; the host reads the queue length once per 16 levels only
+        const uint32_t grid = uint32_t(sms) * 8;
+        for (bool more = true; more;) {
+            for (int k = 0; k < 16; ++k, ++levels)
+                k_collapse<<<grid, 128, 0, s>>>(q0, n, levels, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 0u);
+            c->stats.kernelLaunches += 16;
+            uint32_t pending = 0;
+            PLT_CUDA(cudaMemcpyAsync(&pending, levelCounts + levels % 3u, 4, cudaMemcpyDeviceToHost, s));
             PLT_CUDA(cudaStreamSynchronize(s));
-            std::swap(q0, q1);
-            if (++levels > 4096) { setError("BVH collapse did not terminate"); return PLTPT_ERR_CUDA; }
+            more = pending > 0;
+            if (levels > 4096) { setError("BVH collapse did not terminate"); return PLTPT_ERR_CUDA; }
         }
+        float rootCost = 0.f;
+        float4 rl, rh;
+        PLT_CUDA(cudaMemcpyAsync(&rootCost, sah.cost, 4, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaMemcpyAsync(&rl, nodeLo, 16, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaMemcpyAsync(&rh, nodeHi, 16, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaStreamSynchronize(s));
+        const float ra = (rh.x - rl.x) * (rh.y - rl.y) + (rh.y - rl.y) * (rh.z - rl.z) + (rh.z - rl.z) * (rh.x - rl.x);
+        c->stats.bvhSahCost = ra > 0.f ? double(rootCost) / double(ra) : 0.0;
+        sahBuf.release();
     }
     uint32_t finalCounters[3] = {0, 0, 0};
     PLT_CUDA(cudaMemcpyAsync(finalCounters, counters, 12, cudaMemcpyDeviceToHost, s));

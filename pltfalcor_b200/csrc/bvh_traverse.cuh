@@ -66,14 +66,15 @@ struct Hit {
 };
 
 constexpr int kTraversalStack = 160;
-#ifndef PLT_TRAVERSE_DEDUP
-#define PLT_TRAVERSE_DEDUP 0  // 1: traverseBvh() drives processNode() instead of its own copy of the node body (measured before the copy is deleted)
-#endif
+
 
 // Traversal of the compressed wide BVH.  processNode() handles ONE popped node (children slab tests, leaf triangles, ordered push
 // of the inner children).  traverseBvh() runs a ray to completion in the calling thread; the trace kernels of non-trivial scenes
 // drive the same code through travPersistent(), where a lane whose ray has finished takes the next ray of the queue instead
 // of idling until the slowest ray of its warp is done.
+// (Round 2 also measured a node-GROUP stack after Ylitie et al. 2017 -- one stack entry per node, children visited in octant
+// order, branch-free slab tests: 9.2 -> 11.3 ms on the 10 M-triangle city, 5.9 -> 7.7 ms for the manifold walks; rejected,
+// profiles/r2c_kernel_times.log.)
 // ANY = true: finishes at the first accepted triangle.  `overflow` (optional) counts stack overflows (must stay 0; tests check).
 struct TraversalCounters { uint32_t nodes, tris; };
 struct RayConst {
@@ -169,107 +170,24 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
         }
     return false;
 }
-// One ray to completion in the calling thread.  The node body is spelled out here a second time on purpose: routing this loop
-// through processNode() cost the manifold-walk kernel 40 % (7.2 -> 10.1 ms on the grating scene, profiles/r1_kernel_times_noise.log).
+// One ray to completion in the calling thread: the same processNode() the persistent-lane driver steps through (one node body, so the
+// bit-exact hit-ID checks of either driver cover the arithmetic of both; measured equal to a hand-inlined copy, profiles/r2a_variants.log).
 template <bool ANY>
 PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr,
                        TraversalCounters* tc = nullptr) {
     best.instanceID = 0xffffffffu;
     best.t = tmax;
-    const RayPrep rp = prepRay(o, d);
-    const float tiny = 1e-30f;
-    const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
+    RayConst R;
+    rayConstInit(R, o, d, tmin, tmax);
     uint32_t stack[kTraversalStack];
     float stackT[ANY ? 1 : kTraversalStack];  // entry distance of the pushed node: a closer hit found meanwhile culls it at pop time
     int sp = 0;
     stack[sp++] = 0;
     if (!ANY) stackT[0] = tmin;
-#if PLT_TRAVERSE_DEDUP
-    RayConst R;
-    rayConstInit(R, o, d, tmin, tmax);
     while (sp > 0) {
         const uint32_t ni = stack[--sp];
-        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;
+        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit in processNode: exact-t ties are still visited)
         if (processNode<ANY>(nodes, tris, R, ni, best, stack, stackT, sp, overflow, tc)) return true;
-    }
-    return best.valid();
-#endif
-    while (sp > 0) {
-        const uint32_t ni = stack[--sp];
-        if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit below: exact-t ties are still visited)
-        if (tc) ++tc->nodes;
-        const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
-        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-        const uint32_t imask = n0.w >> 24;
-        const uint32_t childBase = n1.x, triBase = n1.y;
-        const uint32_t metaLo = n1.z, metaHi = n1.w;
-        // Slab distances in one FMA per plane: t = q * (s * id) + (p - o) * id.  The library is built with -fmad=false
-        // (fp32 parity of the shading math with the oracle), so the traversal asks for its FMAs explicitly.
-        // Error bound of a plane distance: 4u (|(p-o) id| + 255 |s id|), u = 2^-24; it is folded into the two per-axis
-        // offsets (near planes pulled in, far planes pushed out), so the test stays conservative at no per-child cost.
-        const float sxi = __uint_as_float((n0.w & 0xffu) << 23) * idx, syi = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * idy, szi = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * idz;
-        const float pxi = (__uint_as_float(n0.x) - o.x) * idx, pyi = (__uint_as_float(n0.y) - o.y) * idy, pzi = (__uint_as_float(n0.z) - o.z) * idz;
-        const float ex = 3e-7f * fmaf(255.f, fabsf(sxi), fabsf(pxi)), ey = 3e-7f * fmaf(255.f, fabsf(syi), fabsf(pyi)), ez = 3e-7f * fmaf(255.f, fabsf(szi), fabsf(pzi));
-        const float pxn = pxi - ex, pxf = pxi + ex, pyn = pyi - ey, pyf = pyi + ey, pzn = pzi - ez, pzf = pzi + ez;
-        // quantised planes: n2 = qlox[0..7] (x,y) qloy[0..7] (z,w); n3 = qloz, qhix; n4 = qhiy, qhiz.  Per axis the plane
-        // the ray enters through is `lo` for a positive direction component and `hi` for a negative one.
-        const uint32_t nxA = negx ? n3.z : n2.x, nxB = negx ? n3.w : n2.y, fxA = negx ? n2.x : n3.z, fxB = negx ? n2.y : n3.w;
-        const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
-        const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
-        float nearT[8];
-        uint32_t innerHits = 0, triMask = 0;
-        // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
-        const float tfarLimit = best.t * 1.000002f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xffu;
-            const bool inner = (imask >> i) & 1u;
-            if (meta == 0 && !inner) continue;
-            const int sh = (i & 3) * 8;
-            const float tnx = fmaf(float(((i < 4 ? nxA : nxB) >> sh) & 0xffu), sxi, pxn), tfx = fmaf(float(((i < 4 ? fxA : fxB) >> sh) & 0xffu), sxi, pxf);
-            const float tny = fmaf(float(((i < 4 ? nyA : nyB) >> sh) & 0xffu), syi, pyn), tfy = fmaf(float(((i < 4 ? fyA : fyB) >> sh) & 0xffu), syi, pyf);
-            const float tnz = fmaf(float(((i < 4 ? nzA : nzB) >> sh) & 0xffu), szi, pzn), tfz = fmaf(float(((i < 4 ? fzA : fzB) >> sh) & 0xffu), szi, pzf);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
-            if (!(tn <= tf)) continue;
-            if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
-            else triMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);  // the leaf's triangles: slots [offset, offset + count) of this node's <= 24
-        }
-        // The triangles of all intersected leaf children in ONE loop after the slab tests: tested inside the unrolled child loop, every
-        // child was a separate divergence point (a lane with a leaf hit ran the triangle test while its 31 neighbours waited).
-        while (triMask) {
-            const uint32_t k = uint32_t(__ffs(int(triMask))) - 1u;
-            triMask &= triMask - 1u;
-            const float4* tp = reinterpret_cast<const float4*>(tris + triBase + k);
-            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-            float t, u, v;
-            if (tc) ++tc->tris;
-            if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
-            if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
-            const uint32_t g = __float_as_uint(q2.w);
-            if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
-            best.t = t; best.u = u; best.v = v;
-            best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
-        }
-        // push the intersected inner children, farthest first, so the nearest is popped next
-        while (innerHits) {
-            int far = -1;
-            float ft = -1.f;
-            if (ANY) far = __ffs(innerHits) - 1;
-            else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (((innerHits >> i) & 1u) && (far < 0 || nearT[i] > ft)) { far = i; ft = nearT[i]; }
-            }
-            innerHits &= ~(1u << far);
-            if (sp < kTraversalStack) {
-                if (!ANY) stackT[sp] = ft;
-                stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
-            } else if (overflow) atomicAdd(overflow, 1u);
-        }
     }
     return best.valid();
 }

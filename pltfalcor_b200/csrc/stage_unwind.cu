@@ -64,7 +64,7 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
 }
 
 #ifndef PLT_UNWIND_STAGE
-#define PLT_UNWIND_STAGE 1
+#define PLT_UNWIND_STAGE 0  // measured on B200 (profiles/r2a_variants.log): 1.78 ms with the staging, 1.57 ms without -- left off
 #endif
 #if PLT_UNWIND_STAGE
 // Asynchronous global -> shared copies (LDGSTS): the gather of a thread's NEXT item runs under the BSDF arithmetic of its current one

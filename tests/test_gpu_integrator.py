@@ -39,8 +39,12 @@ W, H = 96, 54
 # Gates sit just above what is measured on B200 (profiles/parity_metrics.json is the record of the last run): a regression that
 # breaks one path in a hundred must fail.  Paths legitimately fork where a random number falls within rounding of a branch
 # threshold (delta/scatter pick, Russian roulette, Fresnel R/T) -- more often on scenes with many specular chains.
-MIN_IDENTICAL_PATHS = {"cornell": 0.995, "grating_sphere": 0.99, "layered": 0.99, "city": 0.99, "env": 0.99, "analytic": 0.995}
-MIN_PIXELS_WITHIN_1E3 = {"cornell": 0.995, "grating_sphere": 0.97, "layered": 0.985, "city": 0.985, "env": 0.985, "analytic": 0.99}
+MIN_IDENTICAL_PATHS = {"cornell": 0.995, "grating_sphere": 0.998, "layered": 0.998, "city": 0.998, "env": 0.998, "analytic": 0.998}
+# Pixels of identical paths that still differ carry a manifold walk: 60 Newton / line-search iterations in fp32 are chaotic for
+# ill-conditioned chains, so a walk may converge on one side and give up on the other (grating + sphere: 20 % of the pixels park a
+# walk, 1.7 % end differently; measured figures in profiles/parity_metrics.json).
+MIN_PIXELS_WITHIN_1E3 = {"cornell": 0.995, "grating_sphere": 0.975, "layered": 0.985, "city": 0.995, "env": 0.995, "analytic": 0.995}
+MIN_PIXELS_WITHIN_1E2 = {"cornell": 0.995, "grating_sphere": 0.975, "layered": 0.985, "city": 0.995, "env": 0.995, "analytic": 0.995}
 
 
 def test_sample_stage_bounce_records(loaded):
@@ -56,7 +60,7 @@ def test_sample_stage_bounce_records(loaded):
         parity.record(f"bounces/{name}/frame{frame}", m)
         assert m["identical_paths"] >= MIN_IDENTICAL_PATHS[name], (name, m)
         assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3, (name, m)
-        assert m["max_contribution_rel"] <= 5e-3, (name, m)
+        assert m["max_contribution_rel"] <= 1e-3, (name, m)  # measured: <= 5.7e-4 (a product of up to nine sampling pdfs)
     s = p.stats()
     assert s["traversalStackOverflows"] == 0 and s["droppedConnections"] == 0
 
@@ -77,7 +81,7 @@ def test_single_frame_rgb_and_guides(loaded):
     assert (gpu["color"][..., 3] == 1).all() and (gpu["color"][..., :3] >= 0).all()
     # per-path radiance is a product of up to ~40 BSDF evaluations each good to 1e-4; MNEE paths amplify rounding further
     assert m["frac_pixels_within_1e-3"] >= MIN_PIXELS_WITHIN_1E3[name], (name, m)
-    assert m["frac_pixels_within_1e-2"] >= 0.995, (name, m)
+    assert m["frac_pixels_within_1e-2"] >= MIN_PIXELS_WITHIN_1E2[name], (name, m)
     # the frame means include the few forked paths (different, equally valid samples): bounded by their share, not by rounding
     assert m["mean_rel_diff"] <= 0.02, (name, m)
     # guide buffers: albedo / view-space normal at the first non-delta vertex

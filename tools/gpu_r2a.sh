@@ -5,7 +5,7 @@ out=gpurun_out
 mkdir -p $out
 V=pltfalcor_b200/build/variants
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/r2a_smi.txt 2>&1
-timeout 1800 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_trace.py::test_closest_hit_bit_exact_10m_triangles > $out/r2a_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/r2a_pytest_gpu.log
+timeout 1800 python -m pytest tests -m gpu -q --deselect tests/test_gpu_trace.py::test_closest_hit_bit_exact_10m_triangles > $out/r2a_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/r2a_pytest_gpu.log
 timeout 600 python -m pytest tests/test_gpu_trace.py::test_closest_hit_bit_exact_10m_triangles -q > $out/r2a_pytest_10m.log 2>&1; echo "pytest exit $?" >> $out/r2a_pytest_10m.log
 for v in base nostage dedup; do timeout 300 python tools/variants.py one $V/$v/libpltpt.so 16; done > $out/r2a_variants.log 2>&1
 for v in base dedup; do for s in grating city; do PLTPT_LIB=$V/$v/libpltpt.so timeout 300 python tools/kernel_times.py $s 1920 1080 4; done; done > $out/r2a_kernel_times.log 2>&1

@@ -34,7 +34,7 @@ p.render_accumulate(cam, 2, 1, frames, w, h, acc)
 torch.cuda.synchronize()
 s = p.stats()
 paths = w * h * frames
-print(json.dumps({"scene": name, "options": opts, "triangles": int(s["triangleCount"]),
+print(json.dumps({"scene": name, "options": opts, "triangles": int(s["triangleCount"]), "bvh_nodes": int(s["bvhNodes"]), "bvh_build_ms": round(s["bvhBuildMs"], 2), "bvh_sah_cost": round(s.get("bvhSahCost", 0.0), 2),
                   "kernels_ms_per_frame": {n: round(s["kernelMs"][n] / frames, 3) for n in L.KERNEL_CLASSES if s["kernelLaunchCount"][n]},
                   "mean_vertices": round(s["totalPathVertices"] / paths, 2), "mnee_iterations_last_frame": int(s["mneeIterations"]), "mnee_walks_last_frame": int(s["mneeWalks"]),
                   "bvh_nodes_per_path": round(s["traversalNodesVisited"] / paths, 1), "bvh_triangles_per_path": round(s["traversalTrianglesTested"] / paths, 1),

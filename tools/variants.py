@@ -16,10 +16,9 @@ sys.path.insert(0, ROOT)
 from pltfalcor_b200 import build as B  # noqa: E402
 
 VDIR = os.path.join(B._HERE, "build", "variants")
-VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments of round 1 and their outcomes are listed in DESIGN.md section 3
+VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their outcomes are listed in DESIGN.md section 3
     "base": {},
-    "nostage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=0"]},                       # k_unwind_step without the cp.async staging of the next item
-    "dedup": {s: ["-DPLT_TRAVERSE_DEDUP=1"] for s in B.SOURCES},                    # traverseBvh() through processNode()
+    "stage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=1"]},                          # k_unwind_step with cp.async staging of the thread's next item
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
