@@ -102,14 +102,17 @@ inline float4x4 mul(const float4x4& A, const float4x4& B) {
 inline float4x4 MuellerFresnel(float2 fs, float2 fp) {
     const float Rp = cnorm2(fp), Rs = cnorm2(fs);
     const float m00 = (Rp + Rs) / 2.f, m01 = (Rp - Rs) / 2.f;
-    const float2 sp = cmul(fs, cconj(fp));
+    // Reference behaviour (Mueller.slang:76-77, found by the comparison with the transpiled reference text, oracle/ref_compare.cpp):
+    // `fs*cconj(fp)` is the COMPONENT-WISE float2 product, not the complex one, so m22 = Re fs Re fp and m23 = -Im fs Im fp
+    // (the physical values would be Re / Im of fs conj(fp)).  Identical for real coefficients (dielectrics); differs for conductors.
+    const float2 sp = fs * cconj(fp);
     const float m22 = sp.x, m23 = sp.y;
     return make4x4(m00, m01, 0, 0, m01, m00, 0, 0, 0, 0, m22, m23, 0, 0, -m23, m22);
 }
 inline float4x4 invOneMinusMuellerFresnel(float2 fs, float2 fp) {
     const float Rp = cnorm2(fp), Rs = cnorm2(fs);
     const float m00 = (Rp + Rs) / 2, m01 = (Rp - Rs) / 2;
-    const float2 sp = cmul(fs, cconj(fp));
+    const float2 sp = fs * cconj(fp);  // component-wise, as in MuellerFresnel above (Mueller.slang:87-88)
     const float m22 = sp.x, m23 = sp.y;
     const float2x2 minor1 = float2x2(1, 0, 0, 1) - float2x2(m00, m01, m01, m00);
     const float2x2 minor2 = float2x2(1, 0, 0, 1) - float2x2(m22, m23, -m23, m22);

@@ -1,0 +1,202 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// ref_shims_post.h — second half of oracle/ref_compare.cpp (included after both implementations and the helpers are visible):
+// spectral-profile lookups, diffraction gratings, differential reflect / refract, and eval / sample / pdf / lambdaPdf of the ten PLT
+// BSDFs through their IMaterialInstance wrappers -- oracle (orc::) against the transpiled reference text (ref::).
+#pragma once
+
+namespace {
+ref::ShadingData R(const orc::ShadingData& s) {
+    ref::ShadingData o;
+    o.posW = R(s.posW); o.V = R(s.V); o.N = R(s.N); o.T = R(s.T); o.B = R(s.B); o.faceN = R(s.faceN); o.uv = R(s.uv); o.frontFacing = s.frontFacing; o.materialID = s.materialID;
+    return o;
+}
+ref::PLTBeam R(const orc::PLTBeam& b) {
+    ref::PLTBeam o;
+    o.L = R(b.L); o.L1 = R(b.L1); o.L2 = R(b.L2); o.L3 = R(b.L3); o.wavelengths = R(b.wavelengths); o.spectralPDFs = R(b.spectralPDFs); o.hwss_comps = b.hwss_comps;
+    o.Theta.D = R(b.Theta.D); o.Theta.r_m = b.Theta.r_m; o.posW = R(b.posW); o.r = R(b.r); o.t = R(b.t); o.distant = b.distant;
+    return o;
+}
+ref::float3pdv R(const orc::float3pdv& v) { ref::float3pdv o; o.v = R(v.v); o.ddu = R(v.ddu); o.ddv = R(v.ddv); return o; }
+void addK(Cmp& c, const orc::float3kpdv& a, const ref::float3kpdv& b) { c.add(a.v, b.v); c.add(a.ddu, b.ddu); c.add(a.ddv, b.ddv); c.add(a.ddl, b.ddl); }
+
+orc::ShadingData randomShadingData(Rnd& r) {
+    orc::ShadingData sd;
+    sd.N = r.dir(); sd.T = orc::perp_stark(sd.N); sd.B = orc::cross(sd.N, sd.T);
+    sd.posW = r.f3(-1.f, 1.f); sd.faceN = sd.N; sd.uv = r.f2(0.f, 1.f);
+    orc::float3 v = r.dirUp();
+    if (v.z < 0.02f) v = orc::normalize(orc::float3(v.x, v.y, 0.02f));
+    sd.V = sd.fromLocal(v);
+    return sd;
+}
+// a lobe word the wrappers accept for the material (the sample() of the material itself provides realistic ones)
+const uint32_t kLobeChoices[] = {orc::L_DiffuseReflection, orc::L_ScatterReflection, orc::L_DeltaReflection, orc::L_ScatterTransmission, orc::L_DeltaTransmission,
+                                 orc::L_DispersiveDeltaTransmission, orc::L_NonDelta, orc::L_Delta, orc::L_All};
+
+// One material of each kind with random parameters, set field by field on both sides (the *Material.slang loaders that unpack the
+// 128-byte blob need the texture system and are outside this comparison; tests/test_ingest.py covers the packing).
+struct Pair {
+    orc::MaterialInstance o;
+    int kind;
+    ref::PLTDiffuseBSDF diffuse; ref::PLTConductorBSDF conductor; ref::PLTDielectricBSDF dielectric; ref::PLTOpaqueDielectricBSDF opaque; ref::PLTThinDielectricBSDF thin;
+    ref::PLTCoatedConductorBSDF coatedC; ref::PLTCoatedOpaqueDielectricBSDF coatedD; ref::PLTDiffractionGratedConductorBSDF gratedC; ref::PLTDiffractionGratedOpaqueDielectricBSDF gratedD;
+    ref::PLTMultiLayeredStackBSDF stack;
+};
+const char* kKindNames[10] = {"PLTDiffuseBSDF", "PLTConductorBSDF", "PLTDielectricBSDF", "PLTOpaqueDielectricBSDF", "PLTThinDielectricBSDF", "PLTCoatedConductorBSDF",
+                              "PLTCoatedOpaqueDielectricBSDF", "PLTDiffractionGratedConductorBSDF", "PLTDiffractionGratedOpaqueDielectricBSDF", "PLTMultiLayeredStackBSDF"};
+void makePair(Pair& p, int kind, Rnd& r, const orc::ProfileTable* prof, const orc::ShadingData& sd) {
+    p.kind = kind;
+    p.o = orc::MaterialInstance();
+    p.o.prof = prof;
+    const orc::float3 col = r.f3(0.05f, 1.f);
+    const float rough = r.u() < 0.15f ? 0.f : r.range(0.01f, 0.6f), gamma = r.range(1.5f, 4.f), extEta = r.u() < .5f ? 1.f : r.range(1.f, 1.4f);
+    const uint32_t n = uint32_t(r.u() * 1.999f) * 2u, k = n + 1u;  // profile ids (n, k) of one of the two tabulated conductors
+    switch (kind) {
+        case 0: p.o.type = PLTPT_MATERIAL_DIFFUSE; p.o.diffuse.albedo = col; p.diffuse.bxdf.albedo = R(col); break;
+        case 1: p.o.type = PLTPT_MATERIAL_CONDUCTOR;
+            p.o.conductor.specular = col; p.o.conductor.gfs = orc::FractalSurface(rough, gamma); p.o.conductor.etaN = n; p.o.conductor.etaK = k; p.o.conductor.extEta = extEta; p.o.conductor.prof = prof;
+            p.conductor.bxdf.specular = R(col); p.conductor.bxdf.gfs = ref::FractalSurface(rough, gamma); p.conductor.bxdf.etaN = n; p.conductor.bxdf.etaK = k; p.conductor.bxdf.extEta = extEta; break;
+        case 2: { p.o.type = PLTPT_MATERIAL_DIELECTRIC;
+            const orc::float3 tr = r.f3(0.3f, 1.f); const float etaInt = r.range(1.2f, 2.2f), B = r.u() < .5f ? 0.f : r.range(0.f, 0.02f);
+            p.o.dielectric.specular = col; p.o.dielectric.transmission = tr; p.o.dielectric.gfs = orc::GaussianSurface(rough); p.o.dielectric.etaInt = etaInt; p.o.dielectric.etaExt = extEta; p.o.dielectric.dispersionB = B;
+            p.dielectric.bxdf.specular = R(col); p.dielectric.bxdf.transmission = R(tr); p.dielectric.bxdf.gfs = ref::GaussianSurface(rough); p.dielectric.bxdf.etaInt = etaInt; p.dielectric.bxdf.etaExt = extEta; p.dielectric.bxdf.dispersionB = B; break; }
+        case 3: p.o.type = PLTPT_MATERIAL_OPAQUE_DIELECTRIC; p.o.opaque.albedo = col; p.o.opaque.gfs = orc::FractalSurface(rough);
+            p.opaque.bxdf.albedo = R(col); p.opaque.bxdf.gfs = ref::FractalSurface(rough); break;
+        case 4: { p.o.type = PLTPT_MATERIAL_THIN_DIELECTRIC;
+            const orc::float2 oa = r.f2(-.5f, .5f); const float eta = r.range(1.2f, 1.9f), tau = r.range(0.01f, 1.f), bir = r.u() < .3f ? 0.f : r.range(0.f, 0.2f);
+            p.o.thin.opticAxis_xy = oa; p.o.thin.etaAvg = eta; p.o.thin.tau = tau; p.o.thin.birefringence = bir;
+            p.thin.bxdf.opticAxis_xy = R(oa); p.thin.bxdf.etaAvg = eta; p.thin.bxdf.tau = tau; p.thin.bxdf.birefringence = bir; break; }
+        case 5: case 6: { const bool cond = kind == 5; p.o.type = cond ? PLTPT_MATERIAL_COATED_CONDUCTOR : PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC;
+            const float coat = r.range(1.2f, 1.8f), tau = r.u() < .2f ? r.range(0.f, .05f) : r.range(0.05f, 5.f);
+            p.o.coated.conductor = cond; p.o.coated.specular = col; p.o.coated.gfs = orc::FractalSurface(rough); p.o.coated.etaN = n; p.o.coated.etaK = k; p.o.coated.extEta = extEta; p.o.coated.coatIOR = coat; p.o.coated.tau = tau; p.o.coated.prof = prof;
+            if (cond) { p.coatedC.bxdf.specular = R(col); p.coatedC.bxdf.gfs = ref::FractalSurface(rough); p.coatedC.bxdf.etaN = n; p.coatedC.bxdf.etaK = k; p.coatedC.bxdf.extEta = extEta; p.coatedC.bxdf.coatIOR = coat; p.coatedC.bxdf.tau = tau; }
+            else { p.coatedD.bxdf.albedo = R(col); p.coatedD.bxdf.gfs = ref::FractalSurface(rough); p.coatedD.bxdf.extEta = extEta; p.coatedD.bxdf.coatIOR = coat; p.coatedD.bxdf.tau = tau; }
+            break; }
+        case 7: case 8: { const bool cond = kind == 7; p.o.type = cond ? PLTPT_MATERIAL_GRATED_CONDUCTOR : PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC;
+            const float dir = r.range(-3.f, 3.f), q = r.range(0.02f, 0.5f), mult = r.range(.5f, 1.5f);
+            const orc::float2 ip(1.f / r.range(1.f, 6.f), r.u() < .5f ? 0.f : 1.f / r.range(1.f, 6.f));
+            const uint32_t lobes = 1u + uint32_t(r.u() * 7.99f), gtype = uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u);
+            p.o.grated.conductor = cond;
+            p.o.grated.baseC.specular = col; p.o.grated.baseC.gfs = orc::FractalSurface(rough); p.o.grated.baseC.etaN = n; p.o.grated.baseC.etaK = k; p.o.grated.baseC.extEta = extEta; p.o.grated.baseC.prof = prof;
+            p.o.grated.baseD.albedo = col; p.o.grated.baseD.gfs = orc::FractalSurface(rough);
+            p.o.grated.grating = orc::DiffractionGrating(dir, sd, ip, q, lobes, gtype, mult);
+            ref::ShadingData rsd = R(sd);
+            if (cond) { p.gratedC.bxdf.base.specular = R(col); p.gratedC.bxdf.base.gfs = ref::FractalSurface(rough); p.gratedC.bxdf.base.etaN = n; p.gratedC.bxdf.base.etaK = k; p.gratedC.bxdf.base.extEta = extEta;
+                        p.gratedC.bxdf.grating = ref::DiffractionGrating(dir, rsd, R(ip), q, lobes, gtype, mult); }
+            else { p.gratedD.bxdf.base.albedo = R(col); p.gratedD.bxdf.base.gfs = ref::FractalSurface(rough); p.gratedD.bxdf.grating = ref::DiffractionGrating(dir, rsd, R(ip), q, lobes, gtype, mult); }
+            break; }
+        default: { p.o.type = PLTPT_MATERIAL_MULTILAYERED_STACK;
+            const orc::float2 ior(r.range(1.2f, 1.6f), r.range(1.8f, 2.6f)), th(r.range(0.05f, 0.3f), r.range(0.05f, 0.3f)); const uint32_t layers = 1u + uint32_t(r.u() * 20.f);
+            p.o.stack.albedo = col; p.o.stack.extEta = extEta; p.o.stack.ior = ior; p.o.stack.thickness = th; p.o.stack.layers = layers;
+            p.stack.bxdf.albedo = R(col); p.stack.bxdf.extEta = extEta; p.stack.bxdf.ior = R(ior); p.stack.bxdf.thickness = R(th); p.stack.bxdf.layers = layers; break; }
+    }
+}
+#define REF_DISPATCH(p, CALL)                                                                                                           \
+    switch ((p).kind) { case 0: (p).diffuse.CALL; break; case 1: (p).conductor.CALL; break; case 2: (p).dielectric.CALL; break; case 3: (p).opaque.CALL; break; case 4: (p).thin.CALL; break; \
+                        case 5: (p).coatedC.CALL; break; case 6: (p).coatedD.CALL; break; case 7: (p).gratedC.CALL; break; case 8: (p).gratedD.CALL; break; default: (p).stack.CALL; break; }
+#define REF_DISPATCH_R(p, OUT, CALL)                                                                                                    \
+    switch ((p).kind) { case 0: OUT = (p).diffuse.CALL; break; case 1: OUT = (p).conductor.CALL; break; case 2: OUT = (p).dielectric.CALL; break; case 3: OUT = (p).opaque.CALL; break; case 4: OUT = (p).thin.CALL; break; \
+                        case 5: OUT = (p).coatedC.CALL; break; case 6: OUT = (p).coatedD.CALL; break; case 7: OUT = (p).gratedC.CALL; break; case 8: OUT = (p).gratedD.CALL; break; default: OUT = (p).stack.CALL; break; }
+}  // namespace
+
+static void ref_compare_more(int N, Rnd& r) {
+    // ---- spectral profiles: two tabulated "conductors" (n, k tables, no icdf) and one emitter (pdf + icdf), random but well formed
+    static PltptSpectralProfile prof[5];
+    static ref::SpectralProfile rprof[5];
+    for (int i = 0; i < 5; ++i) {
+        PltptSpectralProfile& p = prof[i];
+        p.bins = i == 4 ? 128u : 20u + uint32_t(r.u() * 100.f);
+        p.minWavelength = i == 4 ? 380.f : r.range(300.f, 400.f); p.maxWavelength = i == 4 ? 720.f : r.range(700.f, 900.f);
+        p.intensity = i == 4 ? r.range(.5f, 5.f) : 1.f;
+        float acc = 0.f;
+        for (uint32_t b = 0; b < 128; ++b) { p.pdf[b] = b < p.bins ? (i % 2 == 0 ? r.range(0.1f, 1.6f) : r.range(1.5f, 6.f)) : 0.f; acc += p.pdf[b]; }
+        float c = 0.f;
+        for (uint32_t b = 0; b < 128; ++b) { c += p.pdf[b] / acc; p.icdf[b] = b < p.bins ? std::fmin(c, 1.f) : 1.f; }
+        p.rgb[0] = p.rgb[1] = p.rgb[2] = 1.f;
+        ref::SpectralProfile& q = rprof[i];
+        q.rgb = ref::float3(1.f); q.intensity = p.intensity; q.bins = p.bins; q.minWavelength = p.minWavelength; q.maxWavelength = p.maxWavelength;
+        for (int b = 0; b < 128; ++b) { q.pdf[b] = p.pdf[b]; q.icdf[b] = p.icdf[b]; }
+    }
+    static orc::ProfileTable table;
+    table.profiles = prof; table.count = 5;
+    ref::gScene.spectralProfiles = rprof;
+    for (int i = 0; i < N; ++i) {
+        const uint32_t id = uint32_t(r.u() * 4.999f);
+        const float l = r.range(350.f, 760.f);
+        const orc::float4 wl = r.wavelengths();
+        { Cmp c("Scene.evalSpectrum"); c.add(table.evalSpectrum(id, l), ref::gScene.evalSpectrum(id, l)); c.add(table.evalSpectrum(id, wl), ref::gScene.evalSpectrum(id, R(wl)));
+          c.add(table.evalSpectrum(PLTPT_NO_SPECTRAL_PROFILE, l), ref::gScene.evalSpectrum(ref::BasicMaterialData::no_spectral_profile, l)); }
+        { Cmp c("Scene.sampleSpectrum"); const bool imp = r.u() < .5f; orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 3u); RefSG g1{g0};
+          orc::float4 w0; ref::float4 w1; const float hero = r.range(380.f, 720.f);
+          c.add(table.sampleSpectrum(4u, hero, g0, imp, w0), ref::gScene.sampleSpectrum(4u, hero, g1, imp, w1)); c.add(w0, w1); }
+        { Cmp c("SpectrumSampler.hwssWavelengths"); const float hero = r.range(380.f, 720.f); c.add(orc::SpectrumSampler::hwssWavelengths(hero), ref::SpectrumSampler::hwssWavelengths(hero));
+          const float u = r.u(); c.add(orc::SpectrumSampler::sampleOne(u), ref::SpectrumSampler::sampleOne(u)); }
+    }
+    // ---- DifferentialShadingGeometry.slang: reflect / refract derivatives
+    for (int i = 0; i < N; ++i) {
+        Cmp c("DifferentialShadingGeometry.reflect_refractDerivatives");
+        orc::float3pdv wi, n;
+        n.v = r.dir(); n.ddu = r.f3(-1.f, 1.f); n.ddv = r.f3(-1.f, 1.f);
+        wi.v = r.dir(); wi.ddu = r.f3(-1.f, 1.f); wi.ddv = r.f3(-1.f, 1.f);
+        addK(c, orc::reflectDerivatives(wi, n), ref::reflectDerivatives(R(wi), R(n)));
+        const float eta = r.range(1.1f, 2.f), de = r.range(-1e-3f, 1e-3f);
+        addK(c, orc::refractDerivatives(wi, n, eta, de, -de), ref::refractDerivatives(R(wi), R(n), eta, de, -de));
+    }
+    // ---- DiffractionGrating.slang
+    for (int i = 0; i < N; ++i) {
+        const orc::ShadingData sd = randomShadingData(r);
+        ref::ShadingData rsd = R(sd);
+        const float dir = r.range(-3.f, 3.f), q = r.range(0.02f, 0.5f), mult = r.range(.5f, 1.5f);
+        const orc::float2 ip(1.f / r.range(1.f, 6.f), r.u() < .5f ? 0.f : 1.f / r.range(1.f, 6.f));
+        const uint32_t lobes = 1u + uint32_t(r.u() * 7.99f), gtype = uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u);
+        const orc::DiffractionGrating a(dir, sd, ip, q, lobes, gtype, mult); ref::DiffractionGrating b(dir, rsd, R(ip), q, lobes, gtype, mult);
+        const orc::float3 wi = r.dirUp(), hint = r.dirUp();
+        const orc::float4 k = r.ks();
+        const float lambda = r.range(0.38f, 0.72f);
+        { Cmp c("DiffractionGrating.setup_alpha"); c.add(a.gratingX, b.gratingX); c.add(a.alpha(wi, k.x), b.alpha(R(wi), k.x)); c.add(a.alpha(wi, k), b.alpha(R(wi), R(k))); c.add(a.is1DGrating(), b.is1DGrating());
+          const orc::ShadingData g0 = a.localGratingShadingFrame(sd); ref::ShadingData g1 = b.localGratingShadingFrame(rsd); c.add(g0.T, g1.T); c.add(g0.B, g1.B); c.add(g0.N, g1.N); }
+        orc::int2 lb; lb.x = int(r.range(-7.99f, 7.99f)); lb.y = ip.y == 0.f ? 0 : int(r.range(-3.99f, 3.99f));
+        const ref::int2 rlb(lb.x, lb.y);
+        { Cmp c("DiffractionGrating.lobeIntensity_diffract"); c.add(a.lobeIntensity(lb, wi, lambda), b.lobeIntensity(rlb, R(wi), lambda)); c.add(a.diffract(wi, lb, lambda), b.diffract(R(wi), rlb, lambda)); }
+        { Cmp c("DiffractionGrating.closestLobeHint"); const float al = r.u() < .1f ? 0.f : (r.u() < .1f ? 1.f : r.u()); const orc::int2 h0 = a.closestLobeHint(wi, hint, al, lambda); const ref::int2 h1 = b.closestLobeHint(R(wi), R(hint), al, lambda);
+          c.add(h0.x, h1.x); c.add(h0.y, h1.y); }
+        { Cmp c("DiffractionGrating.sampleLobe"); orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 5u); RefSG g1{g0}; orc::float2 p0; ref::float2 p1; ref::float3 woUnused;
+          const orc::int2 s0 = a.sampleLobe(wi, p0, lambda, g0); const ref::int2 s1 = b.sampleLobe(R(wi), woUnused, p1, lambda, g1); c.add(s0.x, s1.x); c.add(s0.y, s1.y); c.add(p0, p1); }
+    }
+    // ---- the ten BSDFs through their IMaterialInstance wrappers
+    for (int i = 0; i < N; ++i) {
+        const int kind = i % 10;
+        const orc::ShadingData sd = randomShadingData(r);
+        ref::ShadingData rsd = R(sd);
+        static Pair p;
+        makePair(p, kind, r, &table, sd);
+        const float wavelength = r.range(380.f, 720.f);
+        // sample(): the generator streams must stay in step as well
+        orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 11u); RefSG g1{g0};
+        orc::BSDFSample s0; ref::BSDFSample s1;
+        // The grated BSDFs leave the `out float pdf` of their sample() unwritten when the lobe mask excludes either the delta or the scatter
+        // lobes and no hint is given (PLTDiffractionGratedConductorBSDF.slang:132-141) and then multiply it -- undefined in the reference,
+        // never reached by the integrator (its masks are All, or Delta with a hint).  The oracle defines the start value as 1; same here.
+        s1.pdf = 1.f;
+        const uint32_t mask = r.u() < .7f ? uint32_t(orc::L_All) : kLobeChoices[uint32_t(r.u() * 8.99f)];
+        orc::float3 hint = r.u() < .5f ? orc::float3(0.f) : r.dir();
+        const bool v0 = p.o.sample(sd, g0, s0, wavelength, mask, hint);
+        bool v1 = false;
+        REF_DISPATCH_R(p, v1, sample(rsd, g1, s1, wavelength, mask, R(hint)));
+        { Cmp c(std::string(kKindNames[kind]) + ".sample"); c.add(v0, v1); c.add(g0.next(), g1.next());
+          if (v0 && v1) { c.add(s0.wo, s1.wo); c.add(s0.pdf, s1.pdf); c.add(s0.lobe, s1.lobe); c.add(s0.weight, s1.weight); } }
+        // eval(): a sampled direction with its own lobe (the case the integrator evaluates), or a random direction and lobe
+        const bool useSampled = v0 && v1 && r.u() < .6f;
+        const orc::float3 toEye = useSampled ? s0.wo : sd.fromLocal(r.dir());
+        const uint32_t lobe = useSampled ? s0.lobe : kLobeChoices[uint32_t(r.u() * 8.99f)];
+        ref::PLTBeam rb;
+        orc::PLTBeam b = randomBeam(r, rb);
+        b.r = -sd.V; b.t = orc::perp_stark(b.r); b.propagate(sd.posW);   // arrives along -V, like forwardUnwindStep
+        if (r.u() < .2f) b.hwss_comps = 1;
+        rb = R(b);
+        { Cmp c(std::string(kKindNames[kind]) + ".lambdaPdf"); ref::float4 l1; REF_DISPATCH_R(p, l1, lambdaPdf(rsd, R(toEye), lobe, rb, rb.wavelengths)); c.add(p.o.lambdaPdf(sd, toEye, lobe, b, b.wavelengths), l1); }
+        p.o.eval(sd, toEye, lobe, b);
+        REF_DISPATCH(p, eval(rsd, R(toEye), lobe, rb));
+        { Cmp c(std::string(kKindNames[kind]) + ".eval"); c.add(b, rb); }
+        { Cmp c(std::string(kKindNames[kind]) + ".pdf"); float q1 = 0.f; const orc::float3 toLight = sd.fromLocal(r.dirUp()); REF_DISPATCH_R(p, q1, pdf(rsd, R(toLight), wavelength)); c.add(p.o.pdf(sd, toLight, wavelength), q1); }
+    }
+}

@@ -62,4 +62,16 @@ struct SpectralProfile {  // Scene/Material/BasicMaterialData.slang:43-54
     float icdf[128];
 };
 
+struct BasicMaterialData { static constexpr uint no_spectral_profile = uint(-1); };  // Scene/Material/BasicMaterialData.slang:65
+typedef uint uint32_t_;
+// Rendering/Materials/IMaterialInstance.slang:53-88 (the reference's `property` accessors are not used by the BSDF code)
+struct BSDFProperties {
+    uint emissionSpectralId = BasicMaterialData::no_spectral_profile;
+    float3 emissionRGB = .0f;
+    float3 albedo = .0f;
+    float roughness = .0f;
+    uint flags = 0;
+    enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
+};
+
 }  // namespace ref

@@ -15,7 +15,6 @@
 
 #include "plt_integrator.h"   // the oracle: orc::
 #include "_ref/ref_gen.h"     // the transpiled reference: ref::
-#include "ref/ref_shims_post.h"
 
 namespace {
 struct Stat { uint64_t n = 0, nonfiniteMismatch = 0; double maxUlp = 0, maxRel = 0, maxAbs = 0; };
@@ -93,7 +92,10 @@ orc::PLTBeam randomBeam(Rnd& r, ref::PLTBeam& rb) {
     rb.L1 = R(b.L1); rb.L2 = R(b.L2); rb.L3 = R(b.L3);
     return b;
 }
+// the reference's generic code takes any generator with next(); wrapped so that argument-dependent lookup stays inside namespace ref
+struct RefSG { orc::SampleGenerator g; ref::uint next() { return g.next(); } };
 }  // namespace
+#include "ref/ref_shims_post.h"
 
 int main(int argc, char** argv) {
     const int N = argc > 1 ? std::atoi(argv[1]) : 100000;
@@ -190,7 +192,7 @@ int main(int argc, char** argv) {
             if (rough > 0.f) {
                 Cmp c("FractalSurface.eval_pdf_sample");
                 c.add(a.eval(k.x, h), b.eval(k.x, R(h))); c.add(a.pdf(wi, wo, k.x), b.pdf(R(wi), R(wo), k.x));
-                orc::SampleGenerator g0(orc::uint2{uint32_t(i & 0xffff), uint32_t(i >> 16)}, 7u), g1 = g0;
+                orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 7u); RefSG g1{g0};
                 float p0, p1;
                 c.add(a.sample(wi, g0, k.z, p0), b.sample(R(wi), g1, k.z, p1)); c.add(p0, p1); c.add(g0.next(), g1.next());
             }
@@ -204,7 +206,7 @@ int main(int argc, char** argv) {
                 ref::PLTBeam rb; const orc::PLTBeam beam = randomBeam(r, rb);
                 c.add(a.eval(k.x, beam.invTheta(1.f), beam.Q(), h), b.eval(k.x, rb.invTheta(1.f), rb.Q(), R(h)));
                 c.add(a.pdf(wi, wo, k.x), b.pdf(R(wi), R(wo), k.x));
-                orc::SampleGenerator g0(orc::uint2{uint32_t(i & 0xffff), uint32_t(i >> 16)}, 9u), g1 = g0;
+                orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 9u); RefSG g1{g0};
                 float p0, p1;
                 c.add(a.sample(wi, g0, k.w, p0), b.sample(R(wi), g1, k.w, p1)); c.add(p0, p1);
             }

@@ -24,6 +24,7 @@ Rewrite rules (all mechanical; each is a regular expression or a brace-matched b
   R9  `A.B` static access -> `A::B` for the names in STATIC_SCOPES; `struct X : IFoo` loses the interface list
   R10 `static const float` -> `static constexpr float`; struct-typed `const` locals / parameters lose `const` (Slang methods are
       callable on them; C++ would need const-qualified methods), structs get their trailing `;`
+  R12 `let x = e` -> `auto x = e`
   R11 the handful of vector-condition ternaries (`c ? a : b` with bool2 `c`, DiffractionGrating.slang only) -> select(c, a, b); listed in PATCHES
       with the exact source text they replace -- the script fails if a patch no longer matches.
 """
@@ -52,16 +53,49 @@ SOURCES = [
     ("Rendering/Materials/PLT/FractalSurface.slang", None),
     ("Rendering/Materials/PLT/GaussianSurface.slang", None),
     ("Rendering/Materials/PLT/Birefringence.slang", None),
+    ("Utils/Color/SpectrumSampler.slang", None),
+    ("Scene/Scene.slang", ("members", "Scene", ["evalSpectrumRGB", "evalSpectrum", "sampleSpectrum"], "SpectralProfile* spectralProfiles = nullptr;")),
+    ("Rendering/Materials/BSDFSample.slang", None),
+    ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives"]),
+    ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
+    ("Rendering/Materials/PLT/DiffractionGrating.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffuseBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTConductorBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTOpaqueDielectricBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTDielectricBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTThinDielectricBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTCoatedConductorBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTCoatedOpaqueDielectricBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffractionGratedConductorBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTMultiLayeredStackBSDF.slang", None),
 ]
 
-STATIC_SCOPES = ["SpectrumUtils", "Birefringence"]
-PROPERTY_USES = [r"gfs\.q", r"gfs\.roughness", r"surface\.q", r"surface\.roughness"]
+STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
+# property reads outside the declaring struct: `roughness` is a property of both surface types, `q` of FractalSurface only (a plain
+# field of GaussianSurface) -- decided per file by the surface type the file's BxDF declares (`typedef ... SurfaceType`)
+PROPERTY_USES = [r"gfs\.roughness"]
+PROPERTY_USES_FRACTAL = [r"gfs\.q"]
 # exact-text patches: (file suffix, old, new, why)
 PATCHES = [
     ("Utils/Math/MathHelpers.slang", "float1 sqr(float1 v) { return v*v; }", "", "float1 (1-vectors) are not modelled"),
     ("Utils/Color/SpectrumUtils.slang", "static const float3 rgbWavelengths = float3(630,532,467);", "static inline const float3 rgbWavelengths = float3(630,532,467);",
      "C++ needs `inline` for a class-type static data member defined in the class"),
     ("Utils/Color/ColorHelpers.slang", "static const float3x3 M =\n    {", "static const float3x3 M =\n    float3x3{", "list-initialisation of the matrix type"),
+    # R11: vector-condition ternaries -> select()
+    ("Utils/Color/SpectrumSampler.slang", "hwss -= hwss > hwss_t(maxWavelength) ? hwss_t(spanWavelength) : hwss_t(.0f);",
+     "hwss -= select(hwss > hwss_t(maxWavelength), hwss_t(spanWavelength), hwss_t(.0f));", "R11"),
+    ("Scene/Scene.slang", "return zeros ? hwss_t(.0f) : sp.intensity * lerp(a, b, w);", "return select(zeros, hwss_t(.0f), sp.intensity * lerp(a, b, w));", "R11"),
+    ("PLT/DiffractionGrating.slang", "const float2 sini = li2 > FLT_EPSILON ?  wiLocal.xy / sqrt(li2) : .0f;", "const float2 sini = select(li2 > FLT_EPSILON,  wiLocal.xy / sqrt(li2), .0f);", "R11"),
+    ("PLT/DiffractionGrating.slang", "const float2 sino = lo2 > FLT_EPSILON ? -woHint.xy  / sqrt(lo2) : .0f;", "const float2 sino = select(lo2 > FLT_EPSILON, -woHint.xy  / sqrt(lo2), .0f);", "R11"),
+    ("PLT/DiffractionGrating.slang", "lobe = alpha==.0f && lobe==0 ? sign(l) : lobe;", "lobe = int2(select(bool2(alpha==.0f) && lobe==0, sign(l), lobe));", "R11 (+ the implicit float2 -> int2 conversion of the assignment)"),
+    ("PLT/DiffractionGrating.slang", "const bool2 select = abs(rand)<float2(cdf) && lobe==0;\n            pdf = select ? float2(p) : pdf;\n            lobe = select ? int2(l+1) : lobe;",
+     "const bool2 sel = abs(rand)<float2(cdf) && lobe==0;\n            pdf = select(sel, float2(p), pdf);\n            lobe = select(sel, int2(l+1), lobe);", "R11 (the local variable is called `select` in the reference)"),
+    ("PLT/DiffractionGrating.slang", "lobe = rand<.0f ? -lobe : lobe;", "lobe = select(rand<.0f, -lobe, lobe);", "R11"),
+    ("PLT/DiffractionGrating.slang", "const float2 sini = p>FLT_EPSILON ? wi.xy/p : .0f;", "const float2 sini = select(p>FLT_EPSILON, wi.xy/p, .0f);", "R11"),
+    ("PLT/DiffractionGrating.slang", "const float2 invp = p>FLT_EPSILON ? 1.f/p : .0f;", "const float2 invp = select(p>FLT_EPSILON, 1.f/p, .0f);", "R11"),
+    ("PLT/PLTDiffractionGratedConductorBSDF.slang", "const int2 sign = lobe<0 ? int2(0) : int2(1);", "const int2 sign = select(lobe<0, int2(0), int2(1));", "R11"),
+    ("PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", "const int2 sign = lobe<0 ? int2(0) : int2(1);", "const int2 sign = select(lobe<0, int2(0), int2(1));", "R11"),
 ]
 
 
@@ -109,6 +143,27 @@ def extract_items(s, names):
     if missing:
         raise SystemExit(f"items not found in the reference source: {missing}")
     return "\n".join("\n".join(found[n]) for n in names)
+
+
+def extract_members(s, names):
+    """Member functions (indented, inside a struct) with the given names, all overloads, in source order."""
+    out = []
+    pat = re.compile(r"^[ \t]+(?:static\s+)?[\w<>,:]+\s+(\w+)\s*(?:<[^>]*>)?\s*\([^;{]*\)\s*\{", re.M)
+    pos = 0
+    while True:
+        m = pat.search(s, pos)
+        if not m:
+            break
+        end = match_brace(s, m.end() - 1)
+        if m.group(1) in names:
+            out.append(s[m.start():end])
+            pos = end
+        else:
+            pos = m.end()
+    found = {re.search(r"(\w+)\s*(?:<[^>]*>)?\s*\(", o).group(1) for o in out}
+    if set(names) - found:
+        raise SystemExit(f"members not found: {set(names) - found}")
+    return "\n".join(out)
 
 
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
@@ -224,6 +279,8 @@ def transpile(path, s, struct_names):
     s = re.sub(r"^\s*(__exported\s+)?import\s+[\w.]+\s*;\s*$", "", s, flags=re.M)
     s = re.sub(r'^\s*#include\s+"[^"]*"\s*$', "", s, flags=re.M)
     s = re.sub(r"^\s*#pragma once\s*$", "", s, flags=re.M)
+    s = re.sub(r"^\s*(BEGIN|END)_NAMESPACE_FALCOR\s*$", "", s, flags=re.M)
+    s = re.sub(r"\blet\s+", "auto ", s)   # R12: `let x = ...` -> `auto x = ...`
     # R4
     s = re.sub(r"\[mutating\]\s*", "", s)
     s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
@@ -247,7 +304,7 @@ def transpile(path, s, struct_names):
     s = re.sub(r"\brgb\.b\b", "rgb.z", s)
     s = re.sub(r"\.([xyzw]{2,4})\b(?!\s*\()", r".\1()", s)
     s = per_function(s, scalar_swizzles)
-    for pu in PROPERTY_USES:
+    for pu in PROPERTY_USES + (PROPERTY_USES_FRACTAL if re.search(r"typedef\s+FractalSurface\s+SurfaceType", s) else []):
         s = re.sub(rf"\b({pu})\b(?!\s*\()", r"\1()", s)
     # R10
     s = re.sub(r"\bstatic\s+const\s+(float|int|uint|bool)\b", r"static constexpr \1", s)
@@ -267,11 +324,11 @@ def main():
         if what == "defines":
             texts.append((path, rule_defines(raw), True))
             continue
-        if what is not None:
-            for suffix, old, new, _why in PATCHES:  # patches address the original text: apply before extraction
-                pass
-            raw_nc = raw
-            raw = extract_items(strip_comments_keep_lines(raw_nc) if False else raw_nc, what)
+        if isinstance(what, tuple) and what[0] == "members":
+            _, sname, names, fields = what
+            raw = f"struct {sname}\n{{\n    {fields}\n" + extract_members(raw, names) + "\n};\nstatic " + sname + " g" + sname + ";\n"
+        elif what is not None:
+            raw = extract_items(raw, what)
         texts.append((path, raw, False))
     struct_names = set()
     for _p, t, _d in texts:

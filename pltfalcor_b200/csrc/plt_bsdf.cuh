@@ -135,10 +135,12 @@ PLT_D float evalFresnelDielectric(float eta, float cosThetaI) { float c; return 
 // ---- Mueller algebra in block form: Materials/PLT/Mueller.slang:34-144 ----------------------
 // {a,b,c,d} == [[a,b,0,0],[b,a,0,0],[0,0,c,d],[0,0,-d,c]]; closed under products and sums.
 struct FM { float a, b, c, d; };
+// Reference behaviour (Mueller.slang:76-77): `fs*cconj(fp)` there is the component-wise float2 product, not the complex one, so the
+// lower block is c = Re fs Re fp, d = -Im fs Im fp (equal to Re / Im of fs conj(fp) only for real coefficients, i.e. dielectrics).
+// Found by compiling the reference's own text for the CPU (oracle/ref_compare.cpp); reproduced as it is.
 PLT_D FM fmFresnel(float2 fs, float2 fp) {
     const float Rp = cnorm2(fp), Rs = cnorm2(fs);
-    const float2 sp = cmul(fs, cconj(fp));
-    return {(Rp + Rs) / 2.f, (Rp - Rs) / 2.f, sp.x, sp.y};
+    return {(Rp + Rs) / 2.f, (Rp - Rs) / 2.f, fs.x * fp.x, fs.y * -fp.y};
 }
 PLT_D FM fmMul(FM A, FM B) { return {A.a * B.a + A.b * B.b, A.a * B.b + A.b * B.a, A.c * B.c - A.d * B.d, A.c * B.d + A.d * B.c}; }
 PLT_D FM fmAdd(FM A, FM B) { return {A.a + B.a, A.b + B.b, A.c + B.c, A.d + B.d}; }

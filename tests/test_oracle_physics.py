@@ -141,7 +141,9 @@ def test_gold_mirror_follows_the_complex_fresnel_equations(osc):
     root = np.sqrt(N * N - si2)
     rs = (ci - root) / (ci + root)
     rp = (N * N * ci - root) / (N * N * ci + root)
-    Rs, Rp, cross = np.abs(rs) ** 2, np.abs(rp) ** 2, rs * np.conj(rp)
+    # lower 2x2 block: the reference multiplies rs and conj(rp) COMPONENT-WISE (`fs*cconj(fp)` on float2, Mueller.slang:76-77; pinned by
+    # tests/test_oracle_ref.py), so the block holds Re rs Re rp and -Im rs Im rp instead of Re / Im of rs conj(rp); reproduced as it is
+    Rs, Rp, cross = np.abs(rs) ** 2, np.abs(rp) ** 2, rs.real * rp.real - 1j * (rs.imag * rp.imag)
     tol = dict(rel=4e-3, abs_=3.5e-3)   # worst cases sit on gold's absorption edge (500-540 nm) between table knots; the median error is 1e-4
     assert _close(M[:, 0, 0], (Rs + Rp) / 2, **tol)
     assert _close(np.hypot(M[:, 0, 1], M[:, 0, 2]), np.abs(Rs - Rp) / 2, **tol)

@@ -1,0 +1,79 @@
+"""Pins the oracle to the reference's own shader text (SURVEY §8c "oracle/_ref").
+
+oracle/ref_transpile.py rewrites the reference's PLT Slang modules -- MathHelpers, SpectrumUtils, Fresnel, Mueller, PLT (the generalized
+ray), Interference, FractalSurface, GaussianSurface, Birefringence, DiffractionGrating, Scene.evalSpectrum / sampleSpectrum, the
+differential reflect / refract helpers and all ten PLT*BSDF modules -- textually into C++ (where /root/reference lies; nothing of it is
+committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
+function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
+  * delta-lobe energies alpha = exp(-x) are the correctly rounded fp32 value (<= 1 ulp from expf; `1 - alpha` then amplifies that ulp
+    in the scatter lobes and their pdfs),
+  * the Airy phasors of the multilayer stack are the correctly rounded fp32 cos / sin (an interference sum that cancels to ~1e-4).
+"""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compare")
+N = 100_000
+
+# largest allowed distance in units in the last place; everything not listed must be bit-exact
+ULP = {
+    "FractalSurface.alpha": 1, "GaussianSurface.alpha": 1, "DiffractionGrating.setup_alpha": 1,
+    # (1 - alpha) and products of it: the single ulp of alpha, amplified by the cancellation
+    "PLTConductorBSDF.sample": 4, "PLTConductorBSDF.eval": 64, "PLTConductorBSDF.pdf": 1024,
+    "PLTOpaqueDielectricBSDF.sample": 4, "PLTOpaqueDielectricBSDF.eval": 64, "PLTOpaqueDielectricBSDF.pdf": 1024,
+    "PLTDielectricBSDF.eval": 64, "PLTDielectricBSDF.pdf": 1024, "PLTDielectricBSDF.sample": 4,
+    "PLTCoatedConductorBSDF.sample": 4, "PLTCoatedConductorBSDF.eval": 64, "PLTCoatedConductorBSDF.pdf": 1024,
+    "PLTCoatedOpaqueDielectricBSDF.sample": 4, "PLTCoatedOpaqueDielectricBSDF.eval": 64, "PLTCoatedOpaqueDielectricBSDF.pdf": 1024,
+    "PLTDiffractionGratedConductorBSDF.sample": 16, "PLTDiffractionGratedConductorBSDF.eval": 1024, "PLTDiffractionGratedConductorBSDF.pdf": 1024,
+    "PLTDiffractionGratedOpaqueDielectricBSDF.sample": 16, "PLTDiffractionGratedOpaqueDielectricBSDF.eval": 1024, "PLTDiffractionGratedOpaqueDielectricBSDF.pdf": 1024,
+}
+# relative bound instead of an ulp bound: the multilayer stack's interference sum (correctly rounded phasors in the oracle)
+REL = {"PLTMultiLayeredStackBSDF.eval": 5e-3}
+
+EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "SpectrumUtils.rgbToSpectrum", "SpectrumUtils.spectrumToRgb", "Fresnel.fresnel_dielectric", "Fresnel.fresnel_conductor",
+            "Mueller.MuellerT", "Mueller.MuellerFresnel", "Mueller.MuellerFresnelRConductor", "Mueller.MuellerFresnelDielectric", "PLT.sourceBeam", "PLT.propagate",
+            "PLT.constructLocalFrame_rotateFrame", "PLT.coherence", "PLT.transformCoherence", "Interference.interfere_phaseShift", "FractalSurface.eval_pdf_sample",
+            "GaussianSurface.eval_pdf_sample", "Birefringence.fresnel_iso_aniso", "Birefringence.fresnel_aniso_iso", "Birefringence.vectors_in_slab", "Scene.evalSpectrum",
+            "Scene.sampleSpectrum", "DifferentialShadingGeometry.reflect_refractDerivatives", "DiffractionGrating.lobeIntensity_diffract", "DiffractionGrating.closestLobeHint",
+            "DiffractionGrating.sampleLobe"] + [f"PLT{m}BSDF.{f}" for m in ("Diffuse", "Conductor", "Dielectric", "OpaqueDielectric", "ThinDielectric", "CoatedConductor", "CoatedOpaqueDielectric",
+                                                                          "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack") for f in ("eval", "sample", "pdf", "lambdaPdf")]
+
+
+@pytest.fixture(scope="module")
+def report():
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])  # no-op when up to date
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/ref_compare is not built and /root/reference is absent (the comparison can only be generated where the reference lies)")
+    out = subprocess.run([BIN, str(N)], capture_output=True, text=True, check=True, timeout=600).stdout
+    rep = json.loads(out)
+    with open(os.path.join(ROOT, "oracle", "_ref", "report.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    return rep
+
+
+def test_every_module_is_compared(report):
+    missing = [k for k in EXPECTED if k not in report]
+    assert not missing, missing
+    thin = {k: v["n"] for k, v in report.items() if v["n"] < 10_000}
+    assert not thin, thin
+    assert sum(v["n"] for v in report.values()) >= 50_000_000
+
+
+def test_oracle_reproduces_the_reference_text(report):
+    bad = {}
+    for name, v in report.items():
+        if v["mismatches"]:
+            bad[name] = v           # a NaN / inf / integer / boolean result differs
+        elif name in REL:
+            if v["max_rel"] > REL[name]:
+                bad[name] = v
+        elif v["max_ulp"] > ULP.get(name, 0):
+            bad[name] = v
+    assert not bad, bad
+    exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
+    assert exact >= 55, exact   # of 80 compared functions / entry points
