@@ -328,6 +328,28 @@ PLTPT_API int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32
                                       const PltptCameraData* camera, uint32_t width, uint32_t height,
                                       double* accum, void* stream);
 
+/* The same restricted to image rows [rowBegin, rowEnd) of every frame (rowBegin a multiple of 4): the image-tile half of the multi-GPU
+ * partition (north-star (e)); pixels outside the rows are not touched, so accumulators of disjoint bands add up to the whole image. */
+PLTPT_API int pltpt_render_accumulate_rows(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount,
+                                           const PltptCameraData* camera, uint32_t width, uint32_t height,
+                                           uint32_t rowBegin, uint32_t rowEnd, double* accum, void* stream);
+/* AccumulatePass output (Accumulate.cs.slang:185-197): color = sum / accumulated frame count, alpha 1.  Device pointers. */
+PLTPT_API int pltpt_resolve_accumulated(PltptHandle h, const double* accum, uint32_t width, uint32_t height, float* color, void* stream);
+/* One converged image for a caller with host memory only: `frameCount` frames accumulated on the device in fp64, resolved, ONE
+ * RGBA32F image copied to `colorHost` (pinned memory recommended).  Returns when the image is on the host. */
+PLTPT_API int pltpt_render_accumulate_host(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount,
+                                           const PltptCameraData* camera, uint32_t width, uint32_t height, float* colorHost);
+/* Several GPUs of one process (north-star (e); one process per GPU uses pltpt_render_accumulate + an NCCL reduce instead):
+ * handles[i] lives on its own device with the same scene.  SAMPLE_INDEX: handle i renders frames firstFrame + i, + n, ... of the whole
+ * image; ROW_BANDS: every handle renders all frames of its band of rows.  Device 0 sums the peers' fp64 accumulators with one kernel
+ * that reads them through NVLink peer mappings, resolves, and copies one image to `colorHost` (may be NULL); `accumOut` (may be NULL)
+ * receives the summed RGBA64F accumulator on handles[0]'s device.  The result equals the single-GPU accumulation of the same frames
+ * up to fp64 summation order. */
+enum { PLTPT_PARTITION_SAMPLE_INDEX = 0, PLTPT_PARTITION_ROW_BANDS = 1 };
+PLTPT_API int pltpt_render_accumulate_multi(const PltptHandle* handles, uint32_t handleCount, uint32_t firstFrame, uint32_t frameCount,
+                                            const PltptCameraData* camera, uint32_t width, uint32_t height, uint32_t partition,
+                                            float* colorHost, double* accumOut);
+
 /* Frames pltpt_render_accumulate keeps in flight (ours; frames are independent, pltpt_sample.rt.slang:154): 0 = the default
  * (every lane the library was built with, each a CUDA stream with private work buffers), 1 = strictly sequential on the
  * caller's stream, n = n frames.

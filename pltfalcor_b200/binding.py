@@ -18,6 +18,7 @@ EXPORTS = [
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
     "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
+    "pltpt_render_accumulate_rows", "pltpt_resolve_accumulated", "pltpt_render_accumulate_host", "pltpt_render_accumulate_multi",
 ]
 
 
@@ -44,6 +45,10 @@ def lib():
         _lib.pltpt_set_scene.argtypes = [vp, vp]
         _lib.pltpt_render_frame.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp]
         _lib.pltpt_render_accumulate.argtypes = [vp, u32, u32, u32, vp, u32, u32, vp, vp]
+        _lib.pltpt_render_accumulate_rows.argtypes = [vp, u32, u32, u32, vp, u32, u32, u32, u32, vp, vp]
+        _lib.pltpt_resolve_accumulated.argtypes = [vp, vp, u32, u32, vp, vp]
+        _lib.pltpt_render_accumulate_host.argtypes = [vp, u32, u32, u32, vp, u32, u32, vp]
+        _lib.pltpt_render_accumulate_multi.argtypes = [vp, u32, u32, u32, vp, u32, u32, u32, vp, vp]
         _lib.pltpt_render_frame_host.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
         _lib.pltpt_render_frame_host_async.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp]
         _lib.pltpt_host_wait.argtypes = [vp, u32]
@@ -67,6 +72,13 @@ def lib():
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
     return _lib
+
+
+def render_accumulate_multi(handles, cam, first_frame, frame_count, width, height, partition=0, color_host=None, accum_out=None):
+    """Single-process multi-GPU accumulation (pltpt_render_accumulate_multi): `handles` = Pltpt objects on distinct devices with the same scene."""
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    ch = None if color_host is None else (color_host.data_ptr() if hasattr(color_host, "data_ptr") else _hp(color_host))
+    _check(lib().pltpt_render_accumulate_multi(arr, len(handles), first_frame, frame_count, C.byref(cam), width, height, partition, ch, _dp(accum_out)))
 
 
 def _check(code):
@@ -200,6 +212,17 @@ class Pltpt:
     def render_accumulate(self, cam, first_frame, frame_step, frame_count, width, height, accum, stream=None):
         """accum: torch float64 CUDA tensor of width*height*4 (RGB sums + sample count)."""
         _check(lib().pltpt_render_accumulate(self.h, first_frame, frame_step, frame_count, C.byref(cam), width, height, _dp(accum), stream))
+
+    def render_accumulate_rows(self, cam, first_frame, frame_step, frame_count, width, height, row_begin, row_end, accum, stream=None):
+        _check(lib().pltpt_render_accumulate_rows(self.h, first_frame, frame_step, frame_count, C.byref(cam), width, height, row_begin, row_end, _dp(accum), stream))
+
+    def resolve_accumulated(self, accum, width, height, color, stream=None):
+        _check(lib().pltpt_resolve_accumulated(self.h, _dp(accum), width, height, _dp(color), stream))
+
+    def render_accumulate_host(self, cam, first_frame, frame_step, frame_count, width, height, color_host):
+        """color_host: pinned torch float32 CPU tensor (h, w, 4) or a numpy array."""
+        ptr = color_host.data_ptr() if hasattr(color_host, "data_ptr") else _hp(color_host)
+        _check(lib().pltpt_render_accumulate_host(self.h, first_frame, frame_step, frame_count, C.byref(cam), width, height, ptr))
 
     # ---- ray queries ------------------------------------------------------------------------------------------
     def trace_closest(self, rays, hits, hit_t=None, stream=None):

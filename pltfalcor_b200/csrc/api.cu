@@ -5,6 +5,8 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 using namespace plt;
 
@@ -672,12 +674,31 @@ __global__ void __launch_bounds__(256) k_accum_add(double* __restrict__ dst, con
     if (i < n) dst[i] += src[i];
 }
 }  // namespace
-extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
-                                       double* accum, void* stream) {
-    if (int r = checkRender(h, cam, w, hgt)) return r;
-    if (!accum) return fail(PLTPT_ERR_INVALID_ARGUMENT, "accum output is null");
-    if (frameStep == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep must be > 0");
-    cudaStream_t user = (cudaStream_t)stream;
+namespace {
+// AccumulatePass output of the Double mode (Accumulate.cs.slang:185-197): running sum / accumulated frame count
+__global__ void __launch_bounds__(256) k_resolve_accum(const double* __restrict__ accum, float4* __restrict__ color, size_t pixels) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const double n = accum[4 * i + 3];
+    const double inv = n > 0.0 ? 1.0 / n : 0.0;
+    color[i] = make_float4(float(accum[4 * i] * inv), float(accum[4 * i + 1] * inv), float(accum[4 * i + 2] * inv), 1.f);
+}
+// Sum of the peers' accumulators into this device's one, read over NVLink peer mappings (no staging copy, no host round trip).
+constexpr int kMaxPeers = 15;
+struct PeerList { const double* p[kMaxPeers]; int n; };
+__global__ void __launch_bounds__(256) k_accum_add_peers(double* __restrict__ dst, PeerList peers, size_t n) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        double s = dst[i];
+        for (int k = 0; k < peers.n; ++k) s += peers.p[k][i];
+        dst[i] = s;
+    }
+}
+
+// Frames {firstFrame + i * frameStep} restricted to image rows [rowBegin, rowEnd) (rows must start on a multiple of 4: primary rays are
+// traced in 8x4 pixel tiles), summed into `accum`.
+int renderAccumulateRows(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, uint32_t rowBegin,
+                         uint32_t rowEnd, double* accum, cudaStream_t user) {
+    if (rowBegin >= rowEnd || rowEnd > hgt || (rowBegin & 3u)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "row range must be non-empty, inside the image and start on a multiple of 4");
     // Two frames in flight (context.h "Frame lanes") unless per-kernel timers are on (they need one stream) or there is one frame.
     const int lanes = h->profiling ? 1 : int(std::min<uint32_t>(frameCount, uint32_t(h->frameOverlap)));
     const size_t accumBytes = size_t(w) * hgt * 4 * sizeof(double);
@@ -703,7 +724,7 @@ extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint3
         float jx = halton(k, 2) + 0.5f, jy = halton(k, 3) + 0.5f;
         jx = (jx - std::floor(jx)) - 0.5f; jy = (jy - std::floor(jy)) - 0.5f;
         c.jitterX = jx / float(w); c.jitterY = jy / float(hgt);
-        if (int r = renderFrame(h, l, f, &c, w, hgt, nullptr, nullptr, nullptr, l == 0 ? accum : h->lanes[l].accum.as<double>(), true, l == 0 ? user : h->lanes[l].stream)) return r;
+        if (int r = renderFrame(h, l, f, &c, w, hgt, nullptr, nullptr, nullptr, l == 0 ? accum : h->lanes[l].accum.as<double>(), true, l == 0 ? user : h->lanes[l].stream, rowBegin, rowEnd)) return r;
     }
     for (int l = 1; l < lanes; ++l) {  // join: the caller's stream waits for the lane, then folds the lane's sums into `accum`
         PltptContext::Lane& ln = h->lanes[l];
@@ -713,6 +734,122 @@ extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint3
         k_accum_add<<<uint32_t((n + 255) / 256), 256, 0, user>>>(accum, ln.accum.as<double>(), n);
         h->stats.kernelLaunches++;
     }
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+}  // namespace
+extern "C" int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
+                                       double* accum, void* stream) {
+    return pltpt_render_accumulate_rows(h, firstFrame, frameStep, frameCount, cam, w, hgt, 0, hgt, accum, stream);
+}
+extern "C" int pltpt_render_accumulate_rows(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
+                                            uint32_t rowBegin, uint32_t rowEnd, double* accum, void* stream) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    if (!accum) return fail(PLTPT_ERR_INVALID_ARGUMENT, "accum output is null");
+    if (frameStep == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep must be > 0");
+    return renderAccumulateRows(h, firstFrame, frameStep, frameCount, cam, w, hgt, rowBegin, rowEnd, accum, (cudaStream_t)stream);
+}
+extern "C" int pltpt_resolve_accumulated(PltptHandle h, const double* accum, uint32_t w, uint32_t hgt, float* color, void* stream) {
+    if (!h || !accum || !color) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (w == 0 || hgt == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "empty image");
+    PLT_CUDA(cudaSetDevice(h->device));
+    const size_t pixels = size_t(w) * hgt;
+    k_resolve_accum<<<uint32_t((pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(accum, reinterpret_cast<float4*>(color), pixels);
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
+// One converged image for a caller with host memory only: `frameCount` frames accumulated on the device (fp64), resolved, one RGBA32F
+// image copied to the host.
+extern "C" int pltpt_render_accumulate_host(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
+                                            float* colorHost) {
+    if (int r = checkRender(h, cam, w, hgt)) return r;
+    if (!colorHost) return fail(PLTPT_ERR_INVALID_ARGUMENT, "color output is null");
+    if (frameStep == 0 || frameCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep and frameCount must be > 0");
+    const size_t pixels = size_t(w) * hgt;
+    PLT_CUDA(h->hostAccum.ensure(pixels * 4 * sizeof(double)));
+    PLT_CUDA(h->outColor.ensure(pixels * 16));
+    PLT_CUDA(cudaMemsetAsync(h->hostAccum.p, 0, pixels * 4 * sizeof(double), 0));
+    if (int r = renderAccumulateRows(h, firstFrame, frameStep, frameCount, cam, w, hgt, 0, hgt, h->hostAccum.as<double>(), 0)) return r;
+    k_resolve_accum<<<uint32_t((pixels + 255) / 256), 256, 0, 0>>>(h->hostAccum.as<double>(), h->outColor.as<float4>(), pixels);
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaMemcpyAsync(colorHost, h->outColor.p, pixels * 16, cudaMemcpyDeviceToHost, 0));
+    PLT_CUDA(cudaStreamSynchronize(0));
+    return PLTPT_OK;
+}
+// The same on several GPUs of one process (north-star (e)): handle i, on its own device with the scene replicated, renders its share --
+// frame indices {firstFrame + i, + n, ...} of the whole image (partition 0), or all frames of its band of rows (partition 1) -- into an
+// accumulator on its device; device 0 then sums the peers' accumulators with one kernel that reads them over NVLink peer mappings,
+// resolves and copies ONE image to the host.  Summation order: handle 0, 1, ... per pixel (deterministic).
+extern "C" int pltpt_render_accumulate_multi(const PltptHandle* handles, uint32_t n, uint32_t firstFrame, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt,
+                                             uint32_t partition, float* colorHost, double* accumOut) {
+    if (!handles || n == 0 || n > uint32_t(kMaxPeers) + 1u) return fail(PLTPT_ERR_INVALID_ARGUMENT, "1 .. 16 handles are needed");
+    if (!colorHost && !accumOut) return fail(PLTPT_ERR_INVALID_ARGUMENT, "no output requested");
+    if (partition > PLTPT_PARTITION_ROW_BANDS) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown partition");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (int r = checkRender(handles[i], cam, w, hgt)) return r;
+        for (uint32_t j = 0; j < i; ++j) if (handles[j]->device == handles[i]->device) return fail(PLTPT_ERR_INVALID_ARGUMENT, "handles must live on distinct devices");
+    }
+    const size_t pixels = size_t(w) * hgt, accumBytes = pixels * 4 * sizeof(double);
+    PltptHandle h0 = handles[0];
+    // peer access from device 0 to every other device (idempotent)
+    PLT_CUDA(cudaSetDevice(h0->device));
+    for (uint32_t i = 1; i < n; ++i) {
+        int can = 0;
+        PLT_CUDA(cudaDeviceCanAccessPeer(&can, h0->device, handles[i]->device));
+        if (!can) return fail(PLTPT_ERR_UNSUPPORTED, "device " + std::to_string(h0->device) + " cannot map the memory of device " + std::to_string(handles[i]->device));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(handles[i]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    // every device renders its share on its own (legacy default) stream, fed by its own host thread (a frame is ~100 launches: one
+    // thread would fill the first device's launch queue before the second device saw any work)
+    const uint32_t band = ((hgt + n - 1) / n + 3u) & ~3u;
+    std::vector<int> status(n, PLTPT_OK);
+    std::vector<std::string> message(n);
+    auto work = [&](uint32_t i) {
+        PltptHandle h = handles[i];
+        auto run = [&]() -> int {
+            PLT_CUDA(cudaSetDevice(h->device));
+            PLT_CUDA(h->hostAccum.ensure(accumBytes));
+            PLT_CUDA(cudaMemsetAsync(h->hostAccum.p, 0, accumBytes, 0));
+            if (partition == PLTPT_PARTITION_SAMPLE_INDEX) {
+                const uint32_t mine = frameCount / n + (i < frameCount % n ? 1u : 0u);
+                if (mine) if (int r = renderAccumulateRows(h, firstFrame + i, n, mine, cam, w, hgt, 0, hgt, h->hostAccum.as<double>(), 0)) return r;
+            } else {
+                const uint32_t r0 = std::min(hgt, i * band), r1 = std::min(hgt, (i + 1) * band);
+                if (r0 < r1) if (int r = renderAccumulateRows(h, firstFrame, 1, frameCount, cam, w, hgt, r0, r1, h->hostAccum.as<double>(), 0)) return r;
+            }
+            PLT_CUDA(cudaStreamSynchronize(0));   // this device's accumulator is final
+            return PLTPT_OK;
+        };
+        status[i] = run();
+        if (status[i]) message[i] = pltpt_last_error();  // (the error text is thread-local)
+    };
+    {
+        std::vector<std::thread> threads;
+        for (uint32_t i = 1; i < n; ++i) threads.emplace_back(work, i);
+        work(0);
+        for (auto& t : threads) t.join();
+    }
+    for (uint32_t i = 0; i < n; ++i) if (status[i]) return fail(status[i], "device " + std::to_string(handles[i]->device) + ": " + message[i]);
+    PeerList peers{};
+    for (uint32_t i = 1; i < n; ++i) peers.p[peers.n++] = handles[i]->hostAccum.as<double>();
+    PLT_CUDA(cudaSetDevice(h0->device));
+    if (peers.n) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h0->device);
+        k_accum_add_peers<<<uint32_t(sms) * 8, 256, 0, 0>>>(h0->hostAccum.as<double>(), peers, pixels * 4);
+        h0->stats.kernelLaunches++;
+    }
+    if (accumOut) PLT_CUDA(cudaMemcpyAsync(accumOut, h0->hostAccum.p, accumBytes, cudaMemcpyDeviceToDevice, 0));
+    if (colorHost) {
+        PLT_CUDA(h0->outColor.ensure(pixels * 16));
+        k_resolve_accum<<<uint32_t((pixels + 255) / 256), 256, 0, 0>>>(h0->hostAccum.as<double>(), h0->outColor.as<float4>(), pixels);
+        h0->stats.kernelLaunches++;
+        PLT_CUDA(cudaMemcpyAsync(colorHost, h0->outColor.p, pixels * 16, cudaMemcpyDeviceToHost, 0));
+    }
+    PLT_CUDA(cudaStreamSynchronize(0));
     PLT_CUDA(cudaGetLastError());
     return PLTPT_OK;
 }

@@ -116,6 +116,7 @@ struct PltptContext {
     int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
     size_t workBudgetBytes = 0; // per-lane work-buffer budget that sizes the row tiles (0 = default 24 GB; pltpt_set_work_budget)
     plt::DevBuf outColor, outAlbedo, outNormal;
+    plt::DevBuf hostAccum;                    // RGBA64F sums of pltpt_render_accumulate_host / _multi
     // pltpt_render_frame_host_async: frame i runs whole on lane i % frameOverlap, on that lane's own stream, into one of that lane's
     // two output image sets; its device-to-host copies run on hostCopyStream behind an event, so the lane starts its next frame
     // (other image set) at once and only waits for a set's previous copy before overwriting that set

@@ -837,6 +837,33 @@ def cornell_box(aspect=16.0 / 9.0, dielectric_roughness=0.1, conductor_roughness
     return b.finalize(), cam
 
 
+def cornell_box_closed(aspect=16.0 / 9.0, albedo=0.8):
+    """Deep-path variant of the Cornell box: the same room closed by a front wall, every wall at albedo 0.8, camera
+    inside.  No path can escape, so paths run to the bounce limit unless Russian roulette ends them: the O(L^2) forward replay of the
+    solve stage is what this workload stresses."""
+    b = SceneBuilder()
+    au = b.add_ior_profiles("Au")
+    lamp = b.add_emission_profile(LAMP, 1.0)
+    white = b.add_diffuse((albedo, albedo, albedo))
+    red = b.add_diffuse((albedo, 0.1 * albedo, 0.1 * albedo))
+    green = b.add_diffuse((0.15 * albedo, albedo, 0.2 * albedo))
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    glass = b.add_dielectric(ior=1.5, roughness=0.1)
+    gold = b.add_conductor(au, roughness=0.3, gamma=3.0)
+    X = 1.6
+    b.add_mesh(quad([-X, 0, 1], [X, 0, 1], [X, 0, -1], [-X, 0, -1]), white)       # floor
+    b.add_mesh(quad([-X, 2, -1], [X, 2, -1], [X, 2, 1], [-X, 2, 1]), white)       # ceiling
+    b.add_mesh(quad([-X, 0, -1], [X, 0, -1], [X, 2, -1], [-X, 2, -1]), white)     # back wall (normal +z)
+    b.add_mesh(quad([X, 0, 1], [-X, 0, 1], [-X, 2, 1], [X, 2, 1]), white)         # front wall (normal -z), behind the camera
+    b.add_mesh(quad([-X, 0, 1], [-X, 0, -1], [-X, 2, -1], [-X, 2, 1]), red)
+    b.add_mesh(quad([X, 0, -1], [X, 0, 1], [X, 2, 1], [X, 2, -1]), green)
+    b.add_mesh(quad([-0.3, 1.995, -0.3], [0.3, 1.995, -0.3], [0.3, 1.995, 0.3], [-0.3, 1.995, 0.3]), light)
+    b.add_mesh(box([-0.6, 0.6, -0.3], [0.3, 0.6, 0.3], rot_y=0.3), gold)
+    b.add_mesh(box([0.6, 0.3, 0.3], [0.3, 0.3, 0.3], rot_y=-0.25), glass)
+    cam = make_camera([0.0, 1.0, 0.95], [0.0, 0.95, -1.0], focal_length=12.0, aspect=aspect)
+    return b.finalize(), cam
+
+
 def env_scene(aspect=16.0 / 9.0, with_emitter=True):
     """Environment-lit scene (EnvMapSampler NEE + onMiss): open ground plane, a rough Au conductor sphere, a smooth
     Dielectric sphere (MNEE towards the distant env light), a coated sphere and a diffuse box under a procedural sky rotated by

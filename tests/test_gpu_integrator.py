@@ -453,3 +453,72 @@ def test_queued_host_frames_equal_the_synchronous_ones(name, torch_cuda):
     with pytest.raises(binding.PltptError):
         binding._check(binding.lib().pltpt_render_frame_host_async(p.h, 0, C.byref(cam), w, h, None, None, None))
     p.close()
+
+
+def test_row_bands_and_host_accumulation(torch_cuda, cornell):
+    """Image-tile half of the multi-GPU partition (north-star (e)): accumulators of disjoint row bands add up to the whole image bit for
+    bit, and pltpt_render_accumulate_host returns sum / count of the same accumulation as one RGBA32F host image."""
+    from pltfalcor_b200 import binding
+    torch = torch_cuda
+    buffers, cam = cornell
+    p = binding.Pltpt(maxBounces=6)
+    p.set_scene(buffers)
+    w, h, frames = 160, 144, 5
+    whole = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda")
+    p.render_accumulate(cam, 3, 2, frames, w, h, whole)
+    bands = torch.zeros_like(whole)
+    for r0, r1 in ((0, 52), (52, 100), (100, 144)):
+        p.render_accumulate_rows(cam, 3, 2, frames, w, h, r0, r1, bands)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, bands) and (whole[..., 3] == frames).all()
+    one = torch.zeros_like(whole)
+    p.render_accumulate_rows(cam, 3, 2, frames, w, h, 52, 100, one)
+    torch.cuda.synchronize()
+    assert (one[:52] == 0).all() and (one[100:] == 0).all() and torch.equal(one[52:100], whole[52:100])
+    with pytest.raises(binding.PltptError):
+        p.render_accumulate_rows(cam, 0, 1, 1, w, h, 50, 100, one)   # bands start on multiples of 4 (8x4 primary-ray tiles)
+    color = torch.zeros((h, w, 4), device="cuda")
+    p.resolve_accumulated(whole, w, h, color)
+    host = torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True)
+    p.render_accumulate_host(cam, 3, 2, frames, w, h, host)
+    torch.cuda.synchronize()
+    assert torch.equal(color.cpu(), host)
+    assert torch.allclose(color[..., :3].double(), whole[..., :3] / frames, rtol=1e-6, atol=0) and (color[..., 3] == 1).all()
+    p.close()
+
+
+@pytest.mark.parametrize("partition", [0, 1])
+def test_multi_gpu_accumulation_equals_single_gpu(torch_cuda, partition):
+    """pltpt_render_accumulate_multi (one process, one handle per GPU, peers summed over NVLink peer mappings): the N-GPU image equals the
+    1-GPU accumulation of the same frames up to fp64 summation order.  Needs >= 2 devices (gpurun --gpus 2); skipped otherwise."""
+    torch = torch_cuda
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    from pltfalcor_b200 import binding, scene
+    n = min(n, 4)
+    buffers, cam = scene.grating_sphere_scene()
+    w, h, frames = 192, 108, 9
+    single = binding.Pltpt(device=0, maxBounces=6)
+    single.set_scene(buffers)
+    want = torch.zeros((h, w, 4), dtype=torch.float64, device="cuda:0")
+    single.render_accumulate(cam, 2, 1, frames, w, h, want)
+    torch.cuda.synchronize()
+    handles = []
+    for d in range(n):
+        q = binding.Pltpt(device=d, maxBounces=6)
+        q.set_scene(buffers)
+        handles.append(q)
+    got = torch.zeros_like(want)
+    host = torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True)
+    binding.render_accumulate_multi(handles, cam, 2, frames, w, h, partition=partition, color_host=host, accum_out=got)
+    torch.cuda.synchronize()
+    assert (got[..., 3] == frames).all()
+    assert torch.allclose(got, want, rtol=1e-12, atol=0)
+    if partition == 1:
+        assert torch.equal(got, want)   # disjoint bands: every pixel is summed on one device in the single-GPU order
+    assert torch.allclose(host[..., :3].double(), (want[..., :3] / frames).cpu(), rtol=1e-6, atol=0)
+    for q in handles:
+        assert q.stats()["droppedConnections"] == 0
+        q.close()
+    single.close()

@@ -58,6 +58,24 @@ def test_frames_of_rank_is_a_disjoint_cover():
         partition.frames_of_rank(2, 2, 0, 1)
 
 
+def test_strong_scaling_and_row_band_partitions_cover_the_job_exactly():
+    from pltfalcor_b200 import partition
+    for world in (1, 2, 3, 4, 8):
+        for total in (0, 1, 7, 64, 65):
+            frames = []
+            for r in range(world):
+                f0, step, n = partition.frames_of_rank_strong(r, world, 11, total)
+                frames += [f0 + i * step for i in range(n)]
+            assert sorted(frames) == list(range(11, 11 + total)), (world, total)
+        for height in (4, 27, 1080, 2160):
+            rows = []
+            for r in range(world):
+                a, b = partition.row_band(r, world, height)
+                assert (a % 4 == 0 or a == b) and a <= b <= height   # (an empty band past the image end may start anywhere)
+                rows += list(range(a, b))
+            assert rows == list(range(height)), (world, height)
+
+
 def test_two_rank_partition_sums_to_the_single_rank_image(tmp_path, oracle):
     import torch.multiprocessing as mp
     world, port, out = 2, _free_port(), str(tmp_path / "sum.npy")
