@@ -550,15 +550,22 @@ __global__ void __launch_bounds__(kSweepThreads, PLT_MINB_SWEEP) k_bsdf_eval_mue
             const float4 wl = hwssWavelengths(__ldg(hero + size_t(g) * n + i), hwss);
             const SD sd = canonicalSd(materialID, Wi);
             float* my = stage + threadIdx.x * stride;
-#pragma unroll kSweepUnroll
-            for (int c = 0; c < 4; ++c) {
-                Beam beam = sourceBeamArea(Wi, -Wi, 1.f, 1.f, mk4(1.f), wl, maxBeamOmega, hwss);
-                const float4 e = mk4(c == 0 ? 1.f : 0.f, c == 1 ? 1.f : 0.f, c == 2 ? 1.f : 0.f, c == 3 ? 1.f : 0.f);
-                beam.L = mk4(e.x); beam.L1 = mk4(e.y); beam.L2 = mk4(e.z); beam.L3 = mk4(e.w);
-                beam.propagate(sd.posW);
-                bsdfEval(m, cx, sd, Wo, lobe, beam);
-                for (int j = 0; j < hwss; ++j) {
-                    const float4 SP = beam.getSP(j);
+            // the four basis Stokes vectors travel through ONE evaluation as the columns of a Beam4: frame rotation, Fresnel terms, surface
+            // statistics and coherence are computed once, only the final matrix-vector products run per column (it was four whole evaluations:
+            // 87 warp-instructions per matrix, profiles/r1_sweep_metrics.json)
+            Beam4 beam;
+            static_cast<Beam&>(beam) = sourceBeamArea(Wi, -Wi, 1.f, 1.f, mk4(1.f), wl, maxBeamOmega, hwss);
+            beam.L = mk4(1.f); beam.L1 = beam.L2 = beam.L3 = mk4(0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                beam.xL[c] = mk4(0.f); beam.xL1[c] = mk4(c == 0 ? 1.f : 0.f); beam.xL2[c] = mk4(c == 1 ? 1.f : 0.f); beam.xL3[c] = mk4(c == 2 ? 1.f : 0.f);
+            }
+            beam.propagate(sd.posW);
+            bsdfEval(m, cx, sd, Wo, lobe, beam);
+            for (int j = 0; j < hwss; ++j) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 SP = getSPc(beam, j, c);
                     my[j * 16 + 0 + c] = SP.x; my[j * 16 + 4 + c] = SP.y; my[j * 16 + 8 + c] = SP.z; my[j * 16 + 12 + c] = SP.w;
                 }
             }

@@ -199,34 +199,75 @@ struct Beam {
         const float x = 1.f / dot(v, mul(invT, v));
         return expf(-.5f * x);
     }
-    // rotateFrame: MuellerT (Mueller.slang:34-53) acts on (L1,L2) only; coherence rotates by R(θ)
-    PLT_D void rotateFrame(float3 newt, float3 newr) {
+    // rotateFrame: MuellerT (Mueller.slang:34-53) acts on (L1,L2) only; coherence rotates by R(θ).  Split in two so that a beam with
+    // several Stokes columns (Beam4 below) rotates all of them with one evaluation of the angle.
+    PLT_D void frameRotation(float3 newt, float& rx, float& ry, float& sint, float& cost) const {
         float theta = atan2f(dot(r, cross(t, newt)), dot(t, newt));
         theta = isfinite(theta) ? theta : .0f;
-        float sint, cost;
         sincosf(theta, &sint, &cost);
-        const float rx = 2 * sint * cost, ry = 1 - 2 * sqr(sint);
+        rx = 2 * sint * cost; ry = 1 - 2 * sqr(sint);
+    }
+    PLT_D void rotateStokes(float4& l1, float4& l2, float rx, float ry) const {
         for (int j = 0; j < comps; ++j) {
-            const float a = lane(L1, j), b = lane(L2, j);
-            setLane(L1, j, rx * a + -ry * b);
-            setLane(L2, j, ry * a + rx * b);
+            const float a = lane(l1, j), b = lane(l2, j);
+            setLane(l1, j, rx * a + -ry * b);
+            setLane(l2, j, ry * a + rx * b);
         }
+    }
+    PLT_D void rotateFrame(float3 newt, float3 newr) {
+        float rx, ry, sint, cost;
+        frameRotation(newt, rx, ry, sint, cost);
+        rotateStokes(L1, L2, rx, ry);
         transformCoherence(M22{cost, -sint, sint, cost});
         r = newr;
         t = newt;
     }
-    PLT_D void constructLocalFrame(float3 newwo) {
-        float3 newt = cross(mk3(0.f, 0.f, 1.f), newwo);
+    PLT_D static float3 localFrameTangent(float3 newwo) {
+        const float3 newt = cross(mk3(0.f, 0.f, 1.f), newwo);
         const float l2 = dot(newt, newt);
-        newt = l2 > 1e-8f ? newt / sqrtf(l2) : perp_stark(newwo);
-        rotateFrame(newt, newwo);
+        return l2 > 1e-8f ? newt / sqrtf(l2) : perp_stark(newwo);
     }
+    PLT_D void constructLocalFrame(float3 newwo) { rotateFrame(localFrameTangent(newwo), newwo); }
     PLT_D void propagate(float3 p) {
         if (!distant) r_m += length(p - posW);
         posW = p;
     }
     PLT_D float3 toLocal(float3 v) const { return mk3(dot(v, t), dot(v, cross(t, r)), dot(v, r)); }
 };
+// A generalized ray that carries FOUR Stokes vectors per wavelength through the same geometry, coherence and wavelengths: the columns
+// of the Mueller matrix when they start as the basis vectors e0..e3 (config 1 of the benchmark, pltpt_bsdf_eval_mueller).  Everything a
+// BSDF computes that does not depend on the Stokes vector -- local frame, rotation angle, Fresnel terms, surface statistics, coherence --
+// is then evaluated once instead of four times.  Column 0 lives in the base class; the BSDFs below are templates over the beam type and
+// reach the Stokes data only through nCols / colL.. / getSPc / setSPc, so the renderer's instantiation (Beam, one column) is unchanged.
+struct Beam4 : Beam {
+    float4 xL[3], xL1[3], xL2[3], xL3[3];
+    PLT_D void setZero() { Beam::setZero(); for (int c = 0; c < 3; ++c) xL[c] = xL1[c] = xL2[c] = xL3[c] = mk4(0.f); }
+    PLT_D void scale(float4 s) { Beam::scale(s); for (int c = 0; c < 3; ++c) { xL[c] *= s; xL1[c] *= s; xL2[c] *= s; xL3[c] *= s; } }
+    PLT_D void rotateFrame(float3 newt, float3 newr) {
+        float rx, ry, sint, cost;
+        frameRotation(newt, rx, ry, sint, cost);
+        rotateStokes(L1, L2, rx, ry);
+        for (int c = 0; c < 3; ++c) rotateStokes(xL1[c], xL2[c], rx, ry);
+        transformCoherence(M22{cost, -sint, sint, cost});
+        r = newr;
+        t = newt;
+    }
+    PLT_D void constructLocalFrame(float3 newwo) { rotateFrame(localFrameTangent(newwo), newwo); }
+};
+template <class B> struct BeamCols { static constexpr int n = 1; };
+template <> struct BeamCols<Beam4> { static constexpr int n = 4; };
+PLT_D float4& colL(Beam& b, int) { return b.L; }
+PLT_D float4& colL1(Beam& b, int) { return b.L1; }
+PLT_D float4& colL2(Beam& b, int) { return b.L2; }
+PLT_D float4& colL3(Beam& b, int) { return b.L3; }
+PLT_D float4& colL(Beam4& b, int c) { return c == 0 ? b.L : b.xL[c - 1]; }
+PLT_D float4& colL1(Beam4& b, int c) { return c == 0 ? b.L1 : b.xL1[c - 1]; }
+PLT_D float4& colL2(Beam4& b, int c) { return c == 0 ? b.L2 : b.xL2[c - 1]; }
+PLT_D float4& colL3(Beam4& b, int c) { return c == 0 ? b.L3 : b.xL3[c - 1]; }
+template <class B> PLT_D float4 getSPc(B& b, int j, int c) { return mk4(lane(colL(b, c), j), lane(colL1(b, c), j), lane(colL2(b, c), j), lane(colL3(b, c), j)); }
+template <class B> PLT_D void setSPc(B& b, int j, int c, float4 s) { setLane(colL(b, c), j, s.x); setLane(colL1(b, c), j, s.y); setLane(colL2(b, c), j, s.z); setLane(colL3(b, c), j, s.w); }
+#define PLT_FOR_COLS(B, c) _Pragma("unroll") for (int c = 0; c < BeamCols<B>::n; ++c)
+
 PLT_D Beam makeBeam(float4 Le, float diffusivity, float3 posW, float3 dir, float4 wl, bool distant, int comps) {
     Beam b;
     b.L = Le; b.L1 = b.L2 = b.L3 = mk4(0.f);
@@ -338,14 +379,18 @@ PLT_D Gaussian matGaussian(const DevMaterial& m) { return {m.surfA, m.surfQ}; }
 constexpr float kMeanK = k2Pi / (kMeanWavelength * 1e-3f);
 
 // =========================================================================== Diffuse (PLTDiffuseBSDF.slang:39-95)
-PLT_D void diffuseEval(const DevMaterial& m, float3 toLight, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void diffuseEval(const DevMaterial& m, float3 toLight, uint32_t lobe, B& beam) {
     const bool valid = (lobe & L_DiffuseReflection) != 0;
     const float4 w = valid ? (fabsf(toLight.z) * k1_Pi) * rgbToSpectrum4(matC0(m), beam.wl) : mk4(0.f);
-    beam.L *= w;
-    beam.L1 = beam.L2 = beam.L3 = mk4(0.f);
+    PLT_FOR_COLS(B, c) {
+        colL(beam, c) *= w;
+        colL1(beam, c) = colL2(beam, c) = colL3(beam, c) = mk4(0.f);
+    }
 }
 // =========================================================================== Conductor (PLTConductorBSDF.slang:44-170)
-PLT_D void conductorEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void conductorEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     const bool isScatter = (lobe & L_ScatterReflection) != 0, isDirect = (lobe & L_DeltaReflection) != 0;
     if ((!isScatter && !isDirect) || (lobe & L_Reflection) == 0) { beam.setZero(); return; }
     const Fractal gfs = matFractal(m);
@@ -356,12 +401,10 @@ PLT_D void conductorEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight
     const float LdotH = fmaxf(.0f, dot(toLight, normalize(h)));
     const float4 iorN = evalSpectrum4(cx.profiles, m.etaN, beam.wl), iorK = evalSpectrum4(cx.profiles, m.etaK, beam.wl);
     for (int j = 0; j < beam.comps; ++j) {
-        const float4 SP = beam.getSP(j);
         const float2 ior = mk2(lane(iorN, j) / m.extEta, lane(iorK, j) / m.extEta);
-        float4 nSP;
-        if (isScatter) nSP = ((1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h)) * fmApply(fmRConductor(LdotH, ior), SP);
-        else nSP = lane(a, j) * fmApply(fmRConductor(toLight.z, ior), SP);
-        beam.setSP(j, nSP * lane(m00, j));
+        const FM M = fmRConductor(isScatter ? LdotH : toLight.z, ior);
+        const float w = isScatter ? (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h) : lane(a, j);
+        PLT_FOR_COLS(B, c) setSPc(beam, j, c, (w * fmApply(M, getSPc(beam, j, c))) * lane(m00, j));
     }
 }
 PLT_D bool fractalBaseSample(const DevMaterial& m, float kSample, bool perWavelengthK, float3 wi, Sample& s, Rng& sg, float wavelength, uint32_t lobeMask) {
@@ -400,7 +443,8 @@ PLT_D float4 conductorLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, float3 
     return ret;
 }
 // =========================================================================== OpaqueDielectric (PLTOpaqueDielectricBSDF.slang:43-147)
-PLT_D void opaqueEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void opaqueEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     const bool isDirect = (lobe & L_Delta) != 0, isScatter = (lobe & L_NonDelta) != 0;
     if ((!isScatter && !isDirect) || (lobe & L_Reflection) == 0) { beam.setZero(); return; }
     const Fractal gfs = matFractal(m);
@@ -408,11 +452,12 @@ PLT_D void opaqueEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32
     const float a = gfs.alpha(toLight, toEye, kMeanK);
     float M = a;
     if (isScatter) M = (1 - a) * fabsf(toLight.z) * gfs.eval(kMeanK, toLight + toEye);
-    for (int j = 0; j < beam.comps; ++j) beam.setSP(j, (M * lane(m00, j)) * beam.getSP(j));
+    for (int j = 0; j < beam.comps; ++j) PLT_FOR_COLS(B, c) setSPc(beam, j, c, (M * lane(m00, j)) * getSPc(beam, j, c));
 }
 // =========================================================================== Dielectric (PLTDielectricBSDF.slang:43-270)
 PLT_D float dielectricIor(const DevMaterial& m, float k) { return (m.f0 + m.f2 * sqr(k * k1_2Pi)) / m.f1; }
-PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     const float zz = toLight.z * toEye.z;
     const bool isReflection = zz > .0f;
     const bool isScatter = (lobe & L_NonDelta) != 0, isDirect = (lobe & L_Delta) != 0;
@@ -435,7 +480,8 @@ PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLigh
             const float J = isReflection ? 1.f : sqr(toEye.z > .0f ? e : 1.f / e);
             const float D = gfs.eval(lane(k, j), invTheta, Q, h);
             const FM M1 = fmDielectric(signf(toLight.z) * LdotH, e, isReflection);
-            beam.setSP(j, (lane(m00, j) * (1 - lane(a, j)) * J * fabsf(toLight.z) * D) * fmApply(M1, beam.getSP(j)));
+            const float w = lane(m00, j) * (1 - lane(a, j)) * J * fabsf(toLight.z) * D;
+            PLT_FOR_COLS(B, c) setSPc(beam, j, c, w * fmApply(M1, getSPc(beam, j, c)));
         }
     } else {
         for (int j = 0; j < beam.comps; ++j) {
@@ -448,7 +494,8 @@ PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLigh
                 evalFresnelDielectric(e, toEye.z, cosThetaT);
                 coh = beam.mutualCoherenceAngular(beam.toLocal(refractLocal(toEye, cosThetaT, e)), toLightBeam);
             }
-            beam.setSP(j, (lane(m00, j) * lane(a, j) * coh * J) * fmApply(M0, beam.getSP(j)));
+            const float w = lane(m00, j) * lane(a, j) * coh * J;
+            PLT_FOR_COLS(B, c) setSPc(beam, j, c, w * fmApply(M0, getSPc(beam, j, c)));
         }
     }
 }
@@ -540,7 +587,8 @@ PLT_D float3 Poynting(float q, float3 E, float K) {
     return normalize(mk3(E.x * (K * E.z - q * E.y), K * E.z * E.y + q * (sqr(E.x) + sqr(E.z)), -q * E.z * E.y - K * (sqr(E.x) + sqr(E.y))));
 }
 }  // namespace biref
-PLT_D void thinBirefringence(const DevMaterial& m, const BsdfCtx& cx, Beam& beam, float3 wi, float4 k) {
+template <class B>
+PLT_D void thinBirefringence(const DevMaterial& m, const BsdfCtx& cx, B& beam, float3 wi, float4 k) {
     using namespace biref;
     const float etaAvg = m.f0, tau = m.f1, bir = m.f2;
     const float2 oaxy = mk2(m.f3, m.f4);
@@ -611,27 +659,31 @@ PLT_D void thinBirefringence(const DevMaterial& m, const BsdfCtx& cx, Beam& beam
     const float4 mutual_coh = beam.mutualCoherence(k, oez * Z);
     const float ph = ei * oez * I.z + OPLo - OPLe;
     const float4 t = mutual_coh * 2.f * mk4(sinf(-k.x * ph), sinf(-k.y * ph), sinf(-k.z * ph), sinf(-k.w * ph));
-    const float4 Lx = .5f * (beam.L + beam.L1), Ly = .5f * (beam.L - beam.L1);
-    const float4 pr = Lx * Ly;
-    const float4 sq = mk4(sqrtf(pr.x), sqrtf(pr.y), sqrtf(pr.z), sqrtf(pr.w));
-    float4 nLx = sqr(ss) * Lx + sqr(ps) * Ly + (ss * ps) * t * sq;
-    float4 nLy = sqr(sp) * Lx + sqr(pp) * Ly + (sp * pp) * t * sq;
-    nLx = mk4(fmaxf(0.f, nLx.x), fmaxf(0.f, nLx.y), fmaxf(0.f, nLx.z), fmaxf(0.f, nLx.w));
-    nLy = mk4(fmaxf(0.f, nLy.x), fmaxf(0.f, nLy.y), fmaxf(0.f, nLy.z), fmaxf(0.f, nLy.w));
-    const float4 newL = nLx + nLy;
-    bool allOk = true, allFinite = true;
-    for (int j = 0; j < cx.hwss; ++j) {
-        const bool f = isfinite(lane(newL, j));
-        allFinite = allFinite && f;
-        allOk = allOk && (lane(beam.L, j) > 1e-6f && f);
+    PLT_FOR_COLS(B, c) {  // the Stokes update is not linear (sqrt of the product of the two linear intensities): column by column
+        float4 &cL = colL(beam, c), &cL1 = colL1(beam, c);
+        const float4 Lx = .5f * (cL + cL1), Ly = .5f * (cL - cL1);
+        const float4 pr = Lx * Ly;
+        const float4 sq = mk4(sqrtf(pr.x), sqrtf(pr.y), sqrtf(pr.z), sqrtf(pr.w));
+        float4 nLx = sqr(ss) * Lx + sqr(ps) * Ly + (ss * ps) * t * sq;
+        float4 nLy = sqr(sp) * Lx + sqr(pp) * Ly + (sp * pp) * t * sq;
+        nLx = mk4(fmaxf(0.f, nLx.x), fmaxf(0.f, nLx.y), fmaxf(0.f, nLx.z), fmaxf(0.f, nLx.w));
+        nLy = mk4(fmaxf(0.f, nLy.x), fmaxf(0.f, nLy.y), fmaxf(0.f, nLy.z), fmaxf(0.f, nLy.w));
+        const float4 newL = nLx + nLy;
+        bool allOk = true, allFinite = true;
+        for (int j = 0; j < cx.hwss; ++j) {
+            const bool f = isfinite(lane(newL, j));
+            allFinite = allFinite && f;
+            allOk = allOk && (lane(cL, j) > 1e-6f && f);
+        }
+        const float4 norm = allOk ? newL / cL : mk4(0.f);
+        cL = allFinite ? newL : mk4(0.f);
+        cL1 = allFinite ? nLx - nLy : mk4(0.f);
+        colL2(beam, c) *= norm;
+        colL3(beam, c) *= norm;
     }
-    const float4 norm = allOk ? newL / beam.L : mk4(0.f);
-    beam.L = allFinite ? newL : mk4(0.f);
-    beam.L1 = allFinite ? nLx - nLy : mk4(0.f);
-    beam.L2 *= norm;
-    beam.L3 *= norm;
 }
-PLT_D void thinEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void thinEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     const float eta = m.f0 / 1.f;
     const float zz = toLight.z * toEye.z;
     const bool isReflection = zz > 0.0f;
@@ -644,7 +696,7 @@ PLT_D void thinEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, flo
     const bool inv = fmInvOneMinus(R, iR) && iR.a > 0;  // zero matrix on failure => iR[0][0] > 0 is false
     const FM M = isReflection ? (inv ? fmAdd(R, fmMul(fmMul(T, R), fmMul(iR, T))) : R) : (inv ? fmMul(T, fmMul(iR, T)) : fmMul(T, T));
     if (m.f2 > .0f && !isReflection) thinBirefringence(m, cx, beam, toLight, k);
-    for (int j = 0; j < beam.comps; ++j) beam.setSP(j, fmApply(M, beam.getSP(j)));
+    for (int j = 0; j < beam.comps; ++j) PLT_FOR_COLS(B, c) setSPc(beam, j, c, fmApply(M, getSPc(beam, j, c)));
 }
 PLT_D bool thinSample(const DevMaterial& m, float3 wi, Sample& s, Rng& sg, uint32_t lobeMask) {
     const bool hasReflection = (lobeMask & L_Reflection) != 0, hasTransmission = (lobeMask & L_Transmission) != 0;
@@ -659,7 +711,8 @@ PLT_D bool thinSample(const DevMaterial& m, float3 wi, Sample& s, Rng& sg, uint3
 }
 // =========================================================================== Coated (PLTCoatedConductorBSDF.slang:45-245, PLTCoatedOpaqueDielectricBSDF.slang:44-244)
 // f0 = coatIOR, f1 = tau, f2 = coatEta() (pre-evaluated), u0 = 1 for the conductor base
-PLT_D void coatedEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void coatedEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     const bool conductor = m.u0 != 0;
     const bool isReflection = toLight.z * toEye.z > 0.0f;
     const bool isScatter = (lobe & L_ScatterReflection) != 0, isDirect = (lobe & L_DeltaReflection) != 0;
@@ -692,32 +745,30 @@ PLT_D void coatedEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, f
             float2 rs, rp;
             const FM M2R = fmRConductor(LdotH, mk2(lane(iorN, j) / coatior, lane(iorK, j) / coatior), rs, rp);
             const FM M = fmMul(fmMul(MiT, M2R), MoT);
-            const float4 SP = beam.getSP(j);
-            float4 nSP = lane(m00, j) * fmApply(M, SP);
-            if (isScatter) nSP *= (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h);
-            else {
-                const float pS = sinf(dist * lane(k, j) * coatior + atan2f(rs.y, rs.x));
-                const float pP = sinf(dist * lane(k, j) * coatior + atan2f(rp.y, rp.x));
-                nSP = interfere(lane(a, j) * nSP, fmApply(MiR, SP), pS, pP, lane(mutual_coh, j));
+            const float ws = isScatter ? (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h) : 0.f;
+            const float pS = isScatter ? 0.f : sinf(dist * lane(k, j) * coatior + atan2f(rs.y, rs.x));
+            const float pP = isScatter ? 0.f : sinf(dist * lane(k, j) * coatior + atan2f(rp.y, rp.x));
+            PLT_FOR_COLS(B, c) {
+                const float4 SP = getSPc(beam, j, c);
+                float4 nSP = lane(m00, j) * fmApply(M, SP);
+                if (isScatter) nSP *= ws;
+                else nSP = interfere(lane(a, j) * nSP, fmApply(MiR, SP), pS, pP, lane(mutual_coh, j));
+                setSPc(beam, j, c, nSP);
             }
-            beam.setSP(j, nSP);
         }
     } else {
         const FM M = fmMul(MiT, MoT);
         for (int j = 0; j < beam.comps; ++j) {
             const float phase = sinf(dist * lane(k, j) * coatior);
-            const float4 SP = beam.getSP(j);
-            float4 nSP = lane(m00, j) * fmApply(M, SP);
-            float4 SPrefl;
-            if (isScatter) {
-                const float w = (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h);
+            const float w = isScatter ? (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h) : lane(a, j);
+            const FM Mr = fmDielectric(isScatter ? LdotH : toLight.z, eta1, true);
+            PLT_FOR_COLS(B, c) {
+                const float4 SP = getSPc(beam, j, c);
+                float4 nSP = lane(m00, j) * fmApply(M, SP);
                 nSP *= w;
-                SPrefl = w * fmApply(fmDielectric(LdotH, eta1, true), SP);
-            } else {
-                nSP *= lane(a, j);
-                SPrefl = lane(a, j) * fmApply(fmDielectric(toLight.z, eta1, true), SP);
+                const float4 SPrefl = w * fmApply(Mr, SP);
+                setSPc(beam, j, c, interfere(nSP, SPrefl, phase, phase, lane(mutual_coh, j)));
             }
-            beam.setSP(j, interfere(nSP, SPrefl, phase, phase, lane(mutual_coh, j)));
         }
     }
 }
@@ -871,7 +922,8 @@ PLT_D void decodeLobeType(uint32_t bsdfLobe, int& lx, int& ly) {
     ly = ((x >> 3) & 0x7) * (2 * ((x >> 7) & 0x1) - 1);
 }
 // =========================================================================== Grated (PLTDiffractionGrated{Conductor,OpaqueDielectric}BSDF.slang)
-PLT_D void gratedEval(const DevMaterial& m, const BsdfCtx& cx, const Grating& g, float3 toLight, float3 toEye, uint32_t bsdfLobe, Beam& beam) {
+template <class B>
+PLT_D void gratedEval(const DevMaterial& m, const BsdfCtx& cx, const Grating& g, float3 toLight, float3 toEye, uint32_t bsdfLobe, B& beam) {
     const bool conductor = m.type == PLTPT_MATERIAL_GRATED_CONDUCTOR;
     const bool isDirect = (bsdfLobe & L_Delta) != 0;
     const float4 lambdas = 1e-3f * beam.wl;
@@ -894,9 +946,13 @@ PLT_D void gratedEval(const DevMaterial& m, const BsdfCtx& cx, const Grating& g,
             const float lam = lane(lambdas, j);
             const float coh = j == 0 ? 1.f : beam.mutualCoherenceAngular(beam.toLocal(g.diffract(toEye, lx, ly, lam)), toLightBeam);
             const float w = lane(m00, j) * (1 - lane(a, j)) * coh * g.lobeIntensity(lx, ly, toLight, lam);
-            float4 SP = beam.getSP(j);
-            if (conductor) SP = fmApply(fmRConductor(toLight.z, mk2(lane(iorN, j) / m.extEta, lane(iorK, j) / m.extEta)), SP);
-            beam.setSP(j, w * SP);
+            FM M = {1.f, 0.f, 1.f, 0.f};
+            if (conductor) M = fmRConductor(toLight.z, mk2(lane(iorN, j) / m.extEta, lane(iorK, j) / m.extEta));
+            PLT_FOR_COLS(B, c) {
+                float4 SP = getSPc(beam, j, c);
+                if (conductor) SP = fmApply(M, SP);
+                setSPc(beam, j, c, w * SP);
+            }
         }
     } else beam.setZero();
 }
@@ -951,7 +1007,8 @@ PLT_D float4 gratedLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, const Grat
 }
 // =========================================================================== MultiLayeredStack (PLTMultiLayeredStackBSDF.slang:42-140)
 // f0/f1 = ior, f2/f3 = thickness, u0 = layers
-PLT_D void stackEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void stackEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_t lobe, B& beam) {
     if ((lobe & L_Delta) == 0 || !(toLight.z * toEye.z > .0f)) { beam.setZero(); return; }
     const float4 k = waveNumbers(beam.wl);
     const float4 m00 = rgbToSpectrum4(matC0(m), beam.wl);
@@ -976,7 +1033,7 @@ PLT_D void stackEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_
             G = cmul(G, mk2(cd, sd));
             G = cdiv(mk2(R + G.x, G.y), mk2(1.f + R * G.x, R * G.y));
         }
-        beam.setSP(j, sqr(G.x) * beam.getSP(j));
+        PLT_FOR_COLS(B, c) setSPc(beam, j, c, sqr(G.x) * getSPc(beam, j, c));
     }
 }
 
@@ -992,7 +1049,8 @@ PLT_D LocalFrame gratingFrame(const SD& sd, const Grating& g) {  // DiffractionG
 }
 
 // IMaterialInstance.eval: local-frame prologue/epilogue (e.g. PLTConductorBSDF.slang:179-196)
-PLT_D void bsdfEval(const DevMaterial& m, const BsdfCtx& cx, const SD& sd, float3 toEye, uint32_t lobe, Beam& beam) {
+template <class B>
+PLT_D void bsdfEval(const DevMaterial& m, const BsdfCtx& cx, const SD& sd, float3 toEye, uint32_t lobe, B& beam) {
     LocalFrame fr = {sd.T, sd.B, sd.N};
     Grating g;
     const bool grated = isGrated(m.type);
