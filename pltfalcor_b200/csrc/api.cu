@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kSweepThreads, PLT_MINB_SWEEP) k_bsdf_eval_mue
             }
             beam.propagate(sd.posW);
             bsdfEval(m, cx, sd, Wo, lobe, beam);
-            for (int j = 0; j < hwss; ++j) {
+            PLT_FOR_LAMBDA(j, hwss) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float4 SP = getSPc(beam, j, c);

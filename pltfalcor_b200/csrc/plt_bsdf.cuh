@@ -208,7 +208,7 @@ struct Beam {
         rx = 2 * sint * cost; ry = 1 - 2 * sqr(sint);
     }
     PLT_D void rotateStokes(float4& l1, float4& l2, float rx, float ry) const {
-        for (int j = 0; j < comps; ++j) {
+        PLT_FOR_LAMBDA(j, comps) {
             const float a = lane(l1, j), b = lane(l2, j);
             setLane(l1, j, rx * a + -ry * b);
             setLane(l2, j, ry * a + rx * b);
@@ -400,7 +400,7 @@ PLT_D void conductorEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight
     const float3 h = toLight + toEye;
     const float LdotH = fmaxf(.0f, dot(toLight, normalize(h)));
     const float4 iorN = evalSpectrum4(cx.profiles, m.etaN, beam.wl), iorK = evalSpectrum4(cx.profiles, m.etaK, beam.wl);
-    for (int j = 0; j < beam.comps; ++j) {
+    PLT_FOR_LAMBDA(j, beam.comps) {
         const float2 ior = mk2(lane(iorN, j) / m.extEta, lane(iorK, j) / m.extEta);
         const FM M = fmRConductor(isScatter ? LdotH : toLight.z, ior);
         const float w = isScatter ? (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h) : lane(a, j);
@@ -439,7 +439,7 @@ PLT_D float4 conductorLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, float3 
     const Fractal gfs = matFractal(m);
     const float4 k = waveNumbers(wl);
     float4 ret = mk4(0.f);
-    for (int j = 0; j < cx.hwss; ++j) setLane(ret, j, gfs.pdf(toEye, toLight, lane(k, j)));
+    PLT_FOR_LAMBDA(j, cx.hwss) setLane(ret, j, gfs.pdf(toEye, toLight, lane(k, j)));
     return ret;
 }
 // =========================================================================== OpaqueDielectric (PLTOpaqueDielectricBSDF.slang:43-147)
@@ -452,7 +452,7 @@ PLT_D void opaqueEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32
     const float a = gfs.alpha(toLight, toEye, kMeanK);
     float M = a;
     if (isScatter) M = (1 - a) * fabsf(toLight.z) * gfs.eval(kMeanK, toLight + toEye);
-    for (int j = 0; j < beam.comps; ++j) PLT_FOR_COLS(B, c) setSPc(beam, j, c, (M * lane(m00, j)) * getSPc(beam, j, c));
+    PLT_FOR_LAMBDA(j, beam.comps) PLT_FOR_COLS(B, c) setSPc(beam, j, c, (M * lane(m00, j)) * getSPc(beam, j, c));
 }
 // =========================================================================== Dielectric (PLTDielectricBSDF.slang:43-270)
 PLT_D float dielectricIor(const DevMaterial& m, float k) { return (m.f0 + m.f2 * sqr(k * k1_2Pi)) / m.f1; }
@@ -475,7 +475,7 @@ PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLigh
         const float LdotH = fmaxf(0.f, dot(toLight, normalize(h)));
         const M22 Q = beam.Q();
         const M22 invTheta = beam.invThetaK(1.f);
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             const float e = lane(eta, j);
             const float J = isReflection ? 1.f : sqr(toEye.z > .0f ? e : 1.f / e);
             const float D = gfs.eval(lane(k, j), invTheta, Q, h);
@@ -484,7 +484,7 @@ PLT_D void dielectricEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLigh
             PLT_FOR_COLS(B, c) setSPc(beam, j, c, w * fmApply(M1, getSPc(beam, j, c)));
         }
     } else {
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             const float e = lane(eta, j);
             const float J = isReflection ? 1.f : sqr(toEye.z > .0f ? e : 1.f / e);
             const FM M0 = fmDielectric(toLight.z, e, isReflection);
@@ -550,7 +550,7 @@ PLT_D float4 dielectricLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, float3
     if (isDirect && !isReflection) {
         const float3 toLightBeam = beam.toLocal(toLight);
         float4 ret = mk4(0.f);
-        for (int j = 0; j < cx.hwss; ++j) {
+        PLT_FOR_LAMBDA(j, cx.hwss) {
             if (j == 0) { ret.x = 1.f; continue; }
             const float e = dielectricIor(m, lane(k, j));
             float cosThetaT;
@@ -561,7 +561,7 @@ PLT_D float4 dielectricLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, float3
     }
     if (isScatter) {
         float4 ret = mk4(0.f);
-        for (int j = 0; j < cx.hwss; ++j) {
+        PLT_FOR_LAMBDA(j, cx.hwss) {
             const float3 wo = isReflection ? toLight : scattered_wo(toLight, dielectricIor(m, lane(k, j)));
             setLane(ret, j, gfs.pdf(toEye, wo, lane(k, j)));
         }
@@ -670,7 +670,7 @@ PLT_D void thinBirefringence(const DevMaterial& m, const BsdfCtx& cx, B& beam, f
         nLy = mk4(fmaxf(0.f, nLy.x), fmaxf(0.f, nLy.y), fmaxf(0.f, nLy.z), fmaxf(0.f, nLy.w));
         const float4 newL = nLx + nLy;
         bool allOk = true, allFinite = true;
-        for (int j = 0; j < cx.hwss; ++j) {
+        PLT_FOR_LAMBDA(j, cx.hwss) {
             const bool f = isfinite(lane(newL, j));
             allFinite = allFinite && f;
             allOk = allOk && (lane(cL, j) > 1e-6f && f);
@@ -696,7 +696,7 @@ PLT_D void thinEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, flo
     const bool inv = fmInvOneMinus(R, iR) && iR.a > 0;  // zero matrix on failure => iR[0][0] > 0 is false
     const FM M = isReflection ? (inv ? fmAdd(R, fmMul(fmMul(T, R), fmMul(iR, T))) : R) : (inv ? fmMul(T, fmMul(iR, T)) : fmMul(T, T));
     if (m.f2 > .0f && !isReflection) thinBirefringence(m, cx, beam, toLight, k);
-    for (int j = 0; j < beam.comps; ++j) PLT_FOR_COLS(B, c) setSPc(beam, j, c, fmApply(M, getSPc(beam, j, c)));
+    PLT_FOR_LAMBDA(j, beam.comps) PLT_FOR_COLS(B, c) setSPc(beam, j, c, fmApply(M, getSPc(beam, j, c)));
 }
 PLT_D bool thinSample(const DevMaterial& m, float3 wi, Sample& s, Rng& sg, uint32_t lobeMask) {
     const bool hasReflection = (lobeMask & L_Reflection) != 0, hasTransmission = (lobeMask & L_Transmission) != 0;
@@ -741,7 +741,7 @@ PLT_D void coatedEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, f
     if (conductor) {
         const float4 iorN = evalSpectrum4(cx.profiles, m.etaN, beam.wl), iorK = evalSpectrum4(cx.profiles, m.etaK, beam.wl);
         const FM MiR = fmDielectric(toLight.z, eta1, true);
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             float2 rs, rp;
             const FM M2R = fmRConductor(LdotH, mk2(lane(iorN, j) / coatior, lane(iorK, j) / coatior), rs, rp);
             const FM M = fmMul(fmMul(MiT, M2R), MoT);
@@ -758,7 +758,7 @@ PLT_D void coatedEval(const DevMaterial& m, const BsdfCtx& cx, float3 toLight, f
         }
     } else {
         const FM M = fmMul(MiT, MoT);
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             const float phase = sinf(dist * lane(k, j) * coatior);
             const float w = isScatter ? (1 - lane(a, j)) * fabsf(toLight.z) * gfs.eval(lane(k, j), h) : lane(a, j);
             const FM Mr = fmDielectric(isScatter ? LdotH : toLight.z, eta1, true);
@@ -828,7 +828,7 @@ PLT_D float4 coatedLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, float3 toL
     const Fractal gfs = matFractal(m);
     const float4 k = waveNumbers(wl);
     float4 ret = mk4(0.f);
-    for (int j = 0; j < cx.hwss; ++j) setLane(ret, j, gfs.pdf(wiIn, woIn, lane(k, j)));
+    PLT_FOR_LAMBDA(j, cx.hwss) setLane(ret, j, gfs.pdf(wiIn, woIn, lane(k, j)));
     return ret;
 }
 // =========================================================================== Diffraction grating (DiffractionGrating.slang:40-266)
@@ -933,7 +933,7 @@ PLT_D void gratedEval(const DevMaterial& m, const BsdfCtx& cx, const Grating& g,
     decodeLobeType(bsdfLobe, lx, ly);
     const float3 toLightBeam = beam.toLocal(toLight);
     bool anyPos = false, anyLt1 = false;
-    for (int j = 0; j < cx.hwss; ++j) { anyPos = anyPos || lane(a, j) > .0f; anyLt1 = anyLt1 || lane(a, j) < 1.f; }
+    PLT_FOR_LAMBDA(j, cx.hwss) { anyPos = anyPos || lane(a, j) > .0f; anyLt1 = anyLt1 || lane(a, j) < 1.f; }
     const bool lobeZero = lx == 0 && ly == 0;
     if (lobeZero && anyPos) {
         if (conductor) conductorEval(m, cx, toLight, toEye, bsdfLobe, beam); else opaqueEval(m, toLight, toEye, bsdfLobe, beam);
@@ -942,7 +942,7 @@ PLT_D void gratedEval(const DevMaterial& m, const BsdfCtx& cx, const Grating& g,
         const float4 m00 = rgbToSpectrum4(matC0(m), beam.wl);
         float4 iorN = mk4(0.f), iorK = mk4(0.f);
         if (conductor) { iorN = evalSpectrum4(cx.profiles, m.etaN, beam.wl); iorK = evalSpectrum4(cx.profiles, m.etaK, beam.wl); }
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             const float lam = lane(lambdas, j);
             const float coh = j == 0 ? 1.f : beam.mutualCoherenceAngular(beam.toLocal(g.diffract(toEye, lx, ly, lam)), toLightBeam);
             const float w = lane(m00, j) * (1 - lane(a, j)) * coh * g.lobeIntensity(lx, ly, toLight, lam);
@@ -995,11 +995,11 @@ PLT_D float4 gratedLambdaPdf(const DevMaterial& m, const BsdfCtx& cx, const Grat
     int lx, ly;
     decodeLobeType(bsdfLobe, lx, ly);
     bool anyLt1 = false;
-    for (int j = 0; j < cx.hwss; ++j) anyLt1 = anyLt1 || lane(a, j) < 1.f;
+    PLT_FOR_LAMBDA(j, cx.hwss) anyLt1 = anyLt1 || lane(a, j) < 1.f;
     if ((lx != 0 || ly != 0) && anyLt1 && isDirect) {
         const float3 toLightBeam = beam.toLocal(toLight);
         float4 ret = mk4(0.f);
-        for (int j = 0; j < cx.hwss; ++j)
+        PLT_FOR_LAMBDA(j, cx.hwss)
             setLane(ret, j, j == 0 ? 1.f : beam.mutualCoherenceAngular(beam.toLocal(g.diffract(toEye, lx, ly, lane(lambdas, j))), toLightBeam));
         return ret;
     }
@@ -1019,7 +1019,7 @@ PLT_D void stackEval(const DevMaterial& m, float3 toLight, float3 toEye, uint32_
     r1 = sqrtf(evalFresnelDielectric(eta2, ct1));
     ct0 = fabsf(ct0); ct1 = fabsf(ct1);
     const uint32_t layers = m.u0;
-    for (int j = 0; j < beam.comps; ++j) {
+    PLT_FOR_LAMBDA(j, beam.comps) {
         float2 G = mk2(sqrtf(lane(m00, j)), 0.f);
         for (uint32_t l = 0; l < layers; ++l) {
             const bool odd = (l & 1) != 0;

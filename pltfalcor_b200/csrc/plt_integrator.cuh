@@ -106,9 +106,8 @@ enum : uint32_t {
     QC_MneeTraceCursor = 80,                // [3] rotating fetch cursors of the trial-ray trace in k_mnee_walk
     QC_LevelCount = 96,                     // [maxBounces + 1 <= 64] entries of vertexList per bounce
     QC_TraceCount = QC_LevelCount + 64,     // entries of traceQueue (sample stage) / deferred entries of half B (solve stage)
-    QC_BinStart = 176,                      // [kQueueTypes + 1] first entry of every type bin in `sorted` (written by k_flip_queue for the replay queues)
 };
-static_assert(QC_SortedCount < QC_JobCount && QC_MneeTraceCursor + 3 <= QC_LevelCount && QC_TraceCount < QC_BinStart && QC_BinStart + kQueueTypes + 1 <= 256, "queueCount slots overlap");
+static_assert(QC_SortedCount < QC_JobCount && QC_MneeTraceCursor + 3 <= QC_LevelCount && QC_TraceCount < 256, "queueCount slots overlap");
 constexpr uint32_t kTraceCountSlot = 64;  // levelCount[kTraceCountSlot] == queueCount[QC_TraceCount]
 constexpr int kJobPlanes = 10;
 
@@ -703,7 +702,7 @@ PLT_D float4 measure(const FrameParams& P, int bounceIdx, float pathContribution
         float s, c;
         sincosf(P.polarizerTheta, &s, &c);
         const float a = 1.f - P.polarizer, h = .5f * P.polarizer;
-        for (int j = 0; j < beam.comps; ++j) {
+        PLT_FOR_LAMBDA(j, beam.comps) {
             const float4 SP = beam.getSP(j);
             // (1-p) I + p * MuellerPolarizer(theta), Mueller.slang linear polariser
             beam.setSP(j, mk4(a * SP.x + h * (SP.x + c * SP.y + s * SP.z), a * SP.y + h * (c * SP.x + c * c * SP.y + c * s * SP.z),
@@ -712,7 +711,7 @@ PLT_D float4 measure(const FrameParams& P, int bounceIdx, float pathContribution
     }
     if (P.opt.HWSSDoMIS) {
         float sum = 0.f;
-        for (int j = 0; j < int(P.opt.HWSS); ++j) sum += lane(beam.spdf, j);
+        PLT_FOR_LAMBDA(j, int(P.opt.HWSS)) sum += lane(beam.spdf, j);
         pathContribution *= sum > kFltEps ? beam.spdf.x / sum : .0f;
     } else pathContribution *= 1.f / float(beam.comps);
     const float3 Lrgb = vmax(mk3(.0f), spectrumToRgb(beam.L, beam.wl, beam.comps) * pathContribution);
@@ -1303,12 +1302,8 @@ struct alignas(16) UnwindItem { float4 job[kJobPlanes]; float4 vtx[4]; float4 di
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head) on its loaded
 // inputs: `v`, `materialID`, `d` = vertex record and bounce direction of the vertex the job evaluates next, `beam`, `h` = the job.
 // Returns true while the job has further vertices to go through.
-// kClass (compile-time knowledge of the material the job list was binned by): 0 = any, 1 = PLTDiffuse, 2 = anything but PLTDiffuse
-template <int kClass = 0>
 PLT_D bool unwindStepLoaded(const FrameParams& P, uint32_t id, const VertexData& v, uint32_t materialID, float4 d, Beam& beam, JobHeader& h, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
     const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-    if (kClass == 1) __builtin_assume(m.type == PLTPT_MATERIAL_DIFFUSE);
-    if (kClass == 2) __builtin_assume(m.type != PLTPT_MATERIAL_DIFFUSE);
     const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
     forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);

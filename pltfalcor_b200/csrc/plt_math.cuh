@@ -9,6 +9,18 @@
 #define PLT_HD __host__ __device__ __forceinline__
 #define PLT_D __device__ __forceinline__
 
+// Loops over the (at most four) wavelength samples of a generalized ray.  PLT_LAMBDA_UNROLL = 1 spells them as four unrolled iterations
+// guarded by the runtime count: lane indices become compile-time constants (no select chains for float4 components) and the four
+// wavelengths form independent instruction streams the scheduler can interleave; 0 keeps the plain runtime-bounded loop.
+#ifndef PLT_LAMBDA_UNROLL
+#define PLT_LAMBDA_UNROLL 0
+#endif
+#if PLT_LAMBDA_UNROLL
+#define PLT_FOR_LAMBDA(j, n) _Pragma("unroll") for (int j = 0; j < 4; ++j) if (j < int(n))
+#else
+#define PLT_FOR_LAMBDA(j, n) for (int j = 0; j < int(n); ++j)
+#endif
+
 namespace plt {
 
 constexpr float kPi = 3.14159265358979323846f;
@@ -324,7 +336,7 @@ PLT_D float3 XYZtoRGB_Rec709(float3 c) {
 }
 PLT_D float3 spectrumToRgb(float4 spectrum, float4 wavelengths, int samples) {
     float3 result = mk3(0.f);
-    for (int i = 0; i < samples; ++i) {
+    PLT_FOR_LAMBDA(i, samples) {
         const float l = lane(wavelengths, i);
         const float3 xyz = wavelengthToXYZ(l) * wavelengthToD65(l) * lane(spectrum, i);
         result += XYZtoRGB_Rec709(xyz);

@@ -58,20 +58,15 @@ __global__ void k_flip_queue(const __grid_constant__ FrameParams P, SortView vie
     uint32_t* qc = P.queueCount;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *view.dstCount = qc[QC_Total];
-        uint32_t run = 0;
-        for (int t = 0; t < kQueueTypes; ++t) { qc[QC_BinStart + t] = run; run += qc[QC_Hist + t]; }  // where every type bin starts in the sorted list
-        qc[QC_BinStart + kQueueTypes] = run;
         for (uint32_t t = QC_Hist; t < QC_SortedCount; ++t) qc[t] = 0;  // histogram, total, cursors
         if (resetTraceQueue) { P.levelCount[kTraceCountSlot] = 0; qc[QC_TraceCursor] = 0; }  // trace queue of the next bounce and the trace kernel's fetch cursor
     }
 }
 
-#ifndef PLT_UNWIND_SPLIT
-#define PLT_UNWIND_SPLIT 0
-#endif
-#ifndef PLT_MINB_UNWIND_DIFFUSE
-#define PLT_MINB_UNWIND_DIFFUSE 6
-#endif
+// (Round 2 also measured the step as four kernels specialised by {diffuse, other material} x {continues, ends in measure()}: the
+// diffuse kernels need 72-80 registers instead of 128, but the four launches per step with their tails cost more than the occupancy
+// gains when the kernels run alone -- 1.54 -> 1.83 ms on the Cornell box, 1.53 -> 3.58 ms on the ten-material city -- and only 2.8 % of
+// the frame time came back with two frames in flight; rejected, profiles/r2e_variants.log.)
 #ifndef PLT_UNWIND_STAGE
 #define PLT_UNWIND_STAGE 0  // measured on B200 (profiles/r2a_variants.log): 1.78 ms with the staging, 1.57 ms without -- left off
 #endif
@@ -129,36 +124,6 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_
     warpAdd(P.counters + 0, evals);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);
 }
-#elif PLT_UNWIND_SPLIT
-// The replay step specialised four ways -- {diffuse vertex, any other material} x {job continues, job ends in measure()} -- so that each
-// kernel carries only the code and the registers of its case (the job list is already sorted by exactly these bins).  A Cornell-box
-// frame replays three quarters of its jobs through diffuse walls, whose BSDF is a cosine and a colour.
-template <bool kFinishing, bool kDiffuse>
-__global__ void __launch_bounds__(kStageThreads, kDiffuse ? PLT_MINB_UNWIND_DIFFUSE : PLT_MINB_UNWIND_STEP) k_unwind_step_t(const __grid_constant__ FrameParams P) {
-    uint32_t evals = 0;
-    const uint32_t* start = P.queueCount + QC_BinStart;
-    const uint32_t stride = gridDim.x * kStageThreads;
-    for (uint32_t type = kDiffuse ? PLTPT_MATERIAL_DIFFUSE : 0u; type < (kDiffuse ? PLTPT_MATERIAL_DIFFUSE + 1u : kFinishingBin); ++type) {
-        if (!kDiffuse && type == PLTPT_MATERIAL_DIFFUSE) continue;
-        const uint32_t bin = type | (kFinishing ? kFinishingBin : 0u);
-        const uint32_t b0 = start[bin], b1 = start[bin + 1];
-        for (uint32_t i = b0 + blockIdx.x * kStageThreads + threadIdx.x; i < b1; i += stride) {
-            const uint32_t id = P.sorted[i], aux = P.sortedAux[i];
-            const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
-            uint32_t materialID;
-            const VertexData v = readVertexCache(P, pixel, int(q), materialID);
-            const float4 d = P.bDir[size_t(q) * P.pixelCount + pixel];
-            Beam beam;
-            JobHeader h;
-            loadJob(P, id, beam, h);
-            __builtin_assume(kFinishing ? h.q == 0u : h.q != 0u);
-            uint32_t nextType = 0, nextAux = 0;
-            if (unwindStepLoaded<kDiffuse ? 1 : 2>(P, id, v, materialID, d, beam, h, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
-        }
-    }
-    warpAdd(P.counters + 0, evals);
-    if (kFinishing && kDiffuse && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 7, (unsigned long long)P.queueCount[QC_SortedCount]);
-}
 #else
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[QC_SortedCount];
@@ -201,15 +166,6 @@ void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint
     k_sort_queue<<<grid, kSortThreads, 0, s>>>(P, v);
     k_flip_queue<<<1, 32, 0, s>>>(P, v, resetTraceQueue);
 }
-#if PLT_UNWIND_SPLIT && !PLT_UNWIND_STAGE
-void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) {
-    k_unwind_step_t<false, true><<<grid, kStageThreads, 0, s>>>(P);
-    k_unwind_step_t<false, false><<<grid, kStageThreads, 0, s>>>(P);
-    k_unwind_step_t<true, true><<<grid, kStageThreads, 0, s>>>(P);
-    k_unwind_step_t<true, false><<<grid, kStageThreads, 0, s>>>(P);
-}
-#else
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_unwind_step<<<grid, kStageThreads, 0, s>>>(P); }
-#endif
 void launchResolve(const FrameParams& P, cudaStream_t s) { k_resolve<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
 }  // namespace plt

@@ -19,10 +19,6 @@ VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their outcomes are listed in DESIGN.md section 3
     "base": {},
     "stage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=1"]},                          # k_unwind_step with cp.async staging of the thread's next item
-    "split": {"stage_unwind.cu": ["-DPLT_UNWIND_SPLIT=1"]},                          # replay step as four kernels: {diffuse, other} x {continues, ends in measure()}
-    "split8": {"stage_unwind.cu": ["-DPLT_UNWIND_SPLIT=1", "-DPLT_MINB_UNWIND_DIFFUSE=8"]},   # ... diffuse kernels capped at 64 registers
-    "sweep2": {"api.cu": ["-DPLT_MINB_SWEEP=2"]},                                    # BSDF sweep kernel at <= 255 registers (Beam4 carries 64 registers of Stokes data)
-    "sweep3": {"api.cu": ["-DPLT_MINB_SWEEP=3"]},                                    # ... at <= 168 registers
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
@@ -35,6 +31,8 @@ def build_variant(name, flags):
     def one(src):
         obj = os.path.join(d, src.replace(".cu", ".o"))
         extra = flags.get(src, [])
+        if extra:
+            extra = B.SOURCE_FLAGS.get(src, []) + extra   # (a later -D of the same macro wins)
         base = [f for f in B.NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in extra)]
         if not extra:  # unchanged source: reuse the product object when it is fresh
             prod = os.path.join(B._HERE, "build", src.replace(".cu", ".o"))
