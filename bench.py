@@ -297,6 +297,8 @@ def main():
     W, K = max(args.warmup, 3), args.steps
     WIDTH, HEIGHT = CONFIGS[args.config][1:3]
     F = args.frames_per_step or CONFIGS[args.config][3]
+    if args.scaling == "strong":
+        F = -(-F // world) * world   # a step's frames split evenly over the ranks (a 2-frame step over 8 GPUs would leave six of them idle)
     hbm_peak, peak_src = peaks()
 
     buffers, cam = build_scene(args.config)
