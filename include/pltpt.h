@@ -144,7 +144,7 @@ typedef struct PltptMaterialBlob {
     float    displacementScale;
     float    displacementOffset;
     uint32_t texBaseColor, texSpecular, texEmissive, texNormalMap;
-    uint32_t texTransmission, texDisplacementMap, texData1, texData2; /* TextureHandle: mode = bits [29,31); only Uniform (0) supported */
+    uint32_t texTransmission, texDisplacementMap, texData1, texData2; /* TextureHandle (Scene/Material/TextureHandle.slang:42-89): textureID = bits [0,29), mode = bits [29,31) (0 Uniform, 1 Texture), udim = bit 31 (rejected) */
     uint32_t _pad1;
 } PltptMaterialBlob;
 #define PLTPT_NO_SPECTRAL_PROFILE 0xffffffffu
@@ -260,6 +260,32 @@ typedef struct PltptBounce {
     float    lastNonDeltaPdf;
 } PltptBounce;
 
+/* One material texture: mip level 0 only (the pass samples at explicit LOD 0), linear layout, row 0 = v 0, row pitch = width * texel size.
+ * Formats: the uncompressed ones a Falcor TextureManager hands out for PLT material parameters. */
+enum {
+    PLTPT_TEXTURE_FORMAT_RGBA32_FLOAT = 0,
+    PLTPT_TEXTURE_FORMAT_RGBA8_UNORM = 1,
+    PLTPT_TEXTURE_FORMAT_RGBA8_UNORM_SRGB = 2, /* rgb decoded to linear before filtering, alpha linear (D3D12 sRGB view) */
+    PLTPT_TEXTURE_FORMAT_RGBA16_FLOAT = 3,
+    PLTPT_TEXTURE_FORMAT_COUNT = 4,
+};
+typedef struct PltptTextureDesc {
+    const void* texels;
+    uint32_t width, height;
+    uint32_t format;
+    uint32_t _pad;
+} PltptTextureDesc;
+/* Sampler state (Core/API/Sampler.h:50-66): magnification filter 0 = Point, 1 = Linear; address modes 0 Wrap, 1 Mirror, 2 Clamp,
+ * 3 Border, 4 MirrorOnce.  Bilinear weights are exact fp32 (the texture unit's 8-bit fixed-point weights are not reproduced). */
+enum { PLTPT_FILTER_POINT = 0, PLTPT_FILTER_LINEAR = 1 };
+enum { PLTPT_ADDRESS_WRAP = 0, PLTPT_ADDRESS_MIRROR = 1, PLTPT_ADDRESS_CLAMP = 2, PLTPT_ADDRESS_BORDER = 3, PLTPT_ADDRESS_MIRROR_ONCE = 4 };
+typedef struct PltptSamplerDesc {
+    uint32_t magFilter, addressU, addressV, _pad;
+    float borderColor[4];
+} PltptSamplerDesc;
+/* BasicMaterialData::flags (BasicMaterialData.slang:102-126): NormalMapType = bits [1,3) (0 None, 1 RGB, 2 RG);
+ * MaterialHeader packedData.y (MaterialData.slang:48-67,118-122): default texture sampler ID = bits [17,25). */
+
 /* Scene description: the subset of `gScene` + light-sampler data the pass reads.
  * If pointersAreDevice != 0 all pointers are CUDA device pointers (the Falcor interop case:
  * Resource::getSharedApiHandle -> cudaImportExternalMemory); otherwise they are host pointers.
@@ -292,6 +318,13 @@ typedef struct PltptSceneDesc {
      * (replaces EnvMapSampler::createImportanceMap, EnvMapSampler.cpp:82-121: 512x512 texels, 64 samples per texel). */
     const float*                 envMapTexels;        uint32_t envMapWidth, envMapHeight;
     PltptEnvMapData              envMap;
+    /* Material textures and samplers (MaterialSystem.slang:283-291: `materialTextures[handle.getTextureID()]` sampled with
+     * `materialSamplers[header.getDefaultTextureSamplerID()]` at explicit LOD 0, pltpt_sample.rt.slang:76, pltpt_solve.rt.slang:53).
+     * The two descriptor arrays are always HOST pointers; every `texels` pointer is host or device like the other scene buffers.
+     * textureCount == 0: every TextureHandle must be Uniform.  samplerCount == 0: the material system's default sampler
+     * (linear filter, wrap addressing; MaterialSystem.cpp:76-79) is used for every material. */
+    const PltptTextureDesc*      textures;            uint32_t textureCount;
+    const PltptSamplerDesc*      samplers;            uint32_t samplerCount;
 } PltptSceneDesc;
 
 /* ------------------------------------------------------------------------------------------
@@ -439,6 +472,13 @@ PLTPT_API int pltpt_update_transforms(PltptHandle h, const float* worldMatrices,
  * ---------------------------------------------------------------------------------------- */
 PLTPT_API int pltpt_envmap_eval(PltptHandle h, uint32_t n, const float* dirs, float* rgbPdf, void* stream);
 PLTPT_API int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Material-texture query (parity check of MaterialSystem::sampleTexture at LOD 0, MaterialSystem.slang:283-291): n texture
+ * coordinates float2 -> float4 texture values through TextureHandle `handle` (Uniform handle: `uniformValue`) and sampler
+ * `samplerID` (>= samplerCount: the default linear / wrap sampler).  Device pointers.
+ * ---------------------------------------------------------------------------------------- */
+PLTPT_API int pltpt_texture_sample(PltptHandle h, uint32_t handle, uint32_t samplerID, const float uniformValue[4], uint32_t n, const float* uv, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Ray queries against the scene BVH (replaces TraceRay, pltpt_sample.rt.slang:174-183,

@@ -104,6 +104,13 @@ class OracleScene:
         lib().oracle_envmap_sample(self.h, C.c_uint32(len(rnd)), _p(rnd), _p(out))
         return out
 
+    def texture_sample(self, handle, sampler_id, uv, uniform=(0, 0, 0, 0)):
+        uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros((len(uv), 4), np.float32)
+        u = np.asarray(uniform, np.float32)
+        lib().oracle_texture_sample(self.h, C.c_uint32(handle), C.c_uint32(sampler_id), _p(u), C.c_uint32(len(uv)), _p(uv), _p(out))
+        return out
+
     def envmap_importance(self):
         out = np.zeros((512, 512), np.float32)
         lib().oracle_envmap_importance(self.h, _p(out))

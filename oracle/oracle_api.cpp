@@ -242,6 +242,15 @@ void oracle_envmap_importance(void* sp, float* out) {
     std::memcpy(out, sc.env.mips[0].data(), sc.env.mips[0].size() * sizeof(float));
 }
 
+// material-texture filter (plt_bsdf.h TextureSystem::sampleTexture): uv float2 -> float4
+void oracle_texture_sample(void* sp, uint32_t handle, uint32_t samplerID, const float uniformValue[4], uint32_t n, const float* uv, float* out) {
+    const Scene& sc = *(Scene*)sp;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float4 c = sc.textures.sampleTexture(handle, samplerID, float2(uv[2 * i], uv[2 * i + 1]), float4(uniformValue[0], uniformValue[1], uniformValue[2], uniformValue[3]));
+        out[4 * i] = c.x; out[4 * i + 1] = c.y; out[4 * i + 2] = c.z; out[4 * i + 3] = c.w;
+    }
+}
+
 void oracle_colour_map(int which, uint32_t n, const float* vals, float* out) {  // 0 = ccMagma, 1 = ccInferno (plt_debug.h)
     for (uint32_t i = 0; i < n; ++i) { const float3 c = which == 0 ? ccMagma(vals[i]) : ccInferno(vals[i]); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }

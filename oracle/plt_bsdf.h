@@ -1171,6 +1171,73 @@ struct MultiLayeredStackBxDF {  // PLTMultiLayeredStackBSDF.slang:42-140
 // ---------------------------------------------------------------------------------------------
 inline float h2f(uint16_t h) { return f16tof32(h); }
 
+// ---------------------------------------------------------------------------------------------
+// Material textures: MaterialSystem.slang:283-291 (sampleTexture: Uniform handle -> the uniform value, Texture handle ->
+// materialTextures[id].SampleLevel(sampler, uv, lod)) with the explicit LOD 0 every PLTPT call site passes
+// (pltpt_sample.rt.slang:76, pltpt_solve.rt.slang:53,229,433, Manifolds.slangh:128,213).  The texture unit is hardware in the
+// reference; the oracle DEFINES the filter the CUDA path must reproduce: D3D texel addressing (texel centres at (i + .5) / size),
+// sRGB decode per texel before filtering, bilinear weights in exact fp32 (not the unit's 8-bit fixed point), address modes of
+// Core/API/Sampler.h:59-66.
+// ---------------------------------------------------------------------------------------------
+struct TextureSystem {
+    const PltptTextureDesc* textures = nullptr;
+    uint32_t textureCount = 0;
+    const PltptSamplerDesc* samplers = nullptr;
+    uint32_t samplerCount = 0;
+
+    static uint32_t handleMode(uint32_t h) { return (h >> 29) & 3u; }       // TextureHandle.slang:54-67
+    static uint32_t handleTextureID(uint32_t h) { return h & 0x1fffffffu; }  // :75
+    static uint32_t samplerIDOf(const PltptMaterialBlob& m) { return (m.header[1] >> 17) & 0xffu; }  // MaterialData.slang:66,122
+    static uint32_t normalMapTypeOf(const PltptMaterialBlob& m) { return (m.flags >> 1) & 3u; }        // BasicMaterialData.slang:106,126
+
+    static float srgbToLinear(float c) { return c <= 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f); }
+    static float4 fetch(const PltptTextureDesc& t, int x, int y) {
+        const size_t i = size_t(y) * t.width + size_t(x);
+        switch (t.format) {
+            case PLTPT_TEXTURE_FORMAT_RGBA32_FLOAT: { const float* p = (const float*)t.texels + 4 * i; return float4(p[0], p[1], p[2], p[3]); }
+            case PLTPT_TEXTURE_FORMAT_RGBA16_FLOAT: { const uint16_t* p = (const uint16_t*)t.texels + 4 * i; return float4(f16tof32(p[0]), f16tof32(p[1]), f16tof32(p[2]), f16tof32(p[3])); }
+            case PLTPT_TEXTURE_FORMAT_RGBA8_UNORM: { const uint8_t* p = (const uint8_t*)t.texels + 4 * i; return float4(p[0] / 255.f, p[1] / 255.f, p[2] / 255.f, p[3] / 255.f); }
+            case PLTPT_TEXTURE_FORMAT_RGBA8_UNORM_SRGB: {
+                const uint8_t* p = (const uint8_t*)t.texels + 4 * i;
+                return float4(srgbToLinear(p[0] / 255.f), srgbToLinear(p[1] / 255.f), srgbToLinear(p[2] / 255.f), p[3] / 255.f);
+            }
+            default: return float4(0.f);
+        }
+    }
+    // texel index under an address mode; false = outside (Border)
+    static bool address(int& i, int n, uint32_t mode) {
+        switch (mode) {
+            case PLTPT_ADDRESS_WRAP: i %= n; if (i < 0) i += n; return true;
+            case PLTPT_ADDRESS_MIRROR: { int p = i % (2 * n); if (p < 0) p += 2 * n; i = p < n ? p : 2 * n - 1 - p; return true; }
+            case PLTPT_ADDRESS_CLAMP: i = i < 0 ? 0 : (i >= n ? n - 1 : i); return true;
+            case PLTPT_ADDRESS_MIRROR_ONCE: if (i < 0) i = -1 - i; i = i >= n ? n - 1 : i; return true;
+            default: return i >= 0 && i < n;  // Border
+        }
+    }
+    float4 texel(const PltptTextureDesc& t, const PltptSamplerDesc& s, int x, int y) const {
+        if (!address(x, int(t.width), s.addressU) || !address(y, int(t.height), s.addressV)) return float4(s.borderColor[0], s.borderColor[1], s.borderColor[2], s.borderColor[3]);
+        return fetch(t, x, y);
+    }
+    float4 sampleLevel0(const PltptTextureDesc& t, const PltptSamplerDesc& s, float2 uv) const {
+        if (s.magFilter == PLTPT_FILTER_POINT) return texel(t, s, int(std::floor(uv.x * float(t.width))), int(std::floor(uv.y * float(t.height))));
+        const float x = uv.x * float(t.width) - .5f, y = uv.y * float(t.height) - .5f;
+        const float x0 = std::floor(x), y0 = std::floor(y);
+        const float fx = x - x0, fy = y - y0;
+        const int ix = int(x0), iy = int(y0);
+        const float4 c00 = texel(t, s, ix, iy), c10 = texel(t, s, ix + 1, iy), c01 = texel(t, s, ix, iy + 1), c11 = texel(t, s, ix + 1, iy + 1);
+        const float4 top = c00 * (1.f - fx) + c10 * fx, bottom = c01 * (1.f - fx) + c11 * fx;
+        return top * (1.f - fy) + bottom * fy;
+    }
+    // ms.sampleTexture(handle, s, uv, uniformValue, lod) with the material's default sampler
+    float4 sampleTexture(uint32_t handle, uint32_t samplerID, float2 uv, float4 uniformValue) const {
+        if (handleMode(handle) == 0) return uniformValue;                              // Mode::Uniform
+        if (handleMode(handle) != 1 || handleTextureID(handle) >= textureCount) return float4(0.f);  // default: float4(0)
+        PltptSamplerDesc def{};                                                          // MaterialSystem.cpp:76-79: linear, wrap
+        def.magFilter = PLTPT_FILTER_LINEAR;
+        return sampleLevel0(textures[handleTextureID(handle)], samplerID < samplerCount ? samplers[samplerID] : def, uv);
+    }
+};
+
 struct MaterialInstance {
     uint32_t type = 0;
     DiffuseBxDF diffuse;
@@ -1187,8 +1254,8 @@ struct MaterialInstance {
 
     static uint32_t materialType(const PltptMaterialBlob& m) { return m.header[0] & 0xffffu; }
     // evalOpacity of each *Material.slang (Dielectric/ThinDielectric halve it; coated return 1)
-    static float evalOpacity(const PltptMaterialBlob& m) {
-        const float a = h2f(m.baseColor[3]);
+    static float evalOpacity(const PltptMaterialBlob& m, const TextureSystem& tex, float2 uv) {
+        const float a = tex.sampleTexture(m.texBaseColor, TextureSystem::samplerIDOf(m), uv, float4(h2f(m.baseColor[0]), h2f(m.baseColor[1]), h2f(m.baseColor[2]), h2f(m.baseColor[3]))).w;
         switch (materialType(m)) {
             case PLTPT_MATERIAL_DIELECTRIC: case PLTPT_MATERIAL_THIN_DIELECTRIC: return .5f * a;
             case PLTPT_MATERIAL_COATED_CONDUCTOR: case PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC: return 1.f;
@@ -1196,19 +1263,21 @@ struct MaterialInstance {
         }
     }
     MaterialInstance() = default;
-    MaterialInstance(const PltptMaterialBlob& m, const ShadingData& sd, const ProfileTable* profiles) : prof(profiles) {
+    MaterialInstance(const PltptMaterialBlob& m, const ShadingData& sd, const ProfileTable* profiles, const TextureSystem& tex) : prof(profiles) {
         type = materialType(m);
-        const float4 base(h2f(m.baseColor[0]), h2f(m.baseColor[1]), h2f(m.baseColor[2]), h2f(m.baseColor[3]));
-        const float4 spec(h2f(m.specular[0]), h2f(m.specular[1]), h2f(m.specular[2]), h2f(m.specular[3]));
-        const float4 data1(h2f(m.data1[0]), h2f(m.data1[1]), h2f(m.data1[2]), h2f(m.data1[3]));
-        const float4 data2(h2f(m.data2[0]), h2f(m.data2[1]), h2f(m.data2[2]), h2f(m.data2[3]));
-        const float3 tran(h2f(m.transmission[0]), h2f(m.transmission[1]), h2f(m.transmission[2]));
+        // every *Material.slang::setupMaterialInstance samples its parameter slots at sd.uv with the material's default sampler
+        const uint32_t smp = TextureSystem::samplerIDOf(m);
+        const float4 base = tex.sampleTexture(m.texBaseColor, smp, sd.uv, float4(h2f(m.baseColor[0]), h2f(m.baseColor[1]), h2f(m.baseColor[2]), h2f(m.baseColor[3])));
+        const float4 spec = tex.sampleTexture(m.texSpecular, smp, sd.uv, float4(h2f(m.specular[0]), h2f(m.specular[1]), h2f(m.specular[2]), h2f(m.specular[3])));
+        const float4 data1 = tex.sampleTexture(m.texData1, smp, sd.uv, float4(h2f(m.data1[0]), h2f(m.data1[1]), h2f(m.data1[2]), h2f(m.data1[3])));
+        const float4 data2 = tex.sampleTexture(m.texData2, smp, sd.uv, float4(h2f(m.data2[0]), h2f(m.data2[1]), h2f(m.data2[2]), h2f(m.data2[3])));
+        const float3 tran = tex.sampleTexture(m.texTransmission, smp, sd.uv, float4(h2f(m.transmission[0]), h2f(m.transmission[1]), h2f(m.transmission[2]), 1.f)).xyz();
         const float IoR = h2f(m.IoR);
         switch (type) {
             case PLTPT_MATERIAL_DIFFUSE:  // PLTDiffuseMaterial.slang:40-50
                 diffuse.albedo = base.xyz();
                 emissionSpectralId = m.emissionSpectralId;
-                emissionRGB = float3(1.f);
+                emissionRGB = tex.sampleTexture(m.texEmissive, smp, sd.uv, float4(1.f)).xyz();
                 break;
             case PLTPT_MATERIAL_CONDUCTOR:  // PLTConductorMaterial.slang:40-57
                 conductor.specular = base.xyz();

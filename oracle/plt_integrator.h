@@ -243,11 +243,11 @@ struct Integrator {
         return t;
     }
     // EmissiveLightSamplerHelpers.slang:56-74 — Le / sampledWavelengths are outputs, the bool result is unused
-    void materialEvalEmissive(uint32_t materialID, float wavelength, bool importanceSample, SampleGenerator& sg, hwss_t& Le, hwss_t& sampledWavelengths) const {
+    void materialEvalEmissive(uint32_t materialID, float2 uv, float wavelength, bool importanceSample, SampleGenerator& sg, hwss_t& Le, hwss_t& sampledWavelengths) const {
         const PltptMaterialBlob& md = scene->d.materialData[materialID];
         const bool isBasic = (md.header[0] >> 31) & 1u;
         if (isBasic && md.emissionSpectralId != PLTPT_NO_SPECTRAL_PROFILE) {
-            const float3 emissionRGB(1.f);
+            const float3 emissionRGB = scene->textures.sampleTexture(md.texEmissive, TextureSystem::samplerIDOf(md), uv, float4(1.f)).xyz();  // :68
             Le = scene->profiles.sampleSpectrum(md.emissionSpectralId, wavelength, sg, importanceSample, sampledWavelengths);
             Le *= SpectrumUtils::rgbToSpectrum(emissionRGB, sampledWavelengths);
         }
@@ -269,7 +269,8 @@ struct Integrator {
         float cosTheta = dot(ls.normalW, -ls.dir);
         if (cosTheta <= 0.f) return false;
         ls.Le = hwss_t(.0f);
-        materialEvalEmissive(tri.materialID, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
+        const float2 uv = tri.texCoords[0] * b[0] + tri.texCoords[1] * b[1] + tri.texCoords[2] * b[2];  // EmissiveTriangle::getTexCoord, LightCollectionShared.slang
+        materialEvalEmissive(tri.materialID, uv, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
         float denom = hlsl_max(FLT_MINf, cosTheta * tri.area);
         ls.pdf = distSqr / denom;
         return true;

@@ -43,6 +43,7 @@ struct RayHit { float t = 0; TriangleHit hit; };
 struct Scene {
     PltptSceneDesc d{};
     ProfileTable profiles;
+    TextureSystem textures;
     EnvMap env;
     // derived
     std::vector<uint32_t> instTriOffset;  // first global triangle of each instance
@@ -57,6 +58,8 @@ struct Scene {
         d = desc;
         profiles.profiles = d.spectralProfiles;
         profiles.count = d.profileCount;
+        textures.textures = d.textures; textures.textureCount = d.textureCount;
+        textures.samplers = d.samplers; textures.samplerCount = d.samplerCount;
         instTriOffset.assign(d.instanceCount + 1, 0);
         for (uint32_t i = 0; i < d.instanceCount; ++i) {
             const PltptMeshDesc& m = d.meshes[d.geometryInstances[i].geometryID];
@@ -155,8 +158,7 @@ struct Scene {
     }
     uint32_t getMaterialID(uint32_t instanceID) const { return d.geometryInstances[instanceID].materialID; }
 
-    // MaterialFactory.slang:79-131 (prepareShadingData) + ShadingUtils.slang:126-152 (orthonormalizeSafe);
-    // textures / normal maps are out of scope (Uniform handles only), so modifyTangentSpace is the identity.
+    // MaterialFactory.slang:79-131 (prepareShadingData) + ShadingUtils.slang:126-152 (orthonormalizeSafe), :199-246 (normal mapping)
     ShadingData prepareShadingData(const VertexData& v, uint32_t materialID, float3 viewDir) const {
         ShadingData sd;
         sd.posW = v.posW;
@@ -182,11 +184,32 @@ struct Scene {
         sd.mtlHeader[0] = m.header[0];
         sd.mtlHeader[1] = m.header[1];
         sd.materialID = materialID;
-        sd.opacity = MaterialInstance::evalOpacity(m);
+        sd.opacity = MaterialInstance::evalOpacity(m, textures, v.texC);
+        if (valid) {  // material.modifyTangentSpace (every PLT material: sample texNormalMap, applyNormalMap), only with a valid tangent space
+            const float3 encodedNormal = textures.sampleTexture(m.texNormalMap, TextureSystem::samplerIDOf(m), sd.uv, float4(0.f)).xyz();
+            applyNormalMap(sd, TextureSystem::normalMapTypeOf(m), encodedNormal);
+        }
         if (!sd.frontFacing && sd.isDoubleSided()) sd.N = -sd.N;
         return sd;
     }
-    MaterialInstance getMaterialInstance(const ShadingData& sd) const { return MaterialInstance(d.materialData[sd.materialID], sd, &profiles); }
+    // ShadingUtils.slang:199-246: applyNormalMap / computeShadingFrameFromNormalMap, ShadingFrame(N, tangentW) -> orthonormalizeSafe (:126-152)
+    static void applyNormalMap(ShadingData& sd, uint32_t type, float3 encodedNormal) {
+        float3 mapN;
+        if (type == 1) mapN = encodedNormal * 2.f - float3(1.f);                 // NormalMapType::RGB, rgbToNormal
+        else if (type == 2) {                                                    // NormalMapType::RG, rgToNormal
+            const float2 rg(encodedNormal.x, encodedNormal.y);
+            mapN = float3(rg.x * 2.f - 1.f, rg.y * 2.f - 1.f, 0.f);
+            mapN.z = std::sqrt(1.f - hlsl_min(hlsl_max(dot(rg, rg), 0.f), 1.f));
+        } else return;                                                           // NormalMapType::None: ShadingFrame(sd) unchanged
+        const float3 n = sd.T * mapN.x + sd.B * mapN.y + sd.N * mapN.z;
+        // ShadingFrame(n, sd.tangentW) (ShadingUtils.slang:61-65): N = normalize(n), then the UNCHECKED orthonormalize (:112-116) --
+        // a perturbed normal parallel to the tangent is the asset's problem there (:236-238) and stays so here
+        sd.N = normalize(n);
+        const float3 tw = sd.tangentW.xyz();
+        sd.T = normalize(tw - sd.N * dot(tw, sd.N));
+        sd.B = cross(sd.N, sd.T) * sd.tangentW.w;
+    }
+    MaterialInstance getMaterialInstance(const ShadingData& sd) const { return MaterialInstance(d.materialData[sd.materialID], sd, &profiles, textures); }
 
     // HitInfo.slang:459-487 / 96-130 (uncompressed 128-bit format, Triangle type = 1)
     void packHit(const TriangleHit& h, uint32_t out[4]) const {

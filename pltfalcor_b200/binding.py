@@ -8,6 +8,8 @@ import numpy as np
 from . import layouts as L
 from .build import LIB
 
+LIB = os.environ.get("PLTPT_LIB") or LIB  # development: a variant built by tools/variants.py
+
 _lib = None
 
 # every symbol include/pltpt.h declares (tests check that the library exports all of them)
@@ -19,6 +21,7 @@ EXPORTS = [
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
     "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
     "pltpt_render_accumulate_rows", "pltpt_resolve_accumulated", "pltpt_render_accumulate_host", "pltpt_render_accumulate_multi",
+    "pltpt_texture_sample",
 ]
 
 
@@ -71,6 +74,7 @@ def lib():
         _lib.pltpt_get_light_collection.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
+        _lib.pltpt_texture_sample.argtypes = [vp, u32, u32, vp, u32, vp, vp, vp]
     return _lib
 
 
@@ -262,6 +266,11 @@ class Pltpt:
     def envmap_sample(self, rnd, out, stream=None):
         """rnd: (n,2) in [0,1); out: (n,8) {dir xyz, pdf, Le rgb, 0}."""
         _check(lib().pltpt_envmap_sample(self.h, rnd.shape[0], _dp(rnd), _dp(out), stream))
+
+    def texture_sample(self, handle, sampler_id, uv, out, uniform=(0.0, 0.0, 0.0, 0.0), stream=None):
+        """uv: (n,2); out: (n,4) — torch CUDA float32 tensors; `handle` is a TextureHandle word (mode << 29 | textureID)."""
+        u = (C.c_float * 4)(*[float(x) for x in uniform])
+        _check(lib().pltpt_texture_sample(self.h, handle, sampler_id, C.cast(u, C.c_void_p), uv.shape[0], _dp(uv), _dp(out), stream))
 
     # ---- BSDF sweeps ------------------------------------------------------------------------------------------
     def bsdf_eval_mueller(self, material_id, lobe, wi, wo, hero, out, stream=None):

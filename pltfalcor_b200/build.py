@@ -11,7 +11,14 @@ SOURCES = ["api.cu", "bvh.cu", "integrator.cu", "stage_sample.cu", "stage_connec
 # per-source flags.  api.cu holds the BSDF sweep kernel: there the wavelength loops are unrolled (PLT_FOR_LAMBDA, plt_math.cuh) -- the four
 # Stokes columns of its beam stay in registers and the sweep runs 1.45x faster; in the rendering kernels the same unrolling costs
 # 6 % on the replay step (profiles/r2f_variants.log), so they keep the runtime-bounded loops.
-SOURCE_FLAGS = {"api.cu": ["-DPLT_LAMBDA_UNROLL=1"]}
+# stage_unwind.cu (the forward replay) evaluates BSDFs along paths that are already fixed: nothing it computes feeds a ray or a branch of
+# the path, so it is held to the 1e-4 BSDF tolerance, not to the operation-by-operation rounding the other stages keep for identical
+# paths.  There division and square root are the MUFU approximations (<= 2 ulp), FMAs are contracted, and PLT_FAST_MATH selects the
+# rsqrt / exp2-log2 / rotation-without-atan2 forms in plt_math.cuh and plt_bsdf.cuh: k_unwind_step 1.54 -> 1.08 ms per Cornell frame with
+# every parity figure unchanged (profiles/r2h_variants.log, r2i_variants.log).  The same flags on stage_connect.cu move light-sampling
+# decisions and were rejected (profiles/r2h_variants.log: fm_uc).
+SOURCE_FLAGS = {"api.cu": ["-DPLT_LAMBDA_UNROLL=1"],
+                "stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
@@ -50,7 +57,8 @@ def build(force=False, verbose=False):
         deps = _deps()
         if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, *SOURCE_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = SOURCE_FLAGS.get(src, [])
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in extra)], *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -151,134 +151,25 @@ float hostFresnelConductor(float n, float k) {  // evalFresnelConductor(eta, 1) 
     const std::complex<float> rs = (one - eta * t) / (one + eta * t), rp = (eta - t) / (eta + t);
     return .5f * (std::norm(rs) + std::norm(rp));
 }
-float hostFresnelDielectric(float eta) {  // evalFresnelDielectric(eta, 1)
-    if (eta == 1) return 0.f;
-    const float rs = (1 - eta) / (1 + eta), rp = (eta - 1) / (eta + 1);
-    return .5f * (rs * rs + rp * rp);
-}
-float roughnessToT(float alpha) {  // FractalSurface.slang:45-53
-    const float meank = k2Pi / (kMeanWavelength * 1e-3f);
-    const float a2 = sqr(std::min(std::max(alpha, .0f), .75f));
-    return std::min(5000.f, (1 - a2) / (4.f * sqr(meank) * a2));
-}
-float TToRoughness(float T) {
-    const float meank = k2Pi / (kMeanWavelength * 1e-3f);
-    return 1.f / std::sqrt(1.f + 4.f * sqr(meank) * T);
-}
-void setFractal(DevMaterial& d, float roughness, float gamma) {
-    d.surfA = roughnessToT(roughness);
-    d.surfGamma = std::max(1.1f, gamma);
-    d.surfQ = TToRoughness(d.surfA);
-    d.roughnessProp = d.surfQ;
-}
-float roughnessToSigma2(float r) { return std::pow(std::min(std::max(1.f - .5f * r, .0f), 1.f), 28.f) * 2500.f; }
-void setGaussian(DevMaterial& d, float roughness) {  // GaussianSurface.slang:52-60
-    const float s2 = roughnessToSigma2(roughness), s2max = roughnessToSigma2(0.1f), s2r0 = roughnessToSigma2(.0f);
-    d.surfQ = (s2r0 - s2) / (s2r0 - s2max);
-    d.surfA = std::min(s2max, s2);
-    d.roughnessProp = 2.f * (1.f - std::pow(d.surfA / 2500.f, 1.f / 28.f));
-}
-
-// Unpacks one MaterialDataBlob exactly as the *Material.slang setupMaterialInstance() functions do (fp16 slots).
-int unpackMaterial(const PltptMaterialBlob& m, const std::vector<PltptSpectralProfile>& profiles, DevMaterial& d) {
+// Derives one MaterialDataBlob into the device record (plt_material.cuh: the same function the textured path runs per hit).  A material
+// with a Texture handle keeps its uniform-value record as a placeholder and is flagged for the per-hit path.
+int unpackMaterial(const PltptMaterialBlob& m, const std::vector<PltptSpectralProfile>& profiles, uint32_t textureCount, DevMaterial& d) {
     std::memset(&d, 0, sizeof(d));
-    for (uint32_t t : {m.texBaseColor, m.texSpecular, m.texEmissive, m.texNormalMap, m.texTransmission, m.texData1, m.texData2})
-        if (((t >> 29) & 3u) != 0) return fail(PLTPT_ERR_UNSUPPORTED, "textured material handles are not supported (TextureHandle::Mode::Uniform only)");
-    d.type = m.header[0] & 0xffffu;
-    d.hdrFlags = (m.header[0] >> 28) & 1u;
-    const float base[4] = {h2f(m.baseColor[0]), h2f(m.baseColor[1]), h2f(m.baseColor[2]), h2f(m.baseColor[3])};
-    const float spec[4] = {h2f(m.specular[0]), h2f(m.specular[1]), h2f(m.specular[2]), h2f(m.specular[3])};
-    const float data1[4] = {h2f(m.data1[0]), h2f(m.data1[1]), h2f(m.data1[2]), h2f(m.data1[3])};
-    const float data2[4] = {h2f(m.data2[0]), h2f(m.data2[1]), h2f(m.data2[2]), h2f(m.data2[3])};
-    const float tran[3] = {h2f(m.transmission[0]), h2f(m.transmission[1]), h2f(m.transmission[2])};
-    const float IoR = h2f(m.IoR);
-    d.c0x = base[0]; d.c0y = base[1]; d.c0z = base[2];
-    d.c1x = d.c1y = d.c1z = 1.f;
-    d.opacity = base[3];
-    d.emissionId = PLTPT_NO_SPECTRAL_PROFILE;
-    d.etaN = m.iorNSpectralId; d.etaK = m.iorKSpectralId;
-    d.extEta = IoR;
-    d.albx = base[0]; d.alby = base[1]; d.albz = base[2];
-    const float meanK = k2Pi / (kMeanWavelength * 1e-3f);
-    switch (d.type) {
-        case PLTPT_MATERIAL_DIFFUSE:  // PLTDiffuseMaterial.slang:40-50, PLTDiffuseBSDF.slang:136-155
-            d.emissionId = m.emissionSpectralId;
-            d.lobes = L_DiffuseReflection;
-            d.propFlags = m.emissionSpectralId != PLTPT_NO_SPECTRAL_PROFILE ? P_IsEmissive : 0;
-            d.roughnessProp = 1.f;
-            break;
-        case PLTPT_MATERIAL_CONDUCTOR: {  // PLTConductorMaterial.slang:40-57, PLTConductorBSDF.slang:218-241
-            setFractal(d, spec[1], spec[0]);
-            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
-            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
-            const float F = hostFresnelConductor(hostEvalSpectrum(profiles, d.etaN, kMeanWavelength), hostEvalSpectrum(profiles, d.etaK, kMeanWavelength));
-            d.albx *= F; d.alby *= F; d.albz *= F;
-            break;
-        }
-        case PLTPT_MATERIAL_DIELECTRIC: {  // PLTDielectricMaterial.slang:40-57, PLTDielectricBSDF.slang:335-360
-            const float B = (tran[0] > 0 || tran[1] > 0 || tran[2] > 0) ? spec[0] : 0.f;
-            d.c1x = tran[0]; d.c1y = tran[1]; d.c1z = tran[2];
-            setGaussian(d, spec[1]);
-            d.f0 = std::max(1.f, IoR - 2.897f * B); d.f1 = spec[3]; d.f2 = B;
-            d.opacity = .5f * base[3];
-            const uint32_t dT = B != 0.f ? L_DispersiveDeltaTransmission : L_DeltaTransmission;
-            d.lobes = d.surfQ == 0.f ? (L_DeltaReflection | dT) : (L_DeltaReflection | dT | L_ScatterReflection | L_ScatterTransmission);
-            d.propFlags = P_IsTransmissive | (d.surfQ < kQcutoffForMS ? P_CanMSTransmissive : 0);
-            const float F = hostFresnelDielectric((d.f0 + B * sqr(meanK * k1_2Pi)) / d.f1);
-            d.albx *= F; d.alby *= F; d.albz *= F;
-            break;
-        }
-        case PLTPT_MATERIAL_OPAQUE_DIELECTRIC:  // PLTOpaqueDielectricMaterial.slang:40-52
-            setFractal(d, spec[1], 3.f);
-            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
-            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
-            break;
-        case PLTPT_MATERIAL_THIN_DIELECTRIC:  // PLTThinDielectricMaterial.slang:40-54
-            d.f0 = IoR; d.f1 = spec[3]; d.f2 = base[0] * spec[0]; d.f3 = base[1]; d.f4 = base[2];
-            d.opacity = .5f * base[3];
-            d.lobes = L_DeltaReflection | L_DeltaTransmission;
-            d.propFlags = P_IsTransmissive | P_CanMSReflective | P_CanMSTransmissive;
-            d.albx = d.alby = d.albz = 1.f;
-            d.roughnessProp = 0.f;
-            break;
-        case PLTPT_MATERIAL_COATED_CONDUCTOR: case PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC: {  // PLTCoatedConductorMaterial.slang:40-60
-            setFractal(d, spec[1], 3.f);
-            d.f0 = data1[3]; d.f1 = data1[0] * spec[2];
-            d.f2 = IoR + (d.f0 - IoR) * (std::min(std::max(d.f1, 0.f), .05f) / .05f);  // coatEta(), PLTCoatedConductorBSDF.slang:65-68
-            d.u0 = d.type == PLTPT_MATERIAL_COATED_CONDUCTOR ? 1u : 0u;
-            d.opacity = 1.f;
-            d.lobes = d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection);
-            d.propFlags = d.surfQ < kQcutoffForMS ? P_CanMSReflective : 0;
-            break;
-        }
-        case PLTPT_MATERIAL_GRATED_CONDUCTOR: case PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC: {  // PLTDiffractionGratedConductorMaterial.slang:41-73
-            setFractal(d, data2[1], 3.f);
-            d.f0 = data1[2];
-            d.f1 = data1[0] > 0.f ? 1.f / data1[0] : 0.f; d.f2 = data1[1] > 0.f ? 1.f / data1[1] : 0.f;
-            d.f3 = data2[0] * spec[0]; d.f4 = spec[1];
-            d.f5 = std::cos(d.f0); d.f6 = std::sin(d.f0);
-            const uint32_t typeAndLobes = m.data1[3];
-            d.u0 = std::min(std::max(typeAndLobes & 0xFFu, 1u), 8u);
-            d.u1 = typeAndLobes >> 8;
-            d.lobes = (d.surfQ == 0.f ? L_DeltaReflection : (L_DeltaReflection | L_ScatterReflection)) | L_DispersiveDeltaReflection;
-            d.propFlags = P_CanMSReflective;
-            const float a = std::exp(-sqr(1.f * d.f3 * meanK));
-            if (d.type == PLTPT_MATERIAL_GRATED_CONDUCTOR) {
-                const float F = hostFresnelConductor(hostEvalSpectrum(profiles, d.etaN, kMeanWavelength), hostEvalSpectrum(profiles, d.etaK, kMeanWavelength));
-                d.albx *= F; d.alby *= F; d.albz *= F;
-            }
-            d.roughnessProp = (1 - a) * d.surfQ;
-            break;
-        }
-        case PLTPT_MATERIAL_MULTILAYERED_STACK:  // PLTMultiLayeredStackMaterial.slang:40-56
-            d.f0 = data2[0]; d.f1 = data2[1]; d.f2 = data1[0]; d.f3 = data1[1]; d.u0 = m.data1[3];
-            d.lobes = L_DeltaReflection;
-            d.propFlags = P_CanMSReflective;
-            d.roughnessProp = 0.f;
-            break;
-        default:
-            return fail(PLTPT_ERR_UNSUPPORTED, "material type " + std::to_string(d.type) + " is not a PLT material (only MaterialType 2..11 are reachable from PLTPT)");
+    bool textured = false;
+    for (uint32_t t : {m.texBaseColor, m.texSpecular, m.texEmissive, m.texNormalMap, m.texTransmission, m.texData1, m.texData2}) {
+        if (t >> 31) return fail(PLTPT_ERR_UNSUPPORTED, "UDIM texture handles are not supported (MATERIAL_SYSTEM_UDIM_INDIRECTION_ENABLED == 0 builds only)");
+        const uint32_t mode = texHandleMode(t);
+        if (mode > 1) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown TextureHandle mode");
+        if (mode == 1 && texHandleID(t) >= textureCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "material references texture " + std::to_string(texHandleID(t)) + " but the scene has " + std::to_string(textureCount));
     }
+    for (uint32_t t : {m.texBaseColor, m.texSpecular, m.texEmissive, m.texTransmission, m.texData1, m.texData2}) textured |= texHandleMode(t) == 1;
+    const uint32_t type = m.header[0] & 0xffffu;
+    const bool cond = type == PLTPT_MATERIAL_CONDUCTOR || type == PLTPT_MATERIAL_GRATED_CONDUCTOR;
+    const float F = cond ? hostFresnelConductor(hostEvalSpectrum(profiles, m.iorNSpectralId, kMeanWavelength), hostEvalSpectrum(profiles, m.iorKSpectralId, kMeanWavelength)) : 0.f;
+    if (!deriveMaterial(m, uniformSlots(m), F, d))
+        return fail(PLTPT_ERR_UNSUPPORTED, "material type " + std::to_string(type) + " is not a PLT material (only MaterialType 2..11 are reachable from PLTPT)");
+    d.hdrFlags = ((m.header[0] >> 28) & 1u ? HF_DoubleSided : 0u) | (textured ? HF_Textured : 0u) |
+                 (texHandleMode(m.texNormalMap) == 1 && blobNormalMapType(m) != 0 ? HF_NormalMap : 0u);
     return PLTPT_OK;
 }
 
@@ -392,6 +283,25 @@ extern "C" int pltpt_envmap_eval(PltptHandle h, uint32_t n, const float* dirs, f
     PLT_CUDA(cudaGetLastError());
     return PLTPT_OK;
 }
+namespace {
+__global__ void k_texture_sample(DevTextures tx, uint32_t handle, uint32_t samplerID, float4 uniformValue, uint32_t n, const float2* __restrict__ uv, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sampleTexture(tx, handle, samplerID, uv[i], uniformValue);
+}
+}  // namespace
+extern "C" int pltpt_texture_sample(PltptHandle h, uint32_t handle, uint32_t samplerID, const float uniformValue[4], uint32_t n, const float* uv, float* out, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (n == 0) return PLTPT_OK;
+    if (!uv || !out || !uniformValue) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    if (texHandleMode(handle) == 1 && texHandleID(handle) >= h->scene.tex.textureCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "texture id out of range");
+    PLT_CUDA(cudaSetDevice(h->device));
+    k_texture_sample<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->scene.tex, handle, samplerID, make_float4(uniformValue[0], uniformValue[1], uniformValue[2], uniformValue[3]), n,
+                                                                      reinterpret_cast<const float2*>(uv), reinterpret_cast<float4*>(out));
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
 extern "C" int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, float* out, void* stream) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
     if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
@@ -404,6 +314,52 @@ extern "C" int pltpt_envmap_sample(PltptHandle h, uint32_t n, const float* rnd, 
     PLT_CUDA(cudaGetLastError());
     return PLTPT_OK;
 }
+
+namespace {
+// Material textures: every texture's mip 0 is copied into ONE device blob (256 B aligned), next to the descriptor and sampler tables and the
+// raw material blobs the per-hit path reads.  The descriptor arrays of the scene description are host memory (include/pltpt.h).
+int uploadTextures(PltptContext* h, const PltptSceneDesc* s, const std::vector<PltptMaterialBlob>& mats, bool dev) {
+    DevScene& d = h->scene;
+    d.tex = DevTextures{};
+    bool any = false;
+    for (const PltptMaterialBlob& m : mats)
+        for (uint32_t t : {m.texBaseColor, m.texSpecular, m.texEmissive, m.texNormalMap, m.texTransmission, m.texData1, m.texData2}) any |= texHandleMode(t) == 1;
+    if (!any) return PLTPT_OK;
+    if (!s->textures) return fail(PLTPT_ERR_INVALID_ARGUMENT, "textured material but PltptSceneDesc::textures is null");
+    static const uint32_t texelBytes[PLTPT_TEXTURE_FORMAT_COUNT] = {16, 4, 4, 8};
+    std::vector<DevTexture> descs(s->textureCount);
+    std::vector<size_t> offset(s->textureCount);
+    size_t total = 0;
+    for (uint32_t i = 0; i < s->textureCount; ++i) {
+        const PltptTextureDesc& t = s->textures[i];
+        if (!t.texels || t.width == 0 || t.height == 0 || t.width > 65536 || t.height > 65536) return fail(PLTPT_ERR_INVALID_ARGUMENT, "texture " + std::to_string(i) + ": null texels or size out of range");
+        if (t.format >= PLTPT_TEXTURE_FORMAT_COUNT) return fail(PLTPT_ERR_UNSUPPORTED, "texture " + std::to_string(i) + ": format " + std::to_string(t.format) + " is not supported (RGBA32F, RGBA16F, RGBA8 UNORM / sRGB)");
+        offset[i] = total;
+        total += (size_t(t.width) * t.height * texelBytes[t.format] + 255) & ~size_t(255);
+    }
+    PLT_CUDA(h->texBlob.ensure(total));
+    for (uint32_t i = 0; i < s->textureCount; ++i) {
+        const PltptTextureDesc& t = s->textures[i];
+        PLT_CUDA(cudaMemcpy(h->texBlob.as<uint8_t>() + offset[i], t.texels, size_t(t.width) * t.height * texelBytes[t.format], dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        descs[i] = DevTexture{h->texBlob.as<uint8_t>() + offset[i], t.width, t.height, t.format, 0};
+    }
+    std::vector<DevSampler> smp(s->samplerCount);
+    for (uint32_t i = 0; i < s->samplerCount; ++i) {
+        const PltptSamplerDesc& q = s->samplers[i];
+        if (q.magFilter > PLTPT_FILTER_LINEAR || q.addressU > PLTPT_ADDRESS_MIRROR_ONCE || q.addressV > PLTPT_ADDRESS_MIRROR_ONCE) return fail(PLTPT_ERR_INVALID_ARGUMENT, "sampler " + std::to_string(i) + ": filter or address mode out of range");
+        smp[i] = DevSampler{q.magFilter, q.addressU, q.addressV, 0, make_float4(q.borderColor[0], q.borderColor[1], q.borderColor[2], q.borderColor[3])};
+    }
+    if (int r = upload(h->texDescs, descs.data(), descs.size() * sizeof(DevTexture), false)) return r;
+    if (int r = upload(h->texSamplers, smp.data(), smp.size() * sizeof(DevSampler), false)) return r;
+    if (int r = upload(h->materialBlobs, mats.data(), mats.size() * sizeof(PltptMaterialBlob), false)) return r;
+    d.tex.textures = h->texDescs.as<DevTexture>();
+    d.tex.samplers = h->texSamplers.as<DevSampler>();
+    d.tex.blobs = h->materialBlobs.as<PltptMaterialBlob>();
+    d.tex.textureCount = s->textureCount;
+    d.tex.samplerCount = s->samplerCount;
+    return PLTPT_OK;
+}
+}  // namespace
 
 extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (!h || !s) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
@@ -438,7 +394,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     }
     std::vector<DevMaterial> dmats(mats.size());
     for (size_t i = 0; i < mats.size(); ++i) {
-        if (int r = unpackMaterial(mats[i], profiles, dmats[i])) return r;
+        if (int r = unpackMaterial(mats[i], profiles, s->textureCount, dmats[i])) return r;
         for (uint32_t id : {dmats[i].emissionId, dmats[i].etaN, dmats[i].etaK})
             if (id != PLTPT_NO_SPECTRAL_PROFILE && id >= s->profileCount) return fail(PLTPT_ERR_INVALID_ARGUMENT, "spectral profile id out of range");
     }
@@ -509,6 +465,7 @@ extern "C" int pltpt_set_scene(PltptHandle h, const PltptSceneDesc* s) {
     if (d.etriCount > 0 && h->opt.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER && !d.alias) return fail(PLTPT_ERR_INVALID_ARGUMENT, "Power emissive sampler needs the triangle alias table");
     if (d.triCount == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "scene has no triangles");
 
+    if (int r = uploadTextures(h, s, mats, dev)) return r;
     if (int r = buildBvh(h, 0)) return r;
     if (int r = buildEnvMap(h, s, dev)) return r;
     h->hasScene = true;

@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 #include "plt_bsdf.cuh"
+#include "plt_material.cuh"
 #include "plt_envmap.cuh"
 
 namespace plt {
@@ -51,6 +52,7 @@ struct DevScene {
     float invWeightsSum;
     uint32_t hitTypeBits, hitInstBits, hitPrimBits;
     DevEnvMap env;  // env.texels == nullptr: the scene has no environment map
+    DevTextures tex; // material textures, samplers and the raw material blobs (read only by materials flagged HF_Textured / HF_NormalMap)
 };
 
 struct DevBuf {
@@ -82,6 +84,7 @@ struct PltptContext {
     plt::DevBuf vertices, indexData, instances, meshes, world, worldIT, materials, profiles, lights, etris, eflux, activeTris, perMeshOffset, alias, instTriOffset;
     plt::DevBuf bvhNodes, bvhTris, bvhScratch[8];
     plt::DevBuf envTexels, envImportance;
+    plt::DevBuf texBlob, texDescs, texSamplers, materialBlobs;
     // host mirrors needed by the host logic
     std::vector<PltptGeometryInstance> hInstances;
     std::vector<PltptMeshDesc> hMeshes;

@@ -202,6 +202,15 @@ struct Beam {
     // rotateFrame: MuellerT (Mueller.slang:34-53) acts on (L1,L2) only; coherence rotates by R(θ).  Split in two so that a beam with
     // several Stokes columns (Beam4 below) rotates all of them with one evaluation of the angle.
     PLT_D void frameRotation(float3 newt, float& rx, float& ry, float& sint, float& cost) const {
+#if PLT_FAST_DEVICE
+        // sin and cos of atan2(y, x) are y / h and x / h: no inverse trigonometry, same rotation (atan2(0, 0) = 0 and a non-finite angle -> identity)
+        const float y = dot(r, cross(t, newt)), x = dot(t, newt), h2 = x * x + y * y;
+        const bool ok = h2 > 0.f && h2 < kFltMax;
+        const float ih = rsqrtf(h2);
+        sint = ok ? y * ih : 0.f; cost = ok ? x * ih : 1.f;
+        rx = 2 * sint * cost; ry = 1 - 2 * sqr(sint);
+        return;
+#endif
         float theta = atan2f(dot(r, cross(t, newt)), dot(t, newt));
         theta = isfinite(theta) ? theta : .0f;
         sincosf(theta, &sint, &cost);
@@ -297,7 +306,13 @@ struct Fractal {
     PLT_D float alpha(float3 wi, float3 wo, float k) const { return exp_cr(-sqr((fabsf(wi.z) + fabsf(wo.z)) * q * k)); }
     PLT_D float4 alpha4(float3 wi, float3 wo, float4 k) const { return mk4(alpha(wi, wo, k.x), alpha(wi, wo, k.y), alpha(wi, wo, k.z), alpha(wi, wo, k.w)); }
     PLT_D bool isDeltaOnly() const { return q == .0f; }
+#if PLT_FAST_DEVICE
+    // x^-p as exp2(-p log2 x) on the MUFU units: x = 1 + T |z|^2 lies in [1, ~1e7], so the absolute error of lg2.approx (2^-22) times
+    // p <= ~3 keeps the result within 1e-6 relative -- the IEEE powf is ~40 instructions, this is 4
+    PLT_D float pGF(float2 z) const { return k1_2Pi * (gamma - 1) * T * exp2f(-.5f * (gamma + 1.f) * __log2f(1 + T * dot(z, z))); }
+#else
     PLT_D float pGF(float2 z) const { return k1_2Pi * (gamma - 1) * T * (1.f / powf(1 + T * dot(z, z), (gamma + 1.f) / 2.f)); }
+#endif
     PLT_D float pdf(float3 wi, float3 wo, float k) const { return pGF(mk2(k * (wi.x + wo.x), k * (wi.y + wo.y))); }
     PLT_D float eval(float k, float3 h) const { return pGF(mk2(k * h.x, k * h.y)); }
     PLT_D float3 sample(float3 wi, Rng& sg, float k, float& pdf) const {

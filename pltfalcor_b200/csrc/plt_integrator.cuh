@@ -201,9 +201,9 @@ PLT_D bool scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& pa
     const uint4 hitInfo = packHit(P.sc, th);
     uint32_t materialID;
     const VertexData v = getVertexData(P.sc, th, materialID);
-    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+    const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
     const float3 wi = -path.dir;
-    const SD sd = prepareShadingData(v, materialID, m, wi);
+    const SD sd = prepareShadingData(P.sc, v, materialID, m, wi);
     if (P.opt.alphaMasking && m.opacity == .0f) {
         path.origin = sd.computeNewRayOrigin(false);
         return true;
@@ -366,24 +366,34 @@ PLT_D bool selectLightType(const FrameParams& P, uint32_t& lightType, float& pdf
     }
     return false;
 }
-struct EmissiveTri { float3 p0, p1, p2, normal; float area; uint32_t materialID; };
+struct EmissiveTri { float3 p0, p1, p2, normal; float area; uint32_t materialID; uint32_t uv0, uv1, uv2; };  // uv: 2 x fp16 per vertex
 // LightCollectionShared.slang:118-135
 PLT_D EmissiveTri loadEmissiveTriangle(const DevScene& sc, uint32_t idx) {
     const float4* p = reinterpret_cast<const float4*>(sc.etris + idx);
     const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
     EmissiveTri t;
     t.p0 = mk3(a.x, a.y, a.z); t.p1 = mk3(b.x, b.y, b.z); t.p2 = mk3(c.x, c.y, c.z);
+    t.uv0 = __float_as_uint(a.w); t.uv1 = __float_as_uint(b.w); t.uv2 = __float_as_uint(c.w);
     t.normal = decodeNormal2x16(__float_as_uint(d.x));
     t.area = d.y;  // stored as fp32 bits
     t.materialID = __float_as_uint(d.z);
     return t;
 }
-// EmissiveLightSamplerHelpers.slang:56-74: emission = profile spectrum x rgbToSpectrum(1,1,1)
-PLT_D void materialEvalEmissive(const FrameParams& P, uint32_t materialID, float wavelength, bool importanceSample, Rng& sg, float4& Le, float4& wl) {
+// EmissiveLightSamplerHelpers.slang:56-74: emission = profile spectrum x rgbToSpectrum(emissionRGB), emissionRGB = texEmissive at `uv`
+// (uniform value 1)
+PLT_D void materialEvalEmissive(const FrameParams& P, const EmissiveTri& tri, float3 b, float wavelength, bool importanceSample, Rng& sg, float4& Le, float4& wl) {
+    const uint32_t materialID = tri.materialID;
     const uint32_t id = __ldg(&P.sc.materials[materialID].emissionId);
     if (id != PLTPT_NO_SPECTRAL_PROFILE) {
+        float3 emissionRGB = mk3(1.f);
+        if (__ldg(&P.sc.materials[materialID].hdrFlags) & HF_Textured) {
+            // EmissiveTriangle::getTexCoord (LightCollectionShared.slang:65-70)
+            const float2 uv = mk2(h2f(tri.uv0 & 0xffffu), h2f(tri.uv0 >> 16)) * b.x + mk2(h2f(tri.uv1 & 0xffffu), h2f(tri.uv1 >> 16)) * b.y + mk2(h2f(tri.uv2 & 0xffffu), h2f(tri.uv2 >> 16)) * b.z;
+            const DevMaterial m = loadMaterialAt(P.sc, materialID, uv);
+            emissionRGB = mk3(m.c1x, m.c1y, m.c1z);
+        }
         Le = sampleSpectrum(P.sc.profiles, id, wavelength, sg, importanceSample, int(P.opt.HWSS), wl);
-        Le *= rgbToSpectrum4(mk3(1.f), wl);
+        Le *= rgbToSpectrum4(emissionRGB, wl);
     }
 }
 struct TriangleLightSample { float3 posW, normalW, dir; float distance; float4 Le, wavelengths; float pdf; };
@@ -401,7 +411,7 @@ PLT_D bool sampleTriangle(const FrameParams& P, float3 posW, uint32_t triangleIn
     ls.normalW = tri.normal;
     const float cosTheta = dot(ls.normalW, -ls.dir);
     if (cosTheta <= 0.f) return false;
-    materialEvalEmissive(P, tri.materialID, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
+    materialEvalEmissive(P, tri, b, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
     ls.pdf = distSqr / fmaxf(kFltMin, cosTheta * tri.area);
     return true;
 }
@@ -671,7 +681,7 @@ PLT_D uint32_t allocJob(const FrameParams& P) {
 
 // pltpt_solve.rt.slang:48-66 (forwardUnwindStep)
 PLT_D void forwardUnwindStep(const FrameParams& P, uint32_t& evals, const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 wo, uint32_t lobe, Beam& beam) {
-    const SD sd = prepareShadingData(v, materialID, m, -beam.r);
+    const SD sd = prepareShadingData(P.sc, v, materialID, m, -beam.r);
     beam.propagate(sd.posW);
     const BsdfCtx cx = {P.sc.profiles, int(P.opt.HWSS)};
     bsdfEval(m, cx, sd, wo, lobe, beam);
@@ -775,7 +785,7 @@ PLT_D void evalEmissive(const FrameParams& P, SolveState& st, uint32_t pixel, in
     const float w = needMIS ? misWeight(bounce.lastNonDeltaPdf, lightPdf) : 1.f;
     float4 wl = mk4(.0f);
     float4 Le = sampleSpectrum(P.sc.profiles, m.emissionId, st.wavelength, st.sg, P.opt.doImportanceSampleEmitters != 0, int(P.opt.HWSS), wl);
-    Le *= w * rgbToSpectrum4(mk3(1.f), wl);
+    Le *= w * rgbToSpectrum4(mk3(m.c1x, m.c1y, m.c1z), wl);  // bsdfProp.emissionRGB (PLTDiffuseBSDF.slang:143), 1 without an emissive texture
     if (!anyPositive(Le, int(P.opt.HWSS))) { writeContribution(P, pixel, bounceIdx, 1, mk3(0.f)); return; }
     const float dist = length(st.pathOrigin - sd.posW);
     Beam beam = sourceBeamArea(sd.posW, bounce.wi, P.opt.sourcingAreaFromEmissiveGeometry, dist, Le, wl, P.opt.sourcingMaxBeamOmega, int(P.opt.HWSS));
@@ -839,8 +849,8 @@ PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float
         uint32_t materialID;
         VertexData v = getVertexData(P.sc, th, materialID);
         v.posW = rayOrigin + t * rayDir;
-        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-        const SD sd = prepareShadingData(v, materialID, m, wi);
+        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
+        const SD sd = prepareShadingData(P.sc, v, materialID, m, wi);
         if (!(m.propFlags & P_CanMSTransmissive)) return false;
         if (!manifoldSampleVertex(packHit(P.sc, th), sd, m, -wi, sg, data) || (data.hits[data.hitCount - 1].lobe & L_Transmission) == 0) return false;
         rayOrigin = shadowRayOrigin(sd, rayDir);
@@ -882,7 +892,7 @@ PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const Man
         VertexData v = getVertexData(P.sc, th, materialID);
         v.posW = r.hits[idx].posW;
         const float3 p2 = idx == 0 ? origin : r.hits[idx - 1].posW;
-        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
         forwardUnwindStep(P, st.evals, v, materialID, m, normalize(p2 - v.posW), r.hits[idx].lobe, beam);
     }
 }
@@ -975,8 +985,8 @@ PLT_D int mneeWalkAdvance(const FrameParams& P, MneeItem& it, MneeWalk& w, bool 
         const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
         const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
         const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
-        const DevMaterial m = loadMaterial(P.sc.materials, materialID);
-        const SD sd = prepareShadingData(v, materialID, m, wiP.v);
+        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
+        const SD sd = prepareShadingData(P.sc, v, materialID, m, wiP.v);
         const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, __float_as_uint(it.posLobe[idx].w), wavelength);
         float lenC;
         float3 positionStepDir;
@@ -1043,9 +1053,9 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
         else {
             uint32_t materialID;
             const VertexData v = readVertexCache(P, it.pixel, int(it.bounceIdx), materialID);
-            const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+            const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
             const float4 d = P.bDir[size_t(it.bounceIdx) * P.pixelCount + it.pixel];
-            const SD sd = prepareShadingData(v, materialID, m, oct_to_ndir_equal_area_snorm(mk2(d.x, d.y)));
+            const SD sd = prepareShadingData(P.sc, v, materialID, m, oct_to_ndir_equal_area_snorm(mk2(d.x, d.y)));
             misBsdfPdf = bsdfPdf(m, sd, lsDir, beam.wl.x);
         }
         beam.scale(misWeight(it.lightDirLsPdf.w, misBsdfPdf * ms.pdf));
@@ -1093,8 +1103,8 @@ PLT_D void connectSetup(const FrameParams& P, uint32_t pixel, int p, bool freshR
     }
     if (!P.perTileSG) c.st.tilesg = c.st.sg;
     c.bounce = readBounce(P, pixel, p);
-    c.m = loadMaterial(P.sc.materials, c.materialID);
-    c.sd = prepareShadingData(c.v, c.materialID, c.m, c.bounce.wi);
+    c.m = loadMaterialAt(P.sc, c.materialID, c.v.texC);
+    c.sd = prepareShadingData(P.sc, c.v, c.materialID, c.m, c.bounce.wi);
 }
 PLT_D void storeSolveRng(const FrameParams& P, uint32_t pixel, const SolveState& st) {
     P.ssRng[pixel] = make_uint4(st.sg.s0, st.sg.s1, st.sg.s2, st.sg.s3);
@@ -1303,7 +1313,7 @@ struct alignas(16) UnwindItem { float4 job[kJobPlanes]; float4 vtx[4]; float4 di
 // inputs: `v`, `materialID`, `d` = vertex record and bounce direction of the vertex the job evaluates next, `beam`, `h` = the job.
 // Returns true while the job has further vertices to go through.
 PLT_D bool unwindStepLoaded(const FrameParams& P, uint32_t id, const VertexData& v, uint32_t materialID, float4 d, Beam& beam, JobHeader& h, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
-    const DevMaterial m = loadMaterial(P.sc.materials, materialID);
+    const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
     const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
     forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);

@@ -21,6 +21,20 @@
 #define PLT_FOR_LAMBDA(j, n) for (int j = 0; j < int(n); ++j)
 #endif
 
+// PLT_FAST_MATH = 1 (set per translation unit, pltfalcor_b200/build.py): the replay stage (stage_unwind.cu) evaluates BSDFs on paths
+// that are already fixed -- no ray is generated and no branch of the path depends on its arithmetic -- so it only has to meet the
+// 1e-4 relative BSDF tolerance, not the operation-by-operation rounding the sample stage keeps for identical paths.  There the
+// IEEE division / square-root sequences (8-12 instructions each plus a slow-path call) become MUFU approximations (<= 2 ulp),
+// normalisation is one rsqrt, and rotations are built from the sine and cosine directly instead of atan2 -> sincos.
+#ifndef PLT_FAST_MATH
+#define PLT_FAST_MATH 0
+#endif
+#if PLT_FAST_MATH && defined(__CUDA_ARCH__)
+#define PLT_FAST_DEVICE 1
+#else
+#define PLT_FAST_DEVICE 0
+#endif
+
 namespace plt {
 
 constexpr float kPi = 3.14159265358979323846f;
@@ -64,7 +78,11 @@ PLT_HD float3& operator/=(float3& a, float s) { a = a / s; return a; }
 PLT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 PLT_HD float3 cross(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 PLT_HD float length(float3 a) { return sqrtf(dot(a, a)); }
+#if PLT_FAST_DEVICE
+PLT_HD float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
+#else
 PLT_HD float3 normalize(float3 a) { return a / length(a); }
+#endif
 PLT_HD float3 vabs(float3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 PLT_HD float3 vmax(float3 a, float3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 PLT_HD float3 vmin(float3 a, float3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
@@ -170,7 +188,11 @@ PLT_HD float3 oct_to_ndir_equal_area_snorm(float2 p) {
     const float r = 1.f - fabsf(d);
     const float phi = (r > 0.f) ? ((fabsf(p.y) - fabsf(p.x)) / r + 1.f) * kPi_4 : 0.f;
     const float f = r * sqrtf(2.f - r * r);
+#if PLT_FAST_DEVICE
+    return mk3(f * signf(p.x) * __cosf(phi), f * signf(p.y) * __sinf(phi), signf(d) * (1.f - r * r));  // phi in [0, pi/2]: abs error < 1e-6
+#else
     return mk3(f * signf(p.x) * cosf(phi), f * signf(p.y) * sinf(phi), signf(d) * (1.f - r * r));
+#endif
 }
 
 // GeometryHelpers.slang:47-61
@@ -318,10 +340,20 @@ PLT_D float xyzG(float x, float lambda, float s1, float s2) {
     // the fit itself is only good to ~1e-2 of the CIE curves (SpectrumUtilsTests.cpp:40-80)
     return __expf(-0.5f * t * t);
 }
+#if PLT_FAST_DEVICE
+// exp(-t^2 / 2) = 2^-(c t)^2 with c = sqrt(log2(e) / 2) folded into the two widths at compile time: subtract, select, multiply, square, ex2
+PLT_D float xyzGFolded(float x, float lambda, float c1, float c2) {
+    const float t = (x - lambda) * (x < lambda ? c1 : c2);
+    return exp2f(-(t * t));
+}
+#define PLT_XYZG(l, lambda, s1, s2) xyzGFolded(l, lambda, 0.84932180028801904272f * (s1), 0.84932180028801904272f * (s2))
+#else
+#define PLT_XYZG(l, lambda, s1, s2) xyzG(l, lambda, s1, s2)
+#endif
 PLT_D float3 wavelengthToXYZ(float l) {
-    return mk3(0.362f * xyzG(l, 442.0f, 0.0624f, 0.0374f) + 1.056f * xyzG(l, 599.8f, 0.0264f, 0.0323f) - 0.065f * xyzG(l, 501.1f, 0.0490f, 0.0382f),
-               0.821f * xyzG(l, 568.8f, 0.0213f, 0.0247f) + 0.286f * xyzG(l, 530.9f, 0.0613f, 0.0322f),
-               1.217f * xyzG(l, 437.0f, 0.0845f, 0.0278f) + 0.681f * xyzG(l, 459.0f, 0.0385f, 0.0725f));
+    return mk3(0.362f * PLT_XYZG(l, 442.0f, 0.0624f, 0.0374f) + 1.056f * PLT_XYZG(l, 599.8f, 0.0264f, 0.0323f) - 0.065f * PLT_XYZG(l, 501.1f, 0.0490f, 0.0382f),
+               0.821f * PLT_XYZG(l, 568.8f, 0.0213f, 0.0247f) + 0.286f * PLT_XYZG(l, 530.9f, 0.0613f, 0.0322f),
+               1.217f * PLT_XYZG(l, 437.0f, 0.0845f, 0.0278f) + 0.681f * PLT_XYZG(l, 459.0f, 0.0385f, 0.0725f));
 }
 PLT_D float wavelengthToD65(float lambda) {
     const float w = (lambda - kMinWavelength) * 0.2f;

@@ -85,8 +85,15 @@ PLT_D VertexData getVertexData(const DevScene& sc, const TriHit& hit, uint32_t& 
     return v;
 }
 
-// MaterialFactory.slang:79-131 (prepareShadingData) + ShadingUtils.slang:126-152; Uniform texture handles only, so no normal mapping.
-PLT_D SD prepareShadingData(const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 viewDir) {
+// The material a hit sees: the scene's pre-derived record, or -- for a material with textured parameter slots -- the record derived from
+// the slots sampled at the hit's texture coordinate (plt_material.cuh; every *Material.slang::setupMaterialInstance).
+PLT_D DevMaterial loadMaterialAt(const DevScene& sc, uint32_t id, float2 uv) {
+    DevMaterial m = loadMaterial(sc.materials, id);
+    if (m.hdrFlags & HF_Textured) m = resolveTexturedMaterial(sc.tex, sc.profiles, id, uv, m.hdrFlags);
+    return m;
+}
+// MaterialFactory.slang:79-131 (prepareShadingData) + ShadingUtils.slang:126-152 (tangent frame), :199-246 (normal mapping).
+PLT_D SD prepareShadingData(const DevScene& sc, const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 viewDir) {
     SD sd;
     sd.posW = v.posW;
     sd.uv = v.texC;
@@ -105,7 +112,11 @@ PLT_D SD prepareShadingData(const VertexData& v, uint32_t materialID, const DevM
     sd.faceN = v.faceNormalW;
     sd.frontFacing = dot(sd.V, sd.faceN) >= 0.f;
     sd.materialID = materialID;
-    if (!sd.frontFacing && (m.hdrFlags & 1u)) sd.N = -sd.N;
+    if (valid && (m.hdrFlags & HF_NormalMap)) {  // modifyTangentSpace: only with a valid tangent space (MaterialFactory.slang:114-120)
+        const Frame3 f = applyNormalMapTextured(sc.tex, materialID, v.texC, v.tangentW, Frame3{sd.T, sd.B, sd.N});
+        sd.T = f.T; sd.B = f.B; sd.N = f.N;
+    }
+    if (!sd.frontFacing && (m.hdrFlags & HF_DoubleSided)) sd.N = -sd.N;
     return sd;
 }
 

@@ -146,6 +146,20 @@ class PltptEnvMapData(C.Structure):
 assert C.sizeof(PltptEnvMapData) == 112
 
 
+class PltptTextureDesc(C.Structure):
+    """One material texture (mip 0, linear layout); include/pltpt.h."""
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class PltptSamplerDesc(C.Structure):
+    """Sampler state (Core/API/Sampler.h:50-66); include/pltpt.h."""
+    _fields_ = [("magFilter", C.c_uint32), ("addressU", C.c_uint32), ("addressV", C.c_uint32), ("_pad", C.c_uint32), ("borderColor", C.c_float * 4)]
+
+
+TEXTURE_FORMATS = {"rgba32f": 0, "rgba8": 1, "rgba8_srgb": 2, "rgba16f": 3}
+assert C.sizeof(PltptTextureDesc) == 24 and C.sizeof(PltptSamplerDesc) == 32
+
+
 class PltptSceneDesc(C.Structure):
     _fields_ = [
         ("vertices", C.c_void_p), ("vertexCount", C.c_uint32),
@@ -165,6 +179,8 @@ class PltptSceneDesc(C.Structure):
         ("pointersAreDevice", C.c_uint32),
         ("envMapTexels", C.c_void_p), ("envMapWidth", C.c_uint32), ("envMapHeight", C.c_uint32),
         ("envMap", PltptEnvMapData),
+        ("textures", C.c_void_p), ("textureCount", C.c_uint32),
+        ("samplers", C.c_void_p), ("samplerCount", C.c_uint32),
     ]
 
 

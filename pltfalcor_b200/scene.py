@@ -327,6 +327,7 @@ class SceneBuffers:
         self.arrays = arrays
         self.scalars = scalars
         self._keep = None
+        self._keep_desc = []  # ctypes descriptor arrays handed out by desc()
 
     def desc(self, arrays=None, device=False) -> L.PltptSceneDesc:
         a = arrays or self.arrays
@@ -362,6 +363,21 @@ class SceneBuffers:
             d.envMap.invTransform[:] = [float(x) for x in np.asarray(e["invTransform"], np.float32).reshape(-1)]
             d.envMap.tint[:] = [float(x) for x in e["tint"]]
             d.envMap.intensity = float(e["intensity"])
+        tex = s.get("textures") or []
+        if tex:  # descriptor arrays are host memory in both cases; they must outlive the call that reads `d`
+            td = (L.PltptTextureDesc * len(tex))()
+            for k, (w, h, fmt) in enumerate(tex):
+                td[k].texels, td[k].width, td[k].height, td[k].format = ptr(f"texture{k}"), w, h, fmt
+            d.textures, d.textureCount = C.cast(td, C.c_void_p), len(tex)
+            self._keep_desc.append(td)
+        smp = s.get("samplers") or []
+        if smp:
+            sd = (L.PltptSamplerDesc * len(smp))()
+            for k, (flt, au, av, border) in enumerate(smp):
+                sd[k].magFilter, sd[k].addressU, sd[k].addressV = flt, au, av
+                sd[k].borderColor[:] = border
+            d.samplers, d.samplerCount = C.cast(sd, C.c_void_p), len(smp)
+            self._keep_desc.append(sd)
         return d
 
     def to_device(self, torch, device="cuda:0"):
@@ -451,6 +467,41 @@ class SceneBuilder:
         self.profiles = []
         self.lights = []
         self.env = None  # (texels HxWx4 f32, EnvMapData dict)
+        self.tangents = {}  # mesh index -> (n, 4) tangents or None
+        self.textures = []  # (texels array, format name)
+        self.samplers = []  # (magFilter, addressU, addressV, borderColor)
+
+    # -- material textures (MaterialSystem.slang:283-291; BasicMaterialData.slang:92-100 slot order)
+    TEX_SLOTS = {"baseColor": 0, "specular": 1, "emissive": 2, "normalMap": 3, "transmission": 4, "displacement": 5, "data1": 6, "data2": 7}
+
+    def add_texture(self, texels, fmt="rgba32f"):
+        """texels: (H, W, 4) float32 for rgba32f, float16 for rgba16f, uint8 for rgba8 / rgba8_srgb.  Returns the texture ID."""
+        dt = {"rgba32f": np.float32, "rgba16f": np.float16, "rgba8": np.uint8, "rgba8_srgb": np.uint8}[fmt]
+        t = np.ascontiguousarray(texels, dt)
+        assert t.ndim == 3 and t.shape[2] == 4
+        self.textures.append((t, fmt))
+        return len(self.textures) - 1
+
+    def add_sampler(self, linear=True, address_u=0, address_v=0, border=(0, 0, 0, 0)):
+        """Sampler IDs index `samplers`; without any sampler every material uses the default (linear, wrap)."""
+        self.samplers.append((1 if linear else 0, int(address_u), int(address_v), tuple(float(x) for x in border)))
+        return len(self.samplers) - 1
+
+    def set_texture(self, material, slot, texture_id, normal_map_type=1):
+        """Points a material's TextureHandle at a texture (TextureHandle::setTextureID: mode = Texture).  For the normal-map slot the
+        BasicMaterialData flags also get the NormalMapType (1 = RGB, 2 = RG)."""
+        m = self.materials[material]
+        m["tex"][self.TEX_SLOTS[slot]] = (1 << 29) | int(texture_id)
+        if slot == "normalMap":
+            m["flags"] = (int(m["flags"]) & ~(3 << 1)) | (int(normal_map_type) << 1)
+
+    def set_sampler(self, material, sampler_id):
+        m = self.materials[material]
+        m["header"][1] = (int(m["header"][1]) & ~(0xFF << 17)) | (int(sampler_id) << 17)
+
+    def set_alpha_mode(self, material, mask=True, threshold=0.5):
+        m = self.materials[material]
+        m["header"][1] = (int(m["header"][1]) & ~0x1FFFF) | int(_half_bits(threshold)) | (int(mask) << 16)
 
     def set_env_map(self, texels, intensity=1.0, tint=(1.0, 1.0, 1.0), rot_y=0.0):
         """EnvMap (Scene/Lights/EnvMap.cpp:60-110): lat-long RGBA32F texels; `rot_y` (radians) is the env map's rotation about +y
@@ -562,10 +613,13 @@ class SceneBuilder:
         return self._add(m)
 
     # -- geometry
-    def add_mesh(self, mesh, material, matrix=None):
+    def add_mesh(self, mesh, material, matrix=None, tangents=None):
+        """`tangents`: optional (n, 4) per-vertex tangent with handedness in w (needed for normal maps: a mesh without tangents gets an
+        invented frame and modifyTangentSpace is skipped, MaterialFactory.slang:112-120)."""
         P, N, UV, I = mesh
         self.meshes.append((np.asarray(P, f32), np.asarray(N, f32), np.asarray(UV, f32), np.asarray(I, np.uint32),
                             material, np.eye(4, dtype=f32) if matrix is None else np.asarray(matrix, f32)))
+        self.tangents[len(self.meshes) - 1] = None if tangents is None else np.asarray(tangents, f32)
         return len(self.meshes) - 1
 
     def add_instance(self, mesh_index, material, matrix):
@@ -645,7 +699,7 @@ class SceneBuilder:
         vb, ib, max_prims = 0, 0, 0
         mesh_offsets = []
         for i, (P, N, UV, I, material, M) in enumerate(self.meshes):
-            verts.append(pack_vertices(P, N, UV))
+            verts.append(pack_vertices(P, N, UV, self.tangents.get(i)))
             idx.append(I)
             md = np.zeros((), L.mesh_desc_dtype)
             md["vbOffset"], md["ibOffset"], md["vertexCount"], md["indexCount"], md["materialID"] = vb, ib, len(P), len(I), material
@@ -726,6 +780,10 @@ class SceneBuilder:
         if self.env is not None:
             arrays["envMapTexels"] = self.env[0]
             scalars.update(envMapWidth=self.env[0].shape[1], envMapHeight=self.env[0].shape[0], envMap=self.env[1])
+        for k, (t, fmt) in enumerate(self.textures):
+            arrays[f"texture{k}"] = t
+        scalars["textures"] = [(t.shape[1], t.shape[0], L.TEXTURE_FORMATS[fmt]) for t, fmt in self.textures]
+        scalars["samplers"] = list(self.samplers)
         return SceneBuffers(arrays, scalars)
 
 
@@ -861,6 +919,102 @@ def cornell_box_closed(aspect=16.0 / 9.0, albedo=0.8):
     b.add_mesh(box([-0.6, 0.6, -0.3], [0.3, 0.6, 0.3], rot_y=0.3), gold)
     b.add_mesh(box([0.6, 0.3, 0.3], [0.3, 0.3, 0.3], rot_y=-0.25), glass)
     cam = make_camera([0.0, 1.0, 0.95], [0.0, 0.95, -1.0], focal_length=12.0, aspect=aspect)
+    return b.finalize(), cam
+
+
+def quad_tangents(mesh):
+    """Per-vertex tangents of a quad() mesh: T along increasing u (p1 - p0), handedness so that cross(N, T) * w follows increasing v."""
+    P, N, UV, I = mesh
+    t = (P[1] - P[0]) / np.linalg.norm(P[1] - P[0])
+    w = 1.0 if np.dot(np.cross(N[0], t), P[3] - P[0]) > 0 else -1.0
+    return np.tile(np.append(t, w).astype(f32), (len(P), 1))
+
+
+def procedural_textures(seed=5):
+    """Synthetic material textures (no asset files offline), one per supported format: an sRGB colour checker with per-texel noise
+    (RGBA8 sRGB, alpha 1), a tangent-space normal map of a sinusoidal bump field (RGBA8 UNORM), a specular-slot map that varies the
+    roughness (RGBA32F; .x = gamma, .y = roughness), a base-colour map in RGBA16F, and a cut-out whose alpha is exactly 0 or 1."""
+    rng = np.random.default_rng(seed)
+    H, W = 64, 96
+    y, x = np.mgrid[0:H, 0:W]
+    checker = ((x // 12 + y // 8) % 2).astype(np.float64)
+    col = np.stack([0.25 + 0.6 * checker, 0.55 - 0.3 * checker, 0.2 + 0.5 * (x / W)], -1) + rng.uniform(-0.05, 0.05, (H, W, 3))
+    albedo = np.concatenate([np.clip(col, 0, 1), np.ones((H, W, 1))], -1)
+    albedo8 = np.round(albedo * 255).astype(np.uint8)
+    u, v = (x + 0.5) / W, (y + 0.5) / H
+    dhdu, dhdv = 0.35 * np.cos(6 * np.pi * u) * np.cos(4 * np.pi * v), -0.35 * np.sin(6 * np.pi * u) * np.sin(4 * np.pi * v)
+    n = np.stack([-dhdu, -dhdv, np.ones_like(u)], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    normal8 = np.round(np.concatenate([n * 0.5 + 0.5, np.ones((H, W, 1))], -1) * 255).astype(np.uint8)
+    spec = np.zeros((32, 32, 4), f32)
+    yy, xx = np.mgrid[0:32, 0:32]
+    spec[..., 0] = 3.0                                              # gamma
+    spec[..., 1] = 0.15 + 0.35 * (0.5 + 0.5 * np.sin(xx * 0.7) * np.cos(yy * 0.5))  # roughness
+    spec[..., 2] = spec[..., 3] = 1.0
+    base16 = np.concatenate([0.2 + 0.7 * rng.uniform(size=(16, 16, 3)), np.ones((16, 16, 1))], -1).astype(np.float16)
+    cut = np.ones((16, 16, 4), f32)
+    cut[..., :3] = [0.7, 0.7, 0.2]
+    cut[..., 3] = ((xx[:16, :16] + yy[:16, :16]) % 2).astype(f32)   # alternating opaque / fully transparent texels
+    emis = np.ones((8, 8, 4), f32)
+    emis[..., 0], emis[..., 1], emis[..., 2] = 0.2 + 0.8 * (xx[:8, :8] / 7.0), 0.9, 1.0 - 0.7 * (yy[:8, :8] / 7.0)
+    return dict(albedo8=albedo8, normal8=normal8, spec=spec, base16=base16, cut=cut, emis=emis)
+
+
+def textured_scene(aspect=16.0 / 9.0):
+    """Cornell-shaped room whose materials read their parameter slots from textures (MaterialSystem.slang:283-291): an
+    sRGB base-colour map on the floor, a normal-mapped Au conductor with a roughness map on the back wall, an RGBA16F base-colour map on
+    an opaque dielectric box (clamp sampler), an emissive texture on the ceiling emitter, and an alpha cut-out (point sampler, alpha
+    exactly 0 or 1) in front of the camera that the alpha-masking of the sample stage passes through."""
+    b = SceneBuilder()
+    tex = procedural_textures()
+    au = b.add_ior_profiles("Au")
+    lamp = b.add_emission_profile(LAMP, 1.0)
+    t_albedo = b.add_texture(tex["albedo8"], "rgba8_srgb")
+    t_normal = b.add_texture(tex["normal8"], "rgba8")
+    t_spec = b.add_texture(tex["spec"], "rgba32f")
+    t_base16 = b.add_texture(tex["base16"], "rgba16f")
+    t_cut = b.add_texture(tex["cut"], "rgba32f")
+    t_emis = b.add_texture(tex["emis"], "rgba32f")
+    s_wrap = b.add_sampler(True, 0, 0)
+    s_clamp = b.add_sampler(True, 2, 2)
+    s_point = b.add_sampler(False, 1, 4)          # point filter, mirror in u, mirror-once in v
+    s_border = b.add_sampler(True, 3, 3, (0.1, 0.6, 0.1, 1.0))
+    white = b.add_diffuse((0.73, 0.73, 0.73))
+    floor = b.add_diffuse((1.0, 1.0, 1.0))
+    b.set_texture(floor, "baseColor", t_albedo); b.set_sampler(floor, s_wrap)
+    red = b.add_diffuse((0.65, 0.05, 0.05))
+    green = b.add_diffuse((1.0, 1.0, 1.0))
+    b.set_texture(green, "baseColor", t_base16); b.set_sampler(green, s_border)
+    light = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    b.set_texture(light, "emissive", t_emis); b.set_sampler(light, s_clamp)
+    gold = b.add_conductor(au, roughness=0.3, gamma=3.0)
+    b.set_texture(gold, "specular", t_spec); b.set_texture(gold, "normalMap", t_normal, 1); b.set_sampler(gold, s_wrap)
+    coat = b.add_opaque_dielectric((1.0, 1.0, 1.0), roughness=0.2)
+    b.set_texture(coat, "baseColor", t_base16); b.set_texture(coat, "normalMap", t_normal, 2); b.set_sampler(coat, s_clamp)
+    cutout = b.add_diffuse((1.0, 1.0, 1.0), double_sided=True)
+    b.set_texture(cutout, "baseColor", t_cut); b.set_sampler(cutout, s_point)
+    X = 1.6
+    m = quad([-X, 0, 1], [X, 0, 1], [X, 0, -1], [-X, 0, -1]); m = (m[0], m[1], m[2] * np.array([3.0, 2.0], f32), m[3])
+    b.add_mesh(m, floor)                                                                                  # floor, uv tiled 3 x 2 (wrap)
+    b.add_mesh(quad([-X, 2, -1], [X, 2, -1], [X, 2, 1], [-X, 2, 1]), white)
+    back = quad([-X, 0, -1], [X, 0, -1], [X, 2, -1], [-X, 2, -1])
+    b.add_mesh(back, gold, tangents=quad_tangents(back))                                                  # normal-mapped conductor wall
+    b.add_mesh(quad([-X, 0, 1], [-X, 0, -1], [-X, 2, -1], [-X, 2, 1]), red)
+    rw = quad([X, 0, -1], [X, 0, 1], [X, 2, 1], [X, 2, -1]); rw = (rw[0], rw[1], rw[2] * np.array([1.5, 1.5], f32) - np.array([0.25, 0.25], f32), rw[3])
+    b.add_mesh(rw, green)                                                                                 # uv beyond [0,1]: border colour
+    b.add_mesh(quad([-0.4, 1.995, -0.4], [0.4, 1.995, -0.4], [0.4, 1.995, 0.4], [-0.4, 1.995, 0.4]), light)
+    bx = box([0.5, 0.35, 0.2], [0.35, 0.35, 0.35], rot_y=-0.3)
+    P, N, UV, I = bx
+    T = np.zeros((len(P), 4), f32)                # per-face tangents: any unit vector orthogonal to the face normal, w = +1
+    for i in range(len(P)):
+        a = np.array([0.0, 1.0, 0.0]) if abs(N[i][1]) < 0.9 else np.array([1.0, 0.0, 0.0])
+        t = np.cross(a, N[i]); t /= np.linalg.norm(t)
+        T[i] = [t[0], t[1], t[2], 1.0]
+    b.add_mesh(bx, coat, tangents=T)
+    cq = quad([-1.2, 0.3, 0.6], [-0.2, 0.3, 0.6], [-0.2, 1.3, 0.6], [-1.2, 1.3, 0.6])
+    cq = (cq[0], cq[1], cq[2] * np.array([1.0, 2.5], f32) - np.array([0.0, 1.0], f32), cq[3])               # v in [-1, 1.5]: mirror-once
+    b.add_mesh(cq, cutout)
+    cam = make_camera([0.0, 1.0, 3.5], [0.0, 1.0, 0.0], focal_length=35.0, aspect=aspect)
     return b.finalize(), cam
 
 

@@ -17,7 +17,8 @@ def pytest_sessionfinish(session, exitstatus):
     import json
     from tests import parity
     out = os.path.join(ROOT, "gpurun_out")
-    for name, data in (("parity_metrics.json", parity.METRICS), ("image_parity.json", parity.IMAGE_PARITY)):
+    tag = os.environ.get("PLTPT_PARITY_TAG", "")  # development: keeps the figures of a library variant (PLTPT_LIB) apart
+    for name, data in ((tag + "parity_metrics.json", parity.METRICS), (tag + "image_parity.json", parity.IMAGE_PARITY)):
         if not data:
             continue
         os.makedirs(out, exist_ok=True)

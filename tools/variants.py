@@ -19,6 +19,16 @@ VDIR = os.path.join(B._HERE, "build", "variants")
 VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their outcomes are listed in DESIGN.md section 3
     "base": {},
     "stage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=1"]},                          # k_unwind_step with cp.async staging of the thread's next item
+    "fm_flags": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true"]},
+    "fm_u": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"]},
+    "fm_uc": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true"]},
+    "ufm_u": {"stage_unwind.cu": ["-use_fast_math", "-DPLT_FAST_MATH=1"]},
+    "fm_mb5": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_MINB_UNWIND_STEP=5"]},
+    "fm_mb3": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_MINB_UNWIND_STEP=3"]},
+    "fm_unroll": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_LAMBDA_UNROLL=1"]},
+    "c_fmad": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-fmad=true"]},
+    "c_div": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-div=false"]},
+    "c_sqrt": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-sqrt=false"]},
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
