@@ -504,19 +504,31 @@ def main():
             # (R + F = 436 B).  Traversal kernels (closest-hit trace, shadow rays, manifold-walk trial rays run the same node /
             # triangle code): unit = one BVH node visited or leaf triangle tested, 80 B / 48 B, against their summed duration.
             trav_ms = sum(kms[k] for k in TRAVERSAL_CLASSES)
-            top = max(kernels, key=lambda k: kernels[k]["ms_per_frame"])
-            if top in TRAVERSAL_CLASSES or trav_ms > kms.get("unwind_step", 0.0) * 1.5:
-                bvh_bytes = stats["traversalNodesVisited"] * NODE_BYTES + stats["traversalTrianglesTested"] * TRI_BYTES
-                launches = sum(kcount[k] for k in TRAVERSAL_CLASSES)
-                roof = {"kernel": "k_trace + k_shadow_trace + k_mnee_walk (BVH traversal: " + top + " is the largest class)", "kernel_ms": trav_ms / max(launches, 1), "launches": int(launches),
-                        "units_per_launch": (stats["traversalNodesVisited"] + stats["traversalTrianglesTested"]) / max(launches, 1),
-                        "algorithmic_bytes_per_unit": "80 B per node visited, 48 B per leaf triangle tested", "achieved": bvh_bytes / (trav_ms * 1e-3) / 1e9,
-                        "share_of_frame": trav_ms / frames / timed_sum if timed_sum else None, "traffic_key": args.config + ":traversal"}
-            else:
-                k_ms_total, k_launches, units = kms["unwind_step"], kcount["unwind_step"], stats["unwindJobSteps"]
-                roof = {"kernel": "k_unwind_step", "kernel_ms": k_ms_total / k_launches, "launches": int(k_launches), "units_per_launch": units / k_launches,
-                        "algorithmic_bytes_per_unit": R_BOUNCE + F_VERTEX_FETCH, "achieved": units * (R_BOUNCE + F_VERTEX_FETCH) / (k_ms_total * 1e-3) / 1e9,
-                        "share_of_frame": kernels["unwind_step"]["share_of_frame"], "traffic_key": "k_unwind_step"}
+            bvh_bytes = stats["traversalNodesVisited"] * NODE_BYTES + stats["traversalTrianglesTested"] * TRI_BYTES
+            trav_launches = sum(kcount[k] for k in TRAVERSAL_CLASSES)
+            # candidates: (kernel name, summed ms, launches, units, algorithmic bytes per unit or None for the traversal group, traffic key)
+            cand = {
+                "unwind_step": ("k_unwind_step", kms.get("unwind_step", 0.0), kcount.get("unwind_step", 0), stats["unwindJobSteps"], R_BOUNCE + F_VERTEX_FETCH, "k_unwind_step"),
+                "shade": ("k_shade", kms.get("shade", 0.0), kcount.get("shade", 0), stats["totalPathVertices"], F_VERTEX_FETCH + R_BOUNCE, "k_shade"),
+                "connect_a": ("k_connect_a", kms.get("connect_a", 0.0), kcount.get("connect_a", 0), stats["totalPathVertices"], R_BOUNCE + F_VERTEX_FETCH + LIGHT_FETCH, "k_connect_a"),
+                "traversal": ("k_trace + k_shadow_trace + k_mnee_walk (BVH traversal)", trav_ms, trav_launches, stats["traversalNodesVisited"] + stats["traversalTrianglesTested"], None, args.config + ":traversal"),
+            }
+            per_kernel = {}
+            for key, (name, ms_total, launches, units, bpu, tkey) in cand.items():
+                if not launches or ms_total <= 0:
+                    continue
+                alg = bvh_bytes if bpu is None else units * bpu
+                per_kernel[key] = {"kernel": name, "ms_per_frame": ms_total / frames, "share_of_frame": ms_total / frames / timed_sum if timed_sum else None, "launches": int(launches),
+                                   "units_per_launch": units / launches, "algorithmic_bytes_per_unit": bpu if bpu is not None else "80 B per node visited, 48 B per leaf triangle tested",
+                                   "achieved": alg / (ms_total * 1e-3) / 1e9, "frac": alg / (ms_total * 1e-3) / 1e9 / hbm_peak, "traffic_key": tkey}
+            # the dominant kernel (largest share of the step) is the one the roofline block reports; the others ride along in roofline.kernels
+            top = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_frame"])
+            t = per_kernel[top]
+            roof = {"kernel": t["kernel"], "kernel_ms": t["ms_per_frame"] * frames / t["launches"], "launches": t["launches"], "units_per_launch": t["units_per_launch"],
+                    "algorithmic_bytes_per_unit": t["algorithmic_bytes_per_unit"], "achieved": t["achieved"], "share_of_frame": t["share_of_frame"], "traffic_key": t["traffic_key"]}
+            for v in per_kernel.values():
+                v["traffic"] = ncu_traffic(v.pop("traffic_key"))
+            roof["kernels"] = per_kernel
             roof["timer"] = "CUDA events after every launch on the launching stream; frames run one at a time (sequential_ms_per_frame) so that every kernel is timed alone"
             traffic = ncu_traffic(roof.pop("traffic_key"))
             out["sequential_ms_per_frame"] = seq_ms

@@ -366,6 +366,15 @@ PLTPT_API int pltpt_render_accumulate(PltptHandle h, uint32_t firstFrame, uint32
 PLTPT_API int pltpt_render_accumulate_rows(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount,
                                            const PltptCameraData* camera, uint32_t width, uint32_t height,
                                            uint32_t rowBegin, uint32_t rowEnd, double* accum, void* stream);
+/* AccumulatePass stepped frame by frame, all three precision modes (Accumulate.cs.slang:73-198; the PLTPathTracer.py graph runs the
+ * colour through Double and the albedo / normal guides through Single): folds `curFrame` (RGBA32F) into the running state and writes
+ * the pass's output.  `accumCount` = frames accumulated before this one (gAccumCount); state buffers start zeroed: `lastFrameSum` is
+ * RGBA32F for the single-precision modes and RGBA64F (4 doubles per pixel) for Double, `lastFrameCorr` (RGBA32F) only for
+ * SingleCompensated.  movingAverage != 0 selects the exponential form the pass switches to at its frame limit (OverflowMode::EMA).
+ * Device pointers.  (pltpt_render_accumulate is the fused form of Double for a whole accumulation.) */
+enum { PLTPT_ACCUMULATE_SINGLE = 0, PLTPT_ACCUMULATE_SINGLE_COMPENSATED = 1, PLTPT_ACCUMULATE_DOUBLE = 2 };
+PLTPT_API int pltpt_accumulate_frame(PltptHandle h, uint32_t precision, uint32_t accumCount, int movingAverage, uint32_t width, uint32_t height,
+                                     const float* curFrame, void* lastFrameSum, float* lastFrameCorr, float* outputFrame, void* stream);
 /* AccumulatePass output (Accumulate.cs.slang:185-197): color = sum / accumulated frame count, alpha 1.  Device pointers. */
 PLTPT_API int pltpt_resolve_accumulated(PltptHandle h, const double* accum, uint32_t width, uint32_t height, float* color, void* stream);
 /* One converged image for a caller with host memory only: `frameCount` frames accumulated on the device in fp64, resolved, ONE

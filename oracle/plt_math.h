@@ -13,6 +13,11 @@
 
 namespace orc {
 
+// normalize(): an HLSL intrinsic whose precision the reference leaves to the GPU (DXIL lowers it to v * rsqrt(dot(v, v)) with an approximate
+// rsqrt).  The oracle DEFINES it as v * (1 / sqrt(dot(v, v))) with a correctly rounded square root and reciprocal: three products instead
+// of three divisions -- exactly reproducible on the CPU and on the GPU, and a sixth of the sample stage's instructions cheaper there than
+// the v / length(v) form rounds 1 and 2 started with.  Divisions the Slang text spells out stay divisions.
+//
 // HLSL / DXIL min and max return the non-NaN operand (IEEE 754-2008 minNum / maxNum), exactly like CUDA fminf / fmaxf and
 // unlike std::min / std::max.  Every min / max of the restated Slang code goes through these.
 inline float hlsl_max(float a, float b) { return std::fmax(a, b); }
@@ -97,7 +102,7 @@ struct float4 {
     inline bool all_eq(T a, float s) { for (int i = 0; i < N; ++i) if (!(a[i] == s)) return false; return true; } \
     inline bool all_finite(T a) { for (int i = 0; i < N; ++i) if (!std::isfinite(a[i])) return false; return true; } \
     inline float length(T a) { return std::sqrt(dot(a, a)); }                                                  \
-    inline T normalize(T a) { return a / length(a); }
+    inline T normalize(T a) { return a * (1.f / length(a)); }
 
 ORC_VEC_OPS(float2, 2)
 ORC_VEC_OPS(float3, 3)

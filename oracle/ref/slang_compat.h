@@ -176,7 +176,7 @@ template <class T, int N> T dot(const vec<T, N>& a, const vec<T, N>& b) { T r = 
 inline float dot(float a, float b) { return a * b; }
 template <int N> float length(const vec<float, N>& a) { return std::sqrt(dot(a, a)); }
 template <int N> float distance(const vec<float, N>& a, const vec<float, N>& b) { return length(a - b); }
-template <int N> vec<float, N> normalize(const vec<float, N>& a) { return a / length(a); }
+template <int N> vec<float, N> normalize(const vec<float, N>& a) { return a * (1.f / length(a)); }  // the oracle's definition of the intrinsic (oracle/plt_math.h)
 inline float3 cross(const float3& a, const float3& b) { return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 template <int N> vec<float, N> reflect(const vec<float, N>& i, const vec<float, N>& n) { return i - 2.f * dot(n, i) * n; }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
     "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
     "pltpt_render_accumulate_rows", "pltpt_resolve_accumulated", "pltpt_render_accumulate_host", "pltpt_render_accumulate_multi",
-    "pltpt_texture_sample",
+    "pltpt_texture_sample", "pltpt_accumulate_frame",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
         _lib.pltpt_get_light_collection.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
+        _lib.pltpt_accumulate_frame.argtypes = [vp, u32, u32, C.c_int, u32, u32, vp, vp, vp, vp, vp]
         _lib.pltpt_texture_sample.argtypes = [vp, u32, u32, vp, u32, vp, vp, vp]
     return _lib
 
@@ -266,6 +267,11 @@ class Pltpt:
     def envmap_sample(self, rnd, out, stream=None):
         """rnd: (n,2) in [0,1); out: (n,8) {dir xyz, pdf, Le rgb, 0}."""
         _check(lib().pltpt_envmap_sample(self.h, rnd.shape[0], _dp(rnd), _dp(out), stream))
+
+    def accumulate_frame(self, precision, accum_count, cur, last_sum, out, last_corr=None, moving_average=False, stream=None):
+        """AccumulatePass, one frame (precision 0 Single, 1 SingleCompensated, 2 Double); torch CUDA tensors, cur / out (H, W, 4) float32."""
+        h, w = cur.shape[:2]
+        _check(lib().pltpt_accumulate_frame(self.h, precision, accum_count, int(moving_average), w, h, _dp(cur), _dp(last_sum), _dp(last_corr) if last_corr is not None else None, _dp(out), stream))
 
     def texture_sample(self, handle, sampler_id, uv, out, uniform=(0.0, 0.0, 0.0, 0.0), stream=None):
         """uv: (n,2); out: (n,4) — torch CUDA float32 tensors; `handle` is a TextureHandle word (mode << 29 | textureID)."""

@@ -713,6 +713,76 @@ extern "C" int pltpt_render_accumulate_rows(PltptHandle h, uint32_t firstFrame, 
     if (frameStep == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frameStep must be > 0");
     return renderAccumulateRows(h, firstFrame, frameStep, frameCount, cam, w, hgt, rowBegin, rowEnd, accum, (cudaStream_t)stream);
 }
+namespace {
+// AccumulatePass, one frame (Source/RenderPasses/AccumulatePass/Accumulate.cs.slang:73-198): the three precision modes with the
+// reference's operations in the reference's order, so a host that steps the pass frame by frame gets the pass's own numbers.
+__global__ void __launch_bounds__(256) k_accumulate_frame(uint32_t precision, uint32_t accumCount, bool movingAverage, size_t pixels, const float4* __restrict__ cur,
+                                                          void* __restrict__ lastSum, float4* __restrict__ lastCorr, float4* __restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const float4 c = cur[i];
+    if (precision == PLTPT_ACCUMULATE_SINGLE) {  // accumulateSingle, :76-112
+        float4* sumBuf = reinterpret_cast<float4*>(lastSum);
+        const float w = __fdiv_rn(1.f, float(accumCount + 1u));
+        const float4 last = sumBuf[i];
+        float4 o;
+        if (movingAverage) {  // lerp(last, cur, w) = last + (cur - last) * w
+            o = mk4(__fadd_rn(last.x, __fmul_rn(__fsub_rn(c.x, last.x), w)), __fadd_rn(last.y, __fmul_rn(__fsub_rn(c.y, last.y), w)),
+                    __fadd_rn(last.z, __fmul_rn(__fsub_rn(c.z, last.z), w)), __fadd_rn(last.w, __fmul_rn(__fsub_rn(c.w, last.w), w)));
+            sumBuf[i] = o;
+        } else {
+            const float4 sum = mk4(__fadd_rn(last.x, c.x), __fadd_rn(last.y, c.y), __fadd_rn(last.z, c.z), __fadd_rn(last.w, c.w));
+            o = mk4(__fmul_rn(sum.x, w), __fmul_rn(sum.y, w), __fmul_rn(sum.z, w), __fmul_rn(sum.w, w));
+            sumBuf[i] = sum;
+        }
+        out[i] = o;
+    } else if (precision == PLTPT_ACCUMULATE_SINGLE_COMPENSATED) {  // accumulateSingleCompensated, :116-145 (Kahan)
+        float4* sumBuf = reinterpret_cast<float4*>(lastSum);
+        const float4 sum = sumBuf[i], corr = lastCorr[i];
+        const float n = float(accumCount + 1u);
+        float s[4] = {sum.x, sum.y, sum.z, sum.w}, k[4] = {corr.x, corr.y, corr.z, corr.w}, v[4] = {c.x, c.y, c.z, c.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float y = __fsub_rn(v[j], k[j]);
+            const float next = __fadd_rn(s[j], y);
+            o[j] = __fdiv_rn(next, n);
+            k[j] = __fsub_rn(__fsub_rn(next, s[j]), y);
+            s[j] = next;
+        }
+        sumBuf[i] = mk4(s[0], s[1], s[2], s[3]);
+        lastCorr[i] = mk4(k[0], k[1], k[2], k[3]);
+        out[i] = mk4(o[0], o[1], o[2], o[3]);
+    } else {  // accumulateDouble, :149-198
+        double* sum = reinterpret_cast<double*>(lastSum) + 4 * i;
+        const double w = __ddiv_rn(1.0, double(accumCount + 1u));
+        const float v[4] = {c.x, c.y, c.z, c.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = sum[j];
+            if (movingAverage) { a = __dadd_rn(__dmul_rn(a, __dsub_rn(1.0, w)), __dmul_rn(double(v[j]), w)); o[j] = float(a); }
+            else { a = __dadd_rn(a, double(v[j])); o[j] = float(__dmul_rn(a, w)); }
+            sum[j] = a;
+        }
+        out[i] = mk4(o[0], o[1], o[2], o[3]);
+    }
+}
+}  // namespace
+extern "C" int pltpt_accumulate_frame(PltptHandle h, uint32_t precision, uint32_t accumCount, int movingAverage, uint32_t w, uint32_t hgt, const float* curFrame,
+                                      void* lastFrameSum, float* lastFrameCorr, float* outputFrame, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (precision > PLTPT_ACCUMULATE_DOUBLE) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown accumulation precision");
+    if (!curFrame || !lastFrameSum || !outputFrame || (precision == PLTPT_ACCUMULATE_SINGLE_COMPENSATED && !lastFrameCorr)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    if (movingAverage && precision == PLTPT_ACCUMULATE_SINGLE_COMPENSATED) return fail(PLTPT_ERR_INVALID_ARGUMENT, "the compensated mode has no moving-average form (Accumulate.cs.slang:116-145)");
+    const size_t pixels = size_t(w) * hgt;
+    if (pixels == 0) return PLTPT_OK;
+    PLT_CUDA(cudaSetDevice(h->device));
+    k_accumulate_frame<<<uint32_t((pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(precision, accumCount, movingAverage != 0, pixels, reinterpret_cast<const float4*>(curFrame), lastFrameSum,
+                                                                                      reinterpret_cast<float4*>(lastFrameCorr), reinterpret_cast<float4*>(outputFrame));
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
 extern "C" int pltpt_resolve_accumulated(PltptHandle h, const double* accum, uint32_t w, uint32_t hgt, float* color, void* stream) {
     if (!h || !accum || !color) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (w == 0 || hgt == 0) return fail(PLTPT_ERR_INVALID_ARGUMENT, "empty image");

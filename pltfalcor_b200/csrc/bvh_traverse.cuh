@@ -90,13 +90,34 @@ PLT_D void rayConstInit(RayConst& R, float3 o, float3 d, float tmin, float tmax)
     R.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
     R.o = o; R.tmin = tmin; R.tmax = tmax;
 }
-// Returns true when ANY and a triangle was accepted.
+// The triangles `triMask` (bits = slots from `triBase`) of the intersected leaf children of one node.  Returns true when ANY and a triangle
+// was accepted.
 template <bool ANY>
-PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, const RayConst& R, uint32_t ni, Hit& best, uint32_t* stack, float* stackT, int& sp,
-                       uint32_t* overflow, TraversalCounters* tc) {
+PLT_D bool testLeafTriangles(const BvhTri* __restrict__ tris, const RayConst& R, uint32_t triBase, uint32_t triMask, Hit& best, TraversalCounters* tc) {
+    while (triMask) {
+        const uint32_t k = uint32_t(__ffs(int(triMask))) - 1u;
+        triMask &= triMask - 1u;
+        const float4* tp = reinterpret_cast<const float4*>(tris + triBase + k);
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        float t, u, v;
+        if (tc) ++tc->tris;
+        if (!intersectTri(R.rp, q0, q1, q2, R.tmin, R.tmax, t, u, v)) continue;
+        if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
+        const uint32_t g = __float_as_uint(q2.w);
+        if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
+        best.t = t; best.u = u; best.v = v;
+        best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
+    }
+    return false;
+}
+// One popped node: slab tests of its children, ordered push of the intersected inner children; the triangles of its intersected leaf
+// children are returned in (triBaseOut, triMaskOut) for testLeafTriangles() -- at once (traverseBvh) or batched over the lanes of a warp
+// (travPersistent with PLT_DEFER_LEAVES).
+template <bool ANY>
+PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uint32_t ni, float bestT, uint32_t* stack, float* stackT, int& sp,
+                       uint32_t* overflow, TraversalCounters* tc, uint32_t& triBaseOut, uint32_t& triMaskOut) {
     const float3 o = R.o;
-    const float idx = R.idx, idy = R.idy, idz = R.idz, tmin = R.tmin, tmax = R.tmax;
-    const RayPrep& rp = R.rp;
+    const float idx = R.idx, idy = R.idy, idz = R.idz, tmin = R.tmin;
     const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
     if (tc) ++tc->nodes;
         const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
@@ -117,10 +138,18 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
         const uint32_t nxA = negx ? n3.z : n2.x, nxB = negx ? n3.w : n2.y, fxA = negx ? n2.x : n3.z, fxB = negx ? n2.y : n3.w;
         const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
         const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
+#ifndef PLT_PUSH_NEAREST
+#define PLT_PUSH_NEAREST 0  // 1: intersected inner children are pushed straight from the slab-test loop and only the nearest is moved to the top
+#endif
+#if PLT_PUSH_NEAREST
+        const int sp0 = sp;
+#else
         float nearT[8];
-        uint32_t innerHits = 0, triMask = 0;
+        uint32_t innerHits = 0;
+#endif
+        uint32_t triMask = 0;
         // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
-        const float tfarLimit = best.t * 1.000002f;
+        const float tfarLimit = bestT * 1.000002f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xffu;
@@ -133,25 +162,33 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
             if (!(tn <= tf)) continue;
+#if PLT_PUSH_NEAREST
+            if (inner) {
+                if (sp < kTraversalStack) {
+                    if (!ANY) stackT[sp] = tn;
+                    stack[sp++] = childBase + __popc(imask & ((1u << i) - 1u));
+                } else if (overflow) atomicAdd(overflow, 1u);
+            }
+#else
             if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
+#endif
             else triMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);  // the leaf's triangles: slots [offset, offset + count) of this node's <= 24
         }
-        // The triangles of all intersected leaf children in ONE loop after the slab tests: tested inside the unrolled child loop, every
-        // child was a separate divergence point (a lane with a leaf hit ran the triangle test while its 31 neighbours waited).
-        while (triMask) {
-            const uint32_t k = uint32_t(__ffs(int(triMask))) - 1u;
-            triMask &= triMask - 1u;
-            const float4* tp = reinterpret_cast<const float4*>(tris + triBase + k);
-            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-            float t, u, v;
-            if (tc) ++tc->tris;
-            if (!intersectTri(rp, q0, q1, q2, tmin, tmax, t, u, v)) continue;
-            if (ANY) { best.t = t; best.instanceID = __float_as_uint(q0.w); return true; }
-            const uint32_t g = __float_as_uint(q2.w);
-            if (best.valid() && (t > best.t || (t == best.t && g > best.globalIndex))) continue;
-            best.t = t; best.u = u; best.v = v;
-            best.instanceID = __float_as_uint(q0.w); best.primitiveIndex = __float_as_uint(q1.w); best.globalIndex = g;
+        // The triangles of all intersected leaf children are tested in ONE loop after the slab tests (testLeafTriangles): tested inside the
+        // unrolled child loop, every child was a separate divergence point.
+        triBaseOut = triBase; triMaskOut = triMask;
+#if PLT_PUSH_NEAREST
+        // the nearest of the children just pushed goes on top (popped next); the others stay in slot order and are culled at pop time
+        if (!ANY && sp - sp0 > 1) {
+            int bestK = sp0;
+            float bt = stackT[sp0];
+            for (int k = sp0 + 1; k < sp; ++k) { const float t = stackT[k]; if (t < bt) { bt = t; bestK = k; } }
+            if (bestK != sp - 1) {
+                const uint32_t n = stack[bestK]; stack[bestK] = stack[sp - 1]; stack[sp - 1] = n;
+                stackT[bestK] = stackT[sp - 1]; stackT[sp - 1] = bt;
+            }
         }
+#else
         // push the intersected inner children, farthest first, so the nearest is popped next
         while (innerHits) {
             int far = -1;
@@ -168,7 +205,7 @@ PLT_D bool processNode(const BvhNode* __restrict__ nodes, const BvhTri* __restri
                 stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
             } else if (overflow) atomicAdd(overflow, 1u);
         }
-    return false;
+#endif
 }
 // One ray to completion in the calling thread: the same processNode() the persistent-lane driver steps through (one node body, so the
 // bit-exact hit-ID checks of either driver cover the arithmetic of both; measured equal to a hand-inlined copy, profiles/r2a_variants.log).
@@ -187,7 +224,9 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
     while (sp > 0) {
         const uint32_t ni = stack[--sp];
         if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit in processNode: exact-t ties are still visited)
-        if (processNode<ANY>(nodes, tris, R, ni, best, stack, stackT, sp, overflow, tc)) return true;
+        uint32_t triBase, triMask;
+        processNode<ANY>(nodes, R, ni, best.t, stack, stackT, sp, overflow, tc, triBase, triMask);
+        if (testLeafTriangles<ANY>(tris, R, triBase, triMask, best, tc)) return true;
     }
     return best.valid();
 }
@@ -216,15 +255,38 @@ PLT_D bool travStep(const BvhNode* __restrict__ nodes, const BvhTri* __restrict_
     if (T.sp <= 0) return true;
     const uint32_t ni = T.stack[--T.sp];
     if (!ANY && T.stackT[T.sp] > T.best.t * 1.000002f) return T.sp == 0;
-    if (processNode<ANY>(nodes, tris, T.R, ni, T.best, T.stack, T.stackT, T.sp, overflow, tc)) { T.sp = 0; return true; }
+    uint32_t triBase, triMask;
+    processNode<ANY>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
+    if (testLeafTriangles<ANY>(tris, T.R, triBase, triMask, T.best, tc)) { T.sp = 0; return true; }
     return T.sp == 0;
+}
+// The same without the triangle tests: the node's leaf triangles are handed back (triMask == 0: none).
+template <bool ANY>
+PLT_D void travStepDeferred(const BvhNode* __restrict__ nodes, Trav<ANY>& T, uint32_t* overflow, TraversalCounters* tc, uint32_t& triBase, uint32_t& triMask) {
+    triMask = 0;
+    if (T.sp <= 0) return;
+    const uint32_t ni = T.stack[--T.sp];
+    if (!ANY && T.stackT[T.sp] > T.best.t * 1.000002f) return;
+    processNode<ANY>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
 }
 
 // Persistent-lane driver for a queue of `n` rays (Aila & Laine 2009, "Understanding the Efficiency of Ray Traversal on GPUs",
 // dynamic fetch): fetch(i, o, d, tmin, tmax) loads ray i (false: nothing to trace for this entry), commit(i, hit, best) consumes its
 // result.  Idle lanes refill from `cursor` (one warp-aggregated bump) once at least kRefillLanes lanes are idle; between refills
 // every lane with a ray processes kStepsPerRound nodes.  All 32 lanes of a warp must call this together.
-constexpr int kRefillLanes = 8, kStepsPerRound = 4;
+// PLT_DEFER_LEAVES = 1: the leaf triangles a lane meets during a round are queued (at most one set per node step) and tested after the
+// round by all lanes together.  Tested inside the step, the triangle code ran for whichever 2-4 lanes of the warp had just met a leaf
+// (a quarter of the kernel's issue slots at 1.8 of 32 lanes on incoherent rays, profiles/r2o_trace_sass_segments.txt).
+#ifndef PLT_TRAV_REFILL
+#define PLT_TRAV_REFILL 8
+#endif
+#ifndef PLT_TRAV_STEPS
+#define PLT_TRAV_STEPS 4
+#endif
+#ifndef PLT_DEFER_LEAVES
+#define PLT_DEFER_LEAVES 0
+#endif
+constexpr int kRefillLanes = PLT_TRAV_REFILL, kStepsPerRound = PLT_TRAV_STEPS;
 template <bool ANY, class Fetch, class Commit>
 PLT_D void travPersistent(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, uint32_t n, uint32_t* cursor, uint32_t* overflow, TraversalCounters* tc,
                           Fetch fetch, Commit commit) {
@@ -251,10 +313,29 @@ PLT_D void travPersistent(const BvhNode* __restrict__ nodes, const BvhTri* __res
             exhausted = base + __popc(idle) >= n;  // warp-uniform
         }
         if (!__any_sync(0xffffffffu, have)) { if (exhausted) break; else continue; }
+#if PLT_DEFER_LEAVES
+        uint32_t pendBase[kStepsPerRound], pendMask[kStepsPerRound];
+        int np = 0;
+#pragma unroll 1
+        for (int s = 0; s < kStepsPerRound; ++s) {
+            if (have && T.sp > 0) {
+                uint32_t tb, tm;
+                travStepDeferred(nodes, T, overflow, tc, tb, tm);
+                if (tm) { pendBase[np] = tb; pendMask[np] = tm; ++np; }
+            }
+        }
+        bool accepted = false;
+        while (np > 0) {
+            --np;
+            if (testLeafTriangles<ANY>(tris, T.R, pendBase[np], pendMask[np], T.best, tc)) { accepted = true; break; }
+        }
+        if (have && (accepted || T.sp <= 0)) { commit(item, T.best.valid(), T.best); have = false; T.sp = 0; }
+#else
 #pragma unroll 1
         for (int s = 0; s < kStepsPerRound; ++s) {
             if (have && travStep(nodes, tris, T, overflow, tc)) { commit(item, T.best.valid(), T.best); have = false; }
         }
+#endif
     }
 }
 

@@ -197,13 +197,14 @@ PLT_D float russianRoulette(float rrVal, float u) {
 }
 // pltpt_sample.rt.slang:63-141 (scatterTriangleMeshClosestHit)
 // Returns true when the hit was alpha-masked: the origin moved behind the surface and the same ray has to be re-traced.
+template <bool kTex = true>
 PLT_D bool scatterClosestHit(const FrameParams& P, uint32_t pixel, PathState& path, const TriHit& th) {
     const uint4 hitInfo = packHit(P.sc, th);
     uint32_t materialID;
     const VertexData v = getVertexData(P.sc, th, materialID);
-    const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
+    const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
     const float3 wi = -path.dir;
-    const SD sd = prepareShadingData(P.sc, v, materialID, m, wi);
+    const SD sd = prepareShadingData<kTex>(P.sc, v, materialID, m, wi);
     if (P.opt.alphaMasking && m.opacity == .0f) {
         path.origin = sd.computeNewRayOrigin(false);
         return true;
@@ -315,6 +316,7 @@ PLT_D uint32_t tracePathCommit(const FrameParams& P, uint32_t pixel, bool hit, c
     return __ldg(&P.sc.materials[materialID].type);
 }
 // scatterTriangleMeshClosestHit on the stored hit; returns true when the path continues with a new ray.
+template <bool kTex = true>
 PLT_D bool shadePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc) {
     PathState path;
     loadPath(P, pixel, path);
@@ -323,7 +325,7 @@ PLT_D bool shadePath(const FrameParams& P, uint32_t pixel, TraversalCounters& tc
     th.instanceID = h.x; th.primitiveIndex = h.y; th.u = __uint_as_float(h.z); th.v = __uint_as_float(h.w);
     // Alpha-masked hits do not count as a bounce (pltpt_sample.rt.slang:83-87): the ray is re-traced at once from behind the
     // surface.  (Rare: kept inline instead of a round trip through the queues; bounded like the oracle's pass-through guard.)
-    for (int guard = 0; scatterClosestHit(P, pixel, path, th); ++guard) {
+    for (int guard = 0; scatterClosestHit<kTex>(P, pixel, path, th); ++guard) {
         float t;
         if (guard >= 4096 || !traceClosestHit(P, tc, path.origin, path.dir, 0.f, kFltMax, th, t)) {
             path.flags |= RF_Miss;
@@ -381,15 +383,16 @@ PLT_D EmissiveTri loadEmissiveTriangle(const DevScene& sc, uint32_t idx) {
 }
 // EmissiveLightSamplerHelpers.slang:56-74: emission = profile spectrum x rgbToSpectrum(emissionRGB), emissionRGB = texEmissive at `uv`
 // (uniform value 1)
+template <bool kTex = true>
 PLT_D void materialEvalEmissive(const FrameParams& P, const EmissiveTri& tri, float3 b, float wavelength, bool importanceSample, Rng& sg, float4& Le, float4& wl) {
     const uint32_t materialID = tri.materialID;
     const uint32_t id = __ldg(&P.sc.materials[materialID].emissionId);
     if (id != PLTPT_NO_SPECTRAL_PROFILE) {
         float3 emissionRGB = mk3(1.f);
-        if (__ldg(&P.sc.materials[materialID].hdrFlags) & HF_Textured) {
+        if (kTex && P.sc.tex.blobs && (__ldg(&P.sc.materials[materialID].hdrFlags) & HF_Textured)) {
             // EmissiveTriangle::getTexCoord (LightCollectionShared.slang:65-70)
             const float2 uv = mk2(h2f(tri.uv0 & 0xffffu), h2f(tri.uv0 >> 16)) * b.x + mk2(h2f(tri.uv1 & 0xffffu), h2f(tri.uv1 >> 16)) * b.y + mk2(h2f(tri.uv2 & 0xffffu), h2f(tri.uv2 >> 16)) * b.z;
-            const DevMaterial m = loadMaterialAt(P.sc, materialID, uv);
+            const DevMaterial m = loadMaterialAt<true>(P.sc, materialID, uv);
             emissionRGB = mk3(m.c1x, m.c1y, m.c1z);
         }
         Le = sampleSpectrum(P.sc.profiles, id, wavelength, sg, importanceSample, int(P.opt.HWSS), wl);
@@ -398,6 +401,7 @@ PLT_D void materialEvalEmissive(const FrameParams& P, const EmissiveTri& tri, fl
 }
 struct TriangleLightSample { float3 posW, normalW, dir; float distance; float4 Le, wavelengths; float pdf; };
 // EmissiveLightSamplerHelpers.slang:86-128
+template <bool kTex = true>
 PLT_D bool sampleTriangle(const FrameParams& P, float3 posW, uint32_t triangleIndex, Rng& sg, float wavelength, bool importanceSample, TriangleLightSample& ls) {
     ls.Le = mk4(0.f); ls.wavelengths = mk4(0.f); ls.pdf = 0.f;
     const EmissiveTri tri = loadEmissiveTriangle(P.sc, triangleIndex);
@@ -411,11 +415,12 @@ PLT_D bool sampleTriangle(const FrameParams& P, float3 posW, uint32_t triangleIn
     ls.normalW = tri.normal;
     const float cosTheta = dot(ls.normalW, -ls.dir);
     if (cosTheta <= 0.f) return false;
-    materialEvalEmissive(P, tri, b, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
+    materialEvalEmissive<kTex>(P, tri, b, wavelength, importanceSample, sg, ls.Le, ls.wavelengths);
     ls.pdf = distSqr / fmaxf(kFltMin, cosTheta * tri.area);
     return true;
 }
 // EmissivePowerSampler.slang:64-90 / EmissiveUniformSampler.slang:56-72
+template <bool kTex = true>
 PLT_D bool emissiveSampleLight(const FrameParams& P, float3 posW, Rng& sg, float wavelength, bool importanceSample, TriangleLightSample& ls) {
     const DevScene& sc = P.sc;
     uint32_t triangleIndex;
@@ -437,7 +442,7 @@ PLT_D bool emissiveSampleLight(const FrameParams& P, float3 posW, Rng& sg, float
         triangleIndex = __ldg(sc.activeTris + idx);
         selectionPdf = 1.f / float(sc.activeTriCount);
     }
-    if (!sampleTriangle(P, posW, triangleIndex, sg, wavelength, importanceSample, ls)) return false;
+    if (!sampleTriangle<kTex>(P, posW, triangleIndex, sg, wavelength, importanceSample, ls)) return false;
     ls.pdf *= selectionPdf;
     return true;
 }
@@ -471,10 +476,11 @@ PLT_D bool generateEnvMapSample(const FrameParams& P, const SD& sd, Rng& sg, flo
     return anyPositive(L, int(P.opt.HWSS));
 }
 // LightSampling.slangh:104-126
+template <bool kTex = true>
 PLT_D bool generateEmissiveSample(const FrameParams& P, const SD& sd, Rng& sg, float wavelength, bool importanceSample, LightSample& ls) {
     if (!P.useEmissive) return false;
     TriangleLightSample tls;
-    if (!emissiveSampleLight(P, sd.posW, sg, wavelength, importanceSample, tls)) return false;
+    if (!emissiveSampleLight<kTex>(P, sd.posW, sg, wavelength, importanceSample, tls)) return false;
     const float4 L = tls.pdf > 0.f ? tls.Le / tls.pdf : mk4(.0f);
     ls.pdf = tls.pdf;
     const float3 lightPos = computeRayOrigin(tls.posW, tls.normalW);
@@ -587,6 +593,7 @@ PLT_D void clearLightSample(LightSample& ls) {
     ls.beam.r = mk3(0.f); ls.beam.t = mk3(0.f);
 }
 // LightSampling.slangh:168-206
+template <bool kTex = true>
 PLT_D bool generateLightSample(const FrameParams& P, const SD& sd, bool sampleReflection, bool sampleTransmission, Rng& sg, Rng& tilesg, float wavelength, bool importanceSample, LightSample& ls) {
     clearLightSample(ls);
     uint32_t lightType;
@@ -595,7 +602,7 @@ PLT_D bool generateLightSample(const FrameParams& P, const SD& sd, bool sampleRe
     if (!success) return false;
     bool valid = false;
     if (P.useEnv && lightType == LT_EnvMap) valid = generateEnvMapSample(P, sd, sg, wavelength, ls);
-    if (P.useEmissive && lightType == LT_Emissive) valid = generateEmissiveSample(P, sd, sg, wavelength, importanceSample, ls);
+    if (P.useEmissive && lightType == LT_Emissive) valid = generateEmissiveSample<kTex>(P, sd, sg, wavelength, importanceSample, ls);
     if (P.useAnalytic && lightType == LT_Analytic) valid = generateAnalyticLightSample(P, sd, sg, wavelength, importanceSample, ls);
     ls.lightType = lightType;
     ls.pdf *= selectionPdf;
@@ -680,8 +687,9 @@ PLT_D uint32_t allocJob(const FrameParams& P) {
 }
 
 // pltpt_solve.rt.slang:48-66 (forwardUnwindStep)
+template <bool kTex = true>
 PLT_D void forwardUnwindStep(const FrameParams& P, uint32_t& evals, const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 wo, uint32_t lobe, Beam& beam) {
-    const SD sd = prepareShadingData(P.sc, v, materialID, m, -beam.r);
+    const SD sd = prepareShadingData<kTex>(P.sc, v, materialID, m, -beam.r);
     beam.propagate(sd.posW);
     const BsdfCtx cx = {P.sc.profiles, int(P.opt.HWSS)};
     bsdfEval(m, cx, sd, wo, lobe, beam);
@@ -837,6 +845,7 @@ PLT_D bool manifoldSampleVertex(uint4 hitInfo, const SD& sd, const DevMaterial& 
 }
 // Manifolds.slangh:110-160
 // `first` (optional): the closest hit of the first segment, already found by the shadow-ray trace kernel.
+template <bool kTex = true>
 PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float3 rayOrigin, float3 rayDir, float rayTMin, float rayTMax, Rng& sg, int maxMSBounces, ManifoldSampleData& data,
                               const TriHit* first = nullptr, float firstT = 0.f) {
     const float3 wi = -rayDir;
@@ -849,8 +858,8 @@ PLT_D bool traceMNEEOccluders(const FrameParams& P, TraversalCounters& tc, float
         uint32_t materialID;
         VertexData v = getVertexData(P.sc, th, materialID);
         v.posW = rayOrigin + t * rayDir;
-        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
-        const SD sd = prepareShadingData(P.sc, v, materialID, m, wi);
+        const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
+        const SD sd = prepareShadingData<kTex>(P.sc, v, materialID, m, wi);
         if (!(m.propFlags & P_CanMSTransmissive)) return false;
         if (!manifoldSampleVertex(packHit(P.sc, th), sd, m, -wi, sg, data) || (data.hits[data.hitCount - 1].lobe & L_Transmission) == 0) return false;
         rayOrigin = shadowRayOrigin(sd, rayDir);
@@ -885,6 +894,7 @@ PLT_D bool manifoldOneStep(const V3pdv& w, const V3kpdv& ws, const V3pdv& p, flo
     return true;
 }
 // Manifolds.slangh:80-93
+template <bool kTex = true>
 PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const ManifoldSampleData& r, float3 origin, Beam& beam) {
     for (int idx = r.hitCount - 1; idx >= 0; --idx) {
         const TriHit th = unpackHit(P.sc, r.hits[idx].hit);
@@ -892,8 +902,8 @@ PLT_D void manifoldForwardUnwind(const FrameParams& P, SolveState& st, const Man
         VertexData v = getVertexData(P.sc, th, materialID);
         v.posW = r.hits[idx].posW;
         const float3 p2 = idx == 0 ? origin : r.hits[idx - 1].posW;
-        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
-        forwardUnwindStep(P, st.evals, v, materialID, m, normalize(p2 - v.posW), r.hits[idx].lobe, beam);
+        const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
+        forwardUnwindStep<kTex>(P, st.evals, v, materialID, m, normalize(p2 - v.posW), r.hits[idx].lobe, beam);
     }
 }
 
@@ -937,6 +947,7 @@ struct alignas(16) MneeWalk {
 };
 enum { WALK_CONTINUE = 0, WALK_CONVERGED = 1, WALK_FAILED = -1 };
 PLT_D float betaGet(const float4& b, int i) { return lane(b, i); }
+template <bool kTex = true>
 PLT_D int mneeWalkAdvance(const FrameParams& P, MneeItem& it, MneeWalk& w, bool first) {
     const int hitCount = int(it.flags & 0xfu);
     const float3 origin = mk3(it.originPdf.x, it.originPdf.y, it.originPdf.z), lightPos = mk3(it.lightPosWl.x, it.lightPosWl.y, it.lightPosWl.z);
@@ -985,8 +996,8 @@ PLT_D int mneeWalkAdvance(const FrameParams& P, MneeItem& it, MneeWalk& w, bool 
         const bool woIsIn = dot(pdvp2.v, dsg.n.v) < .0f;
         const V3pdv wiP = woIsIn ? pdvp0 : pdvp2;
         const V3pdv woP = woIsIn ? pdvp2 : pdvp0;
-        const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
-        const SD sd = prepareShadingData(P.sc, v, materialID, m, wiP.v);
+        const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
+        const SD sd = prepareShadingData<kTex>(P.sc, v, materialID, m, wiP.v);
         const V3kpdv wos = bsdfPartialDerivatives(m, sd, wiP, dsg, __float_as_uint(it.posLobe[idx].w), wavelength);
         float lenC;
         float3 positionStepDir;
@@ -1016,6 +1027,7 @@ PLT_D int mneeWalkAdvance(const FrameParams& P, MneeItem& it, MneeWalk& w, bool 
 
 // k_mnee_finish (Manifolds.slangh:270-281, pltpt_solve.rt.slang:320-361): final visibility of the converged chain, replay of the
 // beam through the found specular vertices, MIS; then the connection joins the unwind queues like any other.
+template <bool kTex = true>
 PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals, TraversalCounters& tc) {
     ManifoldSampleData ms;
     mneeUnpack(it, ms);
@@ -1045,7 +1057,7 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
     beam.scale(1.f / ms.pdf);
     SolveState st;
     st.evals = 0;
-    manifoldForwardUnwind(P, st, ms, origin, beam);
+    manifoldForwardUnwind<kTex>(P, st, ms, origin, beam);
     evals += st.evals;
     if (it.flags & MI_DO_MIS) {
         float misBsdfPdf;
@@ -1053,9 +1065,9 @@ PLT_D void mneeFinish(const FrameParams& P, const MneeItem& it, uint32_t& evals,
         else {
             uint32_t materialID;
             const VertexData v = readVertexCache(P, it.pixel, int(it.bounceIdx), materialID);
-            const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
+            const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
             const float4 d = P.bDir[size_t(it.bounceIdx) * P.pixelCount + it.pixel];
-            const SD sd = prepareShadingData(P.sc, v, materialID, m, oct_to_ndir_equal_area_snorm(mk2(d.x, d.y)));
+            const SD sd = prepareShadingData<kTex>(P.sc, v, materialID, m, oct_to_ndir_equal_area_snorm(mk2(d.x, d.y)));
             misBsdfPdf = bsdfPdf(m, sd, lsDir, beam.wl.x);
         }
         beam.scale(misWeight(it.lightDirLsPdf.w, misBsdfPdf * ms.pdf));
@@ -1083,6 +1095,7 @@ struct ConnectCtx {  // what both halves rebuild for a vertex
     SD sd;
     uint32_t materialID;
 };
+template <bool kTex = true>
 PLT_D void connectSetup(const FrameParams& P, uint32_t pixel, int p, bool freshRng, ConnectCtx& c) {
     uint32_t px, py;
     pixelCoords(P, pixel, px, py);
@@ -1103,8 +1116,8 @@ PLT_D void connectSetup(const FrameParams& P, uint32_t pixel, int p, bool freshR
     }
     if (!P.perTileSG) c.st.tilesg = c.st.sg;
     c.bounce = readBounce(P, pixel, p);
-    c.m = loadMaterialAt(P.sc, c.materialID, c.v.texC);
-    c.sd = prepareShadingData(P.sc, c.v, c.materialID, c.m, c.bounce.wi);
+    c.m = loadMaterialAt<kTex>(P.sc, c.materialID, c.v.texC);
+    c.sd = prepareShadingData<kTex>(P.sc, c.v, c.materialID, c.m, c.bounce.wi);
 }
 PLT_D void storeSolveRng(const FrameParams& P, uint32_t pixel, const SolveState& st) {
     P.ssRng[pixel] = make_uint4(st.sg.s0, st.sg.s1, st.sg.s2, st.sg.s3);
@@ -1126,10 +1139,11 @@ static __device__ __noinline__ void firstVertexDebugViews(const FrameParams& P, 
     writeDebug(P, pixel, 0, 1, ev);
 }
 // Half A (pltpt_solve.rt.slang:245-300): light sample, beam sourcing, delta sample of the current vertex; posts the shadow ray.
+template <bool kTex = true>
 PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
     const int p = int(P.level);
     ConnectCtx c;
-    connectSetup(P, pixel, p, p == 0, c);
+    connectSetup<kTex>(P, pixel, p, p == 0, c);
     if (P.debugView && p == 0) firstVertexDebugViews(P, pixel, c.sd.N, mk3(c.m.albx, c.m.alby, c.m.albz), c.m.roughnessProp, c.sd.uv);
     ConnItem item;
     item.dirPdf = mk4(0.f); item.info = make_uint4(0, 0, 0, 0);
@@ -1141,7 +1155,7 @@ PLT_D void connectA(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
         const bool sampleTransmission = (lobes & L_NonDeltaTransmission) != 0;
         if (sampleReflection || sampleTransmission) {
             LightSample ls;
-            const bool valid = generateLightSample(P, c.sd, sampleReflection, sampleTransmission, c.st.sg, c.st.tilesg, c.st.wavelength, P.opt.doImportanceSampleEmitters != 0, ls);
+            const bool valid = generateLightSample<kTex>(P, c.sd, sampleReflection, sampleTransmission, c.st.sg, c.st.tilesg, c.st.wavelength, P.opt.doImportanceSampleEmitters != 0, ls);
             if (valid && anyPositive(ls.beam.L, int(P.opt.HWSS))) {
                 if (!P.opt.HWSSDoMIS && (c.bounce.flags & RF_HasDispersiveDeltaSegment)) ls.beam.comps = 1;
                 uint32_t flags = CI_TRACE | ((P.doMIS && ls.lightType != LT_Analytic) ? CI_DO_MIS : 0u);
@@ -1226,6 +1240,7 @@ PLT_D bool connectBFast(const FrameParams& P, uint32_t pixel, const ConnItem& it
     }
     return true;
 }
+template <bool kTex = true>
 PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_t& evals, TraversalCounters& tc) {
     const ConnItem item = P.connItems[slot];
     const uint32_t flags = item.info.y;
@@ -1234,7 +1249,7 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
     const uint4 hit = P.shadowHits[slot];
     const bool blocked = hit.x != 0xffffffffu;
     ConnectCtx c;
-    connectSetup(P, pixel, p, false, c);
+    connectSetup<kTex>(P, pixel, p, false, c);
     const float3 lsDir = mk3(item.dirPdf.x, item.dirPdf.y, item.dirPdf.z);
     const float lsPdf = item.dirPdf.w;
     bool connected = false;
@@ -1257,7 +1272,7 @@ PLT_D void connectB(const FrameParams& P, uint32_t slot, uint32_t pixel, uint32_
         if (blocked) {
             TriHit th;
             th.instanceID = hit.x; th.primitiveIndex = hit.y; th.u = __uint_as_float(hit.z); th.v = __uint_as_float(hit.w);
-            ok = traceMNEEOccluders(P, c.st.tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.f, r1.w, c.st.sg, int(P.opt.maxBounces) - p, ms, &th, P.shadowT[slot]);
+            ok = traceMNEEOccluders<kTex>(P, c.st.tc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.f, r1.w, c.st.sg, int(P.opt.maxBounces) - p, ms, &th, P.shadowT[slot]);
         }
         // debug view: a chain that needs no walk (or cannot be walked) reports 0 iterations; parked walks report at their end
         if (P.debugView == DV_MneeIterations && !(ok && ms.hitCount > 0 && ms.pdf >= 1e-6f)) { float4 ev = mk4(0.f); debugEvent(&ev, ccInferno(0.f)); writeDebug(P, pixel, uint32_t(p), 0, ev); }
@@ -1312,11 +1327,12 @@ struct alignas(16) UnwindItem { float4 job[kJobPlanes]; float4 vtx[4]; float4 di
 // One replay step of one connection job (pltpt_solve.rt.slang:68-79 forwardUnwind body / :219-243 evalNEE head) on its loaded
 // inputs: `v`, `materialID`, `d` = vertex record and bounce direction of the vertex the job evaluates next, `beam`, `h` = the job.
 // Returns true while the job has further vertices to go through.
+template <bool kTex = true>
 PLT_D bool unwindStepLoaded(const FrameParams& P, uint32_t id, const VertexData& v, uint32_t materialID, float4 d, Beam& beam, JobHeader& h, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
-    const DevMaterial m = loadMaterialAt(P.sc, materialID, v.texC);
+    const DevMaterial m = loadMaterialAt<kTex>(P.sc, materialID, v.texC);
     const float3 wo = oct_to_ndir_equal_area_snorm(mk2(d.x, d.y));
     const uint32_t lobe = h.firstIsCurrent ? uint32_t(L_NonDelta) : __float_as_uint(d.z);
-    forwardUnwindStep(P, evals, v, materialID, m, wo, lobe, beam);
+    forwardUnwindStep<kTex>(P, evals, v, materialID, m, wo, lobe, beam);
     if (h.q == 0) {
         measureInto(P, h.pixel, h.bounceIdx, h.kind, h.pathContribution, beam);
         return false;
@@ -1327,6 +1343,7 @@ PLT_D bool unwindStepLoaded(const FrameParams& P, uint32_t id, const VertexData&
     storeJob(P, id, beam, h);
     return true;
 }
+template <bool kTex = true>
 PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t& evals, uint32_t& nextType, uint32_t& nextAux) {
     // the queue entry names the vertex: the job record, the vertex record and the bounce direction are independent loads
     const uint32_t pixel = aux & 0x3ffffffu, q = aux >> 26;
@@ -1336,7 +1353,7 @@ PLT_D bool unwindStep(const FrameParams& P, uint32_t id, uint32_t aux, uint32_t&
     Beam beam;
     JobHeader h;
     loadJob(P, id, beam, h);
-    return unwindStepLoaded(P, id, v, materialID, d, beam, h, evals, nextType, nextAux);
+    return unwindStepLoaded<kTex>(P, id, v, materialID, d, beam, h, evals, nextType, nextAux);
 }
 
 // Sums a pixel's connections in the order the reference adds them (bounce ascending, NEE before emissive).

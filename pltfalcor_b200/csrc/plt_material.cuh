@@ -172,6 +172,9 @@ PLT_HD MaterialSlots uniformSlots(const PltptMaterialBlob& m) {
 }
 
 #ifdef __CUDACC__
+#ifndef PLT_TEXCALL
+#define PLT_TEXCALL static __device__ __noinline__
+#endif
 // ---- texture sampling (device): D3D texel addressing, sRGB decode per texel, exact fp32 bilinear weights ---------------------
 PLT_D float srgbToLinear(float c) { return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
 PLT_D float4 fetchTexel(const DevTexture& t, int x, int y) {
@@ -244,7 +247,7 @@ PLT_D float conductorNormalFresnel(const DevProfile* profiles, uint32_t etaN, ui
 }
 // The textured path: the material's slots sampled at `uv`, then the same derivation as on the host.  Out of line: the untextured
 // materials every benchmark scene uses never execute it, and inlined into the stage kernels it would raise their register demand.
-static __device__ __noinline__ DevMaterial resolveTexturedMaterial(const DevTextures& tx, const DevProfile* profiles, uint32_t materialID, float2 uv, uint32_t hdrFlags) {
+PLT_TEXCALL DevMaterial resolveTexturedMaterial(const DevTextures& tx, const DevProfile* profiles, uint32_t materialID, float2 uv, uint32_t hdrFlags) {
     DevMaterial m;
     const PltptMaterialBlob b = loadBlob(tx, materialID);
     const uint32_t smp = blobSamplerID(b);
@@ -267,7 +270,7 @@ static __device__ __noinline__ DevMaterial resolveTexturedMaterial(const DevText
 // material.modifyTangentSpace + applyNormalMap (ShadingUtils.slang:199-246); ShadingFrame(n, tangentW) = normalize + the unchecked
 // orthonormalize (:61-65, :112-116).  `T`, `B`, `N`: the orthonormalised frame of the interpolated normal and tangent.
 struct Frame3 { float3 T, B, N; };
-static __device__ __noinline__ Frame3 applyNormalMapTextured(const DevTextures& tx, uint32_t materialID, float2 uv, float4 tangentW, Frame3 f) {
+PLT_TEXCALL Frame3 applyNormalMapTextured(const DevTextures& tx, uint32_t materialID, float2 uv, float4 tangentW, Frame3 f) {
     const PltptMaterialBlob b = loadBlob(tx, materialID);
     const float4 enc = sampleTexture(tx, b.texNormalMap, blobSamplerID(b), uv, mk4(0.f));
     const uint32_t type = blobNormalMapType(b);

@@ -81,7 +81,10 @@ PLT_HD float length(float3 a) { return sqrtf(dot(a, a)); }
 #if PLT_FAST_DEVICE
 PLT_HD float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
 #else
-PLT_HD float3 normalize(float3 a) { return a / length(a); }
+// The oracle's definition of the HLSL intrinsic (oracle/plt_math.h): one correctly rounded square root, one correctly rounded reciprocal,
+// three products.  (Rounds 1-2 used v / length(v): three IEEE divisions per call were a sixth of k_shade's instructions -- 1.22 -> 1.04 ms,
+// k_connect_a 1.29 -> 1.19 ms per Cornell frame, profiles/r2m_variants.log.)
+PLT_HD float3 normalize(float3 a) { return a * (1.f / length(a)); }
 #endif
 PLT_HD float3 vabs(float3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 PLT_HD float3 vmax(float3 a, float3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }

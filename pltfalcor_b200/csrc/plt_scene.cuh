@@ -11,7 +11,7 @@ struct TriHit {
     float u, v;
     PLT_D float3 weights() const { return mk3(1.f - u - v, u, v); }  // HitInfo.slang:76-79
 };
-struct StaticVertex { float3 position, normal; float4 tangent; float2 texCrd; };
+struct StaticVertex { float3 position, normal; uint32_t packedTangent; float tangentSign; float2 texCrd; };  // tangent xyz decoded on demand (tangentOf)
 struct VertexData { float3 posW, normalW, faceNormalW; float4 tangentW; float2 texC; };  // SceneTypes.slang:311-320
 
 // Scene.slang getLocalIndices / getIndices
@@ -44,10 +44,11 @@ PLT_D StaticVertex fetchVertex(const DevScene& sc, uint32_t index) {
     const uint32_t pk0 = __float_as_uint(a.w), pk1 = __float_as_uint(b.x), pk2 = __float_as_uint(b.y);
     v.texCrd = mk2(b.z, b.w);
     v.normal = normalize(mk3(h2f(pk0 & 0xffff), h2f(pk0 >> 16), h2f(pk1 & 0xffff)));
-    const float3 t = decodeNormal2x16(pk2);
-    v.tangent = mk4(t.x, t.y, t.z, signf(h2f(pk1 >> 16)));
+    v.packedTangent = pk2;
+    v.tangentSign = signf(h2f(pk1 >> 16));
     return v;
 }
+PLT_D float4 tangentOf(const StaticVertex& v) { const float3 t = decodeNormal2x16(v.packedTangent); return mk4(t.x, t.y, t.z, v.tangentSign); }
 PLT_D float3 mulPoint(const float* __restrict__ M, float3 p) {
     return mk3(__ldg(M + 0) * p.x + __ldg(M + 1) * p.y + __ldg(M + 2) * p.z + __ldg(M + 3), __ldg(M + 4) * p.x + __ldg(M + 5) * p.y + __ldg(M + 6) * p.z + __ldg(M + 7),
                __ldg(M + 8) * p.x + __ldg(M + 9) * p.y + __ldg(M + 10) * p.z + __ldg(M + 11));
@@ -72,27 +73,41 @@ PLT_D VertexData getVertexData(const DevScene& sc, const TriHit& hit, uint32_t& 
     VertexData v;
     v.posW = v0.position * b.x; v.posW += v1.position * b.y; v.posW += v2.position * b.z;
     v.normalW = v0.normal * b.x; v.normalW += v1.normal * b.y; v.normalW += v2.normal * b.z;
-    float4 tg = v0.tangent * b.x; tg += v1.tangent * b.y; tg += v2.tangent * b.z;
-    tg.w = signf(tg.w);
+    // A mesh without tangents stores handedness 0 in every vertex (SceneTypes.slang:252-266): the interpolated sign is then 0, the tangent
+    // space is invented from the normal (prepareShadingData) and the tangent's direction is never read -- its three octahedral decodes, the
+    // transform and the normalisation (a fifth of the shading kernel's instructions on such meshes) are skipped; the result is the same.
+    const bool hasTangent = v0.tangentSign != 0.f || v1.tangentSign != 0.f || v2.tangentSign != 0.f;
+    float4 tg = mk4(0.f);
+    if (hasTangent) {
+        tg = tangentOf(v0) * b.x; tg += tangentOf(v1) * b.y; tg += tangentOf(v2) * b.z;
+        tg.w = signf(tg.w);
+    }
     v.texC = v0.texCrd * b.x + v1.texCrd * b.y + v2.texCrd * b.z;
     const float3 N = normalize(cross(v1.position - v0.position, v2.position - v0.position));
     v.faceNormalW = isFrontFaceCW ? -N : N;
     v.posW = mulPoint(worldMat, v.posW);
     v.normalW = normalize(mulVec(worldIT, v.normalW));
     v.faceNormalW = normalize(mulVec(worldIT, v.faceNormalW));
-    const float3 t = normalize(mulVec(worldMat, mk3(tg.x, tg.y, tg.z)));
-    v.tangentW = mk4(t.x, t.y, t.z, tg.w);
+    v.tangentW = mk4(0.f);
+    if (hasTangent) {
+        const float3 t = normalize(mulVec(worldMat, mk3(tg.x, tg.y, tg.z)));
+        v.tangentW = mk4(t.x, t.y, t.z, tg.w);
+    }
     return v;
 }
 
 // The material a hit sees: the scene's pre-derived record, or -- for a material with textured parameter slots -- the record derived from
 // the slots sampled at the hit's texture coordinate (plt_material.cuh; every *Material.slang::setupMaterialInstance).
+// kTex = false: the instantiation the hot stage kernels run on a scene without textured materials (no out-of-line call in their body:
+// its mere presence cost k_connect_a 372 B of spills and 15 % of its time, profiles/r2k_variants.log); the launchers pick by scene.
+template <bool kTex = true>
 PLT_D DevMaterial loadMaterialAt(const DevScene& sc, uint32_t id, float2 uv) {
     DevMaterial m = loadMaterial(sc.materials, id);
-    if (m.hdrFlags & HF_Textured) m = resolveTexturedMaterial(sc.tex, sc.profiles, id, uv, m.hdrFlags);
+    if (kTex && sc.tex.blobs && (m.hdrFlags & HF_Textured)) m = resolveTexturedMaterial(sc.tex, sc.profiles, id, uv, m.hdrFlags);
     return m;
 }
 // MaterialFactory.slang:79-131 (prepareShadingData) + ShadingUtils.slang:126-152 (tangent frame), :199-246 (normal mapping).
+template <bool kTex = true>
 PLT_D SD prepareShadingData(const DevScene& sc, const VertexData& v, uint32_t materialID, const DevMaterial& m, float3 viewDir) {
     SD sd;
     sd.posW = v.posW;
@@ -112,7 +127,7 @@ PLT_D SD prepareShadingData(const DevScene& sc, const VertexData& v, uint32_t ma
     sd.faceN = v.faceNormalW;
     sd.frontFacing = dot(sd.V, sd.faceN) >= 0.f;
     sd.materialID = materialID;
-    if (valid && (m.hdrFlags & HF_NormalMap)) {  // modifyTangentSpace: only with a valid tangent space (MaterialFactory.slang:114-120)
+    if (kTex && sc.tex.blobs && valid && (m.hdrFlags & HF_NormalMap)) {  // (sc.tex.blobs: null for a scene without textured materials -- a uniform test)  // modifyTangentSpace: only with a valid tangent space (MaterialFactory.slang:114-120)
         const Frame3 f = applyNormalMapTextured(sc.tex, materialID, v.texC, v.tangentW, Frame3{sd.T, sd.B, sd.N});
         sd.T = f.T; sd.B = f.B; sd.N = f.N;
     }

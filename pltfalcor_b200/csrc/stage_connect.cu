@@ -39,6 +39,7 @@ __device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long lo
 #endif
 namespace plt {
 namespace {
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_A) k_connect_a
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
-        if (i < n) { connectA(P, i, list[i], evals, tc); ++verts; }
+        if (i < n) { connectA<kTex>(P, i, list[i], evals, tc); ++verts; }
     }
     // warp-aggregated statistics (all lanes reach this point)
     warpAdd(P.counters + 1, verts);
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
 
 // Half B for the entries the shadow-ray kernel could not settle (occluder chain, delta sample of the current vertex, emissive hit),
 // densely packed.
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b_slow(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[kTraceCountSlot];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t k = base + threadIdx.x;
-        if (k < n) { const uint32_t i = P.traceQueue[k]; connectB(P, i, list[i], evals, tc); }
+        if (k < n) { const uint32_t i = P.traceQueue[k]; connectB<kTex>(P, i, list[i], evals, tc); }
     }
     warpAdd(P.counters + 5, tc.nodes);
     warpAdd(P.counters + 6, tc.tris);
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_CONNECT_B) k_connect_b
 // Live walks are kept in two ping-pong lists, converged ones are listed for pass 2; the three list counts rotate through
 // queueCount[QC_MneeRound ..+3) (zeroed per tile; the count two rounds back is re-zeroed by thread 0 while nobody reads it), the number
 // of converged walks is queueCount[QC_MneeDone].
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(const __grid_constant__ FrameParams P) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t n = min(*P.mneeCount, P.mneeCapacity);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
             const bool valid = k < nCur;
             if (valid) {
                 item = round == 0 ? k : cur[k];
-                r = mneeWalkAdvance(P, P.mneeItems[item], P.mneeWalks[item], round == 0);
+                r = mneeWalkAdvance<kTex>(P, P.mneeItems[item], P.mneeWalks[item], round == 0);
                 if (r != WALK_CONTINUE) {
                     iterations += P.mneeWalks[item].iterations;
                     if (P.debugView == DV_MneeIterations) {  // pltpt_solve.rt.slang:318-322
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_walk(cons
     if (iterations) atomicAdd(P.counters + 3, iterations);
 }
 // Pass 2: converged walks, densely packed: final visibility, replay through the specular chain, MIS, hand-over to the unwind queues.
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[QC_MneeDone];
     const uint32_t* doneList = P.mneeLists + 2 * size_t(P.mneeCapacity);
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_MNEE) k_mnee_finish(co
     TraversalCounters tc = {0, 0};
     for (uint32_t base = blockIdx.x * kStageThreads; base < n; base += gridDim.x * kStageThreads) {
         const uint32_t i = base + threadIdx.x;
-        if (i < n) mneeFinish(P, P.mneeItems[doneList[i]], evals, tc);
+        if (i < n) mneeFinish<kTex>(P, P.mneeItems[doneList[i]], evals, tc);
     }
     warpAdd(P.counters + 0, evals);
     warpAdd(P.counters + 5, tc.nodes);
@@ -244,7 +248,10 @@ uint32_t mneeCooperativeGrid(int device) {
     int perSm = 0, sms = 0, cur = 0;
     cudaGetDevice(&cur);
     if (cur != device) cudaSetDevice(device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mnee_walk, kStageThreads, 0);
+    int perSmTex = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mnee_walk<false>, kStageThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmTex, k_mnee_walk<true>, kStageThreads, 0);
+    perSm = std::min(perSm, perSmTex);  // one grid size for both instantiations (textured / untextured scenes)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (cur != device) cudaSetDevice(cur);
     return uint32_t(std::max(perSm, 1) * std::max(sms, 1));
@@ -252,14 +259,26 @@ uint32_t mneeCooperativeGrid(int device) {
 void launchMnee(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     FrameParams Pc = P;
     void* args[] = {&Pc};
-    cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk), dim3(P.mneeGrid), dim3(kStageThreads), args, 0, s);
-    k_mnee_finish<<<grid, kStageThreads, 0, s>>>(P);
+    if (P.sc.tex.blobs) {
+        cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk<true>), dim3(P.mneeGrid), dim3(kStageThreads), args, 0, s);
+        k_mnee_finish<true><<<grid, kStageThreads, 0, s>>>(P);
+    } else {
+        cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_mnee_walk<false>), dim3(P.mneeGrid), dim3(kStageThreads), args, 0, s);
+        k_mnee_finish<false><<<grid, kStageThreads, 0, s>>>(P);
+    }
 }
 void launchConnectMiss(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_miss<<<grid, kStageThreads, 0, s>>>(P); }
-void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_a<<<grid, kStageThreads, 0, s>>>(P); }
+// (the instantiation without the textured-material path for scenes that have no textured material: plt_scene.cuh loadMaterialAt)
+void launchConnectA(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.sc.tex.blobs) k_connect_a<true><<<grid, kStageThreads, 0, s>>>(P);
+    else k_connect_a<false><<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchShadowTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     if (P.tinyScene) k_shadow_trace_simple<<<grid, kStageThreads, 0, s>>>(P);
     else k_shadow_trace<<<grid, kStageThreads, 0, s>>>(P);
 }
-void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_connect_b_slow<<<grid, kStageThreads, 0, s>>>(P); }
+void launchConnectB(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.sc.tex.blobs) k_connect_b_slow<true><<<grid, kStageThreads, 0, s>>>(P);
+    else k_connect_b_slow<false><<<grid, kStageThreads, 0, s>>>(P);
+}
 }  // namespace plt

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace(const _
     warpAdd(P.counters + 6, tc.tris);
 }
 
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADE) k_shade(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.levelCount[P.level];
     const uint32_t* list = P.vertexList + size_t(P.level) * P.pixelCount;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADE) k_shade(const _
         const uint32_t i = base + threadIdx.x;
         if (i < n) {
             const uint32_t pixel = list[i];
-            if (shadePath(P, pixel, tc)) {
+            if (shadePath<kTex>(P, pixel, tc)) {
                 // append to the trace queue of the next bounce (warp-aggregated)
                 const uint32_t active = __activemask();
                 const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
@@ -121,7 +122,10 @@ void launchTrace(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     if (P.tinyScene) k_trace_simple<<<grid, kStageThreads, 0, s>>>(P);
     else k_trace<<<grid, kStageThreads, 0, s>>>(P);
 }
-void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_shade<<<grid, kStageThreads, 0, s>>>(P); }
+void launchShade(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.sc.tex.blobs) k_shade<true><<<grid, kStageThreads, 0, s>>>(P);
+    else k_shade<false><<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchGatherBounces(const FrameParams& P, PltptBounce* out, uint32_t records, cudaStream_t s) {
     k_gather_bounces<<<(P.pixelCount + 127) / 128, 128, 0, s>>>(P, out, records);
 }

@@ -92,6 +92,7 @@ __device__ __forceinline__ void stageUnwindItem(const FrameParams& P, UnwindItem
 }
 // Each thread owns one 240 B slot (stride 60 words: a quarter-warp's 16 B accesses fall into distinct banks).  The slot is read
 // into registers, then refilled for the thread's next item (same thread, program order: no barrier), then the step is computed.
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     __shared__ UnwindItem slots[kStageThreads];
     const uint32_t n = P.queueCount[QC_SortedCount];
@@ -118,13 +119,14 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_
             if (j2 < n) { nnid = P.sorted[j2]; nnaux = P.sortedAux[j2]; }
         }
         uint32_t nextType = 0, nextAux = 0;
-        if (unwindStepLoaded(P, id, v, materialID, d, beam, h, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
+        if (unwindStepLoaded<kTex>(P, id, v, materialID, d, beam, h, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
         id = nid; aux = naux; nid = nnid; naux = nnaux;
     }
     warpAdd(P.counters + 0, evals);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(P.counters + 7, (unsigned long long)n);
 }
 #else
+template <bool kTex>
 __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_step(const __grid_constant__ FrameParams P) {
     const uint32_t n = P.queueCount[QC_SortedCount];
     uint32_t evals = 0;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_
 #endif
         }
         uint32_t nextType = 0, nextAux = 0;
-        if (unwindStep(P, id, aux, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
+        if (unwindStep<kTex>(P, id, aux, evals, nextType, nextAux)) enqueueJob(P, nextType, id, nextAux);
         id = nid; aux = naux;
     }
     warpAdd(P.counters + 0, evals);
@@ -166,6 +168,9 @@ void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint
     k_sort_queue<<<grid, kSortThreads, 0, s>>>(P, v);
     k_flip_queue<<<1, 32, 0, s>>>(P, v, resetTraceQueue);
 }
-void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) { k_unwind_step<<<grid, kStageThreads, 0, s>>>(P); }
+void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) {
+    if (P.sc.tex.blobs) k_unwind_step<true><<<grid, kStageThreads, 0, s>>>(P);
+    else k_unwind_step<false><<<grid, kStageThreads, 0, s>>>(P);
+}
 void launchResolve(const FrameParams& P, cudaStream_t s) { k_resolve<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
 }  // namespace plt

@@ -398,11 +398,15 @@ def test_render_errors(torch_cuda, cornell):
     with pytest.raises(binding.PltptError) as e:
         p.render_frame(cam, 0, 4, 4, None)
     assert e.value.code == 1
-    # textured material handles are rejected loudly (Uniform handles only)
+    # a Texture handle without a texture table is an invalid scene; UDIM handles are unsupported (tests/test_gpu_textures.py has the rest)
     bad = type(buffers)(dict(buffers.arrays), dict(buffers.scalars))
     mats = buffers.arrays["materialData"].copy()
     mats["tex"][0, 0] = 1 << 29
     bad.arrays["materialData"] = mats
+    with pytest.raises(binding.PltptError) as e:
+        p.set_scene(bad)
+    assert e.value.code == 1
+    mats["tex"][0, 0] = (1 << 31) | (1 << 29)
     with pytest.raises(binding.PltptError) as e:
         p.set_scene(bad)
     assert e.value.code == 3

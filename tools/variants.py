@@ -29,6 +29,15 @@ VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their ou
     "c_fmad": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-fmad=true"]},
     "c_div": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-div=false"]},
     "c_sqrt": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-sqrt=false"]},
+    "nrm_rcp": {"stage_sample.cu": ["-DPLT_NORMALIZE_RCP=1"], "stage_connect.cu": ["-DPLT_NORMALIZE_RCP=1"]},  # (breaks oracle parity unless the oracle follows)
+    "trav_r4": {"stage_sample.cu": ["-DPLT_TRAV_REFILL=4"], "stage_connect.cu": ["-DPLT_TRAV_REFILL=4"]},
+    "trav_r16": {"stage_sample.cu": ["-DPLT_TRAV_REFILL=16"], "stage_connect.cu": ["-DPLT_TRAV_REFILL=16"]},
+    "trav_s2": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=2"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=2"]},
+    "trav_s8": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=8"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=8"]},
+    "sweep_fm": {"api.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"]},
+    "push_near": {"stage_sample.cu": ["-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_PUSH_NEAREST=1"]},
+    "defer": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1"]},
+    "defer_push": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"]},
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
