@@ -501,9 +501,11 @@ PLTPT_API int pltpt_trace_closest(PltptHandle h, uint32_t rayCount, const float*
 PLTPT_API int pltpt_trace_any(PltptHandle h, uint32_t rayCount, const float* rays,
                               uint32_t* occluded, void* stream);
 /* Which traversal driver the two ray queries above run through.  The rendering kernels pick by scene size: one ray per thread to
- * completion for trees of a few nodes, persistent lanes that refill from a queue otherwise; AUTO (default) makes the queries follow
- * the same rule, the other two force one driver so that the hit-ID parity checks can cover both on every scene. */
-enum { PLTPT_TRACE_AUTO = 0, PLTPT_TRACE_ONE_RAY_PER_THREAD = 1, PLTPT_TRACE_PERSISTENT_LANES = 2 };
+ * completion (children pushed in order of distance) for trees of a few nodes, persistent lanes that refill from a queue otherwise
+ * (nearest child first, leaf triangles of a round tested by all lanes together); the rays the connect and manifold kernels trace inline
+ * run one ray per thread with the nearest-first push.  AUTO (default) makes the queries follow the trace kernels' rule, the other three
+ * force one driver so that the hit-ID parity checks cover every combination on every scene. */
+enum { PLTPT_TRACE_AUTO = 0, PLTPT_TRACE_ONE_RAY_PER_THREAD = 1, PLTPT_TRACE_PERSISTENT_LANES = 2, PLTPT_TRACE_ONE_RAY_PER_THREAD_NEAREST_FIRST = 3 };
 PLTPT_API int pltpt_set_trace_mode(PltptHandle h, int mode);
 
 /* ------------------------------------------------------------------------------------------
@@ -523,6 +525,12 @@ PLTPT_API int pltpt_bsdf_eval_mueller(PltptHandle h, uint32_t materialID, uint32
                                       const float* wi /*3n*/, const float* wo /*3n*/,
                                       const float* heroWavelengths /*groups*n*/,
                                       float* mueller /*n*groups*HWSS*16*/, void* stream);
+
+/* The same query evaluated with the arithmetic of the forward replay (k_unwind_step is compiled with approximate division / square root and
+ * contracted FMAs): lets the BSDF tolerance tests state how far the renderer's replay is from the oracle on the same
+ * queries.  Same arguments and output layout; a test hook, not a benchmark path. */
+PLTPT_API int pltpt_bsdf_eval_mueller_replay_math(PltptHandle h, uint32_t materialID, uint32_t lobe, uint32_t queryCount, uint32_t groups,
+                                                  const float* wi, const float* wo, const float* heroWavelengths, float* mueller, void* stream);
 
 /* bsdf.sample() + bsdf.pdf(): per query a sample generator seeded SampleGenerator(pixel=(i&0xffff,i>>16), seed)
  * is used.  out = {wo.x, wo.y, wo.z, pdf, asfloat(lobe), weight, valid(0/1), pdf(wi,wo) re-evaluated} per query. */

@@ -21,7 +21,7 @@ EXPORTS = [
     "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
     "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
     "pltpt_render_accumulate_rows", "pltpt_resolve_accumulated", "pltpt_render_accumulate_host", "pltpt_render_accumulate_multi",
-    "pltpt_texture_sample", "pltpt_accumulate_frame",
+    "pltpt_texture_sample", "pltpt_accumulate_frame", "pltpt_bsdf_eval_mueller_replay_math",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         _lib.pltpt_trace_any.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_set_trace_mode.argtypes = [vp, C.c_int]
         _lib.pltpt_bsdf_eval_mueller.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]
+        _lib.pltpt_bsdf_eval_mueller_replay_math.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]
         _lib.pltpt_bsdf_sample.argtypes = [vp, u32, u32, u32, vp, vp, u32, vp, vp]
         _lib.pltpt_get_stats.argtypes = [vp, vp]
         _lib.pltpt_reset_stats.argtypes = [vp]
@@ -283,6 +284,11 @@ class Pltpt:
         """wi, wo: (n,3); hero: (groups,n); out: (n,groups,HWSS,4,4) — torch CUDA float32 tensors."""
         groups, n = hero.shape
         _check(lib().pltpt_bsdf_eval_mueller(self.h, material_id, lobe, n, groups, _dp(wi), _dp(wo), _dp(hero), _dp(out), stream))
+
+    def bsdf_eval_mueller_replay_math(self, material_id, lobe, wi, wo, hero, out, stream=None):
+        """bsdf_eval_mueller with the forward replay's arithmetic (test hook)."""
+        groups, n = hero.shape
+        _check(lib().pltpt_bsdf_eval_mueller_replay_math(self.h, material_id, lobe, n, groups, _dp(wi), _dp(wo), _dp(hero), _dp(out), stream))
 
     def bsdf_sample(self, material_id, lobe_mask, wi, wavelengths, seed, out, stream=None):
         _check(lib().pltpt_bsdf_sample(self.h, material_id, lobe_mask, wi.shape[0], _dp(wi), _dp(wavelengths), seed, _dp(out), stream))

@@ -574,6 +574,23 @@ extern "C" int pltpt_bsdf_eval_mueller(PltptHandle h, uint32_t materialID, uint3
     PLT_CUDA(cudaGetLastError());
     return PLTPT_OK;
 }
+extern "C" int pltpt_bsdf_eval_mueller_replay_math(PltptHandle h, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* wi, const float* wo,
+                                                   const float* hero, float* mueller, void* stream) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
+    if (materialID >= h->materials.bytes / sizeof(DevMaterial)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "materialID out of range");
+    if (n == 0 || groups == 0) return PLTPT_OK;
+    if (!wi || !wo || !hero || !mueller) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null buffer");
+    PLT_CUDA(cudaSetDevice(h->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const uint64_t total = uint64_t(n) * groups;
+    const uint32_t grid = uint32_t(std::min<uint64_t>((total + 127) / 128, uint64_t(sms) * 16));
+    launchBsdfEvalReplayMath(h->scene, materialID, lobe, n, groups, wi, wo, hero, mueller, int(h->opt.HWSS), h->opt.sourcingMaxBeamOmega, grid, (cudaStream_t)stream);
+    h->stats.kernelLaunches++;
+    PLT_CUDA(cudaGetLastError());
+    return PLTPT_OK;
+}
 extern "C" int pltpt_bsdf_sample(PltptHandle h, uint32_t materialID, uint32_t lobeMask, uint32_t n, const float* wi, const float* wavelengths, uint32_t seed, float* out, void* stream) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
     if (!h->hasScene) return fail(PLTPT_ERR_NO_SCENE, "pltpt_set_scene has not been called");
@@ -607,7 +624,7 @@ extern "C" int pltpt_trace_any(PltptHandle h, uint32_t n, const float* rays, uin
 
 extern "C" int pltpt_set_trace_mode(PltptHandle h, int mode) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null handle");
-    if (mode < PLTPT_TRACE_AUTO || mode > PLTPT_TRACE_PERSISTENT_LANES) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown trace mode");
+    if (mode < PLTPT_TRACE_AUTO || mode > PLTPT_TRACE_ONE_RAY_PER_THREAD_NEAREST_FIRST) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown trace mode");
     h->traceMode = mode;
     return PLTPT_OK;
 }

@@ -162,6 +162,87 @@ __global__ void k_fit(int n, const uint32_t* __restrict__ sorted, const float4* 
     }
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) ---------------------------------------------------------------
+// The binary tree is built bottom-up by agglomeration instead of top-down by Morton-code splits: the clusters (initially the triangles in
+// Morton order) each look for the neighbour within kPlocRadius positions whose union with them has the smallest surface area; mutual
+// nearest neighbours merge into a new node, the array is compacted, and the search repeats on the shorter array until one cluster is left.
+// The merges follow the surface-area heuristic locally, where the radix tree only follows the bits of the codes.
+#ifndef PLT_BVH_PLOC
+#define PLT_BVH_PLOC 1  // 0: Karras radix tree (rounds 1-2a), kept for comparison (tools/variants.py: bvh_lbvh)
+#endif
+#ifndef PLT_PLOC_RADIUS
+#define PLT_PLOC_RADIUS 8
+#endif
+constexpr int kPlocRadius = PLT_PLOC_RADIUS, kPlocThreads = 256;
+PLT_D float unionArea(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    const float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return ex * ey + ey * ez + ez * ex;
+}
+// first iteration input: clusters = leaves in Morton order
+__global__ void k_ploc_init(uint32_t n, const uint32_t* __restrict__ sorted, const float4* __restrict__ triLo, const float4* __restrict__ triHi, uint32_t* __restrict__ cl,
+                            float4* __restrict__ clLo, float4* __restrict__ clHi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = sorted[i];
+    cl[i] = i | kLeafBit; clLo[i] = triLo[t]; clHi[i] = triHi[t];
+}
+// nearest neighbour of every cluster within the radius (shared-memory tile of the block's boxes plus a halo of kPlocRadius on both sides)
+__global__ void __launch_bounds__(kPlocThreads) k_ploc_nearest(uint32_t c, const float4* __restrict__ clLo, const float4* __restrict__ clHi, uint32_t* __restrict__ nn) {
+    __shared__ float4 sLo[kPlocThreads + 2 * kPlocRadius], sHi[kPlocThreads + 2 * kPlocRadius];
+    const int base = int(blockIdx.x) * kPlocThreads - kPlocRadius;
+    for (int k = threadIdx.x; k < kPlocThreads + 2 * kPlocRadius; k += kPlocThreads) {
+        const int g = base + k;
+        if (g >= 0 && g < int(c)) { sLo[k] = clLo[g]; sHi[k] = clHi[g]; }
+    }
+    __syncthreads();
+    const int i = int(blockIdx.x) * kPlocThreads + int(threadIdx.x);
+    if (i >= int(c)) return;
+    const int li = int(threadIdx.x) + kPlocRadius;
+    const float4 lo = sLo[li], hi = sHi[li];
+    float best = FLT_MAX;
+    int bestJ = -1;
+#pragma unroll
+    for (int d = -kPlocRadius; d <= kPlocRadius; ++d) {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= int(c)) continue;
+        const float a = unionArea(lo, hi, sLo[li + d], sHi[li + d]);
+        if (a < best) { best = a; bestJ = j; }  // ties go to the lower index: the relation "mutual nearest" stays symmetric
+    }
+    nn[i] = uint32_t(bestJ);
+}
+// mutual nearest neighbours merge: the lower position keeps the new node, the upper one is dropped; everything else is kept
+__global__ void k_ploc_merge(uint32_t c, const uint32_t* __restrict__ cl, const float4* __restrict__ clLo, const float4* __restrict__ clHi, const uint32_t* __restrict__ nn,
+                             uint32_t* __restrict__ nodeCount, uint32_t* __restrict__ left, uint32_t* __restrict__ right, uint32_t* __restrict__ first, uint32_t* __restrict__ last,
+                             uint32_t* __restrict__ parentInner, uint32_t* __restrict__ parentLeaf, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi,
+                             uint32_t* __restrict__ outRef, float4* __restrict__ outLo, float4* __restrict__ outHi, uint32_t* __restrict__ valid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const uint32_t j = nn[i];
+    const bool mutual = j < c && nn[j] == i;
+    if (mutual && i > j) { valid[i] = 0u; return; }
+    valid[i] = 1u;
+    if (!mutual) { outRef[i] = cl[i]; outLo[i] = clLo[i]; outHi[i] = clHi[i]; return; }
+    const uint32_t a = cl[i], b = cl[j];
+    const uint32_t id = atomicAdd(nodeCount, 1u);
+    const float4 alo = clLo[i], ahi = clHi[i], blo = clLo[j], bhi = clHi[j];
+    const float4 lo = mk4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f), hi = mk4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+    left[id] = a; right[id] = b;
+    const uint32_t na = (a & kLeafBit) ? 1u : last[a] + 1u, nb = (b & kLeafBit) ? 1u : last[b] + 1u;
+    first[id] = 0u; last[id] = na + nb - 1u;  // (first, last) only carry the triangle count of the subtree here: last - first + 1
+    if (a & kLeafBit) parentLeaf[a & ~kLeafBit] = id; else parentInner[a] = id;
+    if (b & kLeafBit) parentLeaf[b & ~kLeafBit] = id; else parentInner[b] = id;
+    parentInner[id] = 0xffffffffu;  // until a later merge adopts this node: the last node created stays the root
+    nodeLo[id] = lo; nodeHi[id] = hi;
+    outRef[i] = id; outLo[i] = lo; outHi[i] = hi;
+}
+__global__ void k_ploc_compact(uint32_t c, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ offset, const uint32_t* __restrict__ ref, const float4* __restrict__ lo,
+                               const float4* __restrict__ hi, uint32_t* __restrict__ cl, float4* __restrict__ clLo, float4* __restrict__ clHi, uint32_t* __restrict__ newCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    if (valid[i]) { const uint32_t o = offset[i]; cl[o] = ref[i]; clLo[o] = lo[i]; clHi[o] = hi[i]; }
+    if (i == c - 1) *newCount = offset[i] + valid[i];
+}
+
 // ---- SAH-optimal collapse into wide nodes (Ylitie, Karras, Laine 2017, section 3.1) -------------------------------------------
 constexpr float kCostNode = 1.f, kCostPrim = .3f;
 // per binary internal node: cost[7] = C(n, 1..7); choice[8]: [0] = 1 when C(n,1) is the "own wide node" option (0 = leaf),
@@ -334,8 +415,16 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ que
             ++innerSeen;
         } else {
             node.meta[i] = uint8_t((k << 5) | triOff);
-            const uint32_t fp = tv.firstPos(c[i]);
-            for (uint32_t t = 0; t < k; ++t) outTris[triBase + triOff + t] = srcTris[tv.sorted[fp + t]];
+            // the <= 3 triangles under this binary node, by a walk over its subtree (a PLOC subtree is not a contiguous range of the Morton order)
+            uint32_t st[4];
+            int sp = 0;
+            uint32_t emitted = 0;
+            st[sp++] = c[i];
+            while (sp > 0) {
+                const uint32_t r = st[--sp];
+                if (r & kLeafBit) { outTris[triBase + triOff + emitted] = srcTris[tv.sorted[r & ~kLeafBit]]; ++emitted; }
+                else if (sp + 2 <= 4) { st[sp++] = tv.right[r]; st[sp++] = tv.left[r]; }
+            }
             triOff += k;
         }
     }
@@ -344,13 +433,13 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ que
   }
 }
 
-template <bool ANY>
+template <bool ANY, bool kNearest>
 __global__ void __launch_bounds__(128) k_trace(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, uint32_t n, const float* __restrict__ rays, uint32_t* __restrict__ out,
                                                float* __restrict__ outT, uint32_t* __restrict__ overflow) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i)), b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
         Hit h;
-        const bool hit = traverseBvh<ANY>(nodes, tris, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, h, overflow);
+        const bool hit = traverseBvh<ANY, kNearest>(nodes, tris, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, h, overflow);
         if (ANY) out[i] = hit ? 1u : 0u;
         else {
             reinterpret_cast<uint4*>(out)[i] = hit ? make_uint4(h.instanceID, h.primitiveIndex, __float_as_uint(h.u), __float_as_uint(h.v)) : make_uint4(0xffffffffu, 0u, 0u, 0u);
@@ -452,9 +541,51 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
         c->stats.kernelLaunches++;
         levels = 1;
     } else {
+        uint32_t rootId = 0;
+#if PLT_BVH_PLOC
+        {
+            // cluster arrays (main + the merge pass's output before compaction), nearest-neighbour / keep / offset words, scan scratch
+            DevBuf& ploc = c->lanes[0].work[39];
+            size_t scanBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(n), s);
+            scanBytes = (scanBytes + 255) & ~size_t(255);
+            PLT_CUDA(ploc.ensure(size_t(n) * (2 * 36 + 12) + scanBytes + 256));
+            float4* clLo = ploc.as<float4>();
+            float4* clHi = clLo + n;
+            float4* tmpLo = clHi + n;
+            float4* tmpHi = tmpLo + n;
+            uint32_t* cl = reinterpret_cast<uint32_t*>(tmpHi + n);
+            uint32_t* tmpRef = cl + n;
+            uint32_t* nn = tmpRef + n;
+            uint32_t* valid = nn + n;
+            uint32_t* offset = valid + n;
+            uint32_t* plocWords = offset + n;  // [0] nodes created, [1] clusters after the compaction
+            void* scanTemp = reinterpret_cast<uint8_t*>(plocWords) + 256;
+            PLT_CUDA(cudaMemsetAsync(plocWords, 0, 8, s));
+            k_ploc_init<<<blocksFor(n, 256), 256, 0, s>>>(n, valsOut, triLo.as<float4>(), triHi.as<float4>(), cl, clLo, clHi);
+            uint32_t clusters = n, iterations = 0;
+            while (clusters > 1) {
+                k_ploc_nearest<<<blocksFor(clusters, kPlocThreads), kPlocThreads, 0, s>>>(clusters, clLo, clHi, nn);
+                k_ploc_merge<<<blocksFor(clusters, 256), 256, 0, s>>>(clusters, cl, clLo, clHi, nn, plocWords, left, right, first, last, parentInner, parentLeaf, nodeLo, nodeHi, tmpRef, tmpLo, tmpHi, valid);
+                PLT_CUDA(cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, valid, offset, int(clusters), s));
+                k_ploc_compact<<<blocksFor(clusters, 256), 256, 0, s>>>(clusters, valid, offset, tmpRef, tmpLo, tmpHi, cl, clLo, clHi, plocWords + 1);
+                uint32_t next = 0;
+                PLT_CUDA(cudaMemcpyAsync(&next, plocWords + 1, 4, cudaMemcpyDeviceToHost, s));
+                PLT_CUDA(cudaStreamSynchronize(s));
+                c->stats.kernelLaunches += 4;
+                if (next == 0 || next >= clusters || ++iterations > 4096) { setError("PLOC did not converge: " + std::to_string(clusters) + " -> " + std::to_string(next) + " clusters"); return PLTPT_ERR_CUDA; }
+                clusters = next;
+            }
+            PLT_CUDA(cudaMemcpyAsync(&rootId, cl, 4, cudaMemcpyDeviceToHost, s));
+            PLT_CUDA(cudaStreamSynchronize(s));
+            if (rootId & kLeafBit) { setError("PLOC root is a leaf"); return PLTPT_ERR_CUDA; }
+            ploc.release();
+        }
+#else
         k_radix_tree<<<blocksFor(n - 1, 256), 256, 0, s>>>(int(n), keysOut, left, right, first, last, parentInner, parentLeaf);
         PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(n) * 4, s));
         k_fit<<<blocksFor(n, 256), 256, 0, s>>>(int(n), valsOut, triLo.as<float4>(), triHi.as<float4>(), left, right, parentInner, parentLeaf, nodeLo, nodeHi, arrivals);
+#endif
         // SAH tables of the dynamic programme (7 costs + 8 choices per binary node), bottom-up like the box fit
         DevBuf& sahBuf = c->lanes[0].work[25];
         PLT_CUDA(sahBuf.ensure(size_t(n) * (7 * 4 + 8)));
@@ -463,7 +594,7 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
         PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(n) * 4, s));
         k_sah_costs<<<blocksFor(n, 256), 256, 0, s>>>(int(n), valsOut, triLo.as<float4>(), triHi.as<float4>(), left, right, first, last, parentInner, parentLeaf, nodeLo, nodeHi, arrivals, sah);
         c->stats.kernelLaunches += 6;
-        const CollapseItem root{0u, 0u};
+        const CollapseItem root{rootId, 0u};
         PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
         // top-down: one launch per level over a persistent grid; the host reads the queue length once per 16 levels only
         const uint32_t grid = uint32_t(sms) * 8;
@@ -479,9 +610,9 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
         }
         float rootCost = 0.f;
         float4 rl, rh;
-        PLT_CUDA(cudaMemcpyAsync(&rootCost, sah.cost, 4, cudaMemcpyDeviceToHost, s));
-        PLT_CUDA(cudaMemcpyAsync(&rl, nodeLo, 16, cudaMemcpyDeviceToHost, s));
-        PLT_CUDA(cudaMemcpyAsync(&rh, nodeHi, 16, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaMemcpyAsync(&rootCost, sah.cost + size_t(rootId) * 7, 4, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaMemcpyAsync(&rl, nodeLo + rootId, 16, cudaMemcpyDeviceToHost, s));
+        PLT_CUDA(cudaMemcpyAsync(&rh, nodeHi + rootId, 16, cudaMemcpyDeviceToHost, s));
         PLT_CUDA(cudaStreamSynchronize(s));
         const float ra = (rh.x - rl.x) * (rh.y - rl.y) + (rh.y - rl.y) * (rh.z - rl.z) + (rh.z - rl.z) * (rh.x - rl.x);
         c->stats.bvhSahCost = ra > 0.f ? double(rootCost) / double(ra) : 0.0;
@@ -519,8 +650,11 @@ static int traceLaunch(PltptContext* c, bool any, uint32_t n, const float* rays,
         const uint32_t lgrid = std::min<uint32_t>(blocksFor(n, 128), uint32_t(sms) * 8);
         if (any) k_trace_lanes<true><<<lgrid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, cursor, overflow);
         else k_trace_lanes<false><<<lgrid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, cursor, overflow);
-    } else if (any) k_trace<true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);
-    else k_trace<false><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, overflow);
+    } else if (c->traceMode == PLTPT_TRACE_ONE_RAY_PER_THREAD_NEAREST_FIRST) {  // what traceClosestHit() / occluded() inside the connect and manifold kernels run
+        if (any) k_trace<true, true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);
+        else k_trace<false, true><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, overflow);
+    } else if (any) k_trace<true, false><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, nullptr, overflow);  // the tiny-scene trace kernels
+    else k_trace<false, false><<<grid, 128, 0, s>>>(c->scene.bvhNodes, c->scene.bvhTris, n, rays, out, outT, overflow);
     c->stats.kernelLaunches++;
     (any ? c->stats.raysAny : c->stats.raysClosest) += n;
     PLT_CUDA(cudaGetLastError());

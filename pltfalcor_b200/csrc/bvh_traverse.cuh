@@ -113,7 +113,7 @@ PLT_D bool testLeafTriangles(const BvhTri* __restrict__ tris, const RayConst& R,
 // One popped node: slab tests of its children, ordered push of the intersected inner children; the triangles of its intersected leaf
 // children are returned in (triBaseOut, triMaskOut) for testLeafTriangles() -- at once (traverseBvh) or batched over the lanes of a warp
 // (travPersistent with PLT_DEFER_LEAVES).
-template <bool ANY>
+template <bool ANY, bool kNearest>
 PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uint32_t ni, float bestT, uint32_t* stack, float* stackT, int& sp,
                        uint32_t* overflow, TraversalCounters* tc, uint32_t& triBaseOut, uint32_t& triMaskOut) {
     const float3 o = R.o;
@@ -138,15 +138,13 @@ PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uin
         const uint32_t nxA = negx ? n3.z : n2.x, nxB = negx ? n3.w : n2.y, fxA = negx ? n2.x : n3.z, fxB = negx ? n2.y : n3.w;
         const uint32_t nyA = negy ? n4.x : n2.z, nyB = negy ? n4.y : n2.w, fyA = negy ? n2.z : n4.x, fyB = negy ? n2.w : n4.y;
         const uint32_t nzA = negz ? n4.z : n3.x, nzB = negz ? n4.w : n3.y, fzA = negz ? n3.x : n4.z, fzB = negz ? n3.y : n4.w;
-#ifndef PLT_PUSH_NEAREST
-#define PLT_PUSH_NEAREST 0  // 1: intersected inner children are pushed straight from the slab-test loop and only the nearest is moved to the top
-#endif
-#if PLT_PUSH_NEAREST
+        // kNearest: intersected inner children are pushed straight from the slab-test loop and only the nearest is then moved to the top of
+        // the stack (the others keep slot order and are culled against the closest hit when popped); otherwise all of them are pushed in
+        // order of distance, farthest first.  The ordered push was 28 % of k_trace's issue slots at 6 of 32 lanes on the 10 M-triangle city
+        // (profiles/r2o_trace_sass_segments.txt); on a scene of a handful of nodes it is the faster of the two (profiles/r2o_variants.log).
         const int sp0 = sp;
-#else
         float nearT[8];
         uint32_t innerHits = 0;
-#endif
         uint32_t triMask = 0;
         // exact-t ties in another leaf must still be visited: keep the far limit a few ulps beyond the best hit
         const float tfarLimit = bestT * 1.000002f;
@@ -162,24 +160,21 @@ PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uin
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tfarLimit));
             if (!(tn <= tf)) continue;
-#if PLT_PUSH_NEAREST
             if (inner) {
-                if (sp < kTraversalStack) {
-                    if (!ANY) stackT[sp] = tn;
-                    stack[sp++] = childBase + __popc(imask & ((1u << i) - 1u));
-                } else if (overflow) atomicAdd(overflow, 1u);
+                if (kNearest) {
+                    if (sp < kTraversalStack) {
+                        if (!ANY) stackT[sp] = tn;
+                        stack[sp++] = childBase + __popc(imask & ((1u << i) - 1u));
+                    } else if (overflow) atomicAdd(overflow, 1u);
+                } else { nearT[i] = tn; innerHits |= 1u << i; }
             }
-#else
-            if (inner) { nearT[i] = tn; innerHits |= 1u << i; }
-#endif
             else triMask |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);  // the leaf's triangles: slots [offset, offset + count) of this node's <= 24
         }
         // The triangles of all intersected leaf children are tested in ONE loop after the slab tests (testLeafTriangles): tested inside the
         // unrolled child loop, every child was a separate divergence point.
         triBaseOut = triBase; triMaskOut = triMask;
-#if PLT_PUSH_NEAREST
         // the nearest of the children just pushed goes on top (popped next); the others stay in slot order and are culled at pop time
-        if (!ANY && sp - sp0 > 1) {
+        if (kNearest && !ANY && sp - sp0 > 1) {
             int bestK = sp0;
             float bt = stackT[sp0];
             for (int k = sp0 + 1; k < sp; ++k) { const float t = stackT[k]; if (t < bt) { bt = t; bestK = k; } }
@@ -188,9 +183,8 @@ PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uin
                 stackT[bestK] = stackT[sp - 1]; stackT[sp - 1] = bt;
             }
         }
-#else
         // push the intersected inner children, farthest first, so the nearest is popped next
-        while (innerHits) {
+        while (!kNearest && innerHits) {
             int far = -1;
             float ft = -1.f;
             if (ANY) far = __ffs(innerHits) - 1;
@@ -205,11 +199,10 @@ PLT_D void processNode(const BvhNode* __restrict__ nodes, const RayConst& R, uin
                 stack[sp++] = childBase + __popc(imask & ((1u << far) - 1u));
             } else if (overflow) atomicAdd(overflow, 1u);
         }
-#endif
 }
 // One ray to completion in the calling thread: the same processNode() the persistent-lane driver steps through (one node body, so the
 // bit-exact hit-ID checks of either driver cover the arithmetic of both; measured equal to a hand-inlined copy, profiles/r2a_variants.log).
-template <bool ANY>
+template <bool ANY, bool kNearest = true>
 PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, float3 o, float3 d, float tmin, float tmax, Hit& best, uint32_t* overflow = nullptr,
                        TraversalCounters* tc = nullptr) {
     best.instanceID = 0xffffffffu;
@@ -225,7 +218,7 @@ PLT_D bool traverseBvh(const BvhNode* __restrict__ nodes, const BvhTri* __restri
         const uint32_t ni = stack[--sp];
         if (!ANY && stackT[sp] > best.t * 1.000002f) continue;  // (same slack as tfarLimit in processNode: exact-t ties are still visited)
         uint32_t triBase, triMask;
-        processNode<ANY>(nodes, R, ni, best.t, stack, stackT, sp, overflow, tc, triBase, triMask);
+        processNode<ANY, kNearest>(nodes, R, ni, best.t, stack, stackT, sp, overflow, tc, triBase, triMask);
         if (testLeafTriangles<ANY>(tris, R, triBase, triMask, best, tc)) return true;
     }
     return best.valid();
@@ -256,7 +249,7 @@ PLT_D bool travStep(const BvhNode* __restrict__ nodes, const BvhTri* __restrict_
     const uint32_t ni = T.stack[--T.sp];
     if (!ANY && T.stackT[T.sp] > T.best.t * 1.000002f) return T.sp == 0;
     uint32_t triBase, triMask;
-    processNode<ANY>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
+    processNode<ANY, false>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
     if (testLeafTriangles<ANY>(tris, T.R, triBase, triMask, T.best, tc)) { T.sp = 0; return true; }
     return T.sp == 0;
 }
@@ -266,8 +259,10 @@ PLT_D void travStepDeferred(const BvhNode* __restrict__ nodes, Trav<ANY>& T, uin
     triMask = 0;
     if (T.sp <= 0) return;
     const uint32_t ni = T.stack[--T.sp];
+    // (popping on until an entry survives the cull, so that the lane never idles through a node step, measured slower: city trace 8.2 -> 9.5 ms,
+    // profiles/r2p_kernel_times.log against r2o_kernel_times.log)
     if (!ANY && T.stackT[T.sp] > T.best.t * 1.000002f) return;
-    processNode<ANY>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
+    processNode<ANY, true>(nodes, T.R, ni, T.best.t, T.stack, T.stackT, T.sp, overflow, tc, triBase, triMask);
 }
 
 // Persistent-lane driver for a queue of `n` rays (Aila & Laine 2009, "Understanding the Efficiency of Ray Traversal on GPUs",
@@ -284,7 +279,7 @@ PLT_D void travStepDeferred(const BvhNode* __restrict__ nodes, Trav<ANY>& T, uin
 #define PLT_TRAV_STEPS 4
 #endif
 #ifndef PLT_DEFER_LEAVES
-#define PLT_DEFER_LEAVES 0
+#define PLT_DEFER_LEAVES 1  // 0: the round-1 driver (triangles tested inside the step, ordered push), kept for comparison (tools/variants.py: trav_legacy)
 #endif
 constexpr int kRefillLanes = PLT_TRAV_REFILL, kStepsPerRound = PLT_TRAV_STEPS;
 template <bool ANY, class Fetch, class Commit>

@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_SHADOW_TRACE) k_shadow
         const float4 r0 = P.shadowRays[2 * size_t(i)], r1 = P.shadowRays[2 * size_t(i) + 1];
         const float3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
         Hit h;
-        const bool hit = (item.info.y & CI_ANY_HIT) ? traverseBvh<true>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc)
-                                                    : traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
+        const bool hit = (item.info.y & CI_ANY_HIT) ? traverseBvh<true, false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc)
+                                                    : traverseBvh<false, false>(P.sc.bvhNodes, P.sc.bvhTris, o, d, r0.w, r1.w, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
         shadowAnswer(P, list, i, item, hit, h);
     }
     warpAdd(P.counters + 5, tc.nodes);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_TRACE) k_trace_simple(
         if (live) {
             const float4 o = P.psOrigin[pixel], d = P.psDir[pixel];
             Hit h;
-            const bool hit = traverseBvh<false>(P.sc.bvhNodes, P.sc.bvhTris, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.f, kFltMax, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
+            const bool hit = traverseBvh<false, false>(P.sc.bvhNodes, P.sc.bvhTris, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.f, kFltMax, h, reinterpret_cast<uint32_t*>(P.counters + 2), &tc);
             const uint32_t type = tracePathCommit(P, pixel, hit, h);
             if (type != 0u) enqueueJob<false>(P, type, pixel);
         }

@@ -158,6 +158,37 @@ __global__ void __launch_bounds__(kStageThreads, PLT_MINB_UNWIND_STEP) k_unwind_
 }
 #endif
 
+// The BSDF query of pltpt_bsdf_eval_mueller evaluated with THIS translation unit's arithmetic (approximate division / square root,
+// contracted FMAs, PLT_FAST_MATH) and the renderer's own single-column beam: what k_unwind_step computes for a replayed vertex.  Not a
+// benchmark kernel (four evaluations per matrix, plain stores): it exists so that the BSDF tolerance tests can state how far the replay's
+// arithmetic is from the oracle's (tests/test_gpu_bsdf.py::test_replay_arithmetic_*).
+__global__ void __launch_bounds__(128) k_bsdf_eval_replay_math(DevScene sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* __restrict__ wi,
+                                                               const float* __restrict__ wo, const float* __restrict__ hero, float* __restrict__ out, int hwss, float maxBeamOmega) {
+    const uint64_t total = uint64_t(n) * groups;
+    const DevMaterial m = loadMaterial(sc.materials, materialID);
+    const BsdfCtx cx = {sc.profiles, hwss};
+    for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total; item += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = uint32_t(item / groups), g = uint32_t(item % groups);
+        const float3 Wi = mk3(__ldg(wi + 3 * size_t(i)), __ldg(wi + 3 * size_t(i) + 1), __ldg(wi + 3 * size_t(i) + 2));
+        const float3 Wo = mk3(__ldg(wo + 3 * size_t(i)), __ldg(wo + 3 * size_t(i) + 1), __ldg(wo + 3 * size_t(i) + 2));
+        const float4 wl = hwssWavelengths(__ldg(hero + size_t(g) * n + i), hwss);
+        SD sd;
+        sd.posW = mk3(0.f); sd.V = Wi; sd.N = mk3(0.f, 0.f, 1.f); sd.T = mk3(1.f, 0.f, 0.f); sd.B = mk3(0.f, 1.f, 0.f);
+        sd.faceN = sd.N; sd.uv = mk2(0.f, 0.f); sd.materialID = materialID; sd.frontFacing = true;
+        float* dst = out + item * size_t(hwss) * 16;
+        for (int c = 0; c < 4; ++c) {
+            Beam beam = sourceBeamArea(Wi, -Wi, 1.f, 1.f, mk4(1.f), wl, maxBeamOmega, hwss);
+            beam.L = mk4(c == 0 ? 1.f : 0.f); beam.L1 = mk4(c == 1 ? 1.f : 0.f); beam.L2 = mk4(c == 2 ? 1.f : 0.f); beam.L3 = mk4(c == 3 ? 1.f : 0.f);
+            beam.propagate(sd.posW);
+            bsdfEval(m, cx, sd, Wo, lobe, beam);
+            for (int j = 0; j < hwss; ++j) {
+                const float4 SP = beam.getSP(j);
+                dst[j * 16 + 0 + c] = SP.x; dst[j * 16 + 4 + c] = SP.y; dst[j * 16 + 8 + c] = SP.z; dst[j * 16 + 12 + c] = SP.w;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ FrameParams P) {
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
     if (pixel < P.pixelCount) resolvePixel(P, pixel);
@@ -171,6 +202,10 @@ void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s) {
     if (P.sc.tex.blobs) k_unwind_step<true><<<grid, kStageThreads, 0, s>>>(P);
     else k_unwind_step<false><<<grid, kStageThreads, 0, s>>>(P);
+}
+void launchBsdfEvalReplayMath(const DevScene& sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* wi, const float* wo, const float* hero, float* out, int hwss,
+                              float maxBeamOmega, uint32_t grid, cudaStream_t s) {
+    k_bsdf_eval_replay_math<<<grid, 128, 0, s>>>(sc, materialID, lobe, n, groups, wi, wo, hero, out, hwss, maxBeamOmega);
 }
 void launchResolve(const FrameParams& P, cudaStream_t s) { k_resolve<<<(P.pixelCount + 255) / 256, 256, 0, s>>>(P); }
 }  // namespace plt

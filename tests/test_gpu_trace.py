@@ -25,7 +25,7 @@ def loaded(request, torch_cuda, oracle):
     p.close()
 
 
-MODES = {"one_ray_per_thread": 1, "persistent_lanes": 2}  # include/pltpt.h PLTPT_TRACE_*: both traversal drivers of the renderer
+MODES = {"one_ray_per_thread": 1, "persistent_lanes": 2, "one_ray_per_thread_nearest_first": 3}  # include/pltpt.h PLTPT_TRACE_*: every traversal driver of the renderer
 
 
 def _trace_gpu(torch, p, rays, mode=0):

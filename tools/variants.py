@@ -38,6 +38,12 @@ VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their ou
     "push_near": {"stage_sample.cu": ["-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_PUSH_NEAREST=1"]},
     "defer": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1"]},
     "defer_push": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"]},
+    "trav_legacy": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=0"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=0"], "bvh.cu": ["-DPLT_DEFER_LEAVES=0"]},
+    "defer_s8": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=8"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=8"], "bvh.cu": ["-DPLT_TRAV_STEPS=8"]},
+    "defer_s6": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=6"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=6"], "bvh.cu": ["-DPLT_TRAV_STEPS=6"]},
+    "bvh_lbvh": {"bvh.cu": ["-DPLT_BVH_PLOC=0"]},
+    "ploc_r16": {"bvh.cu": ["-DPLT_PLOC_RADIUS=16"]},
+    "ploc_r4": {"bvh.cu": ["-DPLT_PLOC_RADIUS=4"]},
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
