@@ -177,4 +177,7 @@ int renderFrame(PltptContext* c, int lane, uint32_t frameCount, const PltptCamer
 int renderFrameSplit(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* color, float* albedo, float* normal, cudaStream_t s);
 int sampleStageToHost(PltptContext* c, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t h, float* albedo, float* normal, PltptBounce* host);
 int syncFrameStats(PltptContext* c);
+// stage_unwind.cu: the BSDF query of pltpt_bsdf_eval_mueller evaluated with the replay step's arithmetic (test hook)
+void launchBsdfEvalReplayMath(const DevScene& sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* wi, const float* wo, const float* hero, float* out, int hwss,
+                              float maxBeamOmega, uint32_t grid, cudaStream_t s);
 }  // namespace plt

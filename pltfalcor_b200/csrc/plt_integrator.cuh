@@ -1438,8 +1438,6 @@ uint32_t mneeCooperativeGrid(int device);  // resident CTAs of k_mnee_walk on `d
 void launchSortFlip(const FrameParams& P, SortView v, bool resetTraceQueue, uint32_t grid, cudaStream_t s);
 void launchUnwindStep(const FrameParams& P, uint32_t grid, cudaStream_t s);
 void launchResolve(const FrameParams& P, cudaStream_t s);
-void launchBsdfEvalReplayMath(const DevScene& sc, uint32_t materialID, uint32_t lobe, uint32_t n, uint32_t groups, const float* wi, const float* wo, const float* hero, float* out, int hwss,
-                              float maxBeamOmega, uint32_t grid, cudaStream_t s);  // stage_unwind.cu: the BSDF query with the replay step's arithmetic
 void launchGatherBounces(const FrameParams& P, PltptBounce* out, uint32_t records, cudaStream_t s);
 
 }  // namespace plt
