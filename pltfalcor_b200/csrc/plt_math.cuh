@@ -117,8 +117,15 @@ inline uint32_t asuint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float asfloat(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #endif
 
-// fp16 -> fp32 (f16tof32). Bit-exact, no half type needed.
+// fp16 -> fp32 (f16tof32): exact for every finite value, subnormals included.  On the device it is the hardware conversion (one
+// instruction; the bit manipulation below was a tenth of k_shade's instructions: three vertex normals + texture coordinates per hit,
+// profiles/r2t_shade_lines.txt); the host keeps the portable form.
 PLT_HD float h2f(uint32_t h) {
+#ifdef __CUDA_ARCH__
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((unsigned short)(h & 0xffffu)));
+    return f;
+#endif
     h &= 0xffffu;
     const uint32_t sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1f;
     uint32_t man = h & 0x3ffu, out;

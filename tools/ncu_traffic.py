@@ -4,6 +4,7 @@ utilisation and warp execution efficiency next to it.  Usage: ncu_traffic.py out
 import collections
 import csv
 import json
+import re
 import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "ms": 1.0, "msecond": 1.0, "second": 1e3, "s": 1e3}
@@ -34,7 +35,7 @@ for path in sys.argv[2:]:
         return v * UNIT.get(units[col[name]], 1.0) if scale else v
 
     for r in rows[2:]:
-        k = r[col["Kernel Name"]].split("(")[0].split("::")[-1]  # "plt::<unnamed>::k_x(FrameParams)" (ncu may print "unnamed>::k_x") -> "k_x"
+        k = re.sub(r"<[^<>]*>$", "", r[col["Kernel Name"]].split("(")[0].split("::")[-1])  # "plt::<unnamed>::k_x<0>(FrameParams)" (ncu may print "unnamed>::k_x") -> "k_x"
         a = acc[k]
         rd, wr = get(r, "dram__bytes_read.sum"), get(r, "dram__bytes_write.sum")
         if rd is not None and wr is not None:
