@@ -26,6 +26,8 @@ using namespace Falcor;
 namespace {
 struct SceneFile {
     std::vector<std::vector<char>> blobs;
+    std::vector<PltptTextureDesc> textures;   // descriptor arrays the scene description points at (host memory, include/pltpt.h)
+    std::vector<PltptSamplerDesc> samplers;
     PltptSceneDesc desc{};
     PltptCameraData camera{};
 };
@@ -75,6 +77,24 @@ bool loadScene(const std::string& path, SceneFile& s) {
         if (!readExact(f, wh, sizeof wh) || !readExact(f, &d.envMap, sizeof d.envMap) || !readExact(f, s.blobs.back().data(), envBytes)) return false;
         d.envMapTexels = reinterpret_cast<const float*>(s.blobs.back().data());
         d.envMapWidth = wh[0]; d.envMapHeight = wh[1];
+    }
+    // optional second trailing section: material textures and samplers (pltfalcor_b200/scene.py SceneBuffers.save)
+    uint32_t counts[2] = {0, 0};
+    if (readExact(f, counts, sizeof counts) && (counts[0] || counts[1])) {
+        s.textures.resize(counts[0]);
+        s.samplers.resize(counts[1]);
+        s.blobs.reserve(s.blobs.size() + counts[0]);  // (the descriptors point into the blobs: no reallocation after this)
+        for (auto& t : s.textures) {
+            uint32_t hdr[4];
+            uint64_t bytes = 0;
+            if (!readExact(f, hdr, sizeof hdr) || !readExact(f, &bytes, 8)) return false;
+            s.blobs.emplace_back(bytes);
+            if (bytes && !readExact(f, s.blobs.back().data(), bytes)) return false;
+            t = PltptTextureDesc{s.blobs.back().data(), hdr[0], hdr[1], hdr[2], 0};
+        }
+        for (auto& q : s.samplers) if (!readExact(f, &q, sizeof q)) return false;
+        d.textures = s.textures.data(); d.textureCount = counts[0];
+        d.samplers = s.samplers.data(); d.samplerCount = counts[1];
     }
     return true;
 }

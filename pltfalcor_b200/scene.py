@@ -417,6 +417,18 @@ class SceneBuffers:
                 f.write(np.array([s["envMapWidth"], s["envMapHeight"]], np.uint32).tobytes())
                 f.write(bytes(self.desc().envMap))
                 f.write(np.ascontiguousarray(env).tobytes())
+            # optional second trailing section: material textures and samplers -- u32 texture count, u32 sampler count, per texture
+            # {u32 width, height, format, 0; u64 texel bytes; texels}, per sampler the 32 B PltptSamplerDesc
+            tex, smp = s.get("textures") or [], s.get("samplers") or []
+            f.write(np.array([len(tex), len(smp)], np.uint32).tobytes())
+            for k, (w, h, fmt) in enumerate(tex):
+                raw = np.ascontiguousarray(self.arrays[f"texture{k}"]).tobytes()
+                f.write(np.array([w, h, fmt, 0], np.uint32).tobytes())
+                f.write(np.uint64(len(raw)).tobytes())
+                f.write(raw)
+            for flt, au, av, border in smp:
+                f.write(np.array([flt, au, av, 0], np.uint32).tobytes())
+                f.write(np.array(border, np.float32).tobytes())
 
 
 def _alloc_bits(count):

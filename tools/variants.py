@@ -16,34 +16,25 @@ sys.path.insert(0, ROOT)
 from pltfalcor_b200 import build as B  # noqa: E402
 
 VDIR = os.path.join(B._HERE, "build", "variants")
-VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their outcomes are listed in DESIGN.md section 3
+_FM = ["-prec-div=false", "-prec-sqrt=false", "-fmad=true"]
+_TRAV = ("stage_sample.cu", "stage_connect.cu", "bvh.cu")   # translation units that instantiate the traversal
+VARIANTS = {  # name -> {source: extra nvcc flags}; the experiments and their outcomes are listed in DESIGN.md section 3 (the log behind each in profiles/)
     "base": {},
-    "stage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=1"]},                          # k_unwind_step with cp.async staging of the thread's next item
-    "fm_flags": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true"]},
-    "fm_u": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"]},
-    "fm_uc": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true"]},
-    "ufm_u": {"stage_unwind.cu": ["-use_fast_math", "-DPLT_FAST_MATH=1"]},
-    "fm_mb5": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_MINB_UNWIND_STEP=5"]},
-    "fm_mb3": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_MINB_UNWIND_STEP=3"]},
-    "fm_unroll": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1", "-DPLT_LAMBDA_UNROLL=1"]},
-    "c_fmad": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-fmad=true"]},
-    "c_div": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-div=false"]},
-    "c_sqrt": {"stage_unwind.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"], "stage_connect.cu": ["-prec-sqrt=false"]},
-    "nrm_rcp": {"stage_sample.cu": ["-DPLT_NORMALIZE_RCP=1"], "stage_connect.cu": ["-DPLT_NORMALIZE_RCP=1"]},  # (breaks oracle parity unless the oracle follows)
-    "trav_r4": {"stage_sample.cu": ["-DPLT_TRAV_REFILL=4"], "stage_connect.cu": ["-DPLT_TRAV_REFILL=4"]},
-    "trav_r16": {"stage_sample.cu": ["-DPLT_TRAV_REFILL=16"], "stage_connect.cu": ["-DPLT_TRAV_REFILL=16"]},
-    "trav_s2": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=2"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=2"]},
-    "trav_s8": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=8"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=8"]},
-    "sweep_fm": {"api.cu": ["-prec-div=false", "-prec-sqrt=false", "-fmad=true", "-DPLT_FAST_MATH=1"]},
-    "push_near": {"stage_sample.cu": ["-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_PUSH_NEAREST=1"]},
-    "defer": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1"]},
-    "defer_push": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"], "bvh.cu": ["-DPLT_DEFER_LEAVES=1", "-DPLT_PUSH_NEAREST=1"]},
-    "trav_legacy": {"stage_sample.cu": ["-DPLT_DEFER_LEAVES=0"], "stage_connect.cu": ["-DPLT_DEFER_LEAVES=0"], "bvh.cu": ["-DPLT_DEFER_LEAVES=0"]},
-    "defer_s8": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=8"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=8"], "bvh.cu": ["-DPLT_TRAV_STEPS=8"]},
-    "defer_s6": {"stage_sample.cu": ["-DPLT_TRAV_STEPS=6"], "stage_connect.cu": ["-DPLT_TRAV_STEPS=6"], "bvh.cu": ["-DPLT_TRAV_STEPS=6"]},
-    "bvh_lbvh": {"bvh.cu": ["-DPLT_BVH_PLOC=0"]},
-    "ploc_r16": {"bvh.cu": ["-DPLT_PLOC_RADIUS=16"]},
-    "ploc_r4": {"bvh.cu": ["-DPLT_PLOC_RADIUS=4"]},
+    # -- replay step (product: stage_unwind.cu with _FM + PLT_FAST_MATH, pltfalcor_b200/build.py)
+    "unwind_exact": {"stage_unwind.cu": ["-prec-div=true", "-prec-sqrt=true", "-fmad=false", "-DPLT_FAST_MATH=0"]},   # rounds 1-2a: the oracle's rounding in the replay too
+    "stage": {"stage_unwind.cu": ["-DPLT_UNWIND_STAGE=1"]},                                                            # cp.async staging of the thread's next item (r2a: worse)
+    "ufm_u": {"stage_unwind.cu": ["-use_fast_math"]},                                                                  # r2h: nothing beyond _FM
+    "fm_mb5": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=5"]}, "fm_mb3": {"stage_unwind.cu": ["-DPLT_MINB_UNWIND_STEP=3"]},  # r2i: 96 / 160 registers
+    "fm_unroll": {"stage_unwind.cu": ["-DPLT_LAMBDA_UNROLL=1"]},                                                       # r2i: unrolled wavelength loops
+    # -- the same arithmetic elsewhere (rejected: parity)
+    "fm_uc": {"stage_connect.cu": _FM}, "c_fmad": {"stage_connect.cu": ["-fmad=true"]}, "c_div": {"stage_connect.cu": ["-prec-div=false"]}, "c_sqrt": {"stage_connect.cu": ["-prec-sqrt=false"]},  # r2h, r2j
+    "sweep_fm": {"api.cu": _FM + ["-DPLT_FAST_MATH=1"]},                                                               # r2n: 27 G evals/s, misses the 1e-4 BSDF tolerance
+    # -- traversal (product: deferred leaf tests + nearest-first push in the persistent driver, 8 idle lanes to refill, 4 node steps per round)
+    "trav_legacy": {f: ["-DPLT_DEFER_LEAVES=0"] for f in _TRAV},                                                       # the round-1 driver (r2o, r2p)
+    "trav_r4": {f: ["-DPLT_TRAV_REFILL=4"] for f in _TRAV}, "trav_r16": {f: ["-DPLT_TRAV_REFILL=16"] for f in _TRAV},
+    "trav_s2": {f: ["-DPLT_TRAV_STEPS=2"] for f in _TRAV}, "trav_s6": {f: ["-DPLT_TRAV_STEPS=6"] for f in _TRAV}, "trav_s8": {f: ["-DPLT_TRAV_STEPS=8"] for f in _TRAV},
+    # -- BVH builder (product: PLOC radius 8 + SAH-optimal collapse)
+    "bvh_lbvh": {"bvh.cu": ["-DPLT_BVH_PLOC=0"]}, "ploc_r16": {"bvh.cu": ["-DPLT_PLOC_RADIUS=16"]}, "ploc_r4": {"bvh.cu": ["-DPLT_PLOC_RADIUS=4"]},   # r2q
     "mneeprof": {"stage_connect.cu": ["-DPLT_MNEE_PHASE_TIMERS=1"]},               # per-round phase timers of k_mnee_walk (tools/mnee_profile.py)
 }
 
@@ -58,7 +49,12 @@ def build_variant(name, flags):
         extra = flags.get(src, [])
         if extra:
             extra = B.SOURCE_FLAGS.get(src, []) + extra   # (a later -D of the same macro wins)
-        base = [f for f in B.NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in extra)]
+        # a later -opt=value / -DNAME=value of the same option or macro wins (nvcc rejects a repeated single-value option)
+        last = {}
+        for f in extra:
+            last[f.split("=")[0]] = f
+        extra = [f for f in extra if last[f.split("=")[0]] is f]
+        base = [f for f in B.NVCC_FLAGS if f.split("=")[0] not in last or not f.startswith("-fmad")]
         if not extra:  # unchanged source: reuse the product object when it is fresh
             prod = os.path.join(B._HERE, "build", src.replace(".cu", ".o"))
             if os.path.exists(prod) and all(os.path.getmtime(x) <= os.path.getmtime(prod) for x in B._deps()):
