@@ -107,11 +107,11 @@ extern "C" int pltpt_set_work_budget(PltptHandle h, uint64_t bytes) {
     h->workBudgetBytes = size_t(bytes);
     return PLTPT_OK;
 }
-/* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 or 2 = two (default). */
+/* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 = the default (two), up to the lanes built in (four). */
 extern "C" int pltpt_set_frame_overlap(PltptHandle h, int frames) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (frames < 0 || frames > PltptContext::kLanes) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame overlap out of range (0 = default, 1 .. lanes built in)");
-    h->frameOverlap = frames == 0 ? PltptContext::kLanes : frames;
+    h->frameOverlap = frames == 0 ? PltptContext::kDefaultOverlap : frames;
     return PLTPT_OK;
 }
 extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {

@@ -73,7 +73,10 @@ struct DevBuf {
 }  // namespace plt
 
 #ifndef PLT_LANES
-#define PLT_LANES 2
+#define PLT_LANES 4   // frame lanes built in (streams + private work buffers, allocated when first used); pltpt_set_frame_overlap picks how many run
+#endif
+#ifndef PLT_DEFAULT_OVERLAP
+#define PLT_DEFAULT_OVERLAP 2
 #endif
 struct PltptContext {
     int device = 0;
@@ -116,7 +119,8 @@ struct PltptContext {
     cudaEvent_t guidesReady = nullptr, copyDone = nullptr;  // pltpt_render_frame_host: guide-buffer copies run on copyStream under the solve stage
     cudaStream_t copyStream = nullptr;
     bool armGuides = false, splitGuides = false;  // splitGuides: the last frame was split over both lanes (both guidesReady events count)
-    int frameOverlap = kLanes;  // frames in flight (pltpt_set_frame_overlap)
+    static constexpr int kDefaultOverlap = PLT_DEFAULT_OVERLAP < PLT_LANES ? PLT_DEFAULT_OVERLAP : PLT_LANES;
+    int frameOverlap = kDefaultOverlap;  // frames in flight (pltpt_set_frame_overlap)
     size_t workBudgetBytes = 0; // per-lane work-buffer budget that sizes the row tiles (0 = default 24 GB; pltpt_set_work_budget)
     plt::DevBuf outColor, outAlbedo, outNormal;
     plt::DevBuf hostAccum;                    // RGBA64F sums of pltpt_render_accumulate_host / _multi

@@ -68,7 +68,8 @@ def test_scene_file_carries_the_env_map(tmp_path, env):
     buffers.save(str(path), cam)
     raw = path.read_bytes()
     tex = buffers.arrays["envMapTexels"]
-    assert raw.endswith(tex.tobytes()) and len(raw) > tex.nbytes + 112 + 16
+    # the env-map section is followed by the (here empty) texture / sampler section: two u32 counts
+    assert raw.endswith(tex.tobytes() + b"\0" * 8) and len(raw) > tex.nbytes + 112 + 16 + 8
 
 
 @pytest.mark.gpu
