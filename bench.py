@@ -367,7 +367,7 @@ def main():
         raise SystemExit("connections were dropped or a traversal stack overflowed during the timed region: the result would be biased")
 
     # ---- per-kernel durations: this rank's share of ONE step again with a CUDA event after every launch on the launching stream.  The
-    # timed region above keeps two frames in flight on two streams (kernels of different frames share the SMs, so a per-launch duration
+    # timed region above keeps up to four frames in flight on their own streams (kernels of different frames share the SMs, so a per-launch duration
     # taken there would include the other frame's work); this pass runs the frames one after the other so that every kernel is timed
     # alone, which is what a roofline fraction needs.  Its frame time is reported as `sequential_ms_per_frame`.
     stats, seq_ms, prof_frames = timed_stats, None, 0
@@ -478,7 +478,7 @@ def main():
             "metric": "plt_paths_per_s", "value": value, "unit": "paths/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config][4], "name": args.config, "width": WIDTH, "height": HEIGHT, "max_bounces": MAX_BOUNCES, "hwss": 4, "nee": True, "mis": True, "mnee": True,
-                       "russian_roulette": True, "frames_in_flight": 2, "frames_per_step": F, "paths_per_step": WIDTH * HEIGHT * F * (world if args.scaling == "weak" else 1),
+                       "russian_roulette": True, "frames_in_flight": min(4, F), "frames_per_step": F, "paths_per_step": WIDTH * HEIGHT * F * (world if args.scaling == "weak" else 1),
                        "frames_total": job_frames,
                        "partition": ("frame index modulo n_gpus" if args.partition == "sample" else "bands of image rows, every rank renders all frames of its band") +
                                     "; fp64 accumulators summed by one NCCL reduce inside the timed region",

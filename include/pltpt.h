@@ -473,6 +473,13 @@ PLTPT_API int pltpt_get_light_collection(PltptHandle h, PltptEmissiveTriangle* t
  * single world-space BVH is rebuilt on the GPU, and a library-built light collection is re-derived. */
 PLTPT_API int pltpt_update_transforms(PltptHandle h, const float* worldMatrices, const float* inverseTransposeWorldMatrices, uint32_t matrixCount,
                                       uint32_t pointersAreDevice);
+/* How pltpt_update_transforms brings the BVH up to date: Scene::UpdateMode (Source/Falcor/Scene/Scene.h:169-173; the TLAS mode a host
+ * sets with Scene::setTlasUpdateMode, Scene.h:935, applied at Scene.cpp:3642-3650).  REBUILD (default, like Falcor's TLAS default,
+ * Scene.h:1371): a new tree.  REFIT: the tree keeps its topology, the leaf triangles are re-derived and every node box re-fitted
+ * bottom-up (bvh.cu k_refit_nodes) -- a fraction of the rebuild time, hits stay exact (the triangle test decides them), traversal
+ * cost grows with the distance the instances have moved since the last build, as it does for a refitted TLAS. */
+enum PltptBvhUpdateMode { PLTPT_BVH_UPDATE_REBUILD = 0, PLTPT_BVH_UPDATE_REFIT = 1 };
+PLTPT_API int pltpt_set_bvh_update_mode(PltptHandle h, int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Environment-map queries (parity checks of EnvMap.eval, EnvMap.slang:57-74, and EnvMapSampler.sample / evalPdf,
@@ -570,6 +577,7 @@ typedef struct PltptStats {
     uint64_t mneeWalks;                        /* manifold walks parked for k_mnee in the last tile of the last frame */
     double   bvhSahCost;                       /* SAH cost of the wide BVH relative to the root area (c_node = 1, c_prim = 0.3): the
                                                   minimum the collapse could reach on the binary tree (bvh.cu k_sah_costs) */
+    double   bvhRefitMs;                       /* device time of the last refit (pltpt_update_transforms in PLTPT_BVH_UPDATE_REFIT mode) */
 } PltptStats;
 PLTPT_API int pltpt_get_stats(PltptHandle h, PltptStats* out);
 PLTPT_API int pltpt_reset_stats(PltptHandle h);

@@ -18,7 +18,7 @@ EXPORTS = [
     "pltpt_render_frame", "pltpt_render_accumulate", "pltpt_render_frame_host", "pltpt_sample_stage_host", "pltpt_trace_closest", "pltpt_trace_any",
     "pltpt_bsdf_eval_mueller", "pltpt_bsdf_sample", "pltpt_get_stats", "pltpt_reset_stats", "pltpt_set_profiling",
     "pltpt_envmap_eval", "pltpt_envmap_sample", "pltpt_set_frame_overlap",
-    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_work_budget",
+    "pltpt_spd_load", "pltpt_gen_spectral_profile", "pltpt_pack_material", "pltpt_build_light_collection", "pltpt_get_light_collection", "pltpt_update_transforms", "pltpt_set_bvh_update_mode", "pltpt_set_work_budget",
     "pltpt_render_frame_host_async", "pltpt_host_wait", "pltpt_set_trace_mode",
     "pltpt_render_accumulate_rows", "pltpt_resolve_accumulated", "pltpt_render_accumulate_host", "pltpt_render_accumulate_multi",
     "pltpt_texture_sample", "pltpt_accumulate_frame", "pltpt_bsdf_eval_mueller_replay_math",
@@ -72,6 +72,7 @@ def lib():
         _lib.pltpt_pack_material.argtypes = [vp, vp]
         _lib.pltpt_build_light_collection.argtypes = [vp]
         _lib.pltpt_update_transforms.argtypes = [vp, vp, vp, u32, u32]
+        _lib.pltpt_set_bvh_update_mode.argtypes = [vp, C.c_int]
         _lib.pltpt_get_light_collection.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp]
         _lib.pltpt_envmap_eval.argtypes = [vp, u32, vp, vp, vp]
         _lib.pltpt_envmap_sample.argtypes = [vp, u32, vp, vp, vp]
@@ -180,7 +181,7 @@ class Pltpt:
         _check(lib().pltpt_set_profiling(self.h, 1 if enable else 0))
 
     def set_frame_overlap(self, frames):
-        """Frames render_accumulate keeps in flight: 2 (default) or 1."""
+        """Frames render_accumulate keeps in flight: 0 = default (4), 1 .. 4."""
         _check(lib().pltpt_set_frame_overlap(self.h, int(frames)))
 
     def set_work_budget(self, nbytes):
@@ -245,6 +246,10 @@ class Pltpt:
         """world, world_it: (n,4,4) float32 host arrays (row-major), like SceneBuffers.arrays['worldMatrices']."""
         world, world_it = np.ascontiguousarray(world, np.float32), np.ascontiguousarray(world_it, np.float32)
         _check(lib().pltpt_update_transforms(self.h, _hp(world), _hp(world_it), len(world), 0))
+
+    def set_bvh_update_mode(self, mode):
+        """0 = rebuild (default), 1 = refit (include/pltpt.h PltptBvhUpdateMode; Scene::UpdateMode, Scene.h:169-173)."""
+        _check(lib().pltpt_set_bvh_update_mode(self.h, int(mode)))
 
     # ---- light collection built by the library -------------------------------------------------------------------
     def build_light_collection(self):

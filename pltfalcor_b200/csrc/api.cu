@@ -107,11 +107,17 @@ extern "C" int pltpt_set_work_budget(PltptHandle h, uint64_t bytes) {
     h->workBudgetBytes = size_t(bytes);
     return PLTPT_OK;
 }
-/* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 = the default (two), up to the lanes built in (four). */
+/* Frames kept in flight by pltpt_render_accumulate: 1 = strictly one after the other, 0 = the default (four, all lanes built in). */
 extern "C" int pltpt_set_frame_overlap(PltptHandle h, int frames) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (frames < 0 || frames > PltptContext::kLanes) return fail(PLTPT_ERR_INVALID_ARGUMENT, "frame overlap out of range (0 = default, 1 .. lanes built in)");
     h->frameOverlap = frames == 0 ? PltptContext::kDefaultOverlap : frames;
+    return PLTPT_OK;
+}
+extern "C" int pltpt_set_bvh_update_mode(PltptHandle h, int mode) {
+    if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode != PLTPT_BVH_UPDATE_REBUILD && mode != PLTPT_BVH_UPDATE_REFIT) return fail(PLTPT_ERR_INVALID_ARGUMENT, "unknown BVH update mode");
+    h->bvhUpdateMode = mode;
     return PLTPT_OK;
 }
 extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {
@@ -123,11 +129,11 @@ extern "C" int pltpt_set_profiling(PltptHandle h, int enable) {
 extern "C" int pltpt_reset_stats(PltptHandle h) {
     if (!h) return fail(PLTPT_ERR_INVALID_ARGUMENT, "null argument");
     if (int r = syncFrameStats(h)) return r;
-    const double b = h->stats.bvhBuildMs, sahCost = h->stats.bvhSahCost;
+    const double b = h->stats.bvhBuildMs, sahCost = h->stats.bvhSahCost, refitMs = h->stats.bvhRefitMs;
     const uint64_t n = h->stats.bvhNodes, l = h->stats.bvhLeafTriangles, t = h->stats.triangleCount, ov = h->stats.traversalStackOverflows;
     h->stats = PltptStats{};
     h->stats.traversalStackOverflows = ov;
-    h->stats.bvhSahCost = sahCost;
+    h->stats.bvhSahCost = sahCost; h->stats.bvhRefitMs = refitMs;
     h->stats.bvhBuildMs = b; h->stats.bvhNodes = n; h->stats.bvhLeafTriangles = l; h->stats.triangleCount = t;
     return PLTPT_OK;
 }
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(256) k_accum_add_peers(double* __restrict__ ds
 int renderAccumulateRows(PltptHandle h, uint32_t firstFrame, uint32_t frameStep, uint32_t frameCount, const PltptCameraData* cam, uint32_t w, uint32_t hgt, uint32_t rowBegin,
                          uint32_t rowEnd, double* accum, cudaStream_t user) {
     if (rowBegin >= rowEnd || rowEnd > hgt || (rowBegin & 3u)) return fail(PLTPT_ERR_INVALID_ARGUMENT, "row range must be non-empty, inside the image and start on a multiple of 4");
-    // Two frames in flight (context.h "Frame lanes") unless per-kernel timers are on (they need one stream) or there is one frame.
+    // frameOverlap frames in flight (context.h "Frame lanes") unless per-kernel timers are on (they need one stream) or there are fewer frames.
     const int lanes = h->profiling ? 1 : int(std::min<uint32_t>(frameCount, uint32_t(h->frameOverlap)));
     const size_t accumBytes = size_t(w) * hgt * 4 * sizeof(double);
     if (lanes > 1) {

@@ -345,7 +345,7 @@ PLT_D uint32_t quantHi(float origin, float s, float v) {
 // other queue under counts[(level + 1) % 3]; counts[(level + 2) % 3] is re-zeroed for the level after that (nobody reads it meanwhile).
 __global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ queues, uint32_t queueStride, uint32_t level, uint32_t* __restrict__ levelCounts,
                                                   uint32_t* __restrict__ counters /*0 nodes,1 tris,2 max children seen*/, TreeView tv, SahTables sah, const BvhTri* __restrict__ srcTris,
-                                                  BvhNode* __restrict__ outNodes, BvhTri* __restrict__ outTris, uint32_t rootIsLeaf) {
+                                                  BvhNode* __restrict__ outNodes, BvhTri* __restrict__ outTris, uint32_t* __restrict__ outParent, uint32_t rootIsLeaf) {
     const CollapseItem* items = queues + size_t(level & 1u) * queueStride;
     CollapseItem* nextItems = queues + size_t((level + 1u) & 1u) * queueStride;
     const uint32_t nItems = levelCounts[level % 3u];
@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ que
             imask |= 1u << i;
             node.meta[i] = uint8_t(0x20u | (24u + uint32_t(i)));
             nextItems[nextBase + innerSeen] = CollapseItem{c[i], childBase + innerSeen};
+            outParent[childBase + innerSeen] = item.wide;  // for the bottom-up refit (k_refit_nodes)
             ++innerSeen;
         } else {
             node.meta[i] = uint8_t((k << 5) | triOff);
@@ -431,6 +432,77 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseItem* __restrict__ que
     node.imask = uint8_t(imask);
     outNodes[item.wide] = node;
   }
+}
+
+// ---- refit (pltpt_update_transforms in PLTPT_BVH_UPDATE_REFIT mode; the reference's UpdateMode::Refit, Scene.cpp:3642-3647,3720) ----
+// The tree keeps its topology: every leaf triangle is re-derived from its (instance, primitive) with the new matrices, then the node
+// boxes are re-fitted bottom-up -- a thread starts at every node without inner children and climbs while it is the last of a node's
+// inner children to arrive -- and the child boxes re-quantised on the node's new grid with the builder's conservative rounding.
+__global__ void k_refit_tris(DevScene sc, BvhTri* __restrict__ tris) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= sc.triCount) return;
+    const uint32_t inst = tris[g].instanceID, prim = tris[g].primitiveIndex;
+    uint32_t idx[3];
+    fetchIndices(sc, inst, prim, idx);
+    const float* M = sc.world + 16 * size_t(sc.instances[inst].globalMatrixID);
+    const float3 v0 = worldPoint(M, sc.vertices[idx[0]].position), v1 = worldPoint(M, sc.vertices[idx[1]].position), v2 = worldPoint(M, sc.vertices[idx[2]].position);
+    BvhTri& t = tris[g];
+    t.v0x = v0.x; t.v0y = v0.y; t.v0z = v0.z;
+    t.v1x = v1.x; t.v1y = v1.y; t.v1z = v1.z;
+    t.v2x = v2.x; t.v2y = v2.y; t.v2z = v2.z;
+}
+__global__ void __launch_bounds__(128) k_refit_nodes(uint32_t nNodes, BvhNode* __restrict__ nodes, const BvhTri* __restrict__ tris, const uint32_t* __restrict__ parent,
+                                                     uint32_t* __restrict__ arrivals, float4* boxLo, float4* boxHi) {
+    uint32_t ni = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ni >= nNodes || nodes[ni].imask != 0) return;
+    for (;;) {
+        BvhNode node = nodes[ni];
+        const uint32_t imask = node.imask;
+        float3 clo[8], chi[8];
+        float3 nlo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), nhi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        uint32_t used = 0;
+        for (int i = 0; i < 8; ++i) {
+            const bool inner = (imask >> i) & 1u;
+            const uint32_t meta = node.meta[i];
+            if (!inner && meta == 0) continue;
+            used |= 1u << i;
+            if (inner) {
+                const uint32_t ci = node.childBase + __popc(imask & ((1u << i) - 1u));
+                const float4 l = __ldcg(boxLo + ci), h = __ldcg(boxHi + ci);  // written by another thread of this launch: read through L2
+                clo[i] = mk3(l.x, l.y, l.z); chi[i] = mk3(h.x, h.y, h.z);
+            } else {
+                float3 lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+                const uint32_t cnt = meta >> 5, off = meta & 31u;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const BvhTri t = tris[node.triBase + off + k];
+                    const float3 v0 = mk3(t.v0x, t.v0y, t.v0z), v1 = mk3(t.v1x, t.v1y, t.v1z), v2 = mk3(t.v2x, t.v2y, t.v2z);
+                    lo = vmin(lo, vmin(v0, vmin(v1, v2))); hi = vmax(hi, vmax(v0, vmax(v1, v2)));
+                }
+                clo[i] = lo; chi[i] = hi;
+            }
+            nlo = vmin(nlo, clo[i]); nhi = vmax(nhi, chi[i]);
+        }
+        node.px = nlo.x; node.py = nlo.y; node.pz = nlo.z;
+        const uint32_t ex = gridExponent(nlo.x, nhi.x), ey = gridExponent(nlo.y, nhi.y), ez = gridExponent(nlo.z, nhi.z);
+        node.ex = uint8_t(ex); node.ey = uint8_t(ey); node.ez = uint8_t(ez);
+        const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+        for (int i = 0; i < 8; ++i) {
+            if (!((used >> i) & 1u)) continue;
+            node.qlox[i] = uint8_t(quantLo(nlo.x, sx, clo[i].x)); node.qhix[i] = uint8_t(quantHi(nlo.x, sx, chi[i].x));
+            node.qloy[i] = uint8_t(quantLo(nlo.y, sy, clo[i].y)); node.qhiy[i] = uint8_t(quantHi(nlo.y, sy, chi[i].y));
+            node.qloz[i] = uint8_t(quantLo(nlo.z, sz, clo[i].z)); node.qhiz[i] = uint8_t(quantHi(nlo.z, sz, chi[i].z));
+        }
+        nodes[ni] = node;
+        if (ni == 0) return;
+        __stcg(boxLo + ni, mk4(nlo.x, nlo.y, nlo.z, 0.f));
+        __stcg(boxHi + ni, mk4(nhi.x, nhi.y, nhi.z, 0.f));
+        __threadfence();
+        const uint32_t p = parent[ni];
+        const uint32_t need = uint32_t(__popc(uint32_t(nodes[p].imask)));
+        if (atomicAdd(arrivals + p, 1u) + 1u < need) return;
+        __threadfence();
+        ni = p;
+    }
 }
 
 template <bool ANY, bool kNearest>
@@ -495,6 +567,7 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
     PLT_CUDA(c->bvhTris.ensure(size_t(n) * sizeof(BvhTri)));
     // a wide node has >= 2 children unless it is the root of a <=3-triangle scene, so #nodes <= max(1, n - 1)
     PLT_CUDA(c->bvhNodes.ensure(size_t(n) * sizeof(BvhNode)));
+    PLT_CUDA(c->bvhParent.ensure(size_t(n) * 4));
 
     uint32_t* miscU = misc.as<uint32_t>();
     const uint32_t initMisc[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, /*counters*/ 1u, 0u, 0u, /*overflow*/ 0u, /*query cursor*/ 0u, /*level counts*/ 0, 0, 0, 0, 0};
@@ -537,7 +610,7 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
         // no internal binary node exists: the root wide node gets the single triangle as its only leaf slot
         const CollapseItem root{0u | kLeafBit, 0u};
         PLT_CUDA(cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, s));
-        k_collapse<<<1, 128, 0, s>>>(q0, n, 0u, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 1u);
+        k_collapse<<<1, 128, 0, s>>>(q0, n, 0u, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), c->bvhParent.as<uint32_t>(), 1u);
         c->stats.kernelLaunches++;
         levels = 1;
     } else {
@@ -600,7 +673,7 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
         const uint32_t grid = uint32_t(sms) * 8;
         for (bool more = true; more;) {
             for (int k = 0; k < 16; ++k, ++levels)
-                k_collapse<<<grid, 128, 0, s>>>(q0, n, levels, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), 0u);
+                k_collapse<<<grid, 128, 0, s>>>(q0, n, levels, levelCounts, counters, tv, sah, srcTris.as<BvhTri>(), c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), c->bvhParent.as<uint32_t>(), 0u);
             c->stats.kernelLaunches += 16;
             uint32_t pending = 0;
             PLT_CUDA(cudaMemcpyAsync(&pending, levelCounts + levels % 3u, 4, cudaMemcpyDeviceToHost, s));
@@ -634,6 +707,31 @@ int buildBvh(PltptContext* c, cudaStream_t s) {
     sc.bvhTris = c->bvhTris.as<BvhTri>();
     // build scratch is only needed again on the next set_scene
     for (int i = 0; i < 7; ++i) c->bvhScratch[i].release();
+    return PLTPT_OK;
+}
+
+// Refit of the BVH built by buildBvh after the world matrices changed (same topology, new boxes).
+int refitBvh(PltptContext* c, cudaStream_t s) {
+    DevScene& sc = c->scene;
+    const uint32_t n = sc.triCount, nNodes = uint32_t(c->stats.bvhNodes);
+    if (!sc.bvhNodes || !c->bvhParent.p || nNodes == 0) { setError("refit without a built BVH"); return PLTPT_ERR_NO_SCENE; }
+    DevBuf& scratch = c->bvhScratch[0];  // arrivals (4 B) + two float4 boxes per node
+    PLT_CUDA(scratch.ensure(size_t(nNodes) * (4 + 32) + 32));
+    float4* boxLo = scratch.as<float4>();
+    float4* boxHi = boxLo + nNodes;
+    uint32_t* arrivals = reinterpret_cast<uint32_t*>(boxHi + nNodes);
+    cudaEventRecord(c->evA, s);
+    PLT_CUDA(cudaMemsetAsync(arrivals, 0, size_t(nNodes) * 4, s));
+    k_refit_tris<<<blocksFor(n, 256), 256, 0, s>>>(sc, c->bvhTris.as<BvhTri>());
+    k_refit_nodes<<<blocksFor(nNodes, 128), 128, 0, s>>>(nNodes, c->bvhNodes.as<BvhNode>(), c->bvhTris.as<BvhTri>(), c->bvhParent.as<uint32_t>(), arrivals, boxLo, boxHi);
+    cudaEventRecord(c->evB, s);
+    PLT_CUDA(cudaStreamSynchronize(s));
+    PLT_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->evA, c->evB);
+    c->stats.bvhRefitMs = ms;
+    c->stats.kernelLaunches += 2;
+    scratch.release();
     return PLTPT_OK;
 }
 

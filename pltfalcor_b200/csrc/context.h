@@ -76,7 +76,7 @@ struct DevBuf {
 #define PLT_LANES 4   // frame lanes built in (streams + private work buffers, allocated when first used); pltpt_set_frame_overlap picks how many run
 #endif
 #ifndef PLT_DEFAULT_OVERLAP
-#define PLT_DEFAULT_OVERLAP 2
+#define PLT_DEFAULT_OVERLAP 4   // Cornell 1080p: 389 / 480 / 501 / 505 M paths/s with 1 / 2 / 3 / 4 frames in flight (profiles/r2w_overlap.jsonl)
 #endif
 struct PltptContext {
     int device = 0;
@@ -85,7 +85,8 @@ struct PltptContext {
     plt::DevScene scene{};
     // owned device copies
     plt::DevBuf vertices, indexData, instances, meshes, world, worldIT, materials, profiles, lights, etris, eflux, activeTris, perMeshOffset, alias, instTriOffset;
-    plt::DevBuf bvhNodes, bvhTris, bvhScratch[8];
+    plt::DevBuf bvhNodes, bvhTris, bvhParent, bvhScratch[8];  // bvhParent: parent wide node of every wide node (bottom-up refit)
+    int bvhUpdateMode = 0;                    // PLTPT_BVH_UPDATE_REBUILD / _REFIT (pltpt_set_bvh_update_mode)
     plt::DevBuf envTexels, envImportance;
     plt::DevBuf texBlob, texDescs, texSamplers, materialBlobs;
     // host mirrors needed by the host logic
@@ -99,8 +100,9 @@ struct PltptContext {
     int traceMode = 0;                         // pltpt_set_trace_mode: which traversal driver the ray-query entry points use
     uint32_t mneeGrid = 0;                     // cooperative grid of k_mnee_walk on this handle's device (resident CTAs), 0 = not queried yet
     // Frame lanes: frames are independent (every random number derives from (pixel, frameCount), pltpt_sample.rt.slang:154), so
-    // pltpt_render_accumulate keeps two frames in flight on two streams, each with its own work buffers, counters and timers: the
-    // under-filled late bounces of one frame overlap the wide early bounces of the other.  Lane 0 runs on the caller's stream.
+    // pltpt_render_accumulate keeps several frames in flight (frameOverlap, default four), each on its own stream with its own work
+    // buffers, counters and timers: the under-filled late bounces of one frame overlap the wide early bounces of the others.  Lane 0
+    // runs on the caller's stream.  A frame rendered on its own (pltpt_render_frame) is split over lanes 0 and 1 (renderFrameSplit).
     static constexpr uint32_t kTimerRing = 256;
     static constexpr int kLanes = PLT_LANES;
     struct Lane {
@@ -173,6 +175,7 @@ int cudaFail(cudaError_t e, const char* what);
 
 // bvh.cu
 int buildBvh(PltptContext* c, cudaStream_t s);
+int refitBvh(PltptContext* c, cudaStream_t s);
 int traceClosest(PltptContext* c, uint32_t n, const float* rays, uint32_t* hits, float* hitT, cudaStream_t s);
 int traceAny(PltptContext* c, uint32_t n, const float* rays, uint32_t* occluded, cudaStream_t s);
 // integrator.cu

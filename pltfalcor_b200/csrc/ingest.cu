@@ -384,7 +384,7 @@ extern "C" int pltpt_build_light_collection(PltptHandle h) {
 }
 
 // Animated instance transforms (the reference refits / rebuilds its TLAS on demand, Source/Falcor/Scene/Scene.cpp:3624-3700; geometry
-// here lives in ONE world-space BVH, and a full GPU rebuild of 10 M triangles takes ~30 ms, so "refit" is a rebuild): new world and
+// here lives in ONE world-space BVH; pltpt_set_bvh_update_mode picks a full GPU rebuild or a bottom-up refit of it): new world and
 // inverse-transpose matrices for the scene held by `h`, BVH rebuilt, and -- when the library built the light collection itself --
 // the emissive triangles re-derived.  A light collection supplied by the caller is the caller's to refresh (pltpt_set_scene).
 extern "C" int pltpt_update_transforms(PltptHandle h, const float* worldMatrices, const float* inverseTransposeWorldMatrices, uint32_t matrixCount, uint32_t pointersAreDevice) {
@@ -400,7 +400,7 @@ extern "C" int pltpt_update_transforms(PltptHandle h, const float* worldMatrices
     const cudaMemcpyKind kind = pointersAreDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     PLT_CUDA(cudaMemcpy(h->world.p, worldMatrices, size_t(matrixCount) * 64, kind));
     PLT_CUDA(cudaMemcpy(h->worldIT.p, inverseTransposeWorldMatrices, size_t(matrixCount) * 64, kind));
-    if (int r = buildBvh(h, 0)) return r;
+    if (int r = h->bvhUpdateMode == PLTPT_BVH_UPDATE_REFIT ? refitBvh(h, 0) : buildBvh(h, 0)) return r;
     if (h->ownLightCollection) return pltpt_build_light_collection(h);
     return PLTPT_OK;
 }

@@ -233,7 +233,11 @@ public:
     bool useEmissiveLights() const { return mDesc.emissiveTriangleCount > 0; }  // Scene.h: render settings && light collection non-empty
     bool useAnalyticLights() const { return mDesc.lightCount > 0; }
     bool useEnvLight() const { return mHasEnvMap; }
+    enum class UpdateMode { Rebuild, Refit };  // Scene/Scene.h:169-173
+    void setTlasUpdateMode(UpdateMode mode) { mTlasUpdateMode = mode; }  // Scene.h:935
+    UpdateMode getTlasUpdateMode() { return mTlasUpdateMode; }           // Scene.h:939
 private:
+    UpdateMode mTlasUpdateMode = UpdateMode::Rebuild;                    // Scene.h:1371
     PltptSceneDesc mDesc;
     Camera::SharedPtr mpCamera;
     bool mHasEnvMap;

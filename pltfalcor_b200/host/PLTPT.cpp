@@ -143,6 +143,8 @@ void PLTPT::onSceneUpdates(RenderContext* pRenderContext, Scene::UpdateFlags sce
 #else
     const PltptSceneDesc& desc = mpScene->getPltptSceneDesc();
 #endif
+    // the scene's TLAS update mode (Scene.h:935-939) decides between a rebuild and a refit of the library's BVH
+    check(pltpt_set_bvh_update_mode(mHandle, mpScene->getTlasUpdateMode() == Scene::UpdateMode::Refit ? PLTPT_BVH_UPDATE_REFIT : PLTPT_BVH_UPDATE_REBUILD), "pltpt_set_bvh_update_mode");
     check(pltpt_update_transforms(mHandle, desc.worldMatrices, desc.inverseTransposeWorldMatrices, desc.matrixCount, desc.pointersAreDevice), "pltpt_update_transforms");
 }
 

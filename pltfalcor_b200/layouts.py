@@ -199,5 +199,5 @@ class PltptStats(C.Structure):
         ("totalPathVertices", C.c_uint64), ("totalReplaySteps", C.c_uint64), ("totalBsdfEvals", C.c_uint64),
         ("traversalNodesVisited", C.c_uint64), ("traversalTrianglesTested", C.c_uint64), ("droppedConnections", C.c_uint64),
         ("kernelMs", C.c_double * KERNEL_CLASS_COUNT), ("kernelLaunchCount", C.c_uint64 * KERNEL_CLASS_COUNT), ("unwindJobSteps", C.c_uint64), ("mneeWalks", C.c_uint64),
-        ("bvhSahCost", C.c_double),
+        ("bvhSahCost", C.c_double), ("bvhRefitMs", C.c_double),
     ]

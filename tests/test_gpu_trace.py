@@ -180,9 +180,11 @@ def binding_scene(binding, buffers):
     return h
 
 
-def test_updated_transforms_equal_a_scene_built_with_them(torch_cuda, oracle):
-    """pltpt_update_transforms (animated instances; the reference refits its TLAS, Scene.cpp:3624-3700): after moving two meshes the
-    BVH answers exactly like the BVH of a scene created with the moved meshes, and the library-built light collection follows."""
+@pytest.mark.parametrize("mode", ["rebuild", "refit"])
+def test_updated_transforms_equal_a_scene_built_with_them(torch_cuda, oracle, mode):
+    """pltpt_update_transforms (animated instances; the reference rebuilds or refits its TLAS, Scene.cpp:3624-3700, by the scene's
+    UpdateMode, Scene.h:169-173): after moving two meshes the BVH -- rebuilt, or refitted bottom-up with its topology kept -- answers
+    exactly like the BVH of a scene created with the moved meshes, and the library-built light collection follows."""
     torch = torch_cuda
     from pltfalcor_b200 import binding, scene
     buffers, cam = scene.cornell_box()
@@ -195,7 +197,9 @@ def test_updated_transforms_equal_a_scene_built_with_them(torch_cuda, oracle):
     p, q = binding.Pltpt(maxBounces=4), binding.Pltpt(maxBounces=4)
     p.set_scene(buffers)
     p.build_light_collection()
+    p.set_bvh_update_mode(1 if mode == "refit" else 0)
     p.update_transforms(moved, moved_it)
+    assert (p.stats()["bvhRefitMs"] > 0) == (mode == "refit")
     q.set_scene(target)
     q.build_light_collection()
     hp, tp, op = _trace_gpu(torch, p, rays)
@@ -213,3 +217,36 @@ def test_updated_transforms_equal_a_scene_built_with_them(torch_cuda, oracle):
     torch.cuda.synchronize()
     assert torch.equal(img[0], img[1])
     p.close(); q.close()
+
+
+def test_refit_of_a_large_scene_keeps_hits_exact(torch_cuda, oracle):
+    """Refit (PLTPT_BVH_UPDATE_REFIT) on a scene whose tree is deep: every instance of the city moved by its own offset, twice in a row
+    (the second refit starts from refitted boxes); closest hits, hit distances and occlusion answers equal the brute-force oracle's on
+    the moved scene bit for bit through every traversal driver, and the traversal stack never overflows."""
+    torch = torch_cuda
+    from pltfalcor_b200 import binding, scene
+    buffers, cam = scene.city_scene(40_000)
+    rng = np.random.default_rng(11)
+    p = binding.Pltpt(maxBounces=4)
+    p.set_scene(buffers)
+    build_ms = p.stats()["bvhBuildMs"]
+    p.set_bvh_update_mode(1)
+    moved = np.array(buffers.arrays["worldMatrices"], copy=True)
+    for step in range(2):
+        moved[:, :3, 3] += rng.uniform(-0.4, 0.4, (len(moved), 3)).astype(np.float32)
+        moved_it = np.stack([np.linalg.inv(m.astype(np.float64)).T for m in moved]).astype(np.float32)
+        p.update_transforms(moved, moved_it)
+    target = scene.SceneBuffers(dict(buffers.arrays, worldMatrices=moved, inverseTransposeWorldMatrices=moved_it), buffers.scalars)
+    rays = np.concatenate([parity.camera_rays(cam, 96, 54), parity.random_rays(rng, target, 3000)])
+    osc = oracle.OracleScene(target)
+    ref_hits, ref_t = osc.trace_closest(rays, brute=True)
+    ref_occ = osc.trace_any(rays, brute=True)
+    assert (ref_hits[:, 0] != 0xFFFFFFFF).mean() > 0.2
+    for mode in sorted(MODES):
+        h, t, o = _trace_gpu(torch, p, rays, MODES[mode])
+        _assert_bit_exact(f"city-refit/{mode}", osc, rays, h, t, ref_hits, ref_t)
+        assert np.array_equal(o, ref_occ)
+    s = p.stats()
+    assert s["traversalStackOverflows"] == 0 and 0 < s["bvhRefitMs"]
+    print(f"city 40k: build {build_ms:.2f} ms, refit {s['bvhRefitMs']:.3f} ms")
+    p.close()
