@@ -19,7 +19,7 @@ import numpy as np
 from . import layouts as L
 
 f32 = np.float32
-_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "spd_tables.json")
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "spd_tables.json")  # input data of the harness (measured tables), not a test fixture
 
 
 # ----------------------------------------------------------------------------------------------- spectral tables
@@ -47,7 +47,7 @@ _tables_cache = None
 
 
 def bundled_tables():
-    """The small set of reference tables bundled as a fixture (tools/make_golden_tables.py)."""
+    """The small set of measured IOR / emission tables bundled with the harness (pltfalcor_b200/data, written by tools/make_golden_tables.py)."""
     global _tables_cache
     if _tables_cache is None:
         with open(_GOLDEN) as f:

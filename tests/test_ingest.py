@@ -9,7 +9,7 @@ import pytest
 
 from pltfalcor_b200 import layouts as L
 
-GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "spd_tables.json")
+GOLDEN = os.path.join(os.path.dirname(__file__), "..", "pltfalcor_b200", "data", "spd_tables.json")
 
 
 @pytest.fixture(scope="module")

@@ -9,7 +9,7 @@ import os
 import sys
 
 REF = "/root/reference/Source/Tables"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "spd_tables.json")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pltfalcor_b200", "data", "spd_tables.json")
 
 IOR = ["Au", "Ag", "Cu", "Al", "Cr"]
 EMISSION = [
