@@ -50,7 +50,7 @@ CONFIGS = {
     "cornell_closed": ("cornell_box_closed", 1920, 1080, 8, "closed_cornell_box_albedo_0.8_1920x1080_depth8 (deep-path variant of configs[1])", (480, 270)),
     "grating": ("grating_sphere_scene", 1920, 1080, 8, "grated_conductor_plane_dielectric_sphere_mnee_1920x1080_depth8 (BASELINE configs[2])", (480, 270)),
     "layered": ("layered_stress_scene", 3840, 2160, 4, "layered_material_stress_hwss4_3840x2160_depth8 (BASELINE configs[3])", (480, 270)),
-    "city": ("city_scene", 3840, 2160, 2, "synthetic_city_10M_triangles_mixed_plt_materials_3840x2160_depth8 (BASELINE configs[4])", (240, 136)),
+    "city": ("city_scene", 3840, 2160, 4, "synthetic_city_10M_triangles_mixed_plt_materials_3840x2160_depth8 (BASELINE configs[4])", (240, 136)),
 }
 # SURVEY §8(d) algorithmic bytes of the rendering path
 F_VERTEX_FETCH = 396   # indices 12 + 3 vertices 96 + instance 32 + matrices 128 + material 128
