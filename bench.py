@@ -330,7 +330,9 @@ def main():
     step_frames = F * (world if args.scaling == "weak" else 1)   # frames (over all ranks) that make up one step's image
 
     # ---- device-resident timing -------------------------------------------------------------------------------------
-    render(*share(0, max(2, W) * (world if args.partition == "sample" else 1)), accum)  # warm-up frames (also sizes the work buffers)
+    # W warm-up steps of F frames per rank (they also size the work buffers of every frame lane: a lane first used inside the timed region
+    # would put its cudaMalloc there)
+    render(*share(0, max(W * F, 4) * (world if args.partition == "sample" else 1)), accum)
     accum.zero_()
     if world > 1:
         dist.reduce(accum, dst=0)  # warm-up of the NCCL communicator

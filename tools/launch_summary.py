@@ -18,6 +18,8 @@ for r in rows[1:]:
     per[n].append(v)
 build = ("k_world_tris", "k_morton", "k_radix_tree", "k_fit", "k_collapse", "k_sah_costs", "k_ploc_init", "k_ploc_nearest", "k_ploc_merge", "k_ploc_compact")
 tot = sum(a[1] for n, a in agg.items() if n.startswith("k_") and n not in build)
+if len(sys.argv) <= 2 and "k_raygen" in agg:
+    frames = agg["k_raygen"][0]  # one k_raygen launch per frame (untiled frames)
 for n, a in agg.items():
     print(f"{n[:60]:60s} launches {a[0]:4d}  ms/frame {a[1] / 1e6 / frames:9.3f}  share {a[1] / tot:.3f}")
 for n in ("k_trace", "k_shade", "k_connect", "k_unwind_step"):
