@@ -199,4 +199,217 @@ static void ref_compare_more(int N, Rnd& r) {
         { Cmp c(std::string(kKindNames[kind]) + ".eval"); c.add(b, rb); }
         { Cmp c(std::string(kKindNames[kind]) + ".pdf"); float q1 = 0.f; const orc::float3 toLight = sd.fromLocal(r.dirUp()); REF_DISPATCH_R(p, q1, pdf(rsd, R(toLight), wavelength)); c.add(p.o.pdf(sd, toLight, wavelength), q1); }
     }
+    // ---- LightHelpers.slang: the six analytic light samplers behind sampleLight() (LightData.slang is transpiled too: same struct layout)
+    {
+        static orc::Scene osc;
+        osc.profiles = table;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        const char* kLightNames[6] = {"Point", "Directional", "Distant", "Rect", "Disc", "Sphere"};
+        for (int i = 0; i < N; ++i) {
+            PltptLightData L{};
+            ref::LightData Lr;
+            L.type = uint32_t(i % 6);
+            const orc::float3 pos = r.f3(-3.f, 3.f), dir = r.dir();
+            for (int k = 0; k < 3; ++k) { L.posW[k] = pos[k]; L.dirW[k] = dir[k]; }
+            L.openingAngle = r.u() < .4f ? orc::kPi : r.range(0.2f, 1.5f);
+            L.cosOpeningAngle = std::cos(L.openingAngle);
+            L.penumbraAngle = r.u() < .5f ? 0.f : r.range(0.01f, 0.3f);
+            L.cosSubtendedAngle = r.u() < .3f ? 0.9999893f : std::cos(r.range(0.001f, 0.4f));
+            L.intensitySpectrumId = 4u;
+            L.surfaceArea = r.range(0.05f, 8.f);
+            // local-to-world: rotation (random orthonormal frame) * anisotropic scale + translation; IT = inverse transpose of it
+            const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex);
+            const orc::float3 sc = r.f3(0.2f, 2.f);
+            const orc::float3 cols[3] = {ex * sc.x, ey * sc.y, ez * sc.z}, colsIT[3] = {ex / sc.x, ey / sc.y, ez / sc.z};
+            for (int row = 0; row < 3; ++row) {
+                for (int c = 0; c < 3; ++c) { L.transMat[4 * row + c] = cols[c][row]; L.transMatIT[4 * row + c] = colsIT[c][row]; }
+                L.transMat[4 * row + 3] = pos[row]; L.transMatIT[4 * row + 3] = 0.f;
+            }
+            L.transMat[15] = 1.f; L.transMatIT[15] = 1.f;
+            Lr.posW = R(pos); Lr.type = L.type; Lr.dirW = R(dir); Lr.openingAngle = L.openingAngle; Lr.cosOpeningAngle = L.cosOpeningAngle; Lr.cosSubtendedAngle = L.cosSubtendedAngle;
+            Lr.penumbraAngle = L.penumbraAngle; Lr.intensitySpectrumId = L.intensitySpectrumId; Lr.surfaceArea = L.surfaceArea;
+            for (int row = 0; row < 4; ++row) for (int c = 0; c < 4; ++c) { Lr.transMat[row][c] = L.transMat[4 * row + c]; Lr.transMatIT[row][c] = L.transMatIT[4 * row + c]; }
+            const orc::float3 shadingPos = r.f3(-4.f, 4.f);
+            const float hero = r.range(380.f, 720.f);
+            const bool imp = r.u() < .5f;
+            orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 17u); RefSG g1{g0};
+            orc::Integrator::AnalyticLightSample a;
+            ref::AnalyticLightSample b;
+            const bool v0 = integ.sampleAnalyticLight(shadingPos, L, g0, hero, imp, a);
+            const bool v1 = ref::sampleLight(R(shadingPos), Lr, g1, hero, imp, b);
+            Cmp c(std::string("LightHelpers.sample") + kLightNames[L.type]);
+            c.add(v0, v1); c.add(g0.next(), g1.next());
+            if (v0 && v1) { c.add(a.posW, b.posW); c.add(a.normalW, b.normalW); c.add(a.dir, b.dir); c.add(a.distance, b.distance); c.add(a.Li, b.Li); c.add(a.wavelengths, b.wavelengths); c.add(a.pdf, b.pdf); }
+        }
+    }
+    // ---- LightSampling.slangh (the pass's NEE light sampling) with LightsSamplingUtils.slang, ShadowRays.slangh computeNewRayOrigin and
+    // GeometryHelpers.slang computeRayOrigin: light-type selection under every combination of the three switches, and whole analytic-light
+    // samples (light choice, radiance scaling, beam sourcing, ray origin, reflection / transmission filter).  The environment-map and
+    // emissive-triangle samplers need the texture system / the light collection and stand in as "no sample" on the reference side; the
+    // oracle side is never asked for one (those types are switched off in the whole-sample runs).
+    {
+        static orc::Scene osc;
+        osc.profiles = table;
+        static PltptLightData lights[4];
+        static ref::LightData rlights[4];
+        static const float oneTexel[4] = {1.f, 1.f, 1.f, 1.f};
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};  // every field the light sampling reads is set below
+        for (int i = 0; i < N; ++i) {
+            { Cmp c("GeometryHelpers.computeRayOrigin");
+              const float scale = r.u() < .3f ? 0.05f : (r.u() < .5f ? 3.f : 500.f);
+              const orc::float3 pos = r.f3(-scale, scale), nrm = r.dir();
+              c.add(orc::computeRayOrigin(pos, nrm), ref::computeRayOrigin(R(pos), R(nrm))); }
+            const orc::ShadingData sd = randomShadingData(r);
+            ref::ShadingData rsd = R(sd);
+            { Cmp c("ShadowRays.computeNewRayOrigin"); const orc::float3 d = r.dir(); c.add(orc::Integrator::computeNewRayOrigin(sd, d), ref::computeNewRayOrigin(rsd, R(d))); }
+            // light-type selection: the oracle derives its switches from options AND scene content, like PLTPT.cpp:235-243
+            const bool env = r.u() < .5f, emi = r.u() < .5f, ana = r.u() < .5f;
+            integ.opt.useEnvLights = 1; integ.opt.useEmissiveLights = 1; integ.opt.useAnalyticLights = 1;
+            osc.env.texels = env ? oneTexel : nullptr;
+            osc.d.emissiveTriangleCount = emi ? 1u : 0u;
+            osc.d.lightCount = ana ? 1u : 0u;
+            ref::kUseEnvLight = env; ref::kUseEmissiveLights = emi; ref::kUseAnalyticLights = ana;
+            { Cmp c("LightSampling.selectLightType"); orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 19u); RefSG g1{g0};
+              uint32_t t0 = 7u; ref::uint t1 = 7u; float p0 = -1.f, p1 = -1.f;
+              const bool v0 = integ.selectLightType(t0, p0, g0), v1 = ref::selectLightType(t1, p1, g1);
+              c.add(v0, v1); c.add(t0, uint32_t(t1)); if (v0 && v1) c.add(p0, p1); c.add(g0.next(), g1.next()); }
+            // whole samples: analytic lights only
+            osc.env.texels = nullptr; osc.d.emissiveTriangleCount = 0;
+            ref::kUseEnvLight = false; ref::kUseEmissiveLights = false; ref::kUseAnalyticLights = true;
+            const uint32_t count = 1u + uint32_t(r.u() * 3.999f);
+            for (uint32_t k = 0; k < count; ++k) {
+                PltptLightData& L = lights[k];
+                L = PltptLightData{};
+                L.type = uint32_t(r.u() * 5.999f);
+                const orc::float3 pos = r.f3(-3.f, 3.f), dir = r.dir();
+                for (int a = 0; a < 3; ++a) { L.posW[a] = pos[a]; L.dirW[a] = dir[a]; }
+                L.openingAngle = r.u() < .4f ? orc::kPi : r.range(0.2f, 1.5f);
+                L.cosOpeningAngle = std::cos(L.openingAngle);
+                L.penumbraAngle = r.u() < .5f ? 0.f : r.range(0.01f, 0.3f);
+                L.cosSubtendedAngle = r.u() < .3f ? 0.9999893f : std::cos(r.range(0.001f, 0.4f));
+                L.intensitySpectrumId = 4u;
+                L.surfaceArea = r.range(0.05f, 8.f);
+                const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex), sc = r.f3(0.2f, 2.f);
+                const orc::float3 cols[3] = {ex * sc.x, ey * sc.y, ez * sc.z}, colsIT[3] = {ex / sc.x, ey / sc.y, ez / sc.z};
+                for (int row = 0; row < 3; ++row) {
+                    for (int cc = 0; cc < 3; ++cc) { L.transMat[4 * row + cc] = cols[cc][row]; L.transMatIT[4 * row + cc] = colsIT[cc][row]; }
+                    L.transMat[4 * row + 3] = pos[row];
+                }
+                L.transMat[15] = 1.f; L.transMatIT[15] = 1.f;
+                ref::LightData& Lr = rlights[k];
+                Lr = ref::LightData();
+                Lr.posW = R(pos); Lr.type = L.type; Lr.dirW = R(dir); Lr.openingAngle = L.openingAngle; Lr.cosOpeningAngle = L.cosOpeningAngle; Lr.cosSubtendedAngle = L.cosSubtendedAngle;
+                Lr.penumbraAngle = L.penumbraAngle; Lr.intensitySpectrumId = L.intensitySpectrumId; Lr.surfaceArea = L.surfaceArea;
+                for (int row = 0; row < 4; ++row) for (int cc = 0; cc < 4; ++cc) { Lr.transMat[row][cc] = L.transMat[4 * row + cc]; Lr.transMatIT[row][cc] = L.transMatIT[4 * row + cc]; }
+            }
+            osc.d.lights = lights; osc.d.lightCount = count;
+            ref::gScene.lights = rlights; ref::gScene.lightCount = count;
+            const float area = r.range(0.01f, 4.f), omega = r.range(0.001f, 0.1f);
+            integ.opt.sourcingAreaFromEmissiveGeometry = area; integ.opt.sourcingMaxBeamOmega = omega;
+            ref::kSourcingAreaFromEmissiveGeometry = area; ref::kSourcingMaxBeamOmega = omega;
+            const bool perTile = r.u() < .5f, reflOk = r.u() < .8f, transOk = r.u() < .8f, imp = r.u() < .5f;
+            integ.opt.doNEE = 1; integ.opt.NEEUsePerTileSG = perTile ? 1 : 0;
+            ref::kNEEUsePerTileSelectorSG = perTile;
+            const float hero = r.range(380.f, 720.f);
+            orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 23u), t0(uint32_t(i & 0xff), uint32_t(i >> 8), 29u); RefSG g1{g0}, t1{t0};
+            orc::Integrator::LightSample a;
+            ref::LightSample b;
+            const bool v0 = integ.generateLightSample(sd, reflOk, transOk, g0, t0, hero, imp, a);
+            const bool v1 = ref::generateLightSample(rsd, reflOk, transOk, g1, t1, hero, imp, b);
+            Cmp c("LightSampling.generateLightSample_analytic");
+            c.add(v0, v1); c.add(g0.next(), g1.next()); c.add(t0.next(), t1.next());
+            if (v0 && v1) { c.add(a.pdf, b.pdf); c.add(a.origin, b.origin); c.add(a.distance, b.distance); c.add(a.dir, b.dir); c.add(a.lightType, uint32_t(b.lightType)); c.add(a.beam, b.beam); }
+        }
+        osc.d.lights = nullptr; osc.d.lightCount = 0;
+    }
+    // ---- pltpt_solve.rt.slang: `measure` (propagation to the camera, camera polariser, spectral MIS, XYZ fit -> RGB, accumulation) and MISWeight
+    {
+        static orc::Scene osc;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};
+        for (int i = 0; i < N; ++i) {
+            const orc::float3 camPos = r.f3(-5.f, 5.f), w = r.dir() * r.range(0.5f, 3.f);
+            const orc::float3 u = orc::perp_stark(orc::normalize(w)) * r.range(0.3f, 2.f), v = orc::cross(orc::normalize(w), orc::normalize(u)) * r.range(0.3f, 2.f);
+            const float pol = r.u() < .4f ? 0.f : r.u(), theta = r.range(-3.2f, 3.2f);
+            for (int a = 0; a < 3; ++a) { integ.cam.posW[a] = camPos[a]; integ.cam.cameraU[a] = u[a]; integ.cam.cameraV[a] = v[a]; integ.cam.cameraW[a] = w[a]; }
+            integ.cam.polarizer = pol; integ.cam.polarizerTheta = theta;
+            ref::gScene.camera.data.posW = R(camPos); ref::gScene.camera.data.cameraU = R(u); ref::gScene.camera.data.cameraV = R(v); ref::gScene.camera.data.cameraW = R(w);
+            ref::gScene.camera.data.polarizer = pol; ref::gScene.camera.data.polarizerTheta = theta;
+            const bool direct = r.u() < .8f, mis = r.u() < .6f;
+            integ.opt.useDirectLights = direct; integ.opt.HWSSDoMIS = mis; integ.opt.debugView = 0;
+            ref::kUseDirectLights = direct; ref::mHWSSDoMIS = mis;
+            ref::PLTBeam rb;
+            orc::PLTBeam b = randomBeam(r, rb);
+            b.spectralPDFs = r.f4(0.f, 2.f);
+            if (r.u() < .1f) b.spectralPDFs = orc::float4(0.f);
+            if (r.u() < .2f) b.hwss_comps = 1;
+            rb = R(b);
+            const int bounceIdx = int(r.u() * 8.99f);
+            const float contribution = r.range(0.01f, 20.f);
+            orc::Integrator::PLTSolve s0; ref::PLTSolve s1;
+            const orc::float3 start = r.f3(0.f, 2.f);
+            s0.Lrgb = start; s1.Lrgb = R(start);
+            integ.measure(s0, bounceIdx, contribution, b);
+            ref::measure(s1, bounceIdx, contribution, rb);
+            { Cmp c("pltpt_solve.measure"); c.add(s0.Lrgb, s1.Lrgb); c.add(b, rb); }
+            { Cmp c("pltpt_solve.MISWeight"); const float p0 = r.range(0.f, 50.f), p1 = r.range(1e-6f, 50.f); c.add(orc::Integrator::MISWeight(p0, p1), ref::MISWeight(p0, p1)); }
+        }
+    }
+    // ---- packed scene records as the path decodes them: snorm / octahedral normals (FormatConversion.slang, PackedFormats.slang,
+    // MathHelpers.slang oct_to_ndir_snorm), emissive triangles (LightCollectionShared.slang PackedEmissiveTriangle::unpack and the two
+    // interpolators), vertices (SceneTypes.slang PackedStaticVertexData::unpack)
+    {
+        static orc::Scene osc;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        static PltptEmissiveTriangle etri;
+        static PltptPackedVertex vert;
+        osc.d.emissiveTriangles = &etri; osc.d.emissiveTriangleCount = 1;
+        osc.d.vertices = &vert; osc.d.vertexCount = 1;
+        auto halfBits = [&](float lo, float hi) { return ref::f32tof16(r.range(lo, hi)); };
+        for (int i = 0; i < N; ++i) {
+            const uint32_t packed = r.g(), edge = (r.u() < .1f) ? (r.u() < .5f ? 0x80008000u : 0x7fff8001u) : packed;
+            { Cmp c("PackedFormats.decodeNormal2x16"); c.add(orc::decodeNormal2x16(edge), ref::decodeNormal2x16(edge)); c.add(orc::unpackSnorm16(packed & 0xffffu), ref::unpackSnorm16(packed & 0xffffu));
+              const orc::float2 o = r.f2(-1.f, 1.f); c.add(orc::oct_to_ndir_snorm(o), ref::oct_to_ndir_snorm(R(o))); }
+            { Cmp c("LightCollectionShared.PackedEmissiveTriangle_unpack");
+              ref::PackedEmissiveTriangle pt;
+              for (int k = 0; k < 3; ++k) {
+                  const orc::float3 pw = r.f3(-10.f, 10.f);
+                  const uint32_t uv = halfBits(-2.f, 3.f) | (halfBits(-2.f, 3.f) << 16);
+                  float uvf; std::memcpy(&uvf, &uv, 4);
+                  for (int a = 0; a < 3; ++a) etri.posAndTexCoords[k][a] = pw[a];
+                  etri.posAndTexCoords[k][3] = uvf;
+                  pt.posAndTexCoords[k] = ref::float4(pw.x, pw.y, pw.z, uvf);
+              }
+              const float area = r.range(1e-4f, 20.f);
+              etri.normal = r.g(); std::memcpy(&etri.area, &area, 4); etri.materialID = r.g() & 0xffffu; etri.lightIdx = r.g() & 0xffu;
+              pt.normal = etri.normal; pt.area = etri.area; pt.materialID = etri.materialID; pt.lightIdx = etri.lightIdx;
+              const orc::Integrator::EmissiveTriangle a = integ.getEmissiveTriangle(0);
+              ref::EmissiveTriangle b = pt.unpack();
+              for (int k = 0; k < 3; ++k) { c.add(a.posW[k], b.posW[k]); c.add(a.texCoords[k], b.texCoords[k]); }
+              c.add(a.normal, b.normal); c.add(a.area, b.area); c.add(a.materialID, uint32_t(b.materialID));
+              const orc::float3 bary = orc::sample_triangle(r.f2(0.f, 1.f));
+              c.add(a.posW[0] * bary[0] + a.posW[1] * bary[1] + a.posW[2] * bary[2], b.getPosition(R(bary)));          // as sampleTriangle interpolates (plt_integrator.h)
+              c.add(a.texCoords[0] * bary[0] + a.texCoords[1] * bary[1] + a.texCoords[2] * bary[2], b.getTexCoord(R(bary))); }
+            { Cmp c("SceneTypes.PackedStaticVertexData_unpack");
+              const orc::float3 pos = r.f3(-50.f, 50.f); const orc::float2 tc = r.f2(-4.f, 4.f);
+              const uint32_t w0 = halfBits(-1.f, 1.f) | (halfBits(-1.f, 1.f) << 16);
+              const float sgn = r.u() < .2f ? 0.f : (r.u() < .5f ? -1.f : 1.f);
+              const uint32_t w1 = halfBits(-1.f, 1.f) | (ref::f32tof16(sgn) << 16), w2 = r.g();
+              for (int a = 0; a < 3; ++a) vert.position[a] = pos[a];
+              vert.texCrd[0] = tc.x; vert.texCrd[1] = tc.y;
+              vert.packedNormalTangentCurveRadius[0] = w0; vert.packedNormalTangentCurveRadius[1] = w1; vert.packedNormalTangentCurveRadius[2] = w2;
+              ref::PackedStaticVertexData pv;
+              pv.position = R(pos); pv.texCrd = R(tc);
+              pv.packedNormalTangentCurveRadius = ref::float3(ref::asfloat(ref::uint(w0)), ref::asfloat(ref::uint(w1)), ref::asfloat(ref::uint(w2)));
+              const orc::StaticVertexData a = osc.getVertex(0);
+              ref::StaticVertexData b = pv.unpack();
+              c.add(a.position, b.position); c.add(a.normal, b.normal); c.add(a.tangent, b.tangent); c.add(a.texCrd, b.texCrd); }
+        }
+        osc.d.emissiveTriangles = nullptr; osc.d.emissiveTriangleCount = 0; osc.d.vertices = nullptr; osc.d.vertexCount = 0;
+    }
 }

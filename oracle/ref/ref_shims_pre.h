@@ -74,4 +74,29 @@ struct BSDFProperties {
     enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
 };
 
+// ---- what RenderPasses/PLTPT/LightSampling.slangh expects from the pass around it
+// pltpt.slangh:95-118: the pass's compile-time switches (defines set by PLTPT.cpp:222-260) -- variables here so that the comparison can
+// walk through their combinations; pltpt.slangh:77-78: the two sourcing constants of the constant buffer
+static bool kUseEnvLight = false, kUseEmissiveLights = false, kUseAnalyticLights = true, kNEEUsePerTileSelectorSG = false;
+static const bool kForceFullyCoherent = false;
+static float kSourcingAreaFromEmissiveGeometry = 1.f, kSourcingMaxBeamOmega = .025f;
+static const float kRayTMax = 3.402823466e+38f;  // ShadowRays.slangh:47 (= FLT_MAX)
+struct RayDesc { float3 Origin, Direction; float TMin = 0.f, TMax = 0.f; };  // HLSL built-in (LightSample::getVisibilityRay)
+// Rendering/Lights/EnvMapSampler.slang:46-52 and EmissiveLightSamplerInterface.slang:38-49: the sample records; the two samplers
+// themselves need the texture system / the light collection and are outside this comparison -- they stand in as "no sample drawn"
+struct EnvMapSample { float3 dir; float pdf = 0.f; hwss_t Le; hwss_t wavelengths; };
+struct TriangleLightSample { uint triangleIndex = 0; float3 posW, normalW, dir; float distance = 0.f; hwss_t Le, wavelengths; float pdf = 0.f; float2 uv; };
+struct EnvMapSamplerStandIn { bool sample(float2, float, EnvMapSample&) { return false; } };
+struct EmissiveSamplerStandIn { template <class S> bool sampleLight(float3, float3, bool, S&, float, bool, TriangleLightSample&) { return false; } };
+static EnvMapSamplerStandIn envMapSampler;
+static EmissiveSamplerStandIn emissiveSampler;
+
+// ---- what `measure` (pltpt_solve.rt.slang:96-147) expects: the camera block it reads (Scene/Camera/CameraData.slang:36-69, the five
+// fields used), the solve payload (Path.slang:200-225, without its generators), two more switches of pltpt.slangh:95-104
+struct CameraData { float3 posW, cameraU, cameraV, cameraW; float polarizer = 0.f, polarizerTheta = 0.f; };
+struct Camera { CameraData data; };
+struct PLTSolve { float3 Lrgb = .0f; float3 pathOrigin, pathNormal; float wavelength = 0.f; };
+static bool kUseDirectLights = true, mHWSSDoMIS = true;
+#define DO_DEBUG_VIEW 0
+
 }  // namespace ref

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <type_traits>
 
 namespace ref {
@@ -110,6 +111,10 @@ template <class A, class B, int N> vec<arith_t<A, B>, N> select(const vec<bool, 
     vec<arith_t<A, B>, N> r; for (int i = 0; i < N; ++i) r[i] = c[i] ? arith_t<A, B>(a[i]) : arith_t<A, B>(b[i]); return r; }
 template <class A, class B, int N, class = if_scalar<B>> vec<arith_t<A, B>, N> select(const vec<bool, N>& c, const vec<A, N>& a, B b) { return select(c, a, vec<B, N>(b)); }
 template <class A, class B, int N, class = if_scalar<A>> vec<arith_t<A, B>, N> select(const vec<bool, N>& c, A a, const vec<B, N>& b) { return select(c, vec<A, N>(a), b); }
+template <class A, class B, int N, class = if_scalar<A>, class = if_scalar<B>> vec<arith_t<A, B>, N> select(const vec<bool, N>& c, A a, B b) { return select(c, vec<A, N>(a), vec<B, N>(b)); }
+// shifts of integer vectors by a scalar count
+template <class T, int N, class = std::enable_if_t<std::is_integral<T>::value>> vec<T, N> operator>>(const vec<T, N>& a, int s) { vec<T, N> r; for (int i = 0; i < N; ++i) r[i] = T(a[i] >> s); return r; }
+template <class T, int N, class = std::enable_if_t<std::is_integral<T>::value>> vec<T, N> operator<<(const vec<T, N>& a, int s) { vec<T, N> r; for (int i = 0; i < N; ++i) r[i] = T(a[i] << s); return r; }
 
 // ---- scalar intrinsics (fp32; min / max follow IEEE minNum / maxNum like DXIL and like the oracle's hlsl_min / hlsl_max)
 inline float abs(float v) { return std::fabs(v); }
@@ -140,6 +145,7 @@ inline bool isfinite(float v) { return std::isfinite(v); }
 inline bool isnan(float v) { return std::isnan(v); }
 inline bool isinf(float v) { return std::isinf(v); }
 inline float saturate(float v) { return std::fmin(std::fmax(v, 0.f), 1.f); }
+inline float smoothstep(float a, float b, float x) { const float t = saturate((x - a) / (b - a)); return t * t * (3.f - 2.f * t); }  // HLSL intrinsic
 inline float lerp(float a, float b, float t) { return a + t * (b - a); }  // HLSL lerp: x + s*(y-x)
 inline float step(float e, float x) { return x >= e ? 1.f : 0.f; }
 inline float radians(float d) { return d * 0.0174532925199432957692f; }
@@ -158,11 +164,37 @@ inline float asfloat(uint u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float asfloat(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline float asfloat(float f) { return f; }
 inline int asint(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+// HLSL f16tof32 / f32tof16 (the low 16 bits are an IEEE binary16; conversion to half rounds to nearest even)
+inline float f16tof32(uint h) {
+    const uint s = (h >> 15) & 1u, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float v;
+    if (e == 0) v = std::ldexp(float(m), -24);
+    else if (e == 31) v = m ? std::numeric_limits<float>::quiet_NaN() : std::numeric_limits<float>::infinity();
+    else v = std::ldexp(float(m | 0x400u), int(e) - 25);
+    return s ? -v : v;
+}
+inline uint f32tof16(float f) {
+    uint x; std::memcpy(&x, &f, 4);
+    const uint s = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return s | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u);
+    if (x >= 0x477ff000u) return s | 0x7c00u;                       // rounds to infinity
+    if (x < 0x33000001u) return s;                                  // rounds to zero
+    int e = int(x >> 23) - 127;
+    uint m = (x & 0x7fffffu) | 0x800000u;
+    int shift = e < -14 ? 13 + (-14 - e) : 13;
+    uint h = m >> shift;
+    const uint rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    if (e < -14) return s | h;                                      // subnormal half (h may carry into the smallest normal)
+    return s | ((uint(e + 15) << 10) + (h - 0x400u));
+}
 
 // ---- component-wise vector intrinsics
 #define REF_MAP1(F) template <class T, int N> auto F(const vec<T, N>& a) { vec<decltype(F(a[0])), N> r; for (int i = 0; i < N; ++i) r[i] = F(a[i]); return r; }
 REF_MAP1(abs) REF_MAP1(sqrt) REF_MAP1(rsqrt) REF_MAP1(exp) REF_MAP1(exp2) REF_MAP1(log) REF_MAP1(log2) REF_MAP1(sin) REF_MAP1(cos) REF_MAP1(tan) REF_MAP1(asin) REF_MAP1(acos) REF_MAP1(atan)
 REF_MAP1(floor) REF_MAP1(ceil) REF_MAP1(round) REF_MAP1(trunc) REF_MAP1(frac) REF_MAP1(sign) REF_MAP1(isfinite) REF_MAP1(isnan) REF_MAP1(isinf) REF_MAP1(saturate)
+REF_MAP1(asint) REF_MAP1(asuint) REF_MAP1(asfloat)
 #undef REF_MAP1
 #define REF_MAP2(F)                                                                                                                                 \
     template <class A, class B, int N> auto F(const vec<A, N>& a, const vec<B, N>& b) { vec<decltype(F(a[0], b[0])), N> r; for (int i = 0; i < N; ++i) r[i] = F(a[i], b[i]); return r; } \
@@ -191,6 +223,10 @@ template <int R, int C> struct mat {
     template <class... V, class = std::enable_if_t<sizeof...(V) == size_t(R) && (std::is_same<V, vec<float, C>>::value && ...)>, class = void> mat(V... v) {
         const vec<float, C> t[] = {v...};
         for (int r = 0; r < R; ++r) rows[r] = t[r];
+    }
+    // (float3x3)M of a float4x4: the upper-left block (HLSL matrix truncation cast; LightHelpers.slang sampleDistantLight)
+    template <int R2, int C2, class = std::enable_if_t<(R2 >= R && C2 >= C && (R2 != R || C2 != C))>> explicit mat(const mat<R2, C2>& M) {
+        for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) rows[r][c] = M[r][c];
     }
     vec<float, C>& operator[](int r) { return rows[r]; }
     const vec<float, C>& operator[](int r) const { return rows[r]; }

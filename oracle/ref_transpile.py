@@ -25,6 +25,8 @@ Rewrite rules (all mechanical; each is a regular expression or a brace-matched b
   R10 `static const float` -> `static constexpr float`; struct-typed `const` locals / parameters lose `const` (Slang methods are
       callable on them; C++ would need const-qualified methods), structs get their trailing `;`
   R12 `let x = e` -> `auto x = e`
+  R13 `enum class X : T` -> `enum X : T` (Slang converts a scoped enumerator to its underlying type in `switch (uint)` / `uint(...)`; C++
+      only does so for an unscoped enumeration, whose enumerators can still be written `X::Name`)
   R11 the handful of vector-condition ternaries (`c ? a : b` with bool2 `c`, DiffractionGrating.slang only) -> select(c, a, b); listed in PATCHES
       with the exact source text they replace -- the script fails if a patch no longer matches.
 """
@@ -42,8 +44,12 @@ SOURCES = [
     ("Utils/Math/MathHelpers.slang", ["sqr", "norm2", "factorial", "c_t", "cnorm2", "cabs", "csqrt", "cconj", "creal", "cimag", "cmul", "cdiv", "csqr", "carg", "sinc",
                                       "sample_disk", "sample_cone", "sample_sphere", "sample_disk_concentric", "sample_cosine_hemisphere_concentric", "cosine_hemisphere_concentric_pdf",
                                       "sample_triangle", "sample_boxmueller", "boxmueller_pdf", "sample_boxmueller_truncated", "boxmueller_truncated_pdf", "tryInvert", "inverse",
-                                      "diag2", "ident2", "svd_symmetric", "perp_stark", "BesselJ_saa", "BesselJ_laa", "BesselJ", "ndir_to_oct_equal_area_snorm", "oct_to_ndir_equal_area_snorm",
-                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm"]),
+                                      "diag2", "ident2", "diag4", "ident4", "svd_symmetric", "perp_stark", "BesselJ_saa", "BesselJ_laa", "BesselJ", "ndir_to_oct_equal_area_snorm", "oct_to_ndir_equal_area_snorm",
+                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm", "oct_wrap", "oct_to_ndir_snorm"]),
+    ("Utils/Math/FormatConversion.slang", ["unpackSnorm16", "unpackSnorm2x16"]),
+    ("Utils/Math/PackedFormats.slang", ["decodeNormal2x16"]),
+    ("Scene/Lights/LightCollectionShared.slang", None),
+    ("Scene/SceneTypes.slang", ["StaticVertexData", "PackedStaticVertexData"]),
     ("Utils/Color/ColorHelpers.slang", ["XYZtoRGB_Rec709"]),
     ("Utils/Color/SpectrumUtils.slang", None),
     ("Rendering/Materials/Fresnel.slang", None),
@@ -54,7 +60,9 @@ SOURCES = [
     ("Rendering/Materials/PLT/GaussianSurface.slang", None),
     ("Rendering/Materials/PLT/Birefringence.slang", None),
     ("Utils/Color/SpectrumSampler.slang", None),
-    ("Scene/Scene.slang", ("members", "Scene", ["evalSpectrumRGB", "evalSpectrum", "sampleSpectrum"], "SpectralProfile* spectralProfiles = nullptr;")),
+    ("Scene/Lights/LightData.slang", None),
+    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight"],
+                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera;")),
     ("Rendering/Materials/BSDFSample.slang", None),
     ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives"]),
     ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
@@ -69,6 +77,12 @@ SOURCES = [
     ("Rendering/Materials/PLT/PLTDiffractionGratedConductorBSDF.slang", None),
     ("Rendering/Materials/PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", None),
     ("Rendering/Materials/PLT/PLTMultiLayeredStackBSDF.slang", None),
+    ("Rendering/Lights/LightHelpers.slang", None),
+    ("Utils/Geometry/GeometryHelpers.slang", ["computeRayOrigin"]),
+    ("Rendering/Utils/LightsSamplingUtils.slang", None),
+    ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
+    ("../RenderPasses/PLTPT/LightSampling.slangh", None),
+    ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
 ]
 
 STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
@@ -94,6 +108,20 @@ PATCHES = [
     ("PLT/DiffractionGrating.slang", "lobe = rand<.0f ? -lobe : lobe;", "lobe = select(rand<.0f, -lobe, lobe);", "R11"),
     ("PLT/DiffractionGrating.slang", "const float2 sini = p>FLT_EPSILON ? wi.xy/p : .0f;", "const float2 sini = select(p>FLT_EPSILON, wi.xy/p, .0f);", "R11"),
     ("PLT/DiffractionGrating.slang", "const float2 invp = p>FLT_EPSILON ? 1.f/p : .0f;", "const float2 invp = select(p>FLT_EPSILON, 1.f/p, .0f);", "R11"),
+    ("Utils/Math/MathHelpers.slang", "return (1.f - abs(v.yx)) * (v.xy >= 0.f ? 1.f : -1.f);", "return (1.f - abs(v.yx)) * select(v.xy >= 0.f, 1.f, -1.f);", "R11"),
+    ("Utils/Math/MathHelpers.slang", "n.xy = (n.z < 0.0) ? oct_wrap(n.xy) : n.xy;", "{ const float2 nxy = (n.z < 0.0) ? oct_wrap(n.xy) : n.xy; n.x = nxy.x; n.y = nxy.y; }",
+     "swizzle on the left-hand side (R8 models read-only swizzles)"),
+    ("Lights/LightCollectionShared.slang", "#ifndef HOST_CODE\n    [mutating] void pack(const EmissiveTriangle tri)", "#if 0\n    [mutating] void pack(const EmissiveTriangle tri)",
+     "`pack` writes through swizzles (`.xyz = ...`); the path only unpacks"),
+    ("Scene/SceneTypes.slang", "v.tangent.xyz = decodeNormal2x16(asuint(packedNormalTangentCurveRadius.z));",
+     "{ const float3 txyz = decodeNormal2x16(asuint(packedNormalTangentCurveRadius.z)); v.tangent.x = txyz.x; v.tangent.y = txyz.y; v.tangent.z = txyz.z; }",
+     "swizzle on the left-hand side"),
+    ("Scene/SceneTypes.slang", "#else // !HOST_CODE\n    [mutating] void pack(const StaticVertexData v)", "#elif 0\n    [mutating] void pack(const StaticVertexData v)",
+     "the shader-side `pack` is not used by the path (vertices arrive packed); only `unpack` is compared"),
+    ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
+    ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
+    ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",
+     "an array parameter is already passed by reference in C++ (R7 would make it an array of references)"),
     ("PLT/PLTDiffractionGratedConductorBSDF.slang", "const int2 sign = lobe<0 ? int2(0) : int2(1);", "const int2 sign = select(lobe<0, int2(0), int2(1));", "R11"),
     ("PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", "const int2 sign = lobe<0 ? int2(0) : int2(1);", "const int2 sign = select(lobe<0, int2(0), int2(1));", "R11"),
 ]
@@ -281,10 +309,13 @@ def transpile(path, s, struct_names):
     s = re.sub(r"^\s*#pragma once\s*$", "", s, flags=re.M)
     s = re.sub(r"^\s*(BEGIN|END)_NAMESPACE_FALCOR\s*$", "", s, flags=re.M)
     s = re.sub(r"\blet\s+", "auto ", s)   # R12: `let x = ...` -> `auto x = ...`
+    s = re.sub(r"\benum\s+class\s+(\w+)\s*:", r"enum \1 :", s)   # R13
     # R4
     s = re.sub(r"\[mutating\]\s*", "", s)
     s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
     s = re.sub(r"\bno_diff\s+", "", s)
+    s = re.sub(r"\bprecise\s+", "", s)          # every operation is individually rounded here anyway (-ffp-contract=off)
+    s = re.sub(r"\s*\bCONST_FUNCTION\b", "", s)  # Utils/HostDeviceShared.slangh: empty in shader code
     # R2
     s = rule_literals(s)
     # R6
