@@ -4,6 +4,18 @@
 // BSDFs through their IMaterialInstance wrappers -- oracle (orc::) against the transpiled reference text (ref::).
 #pragma once
 
+namespace ref {
+// which transpiled emissive sampler LightSampling.slangh's `emissiveSampler` stands for: 0 = none (no sample drawn), 1 = uniform, 2 = power
+static int gEmissiveKind = 0;
+static EmissiveUniformSampler gUniformSampler;
+static EmissivePowerSampler gPowerSampler;
+template <class S> bool emissiveSamplerDispatch(float3 posW, float3 normalW, bool upperHemisphere, S& sg, float wavelength, bool importanceSampleSpectrum, TriangleLightSample& ls) {
+    if (gEmissiveKind == 1) return gUniformSampler.sampleLight(posW, normalW, upperHemisphere, sg, wavelength, importanceSampleSpectrum, ls);
+    if (gEmissiveKind == 2) return gPowerSampler.sampleLight(posW, normalW, upperHemisphere, sg, wavelength, importanceSampleSpectrum, ls);
+    return false;
+}
+}  // namespace ref
+
 namespace {
 ref::ShadingData R(const orc::ShadingData& s) {
     ref::ShadingData o;
@@ -411,5 +423,186 @@ static void ref_compare_more(int N, Rnd& r) {
               c.add(a.position, b.position); c.add(a.normal, b.normal); c.add(a.tangent, b.tangent); c.add(a.texCrd, b.texCrd); }
         }
         osc.d.emissiveTriangles = nullptr; osc.d.emissiveTriangleCount = 0; osc.d.vertices = nullptr; osc.d.vertexCount = 0;
+    }
+    // ---- emissive-triangle sampling: EmissiveLightSamplerHelpers.slang (materialEvalEmissive, sampleTriangle, evalTrianglePdf),
+    // EmissiveUniformSampler.slang and EmissivePowerSampler.slang (sampleLight, evalPdf) over LightCollection.slang, on small random light
+    // collections (packed triangles, flux table, active list, alias table) with untextured emitters
+    {
+        static orc::Scene osc;
+        osc.profiles = table;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};
+        constexpr uint32_t kMax = 6;
+        static PltptEmissiveTriangle tris[kMax];
+        static PltptEmissiveFlux flux[kMax];
+        static uint32_t active[kMax], alias[2 * kMax];
+        static ref::uint2 ralias[kMax];
+        static PltptMaterialBlob mats[2];
+        static ref::BasicMaterialData rmats[2];
+        static ref::PackedEmissiveTriangle rtris[kMax];
+        static ref::EmissiveFlux rflux[kMax];
+        mats[0] = PltptMaterialBlob{}; mats[1] = PltptMaterialBlob{};
+        mats[0].header[0] = 1u << 31; mats[0].emissionSpectralId = 4u;                             // emissive basic material
+        mats[1].header[0] = 1u << 31; mats[1].emissionSpectralId = PLTPT_NO_SPECTRAL_PROFILE;      // basic, not emissive: Le stays 0
+        rmats[0].emissionSpectralId = 4u; rmats[1].emissionSpectralId = ref::BasicMaterialData::no_spectral_profile;
+        osc.d.materialData = mats; osc.d.materialCount = 2;
+        ref::gScene.materials.basic = rmats;
+        ref::EmissiveUniformSampler& uniformSampler = ref::gUniformSampler;
+        ref::EmissivePowerSampler& powerSampler = ref::gPowerSampler;
+        static PltptLightData pointLight;
+        static ref::LightData rpointLight;
+        for (int i = 0; i < N; ++i) {
+            const uint32_t n = 1u + uint32_t(r.u() * (kMax - 0.001f));
+            float total = 0.f;
+            for (uint32_t t = 0; t < n; ++t) {
+                const orc::float3 v0 = r.f3(-3.f, 3.f), v1 = v0 + r.f3(-1.f, 1.f), v2 = v0 + r.f3(-1.f, 1.f);
+                const orc::float3 vs[3] = {v0, v1, v2};
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t uv = ref::f32tof16(r.u()) | (ref::f32tof16(r.u()) << 16);
+                    float uvf; std::memcpy(&uvf, &uv, 4);
+                    for (int a = 0; a < 3; ++a) tris[t].posAndTexCoords[k][a] = vs[k][a];
+                    tris[t].posAndTexCoords[k][3] = uvf;
+                    rtris[t].posAndTexCoords[k] = ref::float4(vs[k].x, vs[k].y, vs[k].z, uvf);
+                }
+                const float area = 0.5f * orc::length(orc::cross(v1 - v0, v2 - v0));
+                tris[t].normal = r.g(); std::memcpy(&tris[t].area, &area, 4); tris[t].materialID = r.u() < .85f ? 0u : 1u; tris[t].lightIdx = 0;
+                rtris[t].normal = tris[t].normal; rtris[t].area = tris[t].area; rtris[t].materialID = tris[t].materialID; rtris[t].lightIdx = 0;
+                flux[t].flux = r.range(0.01f, 5.f); total += flux[t].flux;
+                rflux[t].flux = flux[t].flux;
+                active[t] = n - 1u - t;  // a permutation: the active list is an indirection
+                const uint32_t above = uint32_t(r.u() * (n - 0.001f)), below = uint32_t(r.u() * (n - 0.001f));
+                const uint32_t px = (ref::f32tof16(r.u()) << 16) | ((above >> 8) & 0xffffu), py = ((above & 0xffu) << 24) | (below & 0xffffffu);
+                alias[2 * t] = px; alias[2 * t + 1] = py; ralias[t] = ref::uint2(px, py);
+            }
+            const float invSum = 1.f / total;
+            osc.d.emissiveTriangles = tris; osc.d.emissiveTriangleCount = n; osc.d.emissiveFlux = flux; osc.d.activeTriangles = active; osc.d.activeTriangleCount = n;
+            osc.d.triangleAliasTable = alias; osc.d.invWeightsSum = invSum;
+            ref::LightCollection& lc = ref::gScene.lightCollection;
+            lc.triangleCount = n; lc.activeTriangleCount = n; lc.triangleData.p = rtris; lc.activeTriangles.p = active; lc.fluxData.p = rflux;
+            powerSampler._emissivePower.invWeightsSum = invSum; powerSampler._emissivePower.triangleAliasTable.p = ralias;
+            const bool power = r.u() < .5f, imp = r.u() < .5f;
+            integ.opt.emissiveSampler = power ? PLTPT_EMISSIVE_SAMPLER_POWER : PLTPT_EMISSIVE_SAMPLER_UNIFORM;
+            const orc::float3 shadingPos = r.f3(-4.f, 4.f), shadingN = r.dir();
+            const float hero = r.range(380.f, 720.f);
+            orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 31u); RefSG g1{g0};
+            orc::Integrator::TriangleLightSample a;
+            ref::TriangleLightSample b;
+            const bool v0 = integ.emissiveSampleLight(shadingPos, g0, hero, imp, a);
+            const bool v1 = power ? powerSampler.sampleLight(R(shadingPos), R(shadingN), false, g1, hero, imp, b) : uniformSampler.sampleLight(R(shadingPos), R(shadingN), false, g1, hero, imp, b);
+            { Cmp c(power ? "EmissivePowerSampler.sampleLight" : "EmissiveUniformSampler.sampleLight");
+              c.add(v0, v1); c.add(g0.next(), g1.next()); c.add(a.triangleIndex, uint32_t(b.triangleIndex));
+              if (v0 && v1) { c.add(a.posW, b.posW); c.add(a.normalW, b.normalW); c.add(a.dir, b.dir); c.add(a.distance, b.distance); c.add(a.Le, b.Le); c.add(a.wavelengths, b.wavelengths); c.add(a.pdf, b.pdf); } }
+            { Cmp c(power ? "EmissivePowerSampler.evalPdf" : "EmissiveUniformSampler.evalPdf");
+              ref::TriangleLightHit hit;
+              const uint32_t ti = r.u() < .05f ? 0xffffffffu : uint32_t(r.u() * (n - 0.001f));
+              const orc::float3 hp = r.f3(-3.f, 3.f), hn = r.dir();
+              hit.triangleIndex = ti; hit.posW = R(hp); hit.normalW = R(hn);
+              const float p0 = integ.emissiveEvalPdf(shadingPos, ti, hp, hn);
+              const float p1 = power ? powerSampler.evalPdf(R(shadingPos), R(shadingN), false, hit) : uniformSampler.evalPdf(R(shadingPos), R(shadingN), false, hit);
+              c.add(p0, p1); }
+            // the pass's whole NEE sample with emissive triangles in the mix (LightSampling.slangh generateEmissiveSample + two-way selection
+            // with one analytic point light)
+            {
+                const bool withAnalytic = r.u() < .5f;
+                pointLight = PltptLightData{};
+                const orc::float3 lp = r.f3(-3.f, 3.f), ld = r.dir();
+                for (int k = 0; k < 3; ++k) { pointLight.posW[k] = lp[k]; pointLight.dirW[k] = ld[k]; }
+                pointLight.type = 0; pointLight.openingAngle = orc::kPi; pointLight.cosOpeningAngle = -1.f; pointLight.intensitySpectrumId = 4u; pointLight.cosSubtendedAngle = 0.9999893f;
+                rpointLight = ref::LightData();
+                rpointLight.posW = R(lp); rpointLight.dirW = R(ld); rpointLight.type = 0; rpointLight.openingAngle = pointLight.openingAngle; rpointLight.cosOpeningAngle = -1.f;
+                rpointLight.intensitySpectrumId = 4u; rpointLight.cosSubtendedAngle = pointLight.cosSubtendedAngle;
+                osc.d.lights = &pointLight; osc.d.lightCount = withAnalytic ? 1u : 0u;
+                ref::gScene.lights = &rpointLight; ref::gScene.lightCount = withAnalytic ? 1u : 0u;
+                integ.opt.useEmissiveLights = 1; integ.opt.useAnalyticLights = 1; integ.opt.useEnvLights = 1; integ.opt.doNEE = 1; integ.opt.NEEUsePerTileSG = 0;
+                ref::kUseEnvLight = false; ref::kUseEmissiveLights = true; ref::kUseAnalyticLights = withAnalytic; ref::kNEEUsePerTileSelectorSG = false;
+                const float area = r.range(0.01f, 4.f), omega = r.range(0.001f, 0.1f);
+                integ.opt.sourcingAreaFromEmissiveGeometry = area; integ.opt.sourcingMaxBeamOmega = omega;
+                ref::kSourcingAreaFromEmissiveGeometry = area; ref::kSourcingMaxBeamOmega = omega;
+                ref::gEmissiveKind = power ? 2 : 1;
+                const orc::ShadingData sd = randomShadingData(r);
+                ref::ShadingData rsd = R(sd);
+                orc::SampleGenerator h0(uint32_t(i & 0xffff), uint32_t(i >> 16), 37u), t0(uint32_t(i & 0xff), uint32_t(i >> 8), 41u); RefSG h1{h0}, t1{t0};
+                orc::Integrator::LightSample la;
+                ref::LightSample lb;
+                const bool w0 = integ.generateLightSample(sd, true, true, h0, t0, hero, imp, la);
+                const bool w1 = ref::generateLightSample(rsd, true, true, h1, t1, hero, imp, lb);
+                Cmp c("LightSampling.generateLightSample_emissive");
+                c.add(w0, w1); c.add(h0.next(), h1.next());
+                if (w0 && w1) { c.add(la.pdf, lb.pdf); c.add(la.origin, lb.origin); c.add(la.distance, lb.distance); c.add(la.dir, lb.dir); c.add(la.lightType, uint32_t(lb.lightType)); c.add(la.beam, lb.beam); }
+                ref::gEmissiveKind = 0;
+                osc.d.lights = nullptr; osc.d.lightCount = 0; ref::gScene.lightCount = 0;
+            }
+        }
+        osc.d.emissiveTriangles = nullptr; osc.d.emissiveTriangleCount = 0; osc.d.activeTriangleCount = 0; osc.d.materialData = nullptr; osc.d.materialCount = 0;
+    }
+    // ---- environment map: EnvMap.slang (eval, toLocal / toWorld, lat-long mapping), EnvMapSampler.slang (hierarchical importance sampling,
+    // evalPdf) and the pass's generateEnvMapSample.  Texel loads and the two texture filters are services of the texture unit: both sides
+    // read the oracle's lat-long texels, its importance-map mips and its fp32 filters (plt_envmap.h)
+    {
+        static orc::Scene osc;
+        osc.profiles = table;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};
+        constexpr uint32_t W = 32, H = 16;
+        static float texels[W * H * 4];
+        for (uint32_t t = 0; t < W * H; ++t) {
+            const float sun = (t == 5 * W + 20 || t == 5 * W + 21) ? 80.f : 1.f;  // a bright spot, so that the importance map is far from uniform
+            texels[4 * t] = sun * r.range(0.05f, 1.f); texels[4 * t + 1] = sun * r.range(0.05f, 1.f); texels[4 * t + 2] = sun * r.range(0.05f, 1.f); texels[4 * t + 3] = 1.f;
+        }
+        PltptSceneDesc d{};
+        d.envMapTexels = texels; d.envMapWidth = W; d.envMapHeight = H;
+        const float ang = 0.7f, ca = std::cos(ang), sa = std::sin(ang);
+        const float rot[12] = {ca, 0.f, sa, 0.f, 0.f, 1.f, 0.f, 0.f, -sa, 0.f, ca, 0.f}, inv[12] = {ca, 0.f, -sa, 0.f, 0.f, 1.f, 0.f, 0.f, sa, 0.f, ca, 0.f};
+        for (int k = 0; k < 12; ++k) { d.envMap.transform[k] = rot[k]; d.envMap.invTransform[k] = inv[k]; }
+        d.envMap.tint[0] = 0.9f; d.envMap.tint[1] = 1.f; d.envMap.tint[2] = 0.8f; d.envMap.intensity = 1.7f;
+        osc.env.init(d);
+        const orc::EnvMap& env = osc.env;
+        ref::EnvMap& renv = ref::gScene.envMap;
+        for (int row = 0; row < 3; ++row) for (int c = 0; c < 4; ++c) { renv.data.transform[row][c] = rot[4 * row + c]; renv.data.invTransform[row][c] = inv[4 * row + c]; }
+        renv.data.tint = ref::float3(0.9f, 1.f, 0.8f); renv.data.intensity = 1.7f;
+        renv.envMap.ctx = &env; renv.envMap.width = W; renv.envMap.height = H;
+        renv.envMap.loadFn = [](const void* c, int x, int y, int) { const orc::float3 t = static_cast<const orc::EnvMap*>(c)->texel(x, y); return ref::float4(t.x, t.y, t.z, 1.f); };
+        renv.envMap.sampleFn = [](const void* c, ref::float2 uv, float) { const orc::float3 t = static_cast<const orc::EnvMap*>(c)->sampleBilinear(orc::float2(uv.x, uv.y)); return ref::float4(t.x, t.y, t.z, 1.f); };
+        ref::EnvMapSampler& smp = ref::envMapSampler;
+        smp.importanceMap.ctx = &env; smp.importanceMap.width = smp.importanceMap.height = orc::EnvMap::kDimension;
+        smp.importanceMap.loadFn = [](const void* c, int x, int y, int mip) { return static_cast<const orc::EnvMap*>(c)->load(uint32_t(x), uint32_t(y), uint32_t(mip)); };
+        smp.importanceMap.sampleFn = [](const void* c, ref::float2 uv, float) {  // point sampling, clamp to edge
+            const int dim = int(orc::EnvMap::kDimension);
+            const int x = std::min(std::max(int(std::floor(uv.x * float(dim))), 0), dim - 1), y = std::min(std::max(int(std::floor(uv.y * float(dim))), 0), dim - 1);
+            return static_cast<const orc::EnvMap*>(c)->load(uint32_t(x), uint32_t(y), 0u); };
+        smp.importanceInvDim = ref::float2(1.f / float(orc::EnvMap::kDimension));
+        smp.importanceBaseMip = env.baseMip;
+        integ.opt.useEnvLights = 1; integ.opt.useEmissiveLights = 1; integ.opt.useAnalyticLights = 1; integ.opt.doNEE = 1;
+        ref::kUseEnvLight = true; ref::kUseEmissiveLights = false; ref::kUseAnalyticLights = false; ref::kNEEUsePerTileSelectorSG = false; ref::gEmissiveKind = 0;
+        for (int i = 0; i < N; ++i) {
+            const orc::float3 dir = r.dir();
+            { Cmp c("EnvMap.eval_toLocal_toWorld"); c.add(env.eval(dir), renv.eval(R(dir))); c.add(env.toLocal(dir), renv.toLocal(R(dir))); c.add(env.toWorld(dir), renv.toWorld(R(dir)));
+              c.add(orc::world_to_latlong_map(dir), ref::world_to_latlong_map(R(dir))); }
+            const orc::float2 rnd = r.f2(0.f, 1.f);
+            const float hero = r.range(380.f, 720.f);
+            { Cmp c("EnvMapSampler.sample"); orc::EnvMap::Sample a; ref::EnvMapSample b;
+              const bool v0 = env.sample(rnd, a), v1 = smp.sample(R(rnd), hero, b);
+              c.add(v0, v1); c.add(a.dir, b.dir); c.add(a.pdf, b.pdf);
+              const orc::float4 wl = orc::SpectrumSampler::hwssWavelengths(hero);
+              c.add(wl, b.wavelengths); c.add(orc::SpectrumUtils::rgbToSpectrum(a.Le, wl), b.Le); }
+            { Cmp c("EnvMapSampler.evalPdf"); c.add(env.evalPdf(dir), smp.evalPdf(R(dir))); }
+            {
+                const float omega = r.range(0.001f, 0.1f);
+                integ.opt.sourcingMaxBeamOmega = omega; ref::kSourcingMaxBeamOmega = omega;
+                const orc::ShadingData sd = randomShadingData(r);
+                ref::ShadingData rsd = R(sd);
+                orc::SampleGenerator h0(uint32_t(i & 0xffff), uint32_t(i >> 16), 43u), t0(1u, 2u, 47u); RefSG h1{h0}, t1{t0};
+                orc::Integrator::LightSample la;
+                ref::LightSample lb;
+                const bool w0 = integ.generateLightSample(sd, true, true, h0, t0, hero, false, la);
+                const bool w1 = ref::generateLightSample(rsd, true, true, h1, t1, hero, false, lb);
+                Cmp c("LightSampling.generateLightSample_env");
+                c.add(w0, w1); c.add(h0.next(), h1.next());
+                if (w0 && w1) { c.add(la.pdf, lb.pdf); c.add(la.origin, lb.origin); c.add(la.distance, lb.distance); c.add(la.dir, lb.dir); c.add(la.lightType, uint32_t(lb.lightType)); c.add(la.beam, lb.beam); }
+            }
+        }
+        ref::kUseEnvLight = false;
     }
 }

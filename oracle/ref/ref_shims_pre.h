@@ -62,7 +62,42 @@ struct SpectralProfile {  // Scene/Material/BasicMaterialData.slang:43-54
     float icdf[128];
 };
 
-struct BasicMaterialData { static constexpr uint no_spectral_profile = uint(-1); };  // Scene/Material/BasicMaterialData.slang:65
+// Scene/Material/BasicMaterialData.slang:65,95-138: the three members materialEvalEmissive reads
+struct TextureHandleStandIn {};
+struct BasicMaterialData {
+    static constexpr uint no_spectral_profile = uint(-1);
+    uint emissionSpectralId = no_spectral_profile;
+    TextureHandleStandIn texEmissive;
+    bool isEmissive() { return emissionSpectralId != no_spectral_profile; }
+};
+// HLSL resource types and the few engine types LightCollection.slang / the emissive samplers name
+template <class T> struct StructuredBuffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };  // a load returns a copy
+template <class T> struct Buffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };
+struct MeshLightData { uint instanceID = 0, triangleOffset = 0, triangleCount = 0, materialID = 0; };  // Scene/Lights/MeshLightData.slang:36-42 (not read by the path)
+struct GeometryInstanceID { uint index = 0; };                                                          // Scene/SceneTypes.slang:57-70
+struct SamplerState {};
+// HLSL Texture2D<T>: texel loads and SampleLevel are services of the texture unit -- provided by the caller of the comparison (the oracle's
+// importance-map mips and its fp32 bilinear filter, plt_envmap.h), not part of the text under comparison
+template <class T> struct Texture2D {
+    const void* ctx = nullptr;
+    T (*loadFn)(const void* ctx, int x, int y, int mip) = nullptr;
+    T (*sampleFn)(const void* ctx, float2 uv, float lod) = nullptr;
+    uint width = 0, height = 0;
+    T Load(int3 p) const { return loadFn(ctx, p.x, p.y, p.z); }
+    T operator[](uint2 p) const { return loadFn(ctx, int(p.x), int(p.y), 0); }
+    T SampleLevel(SamplerState, float2 uv, float lod) const { return sampleFn(ctx, uv, lod); }
+    void GetDimensions(uint& w, uint& h) const { w = width; h = height; }
+};
+struct ExplicitLodTextureSampler { float lod; };                                                        // Scene/Material/TextureSampler.slang:74-87
+// Scene/Material/MaterialSystem.slang:120-291: what materialEvalEmissive asks of the material system.  Untextured emitters only: a Uniform
+// texture handle makes sampleTexture return the `uniformValue` argument (MaterialSystem.slang:283-291)
+struct MaterialSystemStandIn {
+    const BasicMaterialData* basic = nullptr;
+    bool isBasicMaterial(uint) { return true; }
+    BasicMaterialData getBasicMaterialData(uint materialID) { return basic[materialID]; }
+    SamplerState getDefaultTextureSampler(uint) { return {}; }
+    float4 sampleTexture(TextureHandleStandIn, SamplerState, float2, float4 uniformValue, ExplicitLodTextureSampler) { return uniformValue; }
+};
 typedef uint uint32_t_;
 // Rendering/Materials/IMaterialInstance.slang:53-88 (the reference's `property` accessors are not used by the BSDF code)
 struct BSDFProperties {
@@ -84,11 +119,16 @@ static const float kRayTMax = 3.402823466e+38f;  // ShadowRays.slangh:47 (= FLT_
 struct RayDesc { float3 Origin, Direction; float TMin = 0.f, TMax = 0.f; };  // HLSL built-in (LightSample::getVisibilityRay)
 // Rendering/Lights/EnvMapSampler.slang:46-52 and EmissiveLightSamplerInterface.slang:38-49: the sample records; the two samplers
 // themselves need the texture system / the light collection and are outside this comparison -- they stand in as "no sample drawn"
-struct EnvMapSample { float3 dir; float pdf = 0.f; hwss_t Le; hwss_t wavelengths; };
 struct TriangleLightSample { uint triangleIndex = 0; float3 posW, normalW, dir; float distance = 0.f; hwss_t Le, wavelengths; float pdf = 0.f; float2 uv; };
-struct EnvMapSamplerStandIn { bool sample(float2, float, EnvMapSample&) { return false; } };
-struct EmissiveSamplerStandIn { template <class S> bool sampleLight(float3, float3, bool, S&, float, bool, TriangleLightSample&) { return false; } };
-static EnvMapSamplerStandIn envMapSampler;
+struct TriangleLightHit { uint triangleIndex = 0; float3 posW, normalW; };  // EmissiveLightSamplerInterface.slang:54-59
+// `emissiveSampler` is EmissiveUniformSampler or EmissivePowerSampler by a define (EmissiveLightSampler.slang:36-52); both are transpiled
+// further down, so the stand-in forwards to emissiveSamplerDispatch (ref_shims_post.h, found by argument-dependent lookup at instantiation),
+// which calls the transpiled sampler the comparison has selected, or draws no sample
+struct EmissiveSamplerStandIn {
+    template <class S> bool sampleLight(float3 posW, float3 normalW, bool upperHemisphere, S& sg, float wavelength, bool importanceSampleSpectrum, TriangleLightSample& ls) {
+        return emissiveSamplerDispatch(posW, normalW, upperHemisphere, sg, wavelength, importanceSampleSpectrum, ls);
+    }
+};
 static EmissiveSamplerStandIn emissiveSampler;
 
 // ---- what `measure` (pltpt_solve.rt.slang:96-147) expects: the camera block it reads (Scene/Camera/CameraData.slang:36-69, the five

@@ -35,6 +35,7 @@ template <class T> struct vec<T, 3> {
     vec() = default;
     vec(T a, T b, T c) : x(a), y(b), z(c) {}
     vec(vec<T, 2> a, T c) : x(a.x), y(a.y), z(c) {}
+    template <class U, class S, class = std::enable_if_t<!std::is_same<U, T>::value && std::is_arithmetic<S>::value>> vec(vec<U, 2> a, S c) : x(T(a.x)), y(T(a.y)), z(T(c)) {}  // int3(uint2, int)
     vec(T a, vec<T, 2> b) : x(a), y(b.x), z(b.y) {}
     template <class U, class = std::enable_if_t<std::is_arithmetic<U>::value>> vec(U s) : x(T(s)), y(T(s)), z(T(s)) {}
     template <class U> explicit vec(const vec<U, 3>& o) : x(T(o.x)), y(T(o.y)), z(T(o.z)) {}

@@ -45,10 +45,13 @@ SOURCES = [
                                       "sample_disk", "sample_cone", "sample_sphere", "sample_disk_concentric", "sample_cosine_hemisphere_concentric", "cosine_hemisphere_concentric_pdf",
                                       "sample_triangle", "sample_boxmueller", "boxmueller_pdf", "sample_boxmueller_truncated", "boxmueller_truncated_pdf", "tryInvert", "inverse",
                                       "diag2", "ident2", "diag4", "ident4", "svd_symmetric", "perp_stark", "BesselJ_saa", "BesselJ_laa", "BesselJ", "ndir_to_oct_equal_area_snorm", "oct_to_ndir_equal_area_snorm",
-                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm", "oct_wrap", "oct_to_ndir_snorm"]),
+                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm", "oct_wrap", "oct_to_ndir_snorm", "world_to_latlong_map", "latlong_map_to_world"]),
     ("Utils/Math/FormatConversion.slang", ["unpackSnorm16", "unpackSnorm2x16"]),
     ("Utils/Math/PackedFormats.slang", ["decodeNormal2x16"]),
     ("Scene/Lights/LightCollectionShared.slang", None),
+    ("Scene/Lights/LightCollection.slang", None),
+    ("Scene/Lights/EnvMapData.slang", None),
+    ("Scene/Lights/EnvMap.slang", None),
     ("Scene/SceneTypes.slang", ["StaticVertexData", "PackedStaticVertexData"]),
     ("Utils/Color/ColorHelpers.slang", ["XYZtoRGB_Rec709"]),
     ("Utils/Color/SpectrumUtils.slang", None),
@@ -62,7 +65,7 @@ SOURCES = [
     ("Utils/Color/SpectrumSampler.slang", None),
     ("Scene/Lights/LightData.slang", None),
     ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight"],
-                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera;")),
+                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap;")),
     ("Rendering/Materials/BSDFSample.slang", None),
     ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives"]),
     ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
@@ -78,6 +81,11 @@ SOURCES = [
     ("Rendering/Materials/PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", None),
     ("Rendering/Materials/PLT/PLTMultiLayeredStackBSDF.slang", None),
     ("Rendering/Lights/LightHelpers.slang", None),
+    ("Rendering/Lights/EmissiveLightSamplerHelpers.slang", None),
+    ("Rendering/Lights/EmissiveUniformSampler.slang", None),
+    ("Rendering/Lights/EmissivePowerSampler.slang", None),
+    ("Rendering/Lights/EnvMapSampler.slang", None),
+    ("literal", "static EnvMapSampler envMapSampler;  // cbuffer CB of the pass (pltpt.slangh:73)"),
     ("Utils/Geometry/GeometryHelpers.slang", ["computeRayOrigin"]),
     ("Rendering/Utils/LightsSamplingUtils.slang", None),
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
@@ -118,6 +126,8 @@ PATCHES = [
      "swizzle on the left-hand side"),
     ("Scene/SceneTypes.slang", "#else // !HOST_CODE\n    [mutating] void pack(const StaticVertexData v)", "#elif 0\n    [mutating] void pack(const StaticVertexData v)",
      "the shader-side `pack` is not used by the path (vertices arrive packed); only `unpack` is compared"),
+    ("Scene/Lights/EnvMap.slang", "return envMap[coord].rgb * getIntensity();", "return envMap[coord].xyz * getIntensity();", "`.rgb` of a texel load (R8 knows xyzw swizzles)"),
+    ("Scene/Lights/EnvMap.slang", "Texture2D       envMap;", "Texture2D<float4> envMap;", "HLSL's bare `Texture2D` is Texture2D<float4>; a C++ member needs the argument spelled out"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",
@@ -312,7 +322,7 @@ def transpile(path, s, struct_names):
     s = re.sub(r"\benum\s+class\s+(\w+)\s*:", r"enum \1 :", s)   # R13
     # R4
     s = re.sub(r"\[mutating\]\s*", "", s)
-    s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
+    s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten|root)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
     s = re.sub(r"\bno_diff\s+", "", s)
     s = re.sub(r"\bprecise\s+", "", s)          # every operation is individually rounded here anyway (-ffp-contract=off)
     s = re.sub(r"\s*\bCONST_FUNCTION\b", "", s)  # Utils/HostDeviceShared.slangh: empty in shader code
@@ -330,6 +340,7 @@ def transpile(path, s, struct_names):
         s = re.sub(rf"\b{sc}\.(?=\w)", sc + "::", s)
     s = re.sub(r"\b(\w+)\.Flags::", r"\1::Flags::", s)
     # R8
+    s = re.sub(r"\)\.rgb\b", ").xyz()", s)   # `.rgb` of a call result (materialEvalEmissive, EnvMap.eval)
     s = re.sub(r"\brgb\.r\b", "rgb.x", s)
     s = re.sub(r"\brgb\.g\b", "rgb.y", s)
     s = re.sub(r"\brgb\.b\b", "rgb.z", s)
@@ -351,6 +362,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     texts = []
     for path, what in SOURCES:
+        if path == "literal":   # a declaration the pass makes outside the transpiled files, placed between two of them
+            texts.append((path, what, True))
+            continue
         raw = read(path)
         if what == "defines":
             texts.append((path, rule_defines(raw), True))

@@ -3,7 +3,8 @@
 oracle/ref_transpile.py rewrites the reference's PLT Slang modules -- MathHelpers, SpectrumUtils, Fresnel, Mueller, PLT (the generalized
 ray), Interference, FractalSurface, GaussianSurface, Birefringence, DiffractionGrating, Scene.evalSpectrum / sampleSpectrum, the
 differential reflect / refract helpers, all ten PLT*BSDF modules, the analytic light samplers (LightData, LightHelpers), the pass's own light sampling
-(LightSampling.slangh with computeRayOrigin / computeNewRayOrigin), `measure` of the solve shader and the packed-record decoders (snorm /
+(LightSampling.slangh with computeRayOrigin / computeNewRayOrigin, over the emissive-triangle samplers, the light collection, the environment map and its
+importance sampler), `measure` of the solve shader and the packed-record decoders (snorm /
 octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) -- textually into C++ (where /root/reference lies; nothing of it is
 committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
 function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
@@ -46,7 +47,9 @@ EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "Spectrum
            [f"LightHelpers.sample{t}" for t in ("Point", "Directional", "Distant", "Rect", "Disc", "Sphere")] + \
            ["GeometryHelpers.computeRayOrigin", "ShadowRays.computeNewRayOrigin", "LightSampling.selectLightType", "LightSampling.generateLightSample_analytic",
             "pltpt_solve.measure", "pltpt_solve.MISWeight", "PackedFormats.decodeNormal2x16", "LightCollectionShared.PackedEmissiveTriangle_unpack",
-            "SceneTypes.PackedStaticVertexData_unpack"]
+            "SceneTypes.PackedStaticVertexData_unpack", "EmissiveUniformSampler.sampleLight", "EmissiveUniformSampler.evalPdf", "EmissivePowerSampler.sampleLight",
+            "EmissivePowerSampler.evalPdf", "LightSampling.generateLightSample_emissive", "EnvMap.eval_toLocal_toWorld", "EnvMapSampler.sample", "EnvMapSampler.evalPdf",
+            "LightSampling.generateLightSample_env"]
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +70,7 @@ def test_every_module_is_compared(report):
     assert not missing, missing
     thin = {k: v["n"] for k, v in report.items() if v["n"] < 10_000}
     assert not thin, thin
-    assert sum(v["n"] for v in report.values()) >= 60_000_000
+    assert sum(v["n"] for v in report.values()) >= 70_000_000
 
 
 def test_oracle_reproduces_the_reference_text(report):
@@ -82,4 +85,4 @@ def test_oracle_reproduces_the_reference_text(report):
             bad[name] = v
     assert not bad, bad
     exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
-    assert exact >= 70, exact   # of 95 compared functions / entry points
+    assert exact >= 79, exact   # of 104 compared functions / entry points
