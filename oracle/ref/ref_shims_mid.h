@@ -1,0 +1,47 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// ref_shims_mid.h -- engine plumbing that needs the transpiled BasicMaterialData / MaterialHeader / TextureHandle (included from
+// oracle/_ref/ref_gen.h, inside namespace ref, right after those): the material system as the PLT material loaders and
+// materialEvalEmissive use it, the base of the material structs, BSDFProperties.  Hand-written; every item cites what it stands in for.
+
+// Rendering/Materials/IMaterialInstance.slang:53-88 (the reference's `property` accessors are not used by the BSDF code)
+struct BSDFProperties {
+    uint emissionSpectralId = BasicMaterialData::no_spectral_profile;
+    float3 emissionRGB = .0f;
+    float3 albedo = .0f;
+    float roughness = .0f;
+    uint flags = 0;
+    enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
+};
+
+// Scene/Material/MaterialSystem.slang:120-291: what the loaders and materialEvalEmissive ask of the material system.  Material blobs are the
+// 128-byte MaterialDataBlob records (header + payload reinterpreted as BasicMaterialData, MaterialSystem.slang:150-160).  A Uniform texture
+// handle makes sampleTexture return the `uniformValue` argument (:283-291); a Texture handle is a texture-unit service: the value comes
+// from `textureFn`, supplied by the caller of the comparison.
+struct MaterialSystemStandIn {
+    const MaterialDataBlob* blobs = nullptr;
+    float4 (*textureFn)(uint textureID, uint samplerID, float2 uv) = nullptr;
+    MaterialHeader getMaterialHeader(uint materialID) const { return blobs[materialID].header; }
+    bool isBasicMaterial(uint materialID) const { return getMaterialHeader(materialID).isBasicMaterial(); }
+    BasicMaterialData getBasicMaterialData(uint materialID) const {
+        static_assert(sizeof(BasicMaterialData) <= sizeof(MaterialPayload), "BasicMaterialData must fit the payload");
+        BasicMaterialData d;
+        std::memcpy(static_cast<void*>(&d), &blobs[materialID].payload, sizeof d);
+        return d;
+    }
+    struct SamplerStateID : SamplerState { uint id = 0; };
+    SamplerState getTextureSampler(uint) const { return {}; }
+    SamplerState getDefaultTextureSampler(uint) const { return {}; }
+    float4 sampleTexture(TextureHandle handle, SamplerState, float2 uv, float4 uniformValue, ExplicitLodTextureSampler) const {
+        if (handle.getMode() == TextureHandle::Mode::Texture && textureFn) return textureFn(handle.getTextureID(), 0u, uv);
+        return uniformValue;
+    }
+};
+typedef MaterialSystemStandIn MaterialSystem;
+
+// Rendering/Materials/IMaterial.slang:91-94: the header every material struct starts with
+struct MaterialBase { MaterialHeader header; };
+// Scene/SceneTypes.slang:311-320 (evalOpacity reads texC)
+struct VertexData { float3 posW, normalW; float4 tangentW; float2 texC; float3 faceNormalW; };
+// Scene/Material/ShadingUtils.slang:199-214 -- normal mapping is NOT part of this comparison yet: the loaders' modifyTangentSpace compiles
+// against this no-op (the oracle's normal mapping is checked against closed-form frames in tests/test_oracle_textures.py)
+inline void applyNormalMap(ShadingData&, NormalMapType, float3) {}

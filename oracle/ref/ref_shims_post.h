@@ -439,15 +439,14 @@ static void ref_compare_more(int N, Rnd& r) {
         static uint32_t active[kMax], alias[2 * kMax];
         static ref::uint2 ralias[kMax];
         static PltptMaterialBlob mats[2];
-        static ref::BasicMaterialData rmats[2];
         static ref::PackedEmissiveTriangle rtris[kMax];
         static ref::EmissiveFlux rflux[kMax];
         mats[0] = PltptMaterialBlob{}; mats[1] = PltptMaterialBlob{};
         mats[0].header[0] = 1u << 31; mats[0].emissionSpectralId = 4u;                             // emissive basic material
         mats[1].header[0] = 1u << 31; mats[1].emissionSpectralId = PLTPT_NO_SPECTRAL_PROFILE;      // basic, not emissive: Le stays 0
-        rmats[0].emissionSpectralId = 4u; rmats[1].emissionSpectralId = ref::BasicMaterialData::no_spectral_profile;
         osc.d.materialData = mats; osc.d.materialCount = 2;
-        ref::gScene.materials.basic = rmats;
+        static_assert(sizeof(ref::MaterialDataBlob) == sizeof(PltptMaterialBlob) && sizeof(PltptMaterialBlob) == 128, "both sides read the same 128-byte material records");
+        ref::gScene.materials.blobs = reinterpret_cast<const ref::MaterialDataBlob*>(mats);
         ref::EmissiveUniformSampler& uniformSampler = ref::gUniformSampler;
         ref::EmissivePowerSampler& powerSampler = ref::gPowerSampler;
         static PltptLightData pointLight;
@@ -604,5 +603,77 @@ static void ref_compare_more(int N, Rnd& r) {
             }
         }
         ref::kUseEnvLight = false;
+    }
+    // ---- the ten PLT material loaders (PLT*Material.slang::setupMaterialInstance over MaterialData.slang / BasicMaterialData.slang /
+    // TextureHandle.slang): both sides unpack the SAME random 128-byte material record; the resulting BSDFs are then compared through
+    // sample / eval / pdf / lambdaPdf (the BSDF code itself is pinned above, so a difference here is a difference in unpacking)
+    {
+        static PltptMaterialBlob blob;
+        static_assert(sizeof(ref::PLTConductorMaterial) <= 128 && sizeof(ref::MaterialHeader) == 8, "material struct = header + BasicMaterialData inside the 128-byte record");
+        ref::gScene.materials.blobs = reinterpret_cast<const ref::MaterialDataBlob*>(&blob);
+        ref::gScene.materials.textureFn = nullptr;
+        orc::TextureSystem noTextures;
+        const uint32_t kTypes[10] = {PLTPT_MATERIAL_DIFFUSE, PLTPT_MATERIAL_CONDUCTOR, PLTPT_MATERIAL_DIELECTRIC, PLTPT_MATERIAL_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_THIN_DIELECTRIC,
+                                     PLTPT_MATERIAL_COATED_CONDUCTOR, PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_GRATED_CONDUCTOR, PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC,
+                                     PLTPT_MATERIAL_MULTILAYERED_STACK};
+        auto half = [&](float lo, float hi) { return uint16_t(ref::f32tof16(r.range(lo, hi))); };
+        for (int i = 0; i < N; ++i) {
+            const int kind = i % 10;
+            blob = PltptMaterialBlob{};
+            blob.header[0] = kTypes[kind] | (1u << 31);
+            for (int k = 0; k < 4; ++k) { blob.baseColor[k] = half(0.05f, 1.f); blob.specular[k] = half(0.02f, 2.5f); blob.data1[k] = half(0.05f, 3.f); blob.data2[k] = half(0.02f, 2.5f); }
+            if (r.u() < .15f) blob.specular[1] = 0;   // roughness 0 where the material keeps it there
+            if (r.u() < .15f) blob.data2[1] = 0;
+            for (int k = 0; k < 3; ++k) blob.transmission[k] = half(0.2f, 1.f);
+            blob.IoR = half(1.f, 2.2f);
+            const uint32_t n = uint32_t(r.u() * 1.999f) * 2u;
+            blob.iorNSpectralId = n; blob.iorKSpectralId = n + 1u;
+            blob.emissionSpectralId = r.u() < .2f ? 4u : PLTPT_NO_SPECTRAL_PROFILE;
+            if (kind == 7 || kind == 8) blob.data1[3] = uint16_t(((uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u)) << 8) | (1u + uint32_t(r.u() * 7.99f)));  // grating type | lobes, raw bits
+            if (kind == 9) blob.data1[3] = uint16_t(1u + uint32_t(r.u() * 11.99f));                                                                             // layer count, raw bits
+            const orc::ShadingData sd = randomShadingData(r);
+            ref::ShadingData rsd = R(sd);
+            static Pair p;
+            p.kind = kind;
+            p.o = orc::MaterialInstance(blob, sd, &table, noTextures);
+            const ref::ExplicitLodTextureSampler lod = {0.f};
+#define REF_LOAD(FIELD, TYPE) { ref::TYPE m; std::memcpy(static_cast<void*>(&m), &blob, sizeof m); p.FIELD = m.setupMaterialInstance(ref::gScene.materials, rsd, lod); }
+            switch (kind) {
+                case 0: REF_LOAD(diffuse, PLTDiffuseMaterial) break;
+                case 1: REF_LOAD(conductor, PLTConductorMaterial) break;
+                case 2: REF_LOAD(dielectric, PLTDielectricMaterial) break;
+                case 3: REF_LOAD(opaque, PLTOpaqueDielectricMaterial) break;
+                case 4: REF_LOAD(thin, PLTThinDielectricMaterial) break;
+                case 5: REF_LOAD(coatedC, PLTCoatedConductorMaterial) break;
+                case 6: REF_LOAD(coatedD, PLTCoatedOpaqueDielectricMaterial) break;
+                case 7: REF_LOAD(gratedC, PLTDiffractionGratedConductorMaterial) break;
+                case 8: REF_LOAD(gratedD, PLTDiffractionGratedOpaqueDielectricMaterial) break;
+                default: REF_LOAD(stack, PLTMultiLayeredStackMaterial) break;
+            }
+#undef REF_LOAD
+            const std::string name = std::string(kKindNames[kind]).replace(std::string(kKindNames[kind]).size() - 4, 4, "Material") + ".setupMaterialInstance";
+            Cmp c(name);
+            const float wavelength = r.range(380.f, 720.f);
+            orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 53u); RefSG g1{g0};
+            orc::BSDFSample s0; ref::BSDFSample s1;
+            s1.pdf = 1.f;  // see the BSDF loop above (grated BSDFs)
+            const bool v0 = p.o.sample(sd, g0, s0, wavelength, uint32_t(orc::L_All), orc::float3(0.f));
+            bool v1 = false;
+            REF_DISPATCH_R(p, v1, sample(rsd, g1, s1, wavelength, uint32_t(orc::L_All), ref::float3(0.f)));
+            c.add(v0, v1); c.add(g0.next(), g1.next());
+            if (v0 && v1) { c.add(s0.wo, s1.wo); c.add(s0.pdf, s1.pdf); c.add(s0.lobe, s1.lobe); c.add(s0.weight, s1.weight); }
+            const bool useSampled = v0 && v1 && r.u() < .6f;
+            const orc::float3 toEye = useSampled ? s0.wo : sd.fromLocal(r.dir());
+            const uint32_t lobe = useSampled ? s0.lobe : kLobeChoices[uint32_t(r.u() * 8.99f)];
+            ref::PLTBeam rb;
+            orc::PLTBeam b = randomBeam(r, rb);
+            b.r = -sd.V; b.t = orc::perp_stark(b.r); b.propagate(sd.posW);
+            rb = R(b);
+            ref::float4 l1; REF_DISPATCH_R(p, l1, lambdaPdf(rsd, R(toEye), lobe, rb, rb.wavelengths)); c.add(p.o.lambdaPdf(sd, toEye, lobe, b, b.wavelengths), l1);
+            p.o.eval(sd, toEye, lobe, b);
+            REF_DISPATCH(p, eval(rsd, R(toEye), lobe, rb));
+            c.add(b, rb);
+            float q1 = 0.f; const orc::float3 toLight = sd.fromLocal(r.dirUp()); REF_DISPATCH_R(p, q1, pdf(rsd, R(toLight), wavelength)); c.add(p.o.pdf(sd, toLight, wavelength), q1);
+        }
     }
 }

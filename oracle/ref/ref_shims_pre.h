@@ -5,7 +5,36 @@
 #pragma once
 #include "slang_compat.h"
 
+// Utils/HostDeviceShared.slangh:39-43,95-101 (shader branch; CONST_FUNCTION is dropped by the transpiler)
+#define EXTRACT_BITS(bits, offset, value) (((value) >> (offset)) & ((1 << (bits)) - 1))
+#define IS_BIT_SET(value, bitOffset) ((value & (1 << bitOffset)) != 0)
+#define PACK_BITS(bits, offset, flags, value) ((((value) & ((1 << (bits)) - 1)) << (offset)) | ((flags) & (~(((1 << (bits)) - 1) << (offset)))))
+#define PACK_BITS_UNSAFE(bits, offset, flags, value) (((value) << (offset)) | ((flags) & (~(((1 << (bits)) - 1) << (offset)))))
+#define SETTER_DECL
+
 namespace ref {
+
+// HLSL float16_t and its vectors as storage types: 16-bit IEEE halves that convert to fp32 exactly when read
+struct float16_t {
+    uint16_t bits = 0;
+    float16_t() = default;
+    float16_t(float f) : bits(uint16_t(f32tof16(f))) {}
+    operator float() const { return f16tof32(bits); }
+};
+inline uint16_t asuint16(float16_t h) { return h.bits; }
+inline float16_t asfloat16(uint16_t b) { float16_t h; h.bits = b; return h; }
+struct float16_t3 {
+    float16_t x, y, z;
+    float16_t3() = default;
+    float16_t3(float f) : x(f), y(f), z(f) {}
+    operator float3() const { return float3(float(x), float(y), float(z)); }
+};
+struct float16_t4 {
+    float16_t x, y, z, w;
+    float16_t4() = default;
+    float16_t4(float f) : x(f), y(f), z(f), w(f) {}
+    operator float4() const { return float4(float(x), float(y), float(z), float(w)); }
+};
 
 // Utils/HWSS.slang:33-37 with HWSS_SAMPLES = 4 (PLTPT's default `HWSS`, PLTPT.h:87)
 static const uint hwss_samples = 4;
@@ -62,14 +91,6 @@ struct SpectralProfile {  // Scene/Material/BasicMaterialData.slang:43-54
     float icdf[128];
 };
 
-// Scene/Material/BasicMaterialData.slang:65,95-138: the three members materialEvalEmissive reads
-struct TextureHandleStandIn {};
-struct BasicMaterialData {
-    static constexpr uint no_spectral_profile = uint(-1);
-    uint emissionSpectralId = no_spectral_profile;
-    TextureHandleStandIn texEmissive;
-    bool isEmissive() { return emissionSpectralId != no_spectral_profile; }
-};
 // HLSL resource types and the few engine types LightCollection.slang / the emissive samplers name
 template <class T> struct StructuredBuffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };  // a load returns a copy
 template <class T> struct Buffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };
@@ -88,26 +109,8 @@ template <class T> struct Texture2D {
     T SampleLevel(SamplerState, float2 uv, float lod) const { return sampleFn(ctx, uv, lod); }
     void GetDimensions(uint& w, uint& h) const { w = width; h = height; }
 };
-struct ExplicitLodTextureSampler { float lod; };                                                        // Scene/Material/TextureSampler.slang:74-87
-// Scene/Material/MaterialSystem.slang:120-291: what materialEvalEmissive asks of the material system.  Untextured emitters only: a Uniform
-// texture handle makes sampleTexture return the `uniformValue` argument (MaterialSystem.slang:283-291)
-struct MaterialSystemStandIn {
-    const BasicMaterialData* basic = nullptr;
-    bool isBasicMaterial(uint) { return true; }
-    BasicMaterialData getBasicMaterialData(uint materialID) { return basic[materialID]; }
-    SamplerState getDefaultTextureSampler(uint) { return {}; }
-    float4 sampleTexture(TextureHandleStandIn, SamplerState, float2, float4 uniformValue, ExplicitLodTextureSampler) { return uniformValue; }
-};
-typedef uint uint32_t_;
-// Rendering/Materials/IMaterialInstance.slang:53-88 (the reference's `property` accessors are not used by the BSDF code)
-struct BSDFProperties {
-    uint emissionSpectralId = BasicMaterialData::no_spectral_profile;
-    float3 emissionRGB = .0f;
-    float3 albedo = .0f;
-    float roughness = .0f;
-    uint flags = 0;
-    enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
-};
+struct ExplicitLodTextureSampler { float lod; };
+typedef ExplicitLodTextureSampler ITextureSampler;  // the interface the loaders take; the pass passes ExplicitLodTextureSampler{0} (Scene/Material/TextureSampler.slang:74-87)
 
 // ---- what RenderPasses/PLTPT/LightSampling.slangh expects from the pass around it
 // pltpt.slangh:95-118: the pass's compile-time switches (defines set by PLTPT.cpp:222-260) -- variables here so that the comparison can

@@ -59,6 +59,7 @@ template <class T> struct vec<T, 4> {
     T& operator[](int i) { return (&x)[i]; }
     const T& operator[](int i) const { return (&x)[i]; }
     vec<T, 2> xy() const { return {x, y}; }
+    vec<T, 2> yz() const { return {y, z}; }
     vec<T, 2> zw() const { return {z, w}; }
     vec<T, 3> xyz() const { return {x, y, z}; }
 };

@@ -64,6 +64,11 @@ SOURCES = [
     ("Rendering/Materials/PLT/Birefringence.slang", None),
     ("Utils/Color/SpectrumSampler.slang", None),
     ("Scene/Lights/LightData.slang", None),
+    ("Scene/Material/MaterialTypes.slang", None),
+    ("Scene/Material/MaterialData.slang", None),
+    ("Scene/Material/TextureHandle.slang", ["TextureHandle"]),
+    ("Scene/Material/BasicMaterialData.slang", ["BasicMaterialData"]),
+    ("literal", '#include "../ref/ref_shims_mid.h"'),
     ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight"],
                            "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap;")),
     ("Rendering/Materials/BSDFSample.slang", None),
@@ -80,6 +85,16 @@ SOURCES = [
     ("Rendering/Materials/PLT/PLTDiffractionGratedConductorBSDF.slang", None),
     ("Rendering/Materials/PLT/PLTDiffractionGratedOpaqueDielectricBSDF.slang", None),
     ("Rendering/Materials/PLT/PLTMultiLayeredStackBSDF.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffuseMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTConductorMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTDielectricMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTOpaqueDielectricMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTThinDielectricMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTCoatedConductorMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTCoatedOpaqueDielectricMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffractionGratedConductorMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTDiffractionGratedOpaqueDielectricMaterial.slang", None),
+    ("Rendering/Materials/PLT/PLTMultiLayeredStackMaterial.slang", None),
     ("Rendering/Lights/LightHelpers.slang", None),
     ("Rendering/Lights/EmissiveLightSamplerHelpers.slang", None),
     ("Rendering/Lights/EmissiveUniformSampler.slang", None),
@@ -128,6 +143,8 @@ PATCHES = [
      "the shader-side `pack` is not used by the path (vertices arrive packed); only `unpack` is compared"),
     ("Scene/Lights/EnvMap.slang", "return envMap[coord].rgb * getIntensity();", "return envMap[coord].xyz * getIntensity();", "`.rgb` of a texel load (R8 knows xyzw swizzles)"),
     ("Scene/Lights/EnvMap.slang", "Texture2D       envMap;", "Texture2D<float4> envMap;", "HLSL's bare `Texture2D` is Texture2D<float4>; a C++ member needs the argument spelled out"),
+    ("PLT/PLTDiffractionGratedConductorMaterial.slang", "const float2 invPitch = pitch>.0f ? 1.f/pitch : .0f;", "const float2 invPitch = select(pitch>.0f, 1.f/pitch, .0f);", "R11"),
+    ("PLT/PLTDiffractionGratedOpaqueDielectricMaterial.slang", "const float2 invPitch = pitch>.0f ? 1.f/pitch : .0f;", "const float2 invPitch = select(pitch>.0f, 1.f/pitch, .0f);", "R11"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",
@@ -265,7 +282,8 @@ def rule_structs(s):
             body = re.sub(rf"\b(\w+)\s+{p}\(\)\(\)\s*\{{", rf"\1 {p}() {{", body)
         body = rule_structs(body)  # nested structs
         tail = s[end:end + 1]
-        out.append(s[pos:m.start()] + f"struct {name} {{" + body + "}" + ("" if tail == ";" else ";"))
+        base = " : MaterialBase" if m.group(2) and "MaterialBase" in m.group(2) else ""   # R9: interfaces go, a real base struct stays
+        out.append(s[pos:m.start()] + f"struct {name}{base} {{" + body + "}" + ("" if tail == ";" else ";"))
         pos = end
     return "".join(out)
 
@@ -341,6 +359,10 @@ def transpile(path, s, struct_names):
     s = re.sub(r"\b(\w+)\.Flags::", r"\1::Flags::", s)
     # R8
     s = re.sub(r"\)\.rgb\b", ").xyz()", s)   # `.rgb` of a call result (materialEvalEmissive, EnvMap.eval)
+    if path.endswith("Material.slang"):   # R8: colour-named swizzles of the sampled texture values
+        s = re.sub(r"\.rgb\b", ".xyz", s)
+        s = re.sub(r"\.rg\b", ".xy", s)
+        s = re.sub(r"\.a\b", ".w", s)
     s = re.sub(r"\brgb\.r\b", "rgb.x", s)
     s = re.sub(r"\brgb\.g\b", "rgb.y", s)
     s = re.sub(r"\brgb\.b\b", "rgb.z", s)
