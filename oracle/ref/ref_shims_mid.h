@@ -28,11 +28,10 @@ struct MaterialSystemStandIn {
         std::memcpy(static_cast<void*>(&d), &blobs[materialID].payload, sizeof d);
         return d;
     }
-    struct SamplerStateID : SamplerState { uint id = 0; };
-    SamplerState getTextureSampler(uint) const { return {}; }
-    SamplerState getDefaultTextureSampler(uint) const { return {}; }
-    float4 sampleTexture(TextureHandle handle, SamplerState, float2 uv, float4 uniformValue, ExplicitLodTextureSampler) const {
-        if (handle.getMode() == TextureHandle::Mode::Texture && textureFn) return textureFn(handle.getTextureID(), 0u, uv);
+    SamplerState getTextureSampler(uint samplerID) const { SamplerState s; s.id = samplerID; return s; }
+    SamplerState getDefaultTextureSampler(uint materialID) const { return getTextureSampler(getMaterialHeader(materialID).getDefaultTextureSamplerID()); }
+    float4 sampleTexture(TextureHandle handle, SamplerState s, float2 uv, float4 uniformValue, ExplicitLodTextureSampler) const {
+        if (handle.getMode() == TextureHandle::Mode::Texture && textureFn) return textureFn(handle.getTextureID(), s.id, uv);
         return uniformValue;
     }
 };
@@ -42,6 +41,3 @@ typedef MaterialSystemStandIn MaterialSystem;
 struct MaterialBase { MaterialHeader header; };
 // Scene/SceneTypes.slang:311-320 (evalOpacity reads texC)
 struct VertexData { float3 posW, normalW; float4 tangentW; float2 texC; float3 faceNormalW; };
-// Scene/Material/ShadingUtils.slang:199-214 -- normal mapping is NOT part of this comparison yet: the loaders' modifyTangentSpace compiles
-// against this no-op (the oracle's normal mapping is checked against closed-form frames in tests/test_oracle_textures.py)
-inline void applyNormalMap(ShadingData&, NormalMapType, float3) {}

@@ -5,6 +5,12 @@
 #pragma once
 
 namespace ref {
+// the texture unit behind MaterialSystemStandIn::sampleTexture for Texture-mode handles: the oracle's filter over the oracle's texture table
+static const orc::TextureSystem* gTextureService = nullptr;
+inline float4 textureServiceFn(uint textureID, uint samplerID, float2 uv) {
+    const orc::float4 v = gTextureService->sampleTexture((1u << 29) | textureID, samplerID, orc::float2(uv.x, uv.y), orc::float4(0.f));
+    return float4(v.x, v.y, v.z, v.w);
+}
 // which transpiled emissive sampler LightSampling.slangh's `emissiveSampler` stands for: 0 = none (no sample drawn), 1 = uniform, 2 = power
 static int gEmissiveKind = 0;
 static EmissiveUniformSampler gUniformSampler;
@@ -19,7 +25,7 @@ template <class S> bool emissiveSamplerDispatch(float3 posW, float3 normalW, boo
 namespace {
 ref::ShadingData R(const orc::ShadingData& s) {
     ref::ShadingData o;
-    o.posW = R(s.posW); o.V = R(s.V); o.N = R(s.N); o.T = R(s.T); o.B = R(s.B); o.faceN = R(s.faceN); o.uv = R(s.uv); o.frontFacing = s.frontFacing; o.materialID = s.materialID;
+    o.posW = R(s.posW); o.V = R(s.V); o.N = R(s.N); o.T = R(s.T); o.B = R(s.B); o.faceN = R(s.faceN); o.uv = R(s.uv); o.frontFacing = s.frontFacing; o.materialID = s.materialID; o.tangentW = R(s.tangentW); o.opacity = s.opacity;
     return o;
 }
 ref::PLTBeam R(const orc::PLTBeam& b) {
@@ -675,5 +681,116 @@ static void ref_compare_more(int N, Rnd& r) {
             c.add(b, rb);
             float q1 = 0.f; const orc::float3 toLight = sd.fromLocal(r.dirUp()); REF_DISPATCH_R(p, q1, pdf(rsd, R(toLight), wavelength)); c.add(p.o.pdf(sd, toLight, wavelength), q1);
         }
+    }
+    // ---- shading data at a hit and textured material slots: MaterialFactory.slang:79-131 prepareShadingData, composed here from the
+    // transpiled pieces in the reference's order -- ShadingUtils.slang computeTangentSpace (ShadingFrame::orthonormalizeSafe), the loaders'
+    // evalOpacity and modifyTangentSpace (applyNormalMap / computeShadingFrameFromNormalMap, RGB and RG maps), the double-sided flip -- and the
+    // loaders' setupMaterialInstance on that shading data with Texture-mode handles (the filter is a texture-unit service: the oracle's)
+    {
+        static orc::Scene osc;
+        osc.profiles = table;
+        static PltptMaterialBlob blob;
+        constexpr int kTex = 3;
+        static float texels[kTex][4 * 4 * 4];
+        static PltptTextureDesc tex[kTex];
+        static PltptSamplerDesc smp[2];
+        for (int t = 0; t < kTex; ++t) {
+            for (int k = 0; k < 64; ++k) texels[t][k] = r.range(0.05f, 1.f);
+            tex[t] = PltptTextureDesc{texels[t], 4u, 4u, PLTPT_TEXTURE_FORMAT_RGBA32_FLOAT, 0u};
+        }
+        smp[0] = PltptSamplerDesc{PLTPT_FILTER_LINEAR, 0u, 0u, 0u, {0.f, 0.f, 0.f, 0.f}};   // linear, wrap
+        smp[1] = PltptSamplerDesc{PLTPT_FILTER_POINT, 2u, 1u, 0u, {0.f, 0.f, 0.f, 0.f}};    // point, clamp / mirror
+        osc.textures.textures = tex; osc.textures.textureCount = kTex; osc.textures.samplers = smp; osc.textures.samplerCount = 2;
+        osc.d.materialData = &blob; osc.d.materialCount = 1;
+        ref::gTextureService = &osc.textures;
+        ref::gScene.materials.blobs = reinterpret_cast<const ref::MaterialDataBlob*>(&blob);
+        ref::gScene.materials.textureFn = ref::textureServiceFn;
+        const uint32_t kTypes[10] = {PLTPT_MATERIAL_DIFFUSE, PLTPT_MATERIAL_CONDUCTOR, PLTPT_MATERIAL_DIELECTRIC, PLTPT_MATERIAL_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_THIN_DIELECTRIC,
+                                     PLTPT_MATERIAL_COATED_CONDUCTOR, PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_GRATED_CONDUCTOR, PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC,
+                                     PLTPT_MATERIAL_MULTILAYERED_STACK};
+        auto half = [&](float lo, float hi) { return uint16_t(ref::f32tof16(r.range(lo, hi))); };
+        auto handle = [&]() { return r.u() < .35f ? ((1u << 29) | uint32_t(r.u() * (kTex - 0.001f))) : 0u; };
+        for (int i = 0; i < N; ++i) {
+            const int kind = i % 10;
+            blob = PltptMaterialBlob{};
+            blob.header[0] = kTypes[kind] | (1u << 31) | (r.u() < .5f ? (1u << 28) : 0u);                 // basic material, double-sided or not
+            blob.header[1] = (r.u() < .5f ? 1u : 0u) << 17;                                                // default texture sampler 0 or 1
+            blob.flags = uint32_t(r.u() * 2.999f) << 1;                                                    // NormalMapType None / RGB / RG
+            for (int k = 0; k < 4; ++k) { blob.baseColor[k] = half(0.05f, 1.f); blob.specular[k] = half(0.02f, 2.5f); blob.data1[k] = half(0.05f, 3.f); blob.data2[k] = half(0.02f, 2.5f); }
+            for (int k = 0; k < 3; ++k) blob.transmission[k] = half(0.2f, 1.f);
+            blob.IoR = half(1.f, 2.2f);
+            const uint32_t n = uint32_t(r.u() * 1.999f) * 2u;
+            blob.iorNSpectralId = n; blob.iorKSpectralId = n + 1u; blob.emissionSpectralId = PLTPT_NO_SPECTRAL_PROFILE;
+            if (kind == 7 || kind == 8) blob.data1[3] = uint16_t(((uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u)) << 8) | (1u + uint32_t(r.u() * 7.99f)));
+            if (kind == 9) blob.data1[3] = uint16_t(1u + uint32_t(r.u() * 11.99f));
+            blob.texBaseColor = handle(); blob.texSpecular = handle(); blob.texData1 = handle(); blob.texData2 = handle(); blob.texTransmission = handle(); blob.texNormalMap = handle();
+            // a hit: interpolated vertex data (unit normal, tangent valid / zero sign / parallel to the normal), view direction on either side
+            orc::VertexData v;
+            v.posW = r.f3(-3.f, 3.f); v.normalW = r.dir(); v.texC = r.f2(-1.5f, 2.5f);
+            v.faceNormalW = orc::normalize(v.normalW + r.f3(-.3f, .3f));
+            const float tsel = r.u();
+            const orc::float3 tdir = tsel < .1f ? v.normalW : (tsel < .15f ? orc::float3(0.f) : r.dir());
+            v.tangentW = orc::float4(tdir.x, tdir.y, tdir.z, tsel < .8f ? (r.u() < .5f ? 1.f : -1.f) : 0.f);
+            const orc::float3 viewDir = r.dir();
+            const orc::ShadingData sd = osc.prepareShadingData(v, 0u, viewDir);
+            // the reference's sequence (MaterialFactory.slang:79-131)
+            ref::VertexData rv;
+            rv.posW = R(v.posW); rv.normalW = R(v.normalW); rv.faceNormalW = R(v.faceNormalW); rv.tangentW = R(v.tangentW); rv.texC = R(v.texC);
+            ref::ShadingData rsd = {};
+            rsd.posW = rv.posW; rsd.uv = rv.texC; rsd.V = R(viewDir); rsd.N = rv.normalW;
+            const bool validTangentSpace = ref::computeTangentSpace(rsd, rv.tangentW);
+            rsd.tangentW = validTangentSpace ? rv.tangentW : ref::float4(rsd.T, 1.f);
+            rsd.faceN = rv.faceNormalW;
+            rsd.frontFacing = ref::dot(rsd.V, rsd.faceN) >= 0.f;
+            rsd.materialID = 0;
+            const ref::ExplicitLodTextureSampler lod = {0.f};
+            ref::MaterialHeader header = ref::gScene.materials.getMaterialHeader(0);
+            static Pair p;
+            p.kind = kind;
+#define REF_MATERIAL(FIELD, TYPE) { ref::TYPE m; std::memcpy(static_cast<void*>(&m), &blob, sizeof m); rsd.opacity = m.evalOpacity(ref::gScene.materials, rv, lod); \
+                if (validTangentSpace) m.modifyTangentSpace(ref::gScene.materials, lod, rsd); \
+                if (!rsd.frontFacing && header.isDoubleSided()) rsd.N = -rsd.N; \
+                p.FIELD = m.setupMaterialInstance(ref::gScene.materials, rsd, lod); }
+            switch (kind) {
+                case 0: REF_MATERIAL(diffuse, PLTDiffuseMaterial) break;
+                case 1: REF_MATERIAL(conductor, PLTConductorMaterial) break;
+                case 2: REF_MATERIAL(dielectric, PLTDielectricMaterial) break;
+                case 3: REF_MATERIAL(opaque, PLTOpaqueDielectricMaterial) break;
+                case 4: REF_MATERIAL(thin, PLTThinDielectricMaterial) break;
+                case 5: REF_MATERIAL(coatedC, PLTCoatedConductorMaterial) break;
+                case 6: REF_MATERIAL(coatedD, PLTCoatedOpaqueDielectricMaterial) break;
+                case 7: REF_MATERIAL(gratedC, PLTDiffractionGratedConductorMaterial) break;
+                case 8: REF_MATERIAL(gratedD, PLTDiffractionGratedOpaqueDielectricMaterial) break;
+                default: REF_MATERIAL(stack, PLTMultiLayeredStackMaterial) break;
+            }
+#undef REF_MATERIAL
+            { Cmp c("MaterialFactory.prepareShadingData");
+              c.add(sd.posW, rsd.posW); c.add(sd.V, rsd.V); c.add(sd.N, rsd.N); c.add(sd.T, rsd.T); c.add(sd.B, rsd.B); c.add(sd.tangentW, rsd.tangentW); c.add(sd.faceN, rsd.faceN);
+              c.add(sd.uv, rsd.uv); c.add(sd.frontFacing, rsd.frontFacing); c.add(sd.opacity, rsd.opacity); }
+            p.o = osc.getMaterialInstance(sd);
+            Cmp c("PLTMaterials.setupMaterialInstance_textured");
+            const float wavelength = r.range(380.f, 720.f);
+            orc::SampleGenerator g0(uint32_t(i & 0xffff), uint32_t(i >> 16), 59u); RefSG g1{g0};
+            orc::BSDFSample s0; ref::BSDFSample s1;
+            s1.pdf = 1.f;
+            const bool v0 = p.o.sample(sd, g0, s0, wavelength, uint32_t(orc::L_All), orc::float3(0.f));
+            bool v1 = false;
+            REF_DISPATCH_R(p, v1, sample(rsd, g1, s1, wavelength, uint32_t(orc::L_All), ref::float3(0.f)));
+            c.add(v0, v1); c.add(g0.next(), g1.next());
+            if (v0 && v1) { c.add(s0.wo, s1.wo); c.add(s0.pdf, s1.pdf); c.add(s0.lobe, s1.lobe); c.add(s0.weight, s1.weight); }
+            const bool useSampled = v0 && v1 && r.u() < .6f;
+            const orc::float3 toEye = useSampled ? s0.wo : sd.fromLocal(r.dir());
+            const uint32_t lobe = useSampled ? s0.lobe : kLobeChoices[uint32_t(r.u() * 8.99f)];
+            if (kind == 9) continue;   // the multilayer stack's eval has its own relative bound (above); its unpacking is covered by sample() and by the untextured run
+            ref::PLTBeam rb;
+            orc::PLTBeam b = randomBeam(r, rb);
+            b.r = -sd.V; b.t = orc::perp_stark(b.r); b.propagate(sd.posW);
+            rb = R(b);
+            p.o.eval(sd, toEye, lobe, b);
+            REF_DISPATCH(p, eval(rsd, R(toEye), lobe, rb));
+            c.add(b, rb);
+        }
+        ref::gScene.materials.textureFn = nullptr;
+        osc.d.materialData = nullptr; osc.d.materialCount = 0;
     }
 }

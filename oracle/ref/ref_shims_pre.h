@@ -62,9 +62,11 @@ template <class S> float3 sampleNext3D(S& sg) {
 // Scene/ShadingData.slang:46-107: the fields and the two frame transforms the PLT BSDFs use
 struct ShadingData {
     float3 posW, V, N, T, B, faceN;
+    float4 tangentW;
     float2 uv;
     bool frontFacing = true;
     uint materialID = 0;
+    float opacity = 1.f;
     float3 fromLocal(float3 v) const { return T * v.x + B * v.y + N * v.z; }
     float3 toLocal(float3 v) const { return float3(dot(v, T), dot(v, B), dot(v, N)); }
 };
@@ -96,7 +98,7 @@ template <class T> struct StructuredBuffer { const T* p = nullptr; T operator[](
 template <class T> struct Buffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };
 struct MeshLightData { uint instanceID = 0, triangleOffset = 0, triangleCount = 0, materialID = 0; };  // Scene/Lights/MeshLightData.slang:36-42 (not read by the path)
 struct GeometryInstanceID { uint index = 0; };                                                          // Scene/SceneTypes.slang:57-70
-struct SamplerState {};
+struct SamplerState { uint id = 0; };  // the sampler's index in the material system's table, so that the texture service can honour it
 // HLSL Texture2D<T>: texel loads and SampleLevel are services of the texture unit -- provided by the caller of the comparison (the oracle's
 // importance-map mips and its fp32 bilinear filter, plt_envmap.h), not part of the text under comparison
 template <class T> struct Texture2D {

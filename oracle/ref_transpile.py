@@ -69,6 +69,7 @@ SOURCES = [
     ("Scene/Material/TextureHandle.slang", ["TextureHandle"]),
     ("Scene/Material/BasicMaterialData.slang", ["BasicMaterialData"]),
     ("literal", '#include "../ref/ref_shims_mid.h"'),
+    ("Scene/Material/ShadingUtils.slang", ["ShadingFrame", "rgbToNormal", "rgToNormal", "computeShadingFrameFromNormalMap", "applyNormalMap", "computeTangentSpace"]),
     ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight"],
                            "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap;")),
     ("Rendering/Materials/BSDFSample.slang", None),
@@ -145,6 +146,9 @@ PATCHES = [
     ("Scene/Lights/EnvMap.slang", "Texture2D       envMap;", "Texture2D<float4> envMap;", "HLSL's bare `Texture2D` is Texture2D<float4>; a C++ member needs the argument spelled out"),
     ("PLT/PLTDiffractionGratedConductorMaterial.slang", "const float2 invPitch = pitch>.0f ? 1.f/pitch : .0f;", "const float2 invPitch = select(pitch>.0f, 1.f/pitch, .0f);", "R11"),
     ("PLT/PLTDiffractionGratedOpaqueDielectricMaterial.slang", "const float2 invPitch = pitch>.0f ? 1.f/pitch : .0f;", "const float2 invPitch = select(pitch>.0f, 1.f/pitch, .0f);", "R11"),
+    ("Scene/Material/ShadingUtils.slang", "    __init() {}\n", "", "the transpiler already emits a defaulted default constructor for a struct with __init (R3)"),
+    ("Scene/Material/ShadingUtils.slang", "n.xy = rg * 2.f - 1.f;", "{ const float2 nxy = rg * 2.f - 1.f; n.x = nxy.x; n.y = nxy.y; }", "swizzle on the left-hand side"),
+    ("Scene/Material/ShadingUtils.slang", "mapN = rgToNormal(encodedNormal.rg);", "mapN = rgToNormal(encodedNormal.xy);", "colour-named swizzle (R8)"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",

@@ -5,7 +5,8 @@ ray), Interference, FractalSurface, GaussianSurface, Birefringence, DiffractionG
 differential reflect / refract helpers, all ten PLT*BSDF modules, the analytic light samplers (LightData, LightHelpers), the pass's own light sampling
 (LightSampling.slangh with computeRayOrigin / computeNewRayOrigin, over the emissive-triangle samplers, the light collection, the environment map and its
 importance sampler), the ten PLT material loaders (PLT*Material.slang over MaterialData / BasicMaterialData / TextureHandle: both sides unpack
-the same 128-byte records), `measure` of the solve shader and the packed-record decoders (snorm /
+the same 128-byte records, with Uniform and with Texture-mode handles), the shading data at a hit (MaterialFactory.slang prepareShadingData composed
+from ShadingUtils.slang: tangent-space orthonormalisation, RGB / RG normal maps, opacity, double-sided flip), `measure` of the solve shader and the packed-record decoders (snorm /
 octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) -- textually into C++ (where /root/reference lies; nothing of it is
 committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
 function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
@@ -39,6 +40,7 @@ ULP = {
 for _m, _b in (("Conductor", 1024), ("Dielectric", 1024), ("OpaqueDielectric", 1024), ("CoatedConductor", 1024), ("CoatedOpaqueDielectric", 1024),
                ("DiffractionGratedConductor", 1024), ("DiffractionGratedOpaqueDielectric", 1024)):
     ULP[f"PLT{_m}Material.setupMaterialInstance"] = _b
+ULP["PLTMaterials.setupMaterialInstance_textured"] = 1024
 # relative bound instead of an ulp bound: the multilayer stack's interference sum (correctly rounded phasors in the oracle)
 REL = {"PLTMultiLayeredStackBSDF.eval": 5e-3, "PLTMultiLayeredStackMaterial.setupMaterialInstance": 5e-3}
 
@@ -56,7 +58,8 @@ EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "Spectrum
             "EmissivePowerSampler.evalPdf", "LightSampling.generateLightSample_emissive", "EnvMap.eval_toLocal_toWorld", "EnvMapSampler.sample", "EnvMapSampler.evalPdf",
             "LightSampling.generateLightSample_env"] + \
            [f"PLT{m}Material.setupMaterialInstance" for m in ("Diffuse", "Conductor", "Dielectric", "OpaqueDielectric", "ThinDielectric", "CoatedConductor", "CoatedOpaqueDielectric",
-                                                               "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack")]
+                                                               "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack")] + \
+           ["MaterialFactory.prepareShadingData", "PLTMaterials.setupMaterialInstance_textured"]
 
 
 @pytest.fixture(scope="module")
@@ -92,4 +95,4 @@ def test_oracle_reproduces_the_reference_text(report):
             bad[name] = v
     assert not bad, bad
     exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
-    assert exact >= 82, exact   # of 114 compared functions / entry points
+    assert exact >= 83, exact   # of 116 compared functions / entry points
