@@ -40,4 +40,4 @@ typedef MaterialSystemStandIn MaterialSystem;
 // Rendering/Materials/IMaterial.slang:91-94: the header every material struct starts with
 struct MaterialBase { MaterialHeader header; };
 // Scene/SceneTypes.slang:311-320 (evalOpacity reads texC)
-struct VertexData { float3 posW, normalW; float4 tangentW; float2 texC; float3 faceNormalW; };
+struct VertexData { float3 posW, normalW; float4 tangentW; float2 texC; float3 faceNormalW; float curveRadius = 0.f; };

@@ -793,4 +793,78 @@ static void ref_compare_more(int N, Rnd& r) {
         ref::gScene.materials.textureFn = nullptr;
         osc.d.materialData = nullptr; osc.d.materialCount = 0;
     }
+    // ---- interpolated vertex data at a hit: Scene.slang computeVertexData + getFaceNormalInObjectSpace (barycentric interpolation of the
+    // unpacked vertices, object -> world by the instance's matrices, face normal by winding) against the oracle's getVertexData on a
+    // one-triangle scene (16- and 32-bit index buffers and non-indexed meshes are the oracle's own fetch: test_gpu_trace / test_ingest)
+    {
+        static orc::Scene osc;
+        static PltptPackedVertex verts[3];
+        static PltptGeometryInstance inst;
+        static PltptMeshDesc mesh;
+        static float world[16], worldIT[16];
+        osc.d.vertices = verts; osc.d.vertexCount = 3; osc.d.geometryInstances = &inst; osc.d.instanceCount = 1; osc.d.meshes = &mesh; osc.d.meshCount = 1;
+        osc.d.worldMatrices = world; osc.d.inverseTransposeWorldMatrices = worldIT; osc.d.matrixCount = 1;
+        auto halfBits = [&](float lo, float hi) { return ref::f32tof16(r.range(lo, hi)); };
+        for (int i = 0; i < N; ++i) {
+            ref::StaticVertexData rvs[3];
+            for (int k = 0; k < 3; ++k) {
+                const orc::float3 pos = r.f3(-5.f, 5.f); const orc::float2 tc = r.f2(-2.f, 3.f);
+                const float sgn = r.u() < .2f ? 0.f : (r.u() < .5f ? -1.f : 1.f);
+                const uint32_t w0 = halfBits(-1.f, 1.f) | (halfBits(-1.f, 1.f) << 16), w1 = halfBits(-1.f, 1.f) | (ref::f32tof16(sgn) << 16), w2 = r.g();
+                for (int a = 0; a < 3; ++a) verts[k].position[a] = pos[a];
+                verts[k].texCrd[0] = tc.x; verts[k].texCrd[1] = tc.y;
+                verts[k].packedNormalTangentCurveRadius[0] = w0; verts[k].packedNormalTangentCurveRadius[1] = w1; verts[k].packedNormalTangentCurveRadius[2] = w2;
+                ref::PackedStaticVertexData pv;
+                pv.position = R(pos); pv.texCrd = R(tc);
+                pv.packedNormalTangentCurveRadius = ref::float3(ref::asfloat(ref::uint(w0)), ref::asfloat(ref::uint(w1)), ref::asfloat(ref::uint(w2)));
+                rvs[k] = pv.unpack();
+            }
+            inst = PltptGeometryInstance{}; mesh = PltptMeshDesc{};
+            const bool cw = r.u() < .5f;
+            inst.flags = cw ? PLTPT_INSTANCE_FLAG_OBJECT_FRONT_FACE_CW : 0u;
+            const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex), sc = r.f3(0.3f, 2.5f), tr = r.f3(-4.f, 4.f);
+            const orc::float3 cols[3] = {ex * sc.x, ey * sc.y, ez * sc.z}, colsIT[3] = {ex / sc.x, ey / sc.y, ez / sc.z};
+            ref::float4x4 wm; ref::float3x3 wit;
+            for (int row = 0; row < 3; ++row) {
+                for (int c = 0; c < 3; ++c) { world[4 * row + c] = cols[c][row]; worldIT[4 * row + c] = colsIT[c][row]; wm[row][c] = world[4 * row + c]; wit[row][c] = worldIT[4 * row + c]; }
+                world[4 * row + 3] = tr[row]; worldIT[4 * row + 3] = 0.f; wm[row][3] = tr[row];
+            }
+            for (int c = 0; c < 4; ++c) { world[12 + c] = worldIT[12 + c] = c == 3 ? 1.f : 0.f; wm[3][c] = world[12 + c]; }
+            orc::TriangleHit hit;
+            hit.instanceID = 0; hit.primitiveIndex = 0;
+            const orc::float3 bary = orc::sample_triangle(r.f2(0.f, 1.f));
+            hit.barycentrics = orc::float2(bary.y, bary.z);
+            const orc::float3 w = hit.getBarycentricWeights();
+            const orc::VertexData a = osc.getVertexData(hit);
+            ref::VertexData b = ref::gScene.computeVertexData(rvs, wm, wit, cw, R(w));
+            Cmp c("Scene.computeVertexData");
+            c.add(a.posW, b.posW); c.add(a.normalW, b.normalW); c.add(a.faceNormalW, b.faceNormalW); c.add(a.tangentW, b.tangentW); c.add(a.texC, b.texC);
+        }
+        osc.d.vertices = nullptr; osc.d.vertexCount = 0; osc.d.instanceCount = 0; osc.d.meshCount = 0; osc.d.matrixCount = 0;
+    }
+    // ---- primary rays and Russian roulette: Camera.slang computeRayPinhole over CameraData.slang (both sides read the same 656-byte camera
+    // block, jitter included), pltpt.slangh RR
+    {
+        static orc::Scene osc;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};
+        static_assert(sizeof(ref::CameraData) == sizeof(PltptCameraData) && sizeof(PltptCameraData) == 656, "CameraData is the 656-byte block of include/pltpt.h");
+        for (int i = 0; i < N; ++i) {
+            PltptCameraData cam{};
+            float* words = reinterpret_cast<float*>(&cam);
+            for (size_t k = 0; k < sizeof(cam) / 4; ++k) words[k] = r.range(-2.f, 2.f);   // every field random: a misplaced one would be picked up
+            cam.jitterX = r.range(-.5f, .5f) / 1920.f; cam.jitterY = r.range(-.5f, .5f) / 1080.f;
+            integ.cam = cam;
+            const uint32_t w = 16u + uint32_t(r.u() * 4000.f), h = 16u + uint32_t(r.u() * 2200.f);
+            integ.width = w; integ.height = h;
+            std::memcpy(static_cast<void*>(&ref::gScene.camera.data), &cam, sizeof cam);
+            const uint32_t px = uint32_t(r.u() * (w - 0.001f)), py = uint32_t(r.u() * (h - 0.001f));
+            orc::float3 o, d;
+            integ.computeRayPinhole(px, py, o, d);
+            ref::Ray ray = ref::gScene.camera.computeRayPinhole(ref::uint2(px, py), ref::uint2(w, h));
+            { Cmp c("Camera.computeRayPinhole"); c.add(o, ray.origin); c.add(d, ray.dir); }
+            { Cmp c("pltpt.RR"); const float v = r.u(), e = r.range(0.2f, 3.f), u = r.u(); c.add(orc::Integrator::RR(v, e, u), ref::RR(v, e, u)); }
+        }
+    }
 }

@@ -121,7 +121,7 @@ static bool kUseEnvLight = false, kUseEmissiveLights = false, kUseAnalyticLights
 static const bool kForceFullyCoherent = false;
 static float kSourcingAreaFromEmissiveGeometry = 1.f, kSourcingMaxBeamOmega = .025f;
 static const float kRayTMax = 3.402823466e+38f;  // ShadowRays.slangh:47 (= FLT_MAX)
-struct RayDesc { float3 Origin, Direction; float TMin = 0.f, TMax = 0.f; };  // HLSL built-in (LightSample::getVisibilityRay)
+struct RayDesc { float3 Origin; float TMin = 0.f; float3 Direction; float TMax = 0.f; };  // HLSL built-in (LightSample::getVisibilityRay, Ray::toRayDesc)
 // Rendering/Lights/EnvMapSampler.slang:46-52 and EmissiveLightSamplerInterface.slang:38-49: the sample records; the two samplers
 // themselves need the texture system / the light collection and are outside this comparison -- they stand in as "no sample drawn"
 struct TriangleLightSample { uint triangleIndex = 0; float3 posW, normalW, dir; float distance = 0.f; hwss_t Le, wavelengths; float pdf = 0.f; float2 uv; };
@@ -136,10 +136,7 @@ struct EmissiveSamplerStandIn {
 };
 static EmissiveSamplerStandIn emissiveSampler;
 
-// ---- what `measure` (pltpt_solve.rt.slang:96-147) expects: the camera block it reads (Scene/Camera/CameraData.slang:36-69, the five
-// fields used), the solve payload (Path.slang:200-225, without its generators), two more switches of pltpt.slangh:95-104
-struct CameraData { float3 posW, cameraU, cameraV, cameraW; float polarizer = 0.f, polarizerTheta = 0.f; };
-struct Camera { CameraData data; };
+// ---- what `measure` (pltpt_solve.rt.slang:96-147) expects (the camera block is the transpiled CameraData.slang / Camera.slang): the solve payload (Path.slang:200-225, without its generators), two more switches of pltpt.slangh:95-104
 struct PLTSolve { float3 Lrgb = .0f; float3 pathOrigin, pathNormal; float wavelength = 0.f; };
 static bool kUseDirectLights = true, mHWSSDoMIS = true;
 #define DO_DEBUG_VIEW 0

@@ -64,13 +64,16 @@ SOURCES = [
     ("Rendering/Materials/PLT/Birefringence.slang", None),
     ("Utils/Color/SpectrumSampler.slang", None),
     ("Scene/Lights/LightData.slang", None),
+    ("Scene/Camera/CameraData.slang", None),
+    ("Utils/Math/Ray.slang", ["Ray"]),
+    ("Scene/Camera/Camera.slang", None),
     ("Scene/Material/MaterialTypes.slang", None),
     ("Scene/Material/MaterialData.slang", None),
     ("Scene/Material/TextureHandle.slang", ["TextureHandle"]),
     ("Scene/Material/BasicMaterialData.slang", ["BasicMaterialData"]),
     ("literal", '#include "../ref/ref_shims_mid.h"'),
     ("Scene/Material/ShadingUtils.slang", ["ShadingFrame", "rgbToNormal", "rgToNormal", "computeShadingFrameFromNormalMap", "applyNormalMap", "computeTangentSpace"]),
-    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight"],
+    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getFaceNormalInObjectSpace", "computeVertexData"],
                            "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap;")),
     ("Rendering/Materials/BSDFSample.slang", None),
     ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives"]),
@@ -107,6 +110,7 @@ SOURCES = [
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
     ("../RenderPasses/PLTPT/LightSampling.slangh", None),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
+    ("../RenderPasses/PLTPT/pltpt.slangh", ["RR"]),
 ]
 
 STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
@@ -149,6 +153,9 @@ PATCHES = [
     ("Scene/Material/ShadingUtils.slang", "    __init() {}\n", "", "the transpiler already emits a defaulted default constructor for a struct with __init (R3)"),
     ("Scene/Material/ShadingUtils.slang", "n.xy = rg * 2.f - 1.f;", "{ const float2 nxy = rg * 2.f - 1.f; n.x = nxy.x; n.y = nxy.y; }", "swizzle on the left-hand side"),
     ("Scene/Material/ShadingUtils.slang", "mapN = rgToNormal(encodedNormal.rg);", "mapN = rgToNormal(encodedNormal.xy);", "colour-named swizzle (R8)"),
+    ("Scene/Scene.slang", "v.tangentW.xyz = mul((float3x3)worldMat, v.tangentW.xyz);", "{ const float3 txyz = mul((float3x3)worldMat, v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }",
+     "swizzle on the left-hand side"),
+    ("Scene/Scene.slang", "v.tangentW.xyz = normalize(v.tangentW.xyz);", "{ const float3 txyz = normalize(v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }", "swizzle on the left-hand side"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",
