@@ -41,3 +41,10 @@ typedef MaterialSystemStandIn MaterialSystem;
 struct MaterialBase { MaterialHeader header; };
 // Scene/SceneTypes.slang:311-320 (evalOpacity reads texC)
 struct VertexData { float3 posW, normalW; float4 tangentW; float2 texC; float3 faceNormalW; float curveRadius = 0.f; };
+// Scene/HitInfo.slang:66-123: the three fields of a triangle hit and its barycentric weights (the packed form is the pass's own business)
+struct TriangleHit {
+    GeometryInstanceID instanceID;
+    uint primitiveIndex = 0;
+    float2 barycentrics;
+    float3 getBarycentricWeights() { return float3(1.f - barycentrics.x - barycentrics.y, barycentrics.x, barycentrics.y); }
+};

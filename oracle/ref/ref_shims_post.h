@@ -837,8 +837,33 @@ static void ref_compare_more(int N, Rnd& r) {
             const orc::float3 w = hit.getBarycentricWeights();
             const orc::VertexData a = osc.getVertexData(hit);
             ref::VertexData b = ref::gScene.computeVertexData(rvs, wm, wit, cw, R(w));
-            Cmp c("Scene.computeVertexData");
-            c.add(a.posW, b.posW); c.add(a.normalW, b.normalW); c.add(a.faceNormalW, b.faceNormalW); c.add(a.tangentW, b.tangentW); c.add(a.texC, b.texC);
+            { Cmp c("Scene.computeVertexData");
+              c.add(a.posW, b.posW); c.add(a.normalW, b.normalW); c.add(a.faceNormalW, b.faceNormalW); c.add(a.tangentW, b.tangentW); c.add(a.texC, b.texC); }
+            // DifferentialShadingGeometry.slang differentialShadingGeometry: positions, normals and tangent frame with their uv-derivatives at the
+            // hit (the manifold solver's geometry); one run in five with all texture coordinates zero (its fallback parameterisation)
+            {
+                const bool zeroUV = (i % 5) == 0;
+                static ref::PackedStaticVertexData rpacked[3];
+                for (int k = 0; k < 3; ++k) {
+                    if (zeroUV) { verts[k].texCrd[0] = 0.f; verts[k].texCrd[1] = 0.f; }
+                    rpacked[k].position = ref::float3(verts[k].position[0], verts[k].position[1], verts[k].position[2]);
+                    rpacked[k].texCrd = ref::float2(verts[k].texCrd[0], verts[k].texCrd[1]);
+                    const uint32_t* pk = verts[k].packedNormalTangentCurveRadius;
+                    rpacked[k].packedNormalTangentCurveRadius = ref::float3(ref::asfloat(ref::uint(pk[0])), ref::asfloat(ref::uint(pk[1])), ref::asfloat(ref::uint(pk[2])));
+                }
+                ref::gScene.vertices.p = rpacked;
+                ref::gScene.indexFn = [](ref::GeometryInstanceID, ref::uint) { return ref::uint3(0u, 1u, 2u); };
+                orc::Integrator integ;
+                integ.scene = &osc;
+                const orc::DifferentialShadingGeometry g0 = integ.differentialShadingGeometry(hit);
+                ref::TriangleHit rhit;
+                rhit.instanceID.index = 0; rhit.primitiveIndex = 0; rhit.barycentrics = R(hit.barycentrics);
+                ref::DifferentialShadingGeometry g1 = ref::differentialShadingGeometry(ref::gScene, rhit);
+                Cmp c("DifferentialShadingGeometry.differentialShadingGeometry");
+                c.add(g0.p.v, g1.p.v); c.add(g0.p.ddu, g1.p.ddu); c.add(g0.p.ddv, g1.p.ddv); c.add(g0.n.v, g1.n.v); c.add(g0.n.ddu, g1.n.ddu); c.add(g0.n.ddv, g1.n.ddv);
+                c.add(g0.s.v, g1.s.v); c.add(g0.s.ddu, g1.s.ddu); c.add(g0.s.ddv, g1.s.ddv); c.add(g0.t.v, g1.t.v); c.add(g0.t.ddu, g1.t.ddu); c.add(g0.t.ddv, g1.t.ddv);
+                c.add(g0.uv, g1.uv); c.add(g0.ngeo, g1.ngeo);
+            }
         }
         osc.d.vertices = nullptr; osc.d.vertexCount = 0; osc.d.instanceCount = 0; osc.d.meshCount = 0; osc.d.matrixCount = 0;
     }
@@ -866,5 +891,19 @@ static void ref_compare_more(int N, Rnd& r) {
             { Cmp c("Camera.computeRayPinhole"); c.add(o, ray.origin); c.add(d, ray.dir); }
             { Cmp c("pltpt.RR"); const float v = r.u(), e = r.range(0.2f, 3.f), u = r.u(); c.add(orc::Integrator::RR(v, e, u), ref::RR(v, e, u)); }
         }
+    }
+    // ---- the manifold solver's Newton step (Manifolds.slangh manifoldOneStep, sphcoords, sphcoordsDerivatives): spherical-coordinate
+    // constraint, its Jacobian from the direction differentials, 2x2 inverse, position step
+    for (int i = 0; i < N; ++i) {
+        Cmp c("Manifolds.manifoldOneStep");
+        orc::float3pdv w, p; orc::float3kpdv ws;
+        w.v = r.dir(); w.ddu = r.f3(-2.f, 2.f); w.ddv = r.f3(-2.f, 2.f);
+        ws.v = r.u() < .5f ? orc::normalize(w.v + r.f3(-.05f, .05f)) : r.dir(); ws.ddu = r.f3(-2.f, 2.f); ws.ddv = r.f3(-2.f, 2.f); ws.ddl = r.f3(-2.f, 2.f);
+        p.v = r.f3(-3.f, 3.f); p.ddu = r.f3(-1.f, 1.f); p.ddv = r.f3(-1.f, 1.f);
+        ref::float3kpdv rws; rws.v = R(ws.v); rws.ddu = R(ws.ddu); rws.ddv = R(ws.ddv); rws.ddl = R(ws.ddl);
+        float l0 = 0.f, l1 = 0.f; orc::float3 s0(0.f); ref::float3 s1(0.f);
+        const bool v0 = orc::Integrator::manifoldOneStep(w, ws, p, l0, s0), v1 = ref::manifoldOneStep(R(w), rws, R(p), l1, s1);
+        c.add(v0, v1); c.add(l0, l1); if (v0 && v1) c.add(s0, s1);
+        c.add(orc::Integrator::sphcoords(w.v), ref::sphcoords(R(w.v)));
     }
 }

@@ -237,6 +237,7 @@ typedef mat<2, 2> float2x2;
 typedef mat<3, 3> float3x3;
 typedef mat<4, 4> float4x4;
 typedef mat<3, 4> float3x4;
+typedef mat<2, 3> float2x3;
 template <int R, int C> vec<float, R> mul(const mat<R, C>& M, const vec<float, C>& v) { vec<float, R> r; for (int i = 0; i < R; ++i) r[i] = dot(M[i], v); return r; }
 template <int R, int C> vec<float, C> mul(const vec<float, R>& v, const mat<R, C>& M) {
     vec<float, C> r; for (int c = 0; c < C; ++c) { float s = v[0] * M[0][c]; for (int i = 1; i < R; ++i) s += v[i] * M[i][c]; r[c] = s; } return r; }

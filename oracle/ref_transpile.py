@@ -73,10 +73,12 @@ SOURCES = [
     ("Scene/Material/BasicMaterialData.slang", ["BasicMaterialData"]),
     ("literal", '#include "../ref/ref_shims_mid.h"'),
     ("Scene/Material/ShadingUtils.slang", ["ShadingFrame", "rgbToNormal", "rgToNormal", "computeShadingFrameFromNormalMap", "applyNormalMap", "computeTangentSpace"]),
-    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getFaceNormalInObjectSpace", "computeVertexData"],
-                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap;")),
+    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getVertex", "getFaceNormalInObjectSpace", "computeVertexData"],
+                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap; "
+                           "StructuredBuffer<PackedStaticVertexData> vertices; uint3 (*indexFn)(GeometryInstanceID, uint) = nullptr; "
+                           "uint3 getIndices(GeometryInstanceID instanceID, uint triangleIndex) { return indexFn(instanceID, triangleIndex); }  /* index-buffer fetch: engine service */")),
     ("Rendering/Materials/BSDFSample.slang", None),
-    ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives"]),
+    ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives", "differentialShadingGeometry"]),
     ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
     ("Rendering/Materials/PLT/DiffractionGrating.slang", None),
     ("Rendering/Materials/PLT/PLTDiffuseBSDF.slang", None),
@@ -111,6 +113,7 @@ SOURCES = [
     ("../RenderPasses/PLTPT/LightSampling.slangh", None),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
     ("../RenderPasses/PLTPT/pltpt.slangh", ["RR"]),
+    ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep"]),
 ]
 
 STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
@@ -156,6 +159,8 @@ PATCHES = [
     ("Scene/Scene.slang", "v.tangentW.xyz = mul((float3x3)worldMat, v.tangentW.xyz);", "{ const float3 txyz = mul((float3x3)worldMat, v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }",
      "swizzle on the left-hand side"),
     ("Scene/Scene.slang", "v.tangentW.xyz = normalize(v.tangentW.xyz);", "{ const float3 txyz = normalize(v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }", "swizzle on the left-hand side"),
+    ("PLTPT/Manifolds.slangh", "const float2x2 do = sphcoordsDerivatives(w);", "const float2x2 do_ = sphcoordsDerivatives(w);", "`do` is a C++ keyword"),
+    ("PLTPT/Manifolds.slangh", "const float2x2 dCdX = do - float2x2(dio);", "const float2x2 dCdX = do_ - float2x2(dio);", "`do` is a C++ keyword"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",

@@ -7,7 +7,7 @@ differential reflect / refract helpers, all ten PLT*BSDF modules, the analytic l
 importance sampler), the ten PLT material loaders (PLT*Material.slang over MaterialData / BasicMaterialData / TextureHandle: both sides unpack
 the same 128-byte records, with Uniform and with Texture-mode handles), the shading data at a hit (MaterialFactory.slang prepareShadingData composed
 from ShadingUtils.slang: tangent-space orthonormalisation, RGB / RG normal maps, opacity, double-sided flip; Scene.slang computeVertexData), primary rays (Camera.slang over the same 656-byte CameraData block), Russian roulette,
-`measure` of the solve shader and the packed-record decoders (snorm /
+the manifold solver's geometry and Newton step (differentialShadingGeometry, manifoldOneStep), `measure` of the solve shader and the packed-record decoders (snorm /
 octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) -- textually into C++ (where /root/reference lies; nothing of it is
 committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
 function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
@@ -60,7 +60,8 @@ EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "Spectrum
             "LightSampling.generateLightSample_env"] + \
            [f"PLT{m}Material.setupMaterialInstance" for m in ("Diffuse", "Conductor", "Dielectric", "OpaqueDielectric", "ThinDielectric", "CoatedConductor", "CoatedOpaqueDielectric",
                                                                "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack")] + \
-           ["MaterialFactory.prepareShadingData", "PLTMaterials.setupMaterialInstance_textured", "Scene.computeVertexData", "Camera.computeRayPinhole", "pltpt.RR"]
+           ["MaterialFactory.prepareShadingData", "PLTMaterials.setupMaterialInstance_textured", "Scene.computeVertexData", "Camera.computeRayPinhole", "pltpt.RR",
+            "Manifolds.manifoldOneStep", "DifferentialShadingGeometry.differentialShadingGeometry"]
 
 
 @pytest.fixture(scope="module")
@@ -96,4 +97,4 @@ def test_oracle_reproduces_the_reference_text(report):
             bad[name] = v
     assert not bad, bad
     exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
-    assert exact >= 86, exact   # of 119 compared functions / entry points
+    assert exact >= 88, exact   # of 121 compared functions / entry points
