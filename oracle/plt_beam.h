@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Parity unpinned by the reference (no PLT tests exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Pinned to the reference's shader text (Fresnel.slang, Mueller.slang,
+// PLT.slang, Interference.slang: oracle/ref_compare.cpp, tests/test_oracle_ref.py).
 // plt_beam.h — Fresnel, Mueller matrices and the generalized ray ("PLT beam").
 #pragma once
 #include "plt_spectrum.h"

@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Parity unpinned by the reference (no PLT tests exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Pinned to the reference's shader text: surface statistics,
+// gratings, birefringence, eval / sample / pdf / lambdaPdf of the ten BSDFs, the ten material loaders on shared 128-byte records, texture-handle
+// decoding (oracle/ref_compare.cpp, tests/test_oracle_ref.py).  The texture FILTER has no source in the reference (hardware): defined here.
 // plt_bsdf.h — surface statistics, the ten PLT BSDFs and material-blob unpacking.
 #pragma once
 #include "plt_beam.h"

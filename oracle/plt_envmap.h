@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Parity unpinned by the reference (no env-map tests exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Pinned to the reference's shader text: EnvMap.slang eval / toLocal /
+// toWorld, EnvMapSampler.slang sample / evalPdf (oracle/ref_compare.cpp).  The importance-map construction (a compute shader) and the bilinear filter
+// (hardware) are restated here and checked on their properties (tests/test_envmap.py).
 // plt_envmap.h — environment map access and hierarchical importance sampling.
 //   Source/Falcor/Scene/Lights/EnvMap.slang:36-134, EnvMapData.slang:36-43, EnvMap.cpp:121-126 (sampler: linear, wrap u / clamp v)
 //   Source/Falcor/Rendering/Lights/EnvMapSampler.slang:53-165, EnvMapSamplerSetup.cs.slang:47-75, EnvMapSampler.cpp:82-121

@@ -1,7 +1,11 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference algorithm; never shipped,
-// never linked into the product library.  Parity status: PRNG / computeRayOrigin / SampledSpectrum
-// leaves are pinned by the reference's own known-answer procedures (tests/test_oracle_leaves.py);
-// everything PLT-specific is "parity unpinned" (the reference has no tests for it).
+// never linked into the product library.  Parity status: PINNED in two ways.  (1) PRNG / computeRayOrigin / SampledSpectrum /
+// XYZ-fit leaves by the reference's own known-answer procedures (tests/test_oracle_leaves.py).  (2) The PLT-specific code -- for which
+// the reference holds no tests -- by the reference's OWN SHADER TEXT: oracle/ref_transpile.py rewrites the Slang modules
+// textually into C++ where /root/reference lies, and oracle/ref_compare.cpp runs them next to these headers on 10^5 seeded inputs per
+// function (121 functions, 98 of them bit-exact, the others inside documented ulp bounds; tests/test_oracle_ref.py).
+// What stays unpinned is named there: ray casting (no source in the reference: the oracle defines the contract) and the ORDER in which
+// the closest-hit / NEE / manifold-walk programs call the pinned functions.
 //
 // plt_math.h — vector types and the subset of Utils/Math/MathHelpers.slang the PLT path calls.
 #pragma once

@@ -1,8 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).
 // plt_scene.h — Falcor scene-buffer access (vertex fetch, shading frame, hit packing) and the ray caster.
+// Vertex unpacking, interpolated vertex data and the shading data at a hit (tangent space, normal maps, double-sided flip) are pinned to the
+// reference's shader text (SceneTypes.slang, Scene.slang computeVertexData, ShadingUtils.slang, MaterialFactory.slang: oracle/ref_compare.cpp).
 //
 // Ray casting: the reference delegates to the D3D12/Vulkan driver + RT cores (Scene.cpp:3092-3760,
-// TraceRay at pltpt_sample.rt.slang:174-183) — no source, "parity unpinned".  The oracle DEFINES the
+// TraceRay at pltpt_sample.rt.slang:174-183) — no source in the reference, so nothing to pin it to: the oracle DEFINES the
 // intersection semantics the CUDA path must reproduce bit-for-bit (DESIGN.md "Intersection contract"):
 //   * triangles are taken in world space: p_w = ((m0*x + m1*y) + m2*z) + m3 per row, each op rounded to fp32;
 //   * watertight test of Woop/Benthin/Wald 2013 with the double-precision fallback on zero edge functions;
