@@ -1,8 +1,9 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see plt_math.h header).  Pinned to the reference's shader text function by
 // function: camera rays, Russian roulette, light-type selection and whole NEE light samples (analytic, emissive uniform / power, environment),
 // emissive-triangle and vertex decoding, shading data, measure / MISWeight, the manifold solver's geometry and Newton step (oracle/ref_compare.cpp,
-// tests/test_oracle_ref.py).  The ORDER in which the closest-hit, NEE / evalEmissive and manifold-walk programs call them is hand-read (they need
-// TraceRay and the bounce buffer) and is checked against closed-form optics and radiometric laws instead (tests/test_oracle_physics.py, _radiometry.py).
+// tests/test_oracle_ref.py).  The sample stage's closest-hit and miss programs are pinned WHOLE (path
+// book-keeping, bounce records, guides).  The ORDER in which the solve stage's NEE / evalEmissive / manifold-walk programs call the pinned functions is
+// hand-read (they interleave TraceRay with the bounce buffer) and is checked against closed-form optics and radiometric laws instead (tests/test_oracle_physics.py, _radiometry.py).
 // plt_integrator.h — the PLTPT sample + solve stages, light sampling, NEE / MNEE, measurement.
 //   Source/RenderPasses/PLTPT/{Path.slang, pltpt.slangh, pltpt_sample.rt.slang, pltpt_solve.rt.slang,
 //   LightSampling.slangh, ShadowRays.slangh, Manifolds.slangh}

@@ -3,9 +3,9 @@
 // XYZ-fit leaves by the reference's own known-answer procedures (tests/test_oracle_leaves.py).  (2) The PLT-specific code -- for which
 // the reference holds no tests -- by the reference's OWN SHADER TEXT: oracle/ref_transpile.py rewrites the Slang modules
 // textually into C++ where /root/reference lies, and oracle/ref_compare.cpp runs them next to these headers on 10^5 seeded inputs per
-// function (121 functions, 98 of them bit-exact, the others inside documented ulp bounds; tests/test_oracle_ref.py).
+// function (123 functions, 98 of them bit-exact, the others inside documented ulp bounds; tests/test_oracle_ref.py).
 // What stays unpinned is named there: ray casting (no source in the reference: the oracle defines the contract) and the ORDER in which
-// the closest-hit / NEE / manifold-walk programs call the pinned functions.
+// the solve stage's NEE / emissive / manifold-walk programs call the pinned functions (the sample stage's closest-hit program is pinned whole).
 //
 // plt_math.h — vector types and the subset of Utils/Math/MathHelpers.slang the PLT path calls.
 #pragma once

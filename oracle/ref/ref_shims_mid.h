@@ -11,6 +11,8 @@ struct BSDFProperties {
     float roughness = .0f;
     uint flags = 0;
     enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
+    bool canManifoldWalkReflective() { return (flags & (uint)Flags::CanManifoldWalkReflective) != 0; }     // :70-88 (property getters)
+    bool canManifoldWalkTransmissive() { return (flags & (uint)Flags::CanManifoldWalkTransmissive) != 0; }
 };
 
 // Scene/Material/MaterialSystem.slang:120-291: what the loaders and materialEvalEmissive ask of the material system.  Material blobs are the
@@ -30,6 +32,9 @@ struct MaterialSystemStandIn {
     }
     SamplerState getTextureSampler(uint samplerID) const { SamplerState s; s.id = samplerID; return s; }
     SamplerState getDefaultTextureSampler(uint materialID) const { return getTextureSampler(getMaterialHeader(materialID).getDefaultTextureSamplerID()); }
+    // MaterialFactory.slang:60-131: dynamic dispatch on the material type -- defined in ref_shims_late.h, once the material structs are complete
+    struct ShadingData prepareShadingData(struct VertexData v, uint materialID, float3 viewDir, ExplicitLodTextureSampler lod) const;
+    struct AnyMaterialInstance getMaterialInstance(struct ShadingData sd, ExplicitLodTextureSampler lod) const;
     float4 sampleTexture(TextureHandle handle, SamplerState s, float2 uv, float4 uniformValue, ExplicitLodTextureSampler) const {
         if (handle.getMode() == TextureHandle::Mode::Texture && textureFn) return textureFn(handle.getTextureID(), s.id, uv);
         return uniformValue;
@@ -47,4 +52,12 @@ struct TriangleHit {
     uint primitiveIndex = 0;
     float2 barycentrics;
     float3 getBarycentricWeights() { return float3(1.f - barycentrics.x - barycentrics.y, barycentrics.x, barycentrics.y); }
+    // the packed form depends on the scene's bit allocation (HitInfo.slang:292-312, set by defines): supplied by the caller of the comparison
+    static inline PackedHitInfo (*packFn)(const TriangleHit&) = nullptr;
+    PackedHitInfo pack() { return packFn(*this); }
 };
+// DXR system values of the hit being shaded (Scene/Raytracing.slang getGeometryInstanceID, HLSL PrimitiveIndex)
+static GeometryInstanceID gCurrentInstanceID;
+static uint gCurrentPrimitiveIndex = 0;
+inline GeometryInstanceID getGeometryInstanceID() { return gCurrentInstanceID; }
+inline uint PrimitiveIndex() { return gCurrentPrimitiveIndex; }

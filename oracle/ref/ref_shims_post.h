@@ -906,4 +906,170 @@ static void ref_compare_more(int N, Rnd& r) {
         c.add(v0, v1); c.add(l0, l1); if (v0 && v1) c.add(s0, s1);
         c.add(orc::Integrator::sphcoords(w.v), ref::sphcoords(R(w.v)));
     }
+    // ---- the closest-hit program of the sample stage, whole: pltpt_sample.rt.slang scatterTriangleMeshClosestHit (with shouldTerminatePath,
+    // pltSampleBSDF), pltpt.slangh appendBounce, Path.slang RayFlags / BounceData / Path -- hit -> vertex data -> shading data -> material
+    // instance -> alpha pass-through / Russian roulette / BSDF sample -> guide outputs -> path book-keeping and the bounce record, on a
+    // four-triangle scene with random materials and random incoming path states.  Slang's dynamic material dispatch is a switch over the ten
+    // transpiled types (ref_shims_late.h); the DXR system values, the packed hit word and the index / matrix fetch are supplied by the caller
+    {
+        constexpr uint32_t kTri = 4, kMaxBounces = 8, kW = 4, kH = 4;
+        static orc::Scene osc;
+        osc.profiles = table;
+        static PltptPackedVertex verts[3 * kTri];
+        static ref::PackedStaticVertexData rverts[3 * kTri];
+        static PltptGeometryInstance insts[kTri];
+        static PltptMeshDesc meshes[kTri];
+        static float world[16 * kTri], worldIT[16 * kTri];
+        static ref::float4x4 rworld[kTri];
+        static ref::float3x3 rworldIT[kTri];
+        static bool cw[kTri];
+        static PltptMaterialBlob blobs[kTri];
+        osc.d.vertices = verts; osc.d.vertexCount = 3 * kTri; osc.d.geometryInstances = insts; osc.d.instanceCount = kTri; osc.d.meshes = meshes; osc.d.meshCount = kTri;
+        osc.d.worldMatrices = world; osc.d.inverseTransposeWorldMatrices = worldIT; osc.d.matrixCount = kTri; osc.d.materialData = blobs; osc.d.materialCount = kTri;
+        osc.d.hitInfoTypeBits = 3; osc.d.hitInfoInstanceIDBits = 2; osc.d.hitInfoPrimitiveIndexBits = 1;
+        orc::Integrator integ;
+        integ.scene = &osc;
+        integ.opt = PltptOptions{};
+        integ.opt.maxBounces = kMaxBounces; integ.opt.HWSS = 4;
+        integ.width = kW; integ.height = kH;
+        static PltptBounce obounces[kW * kH * (kMaxBounces + 1)];
+        static float oalbedo[kW * kH * 4], onormal[kW * kH * 4];
+        integ.bounces = obounces; integ.outAlbedo = oalbedo; integ.outNormal = onormal;
+        // the reference side
+        static ref::BounceData rbounces[kW * kH * (kMaxBounces + 1)];
+        static ref::float4 ralbedo[kW * kH], rnormal[kW * kH];
+        ref::mMaxBounces = kMaxBounces; ref::mTileSize = kW;
+        ref::bounceBuffer.p = rbounces;
+        ref::gOutputAlbedo.p = ralbedo; ref::gOutputAlbedo.width = kW; ref::gOutputNormal.p = rnormal; ref::gOutputNormal.width = kW;
+        ref::gScene.vertices.p = rverts;
+        ref::gScene.materials.blobs = reinterpret_cast<const ref::MaterialDataBlob*>(blobs);
+        ref::gScene.materials.textureFn = nullptr;
+        ref::gScene.indexFn = [](ref::GeometryInstanceID id, ref::uint tri) { return ref::uint3(3u * id.index + 3u * tri, 3u * id.index + 3u * tri + 1u, 3u * id.index + 3u * tri + 2u); };
+        ref::gScene.materialIDFn = [](ref::GeometryInstanceID id) { return id.index; };
+        static const orc::Scene* packScene = &osc;
+        ref::TriangleHit::packFn = [](const ref::TriangleHit& h) {
+            orc::TriangleHit oh; oh.instanceID = h.instanceID.index; oh.primitiveIndex = h.primitiveIndex; oh.barycentrics = orc::float2(h.barycentrics.x, h.barycentrics.y);
+            uint32_t w[4]; packScene->packHit(oh, w); return ref::PackedHitInfo(w[0], w[1], w[2], w[3]); };
+        static ref::float4x4* gW = rworld; static ref::float3x3* gWIT = rworldIT; static bool* gCW = cw;
+        ref::gScene.vertexDataFn = [](ref::TriangleHit hit) {   // Scene.slang:576-585
+            const ref::uint3 vtxIndices = ref::gScene.getIndices(hit.instanceID, hit.primitiveIndex);
+            ref::StaticVertexData vertices[3] = {ref::gScene.getVertex(vtxIndices[0]), ref::gScene.getVertex(vtxIndices[1]), ref::gScene.getVertex(vtxIndices[2])};
+            return ref::gScene.computeVertexData(vertices, gW[hit.instanceID.index], gWIT[hit.instanceID.index], gCW[hit.instanceID.index], hit.getBarycentricWeights()); };
+        const uint32_t kTypes[10] = {PLTPT_MATERIAL_DIFFUSE, PLTPT_MATERIAL_CONDUCTOR, PLTPT_MATERIAL_DIELECTRIC, PLTPT_MATERIAL_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_THIN_DIELECTRIC,
+                                     PLTPT_MATERIAL_COATED_CONDUCTOR, PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_GRATED_CONDUCTOR, PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC,
+                                     PLTPT_MATERIAL_MULTILAYERED_STACK};
+        auto half = [&](float lo, float hi) { return uint16_t(ref::f32tof16(r.range(lo, hi))); };
+        auto halfBits = [&](float lo, float hi) { return ref::f32tof16(r.range(lo, hi)); };
+        for (int i = 0; i < N / 4; ++i) {
+            // geometry and materials of the four instances
+            for (uint32_t t = 0; t < kTri; ++t) {
+                const orc::float3 c0 = r.f3(-3.f, 3.f);
+                for (int k = 0; k < 3; ++k) {
+                    const orc::float3 pos = c0 + r.f3(-1.f, 1.f); const orc::float2 tc = r.f2(-1.f, 2.f);
+                    const float sgn = r.u() < .2f ? 0.f : (r.u() < .5f ? -1.f : 1.f);
+                    const uint32_t w0 = halfBits(-1.f, 1.f) | (halfBits(-1.f, 1.f) << 16), w1 = halfBits(-1.f, 1.f) | (ref::f32tof16(sgn) << 16), w2 = r.g();
+                    PltptPackedVertex& v = verts[3 * t + k];
+                    for (int a = 0; a < 3; ++a) v.position[a] = pos[a];
+                    v.texCrd[0] = tc.x; v.texCrd[1] = tc.y;
+                    v.packedNormalTangentCurveRadius[0] = w0; v.packedNormalTangentCurveRadius[1] = w1; v.packedNormalTangentCurveRadius[2] = w2;
+                    rverts[3 * t + k].position = R(pos); rverts[3 * t + k].texCrd = R(tc);
+                    rverts[3 * t + k].packedNormalTangentCurveRadius = ref::float3(ref::asfloat(ref::uint(w0)), ref::asfloat(ref::uint(w1)), ref::asfloat(ref::uint(w2)));
+                }
+                insts[t] = PltptGeometryInstance{}; meshes[t] = PltptMeshDesc{};
+                cw[t] = r.u() < .5f;
+                insts[t].flags = cw[t] ? PLTPT_INSTANCE_FLAG_OBJECT_FRONT_FACE_CW : 0u;
+                insts[t].globalMatrixID = t; insts[t].materialID = t; insts[t].geometryID = t; insts[t].vbOffset = 3 * t;
+                const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex), sc = r.f3(0.5f, 2.f), tr = r.f3(-2.f, 2.f);
+                const orc::float3 cols[3] = {ex * sc.x, ey * sc.y, ez * sc.z}, colsIT[3] = {ex / sc.x, ey / sc.y, ez / sc.z};
+                float* wm = world + 16 * t; float* wit = worldIT + 16 * t;
+                for (int row = 0; row < 3; ++row) {
+                    for (int c = 0; c < 3; ++c) { wm[4 * row + c] = cols[c][row]; wit[4 * row + c] = colsIT[c][row]; rworld[t][row][c] = wm[4 * row + c]; rworldIT[t][row][c] = wit[4 * row + c]; }
+                    wm[4 * row + 3] = tr[row]; wit[4 * row + 3] = 0.f; rworld[t][row][3] = tr[row];
+                }
+                for (int c = 0; c < 4; ++c) { wm[12 + c] = wit[12 + c] = c == 3 ? 1.f : 0.f; rworld[t][3][c] = wm[12 + c]; }
+                const int kind = int(r.u() * 9.999f);
+                PltptMaterialBlob& blob = blobs[t];
+                blob = PltptMaterialBlob{};
+                blob.header[0] = kTypes[kind] | (1u << 31) | (r.u() < .5f ? (1u << 28) : 0u);
+                for (int k = 0; k < 4; ++k) { blob.baseColor[k] = half(0.05f, 1.f); blob.specular[k] = half(0.02f, 2.5f); blob.data1[k] = half(0.05f, 3.f); blob.data2[k] = half(0.02f, 2.5f); }
+                if (r.u() < .1f) blob.baseColor[3] = 0;   // fully transparent: the alpha pass-through
+                if (r.u() < .15f) blob.specular[1] = 0;
+                for (int k = 0; k < 3; ++k) blob.transmission[k] = half(0.2f, 1.f);
+                blob.IoR = half(1.f, 2.2f);
+                const uint32_t n = uint32_t(r.u() * 1.999f) * 2u;
+                blob.iorNSpectralId = n; blob.iorKSpectralId = n + 1u; blob.emissionSpectralId = r.u() < .2f ? 4u : PLTPT_NO_SPECTRAL_PROFILE;
+                if (kind == 7 || kind == 8) blob.data1[3] = uint16_t(((uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u)) << 8) | (1u + uint32_t(r.u() * 7.99f)));
+                if (kind == 9) blob.data1[3] = uint16_t(1u + uint32_t(r.u() * 11.99f));
+            }
+            PltptCameraData cam{};
+            float* words = reinterpret_cast<float*>(&cam);
+            for (size_t k = 0; k < sizeof(cam) / 4; ++k) words[k] = r.range(-2.f, 2.f);
+            integ.cam = cam;
+            std::memcpy(static_cast<void*>(&ref::gScene.camera.data), &cam, sizeof cam);
+            for (int q = 0; q < 4; ++q) {
+                const bool alpha = r.u() < .8f, rr = r.u() < .7f;
+                integ.opt.alphaMasking = alpha; integ.opt.doRussianRoulette = rr;
+                ref::kAlphaMasking = alpha; ref::kDoRussianRoulette = rr;
+                const uint32_t px = uint32_t(r.u() * (kW - 0.001f)), py = uint32_t(r.u() * (kH - 0.001f));
+                // an incoming path state
+                orc::Path po;
+                po.sg = orc::SampleGenerator(uint32_t(i), uint32_t(q), 61u);
+                po.origin = r.f3(-5.f, 5.f); po.dir = r.dir(); po.normal = r.dir();
+                po.wavelength = r.range(380.f, 720.f); po.weight = r.u() < .2f ? 1.f : r.range(0.01f, 1.f); po.pdf = r.range(0.01f, 5.f); po.thp_modifier = r.range(1.f, 3.f);
+                if (r.u() < .05f) po.pdf = 1e-7f;   // the 1e-6 contribution cut
+                po.id = (py << 16) | px;
+                po.length = r.u() < .15f ? int(kMaxBounces) : int(r.u() * (kMaxBounces - 0.001f));
+                po.flags.flags = (r.g() & 0x7u) | (uint32_t(r.u() * 3.999f) << 16);
+                po.lastNonDeltaPdf = r.range(0.f, 4.f);
+                ref::Path pr;
+                pr.sg.g = po.sg; pr.origin = R(po.origin); pr.dir = R(po.dir); pr.normal = R(po.normal); pr.wavelength = po.wavelength; pr.weight = po.weight; pr.pdf = po.pdf;
+                pr.thp_modifier = po.thp_modifier; pr.id = po.id; pr.length = po.length; pr.flags.flags = po.flags.flags; pr.lastNonDeltaPdf = po.lastNonDeltaPdf;
+                // sentinels in every output both sides may or may not write
+                const int len0 = po.length;
+                PltptBounce& ob = obounces[(size_t(py) * kW + px) * (kMaxBounces + 1) + len0];
+                ref::BounceData& rbnc = rbounces[((px % kW) + (py % kW) * kW) * (kMaxBounces + 1) + len0];
+                std::memset(&ob, 0xcd, sizeof ob); std::memset(static_cast<void*>(&rbnc), 0xcd, sizeof rbnc);
+                for (int k = 0; k < 4; ++k) { oalbedo[(py * kW + px) * 4 + k] = -7.f; onormal[(py * kW + px) * 4 + k] = -7.f; }
+                ralbedo[py * kW + px] = ref::float4(-7.f); rnormal[py * kW + px] = ref::float4(-7.f);
+                // a hit
+                orc::TriangleHit hit;
+                hit.instanceID = uint32_t(r.u() * (kTri - 0.001f)); hit.primitiveIndex = 0;
+                const orc::float3 bary = orc::sample_triangle(r.f2(0.f, 1.f));
+                hit.barycentrics = orc::float2(bary.y, bary.z);
+                integ.scatterClosestHit(po, hit);
+                ref::gCurrentInstanceID.index = hit.instanceID; ref::gCurrentPrimitiveIndex = 0;
+                ref::BuiltInTriangleIntersectionAttributes attribs; attribs.barycentrics = R(hit.barycentrics);
+                ref::scatterTriangleMeshClosestHit(pr, attribs);
+                if (std::getenv("REF_DEBUG")) {
+                    Cmp("dbg.origin").add(po.origin, pr.origin); Cmp("dbg.dir").add(po.dir, pr.dir); Cmp("dbg.normal").add(po.normal, pr.normal); Cmp("dbg.weight").add(po.weight, pr.weight);
+                    Cmp("dbg.pdf").add(po.pdf, pr.pdf); Cmp("dbg.thp").add(po.thp_modifier, pr.thp_modifier); Cmp("dbg.lnd").add(po.lastNonDeltaPdf, pr.lastNonDeltaPdf);
+                    Cmp("dbg.wi").add(ob.encodedWi[0], rbnc.encodedWi.x); Cmp("dbg.contrib").add(ob.pathContribution, rbnc.pathContribution); Cmp("dbg.blnd").add(ob.lastNonDeltaPdf, rbnc.lastNonDeltaPdf);
+                    for (int k = 0; k < 4; ++k) { Cmp("dbg.albedo").add(oalbedo[(py * kW + px) * 4 + k], ralbedo[py * kW + px][k]); Cmp("dbg.gnormal").add(onormal[(py * kW + px) * 4 + k], rnormal[py * kW + px][k]); }
+                }
+                Cmp c("pltpt_sample.scatterTriangleMeshClosestHit");
+                c.add(po.origin, pr.origin); c.add(po.dir, pr.dir); c.add(po.normal, pr.normal); c.add(po.weight, pr.weight); c.add(po.pdf, pr.pdf); c.add(po.thp_modifier, pr.thp_modifier);
+                c.add(po.length, pr.length); c.add(po.flags.flags, uint32_t(pr.flags.flags)); c.add(po.lastNonDeltaPdf, pr.lastNonDeltaPdf); c.add(po.sg.next(), pr.sg.next());
+                for (int k = 0; k < 4; ++k) c.add(ob.hit[k], uint32_t(rbnc.hit[k]));
+                c.add(ob.encodedWi[0], rbnc.encodedWi.x); c.add(ob.encodedWi[1], rbnc.encodedWi.y); c.add(ob.sampledBsdfLobe, uint32_t(rbnc.sampledBsdfLobe)); c.add(ob.flags, uint32_t(rbnc.flags.flags));
+                c.add(ob.pathContribution, rbnc.pathContribution); c.add(ob.lastNonDeltaPdf, rbnc.lastNonDeltaPdf);
+                for (int k = 0; k < 4; ++k) { c.add(oalbedo[(py * kW + px) * 4 + k], ralbedo[py * kW + px][k]); c.add(onormal[(py * kW + px) * 4 + k], rnormal[py * kW + px][k]); }
+                // the miss program on the state the hit left behind (scatterMiss: flag + bounce record with an empty hit word), when the path goes on
+                if (po.flags.valid() && po.length <= int(kMaxBounces)) {
+                    PltptBounce& ob2 = obounces[(size_t(py) * kW + px) * (kMaxBounces + 1) + po.length];
+                    ref::BounceData& rb2 = rbounces[((px % kW) + (py % kW) * kW) * (kMaxBounces + 1) + po.length];
+                    std::memset(&ob2, 0xcd, sizeof ob2); std::memset(static_cast<void*>(&rb2), 0xcd, sizeof rb2);
+                    const uint32_t zero[4] = {0, 0, 0, 0};
+                    po.flags.set(orc::RayFlags::missF, true);                 // plt_integrator.h samplePixel, the miss branch
+                    integ.appendBounce(po, zero, -po.dir, 0);
+                    ref::scatterMiss(pr);
+                    Cmp m("pltpt_sample.scatterMiss");
+                    m.add(po.flags.flags, uint32_t(pr.flags.flags));
+                    for (int k = 0; k < 4; ++k) m.add(ob2.hit[k], uint32_t(rb2.hit[k]));
+                    m.add(ob2.encodedWi[0], rb2.encodedWi.x); m.add(ob2.encodedWi[1], rb2.encodedWi.y); m.add(ob2.sampledBsdfLobe, uint32_t(rb2.sampledBsdfLobe)); m.add(ob2.flags, uint32_t(rb2.flags.flags));
+                    m.add(ob2.pathContribution, rb2.pathContribution); m.add(ob2.lastNonDeltaPdf, rb2.lastNonDeltaPdf);
+                }
+            }
+        }
+        osc.d = PltptSceneDesc{};
+    }
 }

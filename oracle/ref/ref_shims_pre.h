@@ -59,7 +59,8 @@ template <class S> float3 sampleNext3D(S& sg) {
     return sample;
 }
 
-// Scene/ShadingData.slang:46-107: the fields and the two frame transforms the PLT BSDFs use
+float3 computeRayOrigin(float3 pos, float3 normal);  // Utils/Geometry/GeometryHelpers.slang:47-61, transpiled further down
+// Scene/ShadingData.slang:46-107: the fields, the two frame transforms and the ray-origin offset the path uses
 struct ShadingData {
     float3 posW, V, N, T, B, faceN;
     float4 tangentW;
@@ -67,6 +68,7 @@ struct ShadingData {
     bool frontFacing = true;
     uint materialID = 0;
     float opacity = 1.f;
+    float3 computeNewRayOrigin(bool viewside = true) { return computeRayOrigin(posW, (frontFacing == viewside) ? faceN : -faceN); }  // :77-80
     float3 fromLocal(float3 v) const { return T * v.x + B * v.y + N * v.z; }
     float3 toLocal(float3 v) const { return float3(dot(v, T), dot(v, B), dot(v, N)); }
 };
@@ -111,7 +113,7 @@ template <class T> struct Texture2D {
     T SampleLevel(SamplerState, float2 uv, float lod) const { return sampleFn(ctx, uv, lod); }
     void GetDimensions(uint& w, uint& h) const { w = width; h = height; }
 };
-struct ExplicitLodTextureSampler { float lod; };
+struct ExplicitLodTextureSampler { float lod; ExplicitLodTextureSampler(float l = 0.f) : lod(l) {} };
 typedef ExplicitLodTextureSampler ITextureSampler;  // the interface the loaders take; the pass passes ExplicitLodTextureSampler{0} (Scene/Material/TextureSampler.slang:74-87)
 
 // ---- what RenderPasses/PLTPT/LightSampling.slangh expects from the pass around it
@@ -139,6 +141,17 @@ static EmissiveSamplerStandIn emissiveSampler;
 // ---- what `measure` (pltpt_solve.rt.slang:96-147) expects (the camera block is the transpiled CameraData.slang / Camera.slang): the solve payload (Path.slang:200-225, without its generators), two more switches of pltpt.slangh:95-104
 struct PLTSolve { float3 Lrgb = .0f; float3 pathOrigin, pathNormal; float wavelength = 0.f; };
 static bool kUseDirectLights = true, mHWSSDoMIS = true;
+// ---- what the closest-hit program of pltpt_sample.rt.slang expects: more switches of pltpt.slangh:90-118, the pass's resources
+// (pltpt.slangh:84-88,123) as plain arrays, the DXR system values of the current hit, the per-path generator (Utils/Sampling/SampleGenerator:
+// the pass's generator is the xoshiro the oracle restates and pins to PseudorandomTests.cpp; both sides step the same object type)
+static uint mMaxBounces = 8, mTileSize = 512;
+static bool kAlphaMasking = true, kDoRussianRoulette = true;
+typedef uint4 PackedHitInfo;  // Scene/HitInfo.slang:63 (uncompressed hit info)
+template <class T> struct RWTexture2D { T* p = nullptr; uint width = 0; T& operator[](uint2 px) { return p[size_t(px.y) * width + px.x]; } };
+template <class T> struct RWStructuredBuffer { T* p = nullptr; T& operator[](uint i) { return p[i]; } };
+static RWTexture2D<float4> gOutputColor, gOutputNormal, gOutputAlbedo;
+struct BuiltInTriangleIntersectionAttributes { float2 barycentrics; };
+struct SampleGenerator { orc::SampleGenerator g; uint next() { return g.next(); } };
 #define DO_DEBUG_VIEW 0
 
 }  // namespace ref

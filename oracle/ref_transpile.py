@@ -24,6 +24,8 @@ Rewrite rules (all mechanical; each is a regular expression or a brace-matched b
   R9  `A.B` static access -> `A::B` for the names in STATIC_SCOPES; `struct X : IFoo` loses the interface list
   R10 `static const float` -> `static constexpr float`; struct-typed `const` locals / parameters lose `const` (Slang methods are
       callable on them; C++ would need const-qualified methods), structs get their trailing `;`
+      A property with a setter also gets `void set_NAME(T newValue) { BODY }`; in the files that use the RayFlags / BounceData properties,
+      `x.flags.NAME = e;` -> `x.flags.set_NAME(e);`, `x.flags.NAME |= e;` -> `x.flags.set_NAME(x.flags.NAME() | (e));`, reads get `()`
   R12 `let x = e` -> `auto x = e`
   R13 `enum class X : T` -> `enum X : T` (Slang converts a scoped enumerator to its underlying type in `switch (uint)` / `uint(...)`; C++
       only does so for an unscoped enumeration, whose enumerators can still be written `X::Name`)
@@ -76,7 +78,9 @@ SOURCES = [
     ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getVertex", "getFaceNormalInObjectSpace", "computeVertexData"],
                            "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap; "
                            "StructuredBuffer<PackedStaticVertexData> vertices; uint3 (*indexFn)(GeometryInstanceID, uint) = nullptr; "
-                           "uint3 getIndices(GeometryInstanceID instanceID, uint triangleIndex) { return indexFn(instanceID, triangleIndex); }  /* index-buffer fetch: engine service */")),
+                           "uint3 getIndices(GeometryInstanceID instanceID, uint triangleIndex) { return indexFn(instanceID, triangleIndex); }  /* index-buffer fetch: engine service */ "
+                           "VertexData (*vertexDataFn)(TriangleHit) = nullptr; VertexData getVertexData(TriangleHit hit) { return vertexDataFn(hit); }  /* instance -> vertices, matrices: composed by the caller from getVertex / computeVertexData */ "
+                           "uint (*materialIDFn)(GeometryInstanceID) = nullptr; uint getMaterialID(GeometryInstanceID instanceID) { return materialIDFn(instanceID); }")),
     ("Rendering/Materials/BSDFSample.slang", None),
     ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives", "differentialShadingGeometry"]),
     ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
@@ -112,7 +116,10 @@ SOURCES = [
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
     ("../RenderPasses/PLTPT/LightSampling.slangh", None),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
-    ("../RenderPasses/PLTPT/pltpt.slangh", ["RR"]),
+    ("../RenderPasses/PLTPT/Path.slang", ["RayFlags", "BounceData", "Path"]),
+    ("literal", '#include "../ref/ref_shims_late.h"'),
+    ("../RenderPasses/PLTPT/pltpt.slangh", ["appendBounce", "RR"]),
+    ("../RenderPasses/PLTPT/pltpt_sample.rt.slang", ["shouldTerminatePath", "pltSampleBSDF", "scatterMiss", "scatterTriangleMeshClosestHit"]),
     ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep"]),
 ]
 
@@ -161,6 +168,12 @@ PATCHES = [
     ("Scene/Scene.slang", "v.tangentW.xyz = normalize(v.tangentW.xyz);", "{ const float3 txyz = normalize(v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }", "swizzle on the left-hand side"),
     ("PLTPT/Manifolds.slangh", "const float2x2 do = sphcoordsDerivatives(w);", "const float2x2 do_ = sphcoordsDerivatives(w);", "`do` is a C++ keyword"),
     ("PLTPT/Manifolds.slangh", "const float2x2 dCdX = do - float2x2(dio);", "const float2x2 dCdX = do_ - float2x2(dio);", "`do` is a C++ keyword"),
+    ("PLTPT/Path.slang", "    enum class Flags {", "    enum class Flags : uint {", "the mask 0xffff0000 needs an unsigned underlying type in C++ (Slang enums are 32-bit words)"),
+    ("Materials/BSDFSample.slang", "    float   pdf;  ", "    float   pdf = 0.f;  ",
+     "the closest-hit program reads bsdfSample.lobe / .pdf on paths that skipped sample() (pltpt_sample.rt.slang:87-103): a GPU compiler gives the "
+     "unwritten local zeros, C++ an indeterminate value -- zero here, as the oracle defines it"),
+    ("Materials/BSDFSample.slang", "    uint    lobe;  ", "    uint    lobe = 0;  ", "as above"),
+    ("Materials/BSDFSample.slang", "    float   weight;", "    float   weight = 0.f;", "as above"),
     ("Geometry/GeometryHelpers.slang", "float3 iPos = asfloat(asint(pos) + (pos < 0.f ? -iOff : iOff));", "float3 iPos = asfloat(asint(pos) + select(pos < 0.f, -iOff, iOff));", "R11"),
     ("Geometry/GeometryHelpers.slang", "return abs(pos) < origin ? pos + fOff : iPos;", "return select(abs(pos) < origin, pos + fOff, iPos);", "R11"),
     ("PLTPT/LightSampling.slangh", "void getLightTypeSelectionProbabilities(out float p[3]) {", "void getLightTypeSelectionProbabilities(float p[3]) {",
@@ -199,7 +212,7 @@ def extract_items(s, names):
     """Top-level functions / structs with the given names (all overloads of a name in source order), emitted in the order of `names`
     (Slang resolves names regardless of declaration order, C++ needs the callee first)."""
     found = {n: [] for n in names}
-    pat = re.compile(r"^(?:static\s+)?(?:const\s+)?[\w<>,:]+\s+(\w+)\s*\([^;{]*\)\s*\{|^struct\s+(\w+)[^{;]*\{", re.M)
+    pat = re.compile(r"^(?:static\s+)?(?:const\s+)?[\w<>,:]+\s+(\w+)\s*(?:<[^>]*>)?\s*\([^;{]*\)\s*\{|^struct\s+(\w+)[^{;]*\{", re.M)
     pos = 0
     while True:
         m = pat.search(s, pos)
@@ -291,10 +304,15 @@ def rule_structs(s):
             gm = re.search(r"\bget\s*\{", inner)
             gend = match_brace(inner, gm.end() - 1)
             getter = inner[gm.end():gend - 1]
-            body = body[:pm.start()] + f"{pm.group(2)} {pm.group(1)}() {{{getter}}}" + body[pend:]
+            setter = ""
+            sm = re.search(r"\bset\s*\{", inner)
+            if sm:   # R5: `set { BODY }` (implicit parameter `newValue`) -> `void set_NAME(T newValue) { BODY }`
+                send = match_brace(inner, sm.end() - 1)
+                setter = f"\n    void set_{pm.group(1)}({pm.group(2)} newValue) {{{inner[sm.end():send - 1]}}}"
+            body = body[:pm.start()] + f"{pm.group(2)} {pm.group(1)}() {{{getter}}}" + setter + body[pend:]
             props.append(pm.group(1))
         for p in props:  # bare uses inside the struct: not a member access of something else, not already a call, not a declaration
-            body = re.sub(rf"(?<![\w.]){p}\b(?!\s*\()", p + "()", body)
+            body = re.sub(rf"(?<![\w.:]){p}\b(?!\s*\()(?!\s*=[^=])", p + "()", body)   # not `Enum::NAME`, not an enumerator `NAME = value`
             body = re.sub(rf"\b(\w+)\s+{p}\(\)\(\)\s*\{{", rf"\1 {p}() {{", body)
         body = rule_structs(body)  # nested structs
         tail = s[end:end + 1]
@@ -353,11 +371,12 @@ def transpile(path, s, struct_names):
     s = re.sub(r"^\s*#pragma once\s*$", "", s, flags=re.M)
     s = re.sub(r"^\s*(BEGIN|END)_NAMESPACE_FALCOR\s*$", "", s, flags=re.M)
     s = re.sub(r"\blet\s+", "auto ", s)   # R12: `let x = ...` -> `auto x = ...`
-    s = re.sub(r"\benum\s+class\s+(\w+)\s*:", r"enum \1 :", s)   # R13
+    s = re.sub(r"^enum\s+class\s+(\w+)\s*:", r"enum \1 :", s, flags=re.M)   # R13 (namespace-scope enums only: a nested one stays scoped)
     # R4
     s = re.sub(r"\[mutating\]\s*", "", s)
     s = re.sub(r"^\s*\[(?:unroll|ForceInline|Differentiable|BackwardDifferentiable|loop|branch|flatten|root)(?:\([^\]]*\))?\]\s*", "", s, flags=re.M)
     s = re.sub(r"\bno_diff\s+", "", s)
+    s = re.sub(r"^\s*\[shader\([^\]]*\)\]\s*$", "", s, flags=re.M)   # DXR entry-point attributes
     s = re.sub(r"\bprecise\s+", "", s)          # every operation is individually rounded here anyway (-ffp-contract=off)
     s = re.sub(r"\s*\bCONST_FUNCTION\b", "", s)  # Utils/HostDeviceShared.slangh: empty in shader code
     # R2
@@ -384,6 +403,13 @@ def transpile(path, s, struct_names):
     s = re.sub(r"\brgb\.b\b", "rgb.z", s)
     s = re.sub(r"\.([xyzw]{2,4})\b(?!\s*\()", r".\1()", s)
     s = per_function(s, scalar_swizzles)
+    if re.search(r"PLTPT/(Path\.slang|pltpt\.slangh|pltpt_sample\.rt\.slang)$", path):   # R5: RayFlags / BounceData properties with setters
+        props = "MSCompatibleBounces|lastBounceWasDelta|dispersiveDeltaSegment|onlyDelta|miss|terminated"
+        s = re.sub(rf"(\b[\w.]*flags)\.({props})\s*\|=\s*([^;]+);", r"\1.set_\2(\1.\2() | (\3));", s)
+        s = re.sub(rf"(\b[\w.]*flags)\.({props})\s*=(?!=)\s*([^;]+);", r"\1.set_\2(\3);", s)
+        s = re.sub(rf"(\b[\w.]*flags)\.({props})\b(?!\s*\()", r"\1.\2()", s)
+        s = re.sub(r"\bbounce\.wi\s*=(?!=)\s*([^;]+);", r"bounce.set_wi(\1);", s)
+        s = re.sub(r"\bbsdfProp\.(canManifoldWalk(?:Reflective|Transmissive))\b(?!\s*\()", r"bsdfProp.\1()", s)
     for pu in PROPERTY_USES + (PROPERTY_USES_FRACTAL if re.search(r"typedef\s+FractalSurface\s+SurfaceType", s) else []):
         s = re.sub(rf"\b({pu})\b(?!\s*\()", r"\1()", s)
     # R10
@@ -416,7 +442,7 @@ def main():
     struct_names = set()
     for _p, t, _d in texts:
         struct_names.update(re.findall(r"\bstruct\s+(\w+)", t))
-    struct_names.update(["ShadingData", "DifferentialShadingGeometry"])
+    struct_names.update(["ShadingData", "DifferentialShadingGeometry", "BSDFProperties", "IMaterialInstance", "VertexData", "TriangleHit"])   # shim structs
     parts = ["// GENERATED by oracle/ref_transpile.py from the reference's Slang sources under /root/reference -- not part of the repository.",
              "#pragma once", '#include "../ref/slang_compat.h"', '#include "../ref/ref_shims_pre.h"', "namespace ref {"]
     for path, t, is_def in texts:

@@ -7,7 +7,8 @@ differential reflect / refract helpers, all ten PLT*BSDF modules, the analytic l
 importance sampler), the ten PLT material loaders (PLT*Material.slang over MaterialData / BasicMaterialData / TextureHandle: both sides unpack
 the same 128-byte records, with Uniform and with Texture-mode handles), the shading data at a hit (MaterialFactory.slang prepareShadingData composed
 from ShadingUtils.slang: tangent-space orthonormalisation, RGB / RG normal maps, opacity, double-sided flip; Scene.slang computeVertexData), primary rays (Camera.slang over the same 656-byte CameraData block), Russian roulette,
-the manifold solver's geometry and Newton step (differentialShadingGeometry, manifoldOneStep), `measure` of the solve shader and the packed-record decoders (snorm /
+the manifold solver's geometry and Newton step (differentialShadingGeometry, manifoldOneStep), the WHOLE closest-hit and miss programs of the sample
+stage (pltpt_sample.rt.slang over Path.slang and appendBounce: path book-keeping, bounce records, guide outputs), `measure` of the solve shader and the packed-record decoders (snorm /
 octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) -- textually into C++ (where /root/reference lies; nothing of it is
 committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
 function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
@@ -42,6 +43,9 @@ for _m, _b in (("Conductor", 1024), ("Dielectric", 1024), ("OpaqueDielectric", 1
                ("DiffractionGratedConductor", 1024), ("DiffractionGratedOpaqueDielectric", 1024)):
     ULP[f"PLT{_m}Material.setupMaterialInstance"] = _b
 ULP["PLTMaterials.setupMaterialInstance_textured"] = 1024
+# the closest-hit / miss programs multiply the sampled BSDF pdf (see the BSDFs' sample() bounds) into the path state and the bounce record
+ULP["pltpt_sample.scatterTriangleMeshClosestHit"] = 16
+ULP["pltpt_sample.scatterMiss"] = 16
 # relative bound instead of an ulp bound: the multilayer stack's interference sum (correctly rounded phasors in the oracle)
 REL = {"PLTMultiLayeredStackBSDF.eval": 5e-3, "PLTMultiLayeredStackMaterial.setupMaterialInstance": 5e-3}
 
@@ -61,7 +65,7 @@ EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "Spectrum
            [f"PLT{m}Material.setupMaterialInstance" for m in ("Diffuse", "Conductor", "Dielectric", "OpaqueDielectric", "ThinDielectric", "CoatedConductor", "CoatedOpaqueDielectric",
                                                                "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack")] + \
            ["MaterialFactory.prepareShadingData", "PLTMaterials.setupMaterialInstance_textured", "Scene.computeVertexData", "Camera.computeRayPinhole", "pltpt.RR",
-            "Manifolds.manifoldOneStep", "DifferentialShadingGeometry.differentialShadingGeometry"]
+            "Manifolds.manifoldOneStep", "DifferentialShadingGeometry.differentialShadingGeometry", "pltpt_sample.scatterTriangleMeshClosestHit", "pltpt_sample.scatterMiss"]
 
 
 @pytest.fixture(scope="module")
@@ -97,4 +101,4 @@ def test_oracle_reproduces_the_reference_text(report):
             bad[name] = v
     assert not bad, bad
     exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
-    assert exact >= 88, exact   # of 121 compared functions / entry points
+    assert exact >= 88, exact   # of 123 compared functions / entry points
