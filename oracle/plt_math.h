@@ -3,9 +3,10 @@
 // XYZ-fit leaves by the reference's own known-answer procedures (tests/test_oracle_leaves.py).  (2) The PLT-specific code -- for which
 // the reference holds no tests -- by the reference's OWN SHADER TEXT: oracle/ref_transpile.py rewrites the Slang modules
 // textually into C++ where /root/reference lies, and oracle/ref_compare.cpp runs them next to these headers on 10^5 seeded inputs per
-// function (123 functions, 98 of them bit-exact, the others inside documented ulp bounds; tests/test_oracle_ref.py).
-// What stays unpinned is named there: ray casting (no source in the reference: the oracle defines the contract) and the ORDER in which
-// the solve stage's NEE / emissive / manifold-walk programs call the pinned functions (the sample stage's closest-hit program is pinned whole).
+// function, and renders WHOLE FRAMES with the reference's two ray-generation programs (sample and solve stage, NEE / MNEE / emissive / miss /
+// replay, only the intersection search behind TraceRay supplied) beside samplePixel / solvePixel: 126 entries, 99 of them bit-exact, the others
+// inside documented ulp bounds; 49 974 of 49 984 frame pixels equal to the last bit (tests/test_oracle_ref.py).
+// What stays outside the reference's text: ray casting itself (DXR hardware, no source in the reference: the oracle defines the contract).
 //
 // plt_math.h — vector types and the subset of Utils/Math/MathHelpers.slang the PLT path calls.
 #pragma once

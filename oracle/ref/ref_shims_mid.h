@@ -11,6 +11,7 @@ struct BSDFProperties {
     float roughness = .0f;
     uint flags = 0;
     enum Flags : uint { IsTransmissive = 0x1, IsEmissive = 0x2, CanManifoldWalkReflective = 0x4, CanManifoldWalkTransmissive = 0x8 };
+    bool isEmissive() { return (flags & (uint)Flags::IsEmissive) != 0; }
     bool canManifoldWalkReflective() { return (flags & (uint)Flags::CanManifoldWalkReflective) != 0; }     // :70-88 (property getters)
     bool canManifoldWalkTransmissive() { return (flags & (uint)Flags::CanManifoldWalkTransmissive) != 0; }
 };
@@ -54,7 +55,10 @@ struct TriangleHit {
     float3 getBarycentricWeights() { return float3(1.f - barycentrics.x - barycentrics.y, barycentrics.x, barycentrics.y); }
     // the packed form depends on the scene's bit allocation (HitInfo.slang:292-312, set by defines): supplied by the caller of the comparison
     static inline PackedHitInfo (*packFn)(const TriangleHit&) = nullptr;
+    static inline void (*unpackFn)(PackedHitInfo, TriangleHit&) = nullptr;
     PackedHitInfo pack() { return packFn(*this); }
+    TriangleHit() = default;
+    TriangleHit(PackedHitInfo packed) { unpackFn(packed, *this); }
 };
 // DXR system values of the hit being shaded (Scene/Raytracing.slang getGeometryInstanceID, HLSL PrimitiveIndex)
 static GeometryInstanceID gCurrentInstanceID;

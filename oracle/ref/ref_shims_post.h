@@ -20,6 +20,18 @@ template <class S> bool emissiveSamplerDispatch(float3 posW, float3 normalW, boo
     if (gEmissiveKind == 2) return gPowerSampler.sampleLight(posW, normalW, upperHemisphere, sg, wavelength, importanceSampleSpectrum, ls);
     return false;
 }
+float emissiveEvalPdfDispatch(float3 posW, float3 normalW, bool upperHemisphere, TriangleLightHit hit) {
+    if (gEmissiveKind == 1) return gUniformSampler.evalPdf(posW, normalW, upperHemisphere, hit);
+    if (gEmissiveKind == 2) return gPowerSampler.evalPdf(posW, normalW, upperHemisphere, hit);
+    return 0.f;
+}
+// the shader tables of the two stages (PLTPT.cpp:538-548), see TraceRay in ref_shims_late.h
+inline void sbtClosestHit(Path& payload, BuiltInTriangleIntersectionAttributes attribs) { scatterTriangleMeshClosestHit(payload, attribs); }
+inline void sbtMiss(Path& payload) { scatterMiss(payload); }
+inline void sbtClosestHit(VisibilityRayData&, BuiltInTriangleIntersectionAttributes) {}   // no hit group for the visibility ray type: the payload stays "not visible"
+inline void sbtMiss(VisibilityRayData& payload) { visibilityMiss(payload); }
+inline void sbtClosestHit(ShadowRayHit& payload, BuiltInTriangleIntersectionAttributes attribs) { shadowTriangleMeshHit(payload, attribs); }
+inline void sbtMiss(ShadowRayHit&) {}                                                      // no miss program for the shadow ray type: dist stays 0
 }  // namespace ref
 
 namespace {
@@ -116,6 +128,7 @@ void makePair(Pair& p, int kind, Rnd& r, const orc::ProfileTable* prof, const or
                         case 5: OUT = (p).coatedC.CALL; break; case 6: OUT = (p).coatedD.CALL; break; case 7: OUT = (p).gratedC.CALL; break; case 8: OUT = (p).gratedD.CALL; break; default: OUT = (p).stack.CALL; break; }
 }  // namespace
 
+static void ref_compare_frames(int N, Rnd& r, PltptSpectralProfile* prof);
 static void ref_compare_more(int N, Rnd& r) {
     // ---- spectral profiles: two tabulated "conductors" (n, k tables, no icdf) and one emitter (pdf + icdf), random but well formed
     static PltptSpectralProfile prof[5];
@@ -1072,4 +1085,297 @@ static void ref_compare_more(int N, Rnd& r) {
         }
         osc.d = PltptSceneDesc{};
     }
+    ref_compare_frames(N, r, prof);
+}
+
+// ---- WHOLE FRAMES: both ray-generation programs of the pass as the reference wrote them (pltpt_sample.rt.slang main -> TraceRay -> closest-hit /
+// miss programs; pltpt_solve.rt.slang main -> NEE with generateLightSample, visibilityRay / manifoldNEESample (Manifolds.slangh: traceMNEEOccluders,
+// the Newton walk with its line search, manifoldForwardUnwind), evalNEE, evalEmissive, onMiss, forwardUnwind, measure), next to the oracle's
+// samplePixel / solvePixel, on random closed-ish scenes of large triangles with random materials of all ten types, emissive triangles in a light
+// collection, analytic lights of all six kinds and an environment map, under random option sets.  The only thing supplied to the reference text is
+// the intersection search behind TraceRay (ref_shims_late.h): DXR hardware in the reference, the oracle's ray caster here, the same for both sides.
+static void ref_compare_frames(int N, Rnd& r, PltptSpectralProfile* prof) {
+    constexpr uint32_t kTri = 20, kW = 4, kH = 4, kMaxB = 8;
+    static orc::Scene osc;
+    static PltptPackedVertex verts[3 * kTri];
+    static ref::PackedStaticVertexData rverts[3 * kTri];
+    static PltptGeometryInstance insts[kTri];
+    static PltptMeshDesc meshes[kTri];
+    static float world[16 * kTri], worldIT[16 * kTri];
+    static ref::float4x4 rworld[kTri];
+    static ref::float3x3 rworldIT[kTri];
+    static bool cw[kTri];
+    static PltptMaterialBlob blobs[kTri];
+    static PltptEmissiveTriangle etris[kTri];
+    static PltptEmissiveFlux eflux[kTri];
+    static uint32_t eactive[kTri], ealias[2 * kTri], perInst[kTri];
+    static ref::uint2 ralias[kTri];
+    static ref::PackedEmissiveTriangle retris[kTri];
+    static ref::EmissiveFlux rflux[kTri];
+    static PltptLightData lights[2];
+    static ref::LightData rlights[2];
+    static PltptBounce obounces[kW * kH * (kMaxB + 1)];
+    static ref::BounceData rbounces[kW * kH * (kMaxB + 1)];
+    static float ocolor[kW * kH * 4], oalbedo[kW * kH * 4], onormal[kW * kH * 4];
+    static ref::float4 rcolor[kW * kH], ralbedo[kW * kH], rnormal[kW * kH];
+    // one environment map for all scenes (its importance map is expensive to build): swapped into the scene when the scene uses it
+    constexpr uint32_t EW = 16, EH = 8;
+    static float envTexels[EW * EH * 4];
+    static orc::EnvMap sharedEnv;
+    PltptSceneDesc envDesc{};
+    {
+        for (uint32_t t = 0; t < EW * EH; ++t) {
+            const float sun = (t == 2 * EW + 5) ? 60.f : 1.f;
+            envTexels[4 * t] = sun * r.range(0.05f, 1.f); envTexels[4 * t + 1] = sun * r.range(0.05f, 1.f); envTexels[4 * t + 2] = sun * r.range(0.05f, 1.f); envTexels[4 * t + 3] = 1.f;
+        }
+        envDesc.envMapTexels = envTexels; envDesc.envMapWidth = EW; envDesc.envMapHeight = EH;
+        const float ang = -0.4f, ca = std::cos(ang), sa = std::sin(ang);
+        const float rot[12] = {ca, 0.f, sa, 0.f, 0.f, 1.f, 0.f, 0.f, -sa, 0.f, ca, 0.f}, inv[12] = {ca, 0.f, -sa, 0.f, 0.f, 1.f, 0.f, 0.f, sa, 0.f, ca, 0.f};
+        for (int k = 0; k < 12; ++k) { envDesc.envMap.transform[k] = rot[k]; envDesc.envMap.invTransform[k] = inv[k]; }
+        envDesc.envMap.tint[0] = 1.f; envDesc.envMap.tint[1] = 0.9f; envDesc.envMap.tint[2] = 0.8f; envDesc.envMap.intensity = 0.6f;
+        sharedEnv.init(envDesc);
+        ref::EnvMap& renv = ref::gScene.envMap;
+        for (int row = 0; row < 3; ++row) for (int c = 0; c < 4; ++c) { renv.data.transform[row][c] = rot[4 * row + c]; renv.data.invTransform[row][c] = inv[4 * row + c]; }
+        renv.data.tint = ref::float3(1.f, 0.9f, 0.8f); renv.data.intensity = 0.6f;
+        renv.envMap.ctx = &osc.env; renv.envMap.width = EW; renv.envMap.height = EH;
+        renv.envMap.loadFn = [](const void* c, int x, int y, int) { const orc::float3 t = static_cast<const orc::EnvMap*>(c)->texel(x, y); return ref::float4(t.x, t.y, t.z, 1.f); };
+        renv.envMap.sampleFn = [](const void* c, ref::float2 uv, float) { const orc::float3 t = static_cast<const orc::EnvMap*>(c)->sampleBilinear(orc::float2(uv.x, uv.y)); return ref::float4(t.x, t.y, t.z, 1.f); };
+        ref::EnvMapSampler& smp = ref::envMapSampler;
+        smp.importanceMap.ctx = &osc.env; smp.importanceMap.width = smp.importanceMap.height = orc::EnvMap::kDimension;
+        smp.importanceMap.loadFn = [](const void* c, int x, int y, int mip) { return static_cast<const orc::EnvMap*>(c)->load(uint32_t(x), uint32_t(y), uint32_t(mip)); };
+        smp.importanceMap.sampleFn = [](const void* c, ref::float2 uv, float) {
+            const int dim = int(orc::EnvMap::kDimension);
+            const int x = std::min(std::max(int(std::floor(uv.x * float(dim))), 0), dim - 1), y = std::min(std::max(int(std::floor(uv.y * float(dim))), 0), dim - 1);
+            return static_cast<const orc::EnvMap*>(c)->load(uint32_t(x), uint32_t(y), 0u); };
+        smp.importanceInvDim = ref::float2(1.f / float(orc::EnvMap::kDimension));
+        smp.importanceBaseMip = sharedEnv.baseMip;
+    }
+    // the reference side's scene services
+    ref::mTileSize = kW;
+    ref::bounceBuffer.p = rbounces;
+    ref::gOutputColor.p = rcolor; ref::gOutputColor.width = kW; ref::gOutputAlbedo.p = ralbedo; ref::gOutputAlbedo.width = kW; ref::gOutputNormal.p = rnormal; ref::gOutputNormal.width = kW;
+    ref::gScene.vertices.p = rverts;
+    ref::gScene.materials.blobs = reinterpret_cast<const ref::MaterialDataBlob*>(blobs);
+    ref::gScene.materials.textureFn = nullptr;
+    ref::gScene.indexFn = [](ref::GeometryInstanceID id, ref::uint tri) { return ref::uint3(3u * id.index + 3u * tri, 3u * id.index + 3u * tri + 1u, 3u * id.index + 3u * tri + 2u); };
+    ref::gScene.materialIDFn = [](ref::GeometryInstanceID id) { return id.index; };
+    static const orc::Scene* sc = &osc;
+    ref::TriangleHit::packFn = [](const ref::TriangleHit& h) {
+        orc::TriangleHit oh; oh.instanceID = h.instanceID.index; oh.primitiveIndex = h.primitiveIndex; oh.barycentrics = orc::float2(h.barycentrics.x, h.barycentrics.y);
+        uint32_t w[4]; sc->packHit(oh, w); return ref::PackedHitInfo(w[0], w[1], w[2], w[3]); };
+    ref::TriangleHit::unpackFn = [](ref::PackedHitInfo p, ref::TriangleHit& h) {
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w}; const orc::TriangleHit oh = sc->unpackHit(w);
+        h.instanceID.index = oh.instanceID; h.primitiveIndex = oh.primitiveIndex; h.barycentrics = ref::float2(oh.barycentrics.x, oh.barycentrics.y); };
+    static ref::float4x4* gW = rworld; static ref::float3x3* gWIT = rworldIT; static bool* gCW = cw;
+    ref::gScene.vertexDataFn = [](ref::TriangleHit hit) {   // Scene.slang:576-585
+        const ref::uint3 vtxIndices = ref::gScene.getIndices(hit.instanceID, hit.primitiveIndex);
+        ref::StaticVertexData vertices[3] = {ref::gScene.getVertex(vtxIndices[0]), ref::gScene.getVertex(vtxIndices[1]), ref::gScene.getVertex(vtxIndices[2])};
+        return ref::gScene.computeVertexData(vertices, gW[hit.instanceID.index], gWIT[hit.instanceID.index], gCW[hit.instanceID.index], hit.getBarycentricWeights()); };
+    ref::gCastClosest = [](ref::float3 o, ref::float3 d, float tMin, float tMax) {
+        const orc::RayHit h = sc->traceClosest(orc::float3(o.x, o.y, o.z), orc::float3(d.x, d.y, d.z), tMin, tMax);
+        ref::RayCastResult res; res.hit = h.hit.valid();
+        if (res.hit) { res.instanceIndex = h.hit.instanceID; res.primitiveIndex = h.hit.primitiveIndex; res.barycentrics = ref::float2(h.hit.barycentrics.x, h.hit.barycentrics.y); res.t = h.t; }
+        return res; };
+    ref::gCastAny = [](ref::float3 o, ref::float3 d, float tMin, float tMax) { return sc->traceAny(orc::float3(o.x, o.y, o.z), orc::float3(d.x, d.y, d.z), tMin, tMax); };
+    const uint32_t kTypes[10] = {PLTPT_MATERIAL_DIFFUSE, PLTPT_MATERIAL_CONDUCTOR, PLTPT_MATERIAL_DIELECTRIC, PLTPT_MATERIAL_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_THIN_DIELECTRIC,
+                                 PLTPT_MATERIAL_COATED_CONDUCTOR, PLTPT_MATERIAL_COATED_OPAQUE_DIELECTRIC, PLTPT_MATERIAL_GRATED_CONDUCTOR, PLTPT_MATERIAL_GRATED_OPAQUE_DIELECTRIC,
+                                 PLTPT_MATERIAL_MULTILAYERED_STACK};
+    auto half = [&](float lo, float hi) { return uint16_t(ref::f32tof16(r.range(lo, hi))); };
+    auto halfBits = [&](float lo, float hi) { return ref::f32tof16(r.range(lo, hi)); };
+    const int scenes = std::max(4, N / 64);
+    uint64_t pixels = 0, identicalPixels = 0, vertices = 0, mneePixels = 0, evals = 0;
+    for (int i = 0; i < scenes; ++i) {
+        // ---- geometry: large triangles around the origin, one instance (own matrix, own material) each
+        const bool smoothGlass = r.u() < .35f;   // a scene rich in smooth dielectrics: manifold walks
+        for (uint32_t t = 0; t < kTri; ++t) {
+            const orc::float3 c0 = r.dir() * r.range(1.5f, 4.f);
+            for (int k = 0; k < 3; ++k) {
+                const orc::float3 pos = c0 + r.f3(-5.f, 5.f); const orc::float2 tc = r.f2(-1.f, 2.f);
+                const float sgn = r.u() < .2f ? 0.f : (r.u() < .5f ? -1.f : 1.f);
+                const uint32_t w0 = halfBits(-1.f, 1.f) | (halfBits(-1.f, 1.f) << 16), w1 = halfBits(-1.f, 1.f) | (ref::f32tof16(sgn) << 16), w2 = r.g();
+                PltptPackedVertex& v = verts[3 * t + k];
+                for (int a = 0; a < 3; ++a) v.position[a] = pos[a];
+                v.texCrd[0] = tc.x; v.texCrd[1] = tc.y;
+                v.packedNormalTangentCurveRadius[0] = w0; v.packedNormalTangentCurveRadius[1] = w1; v.packedNormalTangentCurveRadius[2] = w2;
+                rverts[3 * t + k].position = R(pos); rverts[3 * t + k].texCrd = R(tc);
+                rverts[3 * t + k].packedNormalTangentCurveRadius = ref::float3(ref::asfloat(ref::uint(w0)), ref::asfloat(ref::uint(w1)), ref::asfloat(ref::uint(w2)));
+            }
+            insts[t] = PltptGeometryInstance{}; meshes[t] = PltptMeshDesc{};
+            meshes[t].vertexCount = 3; meshes[t].indexCount = 0;
+            cw[t] = r.u() < .5f;
+            insts[t].flags = cw[t] ? PLTPT_INSTANCE_FLAG_OBJECT_FRONT_FACE_CW : 0u;
+            insts[t].globalMatrixID = t; insts[t].materialID = t; insts[t].geometryID = t; insts[t].vbOffset = 3 * t;
+            const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex), scl = r.f3(0.7f, 1.4f), tr = r.f3(-.5f, .5f);
+            const orc::float3 cols[3] = {ex * scl.x, ey * scl.y, ez * scl.z}, colsIT[3] = {ex / scl.x, ey / scl.y, ez / scl.z};
+            float* wm = world + 16 * t; float* wit = worldIT + 16 * t;
+            for (int row = 0; row < 3; ++row) {
+                for (int c = 0; c < 3; ++c) { wm[4 * row + c] = cols[c][row]; wit[4 * row + c] = colsIT[c][row]; rworld[t][row][c] = wm[4 * row + c]; rworldIT[t][row][c] = wit[4 * row + c]; }
+                wm[4 * row + 3] = tr[row]; wit[4 * row + 3] = 0.f; rworld[t][row][3] = tr[row];
+            }
+            for (int c = 0; c < 4; ++c) { wm[12 + c] = wit[12 + c] = c == 3 ? 1.f : 0.f; rworld[t][3][c] = wm[12 + c]; }
+            int kind = int(r.u() * 9.999f);
+            if (smoothGlass && r.u() < .6f) kind = r.u() < .5f ? 2 : 4;
+            const bool emitter = r.u() < .25f;   // only the diffuse material emits (PLTDiffuseMaterial.slang:44-47); a few non-diffuse records keep an emission id on purpose
+            if (emitter && r.u() < .9f) kind = 0;
+            PltptMaterialBlob& blob = blobs[t];
+            blob = PltptMaterialBlob{};
+            blob.header[0] = kTypes[kind] | (1u << 31) | (r.u() < .6f ? (1u << 28) : 0u);
+            for (int k = 0; k < 4; ++k) { blob.baseColor[k] = half(0.05f, 1.f); blob.specular[k] = half(0.02f, 2.5f); blob.data1[k] = half(0.05f, 3.f); blob.data2[k] = half(0.02f, 2.5f); }
+            if (r.u() < .08f) blob.baseColor[3] = 0;   // fully transparent: the alpha pass-through
+            if (r.u() < .15f || (smoothGlass && (kind == 2 || kind == 4))) blob.specular[1] = 0;
+            for (int k = 0; k < 3; ++k) blob.transmission[k] = half(0.2f, 1.f);
+            blob.IoR = half(1.05f, 2.2f);
+            const uint32_t n = uint32_t(r.u() * 1.999f) * 2u;
+            blob.iorNSpectralId = n; blob.iorKSpectralId = n + 1u; blob.emissionSpectralId = emitter ? 4u : PLTPT_NO_SPECTRAL_PROFILE;
+            if (kind == 7 || kind == 8) blob.data1[3] = uint16_t(((uint32_t(r.u() * 2.99f) | (r.u() < .2f ? 0x10u : 0u)) << 8) | (1u + uint32_t(r.u() * 7.99f)));
+            if (kind == 9) blob.data1[3] = uint16_t(1u + uint32_t(r.u() * 11.99f));
+        }
+        PltptSceneDesc d{};
+        d.vertices = verts; d.vertexCount = 3 * kTri; d.geometryInstances = insts; d.instanceCount = kTri; d.meshes = meshes; d.meshCount = kTri;
+        d.worldMatrices = world; d.inverseTransposeWorldMatrices = worldIT; d.matrixCount = kTri; d.materialData = blobs; d.materialCount = kTri;
+        d.spectralProfiles = prof; d.profileCount = 5;
+        d.hitInfoTypeBits = 3; d.hitInfoInstanceIDBits = 5; d.hitInfoPrimitiveIndexBits = 1;
+        // ---- the light collection over the emissive instances (LightCollection.slang: packed world-space triangles, flux, active list,
+        // per-instance offsets; EmissivePowerSampler's alias table)
+        uint32_t ne = 0; float total = 0.f;
+        for (uint32_t t = 0; t < kTri; ++t) {
+            perInst[t] = 0xffffffffu;
+            if (blobs[t].emissionSpectralId == PLTPT_NO_SPECTRAL_PROFILE) continue;
+            perInst[t] = ne;
+            const float* wm = world + 16 * t;
+            orc::float3 vs[3];
+            for (int k = 0; k < 3; ++k) {
+                const float* P = verts[3 * t + k].position;
+                for (int row = 0; row < 3; ++row) vs[k][row] = ((wm[4 * row + 0] * P[0] + wm[4 * row + 1] * P[1]) + wm[4 * row + 2] * P[2]) + wm[4 * row + 3];
+                const uint32_t uv = ref::f32tof16(verts[3 * t + k].texCrd[0]) | (ref::f32tof16(verts[3 * t + k].texCrd[1]) << 16);
+                float uvf; std::memcpy(&uvf, &uv, 4);
+                for (int a = 0; a < 3; ++a) etris[ne].posAndTexCoords[k][a] = vs[k][a];
+                etris[ne].posAndTexCoords[k][3] = uvf;
+                retris[ne].posAndTexCoords[k] = ref::float4(vs[k].x, vs[k].y, vs[k].z, uvf);
+            }
+            const orc::float3 fn = orc::cross(vs[1] - vs[0], vs[2] - vs[0]);
+            const float area = 0.5f * orc::length(fn);
+            etris[ne].normal = orc::encodeNormal2x16(orc::normalize(cw[t] ? -fn : fn)); std::memcpy(&etris[ne].area, &area, 4); etris[ne].materialID = t; etris[ne].lightIdx = 0;
+            retris[ne].normal = etris[ne].normal; retris[ne].area = etris[ne].area; retris[ne].materialID = t; retris[ne].lightIdx = 0;
+            eflux[ne].flux = area * r.range(0.5f, 2.f); total += eflux[ne].flux; rflux[ne].flux = eflux[ne].flux;
+            ++ne;
+        }
+        for (uint32_t t = 0; t < ne; ++t) {
+            eactive[t] = t;
+            const uint32_t above = uint32_t(r.u() * (ne - 0.001f)), below = uint32_t(r.u() * (ne - 0.001f));
+            const uint32_t px = (ref::f32tof16(r.u()) << 16) | ((above >> 8) & 0xffffu), py = ((above & 0xffu) << 24) | (below & 0xffffffu);
+            ealias[2 * t] = px; ealias[2 * t + 1] = py; ralias[t] = ref::uint2(px, py);
+        }
+        const float invSum = ne ? 1.f / total : 0.f;
+        d.emissiveTriangles = ne ? etris : nullptr; d.emissiveTriangleCount = ne; d.emissiveFlux = eflux; d.activeTriangles = eactive; d.activeTriangleCount = ne;
+        d.perMeshInstanceOffset = perInst; d.triangleAliasTable = ealias; d.invWeightsSum = invSum;
+        ref::LightCollection& lc = ref::gScene.lightCollection;
+        lc.triangleCount = ne; lc.activeTriangleCount = ne; lc.triangleData.p = retris; lc.activeTriangles.p = eactive; lc.fluxData.p = rflux; lc.perMeshInstanceOffset.p = perInst;
+        ref::gPowerSampler._emissivePower.invWeightsSum = invSum; ref::gPowerSampler._emissivePower.triangleAliasTable.p = ralias;
+        // ---- analytic lights: none, one or two, of any of the six kinds
+        const uint32_t nl = std::min(2u, uint32_t(r.u() * 3.999f));
+        for (uint32_t l = 0; l < nl; ++l) {
+            PltptLightData& L = lights[l]; ref::LightData& Lr = rlights[l];
+            L = PltptLightData{}; Lr = ref::LightData();
+            L.type = uint32_t(r.u() * 5.999f);
+            const orc::float3 pos = r.f3(-2.f, 2.f), dir = r.dir();
+            for (int k = 0; k < 3; ++k) { L.posW[k] = pos[k]; L.dirW[k] = dir[k]; }
+            L.openingAngle = r.u() < .5f ? orc::kPi : r.range(0.4f, 1.5f);
+            L.cosOpeningAngle = std::cos(L.openingAngle);
+            L.penumbraAngle = r.u() < .5f ? 0.f : r.range(0.01f, 0.3f);
+            L.cosSubtendedAngle = r.u() < .3f ? 0.9999893f : std::cos(r.range(0.001f, 0.4f));
+            L.intensitySpectrumId = 4u;
+            L.surfaceArea = r.range(0.05f, 8.f);
+            const orc::float3 ez = r.dir(), ex = orc::perp_stark(ez), ey = orc::cross(ez, ex), scl = r.f3(0.2f, 1.5f);
+            const orc::float3 cols[3] = {ex * scl.x, ey * scl.y, ez * scl.z}, colsIT[3] = {ex / scl.x, ey / scl.y, ez / scl.z};
+            for (int row = 0; row < 3; ++row) {
+                for (int c = 0; c < 3; ++c) { L.transMat[4 * row + c] = cols[c][row]; L.transMatIT[4 * row + c] = colsIT[c][row]; }
+                L.transMat[4 * row + 3] = pos[row]; L.transMatIT[4 * row + 3] = 0.f;
+            }
+            L.transMat[15] = 1.f; L.transMatIT[15] = 1.f;
+            Lr.posW = R(pos); Lr.type = L.type; Lr.dirW = R(dir); Lr.openingAngle = L.openingAngle; Lr.cosOpeningAngle = L.cosOpeningAngle; Lr.cosSubtendedAngle = L.cosSubtendedAngle;
+            Lr.penumbraAngle = L.penumbraAngle; Lr.intensitySpectrumId = L.intensitySpectrumId; Lr.surfaceArea = L.surfaceArea;
+            for (int row = 0; row < 4; ++row) for (int c = 0; c < 4; ++c) { Lr.transMat[row][c] = L.transMat[4 * row + c]; Lr.transMatIT[row][c] = L.transMatIT[4 * row + c]; }
+        }
+        d.lights = nl ? lights : nullptr; d.lightCount = nl;
+        ref::gScene.lights = rlights; ref::gScene.lightCount = nl;
+        osc.init(d);
+        const bool withEnv = r.u() < .5f;
+        if (withEnv) std::swap(osc.env, sharedEnv);
+        // ---- camera: a pinhole at a random place looking at the origin
+        PltptCameraData cam{};
+        {
+            const orc::float3 pos = r.dir() * r.range(0.2f, 2.5f), target = r.f3(-.5f, .5f), up0 = r.dir();
+            const orc::float3 w = orc::normalize(target - pos), u = orc::normalize(orc::cross(w, up0)), v = orc::cross(u, w);
+            const float fd = r.range(0.5f, 3.f), halfH = r.range(0.3f, 1.2f) * fd, halfW = halfH * float(kW) / float(kH);
+            for (int k = 0; k < 3; ++k) { cam.posW[k] = pos[k]; cam.cameraW[k] = w[k] * fd; cam.cameraU[k] = u[k] * halfW; cam.cameraV[k] = v[k] * halfH; }
+            cam.jitterX = r.range(-.5f, .5f) / float(kW); cam.jitterY = r.range(-.5f, .5f) / float(kH);
+            cam.nearZ = 0.1f; cam.farZ = 1000.f; cam.focalDistance = fd;
+            if (r.u() < .3f) { cam.polarizer = r.range(0.2f, 1.f); cam.polarizerTheta = r.range(0.f, 3.f); }
+        }
+        std::memcpy(static_cast<void*>(&ref::gScene.camera.data), &cam, sizeof cam);
+        // ---- options
+        orc::Integrator integ;
+        integ.scene = &osc;
+        PltptOptions& o = integ.opt;
+        o = PltptOptions{}; o.sampleGenerator = 1; o.debugViewIntensity = 1.f;
+        o.maxBounces = 2u + uint32_t(r.u() * (kMaxB - 2 + 0.999f)); o.tileSize = kW; o.HWSS = 4; o.HWSSDoMIS = r.u() < .7f;
+        o.sourcingAreaFromEmissiveGeometry = r.range(0.01f, 4.f); o.sourcingMaxBeamOmega = r.range(0.001f, 0.1f);
+        o.useDirectLights = r.u() < .85f; o.useEnvLights = r.u() < .9f; o.useEmissiveLights = r.u() < .9f; o.useAnalyticLights = r.u() < .9f;
+        o.alphaMasking = r.u() < .8f; o.doNEE = r.u() < .9f; o.doMIS = r.u() < .8f; o.emissiveSampler = r.u() < .5f ? PLTPT_EMISSIVE_SAMPLER_POWER : PLTPT_EMISSIVE_SAMPLER_UNIFORM;
+        o.doRussianRoulette = r.u() < .6f; o.NEEUsePerTileSG = r.u() < .3f; o.doImportanceSampleEmitters = r.u() < .6f; o.doMNEE = r.u() < .75f;
+        o.MNEEMaxOccluders = 2; o.MNEEMaxIterations = r.u() < .5f ? 40u : 12u; o.MNEESolverThreshold = r.u() < .5f ? 1e-5f : 5e-5f;
+        integ.cam = cam; integ.width = kW; integ.height = kH;
+        integ.bounces = obounces; integ.outColor = ocolor; integ.outAlbedo = oalbedo; integ.outNormal = onormal;
+        ref::mMaxBounces = o.maxBounces; ref::mHWSSDoMIS = o.HWSSDoMIS; ref::kUseDirectLights = o.useDirectLights;
+        ref::kUseEnvLight = integ.kUseEnvLight(); ref::kUseEmissiveLights = integ.kUseEmissiveLights(); ref::kUseAnalyticLights = integ.kUseAnalyticLights();   // PLTPT.cpp:232-238
+        ref::kAlphaMasking = o.alphaMasking; ref::kImportanceSampleEmissiveSpectra = o.doImportanceSampleEmitters;
+        ref::kDoNEE = integ.kDoNEE(); ref::kDoMSonNEE = integ.kDoMSonNEE(); ref::kDoMIS = integ.kDoMIS(); ref::kNEEUsePerTileSelectorSG = integ.kNEEUsePerTileSG();
+        ref::kDoRussianRoulette = o.doRussianRoulette;
+        ref::kMNEEMaxIterations = int(o.MNEEMaxIterations); ref::kMNEESolverThreshold = o.MNEESolverThreshold;
+        ref::kSourcingAreaFromEmissiveGeometry = o.sourcingAreaFromEmissiveGeometry; ref::kSourcingMaxBeamOmega = o.sourcingMaxBeamOmega;
+        ref::gEmissiveKind = o.emissiveSampler == PLTPT_EMISSIVE_SAMPLER_POWER ? 2 : 1;
+        ref::kOutputSize = ref::uint2(kW, kH); ref::kTile = ref::uint2(0u, 0u);
+        for (uint32_t frame = 0; frame < 2; ++frame) {
+            integ.frameCount = 7u * uint32_t(i) + frame; ref::gFrameCount = integ.frameCount;
+            std::memset(obounces, 0xcd, sizeof obounces); std::memset(static_cast<void*>(rbounces), 0xcd, sizeof rbounces);
+            for (uint32_t py = 0; py < kH; ++py) for (uint32_t px = 0; px < kW; ++px) {
+                integ.samplePixel(px, py);
+                ref::gDispatchRaysIndex = ref::uint3(px, py, 0u);
+                ref::sampleRayGen();
+            }
+            Cmp cb("pltpt_sample.main_bounce_records"), cg("pltpt_sample.main_guides"), cc("pltpt_solve.main_color");
+            for (uint32_t py = 0; py < kH; ++py) for (uint32_t px = 0; px < kW; ++px) {
+                const uint32_t pix = py * kW + px;
+                // the records of this path, up to the one that ends it (the rest of the slot is never written by either side)
+                for (uint32_t p = 0; p <= o.maxBounces; ++p) {
+                    const PltptBounce& ob = obounces[size_t(pix) * (o.maxBounces + 1) + p];
+                    const ref::BounceData& rb = rbounces[size_t(pix) * (o.maxBounces + 1) + p];
+                    for (int k = 0; k < 4; ++k) cb.add(ob.hit[k], uint32_t(rb.hit[k]));
+                    cb.add(ob.encodedWi[0], rb.encodedWi.x); cb.add(ob.encodedWi[1], rb.encodedWi.y); cb.add(ob.sampledBsdfLobe, uint32_t(rb.sampledBsdfLobe)); cb.add(ob.flags, uint32_t(rb.flags.flags));
+                    cb.add(ob.pathContribution, rb.pathContribution); cb.add(ob.lastNonDeltaPdf, rb.lastNonDeltaPdf);
+                    ++vertices;
+                    orc::RayFlags f; f.flags = ob.flags;
+                    if (f.miss() || f.terminated()) break;
+                }
+                for (int k = 0; k < 4; ++k) { cg.add(oalbedo[pix * 4 + k], ralbedo[pix][k]); cg.add(onormal[pix * 4 + k], rnormal[pix][k]); }
+            }
+            for (uint32_t py = 0; py < kH; ++py) for (uint32_t px = 0; px < kW; ++px) {
+                const uint32_t pix = py * kW + px;
+                integ.solvePixel(px, py);
+                ref::gDispatchRaysIndex = ref::uint3(px, py, 0u);
+                ref::solveRayGen();
+                bool same = true;
+                for (int k = 0; k < 4; ++k) { cc.add(ocolor[pix * 4 + k], rcolor[pix][k]); same = same && ocolor[pix * 4 + k] == rcolor[pix][k]; }
+                ++pixels; identicalPixels += same ? 1u : 0u;
+                mneePixels += (ocolor[pix * 4] > 0.f || ocolor[pix * 4 + 1] > 0.f || ocolor[pix * 4 + 2] > 0.f) ? 1u : 0u;
+            }
+        }
+        evals += integ.statEvals;
+        if (withEnv) std::swap(osc.env, sharedEnv);
+    }
+    { Stat& s = g_stats["pltpt_solve.main_color"]; s.identical = identicalPixels; s.units = pixels; }
+    if (std::getenv("REF_DEBUG")) std::fprintf(stderr, "frames: %llu pixels, %llu lit, %.2f records per path, %llu unwind evals, %llu shadow-type queries of which %llu line-search proposals\n", (unsigned long long)pixels, (unsigned long long)mneePixels, double(vertices) / double(pixels), (unsigned long long)evals, (unsigned long long)ref::gWalks, (unsigned long long)ref::gProposals);
+    ref::gEmissiveKind = 0;
+    osc.d = PltptSceneDesc{};
 }

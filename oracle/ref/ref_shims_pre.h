@@ -131,15 +131,16 @@ struct TriangleLightHit { uint triangleIndex = 0; float3 posW, normalW; };  // E
 // `emissiveSampler` is EmissiveUniformSampler or EmissivePowerSampler by a define (EmissiveLightSampler.slang:36-52); both are transpiled
 // further down, so the stand-in forwards to emissiveSamplerDispatch (ref_shims_post.h, found by argument-dependent lookup at instantiation),
 // which calls the transpiled sampler the comparison has selected, or draws no sample
+float emissiveEvalPdfDispatch(float3 posW, float3 normalW, bool upperHemisphere, struct TriangleLightHit hit);  // ref_shims_post.h
 struct EmissiveSamplerStandIn {
     template <class S> bool sampleLight(float3 posW, float3 normalW, bool upperHemisphere, S& sg, float wavelength, bool importanceSampleSpectrum, TriangleLightSample& ls) {
         return emissiveSamplerDispatch(posW, normalW, upperHemisphere, sg, wavelength, importanceSampleSpectrum, ls);
     }
+    float evalPdf(float3 posW, float3 normalW, bool upperHemisphere, TriangleLightHit hit) { return emissiveEvalPdfDispatch(posW, normalW, upperHemisphere, hit); }
 };
 static EmissiveSamplerStandIn emissiveSampler;
 
 // ---- what `measure` (pltpt_solve.rt.slang:96-147) expects (the camera block is the transpiled CameraData.slang / Camera.slang): the solve payload (Path.slang:200-225, without its generators), two more switches of pltpt.slangh:95-104
-struct PLTSolve { float3 Lrgb = .0f; float3 pathOrigin, pathNormal; float wavelength = 0.f; };
 static bool kUseDirectLights = true, mHWSSDoMIS = true;
 // ---- what the closest-hit program of pltpt_sample.rt.slang expects: more switches of pltpt.slangh:90-118, the pass's resources
 // (pltpt.slangh:84-88,123) as plain arrays, the DXR system values of the current hit, the per-path generator (Utils/Sampling/SampleGenerator:
@@ -151,7 +152,29 @@ template <class T> struct RWTexture2D { T* p = nullptr; uint width = 0; T& opera
 template <class T> struct RWStructuredBuffer { T* p = nullptr; T& operator[](uint i) { return p[i]; } };
 static RWTexture2D<float4> gOutputColor, gOutputNormal, gOutputAlbedo;
 struct BuiltInTriangleIntersectionAttributes { float2 barycentrics; };
-struct SampleGenerator { orc::SampleGenerator g; uint next() { return g.next(); } };
+// Utils/Sampling/SampleGenerator: SampleGenerator(pixel, sampleNumber) -- the pass's generator is the xoshiro the oracle restates and pins to
+// PseudorandomTests.cpp; both sides step the same object type
+struct SampleGenerator {
+    orc::SampleGenerator g;
+    SampleGenerator() = default;
+    SampleGenerator(uint2 pixel, uint sampleNumber) : g(pixel.x, pixel.y, sampleNumber) {}
+    uint next() { return g.next(); }
+};
+static bool kDoNEE = true, kDoMSonNEE = true, kDoMIS = true, kImportanceSampleEmissiveSpectra = true;   // pltpt.slangh:105-116
+static constexpr uint kMNEEMaxMSOccluders = 2;                  // Manifolds.slangh:40-54 (the defines' defaults; PLTPT.h:123-125 holds the same values)
+static int kMNEEMaxIterations = 40;
+static float kMNEESolverThreshold = 1e-5f;
+static const float kShadowRayTMin = 1e-4f;                      // ShadowRays.slangh:46
+// ---- the DXR runtime around the three programs of a stage (HLSL built-ins): launch index, constant buffer (pltpt.slangh:60-75), the
+// acceleration structure handle.  TraceRay itself is in ref_shims_late.h.
+static uint2 kTile = uint2(0u, 0u), kOutputSize = uint2(0u, 0u);
+static uint gFrameCount = 0;
+static uint3 gDispatchRaysIndex = uint3(0u, 0u, 0u);
+inline uint3 DispatchRaysIndex() { return gDispatchRaysIndex; }
+struct RtAccelStandIn {};
+static constexpr uint RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH = 0x4u;
+static constexpr uint defaultVisibilityRayId = 0, defaultShadowRayId = 1;   // ShadowRays.slangh:37-44 with PLTPT.cpp:60-61,221-222
+static constexpr uint rayTypeCount = 2;                         // PLTPT.cpp:60-61: visibility and shadow ray types (the sample stage has one)
 #define DO_DEBUG_VIEW 0
 
 }  // namespace ref

@@ -17,7 +17,7 @@
 #include "_ref/ref_gen.h"     // the transpiled reference: ref::
 
 namespace {
-struct Stat { uint64_t n = 0, nonfiniteMismatch = 0; double maxUlp = 0, maxRel = 0, maxAbs = 0; };
+struct Stat { uint64_t n = 0, nonfiniteMismatch = 0, identical = 0, units = 0; double maxUlp = 0, maxRel = 0, maxAbs = 0; };
 std::map<std::string, Stat> g_stats;
 std::vector<std::string> g_order;
 
@@ -235,7 +235,9 @@ int main(int argc, char** argv) {
     std::printf("{");
     for (size_t i = 0; i < g_order.size(); ++i) {
         const Stat& s = g_stats[g_order[i]];
-        std::printf("%s\n \"%s\": {\"n\": %" PRIu64 ", \"max_ulp\": %.0f, \"max_rel\": %.3e, \"max_abs\": %.3e, \"mismatches\": %" PRIu64 "}", i ? "," : "", g_order[i].c_str(), s.n, s.maxUlp, s.maxRel, s.maxAbs, s.nonfiniteMismatch);
+        std::printf("%s\n \"%s\": {\"n\": %" PRIu64 ", \"max_ulp\": %.0f, \"max_rel\": %.3e, \"max_abs\": %.3e, \"mismatches\": %" PRIu64, i ? "," : "", g_order[i].c_str(), s.n, s.maxUlp, s.maxRel, s.maxAbs, s.nonfiniteMismatch);
+        if (s.units) std::printf(", \"units\": %" PRIu64 ", \"identical_units\": %" PRIu64, s.units, s.identical);
+        std::printf("}");
     }
     std::printf("\n}\n");
     return 0;

@@ -29,6 +29,7 @@ Rewrite rules (all mechanical; each is a regular expression or a brace-matched b
   R12 `let x = e` -> `auto x = e`
   R13 `enum class X : T` -> `enum X : T` (Slang converts a scoped enumerator to its underlying type in `switch (uint)` / `uint(...)`; C++
       only does so for an unscoped enumeration, whose enumerators can still be written `X::Name`)
+  R14 the ray-generation programs `void main()` of the sample and the solve shader -> `sampleRayGen()` / `solveRayGen()`
   R11 the handful of vector-condition ternaries (`c ? a : b` with bool2 `c`, DiffractionGrating.slang only) -> select(c, a, b); listed in PATCHES
       with the exact source text they replace -- the script fails if a patch no longer matches.
 """
@@ -76,7 +77,7 @@ SOURCES = [
     ("literal", '#include "../ref/ref_shims_mid.h"'),
     ("Scene/Material/ShadingUtils.slang", ["ShadingFrame", "rgbToNormal", "rgToNormal", "computeShadingFrameFromNormalMap", "applyNormalMap", "computeTangentSpace"]),
     ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getVertex", "getFaceNormalInObjectSpace", "computeVertexData"],
-                           "SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap; "
+                           "RtAccelStandIn rtAccel; SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap; "
                            "StructuredBuffer<PackedStaticVertexData> vertices; uint3 (*indexFn)(GeometryInstanceID, uint) = nullptr; "
                            "uint3 getIndices(GeometryInstanceID instanceID, uint triangleIndex) { return indexFn(instanceID, triangleIndex); }  /* index-buffer fetch: engine service */ "
                            "VertexData (*vertexDataFn)(TriangleHit) = nullptr; VertexData getVertexData(TriangleHit hit) { return vertexDataFn(hit); }  /* instance -> vertices, matrices: composed by the caller from getVertex / computeVertexData */ "
@@ -115,13 +116,20 @@ SOURCES = [
     ("Rendering/Utils/LightsSamplingUtils.slang", None),
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
     ("../RenderPasses/PLTPT/LightSampling.slangh", None),
+    ("../RenderPasses/PLTPT/Path.slang", ["RayFlags", "BounceData", "Path", "PLTSolve"]),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
-    ("../RenderPasses/PLTPT/Path.slang", ["RayFlags", "BounceData", "Path"]),
     ("literal", '#include "../ref/ref_shims_late.h"'),
-    ("../RenderPasses/PLTPT/pltpt.slangh", ["appendBounce", "RR"]),
-    ("../RenderPasses/PLTPT/pltpt_sample.rt.slang", ["shouldTerminatePath", "pltSampleBSDF", "scatterMiss", "scatterTriangleMeshClosestHit"]),
-    ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep"]),
+    ("../RenderPasses/PLTPT/ShadowRays.slangh", ["VisibilityRayData", "visibilityMiss", "visibilityRay", "ShadowRayHit", "shadowTriangleMeshHit", "shadowRay"]),
+    ("../RenderPasses/PLTPT/pltpt.slangh", ["readBounce", "appendBounce", "RR"]),
+    ("../RenderPasses/PLTPT/pltpt_sample.rt.slang", ["shouldTerminatePath", "pltSampleBSDF", "scatterMiss", "scatterTriangleMeshClosestHit", "main"]),
+    ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["forwardHWSSMis", "forwardUnwindStep", "forwardUnwind", "wasNEEAvailable", "evalEmissive"]),
+    ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep", "MSHitData", "ManifoldSampleData", "manifoldSampleVertex", "traceMNEEOccluders",
+                                                "MNEEStep", "manifoldNEESample"]),
+    ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["manifoldForwardUnwind", "evalNEE", "NEE", "onMiss", "main"]),
 ]
+
+# the two ray-generation programs are both called `main`: renamed after their file (R14)
+ENTRY_POINTS = {"PLTPT/pltpt_sample.rt.slang": "sampleRayGen", "PLTPT/pltpt_solve.rt.slang": "solveRayGen"}
 
 STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
 # property reads outside the declaring struct: `roughness` is a property of both surface types, `q` of FractalSurface only (a plain
@@ -365,6 +373,9 @@ def transpile(path, s, struct_names):
                 raise SystemExit(f"patch for {path} no longer matches: {old[:60]!r}")
             s = s.replace(old, new)
     s = strip_comments_keep_lines(s)
+    for suffix, name in ENTRY_POINTS.items():   # R14
+        if path.endswith(suffix):
+            s = re.sub(r"\bvoid\s+main\s*\(\)", f"void {name}()", s)
     # R1
     s = re.sub(r"^\s*(__exported\s+)?import\s+[\w.]+\s*;\s*$", "", s, flags=re.M)
     s = re.sub(r'^\s*#include\s+"[^"]*"\s*$', "", s, flags=re.M)
@@ -403,13 +414,19 @@ def transpile(path, s, struct_names):
     s = re.sub(r"\brgb\.b\b", "rgb.z", s)
     s = re.sub(r"\.([xyzw]{2,4})\b(?!\s*\()", r".\1()", s)
     s = per_function(s, scalar_swizzles)
-    if re.search(r"PLTPT/(Path\.slang|pltpt\.slangh|pltpt_sample\.rt\.slang)$", path):   # R5: RayFlags / BounceData properties with setters
+    if re.search(r"PLTPT/(Path\.slang|pltpt\.slangh|pltpt_sample\.rt\.slang|pltpt_solve\.rt\.slang)$", path):   # R5: RayFlags / BounceData properties with setters
         props = "MSCompatibleBounces|lastBounceWasDelta|dispersiveDeltaSegment|onlyDelta|miss|terminated"
         s = re.sub(rf"(\b[\w.]*flags)\.({props})\s*\|=\s*([^;]+);", r"\1.set_\2(\1.\2() | (\3));", s)
         s = re.sub(rf"(\b[\w.]*flags)\.({props})\s*=(?!=)\s*([^;]+);", r"\1.set_\2(\3);", s)
-        s = re.sub(rf"(\b[\w.]*flags)\.({props})\b(?!\s*\()", r"\1.\2()", s)
+        s = re.sub(rf"(\b[\w.]*[fF]lags)\.({props})\b(?!\s*\()", r"\1.\2()", s)
+        s = re.sub(r"(\b[\w.]*flags)\.valid\b(?!\s*\()", r"\1.valid()", s)
+        s = re.sub(r"\bbounce\.wi\b(?!\s*[\(=])", "bounce.wi()", s)
         s = re.sub(r"\bbounce\.wi\s*=(?!=)\s*([^;]+);", r"bounce.set_wi(\1);", s)
+        s = re.sub(r"\bbsdfProp\.(canManifoldWalk(?:Reflective|Transmissive)|isEmissive)\b(?!\s*\()", r"bsdfProp.\1()", s)
+    if re.search(r"PLTPT/(Manifolds\.slangh|pltpt_solve\.rt\.slang)$", path):   # R5: ShadowRayHit.isHit, MSHitData.index read outside their structs
+        s = re.sub(r"\.isHit\b(?!\s*\()", ".isHit()", s)
         s = re.sub(r"\bbsdfProp\.(canManifoldWalk(?:Reflective|Transmissive))\b(?!\s*\()", r"bsdfProp.\1()", s)
+        s = re.sub(r"(\bhits\[[^\]]*\])\.index\b(?!\s*\()", r"\1.index()", s)
     for pu in PROPERTY_USES + (PROPERTY_USES_FRACTAL if re.search(r"typedef\s+FractalSurface\s+SurfaceType", s) else []):
         s = re.sub(rf"\b({pu})\b(?!\s*\()", r"\1()", s)
     # R10

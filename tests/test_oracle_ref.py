@@ -8,8 +8,11 @@ importance sampler), the ten PLT material loaders (PLT*Material.slang over Mater
 the same 128-byte records, with Uniform and with Texture-mode handles), the shading data at a hit (MaterialFactory.slang prepareShadingData composed
 from ShadingUtils.slang: tangent-space orthonormalisation, RGB / RG normal maps, opacity, double-sided flip; Scene.slang computeVertexData), primary rays (Camera.slang over the same 656-byte CameraData block), Russian roulette,
 the manifold solver's geometry and Newton step (differentialShadingGeometry, manifoldOneStep), the WHOLE closest-hit and miss programs of the sample
-stage (pltpt_sample.rt.slang over Path.slang and appendBounce: path book-keeping, bounce records, guide outputs), `measure` of the solve shader and the packed-record decoders (snorm /
-octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) -- textually into C++ (where /root/reference lies; nothing of it is
+stage (pltpt_sample.rt.slang over Path.slang and appendBounce: path book-keeping, bounce records, guide outputs), `measure` of the solve shader, the packed-record decoders (snorm /
+octahedral normals, PackedEmissiveTriangle, PackedStaticVertexData) and finally BOTH RAY-GENERATION PROGRAMS WHOLE (pltpt_sample.rt.slang main; pltpt_solve.rt.slang main with NEE,
+evalNEE, evalEmissive, onMiss, forwardUnwind; Manifolds.slangh traceMNEEOccluders / manifoldNEESample / manifoldForwardUnwind; ShadowRays.slangh's ray programs) rendering
+whole frames of random scenes next to the oracle's samplePixel / solvePixel -- only the intersection search behind TraceRay is supplied (DXR hardware in the reference) --
+textually into C++ (where /root/reference lies; nothing of it is
 committed) and oracle/ref_compare.cpp runs them next to the oracle's hand-written restatement on >= 10^5 seeded random inputs per
 function.  The oracle must reproduce the reference text bit for bit, except where its header documents a deliberate definition:
   * delta-lobe energies alpha = exp(-x) are the correctly rounded fp32 value (<= 1 ulp from expf; `1 - alpha` then amplifies that ulp
@@ -46,6 +49,9 @@ ULP["PLTMaterials.setupMaterialInstance_textured"] = 1024
 # the closest-hit / miss programs multiply the sampled BSDF pdf (see the BSDFs' sample() bounds) into the path state and the bounce record
 ULP["pltpt_sample.scatterTriangleMeshClosestHit"] = 16
 ULP["pltpt_sample.scatterMiss"] = 16
+# whole frames: the bounce records carry the sampled pdf's ulp; the pixel colour is a sum of beams evaluated through (1 - alpha) lobes (the eval bounds above)
+ULP["pltpt_sample.main_bounce_records"] = 16
+ULP["pltpt_solve.main_color"] = 1024
 # relative bound instead of an ulp bound: the multilayer stack's interference sum (correctly rounded phasors in the oracle)
 REL = {"PLTMultiLayeredStackBSDF.eval": 5e-3, "PLTMultiLayeredStackMaterial.setupMaterialInstance": 5e-3}
 
@@ -65,7 +71,8 @@ EXPECTED = ["MathHelpers.complex", "MathHelpers.boxmueller_truncated", "Spectrum
            [f"PLT{m}Material.setupMaterialInstance" for m in ("Diffuse", "Conductor", "Dielectric", "OpaqueDielectric", "ThinDielectric", "CoatedConductor", "CoatedOpaqueDielectric",
                                                                "DiffractionGratedConductor", "DiffractionGratedOpaqueDielectric", "MultiLayeredStack")] + \
            ["MaterialFactory.prepareShadingData", "PLTMaterials.setupMaterialInstance_textured", "Scene.computeVertexData", "Camera.computeRayPinhole", "pltpt.RR",
-            "Manifolds.manifoldOneStep", "DifferentialShadingGeometry.differentialShadingGeometry", "pltpt_sample.scatterTriangleMeshClosestHit", "pltpt_sample.scatterMiss"]
+            "Manifolds.manifoldOneStep", "DifferentialShadingGeometry.differentialShadingGeometry", "pltpt_sample.scatterTriangleMeshClosestHit", "pltpt_sample.scatterMiss",
+            "pltpt_sample.main_bounce_records", "pltpt_sample.main_guides", "pltpt_solve.main_color"]
 
 
 @pytest.fixture(scope="module")
@@ -100,5 +107,10 @@ def test_oracle_reproduces_the_reference_text(report):
         elif v["max_ulp"] > ULP.get(name, 0):
             bad[name] = v
     assert not bad, bad
+    # whole frames rendered by the reference's two ray-generation programs and by the oracle: the same paths (integer fields of every bounce record
+    # equal -- a differing hit, lobe or flag word is a "mismatch" above), the same guide images, and all but a handful of pixels equal to the last bit
+    frames = report["pltpt_solve.main_color"]
+    assert frames["units"] >= 40_000 and frames["identical_units"] >= 0.999 * frames["units"], frames
+    assert report["pltpt_sample.main_guides"]["max_ulp"] == 0
     exact = sum(1 for v in report.values() if v["max_ulp"] == 0 and not v["mismatches"])
-    assert exact >= 88, exact   # of 123 compared functions / entry points
+    assert exact >= 98, exact   # of 126 compared functions / entry points
