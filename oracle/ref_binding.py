@@ -1,0 +1,57 @@
+"""ctypes binding of oracle/_ref/libref_frames.so (TEST INFRASTRUCTURE ONLY): frames rendered by the reference's OWN shader text
+(oracle/ref_frames.cpp over the transpile of oracle/ref_transpile.py).  Exists only where /root/reference lies -- it is the
+generator of tests/golden/ref_frames.npz (tools/make_golden_ref.py), not something tests on the GPU box can call."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libref_frames.so")
+_lib = None
+
+
+def available():
+    return os.path.isdir("/root/reference") or os.path.exists(_LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libref_frames.so"])
+        _lib = C.CDLL(_LIB)
+        _lib.ref_scene_create.restype = C.c_void_p
+        _lib.ref_scene_create.argtypes = [C.c_void_p]
+        _lib.ref_scene_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RefScene:
+    """The reference's shader text bound to host-side Falcor-layout buffers (pltfalcor_b200.scene.SceneBuffers)."""
+
+    def __init__(self, buffers):
+        self.buffers = buffers
+        self._desc = buffers.desc()
+        self.h = C.c_void_p(lib().ref_scene_create(C.byref(self._desc)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_scene_destroy(self.h)
+            self.h = None
+
+    def render_frame(self, opts, cam, frame, width, height):
+        from pltfalcor_b200 import layouts as L
+        color = np.zeros((height, width, 4), np.float32)
+        albedo = np.zeros((height, width, 4), np.float32)
+        normal = np.zeros((height, width, 4), np.float32)
+        bounces = np.zeros((height, width, opts.maxBounces + 1), L.bounce_dtype)
+        rc = lib().ref_render_frame(self.h, C.byref(opts), C.byref(cam), C.c_uint32(frame), C.c_uint32(width), C.c_uint32(height), _p(color), _p(albedo), _p(normal), _p(bounces))
+        if rc != 0:
+            raise ValueError("option fixed at compile time in the transpiled reference (HWSS = 4, MNEEMaxOccluders = 2, no debug view)")
+        return dict(color=color, albedo=albedo, normal=normal, bounces=bounces)

@@ -1,0 +1,53 @@
+"""The CUDA path held to FRAMES OF THE REFERENCE ITSELF: tests/golden/ref_frames.npz holds frames rendered by the reference's own shader
+text (tools/make_golden_ref.py over oracle/ref_frames.cpp; see tests/test_oracle_ref_frames.py) -- this test renders the same scenes, cameras,
+frame numbers and option sets through the C ABI and compares bounce records and pixels with the fixture, no oracle in between.
+Gates as in tests/test_gpu_integrator.py (paths fork where a random number sits within rounding of a branch threshold; a manifold walk may
+converge on one side only), scaled to the fixture's 576 pixels per frame."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("make_golden_ref", os.path.join(os.path.dirname(__file__), "..", "tools", "make_golden_ref.py"))
+gold = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gold)
+
+
+@pytest.fixture(scope="module")
+def fixture():
+    return gold.load_fixture()
+
+
+@pytest.mark.parametrize("name", list(gold.CASES))
+def test_cuda_path_reproduces_the_reference_frames(torch_cuda, fixture, name):
+    from pltfalcor_b200 import binding, scene
+    buffers, cam, opts = gold.setup(name)
+    p = binding.Pltpt(**gold.CASES[name][1])
+    try:
+        p.set_scene(buffers)
+        for frame in gold.FRAMES:
+            ref = fixture[(name, frame)]
+            c = scene.with_jitter(cam, frame, gold.W, gold.H)
+            gpu_b = p.sample_stage_host(c, frame, gold.W, gold.H)
+            gpu = p.render_frame_host(c, frame, gold.W, gold.H)
+            m, same = parity.compare_bounces(gpu_b, ref["bounces"])
+            mc = parity.compare_color(gpu["color"], ref["color"], same)
+            m.update(mc)
+            parity.record(f"reference_frames/{name}/frame{frame}", m)
+            assert m["identical_paths"] >= 0.985, (name, frame, m)
+            assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3 and m["max_contribution_rel"] <= 1e-3, (name, frame, m)
+            assert m["nonfinite_gpu"] == 0
+            assert m["frac_pixels_within_1e-3"] >= 0.96, (name, frame, m)
+            # guide images of identical paths (first non-delta hit): fp32 noise only
+            for k in ("albedo", "normal"):
+                d = np.abs(gpu[k] - ref[k])[same]
+                assert (d <= 2e-3).mean() >= 0.995, (name, frame, k, float(d.max()))
+        s = p.stats()
+        assert s["traversalStackOverflows"] == 0 and s["droppedConnections"] == 0
+    finally:
+        p.close()

@@ -1,0 +1,81 @@
+"""Frames of the REFERENCE ITSELF, run here: renders small frames of the harness scenes with the reference's own shader text (both
+ray-generation programs of the PLTPT pass, transpiled textually by oracle/ref_transpile.py and driven by oracle/ref_frames.cpp; only the
+intersection search, the texture unit and the environment importance map are supplied) and stores colour, guide buffers and the bounce
+records under tests/golden/ref_frames.npz.  tests/test_oracle_ref_frames.py holds the oracle to them wherever the tests run.
+Can only be run where /root/reference lies.  Usage: python tools/make_golden_ref.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from pltfalcor_b200 import layouts as L, scene  # noqa: E402
+
+W, H, FRAMES = 32, 18, (3, 4)
+CASES = {
+    "cornell": (scene.cornell_box, dict(maxBounces=6)),
+    "cornell_closed": (scene.cornell_box_closed, dict(maxBounces=8)),
+    "grating": (lambda: scene.grating_sphere_scene(n_lat=16, n_lon=32), dict(maxBounces=6)),
+    "layered": (scene.layered_stress_scene, dict(maxBounces=5)),
+    "env": (scene.env_scene, dict(maxBounces=5)),
+    "textured": (scene.textured_scene, dict(maxBounces=5)),
+    "analytic": (scene.analytic_lights_scene, dict(maxBounces=5)),
+    "city": (lambda: scene.city_scene(4000), dict(maxBounces=5)),
+    "cornell_nomis_norr": (scene.cornell_box, dict(maxBounces=4, doMIS=False, doRussianRoulette=False, HWSSDoMIS=False)),
+    "cornell_nomnee_uniform_tilesg": (scene.cornell_box, dict(maxBounces=5, doMNEE=False, emissiveSampler=0, NEEUsePerTileSG=True, tileSize=8)),
+}
+KEYS = ("color", "albedo", "normal", "hit", "lobe", "flags", "wi", "contribution", "lastpdf")
+
+
+def _pack(r):
+    b = r["bounces"]
+    return dict(color=r["color"], albedo=r["albedo"], normal=r["normal"], hit=b["hit"].astype(np.uint32), lobe=b["sampledBsdfLobe"].astype(np.uint32),
+                flags=b["flags"].astype(np.uint32), wi=b["encodedWi"].astype(np.float32), contribution=b["pathContribution"].astype(np.float32),
+                lastpdf=b["lastNonDeltaPdf"].astype(np.float32))
+
+
+def setup(name):
+    fn, opts = CASES[name]
+    buffers, cam = fn()
+    return buffers, cam, L.make_options(**opts)
+
+
+def render_reference(name, frame):
+    from oracle import ref_binding as rb
+    buffers, cam, opts = setup(name)
+    return _pack(rb.RefScene(buffers).render_frame(opts, scene.with_jitter(cam, frame, W, H), frame, W, H))
+
+
+def render_oracle(name, frame):
+    from oracle import binding as ob
+    buffers, cam, opts = setup(name)
+    return _pack(ob.OracleScene(buffers).render_frame(opts, scene.with_jitter(cam, frame, W, H), frame, W, H, want_bounces=True))
+
+
+def load_fixture():
+    """{(case, frame): dict(color, albedo, normal, bounces)} from tests/golden/ref_frames.npz, the bounce records reassembled in the C ABI's layout."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_frames.npz"))
+    out = {}
+    for name in CASES:
+        for frame in FRAMES:
+            g = {k: z[f"{name}/{frame}/{k}"] for k in KEYS}
+            b = np.zeros(g["lobe"].shape, L.bounce_dtype)
+            b["hit"], b["encodedWi"], b["sampledBsdfLobe"], b["flags"] = g["hit"], g["wi"], g["lobe"], g["flags"]
+            b["pathContribution"], b["lastNonDeltaPdf"] = g["contribution"], g["lastpdf"]
+            out[(name, frame)] = dict(color=g["color"], albedo=g["albedo"], normal=g["normal"], bounces=b)
+    return out
+
+
+def _main():
+    out = {}
+    for name in CASES:
+        for frame in FRAMES:
+            for k, v in render_reference(name, frame).items():
+                out[f"{name}/{frame}/{k}"] = v
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_frames.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    _main()
