@@ -4,7 +4,7 @@
 // the reference holds no tests -- by the reference's OWN SHADER TEXT: oracle/ref_transpile.py rewrites the Slang modules
 // textually into C++ where /root/reference lies, and oracle/ref_compare.cpp runs them next to these headers on 10^5 seeded inputs per
 // function, and renders WHOLE FRAMES with the reference's two ray-generation programs (sample and solve stage, NEE / MNEE / emissive / miss /
-// replay, only the intersection search behind TraceRay supplied) beside samplePixel / solvePixel: 126 entries, 99 of them bit-exact, the others
+// replay, only the intersection search behind TraceRay supplied) beside samplePixel / solvePixel: 127 entries, 100 of them bit-exact, the others
 // inside documented ulp bounds; 49 974 of 49 984 frame pixels equal to the last bit (tests/test_oracle_ref.py).
 // What stays outside the reference's text: ray casting itself (DXR hardware, no source in the reference: the oracle defines the contract).
 //

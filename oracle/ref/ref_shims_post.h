@@ -564,6 +564,23 @@ static void ref_compare_more(int N, Rnd& r) {
             return static_cast<const orc::EnvMap*>(c)->load(uint32_t(x), uint32_t(y), 0u); };
         smp.importanceInvDim = ref::float2(1.f / float(orc::EnvMap::kDimension));
         smp.importanceBaseMip = env.baseMip;
+        // the importance map's base level: the reference's setup pass (EnvMapSamplerSetup.cs.slang main, bound as EnvMapSampler.cpp:101-112 binds it: 512 x 512
+        // texels, 8 x 8 samples each) against the oracle's EnvMap::init.  The mip chain above it is the driver's generateMips (a 2 x 2 box filter).
+        {
+            static float importance[orc::EnvMap::kDimension * orc::EnvMap::kDimension];
+            ref::outputDim = ref::uint2(orc::EnvMap::kDimension, orc::EnvMap::kDimension);
+            ref::outputDimInSamples = ref::uint2(orc::EnvMap::kDimension * orc::EnvMap::kSamplesX, orc::EnvMap::kDimension * orc::EnvMap::kSamplesY);
+            ref::numSamples = ref::uint2(orc::EnvMap::kSamplesX, orc::EnvMap::kSamplesY);
+            ref::invSamples = 1.f / (orc::EnvMap::kSamplesX * orc::EnvMap::kSamplesY);
+            ref::gEnvMap = renv.envMap;
+            ref::gImportanceMap.p = importance; ref::gImportanceMap.width = orc::EnvMap::kDimension;
+            const uint32_t step = N >= 50000 ? 1u : 4u;   // every texel in the full run
+            Cmp c("EnvMapSamplerSetup.main");
+            for (uint32_t y = 0; y < orc::EnvMap::kDimension; y += step) for (uint32_t x = 0; x < orc::EnvMap::kDimension; x += step) {
+                ref::envMapSamplerSetup(ref::uint3(x, y, 0u));
+                c.add(env.load(x, y, 0u), importance[size_t(y) * orc::EnvMap::kDimension + x]);
+            }
+        }
         integ.opt.useEnvLights = 1; integ.opt.useEmissiveLights = 1; integ.opt.useAnalyticLights = 1; integ.opt.doNEE = 1;
         ref::kUseEnvLight = true; ref::kUseEmissiveLights = false; ref::kUseAnalyticLights = false; ref::kNEEUsePerTileSelectorSG = false; ref::gEmissiveKind = 0;
         for (int i = 0; i < N; ++i) {

@@ -116,6 +116,13 @@ template <class T> struct Texture2D {
 struct ExplicitLodTextureSampler { float lod; ExplicitLodTextureSampler(float l = 0.f) : lod(l) {} };
 typedef ExplicitLodTextureSampler ITextureSampler;  // the interface the loaders take; the pass passes ExplicitLodTextureSampler{0} (Scene/Material/TextureSampler.slang:74-87)
 
+// ---- Rendering/Lights/EnvMapSamplerSetup.cs.slang:36-46: constant buffer and resources of the importance-map setup pass (bound by EnvMapSampler.cpp:101-112)
+static uint2 outputDim = uint2(0u, 0u), outputDimInSamples = uint2(0u, 0u), numSamples = uint2(0u, 0u);
+static float invSamples = 0.f;
+static SamplerState gEnvSampler;
+static Texture2D<float4> gEnvMap;
+template <class T> struct RWTexture2D { T* p = nullptr; uint width = 0; T& operator[](uint2 px) { return p[size_t(px.y) * width + px.x]; } };
+static RWTexture2D<float> gImportanceMap;
 // ---- what RenderPasses/PLTPT/LightSampling.slangh expects from the pass around it
 // pltpt.slangh:95-118: the pass's compile-time switches (defines set by PLTPT.cpp:222-260) -- variables here so that the comparison can
 // walk through their combinations; pltpt.slangh:77-78: the two sourcing constants of the constant buffer
@@ -148,7 +155,6 @@ static bool kUseDirectLights = true, mHWSSDoMIS = true;
 static uint mMaxBounces = 8, mTileSize = 512;
 static bool kAlphaMasking = true, kDoRussianRoulette = true;
 typedef uint4 PackedHitInfo;  // Scene/HitInfo.slang:63 (uncompressed hit info)
-template <class T> struct RWTexture2D { T* p = nullptr; uint width = 0; T& operator[](uint2 px) { return p[size_t(px.y) * width + px.x]; } };
 template <class T> struct RWStructuredBuffer { T* p = nullptr; T& operator[](uint i) { return p[i]; } };
 static RWTexture2D<float4> gOutputColor, gOutputNormal, gOutputAlbedo;
 struct BuiltInTriangleIntersectionAttributes { float2 barycentrics; };
@@ -175,6 +181,14 @@ struct RtAccelStandIn {};
 static constexpr uint RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH = 0x4u;
 static constexpr uint defaultVisibilityRayId = 0, defaultShadowRayId = 1;   // ShadowRays.slangh:37-44 with PLTPT.cpp:60-61,221-222
 static constexpr uint rayTypeCount = 2;                         // PLTPT.cpp:60-61: visibility and shadow ray types (the sample stage has one)
+// ---- RenderPasses/AccumulatePass/Accumulate.cs.slang:38-68: constant buffer and resources of the accumulation pass (float input format)
+static uint2 gResolution = uint2(0u, 0u);
+static uint gAccumCount = 0;
+static bool gAccumulate = true, gMovingAverageMode = false;
+typedef float4 InputDataType;
+static Texture2D<InputDataType> gCurFrame;
+static RWTexture2D<float4> gOutputFrame, gLastFrameSum, gLastFrameCorr;
+static RWTexture2D<uint4> gLastFrameSumLo, gLastFrameSumHi;
 #define DO_DEBUG_VIEW 0
 
 }  // namespace ref

@@ -165,6 +165,8 @@ inline uint asuint(uint u) { return u; }
 inline float asfloat(uint u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float asfloat(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline float asfloat(float f) { return f; }
+inline double asdouble(uint lo, uint hi) { const uint64_t b = (uint64_t(hi) << 32) | lo; double d; std::memcpy(&d, &b, 8); return d; }   // HLSL asdouble(lowbits, highbits)
+inline void asuint(double d, uint& lo, uint& hi) { uint64_t b; std::memcpy(&b, &d, 8); lo = uint(b); hi = uint(b >> 32); }          // HLSL asuint(double, out lowbits, out highbits)
 inline int asint(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 // HLSL f16tof32 / f32tof16 (the low 16 bits are an IEEE binary16; conversion to half rounds to nearest even)
 inline float f16tof32(uint h) {

@@ -55,3 +55,17 @@ class RefScene:
         if rc != 0:
             raise ValueError("option fixed at compile time in the transpiled reference (HWSS = 4, MNEEMaxOccluders = 2, no debug view)")
         return dict(color=color, albedo=albedo, normal=normal, bounces=bounces)
+
+
+def accumulate_frames(mode, frames, moving_average):
+    """The reference's AccumulatePass (Accumulate.cs.slang) stepped over `frames` ((h, w, 4) float32 each): the output image after every frame."""
+    h, w, _ = frames[0].shape
+    last = np.zeros((h, w, 4), np.float64 if mode == 2 else np.float32)
+    corr = np.zeros((h, w, 4), np.float32)
+    outs = []
+    for k, c in enumerate(frames):
+        out = np.zeros((h, w, 4), np.float32)
+        rc = lib().ref_accumulate_frame(C.c_uint32(mode), C.c_uint32(k), C.c_int(int(moving_average)), C.c_uint32(w), C.c_uint32(h), _p(np.ascontiguousarray(c, np.float32)), _p(last), _p(corr), _p(out))
+        assert rc == 0
+        outs.append(out)
+    return outs

@@ -191,4 +191,38 @@ int ref_render_frame(void* sp, const PltptOptions* opt, const PltptCameraData* c
     return 0;
 }
 
+// AccumulatePass, one frame: the reference's accumulateSingle / accumulateSingleCompensated / accumulateDouble (Accumulate.cs.slang:73-198) over
+// plain arrays.  precision 0 / 1 / 2 as AccumulatePass::Precision; lastSum is float4 per pixel (0, 1) or four doubles per pixel (2: the pass keeps
+// their bit halves in two uint4 textures, split and joined here); lastCorr only for 1.
+int ref_accumulate_frame(uint32_t precision, uint32_t accumCount, int movingAverage, uint32_t w, uint32_t h, const float* cur, void* lastSum, float* lastCorr, float* out) {
+    if (precision > 2) return -1;
+    const size_t n = size_t(w) * h;
+    ref::gResolution = ref::uint2(w, h); ref::gAccumCount = accumCount; ref::gAccumulate = true; ref::gMovingAverageMode = movingAverage != 0;
+    struct Ctx { const float* p; uint32_t w; } ctx{cur, w};
+    ref::gCurFrame.ctx = &ctx; ref::gCurFrame.width = w; ref::gCurFrame.height = h;
+    ref::gCurFrame.loadFn = [](const void* c, int x, int y, int) { const Ctx* k = static_cast<const Ctx*>(c); const float* t = k->p + 4 * (size_t(y) * k->w + size_t(x)); return ref::float4(t[0], t[1], t[2], t[3]); };
+    std::vector<ref::float4> o(n), sum(n), corr(n);
+    std::vector<ref::uint4> lo(n), hi(n);
+    ref::gOutputFrame.p = o.data(); ref::gOutputFrame.width = w;
+    ref::gLastFrameSum.p = sum.data(); ref::gLastFrameSum.width = w; ref::gLastFrameCorr.p = corr.data(); ref::gLastFrameCorr.width = w;
+    ref::gLastFrameSumLo.p = lo.data(); ref::gLastFrameSumLo.width = w; ref::gLastFrameSumHi.p = hi.data(); ref::gLastFrameSumHi.width = w;
+    float* fs = static_cast<float*>(lastSum); double* ds = static_cast<double*>(lastSum);
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k) {
+            if (precision == 2) { uint64_t b; std::memcpy(&b, &ds[4 * i + k], 8); lo[i][k] = uint32_t(b); hi[i][k] = uint32_t(b >> 32); }
+            else { sum[i][k] = fs[4 * i + k]; if (precision == 1) corr[i][k] = lastCorr[4 * i + k]; }
+        }
+    for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x) {
+        const ref::uint3 id(x, y, 0u);
+        if (precision == 0) ref::accumulateSingle(id); else if (precision == 1) ref::accumulateSingleCompensated(id); else ref::accumulateDouble(id);
+    }
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k) {
+            out[4 * i + k] = o[i][k];
+            if (precision == 2) { const uint64_t b = (uint64_t(hi[i][k]) << 32) | lo[i][k]; std::memcpy(&ds[4 * i + k], &b, 8); }
+            else { fs[4 * i + k] = sum[i][k]; if (precision == 1) lastCorr[4 * i + k] = corr[i][k]; }
+        }
+    return 0;
+}
+
 }  // extern "C"

@@ -29,7 +29,8 @@ Rewrite rules (all mechanical; each is a regular expression or a brace-matched b
   R12 `let x = e` -> `auto x = e`
   R13 `enum class X : T` -> `enum X : T` (Slang converts a scoped enumerator to its underlying type in `switch (uint)` / `uint(...)`; C++
       only does so for an unscoped enumeration, whose enumerators can still be written `X::Name`)
-  R14 the ray-generation programs `void main()` of the sample and the solve shader -> `sampleRayGen()` / `solveRayGen()`
+  R14 the entry points `void main(...)` of the sample shader, the solve shader and the environment-map setup pass -> `sampleRayGen()` /
+      `solveRayGen()` / `envMapSamplerSetup(dispatchThreadID)`; `: SV_...` parameter semantics dropped
   R11 the handful of vector-condition ternaries (`c ? a : b` with bool2 `c`, DiffractionGrating.slang only) -> select(c, a, b); listed in PATCHES
       with the exact source text they replace -- the script fails if a patch no longer matches.
 """
@@ -56,7 +57,7 @@ SOURCES = [
     ("Scene/Lights/EnvMapData.slang", None),
     ("Scene/Lights/EnvMap.slang", None),
     ("Scene/SceneTypes.slang", ["StaticVertexData", "PackedStaticVertexData"]),
-    ("Utils/Color/ColorHelpers.slang", ["XYZtoRGB_Rec709"]),
+    ("Utils/Color/ColorHelpers.slang", ["luminance", "XYZtoRGB_Rec709"]),
     ("Utils/Color/SpectrumUtils.slang", None),
     ("Rendering/Materials/Fresnel.slang", None),
     ("Rendering/Materials/PLT/Mueller.slang", None),
@@ -112,6 +113,7 @@ SOURCES = [
     ("Rendering/Lights/EmissivePowerSampler.slang", None),
     ("Rendering/Lights/EnvMapSampler.slang", None),
     ("literal", "static EnvMapSampler envMapSampler;  // cbuffer CB of the pass (pltpt.slangh:73)"),
+    ("Rendering/Lights/EnvMapSamplerSetup.cs.slang", ["main"]),
     ("Utils/Geometry/GeometryHelpers.slang", ["computeRayOrigin"]),
     ("Rendering/Utils/LightsSamplingUtils.slang", None),
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
@@ -126,10 +128,11 @@ SOURCES = [
     ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep", "MSHitData", "ManifoldSampleData", "manifoldSampleVertex", "traceMNEEOccluders",
                                                 "MNEEStep", "manifoldNEESample"]),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["manifoldForwardUnwind", "evalNEE", "NEE", "onMiss", "main"]),
+    ("../RenderPasses/AccumulatePass/Accumulate.cs.slang", ["accumulateSingle", "accumulateSingleCompensated", "accumulateDouble"]),
 ]
 
 # the two ray-generation programs are both called `main`: renamed after their file (R14)
-ENTRY_POINTS = {"PLTPT/pltpt_sample.rt.slang": "sampleRayGen", "PLTPT/pltpt_solve.rt.slang": "solveRayGen"}
+ENTRY_POINTS = {"PLTPT/pltpt_sample.rt.slang": "sampleRayGen", "PLTPT/pltpt_solve.rt.slang": "solveRayGen", "Lights/EnvMapSamplerSetup.cs.slang": "envMapSamplerSetup"}
 
 STATIC_SCOPES = ["SpectrumUtils", "Birefringence", "SpectrumSampler", "BasicMaterialData", "BSDFProperties"]
 # property reads outside the declaring struct: `roughness` is a property of both surface types, `q` of FractalSurface only (a plain
@@ -220,7 +223,7 @@ def extract_items(s, names):
     """Top-level functions / structs with the given names (all overloads of a name in source order), emitted in the order of `names`
     (Slang resolves names regardless of declaration order, C++ needs the callee first)."""
     found = {n: [] for n in names}
-    pat = re.compile(r"^(?:static\s+)?(?:const\s+)?[\w<>,:]+\s+(\w+)\s*(?:<[^>]*>)?\s*\([^;{]*\)\s*\{|^struct\s+(\w+)[^{;]*\{", re.M)
+    pat = re.compile(r"^(?:static\s+)?(?:inline\s+)?(?:const\s+)?[\w<>,:]+\s+(\w+)\s*(?:<[^>]*>)?\s*\([^;{]*\)\s*\{|^struct\s+(\w+)[^{;]*\{", re.M)
     pos = 0
     while True:
         m = pat.search(s, pos)
@@ -375,7 +378,10 @@ def transpile(path, s, struct_names):
     s = strip_comments_keep_lines(s)
     for suffix, name in ENTRY_POINTS.items():   # R14
         if path.endswith(suffix):
-            s = re.sub(r"\bvoid\s+main\s*\(\)", f"void {name}()", s)
+            s = re.sub(r"\bvoid\s+main\s*\(", f"void {name}(", s)
+
+    if path.endswith(".cs.slang"):
+        s = re.sub(r"\s*:\s*SV_\w+", "", s)   # R14: HLSL system-value semantics of a compute entry point's parameters
     # R1
     s = re.sub(r"^\s*(__exported\s+)?import\s+[\w.]+\s*;\s*$", "", s, flags=re.M)
     s = re.sub(r'^\s*#include\s+"[^"]*"\s*$', "", s, flags=re.M)

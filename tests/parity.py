@@ -130,3 +130,50 @@ def rel_mse(a, b):
     """relMSE as the reference's ImageCompare defines it (Source/Tools/ImageCompare/ImageCompare.cpp:198-207)."""
     a, b = a.astype(np.float64), b.astype(np.float64)
     return float(((a - b) ** 2 / (b ** 2 + 1e-3)).mean())
+
+
+f32, f64 = np.float32, np.float64
+
+
+def accumulate_test_frames(mode, h=19, w=33, n=40):
+    """Seeded input frames of the AccumulatePass tests: values spanning eight decades -- the single-precision sum visibly loses bits, the compensated
+    and double ones must not."""
+    rng = np.random.default_rng(7 + mode)
+    return [(rng.uniform(0, 1, (h, w, 4)) * 10.0 ** rng.integers(-4, 4, (h, w, 1))).astype(f32) for _ in range(n)]
+
+
+def accumulate_pass_restatement(mode, frames, moving_average):
+    """AccumulatePass stepped frame by frame (Accumulate.cs.slang:73-198; mode 0 Single, 1 SingleCompensated, 2 Double): the same fp32 / fp64 operations in
+    the same order, in numpy.  Held to the reference's own shader text by tests/test_oracle_ref_frames.py (tests/golden/ref_accumulate.npz)."""
+    h, w, _ = frames[0].shape
+    if mode == 2:
+        s = np.zeros((h, w, 4), f64)
+    else:
+        s = np.zeros((h, w, 4), f32)
+    corr = np.zeros((h, w, 4), f32)
+    outs = []
+    for n, c in enumerate(frames):
+        if mode == 0:
+            wgt = f32(1.0) / f32(n + 1)
+            if moving_average:
+                o = (s + (c - s) * wgt).astype(f32)
+                s = o
+            else:
+                s = (s + c).astype(f32)
+                o = (s * wgt).astype(f32)
+        elif mode == 1:
+            y = (c - corr).astype(f32)
+            nxt = (s + y).astype(f32)
+            o = (nxt / f32(n + 1)).astype(f32)
+            corr = ((nxt - s).astype(f32) - y).astype(f32)
+            s = nxt
+        else:
+            wgt = f64(1.0) / f64(n + 1)
+            if moving_average:
+                s = s * (f64(1.0) - wgt) + c.astype(f64) * wgt
+                o = s.astype(f32)
+            else:
+                s = s + c.astype(f64)
+                o = (s * wgt).astype(f32)
+        outs.append(o)
+    return outs

@@ -7,39 +7,7 @@ pytestmark = pytest.mark.gpu
 f32, f64 = np.float32, np.float64
 
 
-def _reference(mode, frames, moving_average):
-    h, w, _ = frames[0].shape
-    if mode == 2:
-        s = np.zeros((h, w, 4), f64)
-    else:
-        s = np.zeros((h, w, 4), f32)
-    corr = np.zeros((h, w, 4), f32)
-    outs = []
-    for n, c in enumerate(frames):
-        if mode == 0:
-            wgt = f32(1.0) / f32(n + 1)
-            if moving_average:
-                o = (s + (c - s) * wgt).astype(f32)
-                s = o
-            else:
-                s = (s + c).astype(f32)
-                o = (s * wgt).astype(f32)
-        elif mode == 1:
-            y = (c - corr).astype(f32)
-            nxt = (s + y).astype(f32)
-            o = (nxt / f32(n + 1)).astype(f32)
-            corr = ((nxt - s).astype(f32) - y).astype(f32)
-            s = nxt
-        else:
-            wgt = f64(1.0) / f64(n + 1)
-            if moving_average:
-                s = s * (f64(1.0) - wgt) + c.astype(f64) * wgt
-                o = s.astype(f32)
-            else:
-                s = s + c.astype(f64)
-                o = (s * wgt).astype(f32)
-        outs.append(o)
-    return outs
+from tests.parity import accumulate_pass_restatement as _reference, accumulate_test_frames  # noqa: E402
 
 
 @pytest.mark.parametrize("mode,moving_average", [(0, False), (0, True), (1, False), (2, False), (2, True)])
@@ -47,10 +15,8 @@ def test_accumulate_frame_matches_the_pass(torch_cuda, mode, moving_average):
     torch = torch_cuda
     from pltfalcor_b200 import binding
     p = binding.Pltpt()
-    rng = np.random.default_rng(7 + mode)
     h, w, n = 19, 33, 40
-    # values spanning eight decades: the single-precision sum visibly loses bits, the compensated and double ones must not
-    frames = [(rng.uniform(0, 1, (h, w, 4)) * 10.0 ** rng.integers(-4, 4, (h, w, 1))).astype(f32) for _ in range(n)]
+    frames = accumulate_test_frames(mode, h, w, n)
     ref = _reference(mode, frames, moving_average)
     last = torch.zeros((h, w, 4), dtype=torch.float64 if mode == 2 else torch.float32, device="cuda")
     corr = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda") if mode == 1 else None

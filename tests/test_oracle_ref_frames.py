@@ -51,3 +51,18 @@ def test_fixture_is_regenerated_identically_where_the_reference_lies():
         got = gold.render_reference(name, gold.FRAMES[0])
         ref = fx[(name, gold.FRAMES[0])]
         assert np.array_equal(got["color"], ref["color"]) and np.array_equal(got["hit"], ref["bounces"]["hit"]), name
+
+
+@pytest.mark.parametrize("mode,moving_average", gold.ACC_MODES)
+def test_accumulate_restatement_reproduces_the_reference_pass(mode, moving_average):
+    """tests/golden/ref_accumulate.npz: the AccumulatePass of the reference's own text (Accumulate.cs.slang accumulateSingle / accumulateSingleCompensated /
+    accumulateDouble, transpiled; tools/make_golden_ref.py).  The numpy restatement the GPU test holds pltpt_accumulate_frame to bit for bit
+    (tests/parity.accumulate_pass_restatement) equals it to the last bit in the two single-precision modes.  In the Double mode the weight
+    `double curWeight = 1.0 / (gAccumCount + 1)` depends on how the shader compiler types the unsuffixed literal: the transpile follows HLSL's rule (fp32
+    literal, fp32 division, widened), restatement and CUDA path divide in fp64 -- at most one ulp of the fp32 output, which is the bound asserted here."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_accumulate.npz"))
+    outs = parity.accumulate_pass_restatement(mode, parity.accumulate_test_frames(mode), moving_average)
+    for k in gold.ACC_STEPS:
+        ref = z[f"{mode}/{int(moving_average)}/{k}"]
+        ulp = np.abs(outs[k].view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)).max()
+        assert ulp <= (1 if mode == 2 else 0), (mode, moving_average, k, int(ulp))

@@ -66,6 +66,22 @@ def load_fixture():
     return out
 
 
+ACC_MODES = [(0, False), (0, True), (1, False), (2, False), (2, True)]   # (AccumulatePass precision, moving average)
+ACC_STEPS = (0, 1, 2, 7, 39)                                             # of 40 accumulated frames, the ones kept in the fixture
+
+
+def render_reference_accumulate():
+    """AccumulatePass by the reference's own text (Accumulate.cs.slang, transpiled) over the seeded frames of tests/parity.accumulate_test_frames."""
+    from oracle import ref_binding as rb
+    from tests import parity
+    out = {}
+    for mode, ma in ACC_MODES:
+        outs = rb.accumulate_frames(mode, parity.accumulate_test_frames(mode), ma)
+        for k in ACC_STEPS:
+            out[f"{mode}/{int(ma)}/{k}"] = outs[k]
+    return out
+
+
 def _main():
     out = {}
     for name in CASES:
@@ -74,6 +90,9 @@ def _main():
                 out[f"{name}/{frame}/{k}"] = v
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_frames.npz")
     np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_accumulate.npz")
+    np.savez_compressed(path, **render_reference_accumulate())
     print(path, os.path.getsize(path), "bytes")
 
 
