@@ -18,6 +18,9 @@ static const float kInfernoFit[4][3][6] = {{{1.4787414e-03f, 3.6751310e-02f, 5.4
  {{7.3569958e-01f, 3.6764049e-01f, -6.2249737e-02f, -9.3448598e-02f, 3.3710621e-02f, -2.9206021e-03f}, {2.1589449e-01f, 2.0405012e-01f, 1.1168130e-01f, 1.1148865e-01f, -1.1858878e-01f, 3.3410856e-02f}, {3.2992707e-01f, -2.2107073e-01f, -2.1314454e-01f, 3.9623957e-01f, -4.4381064e-01f, 1.8591876e-01f}},
  {{9.7918506e-01f, 5.9351113e-02f, -4.2589003e-02f, -1.7763508e-01f, -2.3464711e-01f, 4.1358195e-01f}, {5.5765378e-01f, 4.6408360e-01f, 2.0993310e-03f, 1.0345698e-01f, -4.2376193e-02f, -8.4870893e-02f}, {4.0354673e-02f, -5.0338033e-01f, 3.8974506e+00f, -7.7197422e+00f, 8.1019429e+00f, -3.1619149e+00f}}};
 inline float3 colourMapEval(const float (*fit)[3][6], float val) {
+    // the table rule on a non-finite argument: lerp(data[l], data[h], frac(val)) with frac(NaN) = frac(+-inf) = NaN is NaN, which writeDebugOutput then
+    // rejects (pltpt_debug.slangh:21) -- found by rendering the views with the reference's own text (tests/golden/ref_debug_views.npz)
+    if (!std::isfinite(val)) return float3(std::numeric_limits<float>::quiet_NaN());
     val = hlsl_min(hlsl_max(val, 0.f), 255.f / 256.f + 0.99f / 256.f);
     const int s = hlsl_min(int(val * 4.f), 3);
     const float u = val * 4.f - float(s);

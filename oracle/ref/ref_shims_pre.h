@@ -189,6 +189,13 @@ typedef float4 InputDataType;
 static Texture2D<InputDataType> gCurFrame;
 static RWTexture2D<float4> gOutputFrame, gLastFrameSum, gLastFrameCorr;
 static RWTexture2D<uint4> gLastFrameSumLo, gLastFrameSumHi;
-#define DO_DEBUG_VIEW 0
+// DO_DEBUG_VIEW / DEBUG_VIEW_TYPE (PLTPT.cpp:230-231): the pass compiles the debug overlay in only when a view is selected; the two builds of
+// oracle/ref_frames.cpp (-DREF_DEBUG_VIEW=0 / 1) are those two shader variants
+#ifndef REF_DEBUG_VIEW
+#define REF_DEBUG_VIEW 0
+#endif
+#define DO_DEBUG_VIEW REF_DEBUG_VIEW
+static uint kDebugViewType = 0;
+static float kDebugViewIntensity = 1.f;   // pltpt.slangh:85-87
 
 }  // namespace ref

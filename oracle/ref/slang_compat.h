@@ -140,6 +140,7 @@ inline float ceil(float v) { return std::ceil(v); }
 inline float round(float v) { return std::nearbyint(v); }
 inline float trunc(float v) { return std::trunc(v); }
 inline float frac(float v) { return v - std::floor(v); }
+inline int hlsl_ftoi(float v) { return v != v ? 0 : (v >= 2147483648.f ? 2147483647 : (v <= -2147483648.f ? int(-2147483647 - 1) : int(v))); }   // HLSL (int)float: saturating, NaN -> 0
 inline float fmod(float a, float b) { return std::fmod(a, b); }
 inline float sign(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 inline int sign(int v) { return v > 0 ? 1 : (v < 0 ? -1 : 0); }

@@ -9,7 +9,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_ref", "libref_frames.so")
+_LIB_DBG = os.path.join(_HERE, "_ref", "libref_frames_dbg.so")   # the pass's DO_DEBUG_VIEW = 1 shader variant
 _lib = None
+_lib_dbg = None
 
 
 def available():
@@ -28,6 +30,18 @@ def lib():
     return _lib
 
 
+def lib_debug():
+    global _lib_dbg
+    if _lib_dbg is None:
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libref_frames_dbg.so"])
+        _lib_dbg = C.CDLL(_LIB_DBG)
+        _lib_dbg.ref_scene_create.restype = C.c_void_p
+        _lib_dbg.ref_scene_create.argtypes = [C.c_void_p]
+        _lib_dbg.ref_scene_destroy.argtypes = [C.c_void_p]
+    return _lib_dbg
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -35,14 +49,15 @@ def _p(a):
 class RefScene:
     """The reference's shader text bound to host-side Falcor-layout buffers (pltfalcor_b200.scene.SceneBuffers)."""
 
-    def __init__(self, buffers):
+    def __init__(self, buffers, debug=False):
         self.buffers = buffers
         self._desc = buffers.desc()
-        self.h = C.c_void_p(lib().ref_scene_create(C.byref(self._desc)))
+        self._lib = lib_debug() if debug else lib()
+        self.h = C.c_void_p(self._lib.ref_scene_create(C.byref(self._desc)))
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().ref_scene_destroy(self.h)
+            self._lib.ref_scene_destroy(self.h)
             self.h = None
 
     def render_frame(self, opts, cam, frame, width, height):
@@ -51,9 +66,9 @@ class RefScene:
         albedo = np.zeros((height, width, 4), np.float32)
         normal = np.zeros((height, width, 4), np.float32)
         bounces = np.zeros((height, width, opts.maxBounces + 1), L.bounce_dtype)
-        rc = lib().ref_render_frame(self.h, C.byref(opts), C.byref(cam), C.c_uint32(frame), C.c_uint32(width), C.c_uint32(height), _p(color), _p(albedo), _p(normal), _p(bounces))
+        rc = self._lib.ref_render_frame(self.h, C.byref(opts), C.byref(cam), C.c_uint32(frame), C.c_uint32(width), C.c_uint32(height), _p(color), _p(albedo), _p(normal), _p(bounces))
         if rc != 0:
-            raise ValueError("option fixed at compile time in the transpiled reference (HWSS = 4, MNEEMaxOccluders = 2, no debug view)")
+            raise ValueError("option fixed at compile time in the transpiled reference (HWSS = 4, MNEEMaxOccluders = 2; debug views need RefScene(debug=True))")
         return dict(color=color, albedo=albedo, normal=normal, bounces=bounces)
 
 

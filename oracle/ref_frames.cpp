@@ -9,7 +9,7 @@
 // Used by tools/make_golden_ref.py to produce tests/golden/ref_frames.npz -- frames "of the reference itself, run here" -- which pin the
 // oracle (tests/test_oracle_ref_frames.py) wherever the tests run, also where /root/reference is absent.
 // The generated program state is global (shader globals are): one frame at a time, single-threaded.
-// Build: make -C oracle ref   ->  oracle/_ref/libref_frames.so
+// Build: make -C oracle ref   ->  oracle/_ref/libref_frames.so and libref_frames_dbg.so (-DREF_DEBUG_VIEW=1: the pass's DO_DEBUG_VIEW variant)
 #include <cstdio>
 #include <vector>
 
@@ -140,11 +140,14 @@ void* ref_scene_create(const PltptSceneDesc* desc) {
 void ref_scene_destroy(void* s) { if (g == s) g = nullptr; delete static_cast<RefScene*>(s); }
 
 // One frame = the tile loop of PLTPT::execute (PLTPT.cpp:487-495): per tile the sample stage over the tile, then the solve stage.
-// Returns 0, or -1 for an option the transpiled build fixes at compile time (HWSS = 4, MNEE_MAX_MS_OCCLUDERS = 2, no debug view).
+// Returns 0, or -1 for an option the transpiled build fixes at compile time (HWSS = 4, MNEE_MAX_MS_OCCLUDERS = 2; a debug view needs the
+// DO_DEBUG_VIEW = 1 build, libref_frames_dbg.so, which in turn renders nothing else).
 int ref_render_frame(void* sp, const PltptOptions* opt, const PltptCameraData* cam, uint32_t frameCount, uint32_t width, uint32_t height,
                      float* color, float* albedo, float* normal, PltptBounce* bounces) {
     const RefScene& rs = *static_cast<RefScene*>(sp);
-    if (opt->HWSS != ref::hwss_samples || opt->MNEEMaxOccluders != ref::kMNEEMaxMSOccluders || opt->debugView != 0) return -1;
+    // the pass compiles the debug overlay in only when a view is selected (PLTPT.cpp:230): this translation unit is built once without and once with it
+    if (opt->HWSS != ref::hwss_samples || opt->MNEEMaxOccluders != ref::kMNEEMaxMSOccluders || (opt->debugView != 0) != (REF_DEBUG_VIEW != 0)) return -1;
+    ref::kDebugViewType = opt->debugView; ref::kDebugViewIntensity = opt->debugViewIntensity;
     orc::hwss_cfg().samples = 4;
     bind(rs);
     const PltptSceneDesc& d = rs.osc.d;

@@ -119,6 +119,9 @@ SOURCES = [
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["computeNewRayOrigin"]),
     ("../RenderPasses/PLTPT/LightSampling.slangh", None),
     ("../RenderPasses/PLTPT/Path.slang", ["RayFlags", "BounceData", "Path", "PLTSolve"]),
+    ("../RenderPasses/PLTPT/DebugViewType.slangh", None),
+    ("../RenderPasses/PLTPT/ColourCoding.slang", None),
+    ("../RenderPasses/PLTPT/pltpt_debug.slangh", None),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["MISWeight", "measure"]),
     ("literal", '#include "../ref/ref_shims_late.h"'),
     ("../RenderPasses/PLTPT/ShadowRays.slangh", ["VisibilityRayData", "visibilityMiss", "visibilityRay", "ShadowRayHit", "shadowTriangleMeshHit", "shadowRay"]),
@@ -179,6 +182,9 @@ PATCHES = [
     ("Scene/Scene.slang", "v.tangentW.xyz = normalize(v.tangentW.xyz);", "{ const float3 txyz = normalize(v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }", "swizzle on the left-hand side"),
     ("PLTPT/Manifolds.slangh", "const float2x2 do = sphcoordsDerivatives(w);", "const float2x2 do_ = sphcoordsDerivatives(w);", "`do` is a C++ keyword"),
     ("PLTPT/Manifolds.slangh", "const float2x2 dCdX = do - float2x2(dio);", "const float2x2 dCdX = do_ - float2x2(dio);", "`do` is a C++ keyword"),
+    ("PLTPT/ColourCoding.slang", "const int l = clamp((int)val, 0, int(bins)-1);", "const int l = clamp(hlsl_ftoi(val), 0, int(bins)-1);",
+     "HLSL's float -> int conversion saturates and maps NaN to 0; C++'s is undefined outside int's range (the views feed unbounded values)"),
+    ("PLTPT/ColourCoding.slang", "const int h = clamp((int)(val + 1), 0, int(bins) - 1);", "const int h = clamp(hlsl_ftoi(val + 1), 0, int(bins) - 1);", "as above"),
     ("PLTPT/Path.slang", "    enum class Flags {", "    enum class Flags : uint {", "the mask 0xffff0000 needs an unsigned underlying type in C++ (Slang enums are 32-bit words)"),
     ("Materials/BSDFSample.slang", "    float   pdf;  ", "    float   pdf = 0.f;  ",
      "the closest-hit program reads bsdfSample.lobe / .pdf on paths that skipped sample() (pltpt_sample.rt.slang:87-103): a GPU compiler gives the "
@@ -426,6 +432,8 @@ def transpile(path, s, struct_names):
         s = re.sub(rf"(\b[\w.]*flags)\.({props})\s*=(?!=)\s*([^;]+);", r"\1.set_\2(\3);", s)
         s = re.sub(rf"(\b[\w.]*[fF]lags)\.({props})\b(?!\s*\()", r"\1.\2()", s)
         s = re.sub(r"(\b[\w.]*flags)\.valid\b(?!\s*\()", r"\1.valid()", s)
+        s = re.sub(r"(\bdebugOutput|\])\.rgb\b", r"\1.xyz()", s)   # R8: colour-named swizzles of the debug overlay (DO_DEBUG_VIEW branch)
+        s = re.sub(r"\bdebugOutput\.a\b", "debugOutput.w", s)
         s = re.sub(r"\bbounce\.wi\b(?!\s*[\(=])", "bounce.wi()", s)
         s = re.sub(r"\bbounce\.wi\s*=(?!=)\s*([^;]+);", r"bounce.set_wi(\1);", s)
         s = re.sub(r"\bbsdfProp\.(canManifoldWalk(?:Reflective|Transmissive)|isEmissive)\b(?!\s*\()", r"bsdfProp.\1()", s)

@@ -53,3 +53,30 @@ def test_cuda_path_reproduces_the_reference_frames(torch_cuda, fixture, name):
         assert s["traversalStackOverflows"] == 0 and s["droppedConnections"] == 0
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("name", gold.DEBUG_CASES)
+def test_cuda_debug_views_reproduce_the_reference(torch_cuda, name):
+    """The 13 debug views of the CUDA path against the views rendered by the reference's own text (tests/golden/ref_debug_views.npz,
+    DO_DEBUG_VIEW = 1 variant).  Pixels of identical paths: fp32 noise for the direct views, plus the colour-map fit error (<= 0.0084) for the views
+    written through ccMagma / ccInferno."""
+    from pltfalcor_b200 import binding, scene
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_debug_views.npz"))
+    fx = gold.load_fixture()[(name, gold.DEBUG_FRAME)]
+    buffers, cam, _ = gold.setup(name)
+    c = scene.with_jitter(cam, gold.DEBUG_FRAME, gold.W, gold.H)
+    p = binding.Pltpt(**gold.CASES[name][1])
+    try:
+        p.set_scene(buffers)
+        _, same = parity.compare_bounces(p.sample_stage_host(c, gold.DEBUG_FRAME, gold.W, gold.H), fx["bounces"])
+        for view, vname in gold.DEBUG_VIEWS.items():
+            p.set_options(debugView=view)
+            gpu = p.render_frame_host(c, gold.DEBUG_FRAME, gold.W, gold.H)["color"]
+            ref = z[f"{name}/{view}"]
+            assert np.isfinite(gpu).all(), vname
+            d = np.abs(gpu[..., :3] - ref[..., :3]).max(-1)[same]
+            tol = 1.5e-2 if view in gold.COLOUR_MAPPED else 5e-3
+            parity.record(f"reference_debug_views/{name}/{vname}", {"frac_within_tol": float((d <= tol).mean()), "tol": tol, "max_abs": float(d.max())})
+            assert (d <= tol).mean() >= 0.97, (name, vname, float(d.max()))
+    finally:
+        p.close()

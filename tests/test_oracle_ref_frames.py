@@ -66,3 +66,27 @@ def test_accumulate_restatement_reproduces_the_reference_pass(mode, moving_avera
         ref = z[f"{mode}/{int(moving_average)}/{k}"]
         ulp = np.abs(outs[k].view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)).max()
         assert ulp <= (1 if mode == 2 else 0), (mode, moving_average, k, int(ulp))
+
+
+@pytest.mark.parametrize("name", gold.DEBUG_CASES)
+def test_oracle_debug_views_reproduce_the_reference(oracle, name):
+    """tests/golden/ref_debug_views.npz: the pass's 13 debug views rendered by the reference's own text in its DO_DEBUG_VIEW = 1 variant.  Views that
+    write values directly (NaN / inf markers, normals, albedo, roughness, UVs, polarisation, MNEE bounce classes) are reproduced bit for bit; views written
+    through ccMagma / ccInferno carry the error of the polynomial fits that stand in for the reference's 256-entry tables (<= 0.0084 per channel,
+    tests/test_debug_views.py).  This comparison found the one behavioural difference the fits had: a non-finite argument makes the table rule return NaN
+    (frac(inf) = NaN), which writeDebugOutput drops -- now reproduced by oracle and CUDA path."""
+    from pltfalcor_b200 import scene
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_debug_views.npz"))
+    buffers, cam, _ = gold.setup(name)
+    osc = oracle.OracleScene(buffers)
+    c = scene.with_jitter(cam, gold.DEBUG_FRAME, gold.W, gold.H)
+    shown = 0
+    for view, vname in gold.DEBUG_VIEWS.items():
+        ref = z[f"{name}/{view}"]
+        got = osc.render_frame(gold.debug_options(name, view), c, gold.DEBUG_FRAME, gold.W, gold.H)["color"]
+        if view in gold.COLOUR_MAPPED:
+            assert np.abs(got - ref).max() <= 1e-2, (name, vname, float(np.abs(got - ref).max()))
+        else:
+            assert np.array_equal(got, ref), (name, vname, float(np.abs(got - ref).max()))
+        shown += int(ref[..., :3].max() > 0)
+    assert shown >= 10, (name, shown)   # the NaN / inf markers stay black on a healthy render, MNEE bounce classes on a scene without walks

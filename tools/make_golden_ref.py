@@ -82,6 +82,31 @@ def render_reference_accumulate():
     return out
 
 
+DEBUG_VIEWS = {1: "nans", 2: "inf", 3: "path_length", 4: "hwss_comps", 5: "normals", 6: "albedo", 7: "roughness", 8: "UVs", 9: "coherence_area",
+               10: "coherence_anisotropy", 11: "polarization", 12: "mnee_iterations", 13: "mnee_bounces"}   # DebugViewType.slangh:5-20
+COLOUR_MAPPED = (3, 4, 9, 10, 12)   # views written through ccMagma / ccInferno (pltpt_debug.slangh:24-29): the product evaluates polynomial fits of the tables
+DEBUG_CASES = ("cornell", "grating")
+DEBUG_FRAME = 3
+
+
+def debug_options(name, view):
+    opts = dict(CASES[name][1])
+    opts.update(debugView=view)
+    return L.make_options(**opts)
+
+
+def render_reference_debug_views():
+    """The 13 debug views by the reference's own text compiled as the pass compiles it when a view is selected (DO_DEBUG_VIEW = 1, libref_frames_dbg.so)."""
+    from oracle import ref_binding as rb
+    out = {}
+    for name in DEBUG_CASES:
+        buffers, cam, _ = setup(name)
+        rs = rb.RefScene(buffers, debug=True)
+        for view in DEBUG_VIEWS:
+            out[f"{name}/{view}"] = rs.render_frame(debug_options(name, view), scene.with_jitter(cam, DEBUG_FRAME, W, H), DEBUG_FRAME, W, H)["color"]
+    return out
+
+
 def _main():
     out = {}
     for name in CASES:
@@ -90,6 +115,9 @@ def _main():
                 out[f"{name}/{frame}/{k}"] = v
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_frames.npz")
     np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_debug_views.npz")
+    np.savez_compressed(path, **render_reference_debug_views())
     print(path, os.path.getsize(path), "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_accumulate.npz")
     np.savez_compressed(path, **render_reference_accumulate())
