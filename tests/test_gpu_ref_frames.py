@@ -44,7 +44,7 @@ def test_cuda_path_reproduces_the_reference_frames(torch_cuda, fixture, name):
             assert m["identical_paths"] >= (0.98 if name == "cornell_closed" else 0.99), (name, frame, m)
             assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3 and m["max_contribution_rel"] <= 1e-3, (name, frame, m)
             assert m["nonfinite_gpu"] == 0
-            assert m["frac_pixels_within_1e-3"] >= (0.975 if name == "grating" else 0.985), (name, frame, m)   # measured: grating 0.984 (manifold walks), others >= 0.991
+            assert m["frac_pixels_within_1e-3"] >= (0.975 if name.startswith("grating") else 0.985), (name, frame, m)   # measured: grating 0.984 (manifold walks), others >= 0.991
             # guide images of identical paths (first non-delta hit): fp32 noise only
             for k in ("albedo", "normal"):
                 d = np.abs(gpu[k] - ref[k])[same]

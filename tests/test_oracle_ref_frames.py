@@ -38,7 +38,7 @@ def test_oracle_reproduces_the_reference_frames(fixture, name):
         assert identical.mean() >= 0.99, (name, frame, float(identical.mean()))
         rel = np.abs(got["color"] - ref["color"]) / np.maximum(np.abs(ref["color"]), 1e-6)
         assert rel.max() <= 1e-5, (name, frame, float(rel.max()))
-        assert (ref["color"][..., :3].sum(-1) > 0).mean() >= 0.5, (name, frame)   # the fixture is not a black frame
+        assert (ref["color"][..., :3].sum(-1) > 0).mean() >= 0.1, (name, frame)   # the fixture is not a black frame (12 % lit without direct lighting, 64-98 % otherwise)
 
 
 def test_fixture_is_regenerated_identically_where_the_reference_lies():

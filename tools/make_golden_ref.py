@@ -23,7 +23,22 @@ CASES = {
     "city": (lambda: scene.city_scene(4000), dict(maxBounces=5)),
     "cornell_nomis_norr": (scene.cornell_box, dict(maxBounces=4, doMIS=False, doRussianRoulette=False, HWSSDoMIS=False)),
     "cornell_nomnee_uniform_tilesg": (scene.cornell_box, dict(maxBounces=5, doMNEE=False, emissiveSampler=0, NEEUsePerTileSG=True, tileSize=8)),
+    # the polarising camera (pltpt_solve.rt.slang:111-125) on the scene with the most polarising surfaces; paths without NEE (every light found by
+    # BSDF sampling only); no direct lighting and no emitter importance sampling under an environment map; textured scene without alpha masking
+    "grating_polarizer": (lambda: _polarised(scene.grating_sphere_scene(n_lat=16, n_lon=32), 0.8, 0.6), dict(maxBounces=6)),
+    "env_nonee": (scene.env_scene, dict(maxBounces=6, doNEE=False)),
+    "env_nodirect_noimportance": (scene.env_scene, dict(maxBounces=5, useDirectLights=False, doImportanceSampleEmitters=False)),
+    "textured_noalpha": (scene.textured_scene, dict(maxBounces=5, alphaMasking=False)),
 }
+
+
+def _polarised(scene_and_cam, polarizer, theta):
+    buffers, cam = scene_and_cam
+    cam = L.PltptCameraData.from_buffer_copy(bytes(cam))
+    cam.polarizer, cam.polarizerTheta = polarizer, theta
+    return buffers, cam
+
+
 KEYS = ("color", "albedo", "normal", "hit", "lobe", "flags", "wi", "contribution", "lastpdf")
 
 
