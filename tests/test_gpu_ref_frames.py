@@ -39,7 +39,7 @@ def test_cuda_path_reproduces_the_reference_frames(torch_cuda, fixture, name):
             mc = parity.compare_color(gpu["color"], ref["color"], same)
             m.update(mc)
             parity.record(f"reference_frames/{name}/frame{frame}", m)
-            # measured on B200 (profiles/r2aa_reference_frames_metrics.json): 1.0 on seven cases, >= 0.9948 on the open Cornell variants, 0.9878 / 0.9896 in the
+            # measured on B200 (profiles/r2ab_reference_fixture_metrics.json): 1.0 on seven cases, >= 0.9948 on the open Cornell variants, 0.9878 / 0.9896 in the
             # closed box (paths of up to nine vertices: more branch thresholds to fall within rounding of)
             assert m["identical_paths"] >= (0.98 if name == "cornell_closed" else 0.99), (name, frame, m)
             assert m["max_bary_abs"] <= 2e-3 and m["max_wi_abs"] <= 2e-3 and m["max_contribution_rel"] <= 1e-3, (name, frame, m)
