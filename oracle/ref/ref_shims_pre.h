@@ -36,9 +36,13 @@ struct float16_t4 {
     operator float4() const { return float4(float(x), float(y), float(z), float(w)); }
 };
 
-// Utils/HWSS.slang:33-37 with HWSS_SAMPLES = 4 (PLTPT's default `HWSS`, PLTPT.h:87)
-static const uint hwss_samples = 4;
-typedef float4 hwss_t;
+// Utils/HWSS.slang:33-37 with HWSS_SAMPLES = 4 (PLTPT's default `HWSS`, PLTPT.h:87) unless the translation unit is built for another count
+// (-DREF_HWSS=n: the define PLTPT.cpp:226 passes)
+#ifndef REF_HWSS
+#define REF_HWSS 4
+#endif
+static const uint hwss_samples = REF_HWSS;
+typedef vec<float, REF_HWSS> hwss_t;
 
 // Utils/Sampling/SampleGeneratorInterface.slang:48-75: the generator only has to provide next() (32 random bits)
 template <class S> float sampleNext1D(S& sg) {

@@ -17,6 +17,14 @@ namespace ref {
 typedef uint32_t uint;
 
 template <class T, int N> struct vec;
+template <class T> struct vec<T, 1> {   // vector<float, 1>: hwss_t at HWSS = 1
+    T x{};
+    vec() = default;
+    template <class U, class = std::enable_if_t<std::is_arithmetic<U>::value>> vec(U s) : x(T(s)) {}
+    template <class U> explicit vec(const vec<U, 1>& o) : x(T(o.x)) {}
+    T& operator[](int) { return x; }
+    const T& operator[](int) const { return x; }
+};
 template <class T> struct vec<T, 2> {
     T x{}, y{};
     vec() = default;
@@ -63,6 +71,7 @@ template <class T> struct vec<T, 4> {
     vec<T, 2> zw() const { return {z, w}; }
     vec<T, 3> xyz() const { return {x, y, z}; }
 };
+typedef vec<float, 1> float1;
 typedef vec<float, 2> float2;
 typedef vec<float, 3> float3;
 typedef vec<float, 4> float4;

@@ -8,38 +8,28 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "_ref", "libref_frames.so")
-_LIB_DBG = os.path.join(_HERE, "_ref", "libref_frames_dbg.so")   # the pass's DO_DEBUG_VIEW = 1 shader variant
-_lib = None
-_lib_dbg = None
+_DIR = os.path.join(_HERE, "_ref")
+_libs = {}
 
 
 def available():
-    return os.path.isdir("/root/reference") or os.path.exists(_LIB)
+    return os.path.isdir("/root/reference") or os.path.exists(os.path.join(_DIR, "libref_frames.so"))
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(hwss=4, debug=False):
+    """The build of the transpiled pass for these shader defines: HWSS_SAMPLES (PLTPT.cpp:226) and DO_DEBUG_VIEW (PLTPT.cpp:230)."""
+    if debug and hwss != 4:
+        raise ValueError("the debug-view build exists for HWSS = 4 only")
+    name = "libref_frames_dbg.so" if debug else ("libref_frames.so" if hwss == 4 else f"libref_frames_h{hwss}.so")
+    if name not in _libs:
         if os.path.isdir("/root/reference"):
-            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libref_frames.so"])
-        _lib = C.CDLL(_LIB)
-        _lib.ref_scene_create.restype = C.c_void_p
-        _lib.ref_scene_create.argtypes = [C.c_void_p]
-        _lib.ref_scene_destroy.argtypes = [C.c_void_p]
-    return _lib
-
-
-def lib_debug():
-    global _lib_dbg
-    if _lib_dbg is None:
-        if os.path.isdir("/root/reference"):
-            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libref_frames_dbg.so"])
-        _lib_dbg = C.CDLL(_LIB_DBG)
-        _lib_dbg.ref_scene_create.restype = C.c_void_p
-        _lib_dbg.ref_scene_create.argtypes = [C.c_void_p]
-        _lib_dbg.ref_scene_destroy.argtypes = [C.c_void_p]
-    return _lib_dbg
+            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/" + name])
+        l = C.CDLL(os.path.join(_DIR, name))
+        l.ref_scene_create.restype = C.c_void_p
+        l.ref_scene_create.argtypes = [C.c_void_p]
+        l.ref_scene_destroy.argtypes = [C.c_void_p]
+        _libs[name] = l
+    return _libs[name]
 
 
 def _p(a):
@@ -49,10 +39,10 @@ def _p(a):
 class RefScene:
     """The reference's shader text bound to host-side Falcor-layout buffers (pltfalcor_b200.scene.SceneBuffers)."""
 
-    def __init__(self, buffers, debug=False):
+    def __init__(self, buffers, debug=False, hwss=4):
         self.buffers = buffers
         self._desc = buffers.desc()
-        self._lib = lib_debug() if debug else lib()
+        self._lib = lib(hwss, debug)
         self.h = C.c_void_p(self._lib.ref_scene_create(C.byref(self._desc)))
 
     def __del__(self):
@@ -68,7 +58,7 @@ class RefScene:
         bounces = np.zeros((height, width, opts.maxBounces + 1), L.bounce_dtype)
         rc = self._lib.ref_render_frame(self.h, C.byref(opts), C.byref(cam), C.c_uint32(frame), C.c_uint32(width), C.c_uint32(height), _p(color), _p(albedo), _p(normal), _p(bounces))
         if rc != 0:
-            raise ValueError("option fixed at compile time in the transpiled reference (HWSS = 4, MNEEMaxOccluders = 2; debug views need RefScene(debug=True))")
+            raise ValueError("option fixed at compile time in the transpiled reference (MNEEMaxOccluders = 2; HWSS other than 4 needs RefScene(hwss=n), debug views RefScene(debug=True))")
         return dict(color=color, albedo=albedo, normal=normal, bounces=bounces)
 
 

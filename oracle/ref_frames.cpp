@@ -140,7 +140,7 @@ void* ref_scene_create(const PltptSceneDesc* desc) {
 void ref_scene_destroy(void* s) { if (g == s) g = nullptr; delete static_cast<RefScene*>(s); }
 
 // One frame = the tile loop of PLTPT::execute (PLTPT.cpp:487-495): per tile the sample stage over the tile, then the solve stage.
-// Returns 0, or -1 for an option the transpiled build fixes at compile time (HWSS = 4, MNEE_MAX_MS_OCCLUDERS = 2; a debug view needs the
+// Returns 0, or -1 for an option the transpiled build fixes at compile time (HWSS = REF_HWSS -- 4 unless built with -DREF_HWSS=n, libref_frames_h<n>.so --, MNEE_MAX_MS_OCCLUDERS = 2; a debug view needs the
 // DO_DEBUG_VIEW = 1 build, libref_frames_dbg.so, which in turn renders nothing else).
 int ref_render_frame(void* sp, const PltptOptions* opt, const PltptCameraData* cam, uint32_t frameCount, uint32_t width, uint32_t height,
                      float* color, float* albedo, float* normal, PltptBounce* bounces) {
@@ -148,7 +148,7 @@ int ref_render_frame(void* sp, const PltptOptions* opt, const PltptCameraData* c
     // the pass compiles the debug overlay in only when a view is selected (PLTPT.cpp:230): this translation unit is built once without and once with it
     if (opt->HWSS != ref::hwss_samples || opt->MNEEMaxOccluders != ref::kMNEEMaxMSOccluders || (opt->debugView != 0) != (REF_DEBUG_VIEW != 0)) return -1;
     ref::kDebugViewType = opt->debugView; ref::kDebugViewIntensity = opt->debugViewIntensity;
-    orc::hwss_cfg().samples = 4;
+    orc::hwss_cfg().samples = REF_HWSS;
     bind(rs);
     const PltptSceneDesc& d = rs.osc.d;
     // the pass's defines (PLTPT.cpp:216-256) and constant buffer (PLTPT.cpp:440-470)

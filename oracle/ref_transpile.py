@@ -144,7 +144,6 @@ PROPERTY_USES = [r"gfs\.roughness"]
 PROPERTY_USES_FRACTAL = [r"gfs\.q"]
 # exact-text patches: (file suffix, old, new, why)
 PATCHES = [
-    ("Utils/Math/MathHelpers.slang", "float1 sqr(float1 v) { return v*v; }", "", "float1 (1-vectors) are not modelled"),
     ("Utils/Color/SpectrumUtils.slang", "static const float3 rgbWavelengths = float3(630,532,467);", "static inline const float3 rgbWavelengths = float3(630,532,467);",
      "C++ needs `inline` for a class-type static data member defined in the class"),
     ("Utils/Color/ColorHelpers.slang", "static const float3x3 M =\n    {", "static const float3x3 M =\n    float3x3{", "list-initialisation of the matrix type"),

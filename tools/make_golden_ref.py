@@ -29,6 +29,10 @@ CASES = {
     "env_nonee": (scene.env_scene, dict(maxBounces=6, doNEE=False)),
     "env_nodirect_noimportance": (scene.env_scene, dict(maxBounces=5, useDirectLights=False, doImportanceSampleEmitters=False)),
     "textured_noalpha": (scene.textured_scene, dict(maxBounces=5, alphaMasking=False)),
+    # the other hero-wavelength sample counts (HWSS_SAMPLES, hwss_t = vector<float, n>: separate builds of the transpiled pass)
+    "cornell_hwss1": (scene.cornell_box, dict(maxBounces=5, HWSS=1)),
+    "grating_hwss2": (lambda: scene.grating_sphere_scene(n_lat=16, n_lon=32), dict(maxBounces=6, HWSS=2)),
+    "layered_hwss3_nomis": (scene.layered_stress_scene, dict(maxBounces=5, HWSS=3, HWSSDoMIS=False)),
 }
 
 
@@ -58,7 +62,7 @@ def setup(name):
 def render_reference(name, frame):
     from oracle import ref_binding as rb
     buffers, cam, opts = setup(name)
-    return _pack(rb.RefScene(buffers).render_frame(opts, scene.with_jitter(cam, frame, W, H), frame, W, H))
+    return _pack(rb.RefScene(buffers, hwss=int(opts.HWSS)).render_frame(opts, scene.with_jitter(cam, frame, W, H), frame, W, H))
 
 
 def render_oracle(name, frame):
