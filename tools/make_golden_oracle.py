@@ -1,7 +1,6 @@
 """Pins the oracle against itself: renders small frames of the harness scenes with the CPU oracle and stores colour, guide buffers and
 the bounce-record digest under tests/golden/oracle_frames.npz.  Frames of the reference itself are tests/golden/ref_frames.npz (tools/make_golden_ref.py);
-this fixture is the oracle's own output: it makes an accidental change of the oracle (the checker of every GPU parity test) visible,
-also for the HWSS = 1 case the transpiled reference build (HWSS fixed at 4) does not render.  Usage: python tools/make_golden_oracle.py"""
+this fixture is the oracle's own output: it makes an accidental change of the oracle (the checker of every GPU parity test) visible.  Usage: python tools/make_golden_oracle.py"""
 import os
 import sys
 
