@@ -31,11 +31,13 @@ struct MaterialSystemStandIn {
         std::memcpy(static_cast<void*>(&d), &blobs[materialID].payload, sizeof d);
         return d;
     }
+    bool isEmissiveTextured(uint materialID) const { return getBasicMaterialData(materialID).texEmissive.getMode() == TextureHandle::Mode::Texture; }   // MaterialSystem.slang: the emissive slot holds a texture
     SamplerState getTextureSampler(uint samplerID) const { SamplerState s; s.id = samplerID; return s; }
     SamplerState getDefaultTextureSampler(uint materialID) const { return getTextureSampler(getMaterialHeader(materialID).getDefaultTextureSamplerID()); }
     // MaterialFactory.slang:60-131: dynamic dispatch on the material type -- defined in ref_shims_late.h, once the material structs are complete
     struct ShadingData prepareShadingData(struct VertexData v, uint materialID, float3 viewDir, ExplicitLodTextureSampler lod) const;
     struct AnyMaterialInstance getMaterialInstance(struct ShadingData sd, ExplicitLodTextureSampler lod) const;
+    float4 sampleTexture(TextureHandle handle, SamplerState s, float2 uv, float lod) const { return textureFn ? textureFn(handle.getTextureID(), s.id, uv) : float4(0.f); }   // MaterialSystem.slang: explicit-mip overload
     float4 sampleTexture(TextureHandle handle, SamplerState s, float2 uv, float4 uniformValue, ExplicitLodTextureSampler) const {
         if (handle.getMode() == TextureHandle::Mode::Texture && textureFn) return textureFn(handle.getTextureID(), s.id, uv);
         return uniformValue;

@@ -117,6 +117,9 @@ template <class T> struct Texture2D {
     T SampleLevel(SamplerState, float2 uv, float lod) const { return sampleFn(ctx, uv, lod); }
     void GetDimensions(uint& w, uint& h) const { w = width; h = height; }
 };
+// HLSL ByteAddressBuffer (FinalizeIntegration.cs.slang reads the rasterised texel sums of textured emitters through it)
+struct ByteAddressBuffer { const uint* p = nullptr; uint Load(uint address) const { return p[address / 4]; } uint4 Load4(uint address) const { return uint4(p[address / 4], p[address / 4 + 1], p[address / 4 + 2], p[address / 4 + 3]); } };
+typedef vec<uint64_t, 4> uint64_t4;
 struct ExplicitLodTextureSampler { float lod; ExplicitLodTextureSampler(float l = 0.f) : lod(l) {} };
 typedef ExplicitLodTextureSampler ITextureSampler;  // the interface the loaders take; the pass passes ExplicitLodTextureSampler{0} (Scene/Material/TextureSampler.slang:74-87)
 

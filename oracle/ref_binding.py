@@ -50,6 +50,15 @@ class RefScene:
             self._lib.ref_scene_destroy(self.h)
             self.h = None
 
+    def build_light_collection(self):
+        """(emissiveTriangles, emissiveFlux) as the reference's BuildTriangleList / FinalizeIntegration passes build them for this scene's emissive instances."""
+        from pltfalcor_b200 import layouts as L
+        n = int(self._desc.emissiveTriangleCount)
+        tris, flux = np.zeros(n, L.emissive_triangle_dtype), np.zeros(n, L.emissive_flux_dtype)
+        if self._lib.ref_build_light_collection(self.h, _p(tris), _p(flux)) != 0:
+            raise ValueError("perMeshInstanceOffset does not fit emissiveTriangleCount")
+        return tris, flux
+
     def render_frame(self, opts, cam, frame, width, height):
         from pltfalcor_b200 import layouts as L
         color = np.zeros((height, width, 4), np.float32)

@@ -53,6 +53,10 @@ void bind(const RefScene& rs) {
         const ref::uint3 vtxIndices = ref::gScene.getIndices(hit.instanceID, hit.primitiveIndex);
         ref::StaticVertexData vertices[3] = {ref::gScene.getVertex(vtxIndices[0]), ref::gScene.getVertex(vtxIndices[1]), ref::gScene.getVertex(vtxIndices[2])};
         return ref::gScene.computeVertexData(vertices, worldMat, worldInvTransposeMat, isFrontFaceCW, hit.getBarycentricWeights()); };
+    ref::gScene.worldMatrixFn = [](ref::GeometryInstanceID id) {
+        const float* wm = g->osc.d.worldMatrices + 16 * size_t(g->osc.d.geometryInstances[id.index].globalMatrixID);
+        ref::float4x4 m; for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) m[r][c] = wm[4 * r + c]; return m; };
+    ref::gScene.worldFrontFaceCWFn = [](ref::GeometryInstanceID id) { return (g->osc.d.geometryInstances[id.index].flags & PLTPT_INSTANCE_FLAG_WORLD_FRONT_FACE_CW) != 0; };
     // the packed hit word (HitInfo.slang:292-312: bit allocation by scene defines)
     ref::TriangleHit::packFn = [](const ref::TriangleHit& h) {
         orc::TriangleHit oh; oh.instanceID = h.instanceID.index; oh.primitiveIndex = h.primitiveIndex; oh.barycentrics = orc::float2(h.barycentrics.x, h.barycentrics.y);
@@ -225,6 +229,37 @@ int ref_accumulate_frame(uint32_t precision, uint32_t accumCount, int movingAver
             if (precision == 2) { const uint64_t b = (uint64_t(hi[i][k]) << 32) | lo[i][k]; std::memcpy(&ds[4 * i + k], &b, 8); }
             else { fs[4 * i + k] = sum[i][k]; if (precision == 1) lastCorr[4 * i + k] = corr[i][k]; }
         }
+    return 0;
+}
+
+// The light collection's two build passes by the reference's text (BuildTriangleList.cs.slang buildTriangleList, FinalizeIntegration.cs.slang
+// finalizeIntegration), dispatched as LightCollection.cpp:481-500 / :520-540 dispatches them: one buildTriangleList dispatch per mesh light (= emissive
+// instance, in instance order, gLightIdx counting them), one finalizeIntegration over all triangles.  Untextured emitters (the texel sums of textured
+// ones come from a rasterisation pass outside this path).  tris / flux: emissiveTriangleCount entries of the scene's own layout.
+int ref_build_light_collection(void* sp, PltptEmissiveTriangle* tris, PltptEmissiveFlux* flux) {
+    const RefScene& rs = *static_cast<RefScene*>(sp);
+    bind(rs);
+    const PltptSceneDesc& d = rs.osc.d;
+    std::vector<ref::PackedEmissiveTriangle> packed(d.emissiveTriangleCount);
+    std::vector<ref::EmissiveFlux> fl(d.emissiveTriangleCount);
+    ref::gTriangleData.p = packed.data(); ref::gFluxData.p = fl.data();
+    uint32_t lightIdx = 0;
+    for (uint32_t i = 0; i < d.instanceCount; ++i) {
+        if (!d.perMeshInstanceOffset || d.perMeshInstanceOffset[i] == 0xffffffffu) continue;
+        const PltptMeshDesc& m = d.meshes[d.geometryInstances[i].geometryID];
+        ref::gLightIdx = lightIdx++; ref::gMaterialID = d.geometryInstances[i].materialID; ref::gInstanceID = i;
+        ref::gTriangleCount = (m.indexCount > 0 ? m.indexCount : m.vertexCount) / 3; ref::gTriangleOffset = d.perMeshInstanceOffset[i];
+        if (ref::gTriangleOffset + ref::gTriangleCount > d.emissiveTriangleCount) return -1;
+        for (uint32_t t = 0; t < ref::gTriangleCount; ++t) ref::buildTriangleList(ref::uint3(t, 0u, 0u));
+    }
+    ref::gTriangleCount = d.emissiveTriangleCount;
+    for (uint32_t t = 0; t < d.emissiveTriangleCount; ++t) ref::finalizeIntegration(ref::uint3(t % 256u, t / 256u, 0u));
+    for (uint32_t t = 0; t < d.emissiveTriangleCount; ++t) {
+        for (int k = 0; k < 3; ++k) for (int c = 0; c < 4; ++c) tris[t].posAndTexCoords[k][c] = packed[t].posAndTexCoords[k][c];
+        tris[t].normal = packed[t].normal; tris[t].area = packed[t].area; tris[t].materialID = packed[t].materialID; tris[t].lightIdx = packed[t].lightIdx;
+        flux[t].flux = fl[t].flux;
+        for (int c = 0; c < 3; ++c) flux[t].averageRadiance[c] = fl[t].averageRadiance[c];
+    }
     return 0;
 }
 

@@ -49,9 +49,9 @@ SOURCES = [
                                       "sample_disk", "sample_cone", "sample_sphere", "sample_disk_concentric", "sample_cosine_hemisphere_concentric", "cosine_hemisphere_concentric_pdf",
                                       "sample_triangle", "sample_boxmueller", "boxmueller_pdf", "sample_boxmueller_truncated", "boxmueller_truncated_pdf", "tryInvert", "inverse",
                                       "diag2", "ident2", "diag4", "ident4", "svd_symmetric", "perp_stark", "BesselJ_saa", "BesselJ_laa", "BesselJ", "ndir_to_oct_equal_area_snorm", "oct_to_ndir_equal_area_snorm",
-                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm", "oct_wrap", "oct_to_ndir_snorm", "world_to_latlong_map", "latlong_map_to_world"]),
-    ("Utils/Math/FormatConversion.slang", ["unpackSnorm16", "unpackSnorm2x16"]),
-    ("Utils/Math/PackedFormats.slang", ["decodeNormal2x16"]),
+                                      "ndir_to_oct_equal_area_unorm", "oct_to_ndir_equal_area_unorm", "oct_wrap", "ndir_to_oct_snorm", "oct_to_ndir_snorm", "world_to_latlong_map", "latlong_map_to_world"]),
+    ("Utils/Math/FormatConversion.slang", ["floatToSnorm16", "unpackSnorm16", "packSnorm16", "unpackSnorm2x16", "packSnorm2x16"]),
+    ("Utils/Math/PackedFormats.slang", ["encodeNormal2x16", "decodeNormal2x16"]),
     ("Scene/Lights/LightCollectionShared.slang", None),
     ("Scene/Lights/LightCollection.slang", None),
     ("Scene/Lights/EnvMapData.slang", None),
@@ -77,12 +77,15 @@ SOURCES = [
     ("Scene/Material/BasicMaterialData.slang", ["BasicMaterialData"]),
     ("literal", '#include "../ref/ref_shims_mid.h"'),
     ("Scene/Material/ShadingUtils.slang", ["ShadingFrame", "rgbToNormal", "rgToNormal", "computeShadingFrameFromNormalMap", "applyNormalMap", "computeTangentSpace"]),
-    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getVertex", "getFaceNormalInObjectSpace", "computeVertexData"],
+    ("Scene/Scene.slang", ("members", "Scene", ["getLightCount", "evalSpectrumRGB", "evalSpectrum", "sampleSpectrum", "getLight", "getVertex", "getFaceNormalInObjectSpace", "computeVertexData",
+                                                "computeFaceNormalAndAreaW", "getVertexPositionsW", "getVertexTexCoords"],
                            "RtAccelStandIn rtAccel; SpectralProfile* spectralProfiles = nullptr; uint lightCount = 0; LightData* lights = nullptr; Camera camera; LightCollection lightCollection; MaterialSystemStandIn materials; EnvMap envMap; "
                            "StructuredBuffer<PackedStaticVertexData> vertices; uint3 (*indexFn)(GeometryInstanceID, uint) = nullptr; "
                            "uint3 getIndices(GeometryInstanceID instanceID, uint triangleIndex) { return indexFn(instanceID, triangleIndex); }  /* index-buffer fetch: engine service */ "
                            "VertexData (*vertexDataFn)(TriangleHit) = nullptr; VertexData getVertexData(TriangleHit hit) { return vertexDataFn(hit); }  /* instance -> vertices, matrices: composed by the caller from getVertex / computeVertexData */ "
-                           "uint (*materialIDFn)(GeometryInstanceID) = nullptr; uint getMaterialID(GeometryInstanceID instanceID) { return materialIDFn(instanceID); }")),
+                           "uint (*materialIDFn)(GeometryInstanceID) = nullptr; uint getMaterialID(GeometryInstanceID instanceID) { return materialIDFn(instanceID); } "
+                           "float4x4 (*worldMatrixFn)(GeometryInstanceID) = nullptr; float4x4 getWorldMatrix(GeometryInstanceID instanceID) { return worldMatrixFn(instanceID); }  /* Scene.slang:178-182: matrix buffer load */ "
+                           "bool (*worldFrontFaceCWFn)(GeometryInstanceID) = nullptr; bool isWorldFrontFaceCW(GeometryInstanceID instanceID) { return worldFrontFaceCWFn(instanceID); }  /* Scene.slang:212-215: instance flag */")),
     ("Rendering/Materials/BSDFSample.slang", None),
     ("Rendering/Utils/DifferentialShadingGeometry.slang", ["float3pdv", "float3kpdv", "DifferentialShadingGeometry", "reflectDerivatives", "refractDerivatives", "differentialShadingGeometry"]),
     ("Rendering/Materials/PLT/DiffractionGrating.slangh", None),
@@ -131,6 +134,12 @@ SOURCES = [
     ("../RenderPasses/PLTPT/Manifolds.slangh", ["sphcoords", "sphcoordsDerivatives", "manifoldOneStep", "MSHitData", "ManifoldSampleData", "manifoldSampleVertex", "traceMNEEOccluders",
                                                 "MNEEStep", "manifoldNEESample"]),
     ("../RenderPasses/PLTPT/pltpt_solve.rt.slang", ["manifoldForwardUnwind", "evalNEE", "NEE", "onMiss", "main"]),
+    ("literal", "// BuildTriangleList.cs.slang:33-43 / FinalizeIntegration.cs.slang:33-42: constant buffers and resources of the two light-collection passes (one declaration per name)\n"
+                "static uint gLightIdx = 0, gMaterialID = 0, gInstanceID = 0, gTriangleCount = 0, gTriangleOffset = 0;\n"
+                "static RWStructuredBuffer<PackedEmissiveTriangle> gTriangleData;\nstatic RWStructuredBuffer<EmissiveFlux> gFluxData;\n"
+                "static SamplerState gPointSampler;\nstatic ByteAddressBuffer gTexelMax, gTexelSum;   // results of the texture-space rasterisation of textured emitters (EmissiveIntegrator.3d.slang): not produced here"),
+    ("Scene/Lights/BuildTriangleList.cs.slang", ["buildTriangleList"]),
+    ("Scene/Lights/FinalizeIntegration.cs.slang", ["asuint64", "finalizeIntegration"]),
     ("../RenderPasses/AccumulatePass/Accumulate.cs.slang", ["accumulateSingle", "accumulateSingleCompensated", "accumulateDouble"]),
 ]
 
@@ -162,8 +171,9 @@ PATCHES = [
     ("Utils/Math/MathHelpers.slang", "return (1.f - abs(v.yx)) * (v.xy >= 0.f ? 1.f : -1.f);", "return (1.f - abs(v.yx)) * select(v.xy >= 0.f, 1.f, -1.f);", "R11"),
     ("Utils/Math/MathHelpers.slang", "n.xy = (n.z < 0.0) ? oct_wrap(n.xy) : n.xy;", "{ const float2 nxy = (n.z < 0.0) ? oct_wrap(n.xy) : n.xy; n.x = nxy.x; n.y = nxy.y; }",
      "swizzle on the left-hand side (R8 models read-only swizzles)"),
-    ("Lights/LightCollectionShared.slang", "#ifndef HOST_CODE\n    [mutating] void pack(const EmissiveTriangle tri)", "#if 0\n    [mutating] void pack(const EmissiveTriangle tri)",
-     "`pack` writes through swizzles (`.xyz = ...`); the path only unpacks"),
+    ("Lights/LightCollectionShared.slang", "        posAndTexCoords[0].xyz = tri.posW[0];\n        posAndTexCoords[1].xyz = tri.posW[1];\n        posAndTexCoords[2].xyz = tri.posW[2];",
+     "        for (int i = 0; i < 3; i++) { posAndTexCoords[i].x = tri.posW[i].x; posAndTexCoords[i].y = tri.posW[i].y; posAndTexCoords[i].z = tri.posW[i].z; }",
+     "swizzle on the left-hand side (R8 models read-only swizzles)"),
     ("Scene/SceneTypes.slang", "v.tangent.xyz = decodeNormal2x16(asuint(packedNormalTangentCurveRadius.z));",
      "{ const float3 txyz = decodeNormal2x16(asuint(packedNormalTangentCurveRadius.z)); v.tangent.x = txyz.x; v.tangent.y = txyz.y; v.tangent.z = txyz.z; }",
      "swizzle on the left-hand side"),
@@ -179,6 +189,10 @@ PATCHES = [
     ("Scene/Scene.slang", "v.tangentW.xyz = mul((float3x3)worldMat, v.tangentW.xyz);", "{ const float3 txyz = mul((float3x3)worldMat, v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }",
      "swizzle on the left-hand side"),
     ("Scene/Scene.slang", "v.tangentW.xyz = normalize(v.tangentW.xyz);", "{ const float3 txyz = normalize(v.tangentW.xyz); v.tangentW.x = txyz.x; v.tangentW.y = txyz.y; v.tangentW.z = txyz.z; }", "swizzle on the left-hand side"),
+    ("Scene/Scene.slang", "void getVertexPositionsW(const GeometryInstanceID instanceID, const uint triangleIndex, out float3 p[3])",
+     "void getVertexPositionsW(const GeometryInstanceID instanceID, const uint triangleIndex, float3 p[3])", "an array parameter is already passed by reference in C++"),
+    ("Scene/Scene.slang", "void getVertexTexCoords(const GeometryInstanceID instanceID, const uint triangleIndex, out float2 texC[3])",
+     "void getVertexTexCoords(const GeometryInstanceID instanceID, const uint triangleIndex, float2 texC[3])", "an array parameter is already passed by reference in C++"),
     ("PLTPT/Manifolds.slangh", "const float2x2 do = sphcoordsDerivatives(w);", "const float2x2 do_ = sphcoordsDerivatives(w);", "`do` is a C++ keyword"),
     ("PLTPT/Manifolds.slangh", "const float2x2 dCdX = do - float2x2(dio);", "const float2x2 dCdX = do_ - float2x2(dio);", "`do` is a C++ keyword"),
     ("PLTPT/ColourCoding.slang", "const int l = clamp((int)val, 0, int(bins)-1);", "const int l = clamp(hlsl_ftoi(val), 0, int(bins)-1);",

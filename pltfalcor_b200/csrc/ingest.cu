@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(128) k_build_emissive(DevScene sc, const uint3
         pw[k] = mulPoint(M, mk3(v.position[0], v.position[1], v.position[2]));
         uv[k] = mk2(v.texCrd[0], v.texCrd[1]);
     }
-    const float3 n = cross(pw[1] - pw[0], pw[2] - pw[0]);
+    float3 n = cross(pw[1] - pw[0], pw[2] - pw[0]);
     const float len = length(n);
+    if (gi.flags & PLTPT_INSTANCE_FLAG_WORLD_FRONT_FACE_CW) n = mk3(-n.x, -n.y, -n.z);   // Scene.slang:493-494 (computeFaceNormalAndAreaW): winding in world space
     PltptEmissiveTriangle e;
     for (int k = 0; k < 3; ++k) {
         e.posAndTexCoords[k][0] = pw[k].x; e.posAndTexCoords[k][1] = pw[k].y; e.posAndTexCoords[k][2] = pw[k].z;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(128) k_build_emissive(DevScene sc, const uint3
     e.normal = dEncodeNormal2x16(n / len);
     e.area = __float_as_uint(area);
     e.materialID = gi.materialID;
-    e.lightIdx = 0;
+    e.lightIdx = lo;   // index of the mesh light (LightCollection.cpp:481-485: one dispatch per emissive instance, in instance order)
     tris[t] = e;
     const float* rgb = rgbOfMaterial + 3 * size_t(gi.materialID);
     const float r = fmaxf(rgb[0], 0.f), g = fmaxf(rgb[1], 0.f), b = fmaxf(rgb[2], 0.f);

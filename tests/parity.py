@@ -177,3 +177,15 @@ def accumulate_pass_restatement(mode, frames, moving_average):
                 o = (s * wgt).astype(f32)
         outs.append(o)
     return outs
+
+
+def snorm2x16_steps(a, b):
+    """Largest distance, in 16-bit snorm quantisation steps, between two arrays of 2x16-snorm packed words (octahedral normals)."""
+    a, b = np.asarray(a, np.uint32), np.asarray(b, np.uint32)
+    worst = 0
+    for shift in (0, 16):
+        da = ((a >> shift) & 0xffff).astype(np.int64)
+        db = ((b >> shift) & 0xffff).astype(np.int64)
+        da, db = np.where(da >= 32768, da - 65536, da), np.where(db >= 32768, db - 65536, db)
+        worst = max(worst, int(np.abs(da - db).max()) if da.size else 0)
+    return worst

@@ -80,3 +80,34 @@ def test_cuda_debug_views_reproduce_the_reference(torch_cuda, name):
             assert (d <= tol).mean() >= 0.97, (name, vname, float(d.max()))
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("name", list(gold.LIGHT_COLLECTION_CASES))
+def test_built_light_collection_matches_the_reference_passes(torch_cuda, name):
+    """pltpt_build_light_collection (csrc/ingest.cu) against the tables the reference's own BuildTriangleList / FinalizeIntegration passes build
+    (tests/golden/ref_light_collection.npz): world-space vertices, fp16 uv pairs, areas, octahedral normals -- including the mirrored instance whose face
+    normal the reference flips back (IsWorldFrontFaceCW) --, material and mesh-light indices, flux and average radiance."""
+    from pltfalcor_b200 import binding, layouts as L
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_light_collection.npz"))
+    buffers, _ = gold.LIGHT_COLLECTION_CASES[name]()
+    ref_t = z[f"{name}/tris"].view(L.emissive_triangle_dtype).reshape(-1)
+    ref_f = z[f"{name}/flux"].view(L.emissive_flux_dtype).reshape(-1)
+    p = binding.Pltpt(maxBounces=4)
+    try:
+        p.set_scene(buffers)
+        p.build_light_collection()
+        built = p.get_light_collection(buffers.scalars["instanceCount"])
+        a, f = built["emissiveTriangles"], built["emissiveFlux"]
+        assert len(a) == len(ref_t)
+        assert np.array_equal(built["perMeshInstanceOffset"], buffers.arrays["perMeshInstanceOffset"])
+        exact = {"positions": bool(np.array_equal(a["posAndTexCoords"], ref_t["posAndTexCoords"])), "normals": bool(np.array_equal(a["normal"], ref_t["normal"])),
+                 "areas": bool(np.array_equal(a["area"], ref_t["area"])), "flux": bool(np.array_equal(f["flux"], ref_f["flux"]))}
+        parity.record(f"reference_light_collection/{name}", exact)
+        assert np.allclose(a["posAndTexCoords"][..., :3], ref_t["posAndTexCoords"][..., :3], rtol=2e-6, atol=2e-6)
+        assert np.array_equal(a["posAndTexCoords"][..., 3].view(np.uint32), ref_t["posAndTexCoords"][..., 3].view(np.uint32))
+        assert np.array_equal(a["materialID"], ref_t["materialID"]) and np.array_equal(a["lightIdx"], ref_t["lightIdx"])
+        assert np.allclose(a["area"].view(np.float32), ref_t["area"].view(np.float32), rtol=2e-5)
+        assert parity.snorm2x16_steps(a["normal"], ref_t["normal"]) <= 1
+        assert np.allclose(f["flux"], ref_f["flux"], rtol=2e-5) and np.allclose(f["averageRadiance"], ref_f["averageRadiance"], rtol=1e-6)
+    finally:
+        p.close()

@@ -90,3 +90,33 @@ def test_oracle_debug_views_reproduce_the_reference(oracle, name):
             assert np.array_equal(got, ref), (name, vname, float(np.abs(got - ref).max()))
         shown += int(ref[..., :3].max() > 0)
     assert shown >= 10, (name, shown)   # the NaN / inf markers stay black on a healthy render, MNEE bounce classes on a scene without walks
+
+
+@pytest.mark.parametrize("name", list(gold.LIGHT_COLLECTION_CASES))
+def test_harness_light_collection_matches_the_reference_passes(name):
+    """tests/golden/ref_light_collection.npz: emissive-triangle and flux tables as the reference's own BuildTriangleList / FinalizeIntegration passes build them
+    (transpiled; dispatched per mesh light as LightCollection.cpp does).  The scene harness builds the tables it hands to pltpt_set_scene in numpy (fp64
+    transform, rounded): same triangles, same uv bits, areas / flux within fp32 rounding, normals within one snorm step -- except that the harness knows nothing
+    of mirrored instances, whose face normal the reference flips back (IsWorldFrontFaceCW, Scene.slang:493-494): the fixture's `emitters` case holds one, and
+    pltpt_build_light_collection is held to it on the GPU (tests/test_gpu_ref_frames.py)."""
+    from pltfalcor_b200 import layouts as L
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_light_collection.npz"))
+    buffers, _ = gold.LIGHT_COLLECTION_CASES[name]()
+    ref_t = z[f"{name}/tris"].view(L.emissive_triangle_dtype).reshape(-1)
+    ref_f = z[f"{name}/flux"].view(L.emissive_flux_dtype).reshape(-1)
+    a, f = buffers.arrays["emissiveTriangles"], buffers.arrays["emissiveFlux"]
+    assert len(a) == len(ref_t) > 0
+    assert np.allclose(a["posAndTexCoords"][..., :3], ref_t["posAndTexCoords"][..., :3], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(a["posAndTexCoords"][..., 3].view(np.uint32), ref_t["posAndTexCoords"][..., 3].view(np.uint32))
+    assert np.array_equal(a["materialID"], ref_t["materialID"])
+    assert np.allclose(a["area"].view(np.float32), ref_t["area"].view(np.float32), rtol=1e-5)
+    flagged = (buffers.arrays["geometryInstances"]["flags"] & 0x10) != 0
+    keep = np.ones(len(a), bool)
+    for i in np.nonzero(flagged)[0]:   # triangles of mirrored instances: the harness does not flip
+        first = int(buffers.arrays["perMeshInstanceOffset"][i])
+        keep[first:first + 2] = False
+    assert parity.snorm2x16_steps(a["normal"][keep], ref_t["normal"][keep]) <= 1
+    if name == "emitters":
+        assert (~keep).sum() == 2 and parity.snorm2x16_steps(a["normal"][~keep], ref_t["normal"][~keep]) > 30000   # the flip is in the fixture
+        assert sorted(set(ref_t["lightIdx"].tolist())) == [0, 1, 2]
+    assert np.allclose(f["flux"], ref_f["flux"], rtol=1e-5) and np.allclose(f["averageRadiance"], ref_f["averageRadiance"], rtol=1e-6)

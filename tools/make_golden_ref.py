@@ -126,6 +126,46 @@ def render_reference_debug_views():
     return out
 
 
+def emitters_scene():
+    """Many emissive triangles under non-trivial instance transforms: a rotated, anisotropically scaled emissive sphere, an emissive quad, a second
+    instance of that quad under a MIRRORING transform (negative determinant: Falcor marks such an instance IsWorldFrontFaceCW, SceneBuilder.cpp, and
+    computeFaceNormalAndAreaW flips the face normal, Scene.slang:493-494), and a non-emissive mesh between them."""
+    import math
+    b = scene.SceneBuilder()
+    lamp = b.add_emission_profile(scene.LAMP, 1.0)
+    dim = b.add_emission_profile(scene.LAMP, 0.25)
+    white = b.add_diffuse((0.7, 0.7, 0.7))
+    e1 = b.add_diffuse((0.0, 0.0, 0.0), emission_profile=lamp)
+    e2 = b.add_diffuse((0.1, 0.1, 0.1), emission_profile=dim)
+    c, s_ = math.cos(0.7), math.sin(0.7)
+    R = np.array([[c, 0, s_, 0.3], [0, 1, 0, 1.1], [-s_, 0, c, -0.2], [0, 0, 0, 1]], np.float64) @ np.diag([0.9, 1.7, 0.6, 1.0])
+    b.add_mesh(scene.uv_sphere([0.1, 0.2, -0.1], 0.35, n_lat=8, n_lon=12), e1, matrix=R.astype(np.float32))
+    b.add_mesh(scene.quad([-2, 0, 2], [2, 0, 2], [2, 0, -2], [-2, 0, -2]), white)
+    q = b.add_mesh(scene.quad([-0.3, 1.9, -0.3], [0.3, 1.9, -0.3], [0.3, 1.9, 0.3], [-0.3, 1.9, 0.3]), e2)
+    mirror = np.diag([-1.0, 1.0, 1.0, 1.0])
+    mirror[:3, 3] = (1.2, -0.4, 0.5)
+    b.add_instance(q, e2, mirror.astype(np.float32))
+    buffers = b.finalize()
+    inst = buffers.arrays["geometryInstances"]
+    inst["flags"][len(inst) - 1] |= 0x10   # PLTPT_INSTANCE_FLAG_WORLD_FRONT_FACE_CW: the mirrored instance
+    cam = scene.make_camera([0.0, 1.0, 3.5], [0.0, 1.0, 0.0], focal_length=35.0, aspect=16.0 / 9.0)
+    return buffers, cam
+
+
+LIGHT_COLLECTION_CASES = {"cornell": scene.cornell_box, "layered": scene.layered_stress_scene, "emitters": emitters_scene}
+
+
+def render_reference_light_collections():
+    """Emissive-triangle and flux tables as the reference's BuildTriangleList / FinalizeIntegration passes build them."""
+    from oracle import ref_binding as rb
+    out = {}
+    for name, fn in LIGHT_COLLECTION_CASES.items():
+        buffers, _ = fn()
+        tris, flux = rb.RefScene(buffers).build_light_collection()
+        out[f"{name}/tris"], out[f"{name}/flux"] = tris.view(np.uint32).reshape(len(tris), 16), flux.view(np.float32).reshape(len(flux), 4)
+    return out
+
+
 def _main():
     out = {}
     for name in CASES:
@@ -137,6 +177,9 @@ def _main():
     print(path, os.path.getsize(path), "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_debug_views.npz")
     np.savez_compressed(path, **render_reference_debug_views())
+    print(path, os.path.getsize(path), "bytes")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_light_collection.npz")
+    np.savez_compressed(path, **render_reference_light_collections())
     print(path, os.path.getsize(path), "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_accumulate.npz")
     np.savez_compressed(path, **render_reference_accumulate())
