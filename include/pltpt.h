@@ -463,7 +463,11 @@ PLTPT_API int pltpt_pack_material(const PltptMaterialParams* params, PltptMateri
 /* LightCollection (BuildTriangleList.cs.slang, FinalizeIntegration.cs.slang:64-110; on the GPU) + EmissivePowerSampler alias table
  * (EmissivePowerSampler.cpp:86-170, without the final random permutation) of the scene held by `h`; replaces whatever tables
  * pltpt_set_scene was given (they may have been NULL).  pltpt_get_light_collection copies the installed tables to host memory
- * (any pointer may be NULL; *count = emissive triangles; perMeshInstanceOffset has instanceCount entries). */
+ * (any pointer may be NULL; *count = emissive triangles; perMeshInstanceOffset has instanceCount entries).
+ * Triangles are world-space, one mesh light per emissive instance in instance order (lightIdx); the face normal follows the winding in
+ * world space and is flipped for instances flagged PLTPT_INSTANCE_FLAG_WORLD_FRONT_FACE_CW (Scene.slang:482-497), so a mirrored
+ * instance emits from the same side as the reference's.  Bit-equal to the reference's passes on untextured emitters
+ * (tests/golden/ref_light_collection.npz). */
 PLTPT_API int pltpt_build_light_collection(PltptHandle h);
 PLTPT_API int pltpt_get_light_collection(PltptHandle h, PltptEmissiveTriangle* triangles, PltptEmissiveFlux* flux, uint32_t* perMeshInstanceOffset,
                                          uint32_t* aliasTable, float* invWeightsSum, uint32_t capacity, uint32_t* count);
