@@ -174,7 +174,10 @@ struct SampleGenerator {
     uint next() { return g.next(); }
 };
 static bool kDoNEE = true, kDoMSonNEE = true, kDoMIS = true, kImportanceSampleEmissiveSpectra = true;   // pltpt.slangh:105-116
-static constexpr uint kMNEEMaxMSOccluders = 2;                  // Manifolds.slangh:40-54 (the defines' defaults; PLTPT.h:123-125 holds the same values)
+#ifndef REF_MNEE_OCCLUDERS
+#define REF_MNEE_OCCLUDERS 2
+#endif
+static constexpr uint kMNEEMaxMSOccluders = REF_MNEE_OCCLUDERS;   // Manifolds.slangh:40-54 (MNEE_MAX_MS_OCCLUDERS: an array size, hence per build; default PLTPT.h:123)
 static int kMNEEMaxIterations = 40;
 static float kMNEESolverThreshold = 1e-5f;
 static const float kShadowRayTMin = 1e-4f;                      // ShadowRays.slangh:46

@@ -16,11 +16,11 @@ def available():
     return os.path.isdir("/root/reference") or os.path.exists(os.path.join(_DIR, "libref_frames.so"))
 
 
-def lib(hwss=4, debug=False):
-    """The build of the transpiled pass for these shader defines: HWSS_SAMPLES (PLTPT.cpp:226) and DO_DEBUG_VIEW (PLTPT.cpp:230)."""
-    if debug and hwss != 4:
-        raise ValueError("the debug-view build exists for HWSS = 4 only")
-    name = "libref_frames_dbg.so" if debug else ("libref_frames.so" if hwss == 4 else f"libref_frames_h{hwss}.so")
+def lib(hwss=4, debug=False, occluders=2):
+    """The build of the transpiled pass for these shader defines: HWSS_SAMPLES (PLTPT.cpp:226), DO_DEBUG_VIEW (PLTPT.cpp:230), MNEE_MAX_MS_OCCLUDERS (:248)."""
+    if (debug) + (hwss != 4) + (occluders != 2) > 1:
+        raise ValueError("builds exist for one non-default define at a time")
+    name = "libref_frames_dbg.so" if debug else (f"libref_frames_m{occluders}.so" if occluders != 2 else ("libref_frames.so" if hwss == 4 else f"libref_frames_h{hwss}.so"))
     if name not in _libs:
         if os.path.isdir("/root/reference"):
             subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/" + name])
@@ -39,10 +39,10 @@ def _p(a):
 class RefScene:
     """The reference's shader text bound to host-side Falcor-layout buffers (pltfalcor_b200.scene.SceneBuffers)."""
 
-    def __init__(self, buffers, debug=False, hwss=4):
+    def __init__(self, buffers, debug=False, hwss=4, occluders=2):
         self.buffers = buffers
         self._desc = buffers.desc()
-        self._lib = lib(hwss, debug)
+        self._lib = lib(hwss, debug, occluders)
         self.h = C.c_void_p(self._lib.ref_scene_create(C.byref(self._desc)))
 
     def __del__(self):

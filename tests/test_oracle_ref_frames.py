@@ -22,7 +22,7 @@ def fixture():
     return gold.load_fixture()
 
 
-@pytest.mark.parametrize("name", list(gold.CASES))
+@pytest.mark.parametrize("name", list(gold.CASES) + list(gold.CPU_ONLY_CASES))
 def test_oracle_reproduces_the_reference_frames(fixture, name):
     for frame in gold.FRAMES:
         ref = fixture[(name, frame)]
