@@ -7,10 +7,15 @@ ref_transpile.py — compiles the reference's own PLT shader text for the CPU.
 physics core is, however, plain C-like code.  This script reads the modules listed in SOURCES from /root/reference where they lie,
 applies the purely TEXTUAL rewrite rules below (no statement of the reference is re-typed by hand, nothing is re-ordered inside a
 function), and writes the result to oracle/_ref/ref_gen.h (git-ignored: reference text never enters the repository).  Together with
-oracle/ref/slang_compat.h (HLSL vector / matrix types and intrinsics in C++) and oracle/ref/ref_shims.h (the few engine services
-the modules call: gScene.evalSpectrum on a caller-provided table, the sample generator, ShadingData) it is compiled by
-`make -C oracle ref` into oracle/_ref/ref_compare, which runs the oracle (namespace orc) and the transpiled reference
-(namespace ref) on the same random inputs and prints the largest deviation per function (tests/test_oracle_ref.py).
+oracle/ref/slang_compat.h (HLSL vector / matrix types and intrinsics in C++) and oracle/ref/ref_shims_{pre,mid,late,end}.h (the engine services
+the modules call: gScene.evalSpectrum on a caller-provided table, the sample generator, ShadingData, Slang's dynamic material dispatch written
+out as a switch, the DXR runtime -- TraceRay over a caller-provided intersection search with the pass's shader tables --, constant buffers
+and resources of the compute passes) it is compiled by `make -C oracle ref` into
+  * oracle/_ref/ref_compare -- runs the oracle (namespace orc) and the transpiled reference (namespace ref) on the same random inputs, from
+    single functions up to whole frames of random scenes, and prints the largest deviation per entry (tests/test_oracle_ref.py);
+  * oracle/_ref/libref_frames*.so (oracle/ref_frames.cpp) -- the reference's two ray-generation programs, its AccumulatePass and its
+    light-collection build passes over scenes in the C ABI's layouts, one build per shader variant (HWSS_SAMPLES 1-4, DO_DEBUG_VIEW,
+    MNEE_MAX_MS_OCCLUDERS): the generator of the fixtures tests/golden/ref_*.npz (tools/make_golden_ref.py).
 
 Rewrite rules (all mechanical; each is a regular expression or a brace-matched block move):
   R1  strip comments-only license headers, `import`, `__exported import`, `#include "*.slangh"`, `#pragma once`
