@@ -206,6 +206,9 @@ struct ProfileTable {
 // ---------------------------------------------------------------------------------------------
 // Host-side table ingestion: Utils/Color/Spectrum.{h,cpp}, SampledSpectrum.h, SceneBuilder.cpp:911-960
 // ---------------------------------------------------------------------------------------------
+// Falcor's HOST lerp, Utils/Math/Common.h:54-57: (1 - t) * a + t * b -- not the shader form (lerpf): found by compiling the reference's own C++
+// (oracle/ref_spectrum.cpp); the profile tables are held to it byte for byte (tests/golden/ref_spectral_profiles.npz)
+inline float hostLerp(float a, float b, float t) { return (1.f - t) * a + t * b; }
 struct PiecewiseLinearSpectrum {
     std::vector<float> wavelengths, values;
     // Spectrum.h:88-106
@@ -215,7 +218,7 @@ struct PiecewiseLinearSpectrum {
         if (it == wavelengths.begin()) return values.front();
         size_t index = size_t(it - wavelengths.begin()) - 1;
         float t = (wavelength - wavelengths[index]) / (wavelengths[index + 1] - wavelengths[index]);
-        return lerpf(values[index], values[index + 1], t);
+        return hostLerp(values[index], values[index + 1], t);
     }
     float leastBinSize() const {
         float size = wavelengths.back() - wavelengths.front();
@@ -241,7 +244,7 @@ struct SampledSpectrum {
         size_t i = (size_t)std::floor(x);
         if (i + 1 >= samples.size()) return samples[samples.size() - 1];
         float w = x - (float)i;
-        return lerpf(samples[i], samples[i + 1], w);
+        return hostLerp(samples[i], samples[i + 1], w);
     }
 };
 // SceneBuilder.cpp:911-960. sp.rgb is left to the caller (needs the CIE 1931 1-nm tables, SpectrumUtils.h:143-151).
@@ -256,7 +259,7 @@ inline PltptSpectralProfile genSpectralProfile(const SampledSpectrum& ss, bool c
     const float r = sp.bins > 1 ? 1.f / float(sp.bins - 1) : 1.f;
     float sum = .0f;
     for (size_t i = 0; i < sp.bins; ++i) {
-        sp.pdf[i] = ss.eval(lerpf(sp.minWavelength, sp.maxWavelength, i * r));
+        sp.pdf[i] = ss.eval(hostLerp(sp.minWavelength, sp.maxWavelength, i * r));
         sum += sp.pdf[i];
     }
     if (sum < FLT_EPS || !computeICdf) return sp;
@@ -267,7 +270,7 @@ inline PltptSpectralProfile genSpectralProfile(const SampledSpectrum& ss, bool c
         const float cdf = icdfi * r;
         while (cdf >= cdfb && pdfi + 1 < sp.bins) { cdfa = cdfb; ++pdfi; cdfb += sp.pdf[pdfi]; }
         const float l = hlsl_min(1.f, (cdf - cdfa) / (cdfb - cdfa));
-        sp.icdf[icdfi] = lerpf((float)std::max<uint32_t>(1, uint32_t(pdfi)) - 1.f, (float)pdfi, l) * r;
+        sp.icdf[icdfi] = hostLerp((float)std::max<uint32_t>(1, uint32_t(pdfi)) - 1.f, (float)pdfi, l) * r;
     }
     return sp;
 }

@@ -83,3 +83,37 @@ def accumulate_frames(mode, frames, moving_average):
         assert rc == 0
         outs.append(out)
     return outs
+
+
+_spectrum = None
+
+
+def spectrum_lib():
+    """oracle/_ref/libref_spectrum.so: the reference's own C++ (Spectrum.cpp, SpectrumUtils.cpp, SampledSpectrum.h, genSpectralProfile), compiled as it lies."""
+    global _spectrum
+    if _spectrum is None:
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libref_spectrum.so"])
+        _spectrum = C.CDLL(os.path.join(_DIR, "libref_spectrum.so"))
+    return _spectrum
+
+
+def profile_from_spd_file(path, scale=1.0, compute_icdf=True):
+    """SpectralProfile (the C ABI's 1052-byte record) as the reference's scene builder makes it from a table on disk: PiecewiseLinearSpectrum::fromFile ->
+    scale -> SampledSpectrum -> genSpectralProfile, run in oracle/_ref/ref_spectrum_tool (a C++ main around the same code: the reader faults inside the
+    interpreter process)."""
+    from pltfalcor_b200 import layouts as L
+    tool = os.path.join(_DIR, "ref_spectrum_tool")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/ref_spectrum_tool"])
+    raw = subprocess.run([tool, str(path), repr(float(scale)), str(int(compute_icdf))], capture_output=True, check=True).stdout
+    return np.frombuffer(raw, L.spectral_profile_dtype)[0]
+
+
+def gen_spectral_profile(wavelengths, values, scale=1.0, compute_icdf=True):
+    from pltfalcor_b200 import layouts as L
+    w, v = np.ascontiguousarray(wavelengths, np.float32), np.ascontiguousarray(values, np.float32)
+    out = np.zeros((), L.spectral_profile_dtype)
+    if spectrum_lib().ref_gen_spectral_profile(C.c_uint32(len(w)), _p(w), _p(v), C.c_float(scale), C.c_int(int(compute_icdf)), out.ctypes.data_as(C.c_void_p)) != 0:
+        raise ValueError("the reference rejected the spectrum")
+    return out

@@ -23,6 +23,9 @@ namespace {
 int ifail(int code, const std::string& msg) { setError(msg); return code; }
 
 // ---- spectra ---------------------------------------------------------------------------------------------------------------
+// Falcor's HOST lerp is (1 - t) * a + t * b (Utils/Math/Common.h:54-57), not the shader form a + t * (b - a): the profile tables are held to the
+// reference's own C++ byte for byte (tests/golden/ref_spectral_profiles.npz), so the form matters
+inline float hostLerp(float a, float b, float t) { return (1.f - t) * a + t * b; }
 struct Pls { const float* w; const float* v; uint32_t n; };
 float plsEval(const Pls& s, float lam) {  // PiecewiseLinearSpectrum::eval
     if (s.n == 0 || lam < s.w[0] || lam > s.w[s.n - 1]) return 0.f;
@@ -30,7 +33,7 @@ float plsEval(const Pls& s, float lam) {  // PiecewiseLinearSpectrum::eval
     if (it == 0) return s.v[0];
     const uint32_t i = it - 1;
     const float t = (lam - s.w[i]) / (s.w[i + 1] - s.w[i]);
-    return s.v[i] + (s.v[i + 1] - s.v[i]) * t;
+    return hostLerp(s.v[i], s.v[i + 1], t);
 }
 struct Sampled { float start, end; std::vector<float> samples; };
 Sampled sampledFromPls(const Pls& s) {  // SampledSpectrum(PiecewiseLinearSpectrum), bin >= 5 nm
@@ -50,7 +53,7 @@ float sampledEval(const Sampled& s, float lam) {  // SampledSpectrum::eval
     const int i = int(std::floor(x));
     if (size_t(i) + 1 >= s.samples.size()) return s.samples.back();
     const float w = x - float(i);
-    return s.samples[i] + (s.samples[i + 1] - s.samples[i]) * w;
+    return hostLerp(s.samples[i], s.samples[i + 1], w);
 }
 // SpectrumUtils::toRGB_D65 (SpectrumUtils.h:78-151): trapezoid sum of XYZ(lambda) D65(lambda) s(lambda) -> Rec.709 / Y_D65.
 // DEVIATION (same as the harness, pltfalcor_b200/scene.py): the reference integrates against the CIE-1931 1 nm tables; this uses the
@@ -204,7 +207,7 @@ extern "C" int pltpt_gen_spectral_profile(uint32_t n, const float* wavelengths, 
     const float r = sp.bins > 1 ? 1.f / float(sp.bins - 1) : 1.f;
     float sum = 0.f;
     for (uint32_t i = 0; i < sp.bins; ++i) {
-        sp.pdf[i] = sampledEval(ss, sp.minWavelength + (sp.maxWavelength - sp.minWavelength) * (float(i) * r));
+        sp.pdf[i] = sampledEval(ss, hostLerp(sp.minWavelength, sp.maxWavelength, float(i) * r));
         sum += sp.pdf[i];
     }
     if (sum < 1.192092896e-07f || !computeICdf) { *out = sp; return PLTPT_OK; }
@@ -216,7 +219,7 @@ extern "C" int pltpt_gen_spectral_profile(uint32_t n, const float* wavelengths, 
         while (cdf >= cdfb && pdfi + 1 < sp.bins) { cdfa = cdfb; ++pdfi; cdfb += sp.pdf[pdfi]; }
         const float l = std::min(1.f, (cdf - cdfa) / (cdfb - cdfa));
         const float a = float(std::max<uint32_t>(1u, pdfi)) - 1.f;
-        sp.icdf[icdfi] = (a + (float(pdfi) - a) * l) * r;
+        sp.icdf[icdfi] = hostLerp(a, float(pdfi), l) * r;
     }
     *out = sp;
     return PLTPT_OK;

@@ -171,6 +171,30 @@ def render_reference_light_collections():
     return out
 
 
+SPECTRAL_SCALES = (1.0, 0.02)
+
+
+def spectral_tables():
+    """(key, path under the reference's Source/Tables, wavelengths, values, computeICdf) of the tables the package ships (pltfalcor_b200/data/spd_tables.json)."""
+    import json
+    t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pltfalcor_b200", "data", "spd_tables.json")))
+    for name, tab in t["emission"].items():
+        yield "emission/" + name, f"emission/{name}.spd", tab["wavelengths"], tab["values"], True
+    for name, nk in t["ior"].items():
+        for part in ("eta", "k"):
+            yield f"ior/{name}.{part}", f"ior/{name}.{part}.spd", nk[part]["wavelengths"], nk[part]["values"], False
+
+
+def render_reference_spectral_profiles():
+    """SpectralProfile records by the reference's own C++ (oracle/ref_spectrum.cpp) from the .spd files where they lie under /root/reference/Source/Tables."""
+    from oracle import ref_binding as rb
+    out = {}
+    for key, rel, _w, _v, icdf in spectral_tables():
+        for scale in SPECTRAL_SCALES:
+            out[f"{key}/{scale}"] = np.frombuffer(rb.profile_from_spd_file(os.path.join("/root/reference/Source/Tables", rel), scale, icdf).tobytes(), np.uint8)
+    return out
+
+
 def _main():
     out = {}
     for name in list(CASES) + list(CPU_ONLY_CASES):
@@ -185,6 +209,9 @@ def _main():
     print(path, os.path.getsize(path), "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_light_collection.npz")
     np.savez_compressed(path, **render_reference_light_collections())
+    print(path, os.path.getsize(path), "bytes")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_spectral_profiles.npz")
+    np.savez_compressed(path, **render_reference_spectral_profiles())
     print(path, os.path.getsize(path), "bytes")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_accumulate.npz")
     np.savez_compressed(path, **render_reference_accumulate())
