@@ -5,10 +5,10 @@
 //   Utils/Color/SampledSpectrum.h       the resampling constructor SampledSpectrum<float>(PiecewiseLinearSpectrum) and `eval`
 //   Utils/Color/SpectrumUtils.{h,cpp}   toRGB_D65 (CIE 1931 tables, D65 white)
 //   Scene/SceneBuilder.cpp:911-958      genSpectralProfile -- that translation unit needs the whole engine, so the one function is cut out by
-//                                       name into oracle/_ref/ref_spectral_gen.h (oracle/Makefile; text extraction only, no rewriting)
+//                                       name into a temporary header (oracle/Makefile; text extraction only, no rewriting)
 // with g++ directly (oracle/Makefile `_ref/libref_spectrum.so`; glm and fmt are vendored under /root/reference/external).  Two of the reference's
 // headers spell fmt formatter specialisations as `struct ::fmt::formatter<...>`, which GCC rejects (MSVC / clang accept): the Makefile writes
-// copies with the leading `::` removed to oracle/_ref/shadow/ and puts that directory first on the include path.  Hand-written here: the
+// copies with the leading `::` removed to a temporary directory that is first on the include path and is deleted after the compile.  Hand-written here: the
 // SpectralProfile struct's C layout is the C ABI's PltptSpectralProfile (BasicMaterialData.slang:43-54, checked by static_assert), the one
 // constructor of Falcor::Exception the two sources call (Core/Errors.cpp:34 without the stack trace), and the extern "C" entry points.
 // Used by tools/make_golden_ref.py to produce tests/golden/ref_spectral_profiles.npz, to which oracle_gen_spectral_profile and the product's
@@ -39,7 +39,7 @@ struct SpectralProfile {
 };
 static_assert(sizeof(SpectralProfile) == sizeof(PltptSpectralProfile) && sizeof(SpectralProfile) == 1052, "the C ABI's profile record is the reference's");
 
-#include "_ref/ref_spectral_gen.h"   // genSpectralProfile, cut from Scene/SceneBuilder.cpp
+#include "ref_spectral_gen.h"   // genSpectralProfile, cut from Scene/SceneBuilder.cpp into the build's temporary directory (oracle/Makefile)
 }  // namespace Falcor
 
 extern "C" {
